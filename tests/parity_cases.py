@@ -1,0 +1,150 @@
+"""Backend-independent parity cases: CUDA path (or its emulation) vs the CPU oracle on the
+same injected weights, inputs and noise draws.  Tolerances follow BASELINE.json north_star:
+<=1e-3 relative on loss terms, <=1e-2 max-abs on reconstructions - the fp32 path is held to
+much tighter bounds, stated per assert."""
+import numpy as np
+import torch
+
+from kcvae_testlib import O, assert_metrics_close, eps_for, frames, make, rel_err, small_config
+
+
+def case_forward(backend, cfg=None, B=3):
+    cfg = cfg or small_config()
+    m, ws = make(cfg, backend)
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    xh, z, mean, logvar = m.call_detailed(x, training=True, eps=eps)
+    oxh, oz, omean, olv = O.call_detailed(cfg, ws, x, eps)
+    assert tuple(xh.shape) == x.shape
+    np.testing.assert_allclose(mean.numpy(), omean.numpy(), atol=2e-5)
+    np.testing.assert_allclose(logvar.numpy(), olv.numpy(), atol=2e-5)
+    np.testing.assert_allclose(z.numpy(), oz.numpy(), atol=3e-5)
+    np.testing.assert_allclose(xh.numpy(), oxh.numpy(), atol=2e-5)     # north_star bar: 1e-2
+    # inference is deterministic: training=False => eps = 0 (src/abstract_cvae.py:125)
+    xh0 = m.call(x, False)
+    oxh0 = O.call_detailed(cfg, ws, x, None)[0]
+    np.testing.assert_allclose(xh0.numpy(), oxh0.numpy(), atol=2e-5)
+    np.testing.assert_array_equal(m(x).numpy(), xh0.numpy())
+    # encode / reparameterize / decode entry points compose to the same thing
+    mean2, lv2 = m.encode(x)
+    z2 = m.reparameterize(mean2, lv2, training=True, eps=eps)
+    logits = m.decode(z2, apply_sigmoid=False)
+    ologits = torch.logit(oxh.double()).numpy()
+    np.testing.assert_allclose(z2.numpy(), oz.numpy(), atol=3e-5)
+    np.testing.assert_allclose(logits.numpy(), ologits, atol=1e-4)
+    np.testing.assert_allclose(m.decode(z2.numpy(), True).numpy(), oxh.numpy(), atol=2e-5)
+
+
+def case_layers(backend, cfg=None, B=2):
+    """every intermediate activation against the oracle (layer-level localisation)."""
+    cfg = cfg or small_config()
+    m, ws = make(cfg, backend)
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    keep = []
+    O.call_detailed(cfg, ws, x, eps, keep=keep)
+    m.call_detailed(x, True, eps=eps)
+    L = len(cfg["model"]["layers"])
+    enc_keep = keep[:L]
+    dec_keep = keep[L + (1 if cfg["model"].get("encoder_dense_filters") else 0):]
+    for l in range(L):
+        got = m.debug_activation(1 + l)
+        np.testing.assert_allclose(got, enc_keep[l].numpy().ravel(), atol=2e-5, err_msg=f"encoder act {l}")
+    for l in range(L + 1):
+        got = m.debug_activation(100 + l)
+        np.testing.assert_allclose(got, dec_keep[l].numpy().ravel(), atol=3e-5, err_msg=f"decoder act {l}")
+
+
+def case_loss(backend, kind="global", cfg=None, B=4, training=True):
+    cfg = cfg or small_config(kind)
+    m, ws = make(cfg, backend, weight_gain=1.6)   # larger weights: non-trivial z statistics
+    x = frames(cfg, B)
+    eps = eps_for(cfg, B) if training else None
+    d, xh = m.compute_loss(x, training=training, return_inf=True, eps=eps)
+    od, oxh, *_ = O.compute_loss(cfg, ws, x, eps)
+    assert_metrics_close(d, od, rtol=2e-4)                              # north_star bar: 1e-3
+    np.testing.assert_allclose(xh.numpy(), oxh.numpy(), atol=3e-5)
+    d2 = m.compute_loss(x, training=training, eps=eps)
+    assert_metrics_close(d2, od, rtol=2e-4)
+    if not training:
+        assert_metrics_close(m.test_step(x), od, rtol=2e-4)
+
+
+def case_grads(backend, kind="global", cfg=None, B=4):
+    cfg = cfg or small_config(kind)
+    m, ws = make(cfg, backend, weight_gain=1.6)
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    d, grads = m.loss_and_grads(x, eps=eps)
+    od, ograds, _, _ = O.loss_and_grads(cfg, ws, x, eps, dtype=torch.float64)
+    assert_metrics_close(d, od, rtol=2e-4)
+    names = [n for n, _ in O.variable_shapes(cfg)]
+    for n, g, og in zip(names, grads, ograds):
+        assert g.shape == tuple(og.shape), n
+        e = rel_err(g, og.numpy())
+        assert e < 2e-4, f"grad {n}: rel err {e}"
+
+
+def case_train_steps(backend, kind="global", cfg=None, B=4, steps=3):
+    cfg = cfg or small_config(kind)
+    m, ws = make(cfg, backend, weight_gain=1.6)
+    m.compile(optimizer=__import__("kcvae_testlib").pkg.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
+    om = O.OracleModel(cfg, ws)
+    for s in range(steps):
+        x, eps = frames(cfg, B, seed=100 + s), eps_for(cfg, B, s)
+        d = m.train_step(x, eps=eps)
+        od, _ = om.train_step(x, eps)
+        assert_metrics_close(d, od, rtol=5e-4, atol=2e-6)
+    lr = float(cfg["training"]["learning_rate"])
+    for n, w, ow in zip([n for n, _ in O.variable_shapes(cfg)], m.get_weights(), om.weights):
+        # Adam normalises every update to ~lr: compare in units of lr (sign flips of
+        # near-zero gradients can move a weight by a fraction of lr)
+        diff = np.abs(w - ow.numpy())
+        assert np.mean(diff) < 0.02 * lr, f"{n}: mean |dw| {np.mean(diff)}"
+        assert np.quantile(diff, 0.99) < 0.5 * lr * steps, f"{n}: q99 |dw| {np.quantile(diff, 0.99)}"
+    mm, vv, t = m.get_optimizer_state()
+    assert t == steps
+    for a, oa in zip(mm, om.optimizer.m):
+        assert rel_err(a, oa.numpy()) < 1e-3
+    d, xh = m.train_step_and_run(frames(cfg, B, seed=7), eps=eps_for(cfg, B, 9))
+    assert tuple(xh.shape) == (B, *cfg["data"]["image_size"])
+
+
+def case_score(backend, cfg=None, B=5):
+    cfg = cfg or small_config()
+    m, ws = make(cfg, backend, weight_gain=2.0)
+    om = O.OracleModel(cfg, ws)
+    batches = [frames(cfg, B, seed=s) for s in range(3)]
+    batches[1][2, 3:9, 4:12, :] = 1.0           # planted anomaly: a saturated patch
+    P = __import__("kcvae_testlib").pkg
+    scale = P.get_data_scale(m, cfg, {"train": batches})
+    oscale = O.get_data_scale(om, batches)
+    for k in ("meu", "sigma", "min", "max"):
+        assert abs(float(scale[k]) - float(oscale[k])) <= 1e-5 + 2e-4 * abs(float(oscale[k])), k
+    np.testing.assert_allclose(scale["z_scores"].numpy(), oscale["z_scores"].numpy(), atol=5e-3)
+    res = P.evaluate_anomalies(m, cfg, {"train": batches}, scale, 1.5)
+    ores = O.evaluate_anomalies(om, batches, oscale, 1.5)
+    np.testing.assert_allclose(res["errs"], ores["errs"], atol=2e-5)
+    np.testing.assert_allclose(res["rec"], ores["rec"], atol=2e-5)
+    np.testing.assert_allclose(res["norm_errs"], ores["norm_errs"], atol=1e-4)
+    np.testing.assert_allclose(res["z_scores"], ores["z_scores"], atol=5e-3)
+    np.testing.assert_array_equal(res["anomalies"], ores["anomalies"])
+    # identical ranking (north_star)
+    assert list(P.rank_anomalies(res["z_scores"])) == list(np.argsort(-ores["z_scores"], kind="stable"))
+
+
+def case_structure(backend):
+    """tests/test_kurtosis_global_cvae.py:60-148 restated against the mirror objects."""
+    for kind in ("global", "single"):
+        cfg = O.unit_test_config("KurtosisSingle" if kind == "single" else None)
+        cfg["data"]["image_size"] = [16, 20, 3]
+        m, _ = make(cfg, backend)
+        L = len(cfg["model"]["layers"])
+        assert len(m.encoder.layers) == L + 3 and len(m.decoder.layers) == L + 3
+        assert m.encoder.layers[-1].variables[0].shape[0] == cfg["model"]["latent_dimensions"] * 2
+        assert list(m.encoder.layers[0].input_shape[1:]) == cfg["data"]["image_size"]
+        for i in range(L):
+            assert m.encoder.layers[i].filters == cfg["model"]["layers"][i]
+        assert m.encoder.layers[-2].units == cfg["model"]["encoder_dense_filters"]
+        for idx in range(2, len(m.decoder.layers) - 1):
+            assert m.decoder.layers[idx].filters == cfg["model"]["layers"][L - idx + 1]
+        assert m.decoder.layers[0].units == (16 // 4) * (20 // 4) * cfg["model"]["decoder_dense_filters"]
+        assert len(m.trainable_weights) == 4 * L + 8
+        assert [tuple(v.shape) for v in m.trainable_weights] == [s for _, s in O.variable_shapes(cfg)]

@@ -1,0 +1,51 @@
+"""Kernel-logic parity on CPU: the CUDA sources compiled by g++ against tests/emu/cuda_emu.h
+(a functional simulator of blocks/threads/__syncthreads/shuffles) vs the oracle.  This does
+NOT replace the GPU parity tests (tests/test_gpu_parity.py, -m gpu); it finds indexing and
+orchestration bugs without spending GPU time and runs in the driver's CPU-only gate."""
+import pytest
+
+import parity_cases as PC
+from kcvae_testlib import small_config
+
+BACKEND = "emu"
+
+
+def test_structure():
+    PC.case_structure(BACKEND)
+
+
+def test_forward_and_layers():
+    PC.case_forward(BACKEND)
+    PC.case_layers(BACKEND)
+
+
+@pytest.mark.parametrize("kind", ["global", "single"])
+@pytest.mark.parametrize("training", [True, False])
+def test_loss(kind, training):
+    PC.case_loss(BACKEND, kind, training=training)
+
+
+@pytest.mark.parametrize("kind", ["global", "single"])
+def test_grads(kind):
+    PC.case_grads(BACKEND, kind)
+
+
+@pytest.mark.parametrize("kind", ["global", "single"])
+def test_train_steps(kind):
+    PC.case_train_steps(BACKEND, kind)
+
+
+def test_score():
+    PC.case_score(BACKEND)
+
+
+@pytest.mark.parametrize("shape", [
+    dict(layers=(4,), enc=0, H=8, W=12),                 # one layer, no encoder Dense
+    dict(layers=(4, 3, 5), enc=6, H=16, W=24),           # three layers
+    dict(layers=(33,), enc=3, H=6, W=10, dec=9, latent=3),  # channel counts that are not tile-friendly
+    dict(layers=(2, 2), enc=2, H=12, W=20, C_=1, latent=1),  # single channel, latent 1
+])
+def test_topologies(shape):
+    cfg = small_config(**shape)
+    PC.case_forward(BACKEND, cfg, B=2)
+    PC.case_grads(BACKEND, cfg=cfg, B=3)

@@ -1,0 +1,935 @@
+// model.cu - the C ABI (include/kcvae.h) and the host-side orchestration of one
+// KurtosisCVAE replica on one B200: topology (src/abstract_cvae.py:22-92), forward
+// (:115-149), loss (src/kurtosis_*_cvae.py), hand-derived backward (tape.gradient, :160),
+// gradient / moment all-reduce over NCCL, fused Adam (train.py:99-101) and the anomaly
+// score (do_anomaly_detection.py:57-117).
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/kcvae.h"
+#include "kernels.h"
+
+#ifndef KCVAE_EMU
+#include <dlfcn.h>
+#include <nccl.h>
+#endif
+
+using namespace kc;
+
+namespace {
+
+std::string g_create_error;
+
+struct Var {
+  int rank;
+  int64_t dims[4];
+  int64_t off, n;
+};
+
+#ifndef KCVAE_EMU
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string& err) {
+    if (lib) return true;
+    // bare soname first: resolves to the copy torch already mapped (same NCCL for both)
+    lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("cannot dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define KC_SYM(name) name = reinterpret_cast<decltype(name)>(dlsym(lib, "nccl" #name)); if (!name) { err = "missing nccl" #name; return false; }
+    KC_SYM(GetUniqueId) KC_SYM(CommInitRank) KC_SYM(AllReduce) KC_SYM(Broadcast) KC_SYM(CommDestroy) KC_SYM(GetErrorString)
+#undef KC_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+#else
+typedef void (*emu_allreduce_fn)(void* buf, int64_t count, int dtype, int op);
+emu_allreduce_fn g_emu_allreduce = nullptr;
+#endif
+
+}  // namespace
+
+struct kcvae_model {
+  kcvae_config cfg;
+  int device = 0;
+  std::string err;
+  // topology
+  int L = 0, H = 0, W = 0, C = 0, latent = 0, enc_dense = 0, flat = 0, dec_units = 0;
+  int64_t P = 0;
+  std::vector<int> eh, ew, ec;  // encoder activation sizes, index 0 = input image
+  std::vector<int> dh, dw, dc;  // decoder activation sizes, index 0 = Dense output grid
+  std::vector<Var> vars;
+  int64_t nparams = 0;
+  // parameters / optimizer (flat fp32, Keras variable order)
+  float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+  int64_t adam_t = 0;
+  float lr = 1e-3f, beta = 0.f;
+  LossWeights lw;
+  uint64_t seed = 0x5eed5eedULL, rng_counter = 0;
+  // workspace
+  int cap_fwd = 0, cap_bwd = 0, last_B = 0;
+  std::vector<float*> act_e, act_d, g_act_e, g_act_d;
+  float *x_in = nullptr, *d1 = nullptr, *head = nullptr, *z = nullptr, *mean = nullptr, *logvar = nullptr;
+  float *eps_buf = nullptr, *xhat = nullptr, *x_noisy = nullptr;
+  float *dlogit = nullptr, *g_z = nullptr, *dhead = nullptr, *g_d1 = nullptr;
+  float *partial = nullptr, *err_buf = nullptr, *score_buf = nullptr;
+  size_t partial_floats = 0;
+  double *dpartial = nullptr, *sums = nullptr, *std_acc = nullptr, *pos_sums = nullptr;
+  float *minmax = nullptr, *metrics_dev = nullptr;
+  // data parallel
+  int rank = 0, world = 1;
+#ifndef KCVAE_EMU
+  ncclComm_t comm = nullptr;
+#endif
+
+  float* wp(int vi) const { return w + vars[vi].off; }
+  float* gp(int vi) const { return g + vars[vi].off; }
+  int vi_enc_conv(int l) const { return 2 * l; }
+  int vi_enc_dense() const { return 2 * L; }
+  int vi_head() const { return 2 * L + (enc_dense ? 2 : 0); }
+  int vi_dec_dense() const { return vi_head() + 2; }
+  int vi_dec_convT(int l) const { return vi_dec_dense() + 2 + 2 * l; }
+  int vi_out() const { return vi_dec_dense() + 2 + 2 * L; }
+};
+
+namespace {
+
+#define KC_CUDA(h, expr)                                                                  \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                      \
+      return KCVAE_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+int fail(kcvae_model* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_create_error = msg;
+  return code;
+}
+
+void pad_before(int n_in, int& before) {  // TF SAME, k=3, s=2
+  const int out = (n_in + 1) / 2;
+  int total = (out - 1) * 2 + 3 - n_in;
+  if (total < 0) total = 0;
+  before = total / 2;
+}
+
+int build_topology(kcvae_model* h) {
+  const kcvae_config& c = h->cfg;
+  if (c.image_h <= 0 || c.image_w <= 0 || c.image_c <= 0) return fail(nullptr, KCVAE_ERR_INVALID, "image_size must be positive");
+  if (c.n_layers < 0 || c.n_layers > KCVAE_MAX_LAYERS) return fail(nullptr, KCVAE_ERR_INVALID, "unsupported number of layers");
+  if (c.latent_dimensions <= 0 || c.latent_dimensions > kMaxLatent) return fail(nullptr, KCVAE_ERR_INVALID, "latent_dimensions out of range (1..1024)");
+  if (c.decoder_dense_filters <= 0) return fail(nullptr, KCVAE_ERR_INVALID, "decoder_dense_filters must be positive");
+  h->L = c.n_layers; h->H = c.image_h; h->W = c.image_w; h->C = c.image_c;
+  h->P = (int64_t)h->H * h->W * h->C;
+  h->latent = c.latent_dimensions;
+  h->enc_dense = c.encoder_dense_filters > 0 ? c.encoder_dense_filters : 0;
+  h->eh = {h->H}; h->ew = {h->W}; h->ec = {h->C};
+  for (int l = 0; l < h->L; ++l) {
+    if (c.layers[l] <= 0) return fail(nullptr, KCVAE_ERR_INVALID, "layer filters must be positive");
+    h->eh.push_back((h->eh.back() + 1) / 2);
+    h->ew.push_back((h->ew.back() + 1) / 2);
+    h->ec.push_back(c.layers[l]);
+  }
+  h->flat = h->eh.back() * h->ew.back() * h->ec.back();
+  // decoder: int(float(H) / 2^L) (src/abstract_cvae.py:60-61)
+  const int h0 = (int)((double)h->H / (double)(1LL << h->L));
+  const int w0 = (int)((double)h->W / (double)(1LL << h->L));
+  if (h0 == 0) return fail(nullptr, KCVAE_ERR_COLLAPSE, "Error: Build Decoder: Width Collapse: Too many layers, check configuration file: " + std::to_string(h->H) + " -> 0: " + std::to_string(h->L) + " Layers");
+  if (w0 == 0) return fail(nullptr, KCVAE_ERR_COLLAPSE, "Error: Build Decoder: Height Collapse: Too many layers, check configuration file: " + std::to_string(h->W) + " -> 0: " + std::to_string(h->L) + " Layers");
+  h->dh = {h0}; h->dw = {w0}; h->dc = {c.decoder_dense_filters};
+  for (int l = 0; l < h->L; ++l) {
+    h->dh.push_back(h->dh.back() * 2);
+    h->dw.push_back(h->dw.back() * 2);
+    h->dc.push_back(c.layers[h->L - 1 - l]);
+  }
+  h->dec_units = h0 * w0 * c.decoder_dense_filters;
+  // variables
+  auto add = [&](std::initializer_list<int64_t> dims) {
+    Var v{}; v.rank = (int)dims.size(); v.n = 1; int i = 0;
+    for (auto d : dims) { v.dims[i++] = d; v.n *= d; }
+    v.off = h->nparams;
+    h->nparams += (v.n + 3) / 4 * 4;  // keep every variable 16-byte aligned in the flat vector
+    h->vars.push_back(v);
+  };
+  for (int l = 0; l < h->L; ++l) { add({3, 3, h->ec[l], h->ec[l + 1]}); add({h->ec[l + 1]}); }
+  int k = h->flat;
+  if (h->enc_dense) { add({k, h->enc_dense}); add({h->enc_dense}); k = h->enc_dense; }
+  add({k, 2 * h->latent}); add({2 * h->latent});
+  add({h->latent, h->dec_units}); add({h->dec_units});
+  for (int l = 0; l < h->L; ++l) { add({3, 3, h->dc[l + 1], h->dc[l]}); add({h->dc[l + 1]}); }
+  add({3, 3, h->C, h->dc[h->L]}); add({h->C});
+  return KCVAE_OK;
+}
+
+template <typename T>
+int dalloc(kcvae_model* h, T** p, size_t n) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  if (n == 0) n = 1;
+  KC_CUDA(h, cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return KCVAE_OK;
+}
+#define KC_TRY(expr) do { int rc_ = (expr); if (rc_ != KCVAE_OK) return rc_; } while (0)
+
+size_t max_partial_floats(const kcvae_model* h, int B) {
+  size_t mx = 1;
+  auto up = [&](size_t v) { if (v > mx) mx = v; };
+  const int L = h->L;
+  for (int l = 0; l < L; ++l) {
+    up(wgrad_partial_floats(B, h->eh[l + 1], h->ec[l + 1], h->ec[l]));
+    up(colsum_partial_floats((int64_t)B * h->eh[l + 1] * h->ew[l + 1], h->ec[l + 1]));
+    up(wgrad_partial_floats(B, h->dh[l], h->dc[l], h->dc[l + 1]));
+    up(colsum_partial_floats((int64_t)B * h->dh[l + 1] * h->dw[l + 1], h->dc[l + 1]));
+  }
+  up(wgrad_partial_floats(B, h->dh[L], h->C, h->dc[L]));
+  up(colsum_partial_floats((int64_t)B * h->dh[L] * h->dw[L], h->C));
+  const int kin = h->enc_dense ? h->enc_dense : h->flat;
+  up(gemm_partial_floats(B, h->enc_dense, h->flat));
+  up(gemm_partial_floats(B, 2 * h->latent, kin));
+  up(gemm_partial_floats(B, h->dec_units, h->latent));
+  up(gemm_partial_floats(h->latent, h->dec_units, B));
+  up(gemm_partial_floats(B, h->latent, h->dec_units));
+  up(gemm_partial_floats(kin, 2 * h->latent, B));
+  up(gemm_partial_floats(B, kin, 2 * h->latent));
+  up(gemm_partial_floats(h->flat, h->enc_dense, B));
+  up(gemm_partial_floats(B, h->flat, h->enc_dense));
+  up(colsum_partial_floats(B, 2 * h->latent));
+  up(colsum_partial_floats(B, h->enc_dense ? h->enc_dense : 1));
+  up(colsum_partial_floats(B, h->dec_units));
+  up(score_partial_floats(B, (int64_t)h->H * h->W));
+  return mx;
+}
+
+int ensure_fwd(kcvae_model* h, int B) {
+  if (B <= h->cap_fwd) return KCVAE_OK;
+  const int L = h->L;
+  h->act_e.resize(L + 1, nullptr);
+  h->act_d.resize(L + 1, nullptr);
+  for (int l = 1; l <= L; ++l) KC_TRY(dalloc(h, &h->act_e[l], (size_t)B * h->eh[l] * h->ew[l] * h->ec[l]));
+  for (int l = 0; l <= L; ++l) KC_TRY(dalloc(h, &h->act_d[l], (size_t)B * h->dh[l] * h->dw[l] * h->dc[l]));
+  KC_TRY(dalloc(h, &h->x_in, (size_t)B * h->P));
+  KC_TRY(dalloc(h, &h->x_noisy, (size_t)B * h->P));
+  KC_TRY(dalloc(h, &h->d1, (size_t)B * (h->enc_dense ? h->enc_dense : 1)));
+  KC_TRY(dalloc(h, &h->head, (size_t)B * 2 * h->latent));
+  KC_TRY(dalloc(h, &h->z, (size_t)B * h->latent));
+  KC_TRY(dalloc(h, &h->mean, (size_t)B * h->latent));
+  KC_TRY(dalloc(h, &h->logvar, (size_t)B * h->latent));
+  KC_TRY(dalloc(h, &h->eps_buf, (size_t)B * h->latent));
+  KC_TRY(dalloc(h, &h->xhat, (size_t)B * h->dh[L] * h->dw[L] * h->C));
+  KC_TRY(dalloc(h, &h->err_buf, (size_t)B * h->H * h->W));
+  KC_TRY(dalloc(h, &h->score_buf, (size_t)B));
+  h->partial_floats = max_partial_floats(h, B);
+  KC_TRY(dalloc(h, &h->partial, h->partial_floats));
+  h->cap_fwd = B;
+  h->cap_bwd = 0;  // partial buffer was sized for this B; backward buffers follow
+  return KCVAE_OK;
+}
+
+int ensure_bwd(kcvae_model* h, int B) {
+  KC_TRY(ensure_fwd(h, B));
+  if (B <= h->cap_bwd) return KCVAE_OK;
+  const int L = h->L;
+  const int Bc = h->cap_fwd;
+  h->g_act_e.resize(L + 1, nullptr);
+  h->g_act_d.resize(L + 1, nullptr);
+  for (int l = 1; l <= L; ++l) KC_TRY(dalloc(h, &h->g_act_e[l], (size_t)Bc * h->eh[l] * h->ew[l] * h->ec[l]));
+  for (int l = 0; l <= L; ++l) KC_TRY(dalloc(h, &h->g_act_d[l], (size_t)Bc * h->dh[l] * h->dw[l] * h->dc[l]));
+  KC_TRY(dalloc(h, &h->dlogit, (size_t)Bc * h->P));
+  KC_TRY(dalloc(h, &h->g_z, (size_t)Bc * h->latent));
+  KC_TRY(dalloc(h, &h->dhead, (size_t)Bc * 2 * h->latent));
+  KC_TRY(dalloc(h, &h->g_d1, (size_t)Bc * (h->enc_dense ? h->enc_dense : 1)));
+  h->cap_bwd = Bc;
+  return KCVAE_OK;
+}
+
+int check_batch(kcvae_model* h, int B) {
+  if (!h) return KCVAE_ERR_INVALID;
+  if (B <= 0) return fail(h, KCVAE_ERR_INVALID, "batch must be positive");
+  return KCVAE_OK;
+}
+int check_recon_shape(kcvae_model* h) {
+  if (h->dh[h->L] != h->H || h->dw[h->L] != h->W)
+    return fail(h, KCVAE_ERR_INVALID, "decoder output " + std::to_string(h->dh[h->L]) + "x" + std::to_string(h->dw[h->L]) +
+                " does not match image " + std::to_string(h->H) + "x" + std::to_string(h->W) +
+                ": image_size must be divisible by 2^len(layers) (x - x_hat does not broadcast)");
+  return KCVAE_OK;
+}
+int post(kcvae_model* h) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { h->err = std::string("kernel launch: ") + cudaGetErrorString(e); return KCVAE_ERR_CUDA; }
+  return KCVAE_OK;
+}
+
+// ------------------------------------------------------------------------------ forward
+void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st) {
+  const float* in = x;
+  for (int l = 0; l < h->L; ++l) {
+    ConvArgs a{};
+    a.in = in; a.w = h->wp(h->vi_enc_conv(l)); a.bias = h->wp(h->vi_enc_conv(l) + 1); a.out = h->act_e[l + 1];
+    a.B = B; a.Hi = h->eh[l]; a.Wi = h->ew[l]; a.Ci = h->ec[l];
+    a.Ho = h->eh[l + 1]; a.Wo = h->ew[l + 1]; a.Co = h->ec[l + 1];
+    a.w_sci = a.Co; a.w_sco = 1;  // HWIO
+    pad_before(a.Hi, a.pad_t); pad_before(a.Wi, a.pad_l);
+    conv_forward(CONV_S2, EPI_BIAS_RELU, a, st);
+    in = h->act_e[l + 1];
+  }
+  const float* flat = in;
+  int k = h->flat;
+  if (h->enc_dense) {
+    GemmArgs ga{};
+    ga.A = flat; ga.a_sm = k; ga.a_sk = 1;
+    ga.Bm = h->wp(h->vi_enc_dense()); ga.b_sk = h->enc_dense; ga.b_sn = 1;
+    ga.C = h->d1; ga.bias = h->wp(h->vi_enc_dense() + 1);
+    ga.M = B; ga.N = h->enc_dense; ga.K = k; ga.partial = h->partial;
+    gemm(ga, st);
+    flat = h->d1; k = h->enc_dense;
+  }
+  GemmArgs ga{};
+  ga.A = flat; ga.a_sm = k; ga.a_sk = 1;
+  ga.Bm = h->wp(h->vi_head()); ga.b_sk = 2 * h->latent; ga.b_sn = 1;
+  ga.C = h->head; ga.bias = h->wp(h->vi_head() + 1);
+  ga.M = B; ga.N = 2 * h->latent; ga.K = k; ga.partial = h->partial;
+  gemm(ga, st);
+}
+
+void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float* out, cudaStream_t st) {
+  const int L = h->L;
+  GemmArgs ga{};
+  ga.A = z; ga.a_sm = h->latent; ga.a_sk = 1;
+  ga.Bm = h->wp(h->vi_dec_dense()); ga.b_sk = h->dec_units; ga.b_sn = 1;
+  ga.C = h->act_d[0]; ga.bias = h->wp(h->vi_dec_dense() + 1); ga.relu = 1;
+  ga.M = B; ga.N = h->dec_units; ga.K = h->latent; ga.partial = h->partial;
+  gemm(ga, st);
+  for (int l = 0; l < L; ++l) {
+    ConvArgs a{};
+    a.in = h->act_d[l]; a.w = h->wp(h->vi_dec_convT(l)); a.bias = h->wp(h->vi_dec_convT(l) + 1); a.out = h->act_d[l + 1];
+    a.B = B; a.Hi = h->dh[l]; a.Wi = h->dw[l]; a.Ci = h->dc[l];
+    a.Ho = h->dh[l + 1]; a.Wo = h->dw[l + 1]; a.Co = h->dc[l + 1];
+    a.w_sci = 1; a.w_sco = a.Ci;  // [kh,kw,out,in]
+    conv_forward(CONVT_S2, EPI_BIAS_RELU, a, st);
+  }
+  ConvArgs a{};
+  a.in = h->act_d[L]; a.w = h->wp(h->vi_out()); a.bias = h->wp(h->vi_out() + 1); a.out = out;
+  a.B = B; a.Hi = h->dh[L]; a.Wi = h->dw[L]; a.Ci = h->dc[L];
+  a.Ho = a.Hi; a.Wo = a.Wi; a.Co = h->C;
+  a.w_sci = 1; a.w_sco = a.Ci; a.flip = 1;
+  conv_forward(CONV_S1, apply_sigmoid ? EPI_BIAS_SIGMOID : EPI_BIAS, a, st);
+}
+
+// encode -> reparameterize -> decode+sigmoid into h->xhat (or user buffer); z/mean/logvar in h
+void run_forward(kcvae_model* h, const float* x, int B, int training, const float* eps, float* xhat, cudaStream_t st) {
+  run_encoder(h, x, B, st);
+  const int gen = (training && !eps) ? 1 : 0;
+  reparameterize(h->head, B, h->latent, eps, gen, h->seed, h->rng_counter, h->z, h->mean, h->logvar,
+                 gen ? h->eps_buf : nullptr, st);
+  if (gen) h->rng_counter += ((uint64_t)B * h->latent + 1) / 2;
+  run_decoder(h, h->z, B, 1, xhat, st);
+  h->last_B = B;
+}
+
+// ------------------------------------------------------------------------- collectives
+// op: 0 sum, 1 min, 2 max
+int allreduce(kcvae_model* h, void* buf, int64_t count, int is_double, int op, cudaStream_t st) {
+  if (h->world <= 1) return KCVAE_OK;
+#ifdef KCVAE_EMU
+  (void)st;
+  if (!g_emu_allreduce) return fail(h, KCVAE_ERR_NCCL, "emu: no allreduce callback installed");
+  g_emu_allreduce(buf, count, is_double, op);
+  return KCVAE_OK;
+#else
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, (size_t)count, is_double ? ncclFloat64 : ncclFloat32,
+                                    op == 1 ? ncclMin : (op == 2 ? ncclMax : ncclSum), h->comm, st);
+  if (r != ncclSuccess) return fail(h, KCVAE_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+  return KCVAE_OK;
+#endif
+}
+
+// ------------------------------------------------------------------------------- losses
+int sums_len(const kcvae_model* h) { return S_Z1 + (h->cfg.model_type == KCVAE_SINGLE ? 4 * h->latent : 4); }
+
+// image + latent statistics (and dlogit when with_grad); all-reduced under DP
+int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier, int with_grad, cudaStream_t st) {
+  const int full = tier == KCVAE_METRICS_FULL;
+  const int Bg = B * h->world;
+  latent_sums(h->z, h->mean, h->logvar, B, h->latent, h->cfg.model_type, h->sums, st);
+  ImageStatsArgs ia{};
+  ia.x = x; ia.xhat = xhat; ia.B = B; ia.P = h->P;
+  ia.sums = h->sums; ia.minmax = h->minmax;
+  ia.std_acc = full ? h->std_acc : nullptr;
+  ia.pos_sums = (full && h->world > 1) ? h->pos_sums : nullptr;
+  ia.dlogit = with_grad ? h->dlogit : nullptr;
+  ia.grad_scale = (float)(2.0 * (double)h->lw.w_mse / ((double)Bg * (double)h->P));
+  ia.want_ce = full && h->cfg.model_type == KCVAE_GLOBAL;
+  ia.partial = h->dpartial;
+  image_stats(ia, st);
+  if (h->world > 1) {
+    KC_TRY(allreduce(h, h->sums, sums_len(h), 1, 0, st));
+    if (full) {
+      KC_TRY(allreduce(h, h->pos_sums, 4 * h->P, 1, 0, st));
+      image_std_from_pos_sums(h->pos_sums, h->P, Bg, h->std_acc, h->dpartial, st);
+      KC_TRY(allreduce(h, h->minmax, 1, 0, 1, st));      // min over ranks of min(xhat)
+      KC_TRY(allreduce(h, h->minmax + 1, 1, 0, 2, st));  // max over ranks of max(xhat)
+    }
+  }
+  return KCVAE_OK;
+}
+
+void run_finalize(kcvae_model* h, int B, int tier, float* d_metrics, cudaStream_t st) {
+  const int full = tier == KCVAE_METRICS_FULL;
+  finalize_metrics(h->sums, h->minmax, full ? h->std_acc : nullptr, B * h->world, h->latent, h->P,
+                   h->cfg.model_type, h->lw, full && h->cfg.model_type == KCVAE_GLOBAL, d_metrics, st);
+}
+
+// ------------------------------------------------------------------------------ backward
+void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
+  const int L = h->L;
+  const int Bg = B * h->world;
+  {  // output Conv2DTranspose (s1): wgrad, bias grad, dgrad (+ReLU mask of its input)
+    const int vi = h->vi_out();
+    WgradArgs wa{};
+    wa.P = h->dlogit; wa.Q = h->act_d[L]; wa.out = h->gp(vi); wa.partial = h->partial;
+    wa.B = B; wa.Hp = h->H; wa.Wp = h->W; wa.Ca = h->C; wa.Hq = h->dh[L]; wa.Wq = h->dw[L]; wa.Cb = h->dc[L];
+    wa.s = 1; wa.d = -1; wa.oy = 1; wa.ox = 1;
+    wa.o_sa = wa.Cb; wa.o_sb = 1;  // [tap][out=a][in=b]
+    conv_wgrad(wa, st);
+    colsum(h->dlogit, (int64_t)B * h->H * h->W, h->C, h->gp(vi + 1), h->partial, st);
+    ConvArgs a{};
+    a.in = h->dlogit; a.w = h->wp(vi); a.mask = h->act_d[L]; a.out = h->g_act_d[L];
+    a.B = B; a.Hi = h->H; a.Wi = h->W; a.Ci = h->C; a.Ho = h->dh[L]; a.Wo = h->dw[L]; a.Co = h->dc[L];
+    a.w_sci = a.Co; a.w_sco = 1; a.flip = 0;  // W[tap][co_fwd = ci'][ci_fwd = co']
+    conv_forward(CONV_S1, EPI_MASK, a, st);
+  }
+  for (int l = L - 1; l >= 0; --l) {  // decoder Conv2DTranspose (s2) layers
+    const int vi = h->vi_dec_convT(l);
+    WgradArgs wa{};
+    wa.P = h->act_d[l]; wa.Q = h->g_act_d[l + 1]; wa.out = h->gp(vi); wa.partial = h->partial;
+    wa.B = B; wa.Hp = h->dh[l]; wa.Wp = h->dw[l]; wa.Ca = h->dc[l];
+    wa.Hq = h->dh[l + 1]; wa.Wq = h->dw[l + 1]; wa.Cb = h->dc[l + 1];
+    wa.s = 2; wa.d = 1; wa.oy = 0; wa.ox = 0;
+    wa.o_sa = 1; wa.o_sb = wa.Ca;  // [tap][out=b][in=a]
+    conv_wgrad(wa, st);
+    colsum(h->g_act_d[l + 1], (int64_t)B * h->dh[l + 1] * h->dw[l + 1], h->dc[l + 1], h->gp(vi + 1), h->partial, st);
+    ConvArgs a{};
+    a.in = h->g_act_d[l + 1]; a.w = h->wp(vi); a.mask = h->act_d[l]; a.out = h->g_act_d[l];
+    a.B = B; a.Hi = h->dh[l + 1]; a.Wi = h->dw[l + 1]; a.Ci = h->dc[l + 1];
+    a.Ho = h->dh[l]; a.Wo = h->dw[l]; a.Co = h->dc[l];
+    a.w_sci = a.Co; a.w_sco = 1;  // W[tap][out_fwd = ci'][in_fwd = co']
+    a.pad_t = 0; a.pad_l = 0;
+    conv_forward(CONV_S2, EPI_MASK, a, st);
+  }
+  {  // decoder Dense (ReLU already folded into g_act_d[0] by the mask above)
+    const int vi = h->vi_dec_dense();
+    const float* G = h->g_act_d[0];
+    GemmArgs ga{};
+    ga.A = h->z; ga.a_sm = 1; ga.a_sk = h->latent;
+    ga.Bm = G; ga.b_sk = h->dec_units; ga.b_sn = 1;
+    ga.C = h->gp(vi); ga.M = h->latent; ga.N = h->dec_units; ga.K = B; ga.partial = h->partial;
+    gemm(ga, st);
+    colsum(G, B, h->dec_units, h->gp(vi + 1), h->partial, st);
+    GemmArgs gz{};
+    gz.A = G; gz.a_sm = h->dec_units; gz.a_sk = 1;
+    gz.Bm = h->wp(vi); gz.b_sk = 1; gz.b_sn = h->dec_units;
+    gz.C = h->g_z; gz.M = B; gz.N = h->latent; gz.K = h->dec_units; gz.partial = h->partial;
+    gemm(gz, st);
+  }
+  latent_backward(h->z, h->g_z, h->sums, B, Bg, h->latent, h->cfg.model_type, h->lw, h->dhead, st);
+  const float* flat_act = L > 0 ? h->act_e[L] : x;
+  const float* relu_mask = L > 0 ? h->act_e[L] : nullptr;
+  float* g_flat = L > 0 ? h->g_act_e[L] : nullptr;
+  {  // encoder head Dense (linear)
+    const int vi = h->vi_head();
+    const float* hin = h->enc_dense ? h->d1 : flat_act;
+    const int kin = h->enc_dense ? h->enc_dense : h->flat;
+    GemmArgs ga{};
+    ga.A = hin; ga.a_sm = 1; ga.a_sk = kin;
+    ga.Bm = h->dhead; ga.b_sk = 2 * h->latent; ga.b_sn = 1;
+    ga.C = h->gp(vi); ga.M = kin; ga.N = 2 * h->latent; ga.K = B; ga.partial = h->partial;
+    gemm(ga, st);
+    colsum(h->dhead, B, 2 * h->latent, h->gp(vi + 1), h->partial, st);
+    float* dst = h->enc_dense ? h->g_d1 : g_flat;
+    if (dst) {
+      GemmArgs gi{};
+      gi.A = h->dhead; gi.a_sm = 2 * h->latent; gi.a_sk = 1;
+      gi.Bm = h->wp(vi); gi.b_sk = 1; gi.b_sn = 2 * h->latent;
+      gi.C = dst; gi.mask = h->enc_dense ? nullptr : relu_mask;
+      gi.M = B; gi.N = kin; gi.K = 2 * h->latent; gi.partial = h->partial;
+      gemm(gi, st);
+    }
+  }
+  if (h->enc_dense) {
+    const int vi = h->vi_enc_dense();
+    GemmArgs ga{};
+    ga.A = flat_act; ga.a_sm = 1; ga.a_sk = h->flat;
+    ga.Bm = h->g_d1; ga.b_sk = h->enc_dense; ga.b_sn = 1;
+    ga.C = h->gp(vi); ga.M = h->flat; ga.N = h->enc_dense; ga.K = B; ga.partial = h->partial;
+    gemm(ga, st);
+    colsum(h->g_d1, B, h->enc_dense, h->gp(vi + 1), h->partial, st);
+    if (g_flat) {
+      GemmArgs gi{};
+      gi.A = h->g_d1; gi.a_sm = h->enc_dense; gi.a_sk = 1;
+      gi.Bm = h->wp(vi); gi.b_sk = 1; gi.b_sn = h->enc_dense;
+      gi.C = g_flat; gi.mask = relu_mask;
+      gi.M = B; gi.N = h->flat; gi.K = h->enc_dense; gi.partial = h->partial;
+      gemm(gi, st);
+    }
+  }
+  for (int l = L - 1; l >= 0; --l) {  // encoder Conv2D (s2) layers
+    const int vi = h->vi_enc_conv(l);
+    const float* in = l > 0 ? h->act_e[l] : x;
+    int pt, pl;
+    pad_before(h->eh[l], pt); pad_before(h->ew[l], pl);
+    WgradArgs wa{};
+    wa.P = h->g_act_e[l + 1]; wa.Q = in; wa.out = h->gp(vi); wa.partial = h->partial;
+    wa.B = B; wa.Hp = h->eh[l + 1]; wa.Wp = h->ew[l + 1]; wa.Ca = h->ec[l + 1];
+    wa.Hq = h->eh[l]; wa.Wq = h->ew[l]; wa.Cb = h->ec[l];
+    wa.s = 2; wa.d = 1; wa.oy = -pt; wa.ox = -pl;
+    wa.o_sa = 1; wa.o_sb = wa.Ca;  // HWIO: [tap][in=b][out=a]
+    conv_wgrad(wa, st);
+    colsum(h->g_act_e[l + 1], (int64_t)B * h->eh[l + 1] * h->ew[l + 1], h->ec[l + 1], h->gp(vi + 1), h->partial, st);
+    if (l > 0) {
+      ConvArgs a{};
+      a.in = h->g_act_e[l + 1]; a.w = h->wp(vi); a.mask = h->act_e[l]; a.out = h->g_act_e[l];
+      a.B = B; a.Hi = h->eh[l + 1]; a.Wi = h->ew[l + 1]; a.Ci = h->ec[l + 1];
+      a.Ho = h->eh[l]; a.Wo = h->ew[l]; a.Co = h->ec[l];
+      a.w_sci = 1; a.w_sco = a.Ci;  // W[tap][in_fwd = co'][out_fwd = ci']
+      a.pad_t = pt; a.pad_l = pl;
+      conv_forward(CONVT_S2, EPI_MASK, a, st);
+    }
+  }
+}
+
+int run_adam(kcvae_model* h, cudaStream_t st) {
+  h->adam_t += 1;
+  const double b1 = 0.9, b2 = 0.999;
+  const double lr_t = (double)h->lr * std::sqrt(1.0 - std::pow(b2, (double)h->adam_t)) / (1.0 - std::pow(b1, (double)h->adam_t));
+  adam_update(h->w, h->g, h->m, h->v, h->nparams, (float)lr_t, (float)b1, (float)b2, 1e-7f, st);
+  return KCVAE_OK;
+}
+
+int step_impl(kcvae_model* h, const float* d_x, int B, const float* d_eps, const float* d_img_noise,
+              float* d_metrics, float* d_xhat, int tier, int do_update, cudaStream_t st) {
+  KC_TRY(check_batch(h, B));
+  KC_TRY(check_recon_shape(h));
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_bwd(h, B));
+  const float* x = d_x;
+  if (d_img_noise) {  // opt-in (unreachable in the reference's train_step, SURVEY Note A)
+    add_noise(d_x, d_img_noise, (int64_t)B * h->P, 0.f, 0, 0, h->x_noisy, st);
+    x = h->x_noisy;
+  }
+  float* xh = d_xhat ? d_xhat : h->xhat;
+  run_forward(h, x, B, 1, d_eps, xh, st);
+  KC_TRY(run_stats(h, d_x, xh, B, tier, 1, st));
+  run_backward(h, x, B, st);
+  if (h->world > 1) KC_TRY(allreduce(h, h->g, h->nparams, 0, 0, st));
+  if (do_update) KC_TRY(run_adam(h, st));
+  run_finalize(h, B, tier, d_metrics ? d_metrics : h->metrics_dev, st);
+  return post(h);
+}
+
+}  // namespace
+
+// ======================================================================================
+//                                        C ABI
+// ======================================================================================
+extern "C" {
+
+int kcvae_abi_version(void) { return KCVAE_ABI_VERSION; }
+
+const char* kcvae_last_error(kcvae_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
+  if (!cfg || !out) return fail(nullptr, KCVAE_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->model_type != KCVAE_GLOBAL && cfg->model_type != KCVAE_SINGLE) return fail(nullptr, KCVAE_ERR_INVALID, "unknown model_type");
+  kcvae_model* h = new kcvae_model();
+  h->cfg = *cfg;
+  h->device = device;
+  int rc = build_topology(h);
+  if (rc != KCVAE_OK) { delete h; return rc; }
+  h->lr = cfg->learning_rate; h->beta = cfg->beta;
+  h->lw = LossWeights{cfg->kurtosis_target, cfg->w_mse, cfg->w_kurtosis, cfg->w_skew, cfg->w_z_l1_reg};
+  auto bail = [&](int code) { g_create_error = h->err; kcvae_destroy(h); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) { h->err = "cudaSetDevice failed (no usable GPU?)"; return bail(KCVAE_ERR_CUDA); }
+  if ((rc = dalloc(h, &h->w, (size_t)h->nparams)) || (rc = dalloc(h, &h->g, (size_t)h->nparams)) ||
+      (rc = dalloc(h, &h->m, (size_t)h->nparams)) || (rc = dalloc(h, &h->v, (size_t)h->nparams)) ||
+      (rc = dalloc(h, &h->sums, (size_t)kSumsLen)) || (rc = dalloc(h, &h->std_acc, 1)) ||
+      (rc = dalloc(h, &h->minmax, 4)) || (rc = dalloc(h, &h->metrics_dev, KCVAE_NUM_METRICS)) ||
+      (rc = dalloc(h, &h->dpartial, image_stats_partial_doubles())))
+    return bail(rc);
+  cudaMemset(h->w, 0, h->nparams * sizeof(float));
+  cudaMemset(h->g, 0, h->nparams * sizeof(float));
+  cudaMemset(h->m, 0, h->nparams * sizeof(float));
+  cudaMemset(h->v, 0, h->nparams * sizeof(float));
+  cudaMemset(h->sums, 0, kSumsLen * sizeof(double));
+  if (cfg->max_batch > 0 && (rc = ensure_fwd(h, cfg->max_batch))) return bail(rc);
+  *out = h;
+  return KCVAE_OK;
+}
+
+int kcvae_destroy(kcvae_handle h) {
+  if (!h) return KCVAE_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+#ifndef KCVAE_EMU
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+#endif
+  for (float* p : h->act_e) if (p) cudaFree(p);
+  for (float* p : h->act_d) if (p) cudaFree(p);
+  for (float* p : h->g_act_e) if (p) cudaFree(p);
+  for (float* p : h->g_act_d) if (p) cudaFree(p);
+  float* fl[] = {h->w, h->g, h->m, h->v, h->x_in, h->d1, h->head, h->z, h->mean, h->logvar, h->eps_buf, h->xhat,
+                 h->x_noisy, h->dlogit, h->g_z, h->dhead, h->g_d1, h->partial, h->err_buf, h->score_buf, h->minmax,
+                 h->metrics_dev};
+  for (float* p : fl) if (p) cudaFree(p);
+  double* dl[] = {h->dpartial, h->sums, h->std_acc, h->pos_sums};
+  for (double* p : dl) if (p) cudaFree(p);
+  delete h;
+  return KCVAE_OK;
+}
+
+int kcvae_num_variables(kcvae_handle h) { return h ? (int)h->vars.size() : KCVAE_ERR_INVALID; }
+
+int64_t kcvae_param_count(kcvae_handle h) {
+  if (!h) return KCVAE_ERR_INVALID;
+  int64_t n = 0;
+  for (const Var& v : h->vars) n += v.n;
+  return n;
+}
+
+int kcvae_variable_info(kcvae_handle h, int idx, int32_t* rank, int64_t dims[4], int64_t* offset) {
+  if (!h || idx < 0 || idx >= (int)h->vars.size()) return KCVAE_ERR_INVALID;
+  const Var& v = h->vars[idx];
+  if (rank) *rank = v.rank;
+  if (dims) for (int i = 0; i < 4; ++i) dims[i] = i < v.rank ? v.dims[i] : 1;
+  if (offset) *offset = v.off;
+  return KCVAE_OK;
+}
+
+// h_flat is the dense concatenation of the variables (no alignment padding), n = param_count
+int kcvae_set_weights(kcvae_handle h, const float* h_flat, int64_t n) {
+  if (!h || !h_flat) return KCVAE_ERR_INVALID;
+  if (n != kcvae_param_count(h)) return fail(h, KCVAE_ERR_INVALID, "set_weights: wrong element count");
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_CUDA(h, cudaDeviceSynchronize());
+  int64_t src = 0;
+  for (const Var& v : h->vars) {
+    KC_CUDA(h, cudaMemcpy(h->w + v.off, h_flat + src, v.n * sizeof(float), cudaMemcpyHostToDevice));
+    src += v.n;
+  }
+  return KCVAE_OK;
+}
+
+static int copy_out_flat(kcvae_handle h, const float* dev, float* h_flat, int64_t n) {
+  if (!h || !h_flat) return KCVAE_ERR_INVALID;
+  if (n != kcvae_param_count(h)) return fail(h, KCVAE_ERR_INVALID, "wrong element count");
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_CUDA(h, cudaDeviceSynchronize());
+  int64_t dst = 0;
+  for (const Var& v : h->vars) {
+    KC_CUDA(h, cudaMemcpy(h_flat + dst, dev + v.off, v.n * sizeof(float), cudaMemcpyDeviceToHost));
+    dst += v.n;
+  }
+  return KCVAE_OK;
+}
+int kcvae_get_weights(kcvae_handle h, float* h_flat, int64_t n) { return copy_out_flat(h, h ? h->w : nullptr, h_flat, n); }
+int kcvae_get_grads(kcvae_handle h, float* h_flat, int64_t n) { return copy_out_flat(h, h ? h->g : nullptr, h_flat, n); }
+
+float* kcvae_weights_device(kcvae_handle h) { return h ? h->w : nullptr; }
+float* kcvae_grads_device(kcvae_handle h) { return h ? h->g : nullptr; }
+
+int kcvae_init_glorot(kcvae_handle h, uint64_t seed, void* stream) {
+  if (!h) return KCVAE_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_CUDA(h, cudaMemsetAsync(h->w, 0, h->nparams * sizeof(float), st));
+  uint32_t sid = 0;
+  for (const Var& v : h->vars) {
+    ++sid;
+    if (v.rank == 1) continue;  // zero biases
+    double fan_in, fan_out;
+    if (v.rank == 4) { fan_in = (double)v.dims[0] * v.dims[1] * v.dims[2]; fan_out = (double)v.dims[0] * v.dims[1] * v.dims[3]; }
+    else { fan_in = (double)v.dims[0]; fan_out = (double)v.dims[1]; }
+    glorot_fill(h->w + v.off, v.n, (float)std::sqrt(6.0 / (fan_in + fan_out)), seed, sid, st);
+  }
+  return post(h);
+}
+
+int kcvae_adam_reset(kcvae_handle h) {
+  if (!h) return KCVAE_ERR_INVALID;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_CUDA(h, cudaDeviceSynchronize());
+  KC_CUDA(h, cudaMemset(h->m, 0, h->nparams * sizeof(float)));
+  KC_CUDA(h, cudaMemset(h->v, 0, h->nparams * sizeof(float)));
+  h->adam_t = 0;
+  return KCVAE_OK;
+}
+
+int kcvae_set_adam_state(kcvae_handle h, const float* h_m, const float* h_v, int64_t n, int64_t t) {
+  if (!h || !h_m || !h_v) return KCVAE_ERR_INVALID;
+  if (n != kcvae_param_count(h)) return fail(h, KCVAE_ERR_INVALID, "set_adam_state: wrong element count");
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_CUDA(h, cudaDeviceSynchronize());
+  int64_t src = 0;
+  for (const Var& v : h->vars) {
+    KC_CUDA(h, cudaMemcpy(h->m + v.off, h_m + src, v.n * sizeof(float), cudaMemcpyHostToDevice));
+    KC_CUDA(h, cudaMemcpy(h->v + v.off, h_v + src, v.n * sizeof(float), cudaMemcpyHostToDevice));
+    src += v.n;
+  }
+  h->adam_t = t;
+  return KCVAE_OK;
+}
+
+int kcvae_get_adam_state(kcvae_handle h, float* h_m, float* h_v, int64_t n, int64_t* t) {
+  if (!h) return KCVAE_ERR_INVALID;
+  if (h_m) KC_TRY(copy_out_flat(h, h->m, h_m, n));
+  if (h_v) KC_TRY(copy_out_flat(h, h->v, h_v, n));
+  if (t) *t = h->adam_t;
+  return KCVAE_OK;
+}
+
+int kcvae_set_learning_rate(kcvae_handle h, float lr) { if (!h) return KCVAE_ERR_INVALID; h->lr = lr; return KCVAE_OK; }
+int kcvae_set_beta(kcvae_handle h, float beta) { if (!h) return KCVAE_ERR_INVALID; h->beta = beta; return KCVAE_OK; }
+int kcvae_set_loss_weights(kcvae_handle h, float kurtosis_target, float w_mse, float w_kurtosis, float w_skew,
+                           float w_z_l1_reg) {
+  if (!h) return KCVAE_ERR_INVALID;
+  h->lw = LossWeights{kurtosis_target, w_mse, w_kurtosis, w_skew, w_z_l1_reg};
+  return KCVAE_OK;
+}
+int kcvae_seed(kcvae_handle h, uint64_t seed) { if (!h) return KCVAE_ERR_INVALID; h->seed = seed; h->rng_counter = 0; return KCVAE_OK; }
+
+// ---- data parallel ---------------------------------------------------------------------
+int kcvae_comm_unique_id(void* out_id128) {
+  if (!out_id128) return KCVAE_ERR_INVALID;
+#ifdef KCVAE_EMU
+  memset(out_id128, 0, 128);
+  return KCVAE_OK;
+#else
+  if (!g_nccl.load(g_create_error)) return KCVAE_ERR_NCCL;
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return KCVAE_ERR_NCCL; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  memcpy(out_id128, &id, 128);
+  return KCVAE_OK;
+#endif
+}
+
+int kcvae_comm_init(kcvae_handle h, const void* id128, int rank, int world_size) {
+  if (!h || !id128 || world_size < 1 || rank < 0 || rank >= world_size) return KCVAE_ERR_INVALID;
+  KC_CUDA(h, cudaSetDevice(h->device));
+#ifndef KCVAE_EMU
+  if (!g_nccl.load(h->err)) return KCVAE_ERR_NCCL;
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclResult_t r = g_nccl.CommInitRank(&h->comm, world_size, id, rank);
+  if (r != ncclSuccess) return fail(h, KCVAE_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+#endif
+  h->rank = rank; h->world = world_size;
+  if (world_size > 1) KC_TRY(dalloc(h, &h->pos_sums, (size_t)4 * h->P));
+  return KCVAE_OK;
+}
+
+int kcvae_comm_world(kcvae_handle h) { return h ? h->world : KCVAE_ERR_INVALID; }
+
+int kcvae_broadcast_weights(kcvae_handle h, int root, void* stream) {
+  if (!h) return KCVAE_ERR_INVALID;
+  if (h->world <= 1) return KCVAE_OK;
+#ifdef KCVAE_EMU
+  (void)root; (void)stream;
+  return fail(h, KCVAE_ERR_UNSUPPORTED, "emu: broadcast not emulated");
+#else
+  ncclResult_t r = g_nccl.Broadcast(h->w, h->w, (size_t)h->nparams, ncclFloat32, root, h->comm, (cudaStream_t)stream);
+  if (r != ncclSuccess) return fail(h, KCVAE_ERR_NCCL, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r));
+  return KCVAE_OK;
+#endif
+}
+
+// ---- forward ---------------------------------------------------------------------------
+int kcvae_encode(kcvae_handle h, const float* d_x, int batch, int training, const float* d_img_noise,
+                 float* d_mean, float* d_logvar, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!d_x || !d_mean || !d_logvar) return fail(h, KCVAE_ERR_INVALID, "encode: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_fwd(h, batch));
+  const float* x = d_x;
+  if (training || d_img_noise) {  // src/abstract_cvae.py:117-118
+    const int64_t n = (int64_t)batch * h->P;
+    add_noise(d_x, d_img_noise, n, h->beta, h->seed, h->rng_counter, h->x_noisy, st);
+    if (!d_img_noise) h->rng_counter += (uint64_t)(n + 1) / 2;
+    x = h->x_noisy;
+  }
+  run_encoder(h, x, batch, st);
+  // split: z computed with eps = 0 into scratch, mean / logvar to the caller
+  reparameterize(h->head, batch, h->latent, nullptr, 0, 0, 0, h->z, d_mean, d_logvar, nullptr, st);
+  h->last_B = batch;
+  return post(h);
+}
+
+int kcvae_reparameterize(kcvae_handle h, const float* d_mean, const float* d_logvar, int batch, int training,
+                         const float* d_eps, float* d_z, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!d_mean || !d_logvar || !d_z) return fail(h, KCVAE_ERR_INVALID, "reparameterize: null pointer");
+  KC_CUDA(h, cudaSetDevice(h->device));
+  const int gen = (training && !d_eps) ? 1 : 0;
+  reparam_from_parts(d_mean, d_logvar, batch, h->latent, d_eps, gen, h->seed, h->rng_counter, d_z, (cudaStream_t)stream);
+  if (gen) h->rng_counter += ((uint64_t)batch * h->latent + 1) / 2;
+  return post(h);
+}
+
+int kcvae_decode(kcvae_handle h, const float* d_z, int batch, int apply_sigmoid, float* d_out, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!d_z || !d_out) return fail(h, KCVAE_ERR_INVALID, "decode: null pointer");
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_fwd(h, batch));
+  run_decoder(h, d_z, batch, apply_sigmoid, d_out, (cudaStream_t)stream);
+  h->last_B = batch;
+  return post(h);
+}
+
+int kcvae_forward(kcvae_handle h, const float* d_x, int batch, int training, const float* d_eps, float* d_xhat,
+                  float* d_z, float* d_mean, float* d_logvar, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!d_x || !d_xhat) return fail(h, KCVAE_ERR_INVALID, "forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_fwd(h, batch));
+  run_forward(h, d_x, batch, training, d_eps, d_xhat, st);
+  const size_t nb = (size_t)batch * h->latent * sizeof(float);
+  if (d_z) KC_CUDA(h, cudaMemcpyAsync(d_z, h->z, nb, cudaMemcpyDeviceToDevice, st));
+  if (d_mean) KC_CUDA(h, cudaMemcpyAsync(d_mean, h->mean, nb, cudaMemcpyDeviceToDevice, st));
+  if (d_logvar) KC_CUDA(h, cudaMemcpyAsync(d_logvar, h->logvar, nb, cudaMemcpyDeviceToDevice, st));
+  return post(h);
+}
+
+// ---- loss / train ------------------------------------------------------------------------
+int kcvae_loss(kcvae_handle h, const float* d_x, int batch, int training, const float* d_eps, float* d_metrics,
+               float* d_xhat, int tier, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!d_x || !d_metrics) return fail(h, KCVAE_ERR_INVALID, "loss: null pointer");
+  KC_TRY(check_recon_shape(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_fwd(h, batch));
+  float* xh = d_xhat ? d_xhat : h->xhat;
+  run_forward(h, d_x, batch, training, d_eps, xh, st);
+  KC_TRY(run_stats(h, d_x, xh, batch, tier, 0, st));
+  run_finalize(h, batch, tier, d_metrics, st);
+  return post(h);
+}
+
+int kcvae_train_step(kcvae_handle h, const float* d_x, int batch, const float* d_eps, const float* d_img_noise,
+                     float* d_metrics, float* d_xhat, int tier, void* stream) {
+  if (!h || !d_x) return KCVAE_ERR_INVALID;
+  return step_impl(h, d_x, batch, d_eps, d_img_noise, d_metrics, d_xhat, tier, 1, (cudaStream_t)stream);
+}
+
+int kcvae_loss_and_grads(kcvae_handle h, const float* d_x, int batch, const float* d_eps, float* d_metrics,
+                         float* d_xhat, int tier, void* stream) {
+  if (!h || !d_x) return KCVAE_ERR_INVALID;
+  return step_impl(h, d_x, batch, d_eps, nullptr, d_metrics, d_xhat, tier, 0, (cudaStream_t)stream);
+}
+
+// ---- scoring ---------------------------------------------------------------------------
+int kcvae_score(kcvae_handle h, const float* d_x, int batch, float* d_err, float* d_score, float* d_err_minmax,
+                float* d_xhat, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!d_x || !d_score) return fail(h, KCVAE_ERR_INVALID, "score: null pointer");
+  KC_TRY(check_recon_shape(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_fwd(h, batch));
+  float* xh = d_xhat ? d_xhat : h->xhat;
+  run_forward(h, d_x, batch, 0, nullptr, xh, st);
+  score(d_x, xh, batch, (int64_t)h->H * h->W, h->C, d_err, d_score, d_err_minmax, h->partial, st);
+  return post(h);
+}
+
+int kcvae_normalize_scores(kcvae_handle h, const float* d_err, const float* d_score, int batch, float meu,
+                           float sigma, float emin, float emax, float threshold, float* d_norm, float* d_z,
+                           uint8_t* d_flags, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!d_score) return fail(h, KCVAE_ERR_INVALID, "normalize_scores: null pointer");
+  KC_CUDA(h, cudaSetDevice(h->device));
+  normalize_scores(d_err, d_score, batch, (int64_t)h->H * h->W, meu, sigma, emin, emax, threshold, d_norm, d_z,
+                   d_flags, (cudaStream_t)stream);
+  return post(h);
+}
+
+// ---- host-buffer entry points -------------------------------------------------------------
+int kcvae_train_step_host(kcvae_handle h, const float* h_x, int batch, const float* h_eps, float* h_metrics,
+                          float* h_xhat, int tier, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!h_x || !h_metrics) return fail(h, KCVAE_ERR_INVALID, "train_step_host: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_bwd(h, batch));
+  KC_CUDA(h, cudaMemcpyAsync(h->x_in, h_x, (size_t)batch * h->P * sizeof(float), cudaMemcpyHostToDevice, st));
+  const float* eps = nullptr;
+  if (h_eps) {
+    KC_CUDA(h, cudaMemcpyAsync(h->eps_buf, h_eps, (size_t)batch * h->latent * sizeof(float), cudaMemcpyHostToDevice, st));
+    eps = h->eps_buf;
+  }
+  KC_TRY(step_impl(h, h->x_in, batch, eps, nullptr, h->metrics_dev, h->xhat, tier, 1, st));
+  KC_CUDA(h, cudaMemcpyAsync(h_metrics, h->metrics_dev, KCVAE_NUM_METRICS * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_xhat) KC_CUDA(h, cudaMemcpyAsync(h_xhat, h->xhat, (size_t)batch * h->P * sizeof(float), cudaMemcpyDeviceToHost, st));
+  KC_CUDA(h, cudaStreamSynchronize(st));
+  return KCVAE_OK;
+}
+
+int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, float* h_score, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!h_x || !h_score) return fail(h, KCVAE_ERR_INVALID, "score_host: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_fwd(h, batch));
+  KC_CUDA(h, cudaMemcpyAsync(h->x_in, h_x, (size_t)batch * h->P * sizeof(float), cudaMemcpyHostToDevice, st));
+  KC_TRY(kcvae_score(h, h->x_in, batch, h_err ? h->err_buf : nullptr, h->score_buf, nullptr, nullptr, stream));
+  if (h_err) KC_CUDA(h, cudaMemcpyAsync(h_err, h->err_buf, (size_t)batch * h->H * h->W * sizeof(float), cudaMemcpyDeviceToHost, st));
+  KC_CUDA(h, cudaMemcpyAsync(h_score, h->score_buf, (size_t)batch * sizeof(float), cudaMemcpyDeviceToHost, st));
+  KC_CUDA(h, cudaStreamSynchronize(st));
+  return KCVAE_OK;
+}
+
+// ---- introspection -------------------------------------------------------------------------
+int64_t kcvae_launch_count(kcvae_handle) { return kc::g_launches; }
+
+int64_t kcvae_debug_activation(kcvae_handle h, int which, float* h_out, int64_t capacity) {
+  if (!h || h->last_B <= 0) return KCVAE_ERR_INVALID;
+  const int B = h->last_B, L = h->L;
+  const float* src = nullptr;
+  int64_t n = 0;
+  if (which >= 1 && which <= L) { src = h->act_e[which]; n = (int64_t)B * h->eh[which] * h->ew[which] * h->ec[which]; }
+  else if (which >= 100 && which <= 100 + L) { int l = which - 100; src = h->act_d[l]; n = (int64_t)B * h->dh[l] * h->dw[l] * h->dc[l]; }
+  else if (which == 200) { src = h->head; n = (int64_t)B * 2 * h->latent; }
+  else if (which == 201) { src = h->z; n = (int64_t)B * h->latent; }
+  else if (which == 300) { src = h->dlogit; n = (int64_t)B * h->P; }
+  else if (which >= 301 && which <= 301 + L && (int)h->g_act_d.size() > which - 301) { int l = which - 301; src = h->g_act_d[l]; n = (int64_t)B * h->dh[l] * h->dw[l] * h->dc[l]; }
+  else if (which == 350) { src = h->g_z; n = (int64_t)B * h->latent; }
+  else if (which == 351) { src = h->dhead; n = (int64_t)B * 2 * h->latent; }
+  else if (which >= 361 && which <= 360 + L && (int)h->g_act_e.size() > which - 360) { int l = which - 360; src = h->g_act_e[l]; n = (int64_t)B * h->eh[l] * h->ew[l] * h->ec[l]; }
+  if (!src) return fail(h, KCVAE_ERR_INVALID, "debug_activation: unknown or unallocated tensor");
+  if (!h_out) return n;
+  if (capacity < n) return fail(h, KCVAE_ERR_INVALID, "debug_activation: buffer too small");
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(h_out, src, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, KCVAE_ERR_CUDA, "debug_activation: copy failed");
+  return n;
+}
+
+#ifdef KCVAE_EMU
+// tests only: route the data-parallel all-reduce through a host callback (gloo in pytest)
+void kcvae_emu_set_allreduce(void (*fn)(void*, int64_t, int, int)) { g_emu_allreduce = fn; }
+#endif
+
+}  // extern "C"

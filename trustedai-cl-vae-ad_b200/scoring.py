@@ -1,0 +1,66 @@
+"""Anomaly scoring loops of do_anomaly_detection.py:57-117 on the CUDA scorer.
+
+Same function names, argument order and returned keys as the reference; the per-batch
+work (forward, per-pixel error, per-frame sum, per-frame min/max) is one kcvae_score call,
+the set-level statistics are a handful of scalars."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .model import _ptr, _wrap
+
+
+def _iter(data):
+    return data['train'] if isinstance(data, dict) else data
+
+
+def get_data_scale(model, config: dict, data):
+    """do_anomaly_detection.py:57-79.  Unlike the reference it does not keep every error map
+    in memory: min/max come from the per-frame (min,max) pairs the kernel emits."""
+    scores, mins, maxs = [], [], []
+    for batch in _iter(data):
+        r = model.score(batch, return_err=False)
+        scores.append(r['score'])
+        mins.append(r['err_minmax'][:, 0])
+        maxs.append(r['err_minmax'][:, 1])
+    err_reduced = torch.cat(scores)
+    meu = err_reduced.mean()
+    sigma = err_reduced.std(unbiased=False)           # tf.math.reduce_std: population
+    return {
+        'meu': _wrap(meu), 'sigma': _wrap(sigma),
+        'min': _wrap(torch.cat(mins).min()), 'max': _wrap(torch.cat(maxs).max()),
+        'z_scores': _wrap((err_reduced - meu) / sigma),
+    }
+
+
+def evaluate_anomalies(model, config: dict, data, data_scale: dict, anomaly_threshold: float, keep_rec: bool = True):
+    """do_anomaly_detection.py:82-117."""
+    meu, sigma = float(data_scale['meu']), float(data_scale['sigma'])
+    emin, emax = float(data_scale['min']), float(data_scale['max'])
+    recs, errs, zs, norms, flags = [], [], [], [], []
+    lib, h = model._lib, model._h
+    for batch in _iter(data):
+        r = model.score(batch, return_err=True, return_rec=keep_rec)
+        B = r['score'].shape[0]
+        norm = torch.empty_like(r['err'])
+        z = torch.empty_like(r['score'])
+        fl = torch.empty(B, dtype=torch.uint8, device=z.device)
+        lib.check(lib.normalize_scores(h, _ptr(r['err']), _ptr(r['score']), B, meu, sigma, emin, emax,
+                                       float(anomaly_threshold), _ptr(norm), _ptr(z), _ptr(fl), model._stream()), h)
+        if keep_rec:
+            recs.append(r['rec'])
+        errs.append(r['err']); zs.append(z); norms.append(norm); flags.append(fl)
+    cat = lambda v: torch.cat(v, 0).cpu().numpy()
+    return {
+        'rec': cat(recs) if keep_rec else None,
+        'errs': cat(errs),
+        'z_scores': cat(zs),
+        'norm_errs': cat(norms),
+        'anomalies': cat(flags).astype(bool),
+    }
+
+
+def rank_anomalies(z_scores: np.ndarray) -> np.ndarray:
+    """Descending z-score order (do_anomaly_detection.py:190, dead code after exit() at :157)."""
+    return np.argsort(-np.asarray(z_scores), kind='stable')
