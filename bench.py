@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py - KurtosisGlobalCVAE train step (+ anomaly scoring) throughput on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port, TF absent)
+
+One JSON line on stdout (rank 0).  A "step" is one train_step (forward, loss, backward,
+gradient all-reduce under DP, Adam) over one synthetic batch of README-config frames
+(224x300x3, layers [32,5], latent 32), BASELINE.json configs[1]: 32 frames per GPU, i.e.
+global batch 256 on 8 GPUs (weak scaling).  Inputs cycle through a pool larger than the
+126 MB L2.  `value` is device-timed with inputs resident in HBM; `e2e` is the same step
+through the host-buffer C-ABI call (pinned host frames, H2D and the metrics D2H inside).
+"""
+import argparse
+import importlib
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 32
+CPU_SAMPLE_BATCH = 16
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--precision", default=os.environ.get("KCVAE_PRECISION", "fp32"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-score", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- clocks sampling
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for ts, r in self.rows:
+            if t0 is not None and not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [c.strip() for c in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------- algorithmic byte table
+def algorithmic_bytes(cfg, B, world):
+    """Per-launch algorithmic bytes of every profiled launcher, SURVEY 8(d) convention:
+    inter-layer activations counted once in bf16 (2 B), x and weights fp32 (4 B), each
+    tensor a kernel reads or writes counted once.  Keys = '<layer tag>/<kernel>'."""
+    from oracle import kcvae_oracle as O
+    t = O.topology(cfg)
+    I = t.H * t.W * t.C
+    enc = [I] + [h * w * c for (h, w), c in zip(t.enc_hw, t.layers)]
+    dec = [t.dec_h0 * t.dec_w0 * t.dec_dense]
+    h, w = t.dec_h0, t.dec_w0
+    for f in reversed(t.layers):
+        h, w = 2 * h, 2 * w
+        dec.append(h * w * f)
+    shapes = dict(O.variable_shapes(cfg))
+    nW = {k: int(__import__("numpy").prod(v)) for k, v in shapes.items()}
+    L = len(t.layers)
+    act = 2  # bytes / activation element
+    tab = {}
+    names = {0: "enc.conv0", 1: "enc.conv1"}
+    for l in range(L):
+        nm = names.get(l, "enc.convN")
+        wk = 4 * nW[f"encoder/conv2d_{l}/kernel"]
+        inb = 4 * enc[0] if l == 0 else act * enc[l]
+        tab[f"{nm}.fwd/conv3x3"] = B * (inb + act * enc[l + 1]) + wk
+        tab[f"{nm}.bwd/wgrad"] = B * (inb + act * enc[l + 1]) + wk
+        tab[f"{nm}.bwd/colsum"] = B * act * enc[l + 1]
+        if l > 0:
+            tab[f"{nm}.bwd/conv3x3"] = B * (act * enc[l + 1] + 2 * act * enc[l]) + wk
+    for l in range(L):
+        nm = "dec.convT_last" if l == L - 1 else "dec.convT"
+        wk = 4 * nW[f"decoder/conv2d_transpose_{l}/kernel"]
+        tab[f"{nm}.fwd/conv3x3"] = B * act * (dec[l] + dec[l + 1]) + wk
+        tab[f"{nm}.bwd/wgrad"] = B * act * (dec[l] + dec[l + 1]) + wk
+        tab[f"{nm}.bwd/colsum"] = B * act * dec[l + 1]
+        tab[f"{nm}.bwd/conv3x3"] = B * act * (dec[l + 1] + 2 * dec[l]) + wk
+    wk = 4 * nW["decoder/conv2d_transpose_out/kernel"]
+    tab["dec.out.fwd/conv3x3"] = B * act * (dec[L] + I) + wk
+    tab["dec.out.bwd/wgrad"] = B * act * (dec[L] + I) + wk
+    tab["dec.out.bwd/colsum"] = B * act * I
+    tab["dec.out.bwd/conv3x3"] = B * act * (I + 2 * dec[L]) + wk
+    wd = 4 * nW["decoder/dense/kernel"]
+    tab["dec.dense.fwd/gemm"] = B * (4 * t.latent + act * dec[0]) + wd
+    tab["dec.dense.bwd/gemm"] = 2 * (B * (4 * t.latent + act * dec[0]) + wd)   # dW and dz launches
+    tab["dec.dense.bwd/colsum"] = B * act * dec[0]
+    if t.enc_dense:
+        we = 4 * nW["encoder/dense/kernel"]
+        tab["enc.dense.fwd/gemm"] = B * (act * enc[L] + 4 * t.enc_dense) + we
+        tab["enc.dense.bwd/gemm"] = 2 * (B * (act * enc[L] + 4 * t.enc_dense) + we)
+    tab["loss/image_stats"] = B * (4 * I + act * I + act * I)      # x, xhat in; dlogit out
+    P = sum(nW.values())
+    tab["optimizer/adam"] = 7 * 4 * P                               # p,g,m,v read; p,m,v written
+    step_bytes = B * (4 * I + act * (5 * (sum(enc[1:]) + sum(dec)) + 3 * I)) + 10 * 4 * P   # SURVEY 8d train
+    return tab, step_bytes
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+# --------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_rates(cfg, steps, warmup, batch):
+    """The reference's CPU implementation of the path.  TensorFlow is not installable in
+    this image, so this is the torch-CPU restatement (oracle), all host threads."""
+    import torch
+    from oracle import kcvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    om = O.OracleModel(cfg)
+    x, eps = O.synthetic_frames(batch, cfg), O.synthetic_eps(batch, cfg)
+    for _ in range(warmup):
+        om.train_step(x, eps)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        om.train_step(x, eps)
+    dt = time.perf_counter() - t0
+    train = steps * batch / dt
+    xt = torch.from_numpy(x)
+    for _ in range(1):
+        O.error_map(xt, om.call(xt)).sum(dim=(1, 2))
+    t0 = time.perf_counter()
+    ns = max(2, steps // 2)
+    for _ in range(ns):
+        O.error_map(xt, om.call(xt)).sum(dim=(1, 2))
+    score = ns * batch / (time.perf_counter() - t0)
+    return train, score, dt / steps * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import kcvae_oracle as O
+    cfg = O.readme_config()
+    steps, warm = min(args.steps, 30), min(args.warmup, 3)
+    train, score, ms = cpu_oracle_rates(cfg, steps, warm, CPU_SAMPLE_BATCH)
+    cores = os.cpu_count() or 1
+    sample = f"{steps} train_steps of batch {CPU_SAMPLE_BATCH} (README config) after {warm} warm-up; torch-CPU restatement, TF unavailable"
+    line = {
+        "impl": "reference", "metric": "train_images_per_sec", "value": train, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "KurtosisGlobalCVAE README config 224x300x3 layers[32,5] latent32 train_step",
+                   "batch": CPU_SAMPLE_BATCH},
+        "cpu_baseline": {"value": train, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
+                         "score_frames_per_sec": score},
+        "e2e": {"value": train, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from oracle import kcvae_oracle as O
+    pkg = importlib.import_module("trustedai-cl-vae-ad_b200")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = O.readme_config()
+    B = args.batch_per_gpu
+    model = pkg.load_model_from_config(cfg, device=local, precision=args.precision, metrics="full")
+    model.set_weights(O.glorot_init(cfg, 1234))
+    model.compile(optimizer=pkg.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
+    model.seed(1000 + rank)
+    if world > 1:
+        model.distribute()
+
+    H, W, C = cfg["data"]["image_size"]
+    batch_bytes = B * H * W * C * 4
+    npool = max(2, math.ceil(L2_BYTES * 1.3 / batch_bytes) + 1)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    pool = [torch.rand((B, H, W, C), generator=g, device=dev, dtype=torch.float32) for _ in range(npool)]
+    host_pool = [torch.rand((B, H, W, C), dtype=torch.float32).pin_memory() for _ in range(min(npool, 4))]
+    metrics_host = torch.empty(16, dtype=torch.float32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier(device_ids=[local])
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for s in range(steps):
+            fn(s)
+        e1.record()
+        sync_all()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    train_fn = lambda s: model.train_step(pool[s % npool])          # eps: on-device Philox
+    for s in range(Wm):
+        train_fn(s)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    n0 = model.launch_count()
+    t0 = clocks.mark()
+    ms_total = timed(train_fn, K)
+    t1 = clocks.mark()
+    launches = model.launch_count() - n0
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+    value = world * B * K / (ms_total * 1e-3)
+
+    # end to end: pinned host frames -> H2D -> step -> metrics D2H, every step
+    e2e_fn = lambda s: model.train_step_host(host_pool[s % len(host_pool)], None, metrics_host)
+    for s in range(3):
+        e2e_fn(s)
+    ms_e2e = timed(e2e_fn, K)
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+
+    # per-launch timing of the same K steps (events on the launching stream)
+    model.profile(True)
+    timed(train_fn, K)
+    rep = model.profile_report()
+    model.profile(False)
+    tab, step_bytes = algorithmic_bytes(cfg, B, world)
+    tot = sum(ms for _, ms in rep.values()) or 1.0
+    top = max(rep.items(), key=lambda kv: kv[1][1])
+    top_key, (top_calls, top_ms) = top
+    peak, peak_src = hbm_peak()
+    roof = {"bound": "hbm", "kernel": top_key, "share_of_step": top_ms / tot, "unit": "GB/s", "peak": peak,
+            "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": None,
+            "convention": "algorithmic bytes: activations bf16, x/weights fp32 (SURVEY 8d)"}
+    if top_key in tab:
+        avg_s = top_ms / top_calls * 1e-3
+        roof["achieved"] = tab[top_key] / avg_s / 1e9
+        roof["frac"] = roof["achieved"] / peak
+        roof["avg_launch_ms"] = top_ms / top_calls
+        roof["algorithmic_bytes_per_launch"] = tab[top_key]
+    else:
+        roof["achieved"], roof["frac"] = None, None
+    step_ach = step_bytes / (ms_total / K * 1e-3) / 1e9
+    roof["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_ach, "frac": step_ach / peak}
+    roof["kernel_breakdown_ms_per_step"] = {k: round(v[1] / K, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:12]}
+
+    # anomaly scoring (do_anomaly_detection.py loops): frames/s resident and end to end
+    score_info = None
+    if not args.no_score:
+        Bs = 128
+        spool = [torch.rand((Bs, H, W, C), generator=g, device=dev, dtype=torch.float32) for _ in range(3)]
+        shost = torch.rand((Bs, H, W, C), dtype=torch.float32).pin_memory()
+        sc_host = torch.empty(Bs, dtype=torch.float32).pin_memory()
+        sfn = lambda s: model.score(spool[s % 3], return_err=True)
+        for s in range(2):
+            sfn(s)
+        Ks = max(3, K // 2)
+        ms_s = timed(sfn, Ks)
+        hfn = lambda s: model.score_host(shost, sc_host)
+        hfn(0)
+        ms_sh = timed(hfn, Ks)
+        score_info = {"metric": "anomaly_score_frames_per_sec", "value": world * Bs * Ks / (ms_s * 1e-3),
+                      "e2e": world * Bs * Ks / (ms_sh * 1e-3), "unit": "frames/s", "batch_per_gpu": Bs,
+                      "outputs": "err map [B,H,W] + per-frame score"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ctrain, cscore, cms = cpu_oracle_rates(cfg, 8, 2, CPU_SAMPLE_BATCH)
+        cpu = {"value": ctrain, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"8 train_steps of batch {CPU_SAMPLE_BATCH} (README config), torch-CPU restatement of the TF path (TF unavailable)",
+               "score_frames_per_sec": cscore, "ms_per_step": cms}
+
+    if rank == 0:
+        line = {
+            "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": "KurtosisGlobalCVAE README config 224x300x3 layers[32,5] latent32 train_step (BASELINE configs[1])",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "metrics_tier": "full", "l2_policy": f"inputs cycle through a {npool * batch_bytes >> 20} MiB pool (> 126 MiB L2)",
+                       "precision": args.precision},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": batch_bytes,
+                    "d2h_bytes_per_step": 16 * 4, "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "score": score_info,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -171,6 +171,10 @@ int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, 
 /* ---- introspection --------------------------------------------------------------------- */
 /* number of kernels this library launched on behalf of handle h since creation */
 int64_t kcvae_launch_count(kcvae_handle h);
+/* per-launch device timing with CUDA events on the launching stream (bench.py roofline):
+ * enable, run steps, then report "<layer tag>/<kernel> <calls> <total ms>" lines */
+int kcvae_profile_enable(int on);
+int64_t kcvae_profile_report(char* buf, int64_t capacity);
 /* copies an internal activation for layer-level parity tests: which = 0..(encoder convs),
  * then decoder stages; returns element count or negative status */
 int64_t kcvae_debug_activation(kcvae_handle h, int which, float* h_out, int64_t capacity);

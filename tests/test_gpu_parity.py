@@ -1,0 +1,200 @@
+"""GPU parity tests proper (-m gpu): libkcvae.so through the C ABI (ctypes) on a B200 vs the
+CPU oracle on the same injected weights / inputs / noise; plus size-independent properties
+at the BASELINE.json sizes.  Tolerances: north_star allows <=1e-3 relative on loss terms and
+<=1e-2 max-abs on reconstructions; the fp32 path is held to tighter bounds, written per assert."""
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as PC
+from kcvae_testlib import O, assert_metrics_close, eps_for, frames, make, pkg, rel_err, small_config
+
+pytestmark = pytest.mark.gpu
+BACKEND = "cuda"
+
+
+def test_native_library_is_the_one_loaded():
+    import importlib
+    lib = importlib.import_module("trustedai-cl-vae-ad_b200._lib").load()
+    assert lib.path.endswith("libkcvae.so") and lib.device_type == "cuda"
+    m, _ = make(small_config(), BACKEND)
+    n0 = m.launch_count()
+    m.call(frames(small_config(), 2))
+    assert m.launch_count() > n0          # our kernels ran
+
+
+def test_structure():
+    PC.case_structure(BACKEND)
+
+
+def test_forward_and_layers_small():
+    PC.case_forward(BACKEND)
+    PC.case_layers(BACKEND)
+
+
+@pytest.mark.parametrize("kind", ["global", "single"])
+@pytest.mark.parametrize("training", [True, False])
+def test_loss_small(kind, training):
+    PC.case_loss(BACKEND, kind, training=training)
+
+
+@pytest.mark.parametrize("kind", ["global", "single"])
+def test_grads_small(kind):
+    PC.case_grads(BACKEND, kind)
+
+
+@pytest.mark.parametrize("kind", ["global", "single"])
+def test_train_steps_small(kind):
+    PC.case_train_steps(BACKEND, kind)
+
+
+def test_score_small():
+    PC.case_score(BACKEND)
+
+
+@pytest.mark.parametrize("shape", [
+    dict(layers=(4,), enc=0, H=8, W=12),
+    dict(layers=(4, 3, 5), enc=6, H=16, W=24),
+    dict(layers=(33,), enc=3, H=6, W=10, dec=9, latent=3),
+    dict(layers=(2, 2), enc=2, H=12, W=20, C_=1, latent=1),
+    dict(layers=(16, 24), enc=8, H=64, W=100, dec=16, latent=16),
+])
+def test_topologies(shape):
+    cfg = small_config(**shape)
+    PC.case_forward(BACKEND, cfg, B=2)
+    PC.case_grads(BACKEND, cfg=cfg, B=3)
+
+
+# ---------------------------------------------------------------- reference-sized configs
+def test_unit_test_config_golden_identities():
+    """tests/test_kurtosis_global_cvae.py:151-178 through the CUDA path: weight-independent
+    golden entries to the reference's 6 places."""
+    cfg = O.unit_test_config()
+    m, ws = make(cfg, BACKEND, bias_scale=0.0)
+    np.random.seed(42)
+    x = np.random.random(size=[1, 224, 300, 3]).astype(np.float32)
+    d = {k: float(v) for k, v in m.compute_loss(x, training=False).items()}
+    assert abs(d["z_kurtosis"] - 1.0) < 1e-5 and abs(d["z_kurtosis_loss"] - 2.0) < 1e-5
+    assert abs(d["skew_loss"]) < 1e-5 and abs(d["x_std_loss"]) < 1e-6
+    assert abs(d["mse"] - 0.083257124) < 2e-4 and abs(d["cross_entropy"] - 6.1276054) < 2e-3
+    od = O.compute_loss(cfg, ws, x)[0]
+    assert_metrics_close(d, od, rtol=1e-4)
+    cfg = O.unit_test_config("KurtosisSingle")
+    m, ws = make(cfg, BACKEND, bias_scale=0.0)
+    np.random.seed(42)
+    x = np.random.random(size=[16, 224, 300, 3]).astype(np.float32)
+    d = m.compute_loss(x, training=False)
+    assert abs(float(d["x_std_loss"]) - 0.07809097) < 2e-5
+    assert_metrics_close(d, O.compute_loss(cfg, ws, x)[0], rtol=2e-4)
+
+
+@pytest.mark.parametrize("kind", ["global", "single"])
+def test_readme_config_loss_and_grads(kind):
+    cfg = O.readme_config("KurtosisSingle" if kind == "single" else None)
+    B = 4
+    m, ws = make(cfg, BACKEND, weight_gain=1.3)
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    d, grads = m.loss_and_grads(x, eps=eps)
+    od, ograds, oxh, _ = O.loss_and_grads(cfg, ws, x, eps)
+    assert_metrics_close(d, od, rtol=5e-4)                        # north_star: 1e-3
+    for (n, _), g, og in zip(O.variable_shapes(cfg), grads, ograds):
+        assert rel_err(g, og.numpy()) < 1e-3, n
+    xh = m.call(x, training=True, eps=eps)
+    assert float(np.max(np.abs(xh.numpy() - oxh.numpy()))) < 1e-4   # north_star: 1e-2
+
+
+def test_readme_config_train_steps():
+    cfg = O.readme_config()
+    PC.case_train_steps(BACKEND, cfg=cfg, B=4, steps=2)
+
+
+def test_readme_config_scoring_and_ranking():
+    cfg = O.readme_config()
+    m, ws = make(cfg, BACKEND)
+    om = O.OracleModel(cfg, ws)
+    x = frames(cfg, 12)
+    for i, b in enumerate((2, 7)):                       # planted anomalies of separated size
+        x[b, 40:40 + 24 * (i + 1), 50:50 + 24 * (i + 1), :] = 1.0
+    r = m.score(x, return_err=True, return_rec=True)
+    oxh = om.call(torch.from_numpy(x))
+    oerr = O.error_map(torch.from_numpy(x), oxh)
+    np.testing.assert_allclose(r["err"].numpy(), oerr.numpy(), atol=2e-5)
+    osc = oerr.sum(dim=(1, 2)).numpy()
+    np.testing.assert_allclose(r["score"].numpy(), osc, rtol=2e-5)
+    assert list(np.argsort(-r["score"].numpy(), kind="stable")) == list(np.argsort(-osc, kind="stable"))
+    assert list(np.argsort(-osc)[:2]) == [7, 2]
+    mm = r["err_minmax"].numpy()
+    np.testing.assert_allclose(mm[:, 0], oerr.numpy().reshape(12, -1).min(1), atol=1e-6)
+    np.testing.assert_allclose(mm[:, 1], oerr.numpy().reshape(12, -1).max(1), atol=2e-5)
+
+
+# --------------------------------------------------- size-independent properties, full sizes
+def test_properties_at_baseline_batch():
+    cfg = O.readme_config()
+    B = 32
+    m, _ = make(cfg, BACKEND)
+    m.compile(optimizer=pkg.Adam(1e-4))
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    # scoring is per-frame independent: score(batch) == concat(score(halves))
+    full = m.score(x)["score"].numpy()
+    halves = np.concatenate([m.score(x[:16])["score"].numpy(), m.score(x[16:])["score"].numpy()])
+    np.testing.assert_allclose(full, halves, rtol=1e-6)
+    # mse of the dict == mean of per-frame scores / (H*W*C)
+    d = m.compute_loss(x, training=False)
+    assert abs(float(d["mse"]) - full.mean() / (224 * 300 * 3)) < 1e-6
+    # train_step reports the loss of the weights BEFORE the update, and loss goes down
+    d0 = m.compute_loss(x, training=True, eps=eps)
+    d1 = m.train_step(x, eps=eps)
+    assert_metrics_close(d1, d0, rtol=1e-6, atol=1e-7)
+    for _ in range(5):
+        m.train_step(x, eps=eps)
+    d2 = m.compute_loss(x, training=True, eps=eps)
+    assert float(d2["loss"]) < float(d0["loss"])
+    # determinism: same inputs, same weights -> bitwise identical metrics
+    a = m.compute_loss(x, training=True, eps=eps)
+    b = m.compute_loss(x, training=True, eps=eps)
+    assert all(float(a[k]) == float(b[k]) for k in a)
+    # loss-only tier agrees on the terms that drive the gradient
+    m.metric_tier = 1
+    c = m.compute_loss(x, training=True, eps=eps)
+    for k in ("loss", "mse", "z_l1", "z_kurtosis_loss", "z_kurtosis", "skew_loss"):
+        assert float(c[k]) == float(a[k])
+
+
+def test_device_rng_and_noise_paths():
+    cfg = small_config()
+    m, ws = make(cfg, BACKEND)
+    x = frames(cfg, 64)
+    m.seed(123)
+    _, z, mean, logvar = m.call_detailed(x, training=True)          # on-device Philox eps
+    e = (z - mean - 0.5 * logvar).numpy().ravel()
+    assert abs(e.mean()) < 0.2 and 0.8 < e.std() < 1.2
+    m.beta = 0.1
+    mean_n, _ = m.encode(x, training=True)                           # N(0, beta^2) image noise
+    mean_c, _ = m.encode(x, training=False)
+    assert float((mean_n - mean_c).abs().max()) > 0
+    noise = np.random.default_rng(0).standard_normal(x.shape).astype(np.float32) * 0.1
+    mean_i, lv_i = m.encode(x, noise=noise)
+    t = O.topology(cfg)
+    om, olv, _ = O.encoder_forward(t, [torch.tensor(w) for w in ws], torch.tensor(x + noise))
+    np.testing.assert_allclose(mean_i.numpy(), om.numpy(), atol=3e-5)
+
+
+def test_error_behaviour():
+    bad = small_config()
+    bad["model"]["layers"] = [4] * 6
+    with pytest.raises(RuntimeError):
+        make(bad, BACKEND)
+    cfg = small_config()
+    del cfg["loss"]["w_x_std"]
+    with pytest.raises(KeyError):
+        pkg.load_model_from_config(cfg)
+    cfg = small_config()
+    cfg["model"]["type"] = "KLGaussian"
+    with pytest.raises(NotImplementedError):
+        pkg.load_model_from_config(cfg)
+    m, _ = make(small_config(), BACKEND)
+    with pytest.raises(ValueError):
+        m.call(np.zeros((2, 8, 8, 3), np.float32))
+    with pytest.raises(RuntimeError):
+        m.train_step(frames(small_config(), 2))          # not compiled

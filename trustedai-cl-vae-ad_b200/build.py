@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(one, srcs))
-    _run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-lcuda", "-ldl"], log)
+    _run([nvcc, "-shared", "-o", LIB, *objs, "-ldl"], log)  # cudart is linked statically (nvcc default)
     with open(os.path.join(objdir, "build.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -21,6 +21,20 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // counted by every launcher; kcvae_launch_count() reports it (bench.py "gpu_launches")
 extern int64_t g_launches;
 
+// ---- per-launch device timing (bench.py roofline): CUDA events on the launching stream ----
+// model.cu sets g_tag to the layer/role before calling a launcher; when profiling is enabled
+// each launcher brackets its kernels with two events keyed "<tag>/<kernel>".
+extern const char* g_tag;
+extern bool g_prof_on;
+void prof_begin(const char* kernel, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(const char* kernel, cudaStream_t s) : st(s), on(g_prof_on) { if (on) prof_begin(kernel, st); }
+  ~ProfScope() { if (on) prof_end(st); }
+};
+
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // grid for a grid-stride kernel: enough blocks for `work` items, capped at `waves` full
 // waves of `per_sm` resident blocks on the 148 SMs

@@ -114,6 +114,7 @@ static void launch_mode(int epi, const ConvArgs& a, cudaStream_t st) {
 }
 
 void conv_forward(int mode, int epi, const ConvArgs& a, cudaStream_t st) {
+  ProfScope prof_("conv3x3", st);
   if (mode == CONV_S2) launch_mode<CONV_S2>(epi, a, st);
   else if (mode == CONV_S1) launch_mode<CONV_S1>(epi, a, st);
   else launch_mode<CONVT_S2>(epi, a, st);
@@ -176,6 +177,7 @@ __global__ void wgrad_reduce_kernel(const float* partial, int chunks, int E, int
 }
 
 void conv_wgrad(const WgradArgs& a, cudaStream_t st) {
+  ProfScope prof_("wgrad", st);
   const int E = 9 * a.Ca * a.Cb;
   const int chunks = wgrad_chunks(a.B, a.Hp, a.Ca, a.Cb);
   const int rows = a.B * a.Hp;
@@ -237,6 +239,7 @@ __global__ void colsum_large_kernel(const float* in, int64_t rows, int C, float*
 }
 
 void colsum(const float* in, int64_t rows, int C, float* out, float* partial, cudaStream_t st) {
+  ProfScope prof_("colsum", st);
   if (C > 256) {
     ++g_launches;
     KC_LAUNCH(colsum_large_kernel, cdiv(C, 256), 256, 0, st, in, rows, C, out);

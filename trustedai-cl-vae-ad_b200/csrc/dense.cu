@@ -94,6 +94,7 @@ __global__ void gemm_splitk_reduce_kernel(GemmArgs a, int splits) {
 }
 
 void gemm(const GemmArgs& a, cudaStream_t st) {
+  ProfScope prof_("gemm", st);
   if (a.M <= 0 || a.N <= 0) return;
   int splits = a.partial ? gemm_splits(a.M, a.N, a.K) : 1;
   int kps = cdiv(cdiv(a.K, splits), TK) * TK;

@@ -108,6 +108,7 @@ __global__ void image_stats_finish_kernel(const double* partial, int blocks, int
 }
 
 void image_stats(const ImageStatsArgs& a, cudaStream_t st) {
+  ProfScope prof_("image_stats", st);
   int blocks = cdiv(a.P, 256);
   if (blocks > kStatBlocks) blocks = kStatBlocks;
   g_launches += 2;
@@ -139,6 +140,7 @@ __global__ void sum_doubles_kernel(const double* partial, int n, double* out) {
 }
 void image_std_from_pos_sums(const double* pos_sums, int64_t P, int B_global, double* std_acc,
                              double* partial, cudaStream_t st) {
+  ProfScope prof_("image_std", st);
   int blocks = cdiv(P, 256);
   if (blocks > kStatBlocks) blocks = kStatBlocks;
   g_launches += 2;
@@ -177,12 +179,14 @@ __global__ void reparam_kernel(const float* head, const float* mean_in, const fl
 void reparameterize(const float* head, int B, int L, const float* eps, int gen_eps, uint64_t seed,
                     uint64_t counter, float* z, float* mean, float* logvar, float* eps_out,
                     cudaStream_t st) {
+  ProfScope prof_("reparam", st);
   ++g_launches;
   KC_LAUNCH(reparam_kernel, grid_for((int64_t)B * L, 256), 256, 0, st, head, (const float*)nullptr,
             (const float*)nullptr, B, L, eps, gen_eps, seed, counter, z, mean, logvar, eps_out);
 }
 void reparam_from_parts(const float* mean, const float* logvar, int B, int L, const float* eps,
                         int gen_eps, uint64_t seed, uint64_t counter, float* z, cudaStream_t st) {
+  ProfScope prof_("reparam", st);
   ++g_launches;
   KC_LAUNCH(reparam_kernel, grid_for((int64_t)B * L, 256), 256, 0, st, (const float*)nullptr, mean,
             logvar, B, L, eps, gen_eps, seed, counter, z, (float*)nullptr, (float*)nullptr,
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(256) latent_sums_kernel(const float* z, const 
 }
 void latent_sums(const float* z, const float* mean, const float* logvar, int B, int L, int model_type,
                  double* sums, cudaStream_t st) {
+  ProfScope prof_("latent_sums", st);
   ++g_launches;
   KC_LAUNCH(latent_sums_kernel, 1, 256, 0, st, z, mean, logvar, B, L, model_type, sums);
 }
@@ -287,6 +292,7 @@ __global__ void finalize_metrics_kernel(const double* sums, const float* minmax,
 void finalize_metrics(const double* sums, const float* minmax, const double* std_acc, int B_global,
                       int L, int64_t P, int model_type, LossWeights lw, int have_ce, float* metrics,
                       cudaStream_t st) {
+  ProfScope prof_("finalize_metrics", st);
   ++g_launches;
   KC_LAUNCH(finalize_metrics_kernel, 1, 32, 0, st, sums, minmax, std_acc, B_global, L, P, model_type, lw,
             have_ce, metrics);
@@ -335,6 +341,7 @@ __global__ void latent_backward_kernel(const float* z, const float* g_z, const d
 }
 void latent_backward(const float* z, const float* g_z, const double* sums, int B_local, int B_global,
                      int L, int model_type, LossWeights lw, float* dhead, cudaStream_t st) {
+  ProfScope prof_("latent_backward", st);
   ++g_launches;
   KC_LAUNCH(latent_backward_kernel, grid_for((int64_t)B_local * L, 128), 128, 0, st, z, g_z, sums, B_local,
             B_global, L, model_type, lw, dhead);
@@ -392,6 +399,7 @@ __global__ void score_finish_kernel(const float* partial, int chunks, int B, flo
 }
 void score(const float* x, const float* xhat, int B, int64_t HW, int C, float* err, float* score_out,
            float* err_minmax, float* partial, cudaStream_t st) {
+  ProfScope prof_("score", st);
   const int chunks = cdiv(HW, kScorePixPerBlock);
   g_launches += 2;
   KC_LAUNCH(score_kernel, dim3(chunks, B), 256, 0, st, x, xhat, HW, C, err, partial);
@@ -415,6 +423,7 @@ __global__ void normalize_scores_kernel(const float* err, const float* score_in,
 void normalize_scores(const float* err, const float* score_in, int B, int64_t HW, float meu, float sigma,
                       float emin, float emax, float thr, float* norm, float* z, uint8_t* flags,
                       cudaStream_t st) {
+  ProfScope prof_("normalize_scores", st);
   ++g_launches;
   KC_LAUNCH(normalize_scores_kernel, grid_for((int64_t)B * HW, 256), 256, 0, st, err, score_in, B, HW, meu,
             sigma, emin, emax, thr, norm, z, flags);
@@ -430,6 +439,7 @@ __global__ void add_noise_kernel(const float* x, const float* noise, int64_t n, 
 }
 void add_noise(const float* x, const float* noise, int64_t n, float stddev, uint64_t seed, uint64_t counter,
                float* out, cudaStream_t st) {
+  ProfScope prof_("add_noise", st);
   ++g_launches;
   KC_LAUNCH(add_noise_kernel, grid_for(n, 256), 256, 0, st, x, noise, n, stddev, seed, counter, out);
 }
@@ -461,6 +471,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, flo
 }
 void adam_update(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2,
                  float eps, cudaStream_t st) {
+  ProfScope prof_("adam", st);
   ++g_launches;
   KC_LAUNCH(adam_kernel, grid_for(n / 4 + 1, 256, 8, 2), 256, 0, st, p, g, m, v, n, lr_t, b1, b2, eps);
 }
@@ -474,6 +485,7 @@ __global__ void glorot_fill_kernel(float* p, int64_t n, float limit, uint64_t se
   }
 }
 void glorot_fill(float* p, int64_t n, float limit, uint64_t seed, uint32_t stream_id, cudaStream_t st) {
+  ProfScope prof_("glorot_fill", st);
   ++g_launches;
   KC_LAUNCH(glorot_fill_kernel, grid_for(n, 256), 256, 0, st, p, n, limit, seed, stream_id);
 }

@@ -18,6 +18,29 @@
 
 using namespace kc;
 
+// ---- per-launch event profiler (see common.cuh) --------------------------------------------
+namespace kc {
+const char* g_tag = "";
+bool g_prof_on = false;
+#ifndef KCVAE_EMU
+namespace {
+struct ProfRec { std::string key; cudaEvent_t e0, e1; };
+std::vector<ProfRec> g_prof_recs;
+}
+void prof_begin(const char* kernel, cudaStream_t st) {
+  ProfRec r;
+  r.key = std::string(g_tag) + "/" + kernel;
+  cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof_recs.push_back(r);
+}
+void prof_end(cudaStream_t st) { if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().e1, st); }
+#else
+void prof_begin(const char*, cudaStream_t) {}
+void prof_end(cudaStream_t) {}
+#endif
+}  // namespace kc
+
 namespace {
 
 std::string g_create_error;
@@ -279,6 +302,7 @@ void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     a.Ho = h->eh[l + 1]; a.Wo = h->ew[l + 1]; a.Co = h->ec[l + 1];
     a.w_sci = a.Co; a.w_sco = 1;  // HWIO
     pad_before(a.Hi, a.pad_t); pad_before(a.Wi, a.pad_l);
+    g_tag = l == 0 ? "enc.conv0.fwd" : (l == 1 ? "enc.conv1.fwd" : "enc.convN.fwd");
     conv_forward(CONV_S2, EPI_BIAS_RELU, a, st);
     in = h->act_e[l + 1];
   }
@@ -290,6 +314,7 @@ void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     ga.Bm = h->wp(h->vi_enc_dense()); ga.b_sk = h->enc_dense; ga.b_sn = 1;
     ga.C = h->d1; ga.bias = h->wp(h->vi_enc_dense() + 1);
     ga.M = B; ga.N = h->enc_dense; ga.K = k; ga.partial = h->partial;
+    g_tag = "enc.dense.fwd";
     gemm(ga, st);
     flat = h->d1; k = h->enc_dense;
   }
@@ -298,6 +323,7 @@ void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st) {
   ga.Bm = h->wp(h->vi_head()); ga.b_sk = 2 * h->latent; ga.b_sn = 1;
   ga.C = h->head; ga.bias = h->wp(h->vi_head() + 1);
   ga.M = B; ga.N = 2 * h->latent; ga.K = k; ga.partial = h->partial;
+  g_tag = "enc.head.fwd";
   gemm(ga, st);
 }
 
@@ -308,6 +334,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   ga.Bm = h->wp(h->vi_dec_dense()); ga.b_sk = h->dec_units; ga.b_sn = 1;
   ga.C = h->act_d[0]; ga.bias = h->wp(h->vi_dec_dense() + 1); ga.relu = 1;
   ga.M = B; ga.N = h->dec_units; ga.K = h->latent; ga.partial = h->partial;
+  g_tag = "dec.dense.fwd";
   gemm(ga, st);
   for (int l = 0; l < L; ++l) {
     ConvArgs a{};
@@ -315,6 +342,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
     a.B = B; a.Hi = h->dh[l]; a.Wi = h->dw[l]; a.Ci = h->dc[l];
     a.Ho = h->dh[l + 1]; a.Wo = h->dw[l + 1]; a.Co = h->dc[l + 1];
     a.w_sci = 1; a.w_sco = a.Ci;  // [kh,kw,out,in]
+    g_tag = l == L - 1 ? "dec.convT_last.fwd" : "dec.convT.fwd";
     conv_forward(CONVT_S2, EPI_BIAS_RELU, a, st);
   }
   ConvArgs a{};
@@ -322,6 +350,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   a.B = B; a.Hi = h->dh[L]; a.Wi = h->dw[L]; a.Ci = h->dc[L];
   a.Ho = a.Hi; a.Wo = a.Wi; a.Co = h->C;
   a.w_sci = 1; a.w_sco = a.Ci; a.flip = 1;
+  g_tag = "dec.out.fwd";
   conv_forward(CONV_S1, apply_sigmoid ? EPI_BIAS_SIGMOID : EPI_BIAS, a, st);
 }
 
@@ -329,6 +358,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
 void run_forward(kcvae_model* h, const float* x, int B, int training, const float* eps, float* xhat, cudaStream_t st) {
   run_encoder(h, x, B, st);
   const int gen = (training && !eps) ? 1 : 0;
+  g_tag = "latent";
   reparameterize(h->head, B, h->latent, eps, gen, h->seed, h->rng_counter, h->z, h->mean, h->logvar,
                  gen ? h->eps_buf : nullptr, st);
   if (gen) h->rng_counter += ((uint64_t)B * h->latent + 1) / 2;
@@ -360,6 +390,7 @@ int sums_len(const kcvae_model* h) { return S_Z1 + (h->cfg.model_type == KCVAE_S
 int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier, int with_grad, cudaStream_t st) {
   const int full = tier == KCVAE_METRICS_FULL;
   const int Bg = B * h->world;
+  g_tag = "loss";
   latent_sums(h->z, h->mean, h->logvar, B, h->latent, h->cfg.model_type, h->sums, st);
   ImageStatsArgs ia{};
   ia.x = x; ia.xhat = xhat; ia.B = B; ia.P = h->P;
@@ -385,6 +416,7 @@ int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier
 
 void run_finalize(kcvae_model* h, int B, int tier, float* d_metrics, cudaStream_t st) {
   const int full = tier == KCVAE_METRICS_FULL;
+  g_tag = "loss";
   finalize_metrics(h->sums, h->minmax, full ? h->std_acc : nullptr, B * h->world, h->latent, h->P,
                    h->cfg.model_type, h->lw, full && h->cfg.model_type == KCVAE_GLOBAL, d_metrics, st);
 }
@@ -400,6 +432,7 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     wa.B = B; wa.Hp = h->H; wa.Wp = h->W; wa.Ca = h->C; wa.Hq = h->dh[L]; wa.Wq = h->dw[L]; wa.Cb = h->dc[L];
     wa.s = 1; wa.d = -1; wa.oy = 1; wa.ox = 1;
     wa.o_sa = wa.Cb; wa.o_sb = 1;  // [tap][out=a][in=b]
+    g_tag = "dec.out.bwd";
     conv_wgrad(wa, st);
     colsum(h->dlogit, (int64_t)B * h->H * h->W, h->C, h->gp(vi + 1), h->partial, st);
     ConvArgs a{};
@@ -416,6 +449,7 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     wa.Hq = h->dh[l + 1]; wa.Wq = h->dw[l + 1]; wa.Cb = h->dc[l + 1];
     wa.s = 2; wa.d = 1; wa.oy = 0; wa.ox = 0;
     wa.o_sa = 1; wa.o_sb = wa.Ca;  // [tap][out=b][in=a]
+    g_tag = l == L - 1 ? "dec.convT_last.bwd" : "dec.convT.bwd";
     conv_wgrad(wa, st);
     colsum(h->g_act_d[l + 1], (int64_t)B * h->dh[l + 1] * h->dw[l + 1], h->dc[l + 1], h->gp(vi + 1), h->partial, st);
     ConvArgs a{};
@@ -429,6 +463,7 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
   {  // decoder Dense (ReLU already folded into g_act_d[0] by the mask above)
     const int vi = h->vi_dec_dense();
     const float* G = h->g_act_d[0];
+    g_tag = "dec.dense.bwd";
     GemmArgs ga{};
     ga.A = h->z; ga.a_sm = 1; ga.a_sk = h->latent;
     ga.Bm = G; ga.b_sk = h->dec_units; ga.b_sn = 1;
@@ -441,6 +476,7 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     gz.C = h->g_z; gz.M = B; gz.N = h->latent; gz.K = h->dec_units; gz.partial = h->partial;
     gemm(gz, st);
   }
+  g_tag = "latent";
   latent_backward(h->z, h->g_z, h->sums, B, Bg, h->latent, h->cfg.model_type, h->lw, h->dhead, st);
   const float* flat_act = L > 0 ? h->act_e[L] : x;
   const float* relu_mask = L > 0 ? h->act_e[L] : nullptr;
@@ -448,6 +484,7 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
   {  // encoder head Dense (linear)
     const int vi = h->vi_head();
     const float* hin = h->enc_dense ? h->d1 : flat_act;
+    g_tag = "enc.head.bwd";
     const int kin = h->enc_dense ? h->enc_dense : h->flat;
     GemmArgs ga{};
     ga.A = hin; ga.a_sm = 1; ga.a_sk = kin;
@@ -467,6 +504,7 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
   }
   if (h->enc_dense) {
     const int vi = h->vi_enc_dense();
+    g_tag = "enc.dense.bwd";
     GemmArgs ga{};
     ga.A = flat_act; ga.a_sm = 1; ga.a_sk = h->flat;
     ga.Bm = h->g_d1; ga.b_sk = h->enc_dense; ga.b_sn = 1;
@@ -493,6 +531,7 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     wa.Hq = h->eh[l]; wa.Wq = h->ew[l]; wa.Cb = h->ec[l];
     wa.s = 2; wa.d = 1; wa.oy = -pt; wa.ox = -pl;
     wa.o_sa = 1; wa.o_sb = wa.Ca;  // HWIO: [tap][in=b][out=a]
+    g_tag = l == 0 ? "enc.conv0.bwd" : (l == 1 ? "enc.conv1.bwd" : "enc.convN.bwd");
     conv_wgrad(wa, st);
     colsum(h->g_act_e[l + 1], (int64_t)B * h->eh[l + 1] * h->ew[l + 1], h->ec[l + 1], h->gp(vi + 1), h->partial, st);
     if (l > 0) {
@@ -511,6 +550,7 @@ int run_adam(kcvae_model* h, cudaStream_t st) {
   h->adam_t += 1;
   const double b1 = 0.9, b2 = 0.999;
   const double lr_t = (double)h->lr * std::sqrt(1.0 - std::pow(b2, (double)h->adam_t)) / (1.0 - std::pow(b1, (double)h->adam_t));
+  g_tag = "optimizer";
   adam_update(h->w, h->g, h->m, h->v, h->nparams, (float)lr_t, (float)b1, (float)b2, 1e-7f, st);
   return KCVAE_OK;
 }
@@ -851,6 +891,7 @@ int kcvae_score(kcvae_handle h, const float* d_x, int batch, float* d_err, float
   KC_TRY(ensure_fwd(h, batch));
   float* xh = d_xhat ? d_xhat : h->xhat;
   run_forward(h, d_x, batch, 0, nullptr, xh, st);
+  g_tag = "score";
   score(d_x, xh, batch, (int64_t)h->H * h->W, h->C, d_err, d_score, d_err_minmax, h->partial, st);
   return post(h);
 }
@@ -925,6 +966,47 @@ int64_t kcvae_debug_activation(kcvae_handle h, int which, float* h_out, int64_t 
   cudaDeviceSynchronize();
   if (cudaMemcpy(h_out, src, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, KCVAE_ERR_CUDA, "debug_activation: copy failed");
   return n;
+}
+
+// ---- per-launch timing ---------------------------------------------------------------------
+int kcvae_profile_enable(int on) {
+  kc::g_prof_on = on != 0;
+  return KCVAE_OK;
+}
+// synchronises the device, then writes one line per key: "<tag>/<kernel> <launcher calls> <total ms>\n"
+// and clears the records.  Returns the number of bytes needed (excluding NUL).
+int64_t kcvae_profile_report(char* buf, int64_t capacity) {
+#ifdef KCVAE_EMU
+  if (buf && capacity > 0) buf[0] = 0;
+  return 0;
+#else
+  cudaDeviceSynchronize();
+  std::vector<std::string> keys;
+  std::vector<double> ms;
+  std::vector<int> cnt;
+  for (auto& r : g_prof_recs) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    size_t i = 0;
+    for (; i < keys.size(); ++i) if (keys[i] == r.key) break;
+    if (i == keys.size()) { keys.push_back(r.key); ms.push_back(0); cnt.push_back(0); }
+    ms[i] += t; cnt[i] += 1;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  g_prof_recs.clear();
+  std::string out;
+  char line[256];
+  for (size_t i = 0; i < keys.size(); ++i) {
+    snprintf(line, sizeof line, "%s %d %.6f\n", keys[i].c_str(), cnt[i], ms[i]);
+    out += line;
+  }
+  if (buf && capacity > 0) {
+    const size_t n = out.size() < (size_t)capacity - 1 ? out.size() : (size_t)capacity - 1;
+    memcpy(buf, out.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)out.size();
+#endif
 }
 
 #ifdef KCVAE_EMU

@@ -618,6 +618,42 @@ class AbstractCVAE:
         return {"err": _wrap(err) if err is not None else None, "score": _wrap(sc), "err_minmax": _wrap(mm),
                 "rec": _wrap(xh) if xh is not None else None}
 
+    # -- host-buffer entry points: H2D / D2H inside the call (bench.py e2e) ---------------------
+    def train_step_host(self, x_host: torch.Tensor, eps_host: Optional[torch.Tensor] = None,
+                        metrics_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One train_step on HOST buffers (ideally pinned): copies x (and eps) to the GPU, runs
+        the step, copies the metrics vector back and synchronises.  Returns float32[16]."""
+        if self.optimizer is None:
+            raise RuntimeError("You must compile your model before training/testing. Use `model.compile(optimizer=...)`.")
+        assert x_host.device.type == "cpu" and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        out = metrics_host if metrics_host is not None else torch.empty(_lib.NUM_METRICS, dtype=torch.float32)
+        self._push_hparams()
+        self._lib.check(self._lib.train_step_host(self._h, _ptr(x_host), x_host.shape[0], _ptr(eps_host), _ptr(out), None,
+                                                  self.metric_tier, self._stream()), self._h)
+        return out
+
+    def score_host(self, x_host: torch.Tensor, score_host: Optional[torch.Tensor] = None,
+                   err_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert x_host.device.type == "cpu" and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        out = score_host if score_host is not None else torch.empty(x_host.shape[0], dtype=torch.float32)
+        self._lib.check(self._lib.score_host(self._h, _ptr(x_host), x_host.shape[0], _ptr(err_host), _ptr(out),
+                                             self._stream()), self._h)
+        return out
+
+    def profile(self, on: bool):
+        self._lib.profile_enable(int(bool(on)))
+
+    def profile_report(self) -> Dict[str, tuple]:
+        """{'<layer tag>/<kernel>': (launcher calls, total ms)} since profiling was enabled."""
+        n = int(self._lib.profile_report(None, 0))
+        buf = C.create_string_buffer(n + 1)
+        self._lib.profile_report(buf, n + 1)
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, c, ms = line.rsplit(" ", 2)
+            out[k] = (int(c), float(ms))
+        return out
+
     def launch_count(self) -> int:
         return int(self._lib.launch_count(self._h))
 
