@@ -87,7 +87,8 @@ int main() {
       {"kmajor M128 N16 K32 shift37", 128, 16, 32, 0, 0, 37, 0, false},
       {"kmajor M128 N32 K64", 128, 32, 64, 0, 0, 0, 0, false},
       {"kmajor M128 N48 K16", 128, 48, 16, 0, 0, 1, 0, false},
-      {"kmajor paired taps gap 34", 128, 16, 32, 0, 0, 2, 34, false},
+      {"kmajor paired chunks, LBO = 131 rows", 128, 16, 32, 0, 0, 2, 131, false},
+      {"kmajor paired chunks, LBO = 34 rows (conv-like shared image)", 128, 16, 32, 0, 0, 2, -34, false},
       {"mnmajor A,B M128 N32 K64", 128, 32, 64, 1, 1, 0, 0, false},
       {"mnmajor A,B M128 N16 K32", 128, 16, 32, 1, 1, 0, 0, false},
       {"kmajor M64 N8 K16 (layout dump)", 64, 8, 16, 0, 0, 0, 0, true},
@@ -95,11 +96,19 @@ int main() {
   };
   int fails = 0;
   for (const Case& c : cases) {
-    const int R = 256;  // rows available in the A image (room for shifts)
+    const int R = 320;  // rows available in the A image (room for shifts)
     std::vector<float> A((size_t)c.M * c.K), B((size_t)c.N * c.K);
     srand(7);
     for (auto& v : A) v = bf2f(f2bf((rand() % 2001 - 1000) / 1000.0f));
     for (auto& v : B) v = bf2f(f2bf((rand() % 2001 - 1000) / 1000.0f));
+    int gap = c.pair_gap;
+    if (gap < 0) {  // conv-like: both K chunks of an MMA read ONE image at rows m and m+gap
+      gap = -gap;
+      std::vector<float> img((size_t)(c.K / 16) * 512 * 8);
+      for (auto& v : img) v = bf2f(f2bf((rand() % 2001 - 1000) / 1000.0f));
+      for (int m = 0; m < c.M; ++m) for (int k = 0; k < c.K; ++k)
+        A[(size_t)m * c.K + k] = img[((size_t)(k / 16) * 512 + m + ((k / 8) & 1 ? gap : 0)) * 8 + (k % 8)];
+    }
     if (c.dump_layout) {
       for (int m = 0; m < c.M; ++m) for (int k = 0; k < c.K; ++k) A[(size_t)m * c.K + k] = k == 0 ? (float)(m + 1) : 0.f;
       for (int n = 0; n < c.N; ++n) for (int k = 0; k < c.K; ++k) B[(size_t)n * c.K + k] = k == 0 ? 1.f + n / 64.f : 0.f;
@@ -110,20 +119,20 @@ int main() {
     if (!c.a_mn) {
       // [chunk][row] x 16 B ; logical (m, k) -> chunk k/8, row m + shift (+ gap for odd chunks when pairing)
       const int chunk_stride_rows = R;
-      ai.assign((size_t)kchunks * chunk_stride_rows * 8 + (size_t)(c.pair_gap + 8) * 8, 0);
+      ai.assign((size_t)kchunks * chunk_stride_rows * 8 + (size_t)(gap + 8) * 8, 0);
       for (int m = 0; m < c.M; ++m) for (int k = 0; k < c.K; ++k) {
         size_t unit;
-        if (c.pair_gap) {  // chunks (2s, 2s+1) live in chunk slot s: even chunk at row, odd chunk at row + gap
-          unit = (size_t)(k / 16) * chunk_stride_rows + m + c.row_shift + ((k / 8) & 1 ? c.pair_gap : 0);
+        if (gap) {  // chunks (2s, 2s+1) live in chunk slot s: even chunk at row, odd chunk at row + gap
+          unit = (size_t)(k / 16) * chunk_stride_rows + m + c.row_shift + ((k / 8) & 1 ? gap : 0);
         } else {
           unit = (size_t)(k / 8) * chunk_stride_rows + m + c.row_shift;
         }
         ai[unit * 8 + (k % 8)] = f2bf(A[(size_t)m * c.K + k]);
       }
       p.a_start = c.row_shift * 16;
-      p.a_lbo = c.pair_gap ? c.pair_gap * 16 : chunk_stride_rows * 16;
+      p.a_lbo = gap ? gap * 16 : chunk_stride_rows * 16;
       p.a_sbo = 128;
-      p.a_kstep = c.pair_gap ? chunk_stride_rows * 16 : 2 * chunk_stride_rows * 16;
+      p.a_kstep = gap ? chunk_stride_rows * 16 : 2 * chunk_stride_rows * 16;
     } else {
       // MN-major from the same [chunk][pixel] tile: M = channels (chunk g = m/8), K = pixels
       // element (m, k) at g*CH + k*16 + (m%8)*2 ; LBO = 8 pixels * 16 B, SBO = chunk stride

@@ -991,9 +991,11 @@ int64_t kcvae_profile_report(char* buf, int64_t capacity) {
     for (; i < keys.size(); ++i) if (keys[i] == r.key) break;
     if (i == keys.size()) { keys.push_back(r.key); ms.push_back(0); cnt.push_back(0); }
     ms[i] += t; cnt[i] += 1;
-    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
   }
-  g_prof_recs.clear();
+  if (buf && capacity > 0) {  // a size query (buf == NULL) keeps the records
+    for (auto& r : g_prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof_recs.clear();
+  }
   std::string out;
   char line[256];
   for (size_t i = 0; i < keys.size(); ++i) {
