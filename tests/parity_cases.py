@@ -87,22 +87,31 @@ def case_train_steps(backend, kind="global", cfg=None, B=4, steps=3):
     m, ws = make(cfg, backend, weight_gain=1.6)
     m.compile(optimizer=__import__("kcvae_testlib").pkg.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
     om = O.OracleModel(cfg, ws)
+    names = [n for n, _ in O.variable_shapes(cfg)]
     for s in range(steps):
         x, eps = frames(cfg, B, seed=100 + s), eps_for(cfg, B, s)
         d = m.train_step(x, eps=eps)
         od, _ = om.train_step(x, eps)
         assert_metrics_close(d, od, rtol=5e-4, atol=2e-6)
+        if s == 0:
+            # Adam state after the first update (identical weights on both sides): tight.
+            # Later steps start from weights that differ by O(eps_fp32 * lr) and ReLU masks of
+            # near-zero activations flip - even the fp32 and fp64 oracles disagree by ~2e-2 on
+            # the decoder Dense moments there - so afterwards only weights/metrics are compared.
+            mm, vv, t = m.get_optimizer_state()
+            assert t == 1
+            for n, a, oa in zip(names, mm, om.optimizer.m):
+                assert rel_err(a, oa.numpy()) < 1e-3, (n, rel_err(a, oa.numpy()))
+            for n, a, oa in zip(names, vv, om.optimizer.v):
+                assert rel_err(a, oa.numpy()) < 2e-3, (n, rel_err(a, oa.numpy()))
     lr = float(cfg["training"]["learning_rate"])
-    for n, w, ow in zip([n for n, _ in O.variable_shapes(cfg)], m.get_weights(), om.weights):
+    for n, w, ow in zip(names, m.get_weights(), om.weights):
         # Adam normalises every update to ~lr: compare in units of lr (sign flips of
         # near-zero gradients can move a weight by a fraction of lr)
         diff = np.abs(w - ow.numpy())
         assert np.mean(diff) < 0.02 * lr, f"{n}: mean |dw| {np.mean(diff)}"
         assert np.quantile(diff, 0.99) < 0.5 * lr * steps, f"{n}: q99 |dw| {np.quantile(diff, 0.99)}"
-    mm, vv, t = m.get_optimizer_state()
-    assert t == steps
-    for a, oa in zip(mm, om.optimizer.m):
-        assert rel_err(a, oa.numpy()) < 1e-2, rel_err(a, oa.numpy())   # weights diverge by O(lr) after step 1
+    assert m.get_optimizer_state()[2] == steps
     d, xh = m.train_step_and_run(frames(cfg, B, seed=7), eps=eps_for(cfg, B, 9))
     assert tuple(xh.shape) == (B, *cfg["data"]["image_size"])
 

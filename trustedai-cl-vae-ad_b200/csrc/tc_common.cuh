@@ -118,7 +118,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* mbar, uint32_t parit
 }
 // bounded wait: returns false if the phase never completes (a wrong descriptor must not hang
 // the GPU box); callers raise a device-side error flag
-__device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity, uint32_t max_spins = 4000000u) {
+__device__ __forceinline__ bool mbar_wait(uint64_t* mbar, uint32_t parity, uint32_t max_spins = (1u << 19)) {
   for (uint32_t i = 0; i < max_spins; ++i)
     if (mbar_try_wait(mbar, parity)) return true;
   return false;

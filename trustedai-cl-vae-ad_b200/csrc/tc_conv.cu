@@ -1,0 +1,289 @@
+// tc_conv.cu - tensor-core (tcgen05 + TMEM + TMA) 3x3 stride-1 implicit-GEMM convolution
+// for the decoder output layer (src/abstract_cvae.py:87-89 Conv2DTranspose k3 s1 'same',
+// SURVEY A4) - 51 % of the forward MACs of the README config.
+//
+//   x_hat[n,y,x,co] = sigmoid(b[co] + sum_{kh,kw,ci} a[n, y+1-kh, x+1-kw, ci] * W[kh,kw,co,ci])
+//
+// Implicit GEMM without im2col.  A persistent CTA per SM walks 32x30-pixel output tiles:
+//   * Cin/8 TMA boxes (cp.async.bulk.tensor.4d) bring the 34x32-pixel bf16 halo tile into
+//     shared memory as [8-channel chunk][pixel] x 16 B - TMA's zero fill supplies the SAME padding;
+//   * that layout is the no-swizzle K-major UMMA operand with linear rows, so each of the
+//     9 taps is the SAME tile read through a descriptor whose start address is shifted by
+//     (dy*32 + dx) pixels: 8 M-tiles x 9 taps x (Cin/16) tcgen05.mma (M=128, N=16, K=16)
+//     accumulate into 8 TMEM accumulators (128 columns), double buffered (256 columns);
+//   * 4 epilogue warps read TMEM (tcgen05.ld 32x32b), add bias, apply the sigmoid and
+//     store x_hat; TMA / MMA / epilogue overlap through mbarrier pipelines.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
+// warps 2..5 = epilogue (TMEM lane groups (warp & 3)).
+#include <cuda.h>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+#include "tc_conv.h"
+
+namespace kc {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TW = 30, TR = 32;            // output tile (cols, rows)
+constexpr int PW = TW + 2, PR = TR + 2;    // halo tile
+constexpr int NPIX = PR * PW;              // 1088 halo pixels
+constexpr int MT = (TR * PW) / 128;        // 8 M-tiles of 128 padded-row positions
+constexpr int NPAD = 16;                   // UMMA N (Cout padded)
+constexpr int kStages = 2;
+constexpr int kThreads = 192;
+static_assert(TR * PW == MT * 128, "tile must be a whole number of M=128 tiles");
+
+// 4-D tiled TMA load: box (8 channels, PW cols, PR rows, 1 image) -> one [pixel] x 16 B chunk plane
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* mbar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(mbar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+struct OutConvParams {
+  const __nv_bfloat16* wimg;  // [9 taps][CIN/16][2 chunks][NPAD][8] bf16 (tc_prep_out_weights)
+  const float* bias;          // [Cout]
+  float* xhat;                // [B,H,W,Cout] fp32
+  int B, H, W, Cout;
+  int tiles_y, tiles_x, num_tiles;
+  int apply_sigmoid;
+  int* error_flag;            // set to 1 if a bounded barrier wait expires
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
+  constexpr int KC = CIN / 8;                        // 16-byte channel chunks
+  constexpr int KS = CIN / 16;                       // K=16 steps per tap
+  constexpr uint32_t CH = NPIX * 16;                 // bytes per chunk plane
+  constexpr uint32_t TILE_BYTES = KC * CH;           // one halo tile
+  constexpr uint32_t WB = 9 * KS * 2 * NPAD * 16;    // weight image bytes
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* s_tile = smem;                                      // kStages x (TILE_BYTES + 128)
+  unsigned char* s_w = smem + kStages * (TILE_BYTES + 128);          // weights
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[NPAD];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup -------------------------------------------------------------------
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreads)
+    reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
+  if (threadIdx.x < NPAD) s_bias[threadIdx.x] = (int)threadIdx.x < p.Cout ? p.bias[threadIdx.x] : 0.f;
+  // the 2 units past each stage's tile are only ever read into discarded columns: zero them
+  if (threadIdx.x < kStages * 8) {
+    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
+    reinterpret_cast<uint4*>(s_tile + s * (TILE_BYTES + 128) + TILE_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ========================================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / (p.tiles_y * p.tiles_x);
+        const int rem = t % (p.tiles_y * p.tiles_x);
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        mbar_expect_tx(&full_bar[s], TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < KC; ++c)   // one box per 8-channel chunk: smem = [chunk][row][col] x 16 B
+          tma_load_4d(s_tile + s * (TILE_BYTES + 128) + c * CH, &tmap, &full_bar[s], c * 8, tx * TW - 1, ty * TR - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==========================================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(128, NPAD);
+      const uint32_t w_base = smem_u32(s_w);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages, a = it & 1;
+        const uint32_t ph = (it / kStages) & 1, aph = (it >> 1) & 1;
+        if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { *p.error_flag = 1; break; }   // epilogue drained TMEM stage
+        if (!mbar_wait(&full_bar[s], ph)) { *p.error_flag = 1; break; }          // TMA landed
+        fence_after_sync();
+        const uint32_t tile_base = smem_u32(s_tile + s * (TILE_BYTES + 128));
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d_tmem = tmem + (uint32_t)(a * MT * NPAD + mt * NPAD);
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const int kh = tap / 3, kw = tap % 3;
+            const uint32_t shift = (uint32_t)((2 - kh) * PW + (2 - kw));   // flipped taps (A4)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint64_t da = make_desc_kmajor_noswz(tile_base + (uint32_t)(2 * ks) * CH + (uint32_t)(mt * 128 + shift) * 16, CH, 128);
+              const uint64_t db = make_desc_kmajor_noswz(w_base + (uint32_t)((tap * KS + ks) * 2 * NPAD * 16), NPAD * 16, 128);
+              mma_bf16_ss(d_tmem, da, db, idesc, (tap | ks) != 0);
+            }
+          }
+        }
+        mma_commit(&empty_bar[s]);    // smem stage reusable once these MMAs have read it
+        mma_commit(&tfull_bar[a]);    // accumulators ready for the epilogue
+      }
+    }
+  } else {
+    // ================================ epilogue warps ======================================
+    const int lg = warp & 3;                      // TMEM lane group this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int n = t / (p.tiles_y * p.tiles_x);
+      const int rem = t % (p.tiles_y * p.tiles_x);
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; break; }
+      fence_after_sync();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        float v[8];
+        tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MT * NPAD + mt * NPAD), v);
+        const int q = mt * 128 + lg * 32 + lane;  // padded-row position
+        const int r = q / PW, c = q % PW;
+        const int oy = ty * TR + r, ox = tx * TW + c;
+        if (c < TW && oy < p.H && ox < p.W) {
+          float* o = p.xhat + (((int64_t)n * p.H + oy) * p.W + ox) * p.Cout;
+#pragma unroll
+          for (int co = 0; co < 8; ++co) {
+            if (co < p.Cout) {
+              float y = v[co] + s_bias[co];
+              if (p.apply_sigmoid) y = 1.0f / (1.0f + __expf(-y));
+              o[co] = y;
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// W [3,3,Cout,Cin] fp32 -> bf16 UMMA B-operand image [tap][ks][chunk(2)][n(NPAD)][8]
+__global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+  const int KS = Cin / 16;
+  const int total = 9 * KS * 2 * NPAD * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % 8;
+    const int n = (i / 8) % NPAD;
+    const int kc = (i / (8 * NPAD)) % 2;
+    const int ks = (i / (16 * NPAD)) % KS;
+    const int tap = i / (16 * NPAD * KS);
+    const int ci = ks * 16 + kc * 8 + j;
+    const float v = n < Cout ? w[((int64_t)tap * Cout + n) * Cin + ci] : 0.f;
+    img[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(out)[i] = o;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+}  // namespace
+
+bool tc_out_conv_supported(int Cin, int Cout) { return (Cin == 16 || Cin == 32) && Cout >= 1 && Cout <= 8; }
+
+size_t tc_out_weight_image_elems(int Cin) { return (size_t)9 * (Cin / 16) * 2 * NPAD * 8; }
+
+void cast_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t st) {
+  ProfScope prof_("cast_bf16", st);
+  ++g_launches;
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256, 8, 2), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+}
+
+void tc_prep_out_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
+  ProfScope prof_("tc_prep_weights", st);
+  ++g_launches;
+  tc_prep_out_weights_kernel<<<8, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+}
+
+// returns 0 on success, nonzero if the tensor map could not be built
+int tc_out_conv(const void* act_bf16, const void* wimg, const float* bias, float* xhat, int B, int H, int W, int Cin,
+                int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  const cuuint32_t box[4] = {8, PW, PR, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(act_bf16), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 2;
+  OutConvParams p{};
+  p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
+  p.bias = bias; p.xhat = xhat; p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.apply_sigmoid = apply_sigmoid;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  ProfScope prof_("tc_out_conv", st);
+  ++g_launches;
+  auto launch = [&](auto kernel, int cin) {
+    const size_t smem = (size_t)kStages * ((size_t)(cin / 8) * NPIX * 16 + 128) + (size_t)9 * (cin / 16) * 2 * NPAD * 16;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  };
+  if (Cin == 16) launch(tc_out_conv_kernel<16>, 16);
+  else launch(tc_out_conv_kernel<32>, 32);
+  return 0;
+}
+
+}  // namespace kc

@@ -1,0 +1,16 @@
+// tc_conv.h - launchers of the tcgen05 / TMA kernels (CUDA build only; not emulated).
+#pragma once
+#include "common.cuh"
+
+namespace kc {
+
+bool tc_out_conv_supported(int Cin, int Cout);
+size_t tc_out_weight_image_elems(int Cin);   // bf16 elements
+void cast_f32_to_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t st);
+// W [3,3,Cout,Cin] fp32 (Keras Conv2DTranspose layout) -> UMMA B-operand image (bf16)
+void tc_prep_out_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
+// x_hat = [sigmoid](bias + conv3x3_s1_flipped(act)) ; act bf16 NHWC [B,H,W,Cin]; returns 0 on success
+int tc_out_conv(const void* act_bf16, const void* wimg_bf16, const float* bias, float* xhat, int B, int H, int W,
+                int Cin, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st);
+
+}  // namespace kc
