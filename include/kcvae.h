@@ -171,6 +171,9 @@ int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, 
 /* ---- introspection --------------------------------------------------------------------- */
 /* number of kernels this library launched on behalf of handle h since creation */
 int64_t kcvae_launch_count(kcvae_handle h);
+/* 1 = tcgen05 tensor-core kernels active for this handle, 0 = fp32 CUDA-core path only;
+ * negative = a tensor-core pipeline reported an error.  Synchronises the device. */
+int kcvae_tc_status(kcvae_handle h);
 /* per-launch device timing with CUDA events on the launching stream (bench.py roofline):
  * enable, run steps, then report "<layer tag>/<kernel> <calls> <total ms>" lines */
 int kcvae_profile_enable(int on);

@@ -198,3 +198,37 @@ def test_error_behaviour():
         m.call(np.zeros((2, 8, 8, 3), np.float32))
     with pytest.raises(RuntimeError):
         m.train_step(frames(small_config(), 2))          # not compiled
+
+
+# ------------------------------------------------------------- tcgen05 tensor-core path (bf16)
+@pytest.mark.parametrize("shape", [
+    dict(layers=(32,), enc=8, H=40, W=52, dec=8, latent=8),      # partial tiles in both directions
+    dict(layers=(16, 6), enc=8, H=64, W=120, dec=8, latent=8),   # Cin = 16, exact tile columns
+    dict(layers=(32, 5), enc=16, H=224, W=300, dec=32, latent=32),  # README config
+])
+def test_tc_output_conv_parity(shape):
+    """precision='bf16': the decoder output layer runs on tcgen05 (tc_conv.cu).  Bars from
+    BASELINE.json north_star: x_hat max-abs <= 1e-2, loss terms <= 1e-3 relative."""
+    cfg = small_config(**shape)
+    B = 3
+    m, ws = make(cfg, BACKEND, weight_gain=1.3, precision="bf16")
+    assert m.tc_status() == 1
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    xh, z, mean, logvar = m.call_detailed(x, training=True, eps=eps)
+    assert m.tc_status() == 1                                   # no pipeline error
+    oxh, oz, _, _ = O.call_detailed(cfg, ws, x, eps)
+    err = float(np.max(np.abs(xh.numpy() - oxh.numpy())))
+    assert err < 1e-2, err
+    assert err < 4e-3, err                                      # what bf16 operands should give
+    np.testing.assert_allclose(z.numpy(), oz.numpy(), atol=3e-5)   # encoder stays fp32
+    d = m.compute_loss(x, training=True, eps=eps)
+    od = O.compute_loss(cfg, ws, x, eps)[0]
+    assert_metrics_close(d, od, rtol=1e-3, atol=1e-6)
+    # logits path (apply_sigmoid=False) and a batch that is not a multiple of anything
+    lg = m.decode(oz.numpy()[:2], apply_sigmoid=False).numpy()
+    olg = torch.logit(O.call_detailed(cfg, ws, x[:2], eps[:2])[0].double()).numpy()
+    assert float(np.max(np.abs(lg - olg))) < 3e-2
+    # the fp32 model on the same weights agrees with the bf16 one within the bf16 bound
+    m32, _ = make(cfg, BACKEND, weight_gain=1.3)
+    assert m32.tc_status() == 0
+    assert float(np.max(np.abs(m32.call(x, True, eps=eps).numpy() - xh.numpy()))) < 4e-3

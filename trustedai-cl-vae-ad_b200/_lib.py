@@ -73,6 +73,7 @@ _SIGS = {
     "kcvae_score_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "kcvae_launch_count": (C.c_int64, [_P]),
     "kcvae_debug_activation": (C.c_int64, [_P, C.c_int, _P, C.c_int64]),
+    "kcvae_tc_status": (C.c_int, [_P]),
     "kcvae_profile_enable": (C.c_int, [C.c_int]),
     "kcvae_profile_report": (C.c_int64, [C.c_char_p, C.c_int64]),
 }

@@ -14,6 +14,7 @@
 #ifndef KCVAE_EMU
 #include <dlfcn.h>
 #include <nccl.h>
+#include "tc_conv.h"
 #endif
 
 using namespace kc;
@@ -107,6 +108,12 @@ struct kcvae_model {
   size_t partial_floats = 0;
   double *dpartial = nullptr, *sums = nullptr, *std_acc = nullptr, *pos_sums = nullptr;
   float *minmax = nullptr, *metrics_dev = nullptr;
+  // tensor-core path (precision == BF16_TC): bf16 copy of the last decoder activation, UMMA
+  // weight image of the output layer, device-side error flag of the bounded barrier waits
+  bool use_tc_out = false;
+  void* a_last_bf16 = nullptr;
+  void* wimg_out = nullptr;
+  int* tc_error = nullptr;
   // data parallel
   int rank = 0, world = 1;
 #ifndef KCVAE_EMU
@@ -250,6 +257,13 @@ int ensure_fwd(kcvae_model* h, int B) {
   KC_TRY(dalloc(h, &h->xhat, (size_t)B * h->dh[L] * h->dw[L] * h->C));
   KC_TRY(dalloc(h, &h->err_buf, (size_t)B * h->H * h->W));
   KC_TRY(dalloc(h, &h->score_buf, (size_t)B));
+#ifndef KCVAE_EMU
+  if (h->use_tc_out) {
+    unsigned short* tmp = reinterpret_cast<unsigned short*>(h->a_last_bf16);
+    KC_TRY(dalloc(h, &tmp, (size_t)B * h->dh[L] * h->dw[L] * h->dc[L]));
+    h->a_last_bf16 = tmp;
+  }
+#endif
   h->partial_floats = max_partial_floats(h, B);
   KC_TRY(dalloc(h, &h->partial, h->partial_floats));
   h->cap_fwd = B;
@@ -351,6 +365,17 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   a.Ho = a.Hi; a.Wo = a.Wi; a.Co = h->C;
   a.w_sci = 1; a.w_sco = a.Ci; a.flip = 1;
   g_tag = "dec.out.fwd";
+#ifndef KCVAE_EMU
+  if (h->use_tc_out) {
+    // tcgen05 implicit GEMM (tc_conv.cu): bf16 operands, fp32 accumulate in TMEM
+    cast_f32_to_bf16(h->act_d[L], h->a_last_bf16, (int64_t)B * a.Hi * a.Wi * a.Ci, st);
+    tc_prep_out_weights(a.w, a.Co, a.Ci, h->wimg_out, st);
+    if (tc_out_conv(h->a_last_bf16, h->wimg_out, a.bias, out, B, a.Hi, a.Wi, a.Ci, a.Co, apply_sigmoid, h->tc_error, st) == 0)
+      return;
+    h->use_tc_out = false;  // tensor map could not be encoded: report through kcvae_tc_status
+    h->err = "tc_out_conv: cuTensorMapEncodeTiled failed; fp32 kernel used";
+  }
+#endif
   conv_forward(CONV_S1, apply_sigmoid ? EPI_BIAS_SIGMOID : EPI_BIAS, a, st);
 }
 
@@ -611,6 +636,15 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
   cudaMemset(h->m, 0, h->nparams * sizeof(float));
   cudaMemset(h->v, 0, h->nparams * sizeof(float));
   cudaMemset(h->sums, 0, kSumsLen * sizeof(double));
+#ifndef KCVAE_EMU
+  if (cfg->precision == KCVAE_PREC_BF16_TC && tc_out_conv_supported(h->dc[h->L], h->C)) {
+    h->use_tc_out = true;
+    unsigned short* wi = nullptr;
+    if ((rc = dalloc(h, &wi, tc_out_weight_image_elems(h->dc[h->L]))) || (rc = dalloc(h, &h->tc_error, 1))) return bail(rc);
+    h->wimg_out = wi;
+    cudaMemset(h->tc_error, 0, sizeof(int));
+  }
+#endif
   if (cfg->max_batch > 0 && (rc = ensure_fwd(h, cfg->max_batch))) return bail(rc);
   *out = h;
   return KCVAE_OK;
@@ -631,6 +665,9 @@ int kcvae_destroy(kcvae_handle h) {
                  h->x_noisy, h->dlogit, h->g_z, h->dhead, h->g_d1, h->partial, h->err_buf, h->score_buf, h->minmax,
                  h->metrics_dev};
   for (float* p : fl) if (p) cudaFree(p);
+  if (h->a_last_bf16) cudaFree(h->a_last_bf16);
+  if (h->wimg_out) cudaFree(h->wimg_out);
+  if (h->tc_error) cudaFree(h->tc_error);
   double* dl[] = {h->dpartial, h->sums, h->std_acc, h->pos_sums};
   for (double* p : dl) if (p) cudaFree(p);
   delete h;
@@ -966,6 +1003,19 @@ int64_t kcvae_debug_activation(kcvae_handle h, int which, float* h_out, int64_t 
   cudaDeviceSynchronize();
   if (cudaMemcpy(h_out, src, n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return fail(h, KCVAE_ERR_CUDA, "debug_activation: copy failed");
   return n;
+}
+
+// 1 = tensor-core kernels active, 0 = fp32 path; negative = a tcgen05 pipeline wait expired
+// (synchronises the device)
+int kcvae_tc_status(kcvae_handle h) {
+  if (!h) return KCVAE_ERR_INVALID;
+  if (!h->tc_error) return 0;
+  int flag = 0;
+  cudaSetDevice(h->device);
+  if (cudaDeviceSynchronize() != cudaSuccess) return fail(h, KCVAE_ERR_CUDA, "tc_status: device error");
+  cudaMemcpy(&flag, h->tc_error, sizeof(int), cudaMemcpyDeviceToHost);
+  if (flag) return fail(h, KCVAE_ERR_CUDA, "tcgen05 pipeline: bounded mbarrier wait expired");
+  return h->use_tc_out ? 1 : 0;
 }
 
 // ---- per-launch timing ---------------------------------------------------------------------

@@ -640,6 +640,10 @@ class AbstractCVAE:
                                              self._stream()), self._h)
         return out
 
+    def tc_status(self) -> int:
+        """1 if the tcgen05 kernels are active, 0 if only the fp32 path runs; raises on a pipeline error."""
+        return self._lib.check(self._lib.tc_status(self._h), self._h)
+
     def profile(self, on: bool):
         self._lib.profile_enable(int(bool(on)))
 
