@@ -134,7 +134,9 @@ static int wgrad_chunks(int B, int Hp, int Ca, int Cb) {
   return (int)want;
 }
 size_t wgrad_partial_floats(int B, int Hp, int Ca, int Cb) {
-  return (size_t)wgrad_chunks(B, Hp, Ca, Cb) * 9 * Ca * Cb;
+  size_t n = (size_t)wgrad_chunks(B, Hp, Ca, Cb);
+  if (n < (size_t)kNumSMs * 2) n = (size_t)kNumSMs * 2;   // the tiled kernel uses <= 2 blocks per SM
+  return n * 9 * Ca * Cb;
 }
 
 __global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a, int E, int rows, int rows_per_chunk) {
@@ -176,9 +178,149 @@ __global__ void wgrad_reduce_kernel(const float* partial, int chunks, int E, int
   out[(int64_t)tap * Ca * Cb + (int64_t)ca * o_sa + (int64_t)cb * o_sb] = s;
 }
 
+
+// ------------------------------------------------------------ weight grads, tiled version
+// Block = row chunk.  For every P row and SEG-pixel segment the P pixels and the three Q rows
+// they touch are staged in shared memory (coalesced); a thread owns an RA x RB block of dW
+// entries of one tap and one pixel phase, so each shared-memory value feeds RA (or RB) FMAs.
+// Phases are folded through shared memory at the end; blocks write partials that
+// wgrad_reduce_kernel sums (deterministic).
+template <int RA, int RB>
+__global__ void __launch_bounds__(256) wgrad_tiled_kernel(WgradArgs a, int rows, int rows_per_chunk, int SEG,
+                                                          int n_at, int n_bt, int nph, int cbp) {
+  KC_DYN_SMEM(float, sm);
+  const int E = 9 * a.Ca * a.Cb;
+  const int n_et = 9 * n_at * n_bt;                 // entry tiles
+  const int qw = a.s * (SEG - 1) + 3;               // Q pixels per staged row
+  float* Ps = sm;                                   // [SEG][Ca]
+  float* Qs = sm + SEG * a.Ca;                      // [3][qw][cbp]
+  const int tid = threadIdx.x;
+  const bool active = tid < n_et * nph;
+  const int et = active ? tid % n_et : 0, ph = active ? tid / n_et : 0;
+  const int bt = et % n_bt, at = (et / n_bt) % n_at, tap = et / (n_bt * n_at);
+  const int kh = tap / 3, kw = tap % 3;
+  const int a0 = at * RA, b0 = bt * RB;
+  const int dmin = a.d < 0 ? 2 * a.d : 0;           // smallest d*kw
+  float acc[RA][RB];
+#pragma unroll
+  for (int i = 0; i < RA; ++i)
+#pragma unroll
+    for (int j = 0; j < RB; ++j) acc[i][j] = 0.f;
+
+  const int r0 = blockIdx.x * rows_per_chunk;
+  const int r1 = min(rows, r0 + rows_per_chunk);
+  for (int r = r0; r < r1; ++r) {
+    const int n = r / a.Hp, i = r % a.Hp;
+    for (int j0 = 0; j0 < a.Wp; j0 += SEG) {
+      const int seg = min(SEG, a.Wp - j0);
+      const int qx_min = a.s * j0 + dmin + a.ox;
+      __syncthreads();
+      {  // stage P segment (contiguous)
+        const float* src = a.P + (((int64_t)r * a.Wp) + j0) * a.Ca;
+        for (int t = tid; t < seg * a.Ca; t += blockDim.x) Ps[t] = __ldg(src + t);
+        for (int t = seg * a.Ca + tid; t < SEG * a.Ca; t += blockDim.x) Ps[t] = 0.f;
+      }
+      for (int k = 0; k < 3; ++k) {  // stage the 3 Q rows (zero outside the image)
+        const int qy = a.s * i + a.d * k + a.oy;
+        const bool vrow = qy >= 0 && qy < a.Hq;
+        const float* src = a.Q + (((int64_t)n * a.Hq + (vrow ? qy : 0)) * a.Wq) * a.Cb;
+        float* dst = Qs + (int64_t)k * qw * cbp;
+        for (int t = tid; t < qw * a.Cb; t += blockDim.x) {
+          const int px = t / a.Cb, c = t % a.Cb;
+          const int qx = qx_min + px;
+          dst[px * cbp + c] = (vrow && qx >= 0 && qx < a.Wq) ? __ldg(src + (int64_t)qx * a.Cb + c) : 0.f;
+        }
+      }
+      __syncthreads();
+      if (active) {
+        const float* qrow = Qs + (int64_t)kh * qw * cbp + (a.d * kw - dmin) * cbp + b0;
+        for (int j = ph; j < seg; j += nph) {
+          float pv[RA], qv[RB];
+#pragma unroll
+          for (int x = 0; x < RA; ++x) pv[x] = (a0 + x < a.Ca) ? Ps[j * a.Ca + a0 + x] : 0.f;
+          const float* qp = qrow + (int64_t)(a.s * j) * cbp;
+#pragma unroll
+          for (int y = 0; y < RB; ++y) qv[y] = (b0 + y < a.Cb) ? qp[y] : 0.f;
+#pragma unroll
+          for (int x = 0; x < RA; ++x)
+#pragma unroll
+            for (int y = 0; y < RB; ++y) acc[x][y] = fmaf(pv[x], qv[y], acc[x][y]);
+        }
+      }
+    }
+  }
+  // fold the pixel phases: sm reused as [nph][E]
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int x = 0; x < RA; ++x)
+#pragma unroll
+      for (int y = 0; y < RB; ++y)
+        if (a0 + x < a.Ca && b0 + y < a.Cb) sm[(int64_t)ph * E + (tap * a.Ca + a0 + x) * a.Cb + b0 + y] = acc[x][y];
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < nph; ++p) s += sm[(int64_t)p * E + e];
+    a.partial[(int64_t)blockIdx.x * E + e] = s;
+  }
+}
+
+struct WgradPlan { int ra, rb, n_at, n_bt, nph, seg, cbp, blocks, rpc; size_t smem; bool ok; };
+static WgradPlan wgrad_plan(int B, int Hp, int Wp, int Ca, int Cb, int s) {
+  WgradPlan p{};
+  if (Ca == 3) { p.ra = 3; p.rb = 8; }
+  else if (Ca == 5) { p.ra = 5; p.rb = 4; }
+  else if (Cb == 3) { p.ra = 8; p.rb = 3; }
+  else if (Cb == 5) { p.ra = 4; p.rb = 5; }
+  else { p.ra = 4; p.rb = 4; }
+  p.n_at = cdiv(Ca, p.ra); p.n_bt = cdiv(Cb, p.rb);
+  const int n_et = 9 * p.n_at * p.n_bt;
+  p.nph = 256 / n_et;
+  p.seg = s == 1 ? 64 : 32;
+  if (p.seg > Wp) p.seg = Wp;
+  p.cbp = Cb % 4 == 0 ? Cb + 4 : Cb + 1;            // de-phase the taps' bank mapping
+  const int qw = s * (p.seg - 1) + 3;
+  const size_t stage = (size_t)p.seg * Ca + (size_t)3 * qw * p.cbp;
+  const size_t fold = (size_t)(p.nph > 0 ? p.nph : 1) * 9 * Ca * Cb;
+  p.smem = (stage > fold ? stage : fold) * sizeof(float);
+  p.ok = p.nph >= 1 && p.smem <= 200 * 1024;
+  const int rows = B * Hp;
+  int blocks = kNumSMs * 2;
+  if (blocks > rows) blocks = rows;
+  p.rpc = cdiv(rows, blocks);
+  p.blocks = cdiv(rows, p.rpc);
+  return p;
+}
+
 void conv_wgrad(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_("wgrad", st);
   const int E = 9 * a.Ca * a.Cb;
+  const WgradPlan pl = wgrad_plan(a.B, a.Hp, a.Wp, a.Ca, a.Cb, a.s);
+  if (pl.ok) {
+    const int rows_t = a.B * a.Hp;
+    g_launches += 2;
+#ifndef KCVAE_EMU
+#define KC_WG_ATTR(k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)
+#else
+#define KC_WG_ATTR(k)
+#endif
+#define KC_WG_LAUNCH(RA_, RB_)                                                                              \
+  {                                                                                                         \
+    auto k = wgrad_tiled_kernel<RA_, RB_>;                                                                  \
+    KC_WG_ATTR(k);                                                                                          \
+    KC_LAUNCH(k, pl.blocks, 256, pl.smem, st, a, rows_t, pl.rpc, pl.seg, pl.n_at, pl.n_bt, pl.nph, pl.cbp); \
+  }
+    if (pl.ra == 3 && pl.rb == 8) KC_WG_LAUNCH(3, 8)
+    else if (pl.ra == 5 && pl.rb == 4) KC_WG_LAUNCH(5, 4)
+    else if (pl.ra == 8 && pl.rb == 3) KC_WG_LAUNCH(8, 3)
+    else if (pl.ra == 4 && pl.rb == 5) KC_WG_LAUNCH(4, 5)
+    else KC_WG_LAUNCH(4, 4)
+#undef KC_WG_LAUNCH
+#undef KC_WG_ATTR
+    KC_LAUNCH(wgrad_reduce_kernel, cdiv(E, 256), 256, 0, st, a.partial, pl.blocks, E, a.Ca, a.Cb, a.o_sa, a.o_sb, a.out);
+    return;
+  }
   const int chunks = wgrad_chunks(a.B, a.Hp, a.Ca, a.Cb);
   const int rows = a.B * a.Hp;
   const int rpc = cdiv(rows, chunks);
