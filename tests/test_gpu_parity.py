@@ -232,3 +232,34 @@ def test_tc_output_conv_parity(shape):
     m32, _ = make(cfg, BACKEND, weight_gain=1.3)
     assert m32.tc_status() == 0
     assert float(np.max(np.abs(m32.call(x, True, eps=eps).numpy() - xh.numpy()))) < 4e-3
+
+
+@pytest.mark.parametrize("shape", [
+    dict(layers=(32,), enc=8, H=40, W=52, dec=8, latent=8),
+    dict(layers=(32, 5), enc=16, H=224, W=300, dec=32, latent=32),
+])
+def test_tc_backward_parity(shape):
+    """precision='bf16' training path: tensor-core forward + data-gradient kernels.  Gradients
+    carry bf16 operand rounding (2^-9 per product, fp32 accumulation): bar 2e-2 of each
+    variable's max |g|; loss terms keep the north_star 1e-3 bar."""
+    cfg = small_config(**shape)
+    B = 3
+    m, ws = make(cfg, BACKEND, weight_gain=1.3, precision="bf16")
+    m32, _ = make(cfg, BACKEND, weight_gain=1.3)
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    d, grads = m.loss_and_grads(x, eps=eps)
+    assert m.tc_status() == 1
+    d32, grads32 = m32.loss_and_grads(x, eps=eps)
+    L = len(cfg["model"]["layers"])
+    ga, ga32 = m.debug_activation(301 + L), m32.debug_activation(301 + L)    # d loss / d a_last
+    assert rel_err(ga, ga32) < 2e-2, rel_err(ga, ga32)
+    od, ograds, _, _ = O.loss_and_grads(cfg, ws, x, eps)
+    assert_metrics_close(d, od, rtol=1e-3, atol=1e-6)
+    for (n, _), g, og in zip(O.variable_shapes(cfg), grads, ograds):
+        assert rel_err(g, og.numpy()) < 2e-2, (n, rel_err(g, og.numpy()))
+    m.compile(optimizer=pkg.Adam(1e-4))
+    l0 = float(m.compute_loss(x, training=True, eps=eps)["loss"])
+    for _ in range(5):
+        m.train_step(x, eps=eps)
+    assert float(m.compute_loss(x, training=True, eps=eps)["loss"]) < l0
+    assert m.tc_status() == 1

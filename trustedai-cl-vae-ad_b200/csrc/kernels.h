@@ -79,6 +79,8 @@ struct ImageStatsArgs {
   double* std_acc;            // [1]: sum_p (std_b x - std_b xhat)^2 (local batch) or nullptr
   double* pos_sums;           // [4*P] per-position sum x, x^2, xhat, xhat^2 (DP) or nullptr
   float* dlogit;              // [B,P] or nullptr: grad_scale*(xhat-x)*xhat*(1-xhat)
+  uint16_t* dl8;              // optional bf16 copy of dlogit as NHWC padded to 8 channels (tensor-core dgrad)
+  int C;                      // image channels (for dl8 indexing)
   float grad_scale;
   int want_ce;                // accumulate S_XHX, S_XH, S_EX
   double* partial;            // workspace >= image_stats_partial_doubles()

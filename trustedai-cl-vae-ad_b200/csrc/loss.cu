@@ -39,7 +39,15 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
         sx += xv; sxx += (double)xv * xv;
         sh += hv; shh += (double)hv * hv;
       }
-      if (a.dlogit) a.dlogit[i] = a.grad_scale * (hv - xv) * hv * (1.0f - hv);
+      if (a.dlogit) {
+        const float gl = a.grad_scale * (hv - xv) * hv * (1.0f - hv);
+        a.dlogit[i] = gl;
+        if (a.dl8) {  // bf16 round-to-nearest-even, channel-padded layout [b][pixel][8]
+          const uint32_t u = __float_as_uint(gl);
+          const uint32_t rb = u + 0x7FFFu + ((u >> 16) & 1u);
+          a.dl8[((int64_t)b * (a.P / a.C) + p / a.C) * 8 + (p % a.C)] = (uint16_t)(rb >> 16);
+        }
+      }
     }
     t_se += se; t_xhx += xhx; t_xh += xh; t_ex += ex;
     if (a.pos_sums) {

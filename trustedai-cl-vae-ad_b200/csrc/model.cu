@@ -110,7 +110,9 @@ struct kcvae_model {
   float *minmax = nullptr, *metrics_dev = nullptr;
   // tensor-core path (precision == BF16_TC): bf16 copy of the last decoder activation, UMMA
   // weight image of the output layer, device-side error flag of the bounded barrier waits
-  bool use_tc_out = false;
+  bool use_tc_out = false, use_tc_dgrad = false;
+  uint16_t* dl8 = nullptr;       // bf16 d(loss)/d(logit), NHWC padded to 8 channels
+  void* wimg_dgrad = nullptr;
   void* a_last_bf16 = nullptr;
   void* wimg_out = nullptr;
   int* tc_error = nullptr;
@@ -284,6 +286,10 @@ int ensure_bwd(kcvae_model* h, int B) {
   KC_TRY(dalloc(h, &h->g_z, (size_t)Bc * h->latent));
   KC_TRY(dalloc(h, &h->dhead, (size_t)Bc * 2 * h->latent));
   KC_TRY(dalloc(h, &h->g_d1, (size_t)Bc * (h->enc_dense ? h->enc_dense : 1)));
+  if (h->use_tc_dgrad) {
+    KC_TRY(dalloc(h, &h->dl8, (size_t)Bc * h->H * h->W * 8));
+    KC_CUDA(h, cudaMemset(h->dl8, 0, (size_t)Bc * h->H * h->W * 8 * sizeof(uint16_t)));   // channel padding stays zero
+  }
   h->cap_bwd = Bc;
   return KCVAE_OK;
 }
@@ -423,6 +429,8 @@ int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier
   ia.std_acc = full ? h->std_acc : nullptr;
   ia.pos_sums = (full && h->world > 1) ? h->pos_sums : nullptr;
   ia.dlogit = with_grad ? h->dlogit : nullptr;
+  ia.dl8 = (with_grad && h->use_tc_dgrad) ? h->dl8 : nullptr;
+  ia.C = h->C;
   ia.grad_scale = (float)(2.0 * (double)h->lw.w_mse / ((double)Bg * (double)h->P));
   ia.want_ce = full && h->cfg.model_type == KCVAE_GLOBAL;
   ia.partial = h->dpartial;
@@ -464,7 +472,14 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     a.in = h->dlogit; a.w = h->wp(vi); a.mask = h->act_d[L]; a.out = h->g_act_d[L];
     a.B = B; a.Hi = h->H; a.Wi = h->W; a.Ci = h->C; a.Ho = h->dh[L]; a.Wo = h->dw[L]; a.Co = h->dc[L];
     a.w_sci = a.Co; a.w_sco = 1; a.flip = 0;  // W[tap][co_fwd = ci'][ci_fwd = co']
-    conv_forward(CONV_S1, EPI_MASK, a, st);
+    bool done = false;
+#ifndef KCVAE_EMU
+    if (h->use_tc_dgrad && h->use_tc_out) {  // tcgen05 paired-tap implicit GEMM (tc_conv.cu)
+      tc_prep_dgrad_weights(a.w, h->C, h->dc[L], h->wimg_dgrad, st);
+      done = tc_out_dgrad(h->dl8, h->wimg_dgrad, h->a_last_bf16, h->g_act_d[L], B, h->H, h->W, h->dc[L], h->tc_error, st) == 0;
+    }
+#endif
+    if (!done) conv_forward(CONV_S1, EPI_MASK, a, st);
   }
   for (int l = L - 1; l >= 0; --l) {  // decoder Conv2DTranspose (s2) layers
     const int vi = h->vi_dec_convT(l);
@@ -643,6 +658,12 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
     if ((rc = dalloc(h, &wi, tc_out_weight_image_elems(h->dc[h->L]))) || (rc = dalloc(h, &h->tc_error, 1))) return bail(rc);
     h->wimg_out = wi;
     cudaMemset(h->tc_error, 0, sizeof(int));
+    if (tc_out_dgrad_supported(h->dc[h->L], h->C)) {
+      unsigned short* wd = nullptr;
+      if ((rc = dalloc(h, &wd, tc_dgrad_weight_image_elems()))) return bail(rc);
+      h->wimg_dgrad = wd;
+      h->use_tc_dgrad = true;
+    }
   }
 #endif
   if (cfg->max_batch > 0 && (rc = ensure_fwd(h, cfg->max_batch))) return bail(rc);
@@ -667,6 +688,8 @@ int kcvae_destroy(kcvae_handle h) {
   for (float* p : fl) if (p) cudaFree(p);
   if (h->a_last_bf16) cudaFree(h->a_last_bf16);
   if (h->wimg_out) cudaFree(h->wimg_out);
+  if (h->wimg_dgrad) cudaFree(h->wimg_dgrad);
+  if (h->dl8) cudaFree(h->dl8);
   if (h->tc_error) cudaFree(h->tc_error);
   double* dl[] = {h->dpartial, h->sums, h->std_acc, h->pos_sums};
   for (double* p : dl) if (p) cudaFree(p);

@@ -206,6 +206,164 @@ __global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __
   }
 }
 
+
+// ============================================================================================
+// Output-layer data gradient on tensor cores:
+//   g_a[n,y,x,ci] = (a[n,y,x,ci] > 0) * sum_{kh,kw,co} dl[n, y-1+kh, x-1+kw, co] * W[kh,kw,co,ci]
+// dl arrives as bf16 NHWC padded to 8 channels (one 16-byte chunk per pixel), so K per tap is 8
+// and two taps are PAIRED into each K=16 MMA: the descriptor's leading byte offset is the
+// distance between the two taps' pixels.  M=128 pixels, N=32 (Cin of the forward layer).
+struct OutDgradParams {
+  const __nv_bfloat16* wimg;   // [5 pairs][2][NPAD_D][8]
+  const __nv_bfloat16* mask;   // forward activation a (bf16 NHWC, Cin channels)
+  float* g_out;                // [B,H,W,Cin] fp32
+  int B, H, W, Cin;
+  int tiles_y, tiles_x, num_tiles;
+  int* error_flag;
+};
+constexpr int NPAD_D = 32;
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) {
+  constexpr uint32_t CH = NPIX * 16;
+  constexpr uint32_t TILE_BYTES = CH;                 // one 8-channel chunk plane
+  constexpr uint32_t STAGE = TILE_BYTES + 128;
+  constexpr uint32_t WB = 5 * 2 * NPAD_D * 16;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* s_tile = smem;
+  unsigned char* s_w = smem + kStages * STAGE;
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreads)
+    reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
+  if (threadIdx.x < kStages * 8) {
+    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
+    reinterpret_cast<uint4*>(s_tile + s * STAGE + TILE_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / (p.tiles_y * p.tiles_x);
+        const int rem = t % (p.tiles_y * p.tiles_x);
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        mbar_expect_tx(&full_bar[s], TILE_BYTES);
+        tma_load_4d(s_tile + s * STAGE, &tmap, &full_bar[s], 0, tx * TW - 1, ty * TR - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(128, NPAD_D);
+      const uint32_t w_base = smem_u32(s_w);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages, a = it & 1;
+        const uint32_t ph = (it / kStages) & 1, aph = (it >> 1) & 1;
+        if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { *p.error_flag = 1; break; }
+        if (!mbar_wait(&full_bar[s], ph)) { *p.error_flag = 1; break; }
+        fence_after_sync();
+        const uint32_t tile_base = smem_u32(s_tile + s * STAGE);
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d_tmem = tmem + (uint32_t)(a * MT * NPAD_D + mt * NPAD_D);
+#pragma unroll
+          for (int pr = 0; pr < 5; ++pr) {
+            const int t0 = 2 * pr, t1 = 2 * pr + 1;
+            const uint32_t sh0 = (uint32_t)((t0 / 3) * PW + (t0 % 3));           // un-flipped taps
+            const uint32_t sh1 = pr < 4 ? (uint32_t)((t1 / 3) * PW + (t1 % 3)) : sh0 + 1;  // pair 4: zero weights
+            const uint64_t da = make_desc_kmajor_noswz(tile_base + (uint32_t)(mt * 128 + sh0) * 16, (sh1 - sh0) * 16, 128);
+            const uint64_t db = make_desc_kmajor_noswz(w_base + (uint32_t)(pr * 2 * NPAD_D * 16), NPAD_D * 16, 128);
+            mma_bf16_ss(d_tmem, da, db, idesc, pr != 0);
+          }
+        }
+        mma_commit(&empty_bar[s]);
+        mma_commit(&tfull_bar[a]);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int n = t / (p.tiles_y * p.tiles_x);
+      const int rem = t % (p.tiles_y * p.tiles_x);
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; break; }
+      fence_after_sync();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        float v[32];
+        const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MT * NPAD_D + mt * NPAD_D);
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + 16, v + 16);
+        const int q = mt * 128 + lg * 32 + lane;
+        const int r = q / PW, c = q % PW;
+        const int oy = ty * TR + r, ox = tx * TW + c;
+        if (c < TW && oy < p.H && ox < p.W) {
+          const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
+          const uint4* mk = reinterpret_cast<const uint4*>(p.mask + pix * p.Cin);
+          float4* o = reinterpret_cast<float4*>(p.g_out + pix * p.Cin);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g * 8 < p.Cin) {
+              const uint4 m = __ldg(mk + g);
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+              float y[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
+                const uint32_t h16 = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+                const bool pos = (h16 & 0x8000u) == 0 && (h16 & 0x7FFFu) != 0;
+                y[j] = pos ? v[g * 8 + j] : 0.f;
+              }
+              o[g * 2] = make_float4(y[0], y[1], y[2], y[3]);
+              o[g * 2 + 1] = make_float4(y[4], y[5], y[6], y[7]);
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// W [3,3,Cout,Cin] fp32 -> paired-tap B image [pair][chunk(2)][n = ci (32)][8 = co]
+__global__ void tc_prep_dgrad_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+  const int total = 5 * 2 * NPAD_D * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % 8;
+    const int n = (i / 8) % NPAD_D;
+    const int kc = (i / (8 * NPAD_D)) % 2;
+    const int pr = i / (16 * NPAD_D);
+    const int tap = 2 * pr + kc;
+    const float v = (tap < 9 && j < Cout && n < Cin) ? w[((int64_t)tap * Cout + j) * Cin + n] : 0.f;
+    img[i] = __float2bfloat16(v);
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n) {
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -250,6 +408,45 @@ void tc_prep_out_weights(const float* w, int Cout, int Cin, void* img, cudaStrea
   ProfScope prof_("tc_prep_weights", st);
   ++g_launches;
   tc_prep_out_weights_kernel<<<8, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+}
+
+
+bool tc_out_dgrad_supported(int Cin, int Cout) { return Cin == 32 && Cout >= 1 && Cout <= 8; }
+size_t tc_dgrad_weight_image_elems() { return (size_t)5 * 2 * NPAD_D * 8; }
+
+void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
+  ProfScope prof_("tc_prep_weights", st);
+  ++g_launches;
+  tc_prep_dgrad_weights_kernel<<<4, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+}
+
+int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, float* g_out, int B, int H, int W,
+                 int Cin, int* error_flag, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint32_t box[4] = {8, PW, PR, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dl8_bf16), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 2;
+  OutDgradParams p{};
+  p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
+  p.mask = reinterpret_cast<const __nv_bfloat16*>(mask_bf16);
+  p.g_out = g_out; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+  p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const size_t smem = (size_t)kStages * ((size_t)NPIX * 16 + 128) + (size_t)5 * 2 * NPAD_D * 16;
+  ProfScope prof_("tc_out_dgrad", st);
+  ++g_launches;
+  cudaFuncSetAttribute(tc_out_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_out_dgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  return 0;
 }
 
 // returns 0 on success, nonzero if the tensor map could not be built

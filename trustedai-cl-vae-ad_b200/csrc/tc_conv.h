@@ -13,4 +13,11 @@ void tc_prep_out_weights(const float* w, int Cout, int Cin, void* img_bf16, cuda
 int tc_out_conv(const void* act_bf16, const void* wimg_bf16, const float* bias, float* xhat, int B, int H, int W,
                 int Cin, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st);
 
+// output-layer data gradient: dl8 = d(loss)/d(logit) as bf16 NHWC padded to 8 channels
+bool tc_out_dgrad_supported(int Cin, int Cout);
+size_t tc_dgrad_weight_image_elems();
+void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
+int tc_out_dgrad(const void* dl8_bf16, const void* wimg_bf16, const void* mask_bf16, float* g_out, int B, int H, int W,
+                 int Cin, int* error_flag, cudaStream_t st);
+
 }  // namespace kc
