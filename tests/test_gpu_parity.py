@@ -257,9 +257,13 @@ def test_tc_backward_parity(shape):
     assert_metrics_close(d, od, rtol=1e-3, atol=1e-6)
     for (n, _), g, og in zip(O.variable_shapes(cfg), grads, ograds):
         assert rel_err(g, og.numpy()) < 2e-2, (n, rel_err(g, og.numpy()))
+    # five optimizer steps on both precisions stay together (same data, same noise)
     m.compile(optimizer=pkg.Adam(1e-4))
-    l0 = float(m.compute_loss(x, training=True, eps=eps)["loss"])
+    m32.compile(optimizer=pkg.Adam(1e-4))
     for _ in range(5):
         m.train_step(x, eps=eps)
-    assert float(m.compute_loss(x, training=True, eps=eps)["loss"]) < l0
+        m32.train_step(x, eps=eps)
+    la = float(m.compute_loss(x, training=True, eps=eps)["loss"])
+    lb = float(m32.compute_loss(x, training=True, eps=eps)["loss"])
+    assert abs(la - lb) < 2e-3 * abs(lb), (la, lb)
     assert m.tc_status() == 1

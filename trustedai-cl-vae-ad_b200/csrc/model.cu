@@ -238,6 +238,9 @@ size_t max_partial_floats(const kcvae_model* h, int B) {
   up(colsum_partial_floats(B, h->enc_dense ? h->enc_dense : 1));
   up(colsum_partial_floats(B, h->dec_units));
   up(score_partial_floats(B, (int64_t)h->H * h->W));
+#ifndef KCVAE_EMU
+  if (h->use_tc_dgrad) up(tc_out_wgrad_partial_floats(h->dc[L], h->C));
+#endif
   return mx;
 }
 
@@ -466,7 +469,13 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     wa.s = 1; wa.d = -1; wa.oy = 1; wa.ox = 1;
     wa.o_sa = wa.Cb; wa.o_sb = 1;  // [tap][out=a][in=b]
     g_tag = "dec.out.bwd";
-    conv_wgrad(wa, st);
+    bool wdone = false;
+#ifndef KCVAE_EMU
+    if (h->use_tc_dgrad && h->use_tc_out && tc_out_wgrad_supported(h->dc[L], h->C) &&
+        h->partial_floats >= tc_out_wgrad_partial_floats(h->dc[L], h->C))
+      wdone = tc_out_wgrad(h->dl8, h->a_last_bf16, h->gp(vi), h->partial, B, h->H, h->W, h->dc[L], h->C, h->tc_error, st) == 0;
+#endif
+    if (!wdone) conv_wgrad(wa, st);
     colsum(h->dlogit, (int64_t)B * h->H * h->W, h->C, h->gp(vi + 1), h->partial, st);
     ConvArgs a{};
     a.in = h->dlogit; a.w = h->wp(vi); a.mask = h->act_d[L]; a.out = h->g_act_d[L];

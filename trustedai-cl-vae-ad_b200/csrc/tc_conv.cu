@@ -364,6 +364,157 @@ __global__ void tc_prep_dgrad_weights_kernel(const float* w, int Cout, int Cin, 
   }
 }
 
+// ============================================================================================
+// Output-layer weight gradient on tensor cores (MN-major operands, K = pixels):
+//   dW[kh,kw,co,ci] = sum_{n,y,x} dl[n,y,x,co] * a[n, y+1-kh, x+1-kw, ci]
+// Per 32x30 tile: B operand = the bf16 halo tile of `a` (TMA, same [chunk][pixel] planes as the
+// forward kernel, read MN-major: N = 32 channels = 4 chunk planes, K = 16 pixels per MMA);
+// A operand = a zero-padded plane of dl (36 rows x 32 cols, 8 channels per pixel) written by
+// the loader warps, read MN-major with M-groups strided by ONE PLANE ROW, so M-group g holds
+// the vertical tap kh = g; the horizontal tap kw is the B start address.  Three accumulators
+// (kw) of M=64 x N=32 stay in TMEM over all tiles of the persistent CTA; each CTA writes one
+// partial dW that a reduction kernel sums (deterministic).
+struct OutWgradParams {
+  const __nv_bfloat16* dl8;    // [B,H,W,8] bf16
+  float* partial;              // [grid][9*Cout*Cin]
+  int B, H, W, Cout, Cin;
+  int tiles_y, tiles_x, num_tiles;
+  int* error_flag;
+};
+constexpr int DLROWS = TR + 4;                 // dl plane rows (-2 .. TR+1)
+constexpr uint32_t DL_BYTES = DLROWS * PW * 16;
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutWgradParams p) {
+  constexpr int KC = 4;                               // Cin = 32
+  constexpr uint32_t CH = NPIX * 16;
+  constexpr uint32_t TILE_BYTES = KC * CH;
+  constexpr uint32_t STAGE = DL_BYTES + TILE_BYTES + 128;   // [dl plane][a tile][pad]
+  constexpr int KSTEPS = NPIX / 16;                   // 68
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x < kStages * 8) {
+    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
+    reinterpret_cast<uint4*>(smem + s * STAGE + DL_BYTES + TILE_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1 + 4); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / (p.tiles_y * p.tiles_x);
+        const int rem = t % (p.tiles_y * p.tiles_x);
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        mbar_expect_tx(&full_bar[s], TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+          tma_load_4d(smem + s * STAGE + DL_BYTES + c * CH, &tmap, &full_bar[s], c * 8, tx * TW - 1, ty * TR - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_f32(64, 32, 1, 1);   // both operands MN-major
+      int it = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if (!mbar_wait(&full_bar[s], ph)) { *p.error_flag = 1; ok = false; break; }
+        fence_after_sync();
+        const uint32_t dl_base = smem_u32(smem + s * STAGE);
+        const uint32_t a_base = dl_base + DL_BYTES;
+#pragma unroll 1
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint64_t da = make_desc_kmajor_noswz(dl_base + (uint32_t)(ks * 16) * 16, 128, PW * 16);
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const uint64_t db = make_desc_kmajor_noswz(a_base + (uint32_t)(ks * 16 + 2 - kw) * 16, 128, CH);
+            mma_bf16_ss(tmem + (uint32_t)(kw * 32), da, db, idesc, (it | ks) != 0);
+          }
+        }
+        mma_commit(&empty_bar[s]);
+      }
+      if (ok) mma_commit(&done_bar);
+    }
+  } else {
+    // ============================ dl-plane loaders (4 warps) ==============================
+    const int lt = threadIdx.x - 64;              // 0..127
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      if (!mbar_wait(&empty_bar[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; break; }
+      const int n = t / (p.tiles_y * p.tiles_x);
+      const int rem = t % (p.tiles_y * p.tiles_x);
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      uint4* dst = reinterpret_cast<uint4*>(smem + s * STAGE);
+      for (int u = lt; u < DLROWS * PW; u += 128) {
+        const int rho = u / PW - 2, c = u % PW;
+        const int y = ty * TR + rho, x = tx * TW + c;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (rho >= 0 && rho < TR && c < TW && y < p.H && x < p.W)
+          v = __ldg(reinterpret_cast<const uint4*>(p.dl8) + ((int64_t)n * p.H + y) * p.W + x);
+        dst[u] = v;
+      }
+      fence_async_smem();       // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    // ================================ final epilogue =====================================
+    const int lg = warp & 3;
+    if (lg < 2 && my_tiles > 0) {
+      if (mbar_wait(&done_bar, 0)) {
+        fence_after_sync();
+        const int E = 9 * p.Cout * p.Cin;
+        float* out = p.partial + (int64_t)blockIdx.x * E;
+#pragma unroll 1
+        for (int kw = 0; kw < 3; ++kw) {
+          float v[32];
+          const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(kw * 32);
+          tmem_ld16(ta, v);
+          tmem_ld16(ta + 16, v + 16);
+          const int m = lg * 16 + lane;              // M row held by this TMEM lane (lanes 0..15 of the group)
+          const int g = m >> 3, co = m & 7;
+          if (lane < 16 && g < 3 && co < p.Cout) {
+            for (int ci = 0; ci < p.Cin; ++ci) out[((g * 3 + kw) * p.Cout + co) * p.Cin + ci] = v[ci];
+          }
+        }
+      } else if (lane == 0) {
+        *p.error_flag = 1;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+__global__ void sum_partials_kernel(const float* partial, int nparts, int E, float* out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float s = 0.f;
+  for (int i = 0; i < nparts; ++i) s += partial[(int64_t)i * E + e];
+  out[e] = s;
+}
+
 __global__ void cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n) {
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -446,6 +597,40 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   ++g_launches;
   cudaFuncSetAttribute(tc_out_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_out_dgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  return 0;
+}
+
+bool tc_out_wgrad_supported(int Cin, int Cout) { return Cin == 32 && Cout >= 1 && Cout <= 8; }
+size_t tc_out_wgrad_partial_floats(int Cin, int Cout) { return (size_t)kNumSMs * 9 * Cout * Cin; }
+
+// dW [3,3,Cout,Cin] (Keras Conv2DTranspose layout) from dl8 [B,H,W,8] bf16 and act [B,H,W,Cin] bf16
+int tc_out_wgrad(const void* dl8_bf16, const void* act_bf16, float* dW, float* partial, int B, int H, int W, int Cin,
+                 int Cout, int* error_flag, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  const cuuint32_t box[4] = {8, PW, PR, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(act_bf16), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 2;
+  OutWgradParams p{};
+  p.dl8 = reinterpret_cast<const __nv_bfloat16*>(dl8_bf16);
+  p.partial = partial; p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.Cin = Cin;
+  p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const size_t smem = (size_t)kStages * ((size_t)DL_BYTES + (size_t)4 * NPIX * 16 + 128);
+  const int E = 9 * Cout * Cin;
+  ProfScope prof_("tc_out_wgrad", st);
+  g_launches += 2;
+  cudaFuncSetAttribute(tc_out_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_out_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  sum_partials_kernel<<<cdiv(E, 256), 256, 0, st>>>(partial, grid, E, dW);
   return 0;
 }
 

@@ -20,4 +20,10 @@ void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img_bf16, cu
 int tc_out_dgrad(const void* dl8_bf16, const void* wimg_bf16, const void* mask_bf16, float* g_out, int B, int H, int W,
                  int Cin, int* error_flag, cudaStream_t st);
 
+// output-layer weight gradient (MN-major tcgen05, K = pixels); partial >= tc_out_wgrad_partial_floats()
+bool tc_out_wgrad_supported(int Cin, int Cout);
+size_t tc_out_wgrad_partial_floats(int Cin, int Cout);
+int tc_out_wgrad(const void* dl8_bf16, const void* act_bf16, float* dW, float* partial, int B, int H, int W, int Cin,
+                 int Cout, int* error_flag, cudaStream_t st);
+
 }  // namespace kc
