@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-per-gpu", type=int, default=PER_GPU_BATCH)
-    ap.add_argument("--precision", default=os.environ.get("KCVAE_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("KCVAE_PRECISION", "bf16"),
+                    help="bf16: tcgen05 decoder kernels (bf16 operands, fp32 accumulate); fp32: CUDA-core path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-score", action="store_true")
     return ap.parse_args()
