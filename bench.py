@@ -26,6 +26,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PER_GPU_BATCH = 32
+_REAL_STDOUT = sys.stdout
 CPU_SAMPLE_BATCH = 16
 L2_BYTES = 126 * 1024 * 1024
 
@@ -205,7 +206,7 @@ def run_reference(args):
         "e2e": {"value": train, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
 
 
 # --------------------------------------------------------------------------------- GPU arm
@@ -354,12 +355,17 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "score": score_info,
         }
-        print(json.dumps(line), flush=True)
+        _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries (NCCL prints its version banner) get stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
