@@ -44,6 +44,23 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int M, int N, int a_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// one lane of a fully converged warp (the others keep executing the same uniform code, so
+// descriptor arithmetic stays on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// advance the start-address field of a descriptor by `units` 16-byte units (no carry out of the
+// 14-bit field for any shared-memory address)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t units) { return desc + (uint64_t)units; }
+
 // D[tmem] (+)= A[smem] . B[smem]^T ; issued by ONE thread
 __device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -119,35 +119,38 @@ tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==========================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16_f32(128, NPAD);
-      const uint32_t w_base = smem_u32(s_w);
-      int it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        const int s = it % kStages, a = it & 1;
-        const uint32_t ph = (it / kStages) & 1, aph = (it >> 1) & 1;
-        if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { *p.error_flag = 1; break; }   // epilogue drained TMEM stage
-        if (!mbar_wait(&full_bar[s], ph)) { *p.error_flag = 1; break; }          // TMA landed
-        fence_after_sync();
-        const uint32_t tile_base = smem_u32(s_tile + s * (TILE_BYTES + 128));
-#pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t d_tmem = tmem + (uint32_t)(a * MT * NPAD + mt * NPAD);
+    // the whole warp runs the (uniform) loop; only the elected lane issues tcgen05 instructions
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16_f32(128, NPAD);
+    const uint64_t db0 = make_desc_kmajor_noswz(smem_u32(s_w), NPAD * 16, 128);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages, a = it & 1;
+      const uint32_t ph = (it / kStages) & 1, aph = (it >> 1) & 1;
+      if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { if (leader) *p.error_flag = 1; break; }   // epilogue drained TMEM stage
+      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; break; }          // TMA landed
+      fence_after_sync();
+      const uint64_t da0 = make_desc_kmajor_noswz(smem_u32(s_tile + s * (TILE_BYTES + 128)), CH, 128);
+#pragma unroll 2
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t d_tmem = tmem + (uint32_t)(a * MT * NPAD + mt * NPAD);
+        const uint64_t da_mt = desc_advance(da0, (uint32_t)(mt * 128));
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const int kh = tap / 3, kw = tap % 3;
-            const uint32_t shift = (uint32_t)((2 - kh) * PW + (2 - kw));   // flipped taps (A4)
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t shift = (uint32_t)((2 - tap / 3) * PW + (2 - tap % 3));   // flipped taps (A4)
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              const uint64_t da = make_desc_kmajor_noswz(tile_base + (uint32_t)(2 * ks) * CH + (uint32_t)(mt * 128 + shift) * 16, CH, 128);
-              const uint64_t db = make_desc_kmajor_noswz(w_base + (uint32_t)((tap * KS + ks) * 2 * NPAD * 16), NPAD * 16, 128);
-              mma_bf16_ss(d_tmem, da, db, idesc, (tap | ks) != 0);
-            }
+          for (int ks = 0; ks < KS; ++ks) {
+            const uint64_t da = desc_advance(da_mt, (uint32_t)(2 * ks) * (CH / 16) + shift);
+            const uint64_t db = desc_advance(db0, (uint32_t)((tap * KS + ks) * 2 * NPAD));
+            if (leader) mma_bf16_ss(d_tmem, da, db, idesc, (tap | ks) != 0);
           }
         }
+      }
+      if (leader) {
         mma_commit(&empty_bar[s]);    // smem stage reusable once these MMAs have read it
         mma_commit(&tfull_bar[a]);    // accumulators ready for the epilogue
       }
+      __syncwarp();
     }
   } else {
     // ================================ epilogue warps ======================================
@@ -269,33 +272,35 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16_f32(128, NPAD_D);
-      const uint32_t w_base = smem_u32(s_w);
-      int it = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        const int s = it % kStages, a = it & 1;
-        const uint32_t ph = (it / kStages) & 1, aph = (it >> 1) & 1;
-        if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { *p.error_flag = 1; break; }
-        if (!mbar_wait(&full_bar[s], ph)) { *p.error_flag = 1; break; }
-        fence_after_sync();
-        const uint32_t tile_base = smem_u32(s_tile + s * STAGE);
-#pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t d_tmem = tmem + (uint32_t)(a * MT * NPAD_D + mt * NPAD_D);
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16_f32(128, NPAD_D);
+    const uint32_t w_base = smem_u32(s_w);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages, a = it & 1;
+      const uint32_t ph = (it / kStages) & 1, aph = (it >> 1) & 1;
+      if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { if (leader) *p.error_flag = 1; break; }
+      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; break; }
+      fence_after_sync();
+      const uint32_t tile_base = smem_u32(s_tile + s * STAGE);
+#pragma unroll 2
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t d_tmem = tmem + (uint32_t)(a * MT * NPAD_D + mt * NPAD_D);
 #pragma unroll
-          for (int pr = 0; pr < 5; ++pr) {
-            const int t0 = 2 * pr, t1 = 2 * pr + 1;
-            const uint32_t sh0 = (uint32_t)((t0 / 3) * PW + (t0 % 3));           // un-flipped taps
-            const uint32_t sh1 = pr < 4 ? (uint32_t)((t1 / 3) * PW + (t1 % 3)) : sh0 + 1;  // pair 4: zero weights
-            const uint64_t da = make_desc_kmajor_noswz(tile_base + (uint32_t)(mt * 128 + sh0) * 16, (sh1 - sh0) * 16, 128);
-            const uint64_t db = make_desc_kmajor_noswz(w_base + (uint32_t)(pr * 2 * NPAD_D * 16), NPAD_D * 16, 128);
-            mma_bf16_ss(d_tmem, da, db, idesc, pr != 0);
-          }
+        for (int pr = 0; pr < 5; ++pr) {
+          const int t0 = 2 * pr, t1 = 2 * pr + 1;
+          const uint32_t sh0 = (uint32_t)((t0 / 3) * PW + (t0 % 3));           // un-flipped taps
+          const uint32_t sh1 = pr < 4 ? (uint32_t)((t1 / 3) * PW + (t1 % 3)) : sh0 + 1;  // pair 4: zero weights
+          const uint64_t da = make_desc_kmajor_noswz(tile_base + (uint32_t)(mt * 128 + sh0) * 16, (sh1 - sh0) * 16, 128);
+          const uint64_t db = make_desc_kmajor_noswz(w_base + (uint32_t)(pr * 2 * NPAD_D * 16), NPAD_D * 16, 128);
+          if (leader) mma_bf16_ss(d_tmem, da, db, idesc, pr != 0);
         }
+      }
+      if (leader) {
         mma_commit(&empty_bar[s]);
         mma_commit(&tfull_bar[a]);
       }
+      __syncwarp();
     }
   } else {
     const int lg = warp & 3;
@@ -430,30 +435,31 @@ tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutWgradParams p) 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16_f32(64, 32, 1, 1);   // both operands MN-major
-      int it = 0;
-      bool ok = true;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        if (!mbar_wait(&full_bar[s], ph)) { *p.error_flag = 1; ok = false; break; }
-        fence_after_sync();
-        const uint32_t dl_base = smem_u32(smem + s * STAGE);
-        const uint32_t a_base = dl_base + DL_BYTES;
-#pragma unroll 1
-        for (int ks = 0; ks < KSTEPS; ++ks) {
-          const uint64_t da = make_desc_kmajor_noswz(dl_base + (uint32_t)(ks * 16) * 16, 128, PW * 16);
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16_f32(64, 32, 1, 1);   // both operands MN-major
+    int it = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
+      fence_after_sync();
+      const uint32_t dl_base = smem_u32(smem + s * STAGE);
+      const uint64_t da0 = make_desc_kmajor_noswz(dl_base, 128, PW * 16);
+      const uint64_t db0 = make_desc_kmajor_noswz(dl_base + DL_BYTES, 128, CH);
+#pragma unroll 4
+      for (int ks = 0; ks < KSTEPS; ++ks) {
+        const uint64_t da = desc_advance(da0, (uint32_t)(ks * 16));
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const uint64_t db = make_desc_kmajor_noswz(a_base + (uint32_t)(ks * 16 + 2 - kw) * 16, 128, CH);
-            mma_bf16_ss(tmem + (uint32_t)(kw * 32), da, db, idesc, (it | ks) != 0);
-          }
+        for (int kw = 0; kw < 3; ++kw) {
+          const uint64_t db = desc_advance(db0, (uint32_t)(ks * 16 + 2 - kw));
+          if (leader) mma_bf16_ss(tmem + (uint32_t)(kw * 32), da, db, idesc, (it | ks) != 0);
         }
-        mma_commit(&empty_bar[s]);
       }
-      if (ok) mma_commit(&done_bar);
+      if (leader) mma_commit(&empty_bar[s]);
+      __syncwarp();
     }
+    if (ok && leader) mma_commit(&done_bar);
   } else {
     // ============================ dl-plane loaders (4 warps) ==============================
     const int lt = threadIdx.x - 64;              // 0..127
