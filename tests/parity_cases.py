@@ -157,3 +157,64 @@ def case_structure(backend):
         assert m.decoder.layers[0].units == (16 // 4) * (20 // 4) * cfg["model"]["decoder_dense_filters"]
         assert len(m.trainable_weights) == 4 * L + 8
         assert [tuple(v.shape) for v in m.trainable_weights] == [s for _, s in O.variable_shapes(cfg)]
+
+
+def case_driver_replay(backend, tmpdir):
+    """Replays the call sequences of train.py:95-131,143-144 and
+    do_anomaly_detection.py:203-222 against the mirror (the scripts themselves need
+    TF/matplotlib and cannot be imported here)."""
+    import os
+    P = __import__("kcvae_testlib").pkg
+    cfg = small_config()
+    cfg["training"]["max_epochs"] = 2
+    cfg["training"]["batch_size"] = 4
+    cls = __import__("kcvae_testlib").model_class(backend, "global")
+    # --- train.py: build_model -> compile -> fit(callbacks=[BetaAnnealing]) -> save
+    vae = cls(__import__("copy").deepcopy(cfg))
+    vae.compile(optimizer=P.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
+    train = [frames(cfg, 4, seed=s) for s in range(3)]
+    val = [frames(cfg, 4, seed=50)]
+
+    class Recorder(P.Callback):
+        def __init__(self):
+            self.epochs, self.batches = [], 0
+        def on_epoch_end(self, epoch, logs=None):
+            self.epochs.append(dict(logs))
+        def on_train_batch_end(self, batch, logs=None):
+            self.batches += 1
+
+    rec = Recorder()
+    beta0 = vae.beta
+    hist = vae.fit(train, validation_data=val, batch_size=4, callbacks=[rec, P.BetaAnnealingCallback()],
+                   shuffle=True, epochs=2, verbose=0)
+    assert rec.batches == 6 and len(rec.epochs) == 2
+    assert set(vae.METRIC_KEYS) <= set(hist.history) and "val_loss" in hist.history
+    assert abs(vae.beta - beta0 * 0.98 ** 2) < 1e-12                    # train.py:46-47
+    assert all(np.isfinite(v) for v in hist.history["loss"])
+    logdir = os.path.join(str(tmpdir), "fit_x")
+    P.save_model_to_directory(vae, logdir)
+    for sub in ("config.yml", "encoder/weights.npz", "decoder/weights.npz", "optimizer.npz"):
+        assert os.path.exists(os.path.join(logdir, sub)), sub
+    pred = vae.predict(val[0])
+    mean, _ = vae.encode(val[0])
+    # --- do_anomaly_detection.py: load_model_from_directory -> data scale -> evaluate
+    orig_load = P.load_model.load_model_from_config if hasattr(P, "load_model") else None
+    model2 = cls(P.load_config(os.path.join(logdir, "config.yml")))
+    model2.load_model(logdir)
+    np.testing.assert_array_equal(model2.predict(val[0]), pred)
+    for a, b in zip(model2.get_weights(), vae.get_weights()):
+        np.testing.assert_array_equal(a, b)
+    assert model2.get_optimizer_state()[2] == 6                        # Adam state restored
+    scale = P.get_data_scale(model2, cfg, {"train": train})
+    res = P.evaluate_anomalies(model2, cfg, {"train": val}, scale, 3.0)
+    assert res["rec"].shape == (4, *cfg["data"]["image_size"]) and res["errs"].shape == (4, 16, 24)
+    assert res["anomalies"].dtype == bool and res["z_scores"].shape == (4,)
+    # sample() and Sequential call
+    assert tuple(vae.sample().shape) == (100, *cfg["data"]["image_size"])
+    head = vae.encoder(val[0])
+    np.testing.assert_allclose(head.numpy()[:, :cfg["model"]["latent_dimensions"]], mean.numpy(), atol=1e-6)
+    # variable views
+    v0 = vae.trainable_weights[0]
+    assert v0.numpy().shape == v0.shape
+    v0.assign(v0.numpy() * 0)
+    assert float(np.abs(vae.get_weights()[0]).max()) == 0.0

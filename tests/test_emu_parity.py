@@ -49,3 +49,30 @@ def test_topologies(shape):
     cfg = small_config(**shape)
     PC.case_forward(BACKEND, cfg, B=2)
     PC.case_grads(BACKEND, cfg=cfg, B=3)
+
+
+def test_driver_replay(tmp_path):
+    PC.case_driver_replay(BACKEND, tmp_path)
+
+
+def test_error_behaviour():
+    import numpy as np
+    from kcvae_testlib import make, model_class, frames
+    bad = small_config()
+    bad["model"]["layers"] = [4] * 6
+    with pytest.raises(RuntimeError, match="Collapse"):
+        make(bad, BACKEND)
+    cfg = small_config()
+    del cfg["loss"]["w_x_std"]
+    with pytest.raises(KeyError):
+        model_class(BACKEND, "global")(cfg)
+    m, _ = make(small_config(), BACKEND)
+    with pytest.raises(ValueError):
+        m.call(np.zeros((2, 8, 8, 3), np.float32))
+    with pytest.raises(RuntimeError):
+        m.train_step(frames(small_config(), 2))          # not compiled
+    odd = small_config(H=18, W=24)                        # not divisible by 2^L: loss cannot broadcast
+    mo, _ = make(odd, BACKEND)
+    mo.encode(frames(odd, 1))                             # encode alone works, like the reference
+    with pytest.raises(Exception, match="divisible"):
+        mo.compute_loss(frames(odd, 1))

@@ -267,3 +267,7 @@ def test_tc_backward_parity(shape):
     lb = float(m32.compute_loss(x, training=True, eps=eps)["loss"])
     assert abs(la - lb) < 2e-3 * abs(lb), (la, lb)
     assert m.tc_status() == 1
+
+
+def test_driver_replay(tmp_path):
+    PC.case_driver_replay(BACKEND, tmp_path)
