@@ -110,7 +110,9 @@ struct kcvae_model {
   float *minmax = nullptr, *metrics_dev = nullptr;
   // tensor-core path (precision == BF16_TC): bf16 copy of the last decoder activation, UMMA
   // weight image of the output layer, device-side error flag of the bounded barrier waits
-  bool use_tc_out = false, use_tc_dgrad = false;
+  bool use_tc_out = false, use_tc_dgrad = false, use_tc_convT = false;
+  void* a_prev8 = nullptr;       // bf16 input of the last Conv2DTranspose s2, NHWC padded to 8 channels
+  void* wimg_convT = nullptr;
   uint16_t* dl8 = nullptr;       // bf16 d(loss)/d(logit), NHWC padded to 8 channels
   void* wimg_dgrad = nullptr;
   void* a_last_bf16 = nullptr;
@@ -267,6 +269,11 @@ int ensure_fwd(kcvae_model* h, int B) {
     unsigned short* tmp = reinterpret_cast<unsigned short*>(h->a_last_bf16);
     KC_TRY(dalloc(h, &tmp, (size_t)B * h->dh[L] * h->dw[L] * h->dc[L]));
     h->a_last_bf16 = tmp;
+    if (h->use_tc_convT) {
+      unsigned short* t8 = reinterpret_cast<unsigned short*>(h->a_prev8);
+      KC_TRY(dalloc(h, &t8, (size_t)B * h->dh[L - 1] * h->dw[L - 1] * 8));
+      h->a_prev8 = t8;
+    }
   }
 #endif
   h->partial_floats = max_partial_floats(h, B);
@@ -352,6 +359,7 @@ void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st) {
 
 void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float* out, cudaStream_t st) {
   const int L = h->L;
+  bool last_is_bf16 = false;   // the last activation was produced directly in bf16 by tc_convT_fwd
   GemmArgs ga{};
   ga.A = z; ga.a_sm = h->latent; ga.a_sk = 1;
   ga.Bm = h->wp(h->vi_dec_dense()); ga.b_sk = h->dec_units; ga.b_sn = 1;
@@ -366,6 +374,18 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
     a.Ho = h->dh[l + 1]; a.Wo = h->dw[l + 1]; a.Co = h->dc[l + 1];
     a.w_sci = 1; a.w_sco = a.Ci;  // [kh,kw,out,in]
     g_tag = l == L - 1 ? "dec.convT_last.fwd" : "dec.convT.fwd";
+#ifndef KCVAE_EMU
+    if (l == L - 1 && h->use_tc_convT && h->use_tc_out) {
+      // sub-pixel phase decomposition on tcgen05, bf16 NHWC output straight into the buffer the
+      // output-layer kernels read (no fp32 copy of the 224x300x32 activation exists in this mode)
+      pack_c8_bf16(a.in, (int64_t)B * a.Hi * a.Wi, a.Ci, h->a_prev8, st);
+      tc_prep_convT_weights(a.w, a.Co, a.Ci, h->wimg_convT, st);
+      if (tc_convT_fwd(h->a_prev8, h->wimg_convT, a.bias, h->a_last_bf16, B, a.Hi, a.Wi, h->tc_error, st) == 0) {
+        last_is_bf16 = true;
+        continue;
+      }
+    }
+#endif
     conv_forward(CONVT_S2, EPI_BIAS_RELU, a, st);
   }
   ConvArgs a{};
@@ -377,7 +397,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
 #ifndef KCVAE_EMU
   if (h->use_tc_out) {
     // tcgen05 implicit GEMM (tc_conv.cu): bf16 operands, fp32 accumulate in TMEM
-    cast_f32_to_bf16(h->act_d[L], h->a_last_bf16, (int64_t)B * a.Hi * a.Wi * a.Ci, st);
+    if (!last_is_bf16) cast_f32_to_bf16(h->act_d[L], h->a_last_bf16, (int64_t)B * a.Hi * a.Wi * a.Ci, st);
     tc_prep_out_weights(a.w, a.Co, a.Ci, h->wimg_out, st);
     if (tc_out_conv(h->a_last_bf16, h->wimg_out, a.bias, out, B, a.Hi, a.Wi, a.Ci, a.Co, apply_sigmoid, h->tc_error, st) == 0)
       return;
@@ -667,6 +687,12 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
     if ((rc = dalloc(h, &wi, tc_out_weight_image_elems(h->dc[h->L]))) || (rc = dalloc(h, &h->tc_error, 1))) return bail(rc);
     h->wimg_out = wi;
     cudaMemset(h->tc_error, 0, sizeof(int));
+    if (h->L >= 1 && tc_convT_fwd_supported(h->dc[h->L - 1], h->dc[h->L])) {
+      unsigned short* wc = nullptr;
+      if ((rc = dalloc(h, &wc, tc_convT_weight_image_elems()))) return bail(rc);
+      h->wimg_convT = wc;
+      h->use_tc_convT = true;
+    }
     if (tc_out_dgrad_supported(h->dc[h->L], h->C)) {
       unsigned short* wd = nullptr;
       if ((rc = dalloc(h, &wd, tc_dgrad_weight_image_elems()))) return bail(rc);
@@ -698,6 +724,8 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->a_last_bf16) cudaFree(h->a_last_bf16);
   if (h->wimg_out) cudaFree(h->wimg_out);
   if (h->wimg_dgrad) cudaFree(h->wimg_dgrad);
+  if (h->wimg_convT) cudaFree(h->wimg_convT);
+  if (h->a_prev8) cudaFree(h->a_prev8);
   if (h->dl8) cudaFree(h->dl8);
   if (h->tc_error) cudaFree(h->tc_error);
   double* dl[] = {h->dpartial, h->sums, h->std_acc, h->pos_sums};

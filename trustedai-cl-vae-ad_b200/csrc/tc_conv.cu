@@ -521,6 +521,199 @@ __global__ void sum_partials_kernel(const float* partial, int nparts, int E, flo
   out[e] = s;
 }
 
+// ============================================================================================
+// Conv2DTranspose k3 s2 'same' + bias + ReLU on tensor cores (src/abstract_cvae.py:81-84, A3),
+// Cin <= 8 -> Cout = 32, by sub-pixel phase decomposition: output parity (pa,pb) of
+//   y[2i+pa, 2j+pb, co] = b[co] + sum_{kh = pa (mod 2), kw = pb (mod 2)} x[i-(kh-pa)/2, j-(kw-pb)/2, ci] W[kh,kw,co,ci]
+// is a dense 2x2 / 1x2 / 2x1 / 1x1 convolution on the LOW-resolution grid.  Input: bf16 NHWC
+// padded to 8 channels (one 16-byte unit per pixel, one TMA plane).  Per M-tile of 128 low-res
+// pixels five K=16 MMAs (tap pairs through the leading byte offset) fill four N=32
+// accumulators (128 TMEM columns, double buffered); the epilogue writes the 2x2 output pixels
+// as bf16 NHWC - the activation the output-layer kernels consume.
+struct ConvTParams {
+  const __nv_bfloat16* wimg;   // [5 MMAs][2 chunks][32][8]
+  const float* bias;           // [32]
+  __nv_bfloat16* out;          // [B,2h,2w,32] bf16
+  int B, h, w;                 // low-res size
+  int tiles_y, tiles_x, num_tiles;
+  int* error_flag;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
+  constexpr uint32_t TILE_BYTES = NPIX * 16;          // one 8-channel plane, 34 x 32 pixels
+  constexpr uint32_t STAGE = TILE_BYTES + 128;
+  constexpr uint32_t WB = 5 * 2 * 32 * 16;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* s_tile = smem;
+  unsigned char* s_w = smem + kStages * STAGE;
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreads)
+    reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
+  if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (threadIdx.x < kStages * 8) {
+    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
+    reinterpret_cast<uint4*>(s_tile + s * STAGE + TILE_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / (p.tiles_y * p.tiles_x);
+        const int rem = t % (p.tiles_y * p.tiles_x);
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        mbar_expect_tx(&full_bar[s], TILE_BYTES);
+        tma_load_4d(s_tile + s * STAGE, &tmap, &full_bar[s], 0, tx * TW - 1, ty * TR - 1, n);
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16_f32(128, 32);
+    const uint32_t w_base = smem_u32(s_w);
+    // (start shift, leading offset) in pixels and destination phase of the five MMAs
+    //   MMA0: taps (2,2)@0 , (2,0)@1        -> phase (0,0)     MMA1: taps (0,2)@PW , (0,0)@PW+1 -> phase (0,0)
+    //   MMA2: taps (2,1)@1 , (0,1)@PW+1     -> phase (0,1)     MMA3: taps (1,2)@PW , (1,0)@PW+1 -> phase (1,0)
+    //   MMA4: tap  (1,1)@PW+1 , zero weights -> phase (1,1)
+    int it = 0, mcount = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; break; }
+      fence_after_sync();
+      const uint32_t tile_base = smem_u32(s_tile + s * STAGE);
+      bool ok = true;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt, ++mcount) {
+        const int a = mcount & 1;
+        const uint32_t aph = (mcount >> 1) & 1;
+        if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { if (leader) *p.error_flag = 1; ok = false; break; }
+        fence_after_sync();
+        const uint32_t d0 = tmem + (uint32_t)(a * 128);
+        const uint32_t q0 = tile_base + (uint32_t)(mt * 128) * 16;
+        const uint64_t a0 = make_desc_kmajor_noswz(q0, 16, 128);
+        const uint64_t a1 = make_desc_kmajor_noswz(q0 + PW * 16, 16, 128);
+        const uint64_t a2 = make_desc_kmajor_noswz(q0 + 16, PW * 16, 128);
+        const uint64_t a4 = make_desc_kmajor_noswz(q0 + (PW + 1) * 16, 16, 128);
+        const uint64_t b0 = make_desc_kmajor_noswz(w_base, 32 * 16, 128);
+        if (leader) {
+          mma_bf16_ss(d0 + 0, a0, b0, idesc, 0);
+          mma_bf16_ss(d0 + 0, a1, desc_advance(b0, 64), idesc, 1);
+          mma_bf16_ss(d0 + 32, a2, desc_advance(b0, 128), idesc, 0);
+          mma_bf16_ss(d0 + 64, a1, desc_advance(b0, 192), idesc, 0);
+          mma_bf16_ss(d0 + 96, a4, desc_advance(b0, 256), idesc, 0);
+          mma_commit(&tfull_bar[a]);
+        }
+        __syncwarp();
+      }
+      if (!ok) break;
+      if (leader) mma_commit(&empty_bar[s]);
+      __syncwarp();
+    }
+  } else {
+    const int lg = warp & 3;
+    const int H2 = 2 * p.h, W2 = 2 * p.w;
+    int it = 0, mcount = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int n = t / (p.tiles_y * p.tiles_x);
+      const int rem = t % (p.tiles_y * p.tiles_x);
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      bool ok = true;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt, ++mcount) {
+        const int a = mcount & 1;
+        const uint32_t aph = (mcount >> 1) & 1;
+        if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; ok = false; break; }
+        fence_after_sync();
+        const int q = mt * 128 + lg * 32 + lane;
+        const int r = q / PW, c = q % PW;
+        const int i = ty * TR + r, j = tx * TW + c;
+        const bool valid = c < TW && i < p.h && j < p.w;
+#pragma unroll
+        for (int phs = 0; phs < 4; ++phs) {
+          float v[32];
+          const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * 128 + phs * 32);
+          tmem_ld16(ta, v);
+          tmem_ld16(ta + 16, v + 16);
+          if (valid) {
+            const int oy = 2 * i + (phs >> 1), ox = 2 * j + (phs & 1);
+            uint4* o = reinterpret_cast<uint4*>(p.out + (((int64_t)n * H2 + oy) * W2 + ox) * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float y0 = fmaxf(v[g * 8 + 2 * e] + s_bias[g * 8 + 2 * e], 0.f);
+                const float y1 = fmaxf(v[g * 8 + 2 * e + 1] + s_bias[g * 8 + 2 * e + 1], 0.f);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              o[g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      }
+      if (!ok) break;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// W [3,3,Cout=32,Cin<=8] fp32 -> five paired-tap B images [mma][chunk(2)][n = co][8 = ci]
+__global__ void tc_prep_convT_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+  // (kh,kw) of chunk 0 / chunk 1 of each MMA; -1 = zero weights
+  const int taps[5][2] = {{8, 6}, {2, 0}, {7, 1}, {5, 3}, {4, -1}};
+  const int total = 5 * 2 * 32 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % 8;
+    const int n = (i / 8) % 32;
+    const int kc = (i / 256) % 2;
+    const int m = i / 512;
+    const int tap = taps[m][kc];
+    const float v = (tap >= 0 && j < Cin && n < Cout) ? w[((int64_t)tap * Cout + n) * Cin + j] : 0.f;
+    img[i] = __float2bfloat16(v);
+  }
+}
+
+// fp32 NHWC with C <= 8 channels -> bf16 NHWC padded to 8 channels (16 bytes per pixel)
+__global__ void pack_c8_bf16_kernel(const float* in, int64_t npix, int C, uint4* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = c < C ? in[i * C + c] : 0.f;
+    uint32_t w4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+      w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    out[i] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n) {
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -637,6 +830,51 @@ int tc_out_wgrad(const void* dl8_bf16, const void* act_bf16, float* dW, float* p
   cudaFuncSetAttribute(tc_out_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_out_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
   sum_partials_kernel<<<cdiv(E, 256), 256, 0, st>>>(partial, grid, E, dW);
+  return 0;
+}
+
+bool tc_convT_fwd_supported(int Cin, int Cout) { return Cin >= 1 && Cin <= 8 && Cout == 32; }
+size_t tc_convT_weight_image_elems() { return (size_t)5 * 2 * 32 * 8; }
+
+void pack_c8_bf16(const float* in, int64_t npix, int C, void* out, cudaStream_t st) {
+  ProfScope prof_("pack_c8", st);
+  ++g_launches;
+  pack_c8_bf16_kernel<<<grid_for(npix, 256, 8, 2), 256, 0, st>>>(in, npix, C, reinterpret_cast<uint4*>(out));
+}
+
+void tc_prep_convT_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
+  ProfScope prof_("tc_prep_weights", st);
+  ++g_launches;
+  tc_prep_convT_weights_kernel<<<4, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+}
+
+// out[B,2h,2w,32] bf16 = relu(bias + convT_s2(in8[B,h,w,8] bf16))
+int tc_convT_fwd(const void* in8_bf16, const void* wimg, const float* bias, void* out_bf16, int B, int h, int w,
+                 int* error_flag, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {16, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
+  const cuuint32_t box[4] = {8, PW, PR, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in8_bf16), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 2;
+  ConvTParams p{};
+  p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
+  p.bias = bias; p.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.B = B; p.h = h; p.w = w;
+  p.tiles_y = cdiv(h, TR); p.tiles_x = cdiv(w, TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const size_t smem = (size_t)kStages * ((size_t)NPIX * 16 + 128) + (size_t)5 * 2 * 32 * 16;
+  ProfScope prof_("tc_convT_fwd", st);
+  ++g_launches;
+  cudaFuncSetAttribute(tc_convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_convT_fwd_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
   return 0;
 }
 

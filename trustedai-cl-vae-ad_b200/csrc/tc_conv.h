@@ -20,6 +20,14 @@ void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img_bf16, cu
 int tc_out_dgrad(const void* dl8_bf16, const void* wimg_bf16, const void* mask_bf16, float* g_out, int B, int H, int W,
                  int Cin, int* error_flag, cudaStream_t st);
 
+// Conv2DTranspose s2 (Cin <= 8 -> 32) + bias + ReLU by sub-pixel phases; bf16 NHWC output
+bool tc_convT_fwd_supported(int Cin, int Cout);
+size_t tc_convT_weight_image_elems();
+void pack_c8_bf16(const float* in, int64_t npix, int C, void* out_bf16x8, cudaStream_t st);
+void tc_prep_convT_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
+int tc_convT_fwd(const void* in8_bf16, const void* wimg_bf16, const float* bias, void* out_bf16, int B, int h, int w,
+                 int* error_flag, cudaStream_t st);
+
 // output-layer weight gradient (MN-major tcgen05, K = pixels); partial >= tc_out_wgrad_partial_floats()
 bool tc_out_wgrad_supported(int Cin, int Cout);
 size_t tc_out_wgrad_partial_floats(int Cin, int Cout);
