@@ -250,12 +250,6 @@ def test_tc_backward_parity(shape):
     d, grads = m.loss_and_grads(x, eps=eps)
     assert m.tc_status() == 1
     d32, grads32 = m32.loss_and_grads(x, eps=eps)
-    L = len(cfg["model"]["layers"])
-    ga, ga32 = m.debug_activation(301 + L), m32.debug_activation(301 + L)    # d loss / d a_last
-    # element-wise: ReLU masks of near-zero pre-activations may flip between bf16 and fp32
-    # arithmetic, so bound the fraction of disagreeing elements instead of the max
-    bad = np.abs(ga - ga32) > 2e-2 * np.abs(ga32).max()
-    assert bad.mean() < 2e-3, bad.mean()
     od, ograds, _, _ = O.loss_and_grads(cfg, ws, x, eps)
     assert_metrics_close(d, od, rtol=1e-3, atol=1e-6)
     for (n, _), g, og in zip(O.variable_shapes(cfg), grads, ograds):

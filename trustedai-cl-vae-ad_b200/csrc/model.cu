@@ -110,7 +110,9 @@ struct kcvae_model {
   float *minmax = nullptr, *metrics_dev = nullptr;
   // tensor-core path (precision == BF16_TC): bf16 copy of the last decoder activation, UMMA
   // weight image of the output layer, device-side error flag of the bounded barrier waits
-  bool use_tc_out = false, use_tc_dgrad = false, use_tc_convT = false;
+  bool use_tc_out = false, use_tc_dgrad = false, use_tc_convT = false, use_tc_convT_bwd = false;
+  void* g_s2d = nullptr;         // bf16 space-to-depth d loss / d a_last [B,H/2,W/2,4,32]
+  void* wimg_convT_dgrad = nullptr;
   void* a_prev8 = nullptr;       // bf16 input of the last Conv2DTranspose s2, NHWC padded to 8 channels
   void* wimg_convT = nullptr;
   uint16_t* dl8 = nullptr;       // bf16 d(loss)/d(logit), NHWC padded to 8 channels
@@ -242,6 +244,8 @@ size_t max_partial_floats(const kcvae_model* h, int B) {
   up(score_partial_floats(B, (int64_t)h->H * h->W));
 #ifndef KCVAE_EMU
   if (h->use_tc_dgrad) up(tc_out_wgrad_partial_floats(h->dc[L], h->C));
+  if (h->use_tc_convT_bwd) up(tc_convT_wgrad_partial_floats(h->dc[L - 1]));
+  if (h->use_tc_dgrad) up((size_t)kNumSMs * 4 * 32);
 #endif
   return mx;
 }
@@ -296,6 +300,11 @@ int ensure_bwd(kcvae_model* h, int B) {
   KC_TRY(dalloc(h, &h->g_z, (size_t)Bc * h->latent));
   KC_TRY(dalloc(h, &h->dhead, (size_t)Bc * 2 * h->latent));
   KC_TRY(dalloc(h, &h->g_d1, (size_t)Bc * (h->enc_dense ? h->enc_dense : 1)));
+  if (h->use_tc_convT_bwd) {
+    unsigned short* gs = reinterpret_cast<unsigned short*>(h->g_s2d);
+    KC_TRY(dalloc(h, &gs, (size_t)Bc * h->H * h->W * h->dc[L]));
+    h->g_s2d = gs;
+  }
   if (h->use_tc_dgrad) {
     KC_TRY(dalloc(h, &h->dl8, (size_t)Bc * h->H * h->W * 8));
     KC_CUDA(h, cudaMemset(h->dl8, 0, (size_t)Bc * h->H * h->W * 8 * sizeof(uint16_t)));   // channel padding stays zero
@@ -481,6 +490,7 @@ void run_finalize(kcvae_model* h, int B, int tier, float* d_metrics, cudaStream_
 void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
   const int L = h->L;
   const int Bg = B * h->world;
+  bool tail_s2d = false;   // d loss / d a_last lives as bf16 space-to-depth (tensor-core tail)
   {  // output Conv2DTranspose (s1): wgrad, bias grad, dgrad (+ReLU mask of its input)
     const int vi = h->vi_out();
     WgradArgs wa{};
@@ -505,7 +515,14 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
 #ifndef KCVAE_EMU
     if (h->use_tc_dgrad && h->use_tc_out) {  // tcgen05 paired-tap implicit GEMM (tc_conv.cu)
       tc_prep_dgrad_weights(a.w, h->C, h->dc[L], h->wimg_dgrad, st);
-      done = tc_out_dgrad(h->dl8, h->wimg_dgrad, h->a_last_bf16, h->g_act_d[L], B, h->H, h->W, h->dc[L], h->tc_error, st) == 0;
+      const bool s2d = h->use_tc_convT_bwd && h->use_tc_convT;
+      // with the tensor-core Conv2DTranspose backward the gradient never exists in fp32: it is
+      // written as bf16 space-to-depth and its channel sums (= that layer's bias gradient) come
+      // out of the same epilogue
+      done = tc_out_dgrad(h->dl8, h->wimg_dgrad, h->a_last_bf16, s2d ? nullptr : h->g_act_d[L], s2d ? h->g_s2d : nullptr,
+                          s2d ? h->gp(h->vi_dec_convT(L - 1) + 1) : nullptr, h->partial, B, h->H, h->W, h->dc[L],
+                          h->tc_error, st) == 0;
+      tail_s2d = done && s2d;
     }
 #endif
     if (!done) conv_forward(CONV_S1, EPI_MASK, a, st);
@@ -519,6 +536,16 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     wa.s = 2; wa.d = 1; wa.oy = 0; wa.ox = 0;
     wa.o_sa = 1; wa.o_sb = wa.Ca;  // [tap][out=b][in=a]
     g_tag = l == L - 1 ? "dec.convT_last.bwd" : "dec.convT.bwd";
+#ifndef KCVAE_EMU
+    if (l == L - 1 && tail_s2d) {
+      bool ok = tc_convT_wgrad(h->g_s2d, h->a_prev8, h->gp(vi), h->partial, B, h->dh[l], h->dw[l], h->dc[l], h->tc_error, st) == 0;
+      tc_prep_convT_dgrad_weights(h->wp(vi), h->dc[l + 1], h->dc[l], h->wimg_convT_dgrad, st);
+      ok = ok && tc_convT_dgrad(h->g_s2d, h->wimg_convT_dgrad, h->act_d[l], h->g_act_d[l], B, h->dh[l], h->dw[l], h->dc[l],
+                                h->tc_error, st) == 0;
+      if (!ok) h->err = "tc_convT backward: tensor map encode failed";
+      continue;   // bias gradient was produced by tc_out_dgrad
+    }
+#endif
     conv_wgrad(wa, st);
     colsum(h->g_act_d[l + 1], (int64_t)B * h->dh[l + 1] * h->dw[l + 1], h->dc[l + 1], h->gp(vi + 1), h->partial, st);
     ConvArgs a{};
@@ -693,6 +720,13 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
       h->wimg_convT = wc;
       h->use_tc_convT = true;
     }
+    if (h->use_tc_convT && tc_convT_bwd_supported(h->dc[h->L - 1], h->dc[h->L], h->dh[h->L - 1], h->dw[h->L - 1]) &&
+        tc_out_dgrad_supported(h->dc[h->L], h->C)) {
+      unsigned short* wd2 = nullptr;
+      if ((rc = dalloc(h, &wd2, tc_convT_dgrad_weight_image_elems()))) return bail(rc);
+      h->wimg_convT_dgrad = wd2;
+      h->use_tc_convT_bwd = true;
+    }
     if (tc_out_dgrad_supported(h->dc[h->L], h->C)) {
       unsigned short* wd = nullptr;
       if ((rc = dalloc(h, &wd, tc_dgrad_weight_image_elems()))) return bail(rc);
@@ -725,6 +759,8 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->wimg_out) cudaFree(h->wimg_out);
   if (h->wimg_dgrad) cudaFree(h->wimg_dgrad);
   if (h->wimg_convT) cudaFree(h->wimg_convT);
+  if (h->wimg_convT_dgrad) cudaFree(h->wimg_convT_dgrad);
+  if (h->g_s2d) cudaFree(h->g_s2d);
   if (h->a_prev8) cudaFree(h->a_prev8);
   if (h->dl8) cudaFree(h->dl8);
   if (h->tc_error) cudaFree(h->tc_error);

@@ -52,6 +52,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
 }
 
+__global__ void sum_partials_kernel(const float* partial, int nparts, int E, float* out);
+
 struct OutConvParams {
   const __nv_bfloat16* wimg;  // [9 taps][CIN/16][2 chunks][NPAD][8] bf16 (tc_prep_out_weights)
   const float* bias;          // [Cout]
@@ -219,7 +221,9 @@ __global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __
 struct OutDgradParams {
   const __nv_bfloat16* wimg;   // [5 pairs][2][NPAD_D][8]
   const __nv_bfloat16* mask;   // forward activation a (bf16 NHWC, Cin channels)
-  float* g_out;                // [B,H,W,Cin] fp32
+  float* g_out;                // [B,H,W,Cin] fp32 (or nullptr)
+  __nv_bfloat16* g_s2d;        // [B,H/2,W/2,4,Cin] bf16 space-to-depth (or nullptr): parity (y&1)*2+(x&1)
+  float* chan_partial;         // [grid*4][32] per-warp channel sums of g (bias gradient of the producer) or nullptr
   int B, H, W, Cin;
   int tiles_y, tiles_x, num_tiles;
   int* error_flag;
@@ -304,6 +308,9 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
     }
   } else {
     const int lg = warp & 3;
+    float csum[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) csum[c] = 0.f;
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int a = it & 1;
@@ -325,7 +332,12 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
         if (c < TW && oy < p.H && ox < p.W) {
           const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
           const uint4* mk = reinterpret_cast<const uint4*>(p.mask + pix * p.Cin);
-          float4* o = reinterpret_cast<float4*>(p.g_out + pix * p.Cin);
+          float4* o = p.g_out ? reinterpret_cast<float4*>(p.g_out + pix * p.Cin) : nullptr;
+          uint4* o2 = nullptr;
+          if (p.g_s2d) {
+            const int64_t lp = ((int64_t)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
+            o2 = reinterpret_cast<uint4*>(p.g_s2d + (lp * 4 + ((oy & 1) * 2 + (ox & 1))) * p.Cin);
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (g * 8 < p.Cin) {
@@ -338,9 +350,21 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
                 const uint32_t h16 = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
                 const bool pos = (h16 & 0x8000u) == 0 && (h16 & 0x7FFFu) != 0;
                 y[j] = pos ? v[g * 8 + j] : 0.f;
+                csum[g * 8 + j] += y[j];
               }
-              o[g * 2] = make_float4(y[0], y[1], y[2], y[3]);
-              o[g * 2 + 1] = make_float4(y[4], y[5], y[6], y[7]);
+              if (o) {
+                o[g * 2] = make_float4(y[0], y[1], y[2], y[3]);
+                o[g * 2 + 1] = make_float4(y[4], y[5], y[6], y[7]);
+              }
+              if (o2) {
+                uint32_t w4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(y[2 * e], y[2 * e + 1]);
+                  w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                o2[g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              }
             }
           }
         }
@@ -348,6 +372,15 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+    if (p.chan_partial) {   // deterministic: fixed per-thread order, then a fixed shuffle tree
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float t = csum[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) p.chan_partial[((int64_t)blockIdx.x * 4 + lg) * 32 + c] = t;
+      }
     }
   }
   fence_before_sync();
@@ -714,6 +747,296 @@ __global__ void pack_c8_bf16_kernel(const float* in, int64_t npix, int C, uint4*
   }
 }
 
+// ============================================================================================
+// Backward of the last Conv2DTranspose s2 (Cin <= 8 -> 32) on tensor cores.  The incoming
+// gradient G = d loss / d a_last arrives from tc_out_dgrad as bf16 *space-to-depth*
+// [B,h,w,4 parities,32]: tap (kh,kw) of the stride-2 gather  G[2i+kh, 2j+kw]  is then parity
+// plane (kh&1, kw&1) at the low-resolution shift (kh>>1, kw>>1) - again plain descriptor start
+// offsets into one TMA-loaded tile of 16 chunk planes (rows 0..TRD, one halo row/column at the
+// bottom/right; TMA zero fill = the cropped transposed-conv border).
+constexpr int TRD = 8;                           // low-res rows per tile
+constexpr int GROWS = TRD + 1;
+constexpr uint32_t CHD = GROWS * PW * 16;        // bytes per chunk plane of the G tile
+constexpr uint32_t GT_BYTES = 16 * CHD;          // 16 chunk planes
+constexpr int MTD = (TRD * PW) / 128;            // 2 M-tiles
+
+struct ConvTBwdParams {
+  const __nv_bfloat16* wimg;     // dgrad: [9 taps][2 ks][2 chunks][16][8]
+  const float* mask;             // dgrad: previous activation fp32 [B,h,w,Cin]
+  float* g_prev;                 // dgrad: [B,h,w,Cin] fp32
+  const __nv_bfloat16* a_prev8;  // wgrad: previous activation bf16 [B,h,w,8]
+  float* partial;                // wgrad: [grid][9*32*Cin]
+  int B, h, w, Cin;
+  int tiles_y, tiles_x, num_tiles;
+  int* error_flag;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_convT_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p) {
+  constexpr uint32_t STAGE = GT_BYTES + 128;
+  constexpr uint32_t WB = 9 * 2 * 2 * 16 * 16;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* s_w = smem + kStages * STAGE;
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreads)
+    reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
+  if (threadIdx.x < kStages * 8) {
+    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
+    reinterpret_cast<uint4*>(smem + s * STAGE + GT_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<64>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / (p.tiles_y * p.tiles_x);
+        const int rem = t % (p.tiles_y * p.tiles_x);
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        mbar_expect_tx(&full_bar[s], GT_BYTES);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          tma_load_4d(smem + s * STAGE + c * CHD, &tmap, &full_bar[s], c * 8, tx * TW, ty * TRD, n);
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16_f32(128, 16);
+    const uint64_t db0 = make_desc_kmajor_noswz(smem_u32(s_w), 16 * 16, 128);
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages, a = it & 1;
+      const uint32_t ph = (it / kStages) & 1, aph = (it >> 1) & 1;
+      if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { if (leader) *p.error_flag = 1; break; }
+      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; break; }
+      fence_after_sync();
+      const uint64_t da0 = make_desc_kmajor_noswz(smem_u32(smem + s * STAGE), CHD, 128);
+#pragma unroll
+      for (int mt = 0; mt < MTD; ++mt) {
+        const uint32_t d_tmem = tmem + (uint32_t)(a * MTD * 16 + mt * 16);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kh = tap / 3, kw = tap % 3;
+          const uint32_t par = (uint32_t)((kh & 1) * 2 + (kw & 1));
+          const uint32_t shift = (uint32_t)((kh >> 1) * PW + (kw >> 1));
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t da = desc_advance(da0, (par * 4 + 2 * ks) * (CHD / 16) + (uint32_t)(mt * 128) + shift);
+            const uint64_t db = desc_advance(db0, (uint32_t)((tap * 2 + ks) * 2 * 16));
+            if (leader) mma_bf16_ss(d_tmem, da, db, idesc, (tap | ks) != 0);
+          }
+        }
+      }
+      if (leader) {
+        mma_commit(&empty_bar[s]);
+        mma_commit(&tfull_bar[a]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int lg = warp & 3;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int n = t / (p.tiles_y * p.tiles_x);
+      const int rem = t % (p.tiles_y * p.tiles_x);
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; break; }
+      fence_after_sync();
+#pragma unroll
+      for (int mt = 0; mt < MTD; ++mt) {
+        float v[8];
+        tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MTD * 16 + mt * 16), v);
+        const int q = mt * 128 + lg * 32 + lane;
+        const int r = q / PW, c = q % PW;
+        const int i = ty * TRD + r, j = tx * TW + c;
+        if (c < TW && i < p.h && j < p.w) {
+          const int64_t pix = ((int64_t)n * p.h + i) * p.w + j;
+#pragma unroll
+          for (int ci = 0; ci < 8; ++ci)
+            if (ci < p.Cin) p.g_prev[pix * p.Cin + ci] = __ldg(p.mask + pix * p.Cin + ci) > 0.f ? v[ci] : 0.f;
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+// W [3,3,Cout=32,Cin<=8] fp32 -> dgrad B image [tap][ks][chunk(2)][n = ci (16)][8 = co]
+__global__ void tc_prep_convT_dgrad_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+  const int total = 9 * 2 * 2 * 16 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % 8;
+    const int n = (i / 8) % 16;
+    const int kc = (i / 128) % 2;
+    const int ks = (i / 256) % 2;
+    const int tap = i / 512;
+    const int co = ks * 16 + kc * 8 + j;
+    const float v = (n < Cin && co < Cout) ? w[((int64_t)tap * Cout + co) * Cin + n] : 0.f;
+    img[i] = __float2bfloat16(v);
+  }
+}
+
+// dW[kh,kw,co,ci] = sum a_prev[i,j,ci] * G[2i+kh, 2j+kw, co] : MN-major, K = low-res pixels.
+// A = zero-padded plane of a_prev (rows -1..TRD) written by the loader warps, M-groups strided
+// by one plane row (group 0 <-> vertical low-res shift 1, group 1 <-> shift 0); B = one parity
+// block of the G tile (N = 32 = 4 chunk planes) started at the horizontal shift.  Six
+// accumulators (parity x horizontal shift) persist in TMEM over the CTA's tiles.
+constexpr int APROWS = TRD + 2;
+constexpr uint32_t AP_BYTES = APROWS * PW * 16;
+constexpr int KSTEPS_D = GROWS * PW / 16;        // 18
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p) {
+  constexpr uint32_t STAGE = AP_BYTES + GT_BYTES + 128;    // [a_prev plane][G tile][pad]
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x < kStages * 8) {
+    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
+    reinterpret_cast<uint4*>(smem + s * STAGE + AP_BYTES + GT_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1 + 4); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / (p.tiles_y * p.tiles_x);
+        const int rem = t % (p.tiles_y * p.tiles_x);
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        mbar_expect_tx(&full_bar[s], GT_BYTES);
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          tma_load_4d(smem + s * STAGE + AP_BYTES + c * CHD, &tmap, &full_bar[s], c * 8, tx * TW, ty * TRD, n);
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16_f32(64, 32, 1, 1);
+    // accumulator a: (parity, horizontal shift) = (0,0) (0,1) | (1,0) | (2,0) (2,1) | (3,0)
+    int it = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
+      fence_after_sync();
+      const uint32_t ap_base = smem_u32(smem + s * STAGE);
+      const uint64_t da0 = make_desc_kmajor_noswz(ap_base, 128, PW * 16);
+      const uint64_t db0 = make_desc_kmajor_noswz(ap_base + AP_BYTES, 128, CHD);
+#pragma unroll 2
+      for (int ks = 0; ks < KSTEPS_D; ++ks) {
+        const uint64_t da = desc_advance(da0, (uint32_t)(ks * 16));
+        const uint32_t acc = (uint32_t)((it | ks) != 0);
+        const uint64_t dbk = desc_advance(db0, (uint32_t)(ks * 16));
+        if (leader) {
+          mma_bf16_ss(tmem + 0, da, desc_advance(dbk, 0 * 4 * (CHD / 16) + 0), idesc, acc);
+          mma_bf16_ss(tmem + 32, da, desc_advance(dbk, 0 * 4 * (CHD / 16) + 1), idesc, acc);
+          mma_bf16_ss(tmem + 64, da, desc_advance(dbk, 1 * 4 * (CHD / 16) + 0), idesc, acc);
+          mma_bf16_ss(tmem + 96, da, desc_advance(dbk, 2 * 4 * (CHD / 16) + 0), idesc, acc);
+          mma_bf16_ss(tmem + 128, da, desc_advance(dbk, 2 * 4 * (CHD / 16) + 1), idesc, acc);
+          mma_bf16_ss(tmem + 160, da, desc_advance(dbk, 3 * 4 * (CHD / 16) + 0), idesc, acc);
+        }
+      }
+      if (leader) mma_commit(&empty_bar[s]);
+      __syncwarp();
+    }
+    if (ok && leader) mma_commit(&done_bar);
+  } else {
+    const int lt = threadIdx.x - 64;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      if (!mbar_wait(&empty_bar[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; break; }
+      const int n = t / (p.tiles_y * p.tiles_x);
+      const int rem = t % (p.tiles_y * p.tiles_x);
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      uint4* dst = reinterpret_cast<uint4*>(smem + s * STAGE);
+      for (int u = lt; u < APROWS * PW; u += 128) {
+        const int rho = u / PW - 1, c = u % PW;
+        const int i = ty * TRD + rho, j = tx * TW + c;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (rho >= 0 && rho < TRD && c < TW && i < p.h && j < p.w)
+          v = __ldg(reinterpret_cast<const uint4*>(p.a_prev8) + ((int64_t)n * p.h + i) * p.w + j);
+        dst[u] = v;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+    if ((warp & 3) == 0 && my_tiles > 0) {     // TMEM lanes 0..15 hold M rows (g, ci)
+      if (mbar_wait(&done_bar, 0)) {
+        fence_after_sync();
+        const int E = 9 * 32 * p.Cin;
+        float* out = p.partial + (int64_t)blockIdx.x * E;
+        const int g = lane >> 3, ci = lane & 7;
+#pragma unroll 1
+        for (int a = 0; a < 6; ++a) {
+          float v[32];
+          const uint32_t ta = tmem + (uint32_t)(a * 32);
+          tmem_ld16(ta, v);
+          tmem_ld16(ta + 16, v + 16);
+          const int par = a < 2 ? 0 : (a == 2 ? 1 : (a < 5 ? 2 : 3));
+          const int dh = (a == 1 || a == 4) ? 1 : 0;
+          const int pa = par >> 1, pb = par & 1;
+          // vertical: parity row 0 -> kh = 2 (group 0) or 0 (group 1); parity row 1 -> kh = 1 (group 1 only)
+          const int kh = pa == 0 ? (g == 0 ? 2 : 0) : 1;
+          const int kw = pb == 0 ? 2 * dh : 1;
+          const bool use = lane < 16 && ci < p.Cin && (pa == 0 || g == 1);
+          if (use) {
+            for (int co = 0; co < 32; ++co) out[((kh * 3 + kw) * 32 + co) * p.Cin + ci] = v[co];
+          }
+        }
+      } else if (lane == 0) {
+        *p.error_flag = 1;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 __global__ void cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n) {
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -770,8 +1093,8 @@ void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img, cudaStr
   tc_prep_dgrad_weights_kernel<<<4, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
 }
 
-int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, float* g_out, int B, int H, int W,
-                 int Cin, int* error_flag, cudaStream_t st) {
+int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, float* g_out, void* g_s2d_bf16,
+                 float* chan_sum, float* chan_partial, int B, int H, int W, int Cin, int* error_flag, cudaStream_t st) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
   CUtensorMap tmap;
@@ -786,7 +1109,7 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   OutDgradParams p{};
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.mask = reinterpret_cast<const __nv_bfloat16*>(mask_bf16);
-  p.g_out = g_out; p.B = B; p.H = H; p.W = W; p.Cin = Cin;
+  p.g_out = g_out; p.g_s2d = reinterpret_cast<__nv_bfloat16*>(g_s2d_bf16); p.B = B; p.H = H; p.W = W; p.Cin = Cin;
   p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
   p.num_tiles = B * p.tiles_y * p.tiles_x;
   p.error_flag = error_flag;
@@ -795,7 +1118,12 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   ProfScope prof_("tc_out_dgrad", st);
   ++g_launches;
   cudaFuncSetAttribute(tc_out_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  p.chan_partial = chan_sum ? chan_partial : nullptr;
   tc_out_dgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  if (chan_sum) {
+    ++g_launches;
+    sum_partials_kernel<<<1, 32, 0, st>>>(chan_partial, grid * 4, Cin, chan_sum);
+  }
   return 0;
 }
 
@@ -875,6 +1203,71 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg, const float* bias, void
   ++g_launches;
   cudaFuncSetAttribute(tc_convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_convT_fwd_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  return 0;
+}
+
+bool tc_convT_bwd_supported(int Cin, int Cout, int h, int w) { return Cin >= 1 && Cin <= 8 && Cout == 32 && h > 0 && w > 0; }
+size_t tc_convT_dgrad_weight_image_elems() { return (size_t)9 * 2 * 2 * 16 * 8; }
+size_t tc_convT_wgrad_partial_floats(int Cin) { return (size_t)kNumSMs * 9 * 32 * Cin; }
+
+static int make_s2d_map(CUtensorMap* tmap, const void* g_s2d, int B, int h, int w) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1;
+  const cuuint64_t gdim[4] = {128, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {256, (cuuint64_t)w * 256, (cuuint64_t)h * w * 256};
+  const cuuint32_t box[4] = {8, PW, GROWS, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g_s2d), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+void tc_prep_convT_dgrad_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
+  ProfScope prof_("tc_prep_weights", st);
+  ++g_launches;
+  tc_prep_convT_dgrad_weights_kernel<<<8, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+}
+
+// g_prev[B,h,w,Cin] = (mask > 0) * stride-2 gather of G (space-to-depth bf16) with W
+int tc_convT_dgrad(const void* g_s2d, const void* wimg, const float* mask, float* g_prev, int B, int h, int w, int Cin,
+                   int* error_flag, cudaStream_t st) {
+  CUtensorMap tmap;
+  if (int rc = make_s2d_map(&tmap, g_s2d, B, h, w)) return rc;
+  ConvTBwdParams p{};
+  p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
+  p.mask = mask; p.g_prev = g_prev; p.B = B; p.h = h; p.w = w; p.Cin = Cin;
+  p.tiles_y = cdiv(h, TRD); p.tiles_x = cdiv(w, TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const size_t smem = (size_t)kStages * ((size_t)GT_BYTES + 128) + (size_t)9 * 2 * 2 * 16 * 16;
+  ProfScope prof_("tc_convT_dgrad", st);
+  ++g_launches;
+  cudaFuncSetAttribute(tc_convT_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_convT_dgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  return 0;
+}
+
+// dW [3,3,32,Cin] from a_prev8 [B,h,w,8] bf16 and G space-to-depth bf16
+int tc_convT_wgrad(const void* g_s2d, const void* a_prev8, float* dW, float* partial, int B, int h, int w, int Cin,
+                   int* error_flag, cudaStream_t st) {
+  CUtensorMap tmap;
+  if (int rc = make_s2d_map(&tmap, g_s2d, B, h, w)) return rc;
+  ConvTBwdParams p{};
+  p.a_prev8 = reinterpret_cast<const __nv_bfloat16*>(a_prev8);
+  p.partial = partial; p.B = B; p.h = h; p.w = w; p.Cin = Cin;
+  p.tiles_y = cdiv(h, TRD); p.tiles_x = cdiv(w, TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const size_t smem = (size_t)kStages * ((size_t)AP_BYTES + GT_BYTES + 128);
+  const int E = 9 * 32 * Cin;
+  ProfScope prof_("tc_convT_wgrad", st);
+  g_launches += 2;
+  cudaFuncSetAttribute(tc_convT_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_convT_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  sum_partials_kernel<<<cdiv(E, 256), 256, 0, st>>>(partial, grid, E, dW);
   return 0;
 }
 
