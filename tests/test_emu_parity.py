@@ -44,6 +44,8 @@ def test_score():
     dict(layers=(4, 3, 5), enc=6, H=16, W=24),           # three layers
     dict(layers=(33,), enc=3, H=6, W=10, dec=9, latent=3),  # channel counts that are not tile-friendly
     dict(layers=(2, 2), enc=2, H=12, W=20, C_=1, latent=1),  # single channel, latent 1
+    dict(layers=(32, 5), enc=6, H=16, W=24, dec=32, latent=6),  # README channel pattern: specialised fp32 kernels
+    dict(layers=(32, 8), enc=0, H=8, W=20, dec=4, latent=4),    # few<->many edge cases (Co = 8, Ci = 4)
 ])
 def test_topologies(shape):
     cfg = small_config(**shape)
@@ -76,3 +78,19 @@ def test_error_behaviour():
     mo.encode(frames(odd, 1))                             # encode alone works, like the reference
     with pytest.raises(Exception, match="divisible"):
         mo.compute_loss(frames(odd, 1))
+
+
+@pytest.mark.parametrize("hw", [(15, 21), (18, 26), (7, 9)])
+def test_encoder_odd_sizes_specialised_kernels(hw):
+    """SAME padding with odd sizes (pad_before = 1) through the specialised conv kernels: the
+    loss cannot broadcast for such sizes (like the reference), but encode() must match."""
+    import numpy as np
+    import torch
+    from kcvae_testlib import O, frames, make
+    cfg = small_config(layers=(32, 5), enc=5, H=hw[0], W=hw[1], dec=8, latent=3)
+    m, ws = make(cfg, BACKEND)
+    x = frames(cfg, 2)
+    mean, lv = m.encode(x)
+    om, olv, _ = O.encoder_forward(O.topology(cfg), [torch.tensor(w) for w in ws], torch.tensor(x))
+    np.testing.assert_allclose(mean.numpy(), om.numpy(), atol=3e-5)
+    np.testing.assert_allclose(lv.numpy(), olv.numpy(), atol=3e-5)

@@ -98,6 +98,315 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(ConvArgs a, int64_t total,
   }
 }
 
+
+// =========================================================================================
+// Specialised fp32 kernels for the channel shapes of the path (one side <= 8 channels, the
+// other 32): same arithmetic as conv3x3_kernel, but a thread owns whole channel vectors of its
+// pixel(s), weights sit in shared memory in [tap][ci][co] order and are read as broadcast
+// float4, so every input value feeds 8-32 FMAs instead of 1.
+// =========================================================================================
+constexpr int MANY = 32;
+
+__device__ __forceinline__ void stage_weights(const ConvArgs& a, float* ws, int cop) {
+  // canonical [tap][ci][cop] (zero padded in co) from the strided source layout
+  const int n = 9 * a.Ci * cop;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int co = i % cop, ci = (i / cop) % a.Ci, tap = i / (cop * a.Ci);
+    ws[i] = co < a.Co ? __ldg(a.w + (int64_t)tap * a.Ci * a.Co + (int64_t)ci * a.w_sci + (int64_t)co * a.w_sco) : 0.f;
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void store_many(const ConvArgs& a, int64_t o, const float* acc, const float* sbias) {
+  float4* dst = reinterpret_cast<float4*>(a.out + o);
+#pragma unroll
+  for (int g = 0; g < MANY / 4; ++g) {
+    float y[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v = acc[g * 4 + e] + sbias[g * 4 + e];
+      if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+      if (EPI == EPI_BIAS_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+      y[e] = v;
+    }
+    if (EPI == EPI_MASK) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(a.mask + o) + g);
+      y[0] = m.x > 0.f ? y[0] : 0.f; y[1] = m.y > 0.f ? y[1] : 0.f;
+      y[2] = m.z > 0.f ? y[2] : 0.f; y[3] = m.w > 0.f ? y[3] : 0.f;
+    }
+    dst[g] = make_float4(y[0], y[1], y[2], y[3]);
+  }
+}
+
+// ---- A: Conv2D s2, Ci <= 8 -> Co = 32.  thread = 2 adjacent output pixels x 32 channels ----
+template <int EPI>
+__global__ void __launch_bounds__(128) conv_s2_few2many_kernel(ConvArgs a, int64_t npairs, int WP) {
+  KC_DYN_SMEM(float, ws);
+  __shared__ float sbias[MANY];
+  stage_weights(a, ws, MANY);
+  if (threadIdx.x < MANY) sbias[threadIdx.x] = (a.bias && EPI != EPI_MASK) ? a.bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < npairs; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int pp = (int)(idx % WP);
+    const int oy = (int)((idx / WP) % a.Ho);
+    const int n = (int)(idx / ((int64_t)WP * a.Ho));
+    const int ox0 = pp * 2;
+    float acc[2][MANY];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int c = 0; c < MANY; ++c) acc[p][c] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = 2 * oy + kh - a.pad_t;
+      if (iy < 0 || iy >= a.Hi) continue;
+      const float* row = a.in + ((int64_t)n * a.Hi + iy) * a.Wi * a.Ci;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ix0 = 2 * ox0 + kw - a.pad_l, ix1 = ix0 + 2;
+        const bool v0 = ix0 >= 0 && ix0 < a.Wi, v1 = ix1 >= 0 && ix1 < a.Wi && ox0 + 1 < a.Wo;
+        const float4* wt = reinterpret_cast<const float4*>(ws + (kh * 3 + kw) * a.Ci * MANY);
+        for (int ci = 0; ci < a.Ci; ++ci) {
+          const float x0 = v0 ? __ldg(row + (int64_t)ix0 * a.Ci + ci) : 0.f;
+          const float x1 = v1 ? __ldg(row + (int64_t)ix1 * a.Ci + ci) : 0.f;
+#pragma unroll
+          for (int g = 0; g < MANY / 4; ++g) {
+            const float4 w = wt[ci * (MANY / 4) + g];
+            acc[0][g * 4 + 0] = fmaf(x0, w.x, acc[0][g * 4 + 0]); acc[1][g * 4 + 0] = fmaf(x1, w.x, acc[1][g * 4 + 0]);
+            acc[0][g * 4 + 1] = fmaf(x0, w.y, acc[0][g * 4 + 1]); acc[1][g * 4 + 1] = fmaf(x1, w.y, acc[1][g * 4 + 1]);
+            acc[0][g * 4 + 2] = fmaf(x0, w.z, acc[0][g * 4 + 2]); acc[1][g * 4 + 2] = fmaf(x1, w.z, acc[1][g * 4 + 2]);
+            acc[0][g * 4 + 3] = fmaf(x0, w.w, acc[0][g * 4 + 3]); acc[1][g * 4 + 3] = fmaf(x1, w.w, acc[1][g * 4 + 3]);
+          }
+        }
+      }
+    }
+    const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox0) * MANY;
+    store_many<EPI>(a, o, acc[0], sbias);
+    if (ox0 + 1 < a.Wo) store_many<EPI>(a, o + MANY, acc[1], sbias);
+  }
+}
+
+// ---- A': Conv2DTranspose s2 gather, Ci <= 8 -> Co = 32.  warp = one output parity phase ----
+template <int EPI>
+__global__ void __launch_bounds__(128) convT_s2_few2many_kernel(ConvArgs a, int64_t nq, int HQ, int WQ) {
+  KC_DYN_SMEM(float, ws);
+  __shared__ float sbias[MANY];
+  stage_weights(a, ws, MANY);
+  if (threadIdx.x < MANY) sbias[threadIdx.x] = (a.bias && EPI != EPI_MASK) ? a.bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int phase = threadIdx.x >> 5, lane = threadIdx.x & 31;   // 4 warps = 4 parity phases
+  const int pa = phase >> 1, pb = phase & 1;
+  for (int64_t q0 = (int64_t)blockIdx.x * 32; q0 < nq; q0 += (int64_t)gridDim.x * 32) {
+    const int64_t q = q0 + lane;
+    if (q >= nq) continue;
+    const int jq = (int)(q % WQ);
+    const int iq = (int)((q / WQ) % HQ);
+    const int n = (int)(q / ((int64_t)WQ * HQ));
+    const int oy = 2 * iq + pa, ox = 2 * jq + pb;
+    if (oy >= a.Ho || ox >= a.Wo) continue;
+    float acc[MANY];
+#pragma unroll
+    for (int c = 0; c < MANY; ++c) acc[c] = 0.f;
+    for (int kh = (pa + a.pad_t) & 1; kh < 3; kh += 2) {
+      const int ty = oy + a.pad_t - kh;
+      if (ty < 0 || (ty >> 1) >= a.Hi) continue;
+      const float* row = a.in + ((int64_t)n * a.Hi + (ty >> 1)) * a.Wi * a.Ci;
+      for (int kw = (pb + a.pad_l) & 1; kw < 3; kw += 2) {
+        const int tx = ox + a.pad_l - kw;
+        if (tx < 0 || (tx >> 1) >= a.Wi) continue;
+        const float* px = row + (int64_t)(tx >> 1) * a.Ci;
+        const float4* wt = reinterpret_cast<const float4*>(ws + (kh * 3 + kw) * a.Ci * MANY);
+        for (int ci = 0; ci < a.Ci; ++ci) {
+          const float x0 = __ldg(px + ci);
+#pragma unroll
+          for (int g = 0; g < MANY / 4; ++g) {
+            const float4 w = wt[ci * (MANY / 4) + g];
+            acc[g * 4 + 0] = fmaf(x0, w.x, acc[g * 4 + 0]);
+            acc[g * 4 + 1] = fmaf(x0, w.y, acc[g * 4 + 1]);
+            acc[g * 4 + 2] = fmaf(x0, w.z, acc[g * 4 + 2]);
+            acc[g * 4 + 3] = fmaf(x0, w.w, acc[g * 4 + 3]);
+          }
+        }
+      }
+    }
+    store_many<EPI>(a, (((int64_t)n * a.Ho + oy) * a.Wo + ox) * MANY, acc, sbias);
+  }
+}
+
+constexpr int FEW = 8;
+template <int EPI>
+__device__ __forceinline__ void store_few(const ConvArgs& a, int64_t o, const float* acc, const float* sbias) {
+#pragma unroll
+  for (int c = 0; c < FEW; ++c) {
+    if (c < a.Co) {
+      float v = acc[c] + sbias[c];
+      if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+      if (EPI == EPI_BIAS_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+      if (EPI == EPI_MASK) v = __ldg(a.mask + o + c) > 0.f ? v : 0.f;
+      a.out[o + c] = v;
+    }
+  }
+}
+__device__ __forceinline__ void fma_4x8(const float4 x, const float4* w, float* acc) {
+  // w: 4 input channels x 8 output channels = 8 float4 (ci-major)
+  const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 w0 = w[i * 2], w1 = w[i * 2 + 1];
+    acc[0] = fmaf(xv[i], w0.x, acc[0]); acc[1] = fmaf(xv[i], w0.y, acc[1]);
+    acc[2] = fmaf(xv[i], w0.z, acc[2]); acc[3] = fmaf(xv[i], w0.w, acc[3]);
+    acc[4] = fmaf(xv[i], w1.x, acc[4]); acc[5] = fmaf(xv[i], w1.y, acc[5]);
+    acc[6] = fmaf(xv[i], w1.z, acc[6]); acc[7] = fmaf(xv[i], w1.w, acc[7]);
+  }
+}
+
+// ---- B1: Conv2D s2, Ci % 4 == 0 -> Co <= 8.  thread = 2 adjacent output pixels x 8 channels ----
+template <int EPI>
+__global__ void __launch_bounds__(128) conv_s2_many2few_kernel(ConvArgs a, int64_t npairs, int WP) {
+  KC_DYN_SMEM(float, ws);
+  __shared__ float sbias[FEW];
+  stage_weights(a, ws, FEW);
+  if (threadIdx.x < FEW) sbias[threadIdx.x] = (a.bias && EPI != EPI_MASK && (int)threadIdx.x < a.Co) ? a.bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int C4 = a.Ci >> 2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < npairs; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int pp = (int)(idx % WP);
+    const int oy = (int)((idx / WP) % a.Ho);
+    const int n = (int)(idx / ((int64_t)WP * a.Ho));
+    const int ox0 = pp * 2;
+    float acc0[FEW], acc1[FEW];
+#pragma unroll
+    for (int c = 0; c < FEW; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = 2 * oy + kh - a.pad_t;
+      if (iy < 0 || iy >= a.Hi) continue;
+      const float* row = a.in + ((int64_t)n * a.Hi + iy) * a.Wi * a.Ci;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ix0 = 2 * ox0 + kw - a.pad_l, ix1 = ix0 + 2;
+        const bool v0 = ix0 >= 0 && ix0 < a.Wi, v1 = ix1 >= 0 && ix1 < a.Wi && ox0 + 1 < a.Wo;
+        const float4* p0 = reinterpret_cast<const float4*>(row + (int64_t)(v0 ? ix0 : 0) * a.Ci);
+        const float4* p1 = reinterpret_cast<const float4*>(row + (int64_t)(v1 ? ix1 : 0) * a.Ci);
+        const float4* wt = reinterpret_cast<const float4*>(ws + (kh * 3 + kw) * a.Ci * FEW);
+        for (int c4 = 0; c4 < C4; ++c4) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 x0 = v0 ? __ldg(p0 + c4) : z;
+          const float4 x1 = v1 ? __ldg(p1 + c4) : z;
+          fma_4x8(x0, wt + c4 * 8, acc0);
+          fma_4x8(x1, wt + c4 * 8, acc1);
+        }
+      }
+    }
+    const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox0) * a.Co;
+    store_few<EPI>(a, o, acc0, sbias);
+    if (ox0 + 1 < a.Wo) store_few<EPI>(a, o + a.Co, acc1, sbias);
+  }
+}
+
+// ---- B2: Conv2DTranspose s2 (pad 0), Ci % 4 == 0 -> Co <= 8.  thread = one input pixel's 2x2 output quad ----
+template <int EPI>
+__global__ void __launch_bounds__(128) convT_s2_many2few_kernel(ConvArgs a, int64_t nq) {
+  KC_DYN_SMEM(float, ws);
+  __shared__ float sbias[FEW];
+  stage_weights(a, ws, FEW);
+  if (threadIdx.x < FEW) sbias[threadIdx.x] = (a.bias && EPI != EPI_MASK && (int)threadIdx.x < a.Co) ? a.bias[threadIdx.x] : 0.f;
+  __syncthreads();
+  const int C4 = a.Ci >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(q % a.Wi);
+    const int i = (int)((q / a.Wi) % a.Hi);
+    const int n = (int)(q / ((int64_t)a.Wi * a.Hi));
+    float acc[4][FEW];
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+      for (int c = 0; c < FEW; ++c) acc[ph][c] = 0.f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di) {
+      if (i - di < 0) continue;
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj) {
+        if (j - dj < 0) continue;
+        const float4* px = reinterpret_cast<const float4*>(a.in + (((int64_t)n * a.Hi + (i - di)) * a.Wi + (j - dj)) * a.Ci);
+        for (int c4 = 0; c4 < C4; ++c4) {
+          const float4 x = __ldg(px + c4);
+#pragma unroll
+          for (int pa = 0; pa < 2 - di; ++pa)            // kh = 2*di + pa <= 2
+#pragma unroll
+            for (int pb = 0; pb < 2 - dj; ++pb) {        // kw = 2*dj + pb <= 2
+              const int tap = (2 * di + pa) * 3 + (2 * dj + pb);
+              fma_4x8(x, reinterpret_cast<const float4*>(ws + tap * a.Ci * FEW) + c4 * 8, acc[pa * 2 + pb]);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) {
+      const int oy = 2 * i + (ph >> 1), ox = 2 * j + (ph & 1);
+      if (oy < a.Ho && ox < a.Wo) store_few<EPI>(a, (((int64_t)n * a.Ho + oy) * a.Wo + ox) * a.Co, acc[ph], sbias);
+    }
+  }
+}
+
+#ifndef KCVAE_EMU
+#define KC_SET_SMEM(k, bytes) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
+#else
+#define KC_SET_SMEM(k, bytes)
+#endif
+#define KC_EPI_SWITCH(KERNEL, ...)                                                               \
+  switch (epi) {                                                                                 \
+    case EPI_BIAS: { auto k = KERNEL<EPI_BIAS>; KC_SET_SMEM(k, smem); KC_LAUNCH(k, grid, 128, smem, st, __VA_ARGS__); break; }           \
+    case EPI_BIAS_RELU: { auto k = KERNEL<EPI_BIAS_RELU>; KC_SET_SMEM(k, smem); KC_LAUNCH(k, grid, 128, smem, st, __VA_ARGS__); break; } \
+    case EPI_BIAS_SIGMOID: { auto k = KERNEL<EPI_BIAS_SIGMOID>; KC_SET_SMEM(k, smem); KC_LAUNCH(k, grid, 128, smem, st, __VA_ARGS__); break; } \
+    default: { auto k = KERNEL<EPI_MASK>; KC_SET_SMEM(k, smem); KC_LAUNCH(k, grid, 128, smem, st, __VA_ARGS__); break; }                 \
+  }
+
+// returns true if a specialised kernel took the launch
+static bool conv_forward_special(int mode, int epi, const ConvArgs& a, cudaStream_t st) {
+  if (a.B <= 0) return false;
+  const bool aligned = ((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.out % 16 == 0) && (!a.mask || (uintptr_t)a.mask % 16 == 0);
+  if (!aligned) return false;
+  if (a.Co == MANY && a.Ci <= 8) {
+    const size_t smem = (size_t)9 * a.Ci * MANY * sizeof(float);
+    if (mode == CONV_S2) {
+      const int WP = cdiv(a.Wo, 2);
+      const int64_t npairs = (int64_t)a.B * a.Ho * WP;
+      const int grid = grid_for(npairs, 128, 4, 16);
+      ++g_launches;
+      KC_EPI_SWITCH(conv_s2_few2many_kernel, a, npairs, WP)
+      return true;
+    }
+    if (mode == CONVT_S2) {
+      const int HQ = cdiv(a.Ho, 2), WQ = cdiv(a.Wo, 2);
+      const int64_t nq = (int64_t)a.B * HQ * WQ;
+      const int grid = grid_for(nq, 32, 4, 16);
+      ++g_launches;
+      KC_EPI_SWITCH(convT_s2_few2many_kernel, a, nq, HQ, WQ)
+      return true;
+    }
+  }
+  if (a.Co <= FEW && a.Ci % 4 == 0 && a.Ci <= 128) {
+    const size_t smem = (size_t)9 * a.Ci * FEW * sizeof(float);
+    if (mode == CONV_S2) {
+      const int WP = cdiv(a.Wo, 2);
+      const int64_t npairs = (int64_t)a.B * a.Ho * WP;
+      const int grid = grid_for(npairs, 128, 8, 16);
+      ++g_launches;
+      KC_EPI_SWITCH(conv_s2_many2few_kernel, a, npairs, WP)
+      return true;
+    }
+    if (mode == CONVT_S2 && a.pad_t == 0 && a.pad_l == 0 && a.Ho == 2 * a.Hi && a.Wo == 2 * a.Wi) {
+      const int64_t nq = (int64_t)a.B * a.Hi * a.Wi;
+      const int grid = grid_for(nq, 128, 4, 16);
+      ++g_launches;
+      KC_EPI_SWITCH(convT_s2_many2few_kernel, a, nq)
+      return true;
+    }
+  }
+  return false;
+}
+
 template <int MODE>
 static void launch_mode(int epi, const ConvArgs& a, cudaStream_t st) {
   const int WG = cdiv(a.Wo, PT);
@@ -115,6 +424,7 @@ static void launch_mode(int epi, const ConvArgs& a, cudaStream_t st) {
 
 void conv_forward(int mode, int epi, const ConvArgs& a, cudaStream_t st) {
   ProfScope prof_("conv3x3", st);
+  if (conv_forward_special(mode, epi, a, st)) return;
   if (mode == CONV_S2) launch_mode<CONV_S2>(epi, a, st);
   else if (mode == CONV_S1) launch_mode<CONV_S1>(epi, a, st);
   else launch_mode<CONVT_S2>(epi, a, st);
