@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(256) wgrad_tiled_kernel(WgradArgs a, int rows,
   const int n_et = 9 * n_at * n_bt;                 // entry tiles
   const int qw = a.s * (SEG - 1) + 3;               // Q pixels per staged row
   float* Ps = sm;                                   // [SEG][Ca]
-  float* Qs = sm + SEG * a.Ca;                      // [3][qw][cbp]
+  float* Qs = sm + ((SEG * a.Ca + 3) & ~3);         // [3][qw][cbp], 16-byte aligned
   const int tid = threadIdx.x;
   const bool active = tid < n_et * nph;
   const int et = active ? tid % n_et : 0, ph = active ? tid / n_et : 0;
@@ -525,32 +525,64 @@ __global__ void __launch_bounds__(256) wgrad_tiled_kernel(WgradArgs a, int rows,
       const int seg = min(SEG, a.Wp - j0);
       const int qx_min = a.s * j0 + dmin + a.ox;
       __syncthreads();
-      {  // stage P segment (contiguous)
+      {  // stage P segment (contiguous in global and in shared memory)
         const float* src = a.P + (((int64_t)r * a.Wp) + j0) * a.Ca;
-        for (int t = tid; t < seg * a.Ca; t += blockDim.x) Ps[t] = __ldg(src + t);
-        for (int t = seg * a.Ca + tid; t < SEG * a.Ca; t += blockDim.x) Ps[t] = 0.f;
+        const int np = seg * a.Ca;
+        if ((np & 3) == 0 && (((uintptr_t)src) & 15) == 0) {
+          const float4* s4 = reinterpret_cast<const float4*>(src);
+          float4* d4 = reinterpret_cast<float4*>(Ps);
+          for (int t = tid; t < (np >> 2); t += blockDim.x) d4[t] = __ldg(s4 + t);
+        } else {
+          for (int t = tid; t < np; t += blockDim.x) Ps[t] = __ldg(src + t);
+        }
+        for (int t = np + tid; t < SEG * a.Ca; t += blockDim.x) Ps[t] = 0.f;
       }
-      for (int k = 0; k < 3; ++k) {  // stage the 3 Q rows (zero outside the image)
-        const int qy = a.s * i + a.d * k + a.oy;
-        const bool vrow = qy >= 0 && qy < a.Hq;
-        const float* src = a.Q + (((int64_t)n * a.Hq + (vrow ? qy : 0)) * a.Wq) * a.Cb;
-        float* dst = Qs + (int64_t)k * qw * cbp;
-        for (int t = tid; t < qw * a.Cb; t += blockDim.x) {
-          const int px = t / a.Cb, c = t % a.Cb;
-          const int qx = qx_min + px;
-          dst[px * cbp + c] = (vrow && qx >= 0 && qx < a.Wq) ? __ldg(src + (int64_t)qx * a.Cb + c) : 0.f;
+      {  // stage the 3 Q rows (zero outside the image); (px, c) advanced incrementally, no div/mod
+        const int step_px = blockDim.x / a.Cb, step_c = blockDim.x % a.Cb;
+        for (int k = 0; k < 3; ++k) {
+          const int qy = a.s * i + a.d * k + a.oy;
+          const bool vrow = qy >= 0 && qy < a.Hq;
+          const float* src = a.Q + (((int64_t)n * a.Hq + (vrow ? qy : 0)) * a.Wq) * a.Cb;
+          float* dst = Qs + (int64_t)k * qw * cbp;
+          int px = tid / a.Cb, c = tid % a.Cb;
+          while (px < qw) {
+            const int qx = qx_min + px;
+            dst[px * cbp + c] = (vrow && qx >= 0 && qx < a.Wq) ? __ldg(src + (int64_t)qx * a.Cb + c) : 0.f;
+            px += step_px; c += step_c;
+            if (c >= a.Cb) { c -= a.Cb; ++px; }
+          }
         }
       }
       __syncthreads();
       if (active) {
         const float* qrow = Qs + (int64_t)kh * qw * cbp + (a.d * kw - dmin) * cbp + b0;
+        const bool pvec = (RA % 4 == 0) && ((a.Ca & 3) == 0) && (a0 + RA <= a.Ca);
+        const bool qvec = (RB % 4 == 0) && ((cbp & 3) == 0) && (b0 + RB <= a.Cb);
+#pragma unroll 2
         for (int j = ph; j < seg; j += nph) {
           float pv[RA], qv[RB];
+          const float* pp = Ps + j * a.Ca + a0;
+          if (pvec) {
 #pragma unroll
-          for (int x = 0; x < RA; ++x) pv[x] = (a0 + x < a.Ca) ? Ps[j * a.Ca + a0 + x] : 0.f;
+            for (int x = 0; x < RA / 4; ++x) {
+              const float4 v = reinterpret_cast<const float4*>(pp)[x];
+              pv[x * 4] = v.x; pv[x * 4 + 1] = v.y; pv[x * 4 + 2] = v.z; pv[x * 4 + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int x = 0; x < RA; ++x) pv[x] = (a0 + x < a.Ca) ? pp[x] : 0.f;
+          }
           const float* qp = qrow + (int64_t)(a.s * j) * cbp;
+          if (qvec) {
 #pragma unroll
-          for (int y = 0; y < RB; ++y) qv[y] = (b0 + y < a.Cb) ? qp[y] : 0.f;
+            for (int y = 0; y < RB / 4; ++y) {
+              const float4 v = reinterpret_cast<const float4*>(qp)[y];
+              qv[y * 4] = v.x; qv[y * 4 + 1] = v.y; qv[y * 4 + 2] = v.z; qv[y * 4 + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int y = 0; y < RB; ++y) qv[y] = (b0 + y < a.Cb) ? qp[y] : 0.f;
+          }
 #pragma unroll
           for (int x = 0; x < RA; ++x)
 #pragma unroll
@@ -579,19 +611,18 @@ __global__ void __launch_bounds__(256) wgrad_tiled_kernel(WgradArgs a, int rows,
 struct WgradPlan { int ra, rb, n_at, n_bt, nph, seg, cbp, blocks, rpc; size_t smem; bool ok; };
 static WgradPlan wgrad_plan(int B, int Hp, int Wp, int Ca, int Cb, int s) {
   WgradPlan p{};
-  if (Ca == 3) { p.ra = 3; p.rb = 8; }
-  else if (Ca == 5) { p.ra = 5; p.rb = 4; }
-  else if (Cb == 3) { p.ra = 8; p.rb = 3; }
-  else if (Cb == 5) { p.ra = 4; p.rb = 5; }
+  if (Ca == 3 && Cb % 8 == 0) { p.ra = 3; p.rb = 8; }
+  else if (Ca == 5 && Cb % 8 == 0) { p.ra = 5; p.rb = 8; }
+  else if (Cb == 3 && Ca % 8 == 0) { p.ra = 8; p.rb = 3; }
+  else if (Cb == 5 && Ca % 8 == 0) { p.ra = 8; p.rb = 5; }
   else { p.ra = 4; p.rb = 4; }
   p.n_at = cdiv(Ca, p.ra); p.n_bt = cdiv(Cb, p.rb);
   const int n_et = 9 * p.n_at * p.n_bt;
   p.nph = 256 / n_et;
-  p.seg = s == 1 ? 64 : 32;
-  if (p.seg > Wp) p.seg = Wp;
+  p.seg = Wp < 160 ? Wp : 160;                     // whole rows when they fit
   p.cbp = Cb % 4 == 0 ? Cb + 4 : Cb + 1;            // de-phase the taps' bank mapping
   const int qw = s * (p.seg - 1) + 3;
-  const size_t stage = (size_t)p.seg * Ca + (size_t)3 * qw * p.cbp;
+  const size_t stage = (size_t)(((size_t)p.seg * Ca + 3) & ~(size_t)3) + (size_t)3 * qw * p.cbp;
   const size_t fold = (size_t)(p.nph > 0 ? p.nph : 1) * 9 * Ca * Cb;
   p.smem = (stage > fold ? stage : fold) * sizeof(float);
   p.ok = p.nph >= 1 && p.smem <= 200 * 1024;
@@ -622,9 +653,9 @@ void conv_wgrad(const WgradArgs& a, cudaStream_t st) {
     KC_LAUNCH(k, pl.blocks, 256, pl.smem, st, a, rows_t, pl.rpc, pl.seg, pl.n_at, pl.n_bt, pl.nph, pl.cbp); \
   }
     if (pl.ra == 3 && pl.rb == 8) KC_WG_LAUNCH(3, 8)
-    else if (pl.ra == 5 && pl.rb == 4) KC_WG_LAUNCH(5, 4)
+    else if (pl.ra == 5 && pl.rb == 8) KC_WG_LAUNCH(5, 8)
     else if (pl.ra == 8 && pl.rb == 3) KC_WG_LAUNCH(8, 3)
-    else if (pl.ra == 4 && pl.rb == 5) KC_WG_LAUNCH(4, 5)
+    else if (pl.ra == 8 && pl.rb == 5) KC_WG_LAUNCH(8, 5)
     else KC_WG_LAUNCH(4, 4)
 #undef KC_WG_LAUNCH
 #undef KC_WG_ATTR
