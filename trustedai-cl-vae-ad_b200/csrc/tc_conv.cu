@@ -34,6 +34,7 @@ constexpr int MT = (TR * PW) / 128;        // 8 M-tiles of 128 padded-row positi
 constexpr int NPAD = 16;                   // UMMA N (Cout padded)
 constexpr int kStages = 2;
 constexpr int kThreads = 192;
+constexpr int kThreadsE = 320;            // kernels with a per-tile epilogue: 2 + 8 warps (two epilogue warps per TMEM lane group)
 static_assert(TR * PW == MT * 128, "tile must be a whole number of M=128 tiles");
 
 // 4-D tiled TMA load: box (8 channels, PW cols, PR rows, 1 image) -> one [pixel] x 16 B chunk plane
@@ -65,7 +66,7 @@ struct OutConvParams {
 };
 
 template <int CIN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsE, 1)
 tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
   constexpr int KC = CIN / 8;                        // 16-byte channel chunks
   constexpr int KS = CIN / 16;                       // K=16 steps per tap
@@ -82,7 +83,7 @@ tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time setup -------------------------------------------------------------------
-  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreads)
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreadsE)
     reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
   if (threadIdx.x < NPAD) s_bias[threadIdx.x] = (int)threadIdx.x < p.Cout ? p.bias[threadIdx.x] : 0.f;
   // the 2 units past each stage's tile are only ever read into discarded columns: zero them
@@ -93,7 +94,7 @@ tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
   if (warp == 0) tmem_alloc<256>(&tmem_slot);
   if (threadIdx.x == 32) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     fence_mbar_init();
   }
   fence_async_smem();
@@ -157,6 +158,7 @@ tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
   } else {
     // ================================ epilogue warps ======================================
     const int lg = warp & 3;                      // TMEM lane group this warp may access
+    const int half = (warp - 2) >> 2;             // two warps per lane group take alternate M-tiles
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int a = it & 1;
@@ -167,7 +169,7 @@ tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
       if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; break; }
       fence_after_sync();
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int mt = half; mt < MT; mt += 2) {
         float v[8];
         tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MT * NPAD + mt * NPAD), v);
         const int q = mt * 128 + lg * 32 + lane;  // padded-row position
@@ -230,7 +232,7 @@ struct OutDgradParams {
 };
 constexpr int NPAD_D = 32;
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsE, 1)
 tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) {
   constexpr uint32_t CH = NPIX * 16;
   constexpr uint32_t TILE_BYTES = CH;                 // one 8-channel chunk plane
@@ -243,7 +245,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreads)
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreadsE)
     reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
   if (threadIdx.x < kStages * 8) {
     const int s = threadIdx.x / 8, j = threadIdx.x % 8;
@@ -252,7 +254,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   if (threadIdx.x == 32) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     fence_mbar_init();
   }
   fence_async_smem();
@@ -308,6 +310,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
     }
   } else {
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
     float csum[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) csum[c] = 0.f;
@@ -321,7 +324,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; break; }
       fence_after_sync();
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int mt = half; mt < MT; mt += 2) {
         float v[32];
         const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MT * NPAD_D + mt * NPAD_D);
         tmem_ld16(ta, v);
@@ -379,7 +382,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
         float t = csum[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) p.chan_partial[((int64_t)blockIdx.x * 4 + lg) * 32 + c] = t;
+        if (lane == 0) p.chan_partial[((int64_t)blockIdx.x * 8 + half * 4 + lg) * 32 + c] = t;
       }
     }
   }
@@ -572,7 +575,7 @@ struct ConvTParams {
   int* error_flag;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsE, 1)
 tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
   constexpr uint32_t TILE_BYTES = NPIX * 16;          // one 8-channel plane, 34 x 32 pixels
   constexpr uint32_t STAGE = TILE_BYTES + 128;
@@ -585,7 +588,7 @@ tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
   __shared__ float s_bias[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreads)
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreadsE)
     reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
   if (threadIdx.x < 32) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (threadIdx.x < kStages * 8) {
@@ -595,7 +598,7 @@ tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
   if (warp == 0) tmem_alloc<256>(&tmem_slot);
   if (threadIdx.x == 32) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
     fence_mbar_init();
   }
   fence_async_smem();
@@ -663,6 +666,7 @@ tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
     }
   } else {
     const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;             // half 0: output rows 2i (phases 0,1); half 1: rows 2i+1
     const int H2 = 2 * p.h, W2 = 2 * p.w;
     int it = 0, mcount = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
@@ -681,7 +685,7 @@ tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
         const int i = ty * TR + r, j = tx * TW + c;
         const bool valid = c < TW && i < p.h && j < p.w;
 #pragma unroll
-        for (int phs = 0; phs < 4; ++phs) {
+        for (int phs = 2 * half; phs < 2 * half + 2; ++phs) {
           float v[32];
           const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * 128 + phs * 32);
           tmem_ld16(ta, v);
@@ -1119,10 +1123,10 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   ++g_launches;
   cudaFuncSetAttribute(tc_out_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   p.chan_partial = chan_sum ? chan_partial : nullptr;
-  tc_out_dgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  tc_out_dgrad_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
   if (chan_sum) {
     ++g_launches;
-    sum_partials_kernel<<<1, 32, 0, st>>>(chan_partial, grid * 4, Cin, chan_sum);
+    sum_partials_kernel<<<1, 32, 0, st>>>(chan_partial, grid * 8, Cin, chan_sum);
   }
   return 0;
 }
@@ -1202,7 +1206,7 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg, const float* bias, void
   ProfScope prof_("tc_convT_fwd", st);
   ++g_launches;
   cudaFuncSetAttribute(tc_convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tc_convT_fwd_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  tc_convT_fwd_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
   return 0;
 }
 
@@ -1298,7 +1302,7 @@ int tc_out_conv(const void* act_bf16, const void* wimg, const float* bias, float
   auto launch = [&](auto kernel, int cin) {
     const size_t smem = (size_t)kStages * ((size_t)(cin / 8) * NPIX * 16 + 128) + (size_t)9 * (cin / 16) * 2 * NPAD * 16;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+    kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
   };
   if (Cin == 16) launch(tc_out_conv_kernel<16>, 16);
   else launch(tc_out_conv_kernel<32>, 32);

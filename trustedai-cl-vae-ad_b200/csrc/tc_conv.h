@@ -19,7 +19,7 @@ size_t tc_dgrad_weight_image_elems();
 void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
 // g_out fp32 NHWC and/or g_s2d bf16 space-to-depth [B,H/2,W/2,4,Cin] (either may be nullptr)
 // chan_sum [Cin] (optional) = sum over all pixels of g = bias gradient of the producing layer;
-// chan_partial >= 148*4*32 floats of scratch
+// chan_partial >= 148*8*32 floats of scratch
 int tc_out_dgrad(const void* dl8_bf16, const void* wimg_bf16, const void* mask_bf16, float* g_out, void* g_s2d_bf16,
                  float* chan_sum, float* chan_partial, int B, int H, int W, int Cin, int* error_flag, cudaStream_t st);
 // backward of the last Conv2DTranspose s2 (Cin <= 8 -> 32) from the space-to-depth gradient
