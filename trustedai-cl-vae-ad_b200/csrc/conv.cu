@@ -445,7 +445,7 @@ static int wgrad_chunks(int B, int Hp, int Ca, int Cb) {
 }
 size_t wgrad_partial_floats(int B, int Hp, int Ca, int Cb) {
   size_t n = (size_t)wgrad_chunks(B, Hp, Ca, Cb);
-  if (n < (size_t)kNumSMs * 2) n = (size_t)kNumSMs * 2;   // the tiled kernel uses <= 2 blocks per SM
+  if (n < (size_t)kNumSMs * 4) n = (size_t)kNumSMs * 4;   // the tiled kernel uses <= 4 blocks per SM
   return n * 9 * Ca * Cb;
 }
 
@@ -537,7 +537,24 @@ __global__ void __launch_bounds__(256) wgrad_tiled_kernel(WgradArgs a, int rows,
         }
         for (int t = np + tid; t < SEG * a.Ca; t += blockDim.x) Ps[t] = 0.f;
       }
-      {  // stage the 3 Q rows (zero outside the image); (px, c) advanced incrementally, no div/mod
+      if ((a.Cb & 3) == 0 && (cbp & 3) == 0 && (((uintptr_t)a.Q) & 15) == 0) {
+        // vectorised staging of the 3 Q rows: one float4 = 4 channels of a pixel
+        const int u_per_px = a.Cb >> 2, cbp4 = cbp >> 2;
+        const int step_px = blockDim.x / u_per_px, step_u = blockDim.x % u_per_px;
+        for (int k = 0; k < 3; ++k) {
+          const int qy = a.s * i + a.d * k + a.oy;
+          const bool vrow = qy >= 0 && qy < a.Hq;
+          const float4* src = reinterpret_cast<const float4*>(a.Q + (((int64_t)n * a.Hq + (vrow ? qy : 0)) * a.Wq) * a.Cb);
+          float4* dst = reinterpret_cast<float4*>(Qs + (int64_t)k * qw * cbp);
+          int px = tid / u_per_px, u = tid % u_per_px;
+          while (px < qw) {
+            const int qx = qx_min + px;
+            dst[px * cbp4 + u] = (vrow && qx >= 0 && qx < a.Wq) ? __ldg(src + (int64_t)qx * u_per_px + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+            px += step_px; u += step_u;
+            if (u >= u_per_px) { u -= u_per_px; ++px; }
+          }
+        }
+      } else {  // scalar staging; (px, c) advanced incrementally, no div/mod
         const int step_px = blockDim.x / a.Cb, step_c = blockDim.x % a.Cb;
         for (int k = 0; k < 3; ++k) {
           const int qy = a.s * i + a.d * k + a.oy;
@@ -627,7 +644,8 @@ static WgradPlan wgrad_plan(int B, int Hp, int Wp, int Ca, int Cb, int s) {
   p.smem = (stage > fold ? stage : fold) * sizeof(float);
   p.ok = p.nph >= 1 && p.smem <= 200 * 1024;
   const int rows = B * Hp;
-  int blocks = kNumSMs * 2;
+  const int per_sm = p.smem <= 48 * 1024 ? 4 : (p.smem <= 70 * 1024 ? 3 : 2);   // co-resident blocks hide the staging
+  int blocks = kNumSMs * per_sm;
   if (blocks > rows) blocks = rows;
   p.rpc = cdiv(rows, blocks);
   p.blocks = cdiv(rows, p.rpc);

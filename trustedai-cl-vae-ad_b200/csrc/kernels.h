@@ -81,6 +81,7 @@ struct ImageStatsArgs {
   float* dlogit;              // [B,P] or nullptr: grad_scale*(xhat-x)*xhat*(1-xhat)
   uint16_t* dl8;              // optional bf16 copy of dlogit as NHWC padded to 8 channels (tensor-core dgrad)
   int C;                      // image channels (for dl8 indexing)
+  float* dbias;               // optional [C]: sum over batch and pixels of d(loss)/d(logit) (output-layer bias gradient)
   float grad_scale;
   int want_ce;                // accumulate S_XHX, S_XH, S_EX
   double* partial;            // workspace >= image_stats_partial_doubles()

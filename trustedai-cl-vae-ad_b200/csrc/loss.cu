@@ -11,17 +11,18 @@ namespace kc {
 
 // ======================================================================= image statistics
 constexpr int kStatBlocks = kNumSMs * 8;
-constexpr int kStatSlots = 8;  // se, xhx, xh, ex, std, min, max, -
+constexpr int kStatSlots = 16;  // se, xhx, xh, ex, std, min, max, -, then 8 per-channel sums of dlogit
 size_t image_stats_partial_doubles() { return (size_t)kStatBlocks * kStatSlots; }
 
 __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
   __shared__ double scratch[32];
   double t_se = 0, t_xhx = 0, t_xh = 0, t_ex = 0, t_std = 0;
+  double t_g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float mn = 3.4e38f, mx = -3.4e38f;
   const bool want_std = a.std_acc != nullptr || a.pos_sums != nullptr;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.P;
        p += (int64_t)gridDim.x * blockDim.x) {
-    float se = 0, xhx = 0, xh = 0, ex = 0;
+    float se = 0, xhx = 0, xh = 0, ex = 0, gsum = 0;
     double sx = 0, sxx = 0, sh = 0, shh = 0;
     for (int b = 0; b < a.B; ++b) {
       const int64_t i = (int64_t)b * a.P + p;
@@ -39,9 +40,10 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
         sx += xv; sxx += (double)xv * xv;
         sh += hv; shh += (double)hv * hv;
       }
-      if (a.dlogit) {
+      if (a.dlogit || a.dl8) {
         const float gl = a.grad_scale * (hv - xv) * hv * (1.0f - hv);
-        a.dlogit[i] = gl;
+        if (a.dlogit) a.dlogit[i] = gl;
+        gsum += gl;
         if (a.dl8) {  // bf16 round-to-nearest-even, channel-padded layout [b][pixel][8]
           const uint32_t u = __float_as_uint(gl);
           const uint32_t rb = u + 0x7FFFu + ((u >> 16) & 1u);
@@ -50,6 +52,11 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
       }
     }
     t_se += se; t_xhx += xhx; t_xh += xh; t_ex += ex;
+    if (a.dbias) {
+      const int ch = (int)(p % a.C);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) t_g[c] += (c == ch) ? (double)gsum : 0.0;
+    }
     if (a.pos_sums) {
       a.pos_sums[p] = sx; a.pos_sums[a.P + p] = sxx;
       a.pos_sums[2 * a.P + p] = sh; a.pos_sums[3 * a.P + p] = shh;
@@ -68,6 +75,12 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
   r = block_sum(t_xh, scratch);  if (threadIdx.x == 0) out[2] = r;
   r = block_sum(t_ex, scratch);  if (threadIdx.x == 0) out[3] = r;
   r = block_sum(t_std, scratch); if (threadIdx.x == 0) out[4] = r;
+  if (a.dbias) {
+    for (int c = 0; c < a.C && c < 8; ++c) {
+      r = block_sum(t_g[c], scratch);
+      if (threadIdx.x == 0) out[8 + c] = r;
+    }
+  }
   // min / max through the same scratch
   __shared__ float fs[64];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -83,7 +96,7 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
 }
 
 __global__ void image_stats_finish_kernel(const double* partial, int blocks, int want_ce,
-                                          double* sums, float* minmax, double* std_acc) {
+                                          double* sums, float* minmax, double* std_acc, float* dbias, int C) {
   __shared__ double scratch[32];
   double v[5] = {0, 0, 0, 0, 0};
   float mn = 3.4e38f, mx = -3.4e38f;
@@ -100,6 +113,14 @@ __global__ void image_stats_finish_kernel(const double* partial, int blocks, int
       if (k == 0) sums[S_SE] = r;
       else if (k < 4) { if (want_ce) sums[S_SE + k] = r; else sums[S_SE + k] = 0.0; }
       else if (std_acc) std_acc[0] = r;
+    }
+  }
+  if (dbias) {
+    for (int c = 0; c < C && c < 8; ++c) {
+      double g = 0;
+      for (int b = threadIdx.x; b < blocks; b += blockDim.x) g += partial[(int64_t)b * kStatSlots + 8 + c];
+      const double r = block_sum(g, scratch);
+      if (threadIdx.x == 0) dbias[c] = (float)r;
     }
   }
   __shared__ float fs[64];
@@ -122,7 +143,7 @@ void image_stats(const ImageStatsArgs& a, cudaStream_t st) {
   g_launches += 2;
   KC_LAUNCH(image_stats_kernel, blocks, 256, 0, st, a);
   KC_LAUNCH(image_stats_finish_kernel, 1, 256, 0, st, a.partial, blocks, a.want_ce, a.sums, a.minmax,
-            a.pos_sums ? nullptr : a.std_acc);
+            a.pos_sums ? nullptr : a.std_acc, a.dbias, a.C);
 }
 
 __global__ void __launch_bounds__(256) image_std_pos_kernel(const double* ps, int64_t P, int B, double* partial) {

@@ -110,6 +110,7 @@ struct kcvae_model {
   float *minmax = nullptr, *metrics_dev = nullptr;
   // tensor-core path (precision == BF16_TC): bf16 copy of the last decoder activation, UMMA
   // weight image of the output layer, device-side error flag of the bounded barrier waits
+  bool tc_failed = false;        // a tensor-core launcher could not run (tensor map encode): the step is invalid
   bool use_tc_out = false, use_tc_dgrad = false, use_tc_convT = false, use_tc_convT_bwd = false;
   void* g_s2d = nullptr;         // bf16 space-to-depth d loss / d a_last [B,H/2,W/2,4,32]
   void* wimg_convT_dgrad = nullptr;
@@ -460,8 +461,12 @@ int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier
   ia.sums = h->sums; ia.minmax = h->minmax;
   ia.std_acc = full ? h->std_acc : nullptr;
   ia.pos_sums = (full && h->world > 1) ? h->pos_sums : nullptr;
-  ia.dlogit = with_grad ? h->dlogit : nullptr;
-  ia.dl8 = (with_grad && h->use_tc_dgrad) ? h->dl8 : nullptr;
+  // tensor-core tail: d(loss)/d(logit) only as bf16 8-channel units, and the output-layer bias
+  // gradient (its channel sums) straight from this pass - no fp32 copy, no colsum pass
+  const bool tc_tail = with_grad && h->use_tc_dgrad && h->use_tc_out && h->C <= 8;
+  ia.dlogit = (with_grad && !tc_tail) ? h->dlogit : nullptr;
+  ia.dl8 = tc_tail ? h->dl8 : nullptr;
+  ia.dbias = tc_tail ? h->gp(h->vi_out() + 1) : nullptr;
   ia.C = h->C;
   ia.grad_scale = (float)(2.0 * (double)h->lw.w_mse / ((double)Bg * (double)h->P));
   ia.want_ce = full && h->cfg.model_type == KCVAE_GLOBAL;
@@ -505,8 +510,11 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
         h->partial_floats >= tc_out_wgrad_partial_floats(h->dc[L], h->C))
       wdone = tc_out_wgrad(h->dl8, h->a_last_bf16, h->gp(vi), h->partial, B, h->H, h->W, h->dc[L], h->C, h->tc_error, st) == 0;
 #endif
-    if (!wdone) conv_wgrad(wa, st);
-    colsum(h->dlogit, (int64_t)B * h->H * h->W, h->C, h->gp(vi + 1), h->partial, st);
+    const bool tc_tail_w = h->use_tc_dgrad && h->use_tc_out && h->C <= 8;
+    if (!wdone && tc_tail_w) h->tc_failed = true;   // no fp32 dlogit exists in this mode
+    if (!wdone && !tc_tail_w) conv_wgrad(wa, st);
+    const bool tc_tail = h->use_tc_dgrad && h->use_tc_out && h->C <= 8;   // bias gradient came from image_stats
+    if (!tc_tail) colsum(h->dlogit, (int64_t)B * h->H * h->W, h->C, h->gp(vi + 1), h->partial, st);
     ConvArgs a{};
     a.in = h->dlogit; a.w = h->wp(vi); a.mask = h->act_d[L]; a.out = h->g_act_d[L];
     a.B = B; a.Hi = h->H; a.Wi = h->W; a.Ci = h->C; a.Ho = h->dh[L]; a.Wo = h->dw[L]; a.Co = h->dc[L];
@@ -525,7 +533,8 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
       tail_s2d = done && s2d;
     }
 #endif
-    if (!done) conv_forward(CONV_S1, EPI_MASK, a, st);
+    if (!done && tc_tail) h->tc_failed = true;
+    if (!done && !tc_tail) conv_forward(CONV_S1, EPI_MASK, a, st);
   }
   for (int l = L - 1; l >= 0; --l) {  // decoder Conv2DTranspose (s2) layers
     const int vi = h->vi_dec_convT(l);
@@ -542,7 +551,7 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
       tc_prep_convT_dgrad_weights(h->wp(vi), h->dc[l + 1], h->dc[l], h->wimg_convT_dgrad, st);
       ok = ok && tc_convT_dgrad(h->g_s2d, h->wimg_convT_dgrad, h->act_d[l], h->g_act_d[l], B, h->dh[l], h->dw[l], h->dc[l],
                                 h->tc_error, st) == 0;
-      if (!ok) h->err = "tc_convT backward: tensor map encode failed";
+      if (!ok) h->tc_failed = true;
       continue;   // bias gradient was produced by tc_out_dgrad
     }
 #endif
@@ -666,6 +675,7 @@ int step_impl(kcvae_model* h, const float* d_x, int B, const float* d_eps, const
   run_forward(h, x, B, 1, d_eps, xh, st);
   KC_TRY(run_stats(h, d_x, xh, B, tier, 1, st));
   run_backward(h, x, B, st);
+  if (h->tc_failed) return fail(h, KCVAE_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed; use precision fp32");
   if (h->world > 1) KC_TRY(allreduce(h, h->g, h->nparams, 0, 0, st));
   if (do_update) KC_TRY(run_adam(h, st));
   run_finalize(h, B, tier, d_metrics ? d_metrics : h->metrics_dev, st);
