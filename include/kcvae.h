@@ -162,6 +162,9 @@ int kcvae_normalize_scores(kcvae_handle h, const float* d_err, const float* d_sc
                            float* d_norm, float* d_z, uint8_t* d_flags, void* stream);
 
 /* ---- host-buffer entry points (H2D / D2H inside the call; end-to-end path) ------------ */
+/* optional pipelining: start the H2D copy of the NEXT call's frames on an internal copy stream
+ * while the current step computes; the next *_host call given the same pointer only waits for it */
+int kcvae_prefetch_host(kcvae_handle h, const float* h_x, int batch);
 /* synchronous: returns after metrics are in h_metrics */
 int kcvae_train_step_host(kcvae_handle h, const float* h_x, int batch, const float* h_eps,
                           float* h_metrics, float* h_xhat, int tier, void* stream);

@@ -272,3 +272,31 @@ def test_tc_backward_parity(shape):
 
 def test_driver_replay(tmp_path):
     PC.case_driver_replay(BACKEND, tmp_path)
+
+
+def test_host_entry_points_and_prefetch():
+    """kcvae_train_step_host / kcvae_score_host with and without kcvae_prefetch_host give the
+    same numbers as the device-pointer entry points."""
+    cfg = O.readme_config()
+    B = 4
+    xs = [torch.from_numpy(frames(cfg, B, seed=s)).pin_memory() for s in range(4)]
+    ma, ws = make(cfg, BACKEND)
+    mb, _ = make(cfg, BACKEND)
+    for m in (ma, mb):
+        m.compile(optimizer=pkg.Adam(1e-4))
+        m.seed(5)
+    out_a, out_b = [], []
+    for s in range(4):
+        out_a.append(ma.train_step_host(xs[s]).clone())
+    for s in range(4):                       # pipelined: copy of step s+1 overlaps step s
+        if s + 1 < 4:
+            mb.prefetch_host(xs[s + 1])
+        out_b.append(mb.train_step_host(xs[s]).clone())
+    for a, b in zip(out_a, out_b):
+        assert torch.equal(a, b)
+    for wa, wb in zip(ma.get_weights(), mb.get_weights()):
+        np.testing.assert_array_equal(wa, wb)
+    sc = ma.score_host(xs[0]).numpy()
+    np.testing.assert_allclose(sc, ma.score(xs[0])["score"].numpy(), rtol=1e-6)
+    mb.prefetch_host(xs[1])
+    np.testing.assert_allclose(mb.score_host(xs[1]).numpy(), mb.score(xs[1])["score"].numpy(), rtol=1e-6)

@@ -69,6 +69,7 @@ _SIGS = {
     "kcvae_score": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _P]),
     "kcvae_normalize_scores": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                          C.c_float, _P, _P, _P, _P]),
+    "kcvae_prefetch_host": (C.c_int, [_P, _P, C.c_int]),
     "kcvae_train_step_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int, _P]),
     "kcvae_score_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "kcvae_launch_count": (C.c_int64, [_P]),

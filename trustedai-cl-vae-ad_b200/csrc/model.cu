@@ -101,6 +101,13 @@ struct kcvae_model {
   // workspace
   int cap_fwd = 0, cap_bwd = 0, last_B = 0;
   std::vector<float*> act_e, act_d, g_act_e, g_act_d;
+  float* x_stage[2] = {nullptr, nullptr};   // double-buffered H2D staging for the *_host entry points
+  const void* pend_src[2] = {nullptr, nullptr};   // host pointer whose prefetch sits in x_stage[i] (not yet consumed)
+  int pend_batch[2] = {0, 0};
+#ifndef KCVAE_EMU
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_done[2] = {nullptr, nullptr}, stage_free[2] = {nullptr, nullptr};
+#endif
   float *x_in = nullptr, *d1 = nullptr, *head = nullptr, *z = nullptr, *mean = nullptr, *logvar = nullptr;
   float *eps_buf = nullptr, *xhat = nullptr, *x_noisy = nullptr;
   float *dlogit = nullptr, *g_z = nullptr, *dhead = nullptr, *g_d1 = nullptr;
@@ -258,7 +265,10 @@ int ensure_fwd(kcvae_model* h, int B) {
   h->act_d.resize(L + 1, nullptr);
   for (int l = 1; l <= L; ++l) KC_TRY(dalloc(h, &h->act_e[l], (size_t)B * h->eh[l] * h->ew[l] * h->ec[l]));
   for (int l = 0; l <= L; ++l) KC_TRY(dalloc(h, &h->act_d[l], (size_t)B * h->dh[l] * h->dw[l] * h->dc[l]));
-  KC_TRY(dalloc(h, &h->x_in, (size_t)B * h->P));
+  KC_TRY(dalloc(h, &h->x_stage[0], (size_t)B * h->P));
+  KC_TRY(dalloc(h, &h->x_stage[1], (size_t)B * h->P));
+  h->x_in = h->x_stage[0];
+  h->pend_src[0] = h->pend_src[1] = nullptr;
   KC_TRY(dalloc(h, &h->x_noisy, (size_t)B * h->P));
   KC_TRY(dalloc(h, &h->d1, (size_t)B * (h->enc_dense ? h->enc_dense : 1)));
   KC_TRY(dalloc(h, &h->head, (size_t)B * 2 * h->latent));
@@ -757,11 +767,15 @@ int kcvae_destroy(kcvae_handle h) {
 #ifndef KCVAE_EMU
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
 #endif
+#ifndef KCVAE_EMU
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 2; ++i) { if (h->stage_free[i]) cudaEventDestroy(h->stage_free[i]); if (h->copy_done[i]) cudaEventDestroy(h->copy_done[i]); }
+#endif
   for (float* p : h->act_e) if (p) cudaFree(p);
   for (float* p : h->act_d) if (p) cudaFree(p);
   for (float* p : h->g_act_e) if (p) cudaFree(p);
   for (float* p : h->g_act_d) if (p) cudaFree(p);
-  float* fl[] = {h->w, h->g, h->m, h->v, h->x_in, h->d1, h->head, h->z, h->mean, h->logvar, h->eps_buf, h->xhat,
+  float* fl[] = {h->w, h->g, h->m, h->v, h->x_stage[0], h->x_stage[1], h->d1, h->head, h->z, h->mean, h->logvar, h->eps_buf, h->xhat,
                  h->x_noisy, h->dlogit, h->g_z, h->dhead, h->g_d1, h->partial, h->err_buf, h->score_buf, h->minmax,
                  h->metrics_dev};
   for (float* p : fl) if (p) cudaFree(p);
@@ -1050,7 +1064,66 @@ int kcvae_normalize_scores(kcvae_handle h, const float* d_err, const float* d_sc
   return post(h);
 }
 
+
+// Brings `batch` frames from host memory into a staging buffer and returns the device pointer
+// the step should read.  If the same host pointer was handed to kcvae_prefetch_host, the copy
+// already runs on the copy stream and the compute stream only waits for its event.
+static int acquire_host_input(kcvae_model* h, const float* h_x, int batch, cudaStream_t st, const float** d_x) {
+  const size_t bytes = (size_t)batch * h->P * sizeof(float);
+#ifndef KCVAE_EMU
+  for (int slot = 0; slot < 2; ++slot) {
+    if (h->pend_src[slot] == h_x && h->pend_batch[slot] == batch) {
+      KC_CUDA(h, cudaStreamWaitEvent(st, h->copy_done[slot], 0));
+      h->pend_src[slot] = nullptr;
+      *d_x = h->x_in = h->x_stage[slot];
+      return KCVAE_OK;
+    }
+  }
+#endif
+  const int slot = h->pend_src[0] ? 1 : 0;   // never a slot that holds an unconsumed prefetch
+  if (h->pend_src[0] && h->pend_src[1]) h->pend_src[1] = nullptr;   // both claimed: drop the newer prefetch
+#ifndef KCVAE_EMU
+  if (h->copy_done[slot]) KC_CUDA(h, cudaStreamWaitEvent(st, h->copy_done[slot], 0));   // an abandoned prefetch may still be landing
+#endif
+  KC_CUDA(h, cudaMemcpyAsync(h->x_stage[slot], h_x, bytes, cudaMemcpyHostToDevice, st));
+  *d_x = h->x_in = h->x_stage[slot];
+  return KCVAE_OK;
+}
+// marks the staging slot used by the step just enqueued on `st` as reusable once the step is done
+static void release_host_input(kcvae_model* h, const float* d_x, cudaStream_t st) {
+#ifndef KCVAE_EMU
+  const int slot = d_x == h->x_stage[1] ? 1 : 0;
+  if (!h->stage_free[slot]) cudaEventCreateWithFlags(&h->stage_free[slot], cudaEventDisableTiming);
+  cudaEventRecord(h->stage_free[slot], st);
+#else
+  (void)h; (void)d_x; (void)st;
+#endif
+}
+
 // ---- host-buffer entry points -------------------------------------------------------------
+int kcvae_prefetch_host(kcvae_handle h, const float* h_x, int batch) {
+  KC_TRY(check_batch(h, batch));
+  if (!h_x) return fail(h, KCVAE_ERR_INVALID, "prefetch_host: null pointer");
+#ifdef KCVAE_EMU
+  return KCVAE_OK;   // the emulator copies inline
+#else
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_fwd(h, batch));
+  if (!h->copy_stream) {
+    KC_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) KC_CUDA(h, cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
+  }
+  // a slot without an unconsumed prefetch; prefer the one the most recent step did not read
+  int slot = h->x_in == h->x_stage[0] ? 1 : 0;
+  if (h->pend_src[slot]) slot = 1 - slot;
+  if (h->pend_src[slot]) return fail(h, KCVAE_ERR_INVALID, "prefetch_host: two prefetches already pending");
+  if (h->stage_free[slot]) KC_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->stage_free[slot], 0));
+  KC_CUDA(h, cudaMemcpyAsync(h->x_stage[slot], h_x, (size_t)batch * h->P * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+  KC_CUDA(h, cudaEventRecord(h->copy_done[slot], h->copy_stream));
+  h->pend_src[slot] = h_x; h->pend_batch[slot] = batch;
+  return KCVAE_OK;
+#endif
+}
 int kcvae_train_step_host(kcvae_handle h, const float* h_x, int batch, const float* h_eps, float* h_metrics,
                           float* h_xhat, int tier, void* stream) {
   KC_TRY(check_batch(h, batch));
@@ -1058,13 +1131,15 @@ int kcvae_train_step_host(kcvae_handle h, const float* h_x, int batch, const flo
   cudaStream_t st = (cudaStream_t)stream;
   KC_CUDA(h, cudaSetDevice(h->device));
   KC_TRY(ensure_bwd(h, batch));
-  KC_CUDA(h, cudaMemcpyAsync(h->x_in, h_x, (size_t)batch * h->P * sizeof(float), cudaMemcpyHostToDevice, st));
+  const float* d_x = nullptr;
+  KC_TRY(acquire_host_input(h, h_x, batch, st, &d_x));
   const float* eps = nullptr;
   if (h_eps) {
     KC_CUDA(h, cudaMemcpyAsync(h->eps_buf, h_eps, (size_t)batch * h->latent * sizeof(float), cudaMemcpyHostToDevice, st));
     eps = h->eps_buf;
   }
-  KC_TRY(step_impl(h, h->x_in, batch, eps, nullptr, h->metrics_dev, h->xhat, tier, 1, st));
+  KC_TRY(step_impl(h, d_x, batch, eps, nullptr, h->metrics_dev, h->xhat, tier, 1, st));
+  release_host_input(h, d_x, st);
   KC_CUDA(h, cudaMemcpyAsync(h_metrics, h->metrics_dev, KCVAE_NUM_METRICS * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (h_xhat) KC_CUDA(h, cudaMemcpyAsync(h_xhat, h->xhat, (size_t)batch * h->P * sizeof(float), cudaMemcpyDeviceToHost, st));
   KC_CUDA(h, cudaStreamSynchronize(st));
@@ -1077,8 +1152,10 @@ int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, 
   cudaStream_t st = (cudaStream_t)stream;
   KC_CUDA(h, cudaSetDevice(h->device));
   KC_TRY(ensure_fwd(h, batch));
-  KC_CUDA(h, cudaMemcpyAsync(h->x_in, h_x, (size_t)batch * h->P * sizeof(float), cudaMemcpyHostToDevice, st));
-  KC_TRY(kcvae_score(h, h->x_in, batch, h_err ? h->err_buf : nullptr, h->score_buf, nullptr, nullptr, stream));
+  const float* d_x = nullptr;
+  KC_TRY(acquire_host_input(h, h_x, batch, st, &d_x));
+  KC_TRY(kcvae_score(h, d_x, batch, h_err ? h->err_buf : nullptr, h->score_buf, nullptr, nullptr, stream));
+  release_host_input(h, d_x, st);
   if (h_err) KC_CUDA(h, cudaMemcpyAsync(h_err, h->err_buf, (size_t)batch * h->H * h->W * sizeof(float), cudaMemcpyDeviceToHost, st));
   KC_CUDA(h, cudaMemcpyAsync(h_score, h->score_buf, (size_t)batch * sizeof(float), cudaMemcpyDeviceToHost, st));
   KC_CUDA(h, cudaStreamSynchronize(st));

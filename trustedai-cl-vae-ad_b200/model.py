@@ -632,6 +632,11 @@ class AbstractCVAE:
                                                   self.metric_tier, self._stream()), self._h)
         return out
 
+    def prefetch_host(self, x_host: torch.Tensor):
+        """Start copying the NEXT step's (pinned) host frames while the current step runs."""
+        assert x_host.device.type == "cpu" and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        self._lib.check(self._lib.prefetch_host(self._h, _ptr(x_host), x_host.shape[0]), self._h)
+
     def score_host(self, x_host: torch.Tensor, score_host: Optional[torch.Tensor] = None,
                    err_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         assert x_host.device.type == "cpu" and x_host.dtype == torch.float32 and x_host.is_contiguous()
