@@ -300,3 +300,36 @@ def test_host_entry_points_and_prefetch():
     np.testing.assert_allclose(sc, ma.score(xs[0])["score"].numpy(), rtol=1e-6)
     mb.prefetch_host(xs[1])
     np.testing.assert_allclose(mb.score_host(xs[1]).numpy(), mb.score(xs[1])["score"].numpy(), rtol=1e-6)
+
+
+# ------------------------------------------------------ the other BASELINE.json configurations
+def test_config3_single_batch128_readme():
+    """BASELINE configs[2]: KurtosisSingleCVAE (per-latent-dimension moments across the batch),
+    README topology, batch 128 on one GPU, both precisions."""
+    cfg = O.readme_config("KurtosisSingle")
+    B = 128
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    m, ws = make(cfg, BACKEND, weight_gain=1.3)
+    od = O.compute_loss(cfg, ws, x, eps)[0]
+    assert_metrics_close(m.compute_loss(x, training=True, eps=eps), od, rtol=5e-4)
+    mt, _ = make(cfg, BACKEND, weight_gain=1.3, precision="bf16")
+    assert_metrics_close(mt.compute_loss(x, training=True, eps=eps), od, rtol=1e-3, atol=1e-6)
+    mt.compile(optimizer=pkg.Adam(1e-4))
+    d = mt.train_step(x, eps=eps)
+    assert_metrics_close(d, od, rtol=1e-3, atol=1e-6)
+    assert mt.tc_status() == 1
+
+
+def test_config5_scaled_model():
+    """BASELINE configs[4] instance pinned by SURVEY 8d: 448x600x3, layers [64,128,32], latent 256
+    (77,960,067 parameters).  Generic kernels (channel counts outside the tensor-core shapes)."""
+    cfg = O.scaled_config()
+    m, ws = make(cfg, BACKEND, bias_scale=0.02)
+    assert m.count_params() == 77_960_067
+    x, eps = frames(cfg, 1), eps_for(cfg, 1)
+    d, grads = m.loss_and_grads(x, eps=eps)
+    od, ograds, oxh, _ = O.loss_and_grads(cfg, ws, x, eps)
+    assert_metrics_close(d, od, rtol=5e-4)
+    for (n, _), g, og in zip(O.variable_shapes(cfg), grads, ograds):
+        assert rel_err(g, og.numpy()) < 2e-3, n
+    assert float(np.max(np.abs(m.call(x, True, eps=eps).numpy() - oxh.numpy()))) < 1e-4
