@@ -130,6 +130,11 @@ struct kcvae_model {
   int* tc_error = nullptr;
   // data parallel
   int rank = 0, world = 1;
+  // collectives run on their own stream so they overlap the backward pass (non-emulated build)
+  cudaStream_t comm_stream = nullptr;
+#ifndef KCVAE_EMU
+  cudaEvent_t ev_fork = nullptr, ev_sums = nullptr, ev_comm = nullptr;
+#endif
 #ifndef KCVAE_EMU
   ncclComm_t comm = nullptr;
 #endif
@@ -458,10 +463,23 @@ int allreduce(kcvae_model* h, void* buf, int64_t count, int is_double, int op, c
 }
 
 // ------------------------------------------------------------------------------- losses
+// order `to` after everything enqueued so far on `from`
+static void stream_after(kcvae_model* h, cudaStream_t from, cudaStream_t to) {
+#ifndef KCVAE_EMU
+  if (from == to) return;
+  cudaEventRecord(h->ev_fork, from);
+  cudaStreamWaitEvent(to, h->ev_fork, 0);
+#else
+  (void)h; (void)from; (void)to;
+#endif
+}
+
 int sums_len(const kcvae_model* h) { return S_Z1 + (h->cfg.model_type == KCVAE_SINGLE ? 4 * h->latent : 4); }
 
 // image + latent statistics (and dlogit when with_grad); all-reduced under DP
-int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier, int with_grad, cudaStream_t st) {
+// cs: stream for the collectives (== st when nothing may overlap, e.g. kcvae_loss)
+int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier, int with_grad, cudaStream_t st,
+              cudaStream_t cs) {
   const int full = tier == KCVAE_METRICS_FULL;
   const int Bg = B * h->world;
   g_tag = "loss";
@@ -483,12 +501,16 @@ int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier
   ia.partial = h->dpartial;
   image_stats(ia, st);
   if (h->world > 1) {
-    KC_TRY(allreduce(h, h->sums, sums_len(h), 1, 0, st));
-    if (full) {
-      KC_TRY(allreduce(h, h->pos_sums, 4 * h->P, 1, 0, st));
-      image_std_from_pos_sums(h->pos_sums, h->P, Bg, h->std_acc, h->dpartial, st);
-      KC_TRY(allreduce(h, h->minmax, 1, 0, 1, st));      // min over ranks of min(xhat)
-      KC_TRY(allreduce(h, h->minmax + 1, 1, 0, 2, st));  // max over ranks of max(xhat)
+    stream_after(h, st, cs);
+    KC_TRY(allreduce(h, h->sums, sums_len(h), 1, 0, cs));   // needed by latent_backward (batch-global moments)
+#ifndef KCVAE_EMU
+    if (cs != st) cudaEventRecord(h->ev_sums, cs);
+#endif
+    if (full) {   // reported-only metrics: nothing on the gradient path waits for these
+      KC_TRY(allreduce(h, h->pos_sums, 4 * h->P, 1, 0, cs));
+      image_std_from_pos_sums(h->pos_sums, h->P, Bg, h->std_acc, h->dpartial, cs);
+      KC_TRY(allreduce(h, h->minmax, 1, 0, 1, cs));      // min over ranks of min(xhat)
+      KC_TRY(allreduce(h, h->minmax + 1, 1, 0, 2, cs));  // max over ranks of max(xhat)
     }
   }
   return KCVAE_OK;
@@ -502,7 +524,8 @@ void run_finalize(kcvae_model* h, int B, int tier, float* d_metrics, cudaStream_
 }
 
 // ------------------------------------------------------------------------------ backward
-void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
+// cs != st: gradient all-reduces are issued on cs as soon as a parameter range is complete
+int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStream_t cs) {
   const int L = h->L;
   const int Bg = B * h->world;
   bool tail_s2d = false;   // d loss / d a_last lives as bf16 space-to-depth (tensor-core tail)
@@ -591,6 +614,15 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
     gz.C = h->g_z; gz.M = B; gz.N = h->latent; gz.K = h->dec_units; gz.partial = h->partial;
     gemm(gz, st);
   }
+  if (h->world > 1) {
+    // every decoder gradient is final: reduce that range (93 % of the parameters) under the encoder backward
+    const int64_t off_dec = h->vars[h->vi_dec_dense()].off;
+    stream_after(h, st, cs);
+    KC_TRY(allreduce(h, h->g + off_dec, h->nparams - off_dec, 0, 0, cs));
+#ifndef KCVAE_EMU
+    if (cs != st) cudaStreamWaitEvent(st, h->ev_sums, 0);   // global moment sums must have landed
+#endif
+  }
   g_tag = "latent";
   latent_backward(h->z, h->g_z, h->sums, B, Bg, h->latent, h->cfg.model_type, h->lw, h->dhead, st);
   const float* flat_act = L > 0 ? h->act_e[L] : x;
@@ -659,6 +691,15 @@ void run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st) {
       conv_forward(CONVT_S2, EPI_MASK, a, st);
     }
   }
+  if (h->world > 1) {
+    const int64_t off_dec = h->vars[h->vi_dec_dense()].off;
+    stream_after(h, st, cs);
+    KC_TRY(allreduce(h, h->g, off_dec, 0, 0, cs));          // encoder range
+#ifndef KCVAE_EMU
+    if (cs != st) { cudaEventRecord(h->ev_comm, cs); cudaStreamWaitEvent(st, h->ev_comm, 0); }
+#endif
+  }
+  return KCVAE_OK;
 }
 
 int run_adam(kcvae_model* h, cudaStream_t st) {
@@ -683,10 +724,10 @@ int step_impl(kcvae_model* h, const float* d_x, int B, const float* d_eps, const
   }
   float* xh = d_xhat ? d_xhat : h->xhat;
   run_forward(h, x, B, 1, d_eps, xh, st);
-  KC_TRY(run_stats(h, d_x, xh, B, tier, 1, st));
-  run_backward(h, x, B, st);
+  cudaStream_t cs = (h->world > 1 && h->comm_stream) ? h->comm_stream : st;
+  KC_TRY(run_stats(h, d_x, xh, B, tier, 1, st, cs));
+  KC_TRY(run_backward(h, x, B, st, cs));
   if (h->tc_failed) return fail(h, KCVAE_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed; use precision fp32");
-  if (h->world > 1) KC_TRY(allreduce(h, h->g, h->nparams, 0, 0, st));
   if (do_update) KC_TRY(run_adam(h, st));
   run_finalize(h, B, tier, d_metrics ? d_metrics : h->metrics_dev, st);
   return post(h);
@@ -766,6 +807,7 @@ int kcvae_destroy(kcvae_handle h) {
   cudaDeviceSynchronize();
 #ifndef KCVAE_EMU
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_sums); cudaEventDestroy(h->ev_comm); }
 #endif
 #ifndef KCVAE_EMU
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -932,6 +974,14 @@ int kcvae_comm_init(kcvae_handle h, const void* id128, int rank, int world_size)
   if (r != ncclSuccess) return fail(h, KCVAE_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
 #endif
   h->rank = rank; h->world = world_size;
+#ifndef KCVAE_EMU
+  if (world_size > 1 && !h->comm_stream) {
+    KC_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    KC_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    KC_CUDA(h, cudaEventCreateWithFlags(&h->ev_sums, cudaEventDisableTiming));
+    KC_CUDA(h, cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
+  }
+#endif
   if (world_size > 1) KC_TRY(dalloc(h, &h->pos_sums, (size_t)4 * h->P));
   return KCVAE_OK;
 }
@@ -1020,7 +1070,7 @@ int kcvae_loss(kcvae_handle h, const float* d_x, int batch, int training, const 
   KC_TRY(ensure_fwd(h, batch));
   float* xh = d_xhat ? d_xhat : h->xhat;
   run_forward(h, d_x, batch, training, d_eps, xh, st);
-  KC_TRY(run_stats(h, d_x, xh, batch, tier, 0, st));
+  KC_TRY(run_stats(h, d_x, xh, batch, tier, 0, st, st));
   run_finalize(h, batch, tier, d_metrics, st);
   return post(h);
 }
