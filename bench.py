@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--batch-per-gpu", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--precision", default=os.environ.get("KCVAE_PRECISION", "bf16"),
                     help="bf16: tcgen05 decoder kernels (bf16 operands, fp32 accumulate); fp32: CUDA-core path")
+    ap.add_argument("--metrics-tier", default="full", choices=["full", "loss_only"],
+                    help="full = the reference's whole metrics dict every step (default); loss_only skips reported-only terms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-score", action="store_true")
     return ap.parse_args()
@@ -226,7 +228,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = O.readme_config()
     B = args.batch_per_gpu
-    model = pkg.load_model_from_config(cfg, device=local, precision=args.precision, metrics="full")
+    model = pkg.load_model_from_config(cfg, device=local, precision=args.precision, metrics=args.metrics_tier)
     model.set_weights(O.glorot_init(cfg, 1234))
     model.compile(optimizer=pkg.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
     model.seed(1000 + rank)
@@ -349,7 +351,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": "KurtosisGlobalCVAE README config 224x300x3 layers[32,5] latent32 train_step (BASELINE configs[1])",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "metrics_tier": "full", "l2_policy": f"inputs cycle through a {npool * batch_bytes >> 20} MiB pool (> 126 MiB L2)",
+                       "metrics_tier": args.metrics_tier, "l2_policy": f"inputs cycle through a {npool * batch_bytes >> 20} MiB pool (> 126 MiB L2)",
                        "precision": args.precision},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": batch_bytes,
                     "d2h_bytes_per_step": 16 * 4, "ms_per_step": ms_e2e / K},
