@@ -145,6 +145,13 @@ def algorithmic_bytes(cfg, B, world):
         we = 4 * nW["encoder/dense/kernel"]
         tab["enc.dense.fwd/gemm"] = B * (act * enc[L] + 4 * t.enc_dense) + we
         tab["enc.dense.bwd/gemm"] = 2 * (B * (act * enc[L] + 4 * t.enc_dense) + we)
+    # tensor-core kernels move the same tensors as the CUDA-core launchers they replace
+    for tc, generic in (("dec.out.fwd/tc_out_conv", "dec.out.fwd/conv3x3"), ("dec.out.bwd/tc_out_dgrad", "dec.out.bwd/conv3x3"),
+                        ("dec.out.bwd/tc_out_wgrad", "dec.out.bwd/wgrad"), ("dec.convT_last.fwd/tc_convT_fwd", "dec.convT_last.fwd/conv3x3"),
+                        ("dec.convT_last.bwd/tc_convT_wgrad", "dec.convT_last.bwd/wgrad"),
+                        ("dec.convT_last.bwd/tc_convT_dgrad", "dec.convT_last.bwd/conv3x3")):
+        if generic in tab:
+            tab[tc] = tab[generic]
     tab["loss/image_stats"] = B * (4 * I + act * I + act * I)      # x, xhat in; dlogit out
     P = sum(nW.values())
     tab["optimizer/adam"] = 7 * 4 * P                               # p,g,m,v read; p,m,v written
