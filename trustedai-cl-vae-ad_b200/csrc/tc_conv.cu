@@ -1041,6 +1041,277 @@ tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
   if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+// ============================================================================================
+// Fused decoder tail (forward / scoring):  a_prev (<= 8 ch, low-res)  --Conv2DTranspose s2,
+// bias, ReLU-->  a_last (32 ch)  --Conv2DTranspose s1, bias, sigmoid-->  x_hat  [--> err, score]
+// The 32-channel full-resolution activation (73 % of all activation bytes of the model) only
+// ever exists as a bf16 halo tile in SHARED MEMORY:
+//   phase A  3 M-tiles x 5 paired-tap MMAs (N=32) on the low-res a_prev tile (TMA) -> TMEM
+//   epi A    TMEM -> bias, ReLU, bf16 -> the [chunk][pixel] halo tile of a_last in smem
+//            (zeros outside the image = SAME padding of the next layer)
+//   phase B  8 M-tiles x 18 MMAs (N=16) on that tile -> TMEM          (as tc_out_conv_kernel)
+//   epi B    TMEM -> bias, sigmoid -> x_hat and/or err = sum_c (x - x_hat)^2, score partials
+// TMEM: 2 x 128 columns (phase A slots) + 2 x 128 columns (phase B buffers) = 512.
+// The a_last smem tile and the phase B accumulators are double buffered, so the tensor pipe
+// works on tile t+1 (phase A) while the epilogue warps finish tile t.
+constexpr int PA = 20;                     // pitch of the low-res a_prev tile
+constexpr int A3ROWS = 21;
+constexpr uint32_t A3_BYTES = A3ROWS * PA * 16;
+constexpr int LR_ROWS = 18, LR_COLS = 17;  // low-res pixels whose 2x2 phases cover the 34x32 halo tile
+constexpr int MTA = 3;                     // phase A M-tiles (LR_ROWS * PA = 360 <= 384)
+
+struct TailParams {
+  const __nv_bfloat16* wimgA;  // convT images [5][2][32][8]
+  const __nv_bfloat16* wimgB;  // out-conv images [9][2][2][16][8]
+  const float* biasA;          // [32]
+  const float* biasB;          // [Cout]
+  const float* x;              // [B,H,W,Cout] fp32 (needed for err / score) or nullptr
+  float* xhat;                 // [B,H,W,Cout] or nullptr
+  float* err;                  // [B,H,W] or nullptr
+  float* score_partial;        // [num_tiles][8][3] (sum, min, max of err per epilogue warp) or nullptr
+  int B, H, W, Cout;
+  int tiles_y, tiles_x, num_tiles;
+  int apply_sigmoid;
+  int* error_flag;
+};
+
+__global__ void __launch_bounds__(kThreadsE, 1)
+tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
+  constexpr uint32_t CH = NPIX * 16;
+  constexpr uint32_t A4_BYTES = 4 * CH;
+  constexpr uint32_t A4_STAGE = A4_BYTES + 128;
+  constexpr uint32_t A3_STAGE = A3_BYTES + 128;
+  constexpr uint32_t WA_BYTES = 5 * 2 * 32 * 16, WB_BYTES = 9 * 2 * 2 * NPAD * 16;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* s_a4 = smem;                               // 2 stages
+  unsigned char* s_a3 = smem + 2 * A4_STAGE;                // 2 stages
+  unsigned char* s_wA = s_a3 + 2 * A3_STAGE;
+  unsigned char* s_wB = s_wA + WA_BYTES;
+  __shared__ uint64_t a3_full[2], a3_empty[2], Afull[2], Aempty[2], a4_ready[2], a4_free[2], Bfull[2], Bempty[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_biasA[32], s_biasB[NPAD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < (int)(WA_BYTES / 16); i += kThreadsE) reinterpret_cast<uint4*>(s_wA)[i] = reinterpret_cast<const uint4*>(p.wimgA)[i];
+  for (int i = threadIdx.x; i < (int)(WB_BYTES / 16); i += kThreadsE) reinterpret_cast<uint4*>(s_wB)[i] = reinterpret_cast<const uint4*>(p.wimgB)[i];
+  if (threadIdx.x < 32) s_biasA[threadIdx.x] = p.biasA[threadIdx.x];
+  if (threadIdx.x < NPAD) s_biasB[threadIdx.x] = (int)threadIdx.x < p.Cout ? p.biasB[threadIdx.x] : 0.f;
+  if (threadIdx.x < 32) {   // pads behind the tiles: only ever read into discarded rows/columns
+    const int s = (threadIdx.x >> 3) & 1, j = threadIdx.x & 7;
+    if (threadIdx.x < 16) reinterpret_cast<uint4*>(s_a4 + s * A4_STAGE + A4_BYTES)[j] = make_uint4(0, 0, 0, 0);
+    else reinterpret_cast<uint4*>(s_a3 + s * A3_STAGE + A3_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a3_full[s], 1); mbar_init(&a3_empty[s], 1);
+      mbar_init(&Afull[s], 1);   mbar_init(&Aempty[s], 8);
+      mbar_init(&a4_ready[s], 8); mbar_init(&a4_free[s], 1);
+      mbar_init(&Bfull[s], 1);   mbar_init(&Bempty[s], 8);
+    }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer: low-res a_prev tiles =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it & 1;
+        if (!mbar_wait(&a3_empty[s], ((it >> 1) & 1) ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / (p.tiles_y * p.tiles_x);
+        const int rem = t % (p.tiles_y * p.tiles_x);
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        mbar_expect_tx(&a3_full[s], A3_BYTES);
+        tma_load_4d(s_a3 + s * A3_STAGE, &tmap, &a3_full[s], 0, (tx * TW) / 2 - 2, (ty * TR) / 2 - 2, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (both phases) ===============================
+    const bool leader = elect_one();
+    const uint32_t idescA = make_idesc_bf16_f32(128, 32), idescB = make_idesc_bf16_f32(128, NPAD);
+    const uint64_t wA0 = make_desc_kmajor_noswz(smem_u32(s_wA), 32 * 16, 128);
+    const uint64_t wB0 = make_desc_kmajor_noswz(smem_u32(s_wB), NPAD * 16, 128);
+    int it = 0, ma = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      if (!mbar_wait(&a3_full[s], ph)) { if (leader) *p.error_flag = 1; break; }
+      fence_after_sync();
+      const uint32_t a3b = smem_u32(s_a3 + s * A3_STAGE);
+#pragma unroll 1
+      for (int mt = 0; mt < MTA; ++mt, ++ma) {
+        const int slot = ma & 1;
+        if (!mbar_wait(&Aempty[slot], ((ma >> 1) & 1) ^ 1)) { if (leader) *p.error_flag = 1; ok = false; break; }
+        fence_after_sync();
+        const uint32_t d0 = tmem + (uint32_t)(slot * 128);
+        const uint32_t q0 = a3b + (uint32_t)(mt * 128) * 16;
+        const uint64_t a0 = make_desc_kmajor_noswz(q0, 16, 128);
+        const uint64_t a1 = make_desc_kmajor_noswz(q0 + PA * 16, 16, 128);
+        const uint64_t a2 = make_desc_kmajor_noswz(q0 + 16, PA * 16, 128);
+        const uint64_t a4d = make_desc_kmajor_noswz(q0 + (PA + 1) * 16, 16, 128);
+        if (leader) {
+          mma_bf16_ss(d0 + 0, a0, wA0, idescA, 0);
+          mma_bf16_ss(d0 + 0, a1, desc_advance(wA0, 64), idescA, 1);
+          mma_bf16_ss(d0 + 32, a2, desc_advance(wA0, 128), idescA, 0);
+          mma_bf16_ss(d0 + 64, a1, desc_advance(wA0, 192), idescA, 0);
+          mma_bf16_ss(d0 + 96, a4d, desc_advance(wA0, 256), idescA, 0);
+          mma_commit(&Afull[slot]);
+        }
+        __syncwarp();
+      }
+      if (!ok) break;
+      if (leader) mma_commit(&a3_empty[s]);
+      __syncwarp();
+      // ---- phase B on the smem tile the epilogue warps just produced
+      if (!mbar_wait(&a4_ready[s], ph)) { if (leader) *p.error_flag = 1; break; }
+      if (!mbar_wait(&Bempty[s], ph ^ 1)) { if (leader) *p.error_flag = 1; break; }
+      fence_after_sync();
+      const uint64_t da0 = make_desc_kmajor_noswz(smem_u32(s_a4 + s * A4_STAGE), CH, 128);
+#pragma unroll 2
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t d_tmem = tmem + (uint32_t)(256 + s * 128 + mt * NPAD);
+        const uint64_t da_mt = desc_advance(da0, (uint32_t)(mt * 128));
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t shift = (uint32_t)((2 - tap / 3) * PW + (2 - tap % 3));
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t da = desc_advance(da_mt, (uint32_t)(2 * ks) * (CH / 16) + shift);
+            const uint64_t db = desc_advance(wB0, (uint32_t)((tap * 2 + ks) * 2 * NPAD));
+            if (leader) mma_bf16_ss(d_tmem, da, db, idescB, (tap | ks) != 0);
+          }
+        }
+      }
+      if (leader) {
+        mma_commit(&a4_free[s]);
+        mma_commit(&Bfull[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue warps (A then B per tile) =====================
+    const int lg = warp & 3, half = (warp - 2) >> 2, ew = (warp - 2);
+    int it = 0, ma = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int n = t / (p.tiles_y * p.tiles_x);
+      const int rem = t % (p.tiles_y * p.tiles_x);
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      const int ty0 = ty * TR, tx0 = tx * TW;
+      if (!mbar_wait(&a4_free[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; break; }   // phase B of tile it-2 done with this stage
+      unsigned char* a4s = s_a4 + s * A4_STAGE;
+      // ---- epilogue A: low-res phases -> bf16 halo tile in shared memory
+#pragma unroll 1
+      for (int mt = 0; mt < MTA; ++mt, ++ma) {
+        const int slot = ma & 1;
+        if (!mbar_wait(&Afull[slot], (ma >> 1) & 1)) { if (lane == 0) *p.error_flag = 1; ok = false; break; }
+        fence_after_sync();
+        const int q = mt * 128 + lg * 32 + lane;
+        const int r = q / PA, c = q % PA;
+        const bool live = r < LR_ROWS && c < LR_COLS;
+#pragma unroll
+        for (int pb = 0; pb < 2; ++pb) {
+          const int phs = half * 2 + pb;              // this warp handles output rows of parity `half`
+          float v[32];
+          const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * 128 + phs * 32);
+          tmem_ld16(ta, v);
+          tmem_ld16(ta + 16, v + 16);
+          const int hr = 2 * r + half - 1, hc = 2 * c + pb - 1;
+          if (live && hr >= 0 && hr < PR && hc >= 0 && hc < PW) {
+            const int Y = ty0 - 1 + hr, X = tx0 - 1 + hc;
+            const bool inside = Y >= 0 && Y < p.H && X >= 0 && X < p.W;
+            uint4* dst = reinterpret_cast<uint4*>(a4s) + (hr * PW + hc);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float y0 = inside ? fmaxf(v[g * 8 + 2 * e] + s_biasA[g * 8 + 2 * e], 0.f) : 0.f;
+                const float y1 = inside ? fmaxf(v[g * 8 + 2 * e + 1] + s_biasA[g * 8 + 2 * e + 1], 0.f) : 0.f;
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              dst[g * (CH / 16)] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&Aempty[slot]);
+      }
+      if (!ok) break;
+      fence_async_smem();          // st.shared of the tile -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a4_ready[s]);
+      // ---- epilogue B: sigmoid, reconstruction error, score partials
+      if (!mbar_wait(&Bfull[s], ph)) { if (lane == 0) *p.error_flag = 1; break; }
+      fence_after_sync();
+      float esum = 0.f, emin = 3.4e38f, emax = -3.4e38f;
+#pragma unroll 1
+      for (int mt = half; mt < MT; mt += 2) {
+        float v[8];
+        tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + s * 128 + mt * NPAD), v);
+        const int q = mt * 128 + lg * 32 + lane;
+        const int r = q / PW, c = q % PW;
+        const int oy = ty0 + r, ox = tx0 + c;
+        if (c < TW && oy < p.H && ox < p.W) {
+          const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
+          float e = 0.f;
+#pragma unroll
+          for (int co = 0; co < 8; ++co) {
+            if (co < p.Cout) {
+              float y = v[co] + s_biasB[co];
+              if (p.apply_sigmoid) y = 1.0f / (1.0f + __expf(-y));
+              if (p.xhat) p.xhat[pix * p.Cout + co] = y;
+              if (p.x) { const float d = __ldg(p.x + pix * p.Cout + co) - y; e = fmaf(d, d, e); }
+            }
+          }
+          if (p.err) p.err[pix] = e;
+          esum += e; emin = fminf(emin, e); emax = fmaxf(emax, e);
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&Bempty[s]);
+      if (p.score_partial) {     // fixed shuffle tree -> deterministic
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          esum += __shfl_xor_sync(0xffffffffu, esum, o);
+          emin = fminf(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+          emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+        }
+        if (lane == 0) {
+          float* o3 = p.score_partial + ((int64_t)t * 8 + ew) * 3;
+          o3[0] = esum; o3[1] = emin; o3[2] = emax;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// per-frame reduction of the per-tile/per-warp partials written by tc_tail_fused_kernel
+__global__ void tail_score_finish_kernel(const float* partial, int tiles_per_frame, int B, float* score, float* err_minmax) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float s = 0.f, mn = 3.4e38f, mx = -3.4e38f;
+  const float* p0 = partial + (int64_t)b * tiles_per_frame * 8 * 3;
+  for (int i = 0; i < tiles_per_frame * 8; ++i) { s += p0[i * 3]; mn = fminf(mn, p0[i * 3 + 1]); mx = fmaxf(mx, p0[i * 3 + 2]); }
+  score[b] = s;
+  if (err_minmax) { err_minmax[2 * b] = mn; err_minmax[2 * b + 1] = mx; }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n) {
   const int64_t n4 = n >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1272,6 +1543,52 @@ int tc_convT_wgrad(const void* g_s2d, const void* a_prev8, float* dW, float* par
   cudaFuncSetAttribute(tc_convT_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_convT_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
   sum_partials_kernel<<<cdiv(E, 256), 256, 0, st>>>(partial, grid, E, dW);
+  return 0;
+}
+
+bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W) {
+  return Cprev >= 1 && Cprev <= 8 && Clast == 32 && Cout >= 1 && Cout <= 8 && H % 2 == 0 && W % 2 == 0;
+}
+size_t tc_tail_score_partial_floats(int B, int H, int W) { return (size_t)B * cdiv(H, TR) * cdiv(W, TW) * 8 * 3; }
+
+// fused Conv2DTranspose s2 -> Conv2DTranspose s1 (+ sigmoid, error map, per-frame score).
+// in8: bf16 [B,H/2,W/2,8]; any of xhat / err / score may be nullptr (x is required for err / score).
+int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, const float* biasA, const float* biasB,
+                  const float* x, float* xhat, float* err, float* score, float* err_minmax, float* score_partial, int B,
+                  int H, int W, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return 1;
+  const int h = H / 2, w = W / 2;
+  CUtensorMap tmap;
+  const cuuint64_t gdim[4] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+  const cuuint64_t gstr[3] = {16, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
+  const cuuint32_t box[4] = {8, PA, A3ROWS, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in8_bf16), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return 2;
+  TailParams p{};
+  p.wimgA = reinterpret_cast<const __nv_bfloat16*>(wimgA);
+  p.wimgB = reinterpret_cast<const __nv_bfloat16*>(wimgB);
+  p.biasA = biasA; p.biasB = biasB; p.x = x; p.xhat = xhat; p.err = err;
+  p.score_partial = score ? score_partial : nullptr;
+  p.B = B; p.H = H; p.W = W; p.Cout = Cout;
+  p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.apply_sigmoid = apply_sigmoid;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const size_t smem = (size_t)2 * ((size_t)4 * NPIX * 16 + 128) + (size_t)2 * (A3_BYTES + 128) + (size_t)5 * 2 * 32 * 16 +
+                      (size_t)9 * 2 * 2 * NPAD * 16;
+  ProfScope prof_("tc_tail_fused", st);
+  ++g_launches;
+  cudaFuncSetAttribute(tc_tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_tail_fused_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
+  if (score) {
+    ++g_launches;
+    tail_score_finish_kernel<<<cdiv(B, 128), 128, 0, st>>>(score_partial, p.tiles_y * p.tiles_x, B, score, err_minmax);
+  }
   return 0;
 }
 

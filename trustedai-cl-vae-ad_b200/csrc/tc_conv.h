@@ -40,6 +40,14 @@ void tc_prep_convT_weights(const float* w, int Cout, int Cin, void* img_bf16, cu
 int tc_convT_fwd(const void* in8_bf16, const void* wimg_bf16, const float* bias, void* out_bf16, int B, int h, int w,
                  int* error_flag, cudaStream_t st);
 
+// fused decoder tail: Conv2DTranspose s2 (Cprev <= 8 -> 32) -> Conv2DTranspose s1 (32 -> Cout) with the
+// 32-channel activation kept in shared memory; optional sigmoid, x_hat, error map and per-frame score
+bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W);
+size_t tc_tail_score_partial_floats(int B, int H, int W);
+int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, const float* biasA, const float* biasB,
+                  const float* x, float* xhat, float* err, float* score, float* err_minmax, float* score_partial, int B,
+                  int H, int W, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st);
+
 // output-layer weight gradient (MN-major tcgen05, K = pixels); partial >= tc_out_wgrad_partial_floats()
 bool tc_out_wgrad_supported(int Cin, int Cout);
 size_t tc_out_wgrad_partial_floats(int Cin, int Cout);
