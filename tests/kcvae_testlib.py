@@ -25,7 +25,7 @@ _EMU = None
 def emu_binding():
     global _EMU
     if _EMU is None:
-        path = _build.build_emu()
+        path = _build.build_emu(sanitize=bool(os.environ.get("KCVAE_EMU_ASAN")))   # ASan: also LD_PRELOAD libasan
         _EMU = _lib.Binding(C.CDLL(path), "cpu", path)
     return _EMU
 

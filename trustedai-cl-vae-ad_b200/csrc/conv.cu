@@ -625,6 +625,219 @@ __global__ void __launch_bounds__(256) wgrad_tiled_kernel(WgradArgs a, int rows,
   }
 }
 
+
+// ------------------------------------------------- weight grads, row-streaming version
+// Same thread tiling as wgrad_tiled_kernel, but the operands arrive through a two-stage
+// cp.async pipeline: while the block accumulates P row r against the three Q rows it touches,
+// row r+1 is already in flight, so the global-load latency that dominated the staged kernel is
+// hidden.  Each row (and the contiguous 3-row Q span) is one linear 16-byte-chunk copy; image
+// borders are handled by clipping each thread's pixel range for its tap, not by padding.
+// Optionally the same pass produces sum_pixels P[., a] (the bias gradient when P is a gradient).
+#ifndef KCVAE_EMU
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#else
+static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+#endif
+
+// elements [k_lo, k_hi) of the float array starting at element `base` of `src` -> dst[mis + k],
+// mis = address misalignment (in floats) of element `base`, so 16-byte chunks line up
+__device__ __forceinline__ int stage_linear(float* dst, const float* src, int64_t base, int k_lo, int k_hi) {
+  const int mis = (int)(((reinterpret_cast<uintptr_t>(src) >> 2) + (uint64_t)base) & 3);
+  int head_end = k_lo + ((4 - ((mis + k_lo) & 3)) & 3);
+  if (head_end > k_hi) head_end = k_hi;
+  const int body = (k_hi - head_end) >> 2;
+  const int tail0 = head_end + (body << 2);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < body; t += nt) cp_async16(dst + mis + head_end + 4 * t, src + base + head_end + 4 * t);
+  if (tid < head_end - k_lo) dst[mis + k_lo + tid] = __ldg(src + base + k_lo + tid);
+  if (tid >= 32 && tid - 32 < k_hi - tail0) dst[mis + tail0 + tid - 32] = __ldg(src + base + tail0 + tid - 32);
+  return mis;
+}
+// npix pixels of C = 4*C4 channels (16-byte aligned source) -> dst[pixel * cpad + c]
+__device__ __forceinline__ void stage_padded(float* dst, const float* src, int npix, int C4, int cpad) {
+  const int total = npix * C4;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) {
+    const int px = t / C4, u = t - px * C4;
+    cp_async16(dst + px * cpad + 4 * u, src + 4 * (int64_t)t);
+  }
+}
+
+struct WgradRowsGeom {
+  int rows, rows_per_block, n_at, n_bt, nph;
+  int p_pad, q_pad;        // 1: channel-padded staging (C % 4 == 0), 0: linear
+  int cap, cbp;            // staged channel strides of P and Q
+  int p_floats, q_floats;  // per-stage buffer sizes (multiples of 4)
+  int want_colsum, pstride;
+};
+
+template <int RA, int RB>
+__global__ void __launch_bounds__(256) wgrad_rows_kernel(WgradArgs a, WgradRowsGeom gm) {
+  KC_DYN_SMEM(float, sm);
+  const int E = 9 * a.Ca * a.Cb;
+  const int n_et = 9 * gm.n_at * gm.n_bt;
+  const int tid = threadIdx.x;
+  const bool active = tid < n_et * gm.nph;
+  const int et = active ? tid % n_et : 0, ph = active ? tid / n_et : 0;
+  const int bt = et % gm.n_bt, at = (et / gm.n_bt) % gm.n_at, tap = et / (gm.n_bt * gm.n_at);
+  const int kh = tap / 3, kw = tap % 3;
+  const int a0 = at * RA, b0 = bt * RB;
+  const int rsel = a.d > 0 ? kh : 2 - kh;          // which row of the staged 3-row span this tap reads
+  const int dlo = a.d < 0 ? 2 * a.d : 0;
+  const int qoff = a.d * kw + a.ox;                // qx = s*j + qoff
+  int jlo = 0, jhi = a.Wp;
+  while (jlo < jhi && a.s * jlo + qoff < 0) ++jlo;
+  while (jhi > jlo && a.s * (jhi - 1) + qoff >= a.Wq) --jhi;
+  const bool cs_thread = gm.want_colsum && active && tap == 4 && bt == 0;
+  const bool pvec = (RA % 4 == 0) && gm.p_pad && (a0 + RA <= a.Ca);
+  const bool qvec = (RB % 4 == 0) && gm.q_pad && (b0 + RB <= a.Cb);
+  const int stage_floats = gm.p_floats + gm.q_floats;
+  const int qrow_f = a.Wq * gm.cbp;
+
+  float acc[RA][RB];
+  float bsum[RA];
+#pragma unroll
+  for (int i = 0; i < RA; ++i) {
+    bsum[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < RB; ++j) acc[i][j] = 0.f;
+  }
+
+  const int r0 = blockIdx.x * gm.rows_per_block;
+  const int r1 = min(gm.rows, r0 + gm.rows_per_block);
+  int pmis[2] = {0, 0}, qmis[2] = {0, 0};
+
+  auto stage = [&](int r, int sidx) {
+    float* Pb = sm + sidx * stage_floats;
+    float* Qb = Pb + gm.p_floats;
+    const int n = r / a.Hp, i = r % a.Hp;
+    const int64_t pbase = (int64_t)r * a.Wp * a.Ca;
+    if (gm.p_pad) stage_padded(Pb, a.P + pbase, a.Wp, a.Ca >> 2, gm.cap);
+    else pmis[sidx] = stage_linear(Pb, a.P, pbase, 0, a.Wp * a.Ca);
+    const int qb = a.s * i + a.oy + dlo;            // first row of the span (may be outside the image)
+    const int lo = qb < 0 ? 0 : qb, hi = qb + 2 >= a.Hq ? a.Hq - 1 : qb + 2;
+    if (lo <= hi) {
+      if (gm.q_pad) {
+        stage_padded(Qb + (lo - qb) * qrow_f, a.Q + (((int64_t)n * a.Hq + lo) * a.Wq) * a.Cb, (hi - lo + 1) * a.Wq,
+                     a.Cb >> 2, gm.cbp);
+      } else {
+        const int rowf = a.Wq * a.Cb;
+        qmis[sidx] = stage_linear(Qb, a.Q, ((int64_t)n * a.Hq + qb) * rowf, (lo - qb) * rowf, (hi - qb + 1) * rowf);
+      }
+    }
+    cp_async_commit();
+  };
+
+  if (r0 < r1) stage(r0, 0);
+  for (int r = r0; r < r1; ++r) {
+    const int sidx = (r - r0) & 1;
+    if (r + 1 < r1) { stage(r + 1, sidx ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    const int i = r % a.Hp;
+    const int qy = a.s * i + a.d * kh + a.oy;
+    if (active && qy >= 0 && qy < a.Hq) {
+      const float* Pb = sm + sidx * stage_floats + (gm.p_pad ? 0 : pmis[sidx]) + a0;
+      const float* Qb = sm + sidx * stage_floats + gm.p_floats + (gm.q_pad ? 0 : qmis[sidx]) + rsel * qrow_f + qoff * gm.cbp + b0;
+      int j = ph;
+      while (j < jlo) j += gm.nph;
+#pragma unroll 2
+      for (; j < jhi; j += gm.nph) {
+        float pv[RA], qv[RB];
+        const float* pp = Pb + j * gm.cap;
+        if (pvec) {
+#pragma unroll
+          for (int x = 0; x < RA / 4; ++x) {
+            const float4 v = reinterpret_cast<const float4*>(pp)[x];
+            pv[x * 4] = v.x; pv[x * 4 + 1] = v.y; pv[x * 4 + 2] = v.z; pv[x * 4 + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int x = 0; x < RA; ++x) pv[x] = (a0 + x < a.Ca) ? pp[x] : 0.f;
+        }
+        const float* qp = Qb + (a.s * j) * gm.cbp;
+        if (qvec) {
+#pragma unroll
+          for (int y = 0; y < RB / 4; ++y) {
+            const float4 v = reinterpret_cast<const float4*>(qp)[y];
+            qv[y * 4] = v.x; qv[y * 4 + 1] = v.y; qv[y * 4 + 2] = v.z; qv[y * 4 + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int y = 0; y < RB; ++y) qv[y] = (b0 + y < a.Cb) ? qp[y] : 0.f;
+        }
+#pragma unroll
+        for (int x = 0; x < RA; ++x)
+#pragma unroll
+          for (int y = 0; y < RB; ++y) acc[x][y] = fmaf(pv[x], qv[y], acc[x][y]);
+        if (cs_thread) {
+#pragma unroll
+          for (int x = 0; x < RA; ++x) bsum[x] += pv[x];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // fold the pixel phases: sm reused as [nph][E + Ca]
+  const int FE = E + (gm.want_colsum ? a.Ca : 0);
+  if (active) {
+#pragma unroll
+    for (int x = 0; x < RA; ++x)
+#pragma unroll
+      for (int y = 0; y < RB; ++y)
+        if (a0 + x < a.Ca && b0 + y < a.Cb) sm[ph * FE + (tap * a.Ca + a0 + x) * a.Cb + b0 + y] = acc[x][y];
+    if (cs_thread) {
+#pragma unroll
+      for (int x = 0; x < RA; ++x)
+        if (a0 + x < a.Ca) sm[ph * FE + E + a0 + x] = bsum[x];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < FE; e += blockDim.x) {
+    float t = 0.f;
+    for (int p = 0; p < gm.nph; ++p) t += sm[p * FE + e];
+    a.partial[(int64_t)blockIdx.x * gm.pstride + e] = t;
+  }
+}
+
+// out[...] = sum over `nparts` partial vectors (stride `pstride`), 8 threads per entry in a fixed order;
+// entries >= E are the fused column sums of P
+constexpr int WR_SLICES = 8;
+__global__ void __launch_bounds__(256) wgrad_reduce_sliced_kernel(const float* __restrict__ partial, int nparts, int pstride,
+                                                                  int E, int FE, int Ca, int Cb, int o_sa, int o_sb,
+                                                                  float* __restrict__ out, float* __restrict__ pcolsum) {
+  __shared__ float red[256];
+  const int oi = threadIdx.x / WR_SLICES, sl = threadIdx.x % WR_SLICES;
+  const int e = blockIdx.x * (256 / WR_SLICES) + oi;
+  float t = 0.f;
+  if (e < FE) {
+    const int per = (nparts + WR_SLICES - 1) / WR_SLICES;
+    const int c0 = sl * per, c1 = min(nparts, c0 + per);
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) t += __ldg(partial + (int64_t)c * pstride + e);
+  }
+  red[threadIdx.x] = t;
+  __syncthreads();
+  if (sl == 0 && e < FE) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < WR_SLICES; ++i) v += red[threadIdx.x + i];
+    if (e < E) {
+      const int cb = e % Cb, ca = (e / Cb) % Ca, tap = e / (Cb * Ca);
+      out[(int64_t)tap * Ca * Cb + (int64_t)ca * o_sa + (int64_t)cb * o_sb] = v;
+    } else {
+      pcolsum[e - E] = v;
+    }
+  }
+}
+
 struct WgradPlan { int ra, rb, n_at, n_bt, nph, seg, cbp, blocks, rpc; size_t smem; bool ok; };
 static WgradPlan wgrad_plan(int B, int Hp, int Wp, int Ca, int Cb, int s) {
   WgradPlan p{};
@@ -652,9 +865,76 @@ static WgradPlan wgrad_plan(int B, int Hp, int Wp, int Ca, int Cb, int s) {
   return p;
 }
 
-void conv_wgrad(const WgradArgs& a, cudaStream_t st) {
+void colsum(const float* in, int64_t rows, int C, float* out, float* partial, cudaStream_t st);
+struct RowsPlan { WgradRowsGeom g; int ra, rb, blocks; size_t smem; bool ok; };
+static RowsPlan wgrad_rows_plan(const WgradArgs& a) {
+  RowsPlan p{};
+  const int Ca = a.Ca, Cb = a.Cb;
+  if (Ca == 3 && Cb % 8 == 0) { p.ra = 3; p.rb = 8; }
+  else if (Ca == 5 && Cb % 8 == 0) { p.ra = 5; p.rb = 8; }
+  else if (Cb == 3 && Ca % 8 == 0) { p.ra = 8; p.rb = 3; }
+  else if (Cb == 5 && Ca % 8 == 0) { p.ra = 8; p.rb = 5; }
+  else { p.ra = 4; p.rb = 4; }
+  WgradRowsGeom& g = p.g;
+  g.n_at = cdiv(Ca, p.ra); g.n_bt = cdiv(Cb, p.rb);
+  const int n_et = 9 * g.n_at * g.n_bt;
+  g.nph = 256 / n_et;
+  if (g.nph < 1 || (a.d != 1 && a.d != -1)) return p;
+  g.p_pad = (Ca % 4 == 0) && ((uintptr_t)a.P % 16 == 0);
+  g.q_pad = (Cb % 4 == 0) && ((uintptr_t)a.Q % 16 == 0);
+  g.cap = g.p_pad ? Ca + 4 : Ca;
+  g.cbp = g.q_pad ? Cb + 4 : Cb;
+  g.p_floats = g.p_pad ? a.Wp * g.cap : ((a.Wp * Ca + 4 + 3) & ~3);
+  g.q_floats = g.q_pad ? 3 * a.Wq * g.cbp : ((3 * a.Wq * Cb + 4 + 3) & ~3);
+  // the fused column sum of P rides on the centre tap, which must be in range for every pixel
+  auto centre_ok = [&](int np, int nq, int off) { return a.d + off >= 0 && a.s * (np - 1) + a.d + off < nq; };
+  g.want_colsum = a.pcolsum && centre_ok(a.Hp, a.Hq, a.oy) && centre_ok(a.Wp, a.Wq, a.ox);
+  const int E = 9 * Ca * Cb;
+  g.pstride = E + (g.want_colsum ? Ca : 0);
+  const size_t stage = (size_t)2 * (g.p_floats + g.q_floats);
+  const size_t fold = (size_t)g.nph * g.pstride;
+  p.smem = (stage > fold ? stage : fold) * sizeof(float);
+  if (p.smem > 200 * 1024) return p;
+  g.rows = a.B * a.Hp;
+  const int per_sm = p.smem <= 100 * 1024 ? 2 : 1;
+  int blocks = kNumSMs * per_sm;
+  if (blocks > g.rows) blocks = g.rows;
+  g.rows_per_block = cdiv(g.rows, blocks);
+  p.blocks = cdiv(g.rows, g.rows_per_block);
+  p.ok = p.blocks >= 1;
+  return p;
+}
+
+// returns true when the column sums of P (a.pcolsum) still have to be computed separately
+static bool conv_wgrad_impl(const WgradArgs& a, cudaStream_t st) {
   ProfScope prof_("wgrad", st);
   const int E = 9 * a.Ca * a.Cb;
+  const RowsPlan rp = wgrad_rows_plan(a);
+  if (rp.ok) {
+    g_launches += 2;
+#ifndef KCVAE_EMU
+#define KC_WR_ATTR(k) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rp.smem)
+#else
+#define KC_WR_ATTR(k)
+#endif
+#define KC_WR_LAUNCH(RA_, RB_)                                   \
+  {                                                              \
+    auto k = wgrad_rows_kernel<RA_, RB_>;                        \
+    KC_WR_ATTR(k);                                               \
+    KC_LAUNCH(k, rp.blocks, 256, rp.smem, st, a, rp.g);          \
+  }
+    if (rp.ra == 3 && rp.rb == 8) KC_WR_LAUNCH(3, 8)
+    else if (rp.ra == 5 && rp.rb == 8) KC_WR_LAUNCH(5, 8)
+    else if (rp.ra == 8 && rp.rb == 3) KC_WR_LAUNCH(8, 3)
+    else if (rp.ra == 8 && rp.rb == 5) KC_WR_LAUNCH(8, 5)
+    else KC_WR_LAUNCH(4, 4)
+#undef KC_WR_LAUNCH
+#undef KC_WR_ATTR
+    const int FE = rp.g.pstride;
+    KC_LAUNCH(wgrad_reduce_sliced_kernel, cdiv(FE, 256 / WR_SLICES), 256, 0, st, a.partial, rp.blocks, rp.g.pstride, E, FE,
+              a.Ca, a.Cb, a.o_sa, a.o_sb, a.out, a.pcolsum);
+    return a.pcolsum && !rp.g.want_colsum;
+  }
   const WgradPlan pl = wgrad_plan(a.B, a.Hp, a.Wp, a.Ca, a.Cb, a.s);
   if (pl.ok) {
     const int rows_t = a.B * a.Hp;
@@ -678,16 +958,21 @@ void conv_wgrad(const WgradArgs& a, cudaStream_t st) {
 #undef KC_WG_LAUNCH
 #undef KC_WG_ATTR
     KC_LAUNCH(wgrad_reduce_kernel, cdiv(E, 256), 256, 0, st, a.partial, pl.blocks, E, a.Ca, a.Cb, a.o_sa, a.o_sb, a.out);
-    return;
+  } else {
+    const int chunks = wgrad_chunks(a.B, a.Hp, a.Ca, a.Cb);
+    const int rows = a.B * a.Hp;
+    const int rpc = cdiv(rows, chunks);
+    dim3 grid(cdiv(E, 256), cdiv(rows, rpc));
+    g_launches += 2;
+    KC_LAUNCH(wgrad_kernel, grid, 256, 0, st, a, E, rows, rpc);
+    KC_LAUNCH(wgrad_reduce_kernel, cdiv(E, 256), 256, 0, st, a.partial, (int)grid.y, E, a.Ca, a.Cb,
+              a.o_sa, a.o_sb, a.out);
   }
-  const int chunks = wgrad_chunks(a.B, a.Hp, a.Ca, a.Cb);
-  const int rows = a.B * a.Hp;
-  const int rpc = cdiv(rows, chunks);
-  dim3 grid(cdiv(E, 256), cdiv(rows, rpc));
-  g_launches += 2;
-  KC_LAUNCH(wgrad_kernel, grid, 256, 0, st, a, E, rows, rpc);
-  KC_LAUNCH(wgrad_reduce_kernel, cdiv(E, 256), 256, 0, st, a.partial, (int)grid.y, E, a.Ca, a.Cb,
-            a.o_sa, a.o_sb, a.out);
+  return a.pcolsum != nullptr;
+}
+
+void conv_wgrad(const WgradArgs& a, cudaStream_t st) {
+  if (conv_wgrad_impl(a, st)) colsum(a.P, (int64_t)a.B * a.Hp * a.Wp, a.Ca, a.pcolsum, a.partial, st);
 }
 
 // ---------------------------------------------------------------------- column sums

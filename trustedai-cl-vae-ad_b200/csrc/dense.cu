@@ -110,4 +110,234 @@ void gemm(const GemmArgs& a, cudaStream_t st) {
   }
 }
 
+// =========================================================================================
+// Wide Dense: the decoder Dense (src/abstract_cvae.py:76) has K = latent (tens) and
+// N = h0*w0*filters (1e5): pure weight/activation streaming.  Three bandwidth kernels replace
+// five generic GEMM launches; every global access is a coalesced float4.
+//   forward   C[b,n]  = relu(bias[n] + sum_k A[b,k] W[k,n])
+//   wgrad     dW[k,n] = sum_b A[b,k] G[b,n]      db[n] = sum_b G[b,n]      (one read of G)
+//   dgrad     dA[b,k] = sum_n G[b,n] W[k,n]      (deterministic two-level reduction over n)
+// =========================================================================================
+constexpr int DW_BT = 8;          // batch rows per thread (forward)
+constexpr int DW_KT = 32;         // k rows per block (wgrad)
+constexpr int DG_NC = 128;        // columns per staged chunk (dgrad)
+constexpr int DG_LD = DG_NC + 4;  // smem row stride == 4 (mod 32): conflict-free float4 reads
+constexpr int DG_SLICES = 8;
+
+bool dense_wide_ok(const void* A, const void* W, const void* C, const void* bias, int M, int N, int K) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return M > 0 && K > 0 && N >= 64 && (N & 3) == 0 && K <= 4096 && al(A) && al(W) && al(C) && (!bias || al(bias));
+}
+
+__global__ void __launch_bounds__(128) dense_wide_fwd_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                             const float* __restrict__ bias, float* __restrict__ C,
+                                                             int M, int N, int K, int relu) {
+  KC_DYN_SMEM(float, As);   // [DW_BT][K]
+  const int m0 = blockIdx.y * DW_BT;
+  for (int i = threadIdx.x; i < DW_BT * K; i += blockDim.x) {
+    const int r = i / K, k = i - r * K;
+    As[i] = (m0 + r < M) ? __ldg(A + (int64_t)(m0 + r) * K + k) : 0.f;
+  }
+  __syncthreads();
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (n >= N) return;
+  float acc[DW_BT][4];
+#pragma unroll
+  for (int r = 0; r < DW_BT; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+  const float4* wp = reinterpret_cast<const float4*>(W + n);
+  const int64_t wstride = N >> 2;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    const float4 w = __ldg(wp + (int64_t)k * wstride);
+#pragma unroll
+    for (int r = 0; r < DW_BT; ++r) {
+      const float a = As[r * K + k];
+      acc[r][0] = fmaf(a, w.x, acc[r][0]); acc[r][1] = fmaf(a, w.y, acc[r][1]);
+      acc[r][2] = fmaf(a, w.z, acc[r][2]); acc[r][3] = fmaf(a, w.w, acc[r][3]);
+    }
+  }
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+#pragma unroll
+  for (int r = 0; r < DW_BT; ++r) {
+    if (m0 + r >= M) break;
+    float4 y = make_float4(acc[r][0] + b4.x, acc[r][1] + b4.y, acc[r][2] + b4.z, acc[r][3] + b4.w);
+    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+    *reinterpret_cast<float4*>(C + (int64_t)(m0 + r) * N + n) = y;
+  }
+}
+
+void dense_wide_forward(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
+                        cudaStream_t st) {
+  ProfScope prof_("dense_wide_fwd", st);
+  dim3 grid(cdiv(N / 4, 128), cdiv(M, DW_BT));
+  const size_t smem = (size_t)DW_BT * K * sizeof(float);
+  ++g_launches;
+#ifndef KCVAE_EMU
+  if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  KC_LAUNCH(dense_wide_fwd_kernel, grid, 128, smem, st, A, W, bias, C, M, N, K, relu);
+}
+
+// block (64 column quads) x (4 k-subgroups of 8): dW tile [32 k][256 n]; grid.y = k tiles
+__global__ void __launch_bounds__(256) dense_wide_wgrad_kernel(const float* __restrict__ A, const float* __restrict__ G,
+                                                               float* __restrict__ dW, float* __restrict__ db,
+                                                               int M, int N, int K) {
+  KC_DYN_SMEM(float, At);   // [M][DW_KT] slice of A for this k tile (zero padded)
+  const int k0 = blockIdx.y * DW_KT;
+  for (int i = threadIdx.x; i < M * DW_KT; i += blockDim.x) {
+    const int b = i / DW_KT, kk = i - b * DW_KT;
+    At[i] = (k0 + kk < K) ? __ldg(A + (int64_t)b * K + k0 + kk) : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int n = (blockIdx.x * 64 + tx) * 4;
+  if (n >= N) return;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* gp = reinterpret_cast<const float4*>(G + n);
+  const int64_t gstride = N >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(At) + ty * 2;
+#pragma unroll 4
+  for (int b = 0; b < M; ++b) {
+    const float4 g = __ldg(gp + (int64_t)b * gstride);
+    const float4 x0 = a4[b * (DW_KT / 4)], x1 = a4[b * (DW_KT / 4) + 1];
+    const float av[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i][0] = fmaf(av[i], g.x, acc[i][0]); acc[i][1] = fmaf(av[i], g.y, acc[i][1]);
+      acc[i][2] = fmaf(av[i], g.z, acc[i][2]); acc[i][3] = fmaf(av[i], g.w, acc[i][3]);
+    }
+    bs.x += g.x; bs.y += g.y; bs.z += g.z; bs.w += g.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + ty * 8 + i;
+    if (k < K) *reinterpret_cast<float4*>(dW + (int64_t)k * N + n) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+  if (db && blockIdx.y == 0 && ty == 0) *reinterpret_cast<float4*>(db + n) = bs;
+}
+
+static int dense_wide_dgrad_blocks(int N) {
+  int nb = cdiv(N, DG_NC);
+  if (nb > kNumSMs * 2) nb = kNumSMs * 2;
+  return nb;
+}
+size_t dense_wide_partial_floats(int M, int N, int K) {
+  return (size_t)dense_wide_dgrad_blocks(N) * cdiv(M, 32) * cdiv(K, 32) * 1024;
+}
+
+// grid (column blocks, b tiles, k tiles); thread = 4x4 (b,k) micro tile x one of 4 column phases
+__global__ void __launch_bounds__(256) dense_wide_dgrad_kernel(const float* __restrict__ G, const float* __restrict__ W,
+                                                               float* __restrict__ partial, int M, int N, int K,
+                                                               int cols_per_block) {
+  __shared__ __align__(16) float Gs[32 * DG_LD];
+  __shared__ __align__(16) float Ws[32 * DG_LD];
+  const int tid = threadIdx.x;
+  const int o = tid & 63, phase = tid >> 6;
+  const int tb = o & 7, tk = o >> 3;
+  const int b0 = blockIdx.y * 32, k0 = blockIdx.z * 32;
+  const int c_begin = blockIdx.x * cols_per_block;
+  const int c_end = min(N, c_begin + cols_per_block);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  for (int c0 = c_begin; c0 < c_end; c0 += DG_NC) {
+    __syncthreads();
+    for (int i = tid; i < 32 * (DG_NC / 4); i += 256) {   // coalesced float4 rows
+      const int r = i / (DG_NC / 4), q = i - r * (DG_NC / 4);
+      const int c = c0 + q * 4;
+      float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), wv = gv;
+      if (c < c_end) {
+        if (b0 + r < M) gv = __ldg(reinterpret_cast<const float4*>(G + (int64_t)(b0 + r) * N + c));
+        if (k0 + r < K) wv = __ldg(reinterpret_cast<const float4*>(W + (int64_t)(k0 + r) * N + c));
+      }
+      *reinterpret_cast<float4*>(Gs + r * DG_LD + q * 4) = gv;
+      *reinterpret_cast<float4*>(Ws + r * DG_LD + q * 4) = wv;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int q = phase; q < DG_NC / 4; q += 4) {
+      float4 g[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        g[i] = *reinterpret_cast<const float4*>(Gs + (tb + 8 * i) * DG_LD + q * 4);
+        w[i] = *reinterpret_cast<const float4*>(Ws + (tk + 8 * i) * DG_LD + q * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(g[i].x, w[j].x, acc[i][j]); acc[i][j] = fmaf(g[i].y, w[j].y, acc[i][j]);
+          acc[i][j] = fmaf(g[i].z, w[j].z, acc[i][j]); acc[i][j] = fmaf(g[i].w, w[j].w, acc[i][j]);
+        }
+    }
+  }
+  // fold the 4 column phases (fixed order): Gs reused as [4][32*32]
+  __syncthreads();
+  float* red = Gs;   // 4096 floats <= 32*DG_LD = 4224
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[phase * 1024 + (tb + 8 * i) * 32 + (tk + 8 * j)] = acc[i][j];
+  __syncthreads();
+  float* out = partial + (((int64_t)blockIdx.x * gridDim.y + blockIdx.y) * gridDim.z + blockIdx.z) * 1024;
+  for (int e = tid; e < 1024; e += 256) out[e] = (red[e] + red[1024 + e]) + (red[2048 + e] + red[3072 + e]);
+}
+
+// dA[b,k] = sum over column blocks, DG_SLICES threads per output, fixed summation order
+__global__ void __launch_bounds__(256) dense_wide_dgrad_reduce_kernel(const float* __restrict__ partial, int nblk, int M,
+                                                                      int K, int bt, int kt, float* __restrict__ dA) {
+  __shared__ float red[256];
+  const int oi = threadIdx.x / DG_SLICES, sl = threadIdx.x % DG_SLICES;
+  const int64_t out_idx = (int64_t)blockIdx.x * (256 / DG_SLICES) + oi;
+  const int64_t total = (int64_t)M * K;
+  float s = 0.f;
+  if (out_idx < total) {
+    const int b = (int)(out_idx / K), k = (int)(out_idx % K);
+    const int tile = (b >> 5) * kt + (k >> 5), e = (b & 31) * 32 + (k & 31);
+    const int per = (nblk + DG_SLICES - 1) / DG_SLICES;
+    const int j0 = sl * per, j1 = min(nblk, j0 + per);
+    const int64_t stride = (int64_t)bt * kt * 1024;
+    const float* p = partial + (int64_t)tile * 1024 + e;
+#pragma unroll 4
+    for (int j = j0; j < j1; ++j) s += __ldg(p + (int64_t)j * stride);
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (sl == 0 && out_idx < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < DG_SLICES; ++i) t += red[threadIdx.x + i];
+    dA[out_idx] = t;
+  }
+}
+
+// G [M,N] (gradient of the Dense output, ReLU mask already applied), A [M,K], W [K,N]
+void dense_wide_backward(const float* A, const float* G, const float* W, float* dW, float* db, float* dA, float* partial,
+                         int M, int N, int K, cudaStream_t st) {
+  {
+    ProfScope prof_("dense_wide_wgrad", st);
+    dim3 grid(cdiv(N / 4, 64), cdiv(K, DW_KT));
+    const size_t smem = (size_t)M * DW_KT * sizeof(float);
+    ++g_launches;
+#ifndef KCVAE_EMU
+    if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    KC_LAUNCH(dense_wide_wgrad_kernel, grid, 256, smem, st, A, G, dW, db, M, N, K);
+  }
+  if (dA) {
+    ProfScope prof_("dense_wide_dgrad", st);
+    const int nblk = dense_wide_dgrad_blocks(N);
+    const int cpb = cdiv(cdiv(N, nblk), DG_NC) * DG_NC;
+    const int nb = cdiv(N, cpb);
+    const int bt = cdiv(M, 32), kt = cdiv(K, 32);
+    g_launches += 2;
+    KC_LAUNCH(dense_wide_dgrad_kernel, dim3(nb, bt, kt), 256, 0, st, G, W, partial, M, N, K, cpb);
+    KC_LAUNCH(dense_wide_dgrad_reduce_kernel, cdiv((int64_t)M * K, 256 / DG_SLICES), 256, 0, st, partial, nb, M, K, bt, kt, dA);
+  }
+}
+
 }  // namespace kc

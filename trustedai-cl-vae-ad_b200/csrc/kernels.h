@@ -30,6 +30,7 @@ struct WgradArgs {
   const float* Q;  // [B,Hq,Wq,Cb]
   float* out;      // 9*Ca*Cb
   float* partial;  // workspace, >= wgrad_partial_floats()
+  float* pcolsum;  // optional [Ca]: sum over all pixels of P (bias gradient when P is a gradient), same pass
   int B, Hp, Wp, Ca, Hq, Wq, Cb;
   int s, d, oy, ox;  // qy = s*i + d*kh + oy ; qx = s*j + d*kw + ox
   int o_sa, o_sb;
@@ -54,6 +55,16 @@ struct GemmArgs {
 };
 size_t gemm_partial_floats(int M, int N, int K);
 void gemm(const GemmArgs& a, cudaStream_t st);
+
+// Wide Dense (K small, N huge, everything row-major and 16-byte aligned): streaming kernels for
+// the decoder Dense.  dense_wide_ok() says whether the shapes / pointers qualify.
+bool dense_wide_ok(const void* A, const void* W, const void* C, const void* bias, int M, int N, int K);
+void dense_wide_forward(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
+                        cudaStream_t st);
+size_t dense_wide_partial_floats(int M, int N, int K);
+// dW[K,N] = A^T G, db[N] = colsum(G) (db may be nullptr), dA[M,K] = G W^T (dA may be nullptr)
+void dense_wide_backward(const float* A, const float* G, const float* W, float* dW, float* db, float* dA, float* partial,
+                         int M, int N, int K, cudaStream_t st);
 
 // --------------------------------------------------------------------- loss (loss.cu)
 // slots of the fp64 `sums` vector shared by the loss kernels (all-reduced under DP)

@@ -247,6 +247,7 @@ size_t max_partial_floats(const kcvae_model* h, int B) {
   up(gemm_partial_floats(B, h->dec_units, h->latent));
   up(gemm_partial_floats(h->latent, h->dec_units, B));
   up(gemm_partial_floats(B, h->latent, h->dec_units));
+  up(dense_wide_partial_floats(B, h->dec_units, h->latent));
   up(gemm_partial_floats(kin, 2 * h->latent, B));
   up(gemm_partial_floats(B, kin, 2 * h->latent));
   up(gemm_partial_floats(h->flat, h->enc_dense, B));
@@ -391,7 +392,10 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   ga.C = h->act_d[0]; ga.bias = h->wp(h->vi_dec_dense() + 1); ga.relu = 1;
   ga.M = B; ga.N = h->dec_units; ga.K = h->latent; ga.partial = h->partial;
   g_tag = "dec.dense.fwd";
-  gemm(ga, st);
+  if (dense_wide_ok(z, ga.Bm, ga.C, ga.bias, B, h->dec_units, h->latent))
+    dense_wide_forward(z, ga.Bm, ga.bias, ga.C, B, h->dec_units, h->latent, 1, st);
+  else
+    gemm(ga, st);
   for (int l = 0; l < L; ++l) {
     ConvArgs a{};
     a.in = h->act_d[l]; a.w = h->wp(h->vi_dec_convT(l)); a.bias = h->wp(h->vi_dec_convT(l) + 1); a.out = h->act_d[l + 1];
@@ -602,17 +606,22 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     const int vi = h->vi_dec_dense();
     const float* G = h->g_act_d[0];
     g_tag = "dec.dense.bwd";
-    GemmArgs ga{};
-    ga.A = h->z; ga.a_sm = 1; ga.a_sk = h->latent;
-    ga.Bm = G; ga.b_sk = h->dec_units; ga.b_sn = 1;
-    ga.C = h->gp(vi); ga.M = h->latent; ga.N = h->dec_units; ga.K = B; ga.partial = h->partial;
-    gemm(ga, st);
-    colsum(G, B, h->dec_units, h->gp(vi + 1), h->partial, st);
-    GemmArgs gz{};
-    gz.A = G; gz.a_sm = h->dec_units; gz.a_sk = 1;
-    gz.Bm = h->wp(vi); gz.b_sk = 1; gz.b_sn = h->dec_units;
-    gz.C = h->g_z; gz.M = B; gz.N = h->latent; gz.K = h->dec_units; gz.partial = h->partial;
-    gemm(gz, st);
+    if (dense_wide_ok(h->z, h->wp(vi), h->gp(vi), h->gp(vi + 1), B, h->dec_units, h->latent) &&
+        dense_wide_ok(G, h->g_z, h->gp(vi), nullptr, B, h->dec_units, h->latent)) {
+      dense_wide_backward(h->z, G, h->wp(vi), h->gp(vi), h->gp(vi + 1), h->g_z, h->partial, B, h->dec_units, h->latent, st);
+    } else {
+      GemmArgs ga{};
+      ga.A = h->z; ga.a_sm = 1; ga.a_sk = h->latent;
+      ga.Bm = G; ga.b_sk = h->dec_units; ga.b_sn = 1;
+      ga.C = h->gp(vi); ga.M = h->latent; ga.N = h->dec_units; ga.K = B; ga.partial = h->partial;
+      gemm(ga, st);
+      colsum(G, B, h->dec_units, h->gp(vi + 1), h->partial, st);
+      GemmArgs gz{};
+      gz.A = G; gz.a_sm = h->dec_units; gz.a_sk = 1;
+      gz.Bm = h->wp(vi); gz.b_sk = 1; gz.b_sn = h->dec_units;
+      gz.C = h->g_z; gz.M = B; gz.N = h->latent; gz.K = h->dec_units; gz.partial = h->partial;
+      gemm(gz, st);
+    }
   }
   if (h->world > 1) {
     // every decoder gradient is final: reduce that range (93 % of the parameters) under the encoder backward
@@ -679,8 +688,8 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     wa.s = 2; wa.d = 1; wa.oy = -pt; wa.ox = -pl;
     wa.o_sa = 1; wa.o_sb = wa.Ca;  // HWIO: [tap][in=b][out=a]
     g_tag = l == 0 ? "enc.conv0.bwd" : (l == 1 ? "enc.conv1.bwd" : "enc.convN.bwd");
+    wa.pcolsum = h->gp(vi + 1);   // bias gradient = column sums of P, same pass
     conv_wgrad(wa, st);
-    colsum(h->g_act_e[l + 1], (int64_t)B * h->eh[l + 1] * h->ew[l + 1], h->ec[l + 1], h->gp(vi + 1), h->partial, st);
     if (l > 0) {
       ConvArgs a{};
       a.in = h->g_act_e[l + 1]; a.w = h->wp(vi); a.mask = h->act_e[l]; a.out = h->g_act_e[l];
