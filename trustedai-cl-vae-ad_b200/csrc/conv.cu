@@ -349,6 +349,289 @@ __global__ void __launch_bounds__(128) convT_s2_many2few_kernel(ConvArgs a, int6
   }
 }
 
+// =========================================================================================
+// Lane-mapped kernels for the 32-channel <-> few-channel layers.  The 32-channel side is spread
+// over the lanes of a warp, so every global access of that side is one coalesced 128-byte line
+// and no shared-memory bank is hit twice:
+//   *_lane_co : few -> many.  lane = output channel; its 9*CI weights live in registers; the
+//               few-channel input rows are staged in shared memory (zero padded) and read as
+//               warp-broadcast float4.
+//   *_lane_ci : many -> few.  lane = input channel; its 9*CO weights live in registers; the
+//               partial sums of a pixel group are folded across the warp with a butterfly that
+//               halves the value count at every step (fixed order, deterministic).
+// =========================================================================================
+__device__ __forceinline__ float lane_epi(float v, int epi, const float* mask, int64_t o) {
+  if (epi == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+  else if (epi == EPI_BIAS_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+  else if (epi == EPI_MASK) v = __ldg(mask + o) > 0.f ? v : 0.f;
+  return v;
+}
+
+// ---- Conv2D s2, CI in {3,4,5,8} -> Co = 32*k.  block = one output row, warp = groups of 4 pixels
+template <int CI>
+__global__ void __launch_bounds__(256) conv_s2_lane_co_kernel(ConvArgs a, int rows, int epi) {
+  KC_DYN_SMEM(float, srow);
+  constexpr int NV = (9 * CI + 3) / 4;           // float4 loads per input row per group
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int co = blockIdx.y * 32 + lane;
+  float w[9][CI];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) w[t][ci] = __ldg(a.w + (int64_t)t * CI * a.Co + (int64_t)ci * a.w_sci + (int64_t)co * a.w_sco);
+  const float bias = (a.bias && epi != EPI_MASK) ? __ldg(a.bias + co) : 0.f;
+  const int Wo4 = (a.Wo + 3) & ~3;
+  const int ncolf = (2 * Wo4 + 1) * CI;           // staged floats per row: column c holds ix = c - pad_l
+  const int RW = ((ncolf + 3) & ~3) + 4;
+  const int shift = a.pad_l * CI, rowf = a.Wi * CI;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / a.Ho, oy = row % a.Ho;
+    __syncthreads();
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = 2 * oy + kh - a.pad_t;
+      const bool vrow = iy >= 0 && iy < a.Hi;
+      const float* src = a.in + ((int64_t)n * a.Hi + (vrow ? iy : 0)) * rowf;
+      float* dst = srow + kh * RW;
+      for (int e = threadIdx.x; e < RW; e += blockDim.x) {
+        const int g = e - shift;
+        dst[e] = (vrow && g >= 0 && g < rowf) ? __ldg(src + g) : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int grp = warp; grp < (Wo4 >> 2); grp += nwarps) {
+      const int ox0 = grp * 4;
+      float acc[4] = {bias, bias, bias, bias};
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const float4* rp = reinterpret_cast<const float4*>(srow + kh * RW + 2 * ox0 * CI);
+        float v[NV * 4];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          const float4 t = rp[q];
+          v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) acc[p] = fmaf(v[(2 * p + kw) * CI + ci], w[kh * 3 + kw][ci], acc[p]);
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int ox = ox0 + p;
+        if (ox < a.Wo) {
+          const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox) * a.Co + co;
+          a.out[o] = lane_epi(acc[p], epi, a.mask, o);
+        }
+      }
+    }
+  }
+}
+
+// ---- Conv2DTranspose s2 (pad 0, Ho = 2 Hi, Wo = 2 Wi), CI in {3,4,5,8} -> Co = 32*k.
+// block = one input row i (output rows 2i, 2i+1), warp = groups of 4 input pixels (8 output columns)
+template <int CI>
+__global__ void __launch_bounds__(256) convT_s2_lane_co_kernel(ConvArgs a, int rows, int epi) {
+  KC_DYN_SMEM(float, srow);
+  constexpr int NV = (5 * CI + 3) / 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int co = blockIdx.y * 32 + lane;
+  float w[9][CI];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) w[t][ci] = __ldg(a.w + (int64_t)t * CI * a.Co + (int64_t)ci * a.w_sci + (int64_t)co * a.w_sco);
+  const float bias = (a.bias && epi != EPI_MASK) ? __ldg(a.bias + co) : 0.f;
+  const int Wi4 = (a.Wi + 3) & ~3;
+  const int ncolf = (Wi4 + 1) * CI;               // column c holds ix = c - 1
+  const int RW = ((ncolf + 3) & ~3) + 4;
+  const int rowf = a.Wi * CI;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / a.Hi, i = row % a.Hi;
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {                 // r = 0: input row i-1, r = 1: input row i
+      const int iy = i - 1 + r;
+      const bool vrow = iy >= 0;
+      const float* src = a.in + ((int64_t)n * a.Hi + (vrow ? iy : 0)) * rowf;
+      float* dst = srow + r * RW;
+      for (int e = threadIdx.x; e < RW; e += blockDim.x) {
+        const int g = e - CI;
+        dst[e] = (vrow && g >= 0 && g < rowf) ? __ldg(src + g) : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int grp = warp; grp < (Wi4 >> 2); grp += nwarps) {
+      const int j0 = grp * 4;
+      float acc[2][8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { acc[0][c] = bias; acc[1][c] = bias; }
+      float v[NV * 4];
+      {  // input row i-1: taps kh = 2 land on output row 2i
+        const float4* rp = reinterpret_cast<const float4*>(srow + j0 * CI);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) { const float4 t = rp[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int ci = 0; ci < CI; ++ci) {
+            const float xc = v[(q + 1) * CI + ci], xl = v[q * CI + ci];   // input columns j0+q and j0+q-1
+            acc[0][2 * q] = fmaf(xc, w[6][ci], fmaf(xl, w[8][ci], acc[0][2 * q]));
+            acc[0][2 * q + 1] = fmaf(xc, w[7][ci], acc[0][2 * q + 1]);
+          }
+      }
+      {  // input row i: kh = 0 -> output row 2i, kh = 1 -> output row 2i+1
+        const float4* rp = reinterpret_cast<const float4*>(srow + RW + j0 * CI);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) { const float4 t = rp[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int ci = 0; ci < CI; ++ci) {
+            const float xc = v[(q + 1) * CI + ci], xl = v[q * CI + ci];
+            acc[0][2 * q] = fmaf(xc, w[0][ci], fmaf(xl, w[2][ci], acc[0][2 * q]));
+            acc[0][2 * q + 1] = fmaf(xc, w[1][ci], acc[0][2 * q + 1]);
+            acc[1][2 * q] = fmaf(xc, w[3][ci], fmaf(xl, w[5][ci], acc[1][2 * q]));
+            acc[1][2 * q + 1] = fmaf(xc, w[4][ci], acc[1][2 * q + 1]);
+          }
+      }
+#pragma unroll
+      for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int ox = 2 * j0 + c;
+          if (ox < a.Wo) {
+            const int64_t o = (((int64_t)n * a.Ho + 2 * i + pa) * a.Wo + ox) * a.Co + co;
+            a.out[o] = lane_epi(acc[pa][c], epi, a.mask, o);
+          }
+        }
+    }
+  }
+}
+
+// N partial values per lane -> their warp totals, one per lane: at every step the lanes exchange
+// half of the values with the partner lane^O and keep the other half.
+template <int N, int O>
+__device__ __forceinline__ void lane_fold(float* v, int lane) {
+  if constexpr (O >= 1) {
+    constexpr int H = (N + 1) / 2;
+    const bool up = (lane & O) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      const float lo = v[i];
+      const float hi = (i + H < N) ? v[i + H] : 0.f;
+      const float keep = up ? hi : lo, send = up ? lo : hi;
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+    }
+    lane_fold<H, O / 2>(v, lane);
+  }
+}
+// index of the value whose total ends up in v[0] of `lane` after lane_fold<N,16>, or -1
+template <int N, int O>
+__device__ __forceinline__ int lane_fold_index(int lane) {
+  if constexpr (O >= 1) {
+    constexpr int H = (N + 1) / 2;
+    const int sub = lane_fold_index<H, O / 2>(lane);
+    if (sub < 0) return -1;
+    const int i = sub + ((lane & O) ? H : 0);
+    return i < N ? i : -1;
+  } else {
+    return 0;
+  }
+}
+
+// ---- Conv2D s2, Ci = 32 -> CO in {5,8}.  warp = pairs of adjacent output pixels
+template <int CO>
+__global__ void __launch_bounds__(256) conv_s2_lane_ci_kernel(ConvArgs a, int64_t npairs, int WP, int epi) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float w[9][CO];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int co = 0; co < CO; ++co) w[t][co] = __ldg(a.w + (int64_t)t * 32 * CO + (int64_t)lane * a.w_sci + (int64_t)co * a.w_sco);
+  const int idx = lane_fold_index<16, 16>(lane);
+  const int mp = idx >> 3, mco = idx & 7;
+  const bool writer = idx >= 0 && mco < CO;
+  const float bias = (writer && a.bias && epi != EPI_MASK) ? __ldg(a.bias + mco) : 0.f;
+  for (int64_t pr = gw; pr < npairs; pr += nw) {
+    const int pp = (int)(pr % WP);
+    const int oy = (int)((pr / WP) % a.Ho);
+    const int n = (int)(pr / ((int64_t)WP * a.Ho));
+    const int ox0 = 2 * pp;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = 2 * oy + kh - a.pad_t;
+      if (iy < 0 || iy >= a.Hi) continue;
+      const float* rowp = a.in + (((int64_t)n * a.Hi + iy) * a.Wi) * 32 + lane;
+      float x[5];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int ix = 2 * ox0 + c - a.pad_l;
+        x[c] = (ix >= 0 && ix < a.Wi) ? __ldg(rowp + (int64_t)ix * 32) : 0.f;
+      }
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+          v[co] = fmaf(x[kw], w[kh * 3 + kw][co], v[co]);
+          v[8 + co] = fmaf(x[2 + kw], w[kh * 3 + kw][co], v[8 + co]);
+        }
+    }
+    lane_fold<16, 16>(v, lane);
+    if (writer && ox0 + mp < a.Wo) {
+      const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox0 + mp) * CO + mco;
+      a.out[o] = lane_epi(v[0] + bias, epi, a.mask, o);
+    }
+  }
+}
+
+// ---- Conv2DTranspose s2 (pad 0, Ho = 2 Hi, Wo = 2 Wi), Ci = 32 -> CO in {5,8}.  warp = one input
+// pixel's 2x2 output quad (9 taps), 4*CO partial sums folded across the warp
+template <int CO>
+__global__ void __launch_bounds__(256) convT_s2_lane_ci_kernel(ConvArgs a, int64_t nq, int epi) {
+  constexpr int NVAL = 4 * CO;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float w[9][CO];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int co = 0; co < CO; ++co) w[t][co] = __ldg(a.w + (int64_t)t * 32 * CO + (int64_t)lane * a.w_sci + (int64_t)co * a.w_sco);
+  const int idx = lane_fold_index<NVAL, 16>(lane);
+  const int mph = idx >= 0 ? idx / CO : 0, mco = idx >= 0 ? idx % CO : 0;
+  const float bias = (idx >= 0 && a.bias && epi != EPI_MASK) ? __ldg(a.bias + mco) : 0.f;
+  for (int64_t q = gw; q < nq; q += nw) {
+    const int j = (int)(q % a.Wi);
+    const int i = (int)((q / a.Wi) % a.Hi);
+    const int n = (int)(q / ((int64_t)a.Wi * a.Hi));
+    const float* px = a.in + ((((int64_t)n * a.Hi + i) * a.Wi) + j) * 32 + lane;
+    const float x00 = __ldg(px);
+    const float x01 = j > 0 ? __ldg(px - 32) : 0.f;                                  // (i, j-1)
+    const float x10 = i > 0 ? __ldg(px - (int64_t)a.Wi * 32) : 0.f;                  // (i-1, j)
+    const float x11 = (i > 0 && j > 0) ? __ldg(px - (int64_t)a.Wi * 32 - 32) : 0.f;  // (i-1, j-1)
+    float v[NVAL];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) {
+      v[0 * CO + co] = fmaf(x00, w[0][co], fmaf(x10, w[6][co], fmaf(x01, w[2][co], x11 * w[8][co])));
+      v[1 * CO + co] = fmaf(x00, w[1][co], x10 * w[7][co]);
+      v[2 * CO + co] = fmaf(x00, w[3][co], x01 * w[5][co]);
+      v[3 * CO + co] = x00 * w[4][co];
+    }
+    lane_fold<NVAL, 16>(v, lane);
+    if (idx >= 0) {
+      const int oy = 2 * i + (mph >> 1), ox = 2 * j + (mph & 1);
+      const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox) * CO + mco;
+      a.out[o] = lane_epi(v[0] + bias, epi, a.mask, o);
+    }
+  }
+}
+
 #ifndef KCVAE_EMU
 #define KC_SET_SMEM(k, bytes) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #else
@@ -363,8 +646,63 @@ __global__ void __launch_bounds__(128) convT_s2_many2few_kernel(ConvArgs a, int6
   }
 
 // returns true if a specialised kernel took the launch
+// lane-mapped kernels: true if one of them took the launch
+static bool conv_forward_lane(int mode, int epi, const ConvArgs& a, cudaStream_t st) {
+  const bool up2 = a.pad_t == 0 && a.pad_l == 0 && a.Ho == 2 * a.Hi && a.Wo == 2 * a.Wi;
+  if (a.Co % 32 == 0 && (a.Ci == 3 || a.Ci == 4 || a.Ci == 5 || a.Ci == 8) && (mode == CONV_S2 || (mode == CONVT_S2 && up2))) {
+    const int rows = mode == CONV_S2 ? a.B * a.Ho : a.B * a.Hi;
+    const int Wq4 = ((mode == CONV_S2 ? a.Wo : a.Wi) + 3) & ~3;
+    const int ncolf = (mode == CONV_S2 ? 2 * Wq4 + 1 : Wq4 + 1) * a.Ci;
+    const int RW = ((ncolf + 3) & ~3) + 4;
+    const size_t smem = (size_t)(mode == CONV_S2 ? 3 : 2) * RW * sizeof(float);
+    if (smem > 160 * 1024) return false;
+    const dim3 grid(rows < kNumSMs * 6 ? rows : kNumSMs * 6, a.Co / 32);
+    ++g_launches;
+#define KC_LANE_CO(KERNEL, CI_)                                 \
+  {                                                             \
+    auto k = KERNEL<CI_>;                                       \
+    if (smem > 48 * 1024) KC_SET_SMEM(k, smem);                 \
+    KC_LAUNCH(k, grid, 256, smem, st, a, rows, epi);            \
+  }
+    if (mode == CONV_S2) {
+      if (a.Ci == 3) KC_LANE_CO(conv_s2_lane_co_kernel, 3)
+      else if (a.Ci == 4) KC_LANE_CO(conv_s2_lane_co_kernel, 4)
+      else if (a.Ci == 5) KC_LANE_CO(conv_s2_lane_co_kernel, 5)
+      else KC_LANE_CO(conv_s2_lane_co_kernel, 8)
+    } else {
+      if (a.Ci == 3) KC_LANE_CO(convT_s2_lane_co_kernel, 3)
+      else if (a.Ci == 4) KC_LANE_CO(convT_s2_lane_co_kernel, 4)
+      else if (a.Ci == 5) KC_LANE_CO(convT_s2_lane_co_kernel, 5)
+      else KC_LANE_CO(convT_s2_lane_co_kernel, 8)
+    }
+#undef KC_LANE_CO
+    return true;
+  }
+  if (a.Ci == 32 && (a.Co == 5 || a.Co == 8)) {
+    if (mode == CONV_S2) {
+      const int WP = cdiv(a.Wo, 2);
+      const int64_t npairs = (int64_t)a.B * a.Ho * WP;
+      const int grid = grid_for(npairs * 32, 256, 8, 4);
+      ++g_launches;
+      if (a.Co == 5) KC_LAUNCH(conv_s2_lane_ci_kernel<5>, grid, 256, 0, st, a, npairs, WP, epi);
+      else KC_LAUNCH(conv_s2_lane_ci_kernel<8>, grid, 256, 0, st, a, npairs, WP, epi);
+      return true;
+    }
+    if (mode == CONVT_S2 && up2) {
+      const int64_t nq = (int64_t)a.B * a.Hi * a.Wi;
+      const int grid = grid_for(nq * 32, 256, 8, 4);
+      ++g_launches;
+      if (a.Co == 5) KC_LAUNCH(convT_s2_lane_ci_kernel<5>, grid, 256, 0, st, a, nq, epi);
+      else KC_LAUNCH(convT_s2_lane_ci_kernel<8>, grid, 256, 0, st, a, nq, epi);
+      return true;
+    }
+  }
+  return false;
+}
+
 static bool conv_forward_special(int mode, int epi, const ConvArgs& a, cudaStream_t st) {
   if (a.B <= 0) return false;
+  if (conv_forward_lane(mode, epi, a, st)) return true;
   const bool aligned = ((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.out % 16 == 0) && (!a.mask || (uintptr_t)a.mask % 16 == 0);
   if (!aligned) return false;
   if (a.Co == MANY && a.Ci <= 8) {
@@ -1009,12 +1347,25 @@ __global__ void colsum_small_kernel(const float* in, int64_t rows, int C, int64_
     partial[(int64_t)blockIdx.x * C + threadIdx.x] = s;
   }
 }
-__global__ void colsum_finish_kernel(const float* partial, int blocks, int C, float* out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.0f;
-  for (int b = 0; b < blocks; ++b) s += partial[(int64_t)b * C + c];
-  out[c] = s;
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* partial, int blocks, int C, float* out) {
+  __shared__ float red[256];   // 8 threads per column, each a contiguous slice of the blocks (fixed order)
+  const int oi = threadIdx.x / WR_SLICES, sl = threadIdx.x % WR_SLICES;
+  const int c = blockIdx.x * (256 / WR_SLICES) + oi;
+  float t = 0.0f;
+  if (c < C) {
+    const int per = (blocks + WR_SLICES - 1) / WR_SLICES;
+    const int b0 = sl * per, b1 = min(blocks, b0 + per);
+#pragma unroll 4
+    for (int b = b0; b < b1; ++b) t += __ldg(partial + (int64_t)b * C + c);
+  }
+  red[threadIdx.x] = t;
+  __syncthreads();
+  if (sl == 0 && c < C) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < WR_SLICES; ++i) s += red[threadIdx.x + i];
+    out[c] = s;
+  }
 }
 __global__ void colsum_large_kernel(const float* in, int64_t rows, int C, float* out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1036,7 +1387,7 @@ void colsum(const float* in, int64_t rows, int C, float* out, float* partial, cu
   const int64_t rpb = (rows + blocks - 1) / blocks;
   g_launches += 2;
   KC_LAUNCH(colsum_small_kernel, blocks, tpb, 0, st, in, rows, C, rpb, partial);
-  KC_LAUNCH(colsum_finish_kernel, cdiv(C, 256), 256, 0, st, partial, blocks, C, out);
+  KC_LAUNCH(colsum_finish_kernel, cdiv(C, 256 / WR_SLICES), 256, 0, st, partial, blocks, C, out);
 }
 
 }  // namespace kc

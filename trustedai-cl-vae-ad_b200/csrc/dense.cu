@@ -82,12 +82,26 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmArgs a, int splits, int k
     }
 }
 
-__global__ void gemm_splitk_reduce_kernel(GemmArgs a, int splits) {
+// 8 threads per output entry, each a contiguous slice of the splits, folded in a fixed order
+constexpr int GR_SLICES = 8;
+__global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(GemmArgs a, int splits) {
+  __shared__ float red[256];
   const int64_t MN = (int64_t)a.M * a.N;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < MN;
-       i += (int64_t)gridDim.x * blockDim.x) {
+  const int oi = threadIdx.x / GR_SLICES, sl = threadIdx.x % GR_SLICES;
+  const int64_t i = (int64_t)blockIdx.x * (256 / GR_SLICES) + oi;
+  float t = 0.0f;
+  if (i < MN) {
+    const int per = (splits + GR_SLICES - 1) / GR_SLICES;
+    const int z0 = sl * per, z1 = min(splits, z0 + per);
+#pragma unroll 4
+    for (int z = z0; z < z1; ++z) t += __ldg(a.partial + (int64_t)z * MN + i);
+  }
+  red[threadIdx.x] = t;
+  __syncthreads();
+  if (sl == 0 && i < MN) {
     float s = 0.0f;
-    for (int z = 0; z < splits; ++z) s += a.partial[(int64_t)z * MN + i];
+#pragma unroll
+    for (int k = 0; k < GR_SLICES; ++k) s += red[threadIdx.x + k];
     const int m = (int)(i / a.N), n = (int)(i % a.N);
     a.C[i] = gemm_epi(s, m, n, a.N, a.bias, a.mask, a.relu);
   }
@@ -106,7 +120,7 @@ void gemm(const GemmArgs& a, cudaStream_t st) {
   KC_LAUNCH(gemm_kernel, grid, 256, 0, st, a, splits, kps);
   if (splits > 1) {
     ++g_launches;
-    KC_LAUNCH(gemm_splitk_reduce_kernel, grid_for((int64_t)a.M * a.N, 256), 256, 0, st, a, splits);
+    KC_LAUNCH(gemm_splitk_reduce_kernel, cdiv((int64_t)a.M * a.N, 256 / GR_SLICES), 256, 0, st, a, splits);
   }
 }
 

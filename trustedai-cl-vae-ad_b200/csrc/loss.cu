@@ -20,34 +20,53 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
   double t_g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   float mn = 3.4e38f, mx = -3.4e38f;
   const bool want_std = a.std_acc != nullptr || a.pos_sums != nullptr;
+  const float* __restrict__ X = a.x;
+  const float* __restrict__ XH = a.xhat;
+  float* __restrict__ DL = a.dlogit;
+  uint16_t* __restrict__ DL8 = a.dl8;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.P;
        p += (int64_t)gridDim.x * blockDim.x) {
     float se = 0, xhx = 0, xh = 0, ex = 0, gsum = 0;
     double sx = 0, sxx = 0, sh = 0, shh = 0;
-    for (int b = 0; b < a.B; ++b) {
-      const int64_t i = (int64_t)b * a.P + p;
-      const float xv = __ldg(a.x + i), hv = __ldg(a.xhat + i);
-      const float d = xv - hv;
-      se = fmaf(d, d, se);
-      mn = fminf(mn, hv);
-      mx = fmaxf(mx, hv);
-      if (a.want_ce) {
-        xhx = fmaf(hv, xv, xhx);
-        xh += hv;
-        ex += expf(xv);
+    const int64_t pix8 = (p / a.C) * 8 + (p % a.C);   // slot inside one frame of the 8-channel bf16 layout
+    const int64_t frame8 = (a.P / a.C) * 8;
+    // four frames per trip: the eight loads are issued before any dependent store
+    for (int b0 = 0; b0 < a.B; b0 += 4) {
+      float xv4[4], hv4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool in = b0 + u < a.B;
+        const int64_t i = (int64_t)(in ? b0 + u : b0) * a.P + p;
+        xv4[u] = __ldg(X + i); hv4[u] = __ldg(XH + i);
       }
-      if (want_std) {
-        sx += xv; sxx += (double)xv * xv;
-        sh += hv; shh += (double)hv * hv;
-      }
-      if (a.dlogit || a.dl8) {
-        const float gl = a.grad_scale * (hv - xv) * hv * (1.0f - hv);
-        if (a.dlogit) a.dlogit[i] = gl;
-        gsum += gl;
-        if (a.dl8) {  // bf16 round-to-nearest-even, channel-padded layout [b][pixel][8]
-          const uint32_t u = __float_as_uint(gl);
-          const uint32_t rb = u + 0x7FFFu + ((u >> 16) & 1u);
-          a.dl8[((int64_t)b * (a.P / a.C) + p / a.C) * 8 + (p % a.C)] = (uint16_t)(rb >> 16);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (b0 + u >= a.B) break;
+        const int b = b0 + u;
+        const int64_t i = (int64_t)b * a.P + p;
+        const float xv = xv4[u], hv = hv4[u];
+        const float d = xv - hv;
+        se = fmaf(d, d, se);
+        mn = fminf(mn, hv);
+        mx = fmaxf(mx, hv);
+        if (a.want_ce) {
+          xhx = fmaf(hv, xv, xhx);
+          xh += hv;
+          ex += expf(xv);
+        }
+        if (want_std) {
+          sx += xv; sxx += (double)xv * xv;
+          sh += hv; shh += (double)hv * hv;
+        }
+        if (DL || DL8) {
+          const float gl = a.grad_scale * (hv - xv) * hv * (1.0f - hv);
+          if (DL) DL[i] = gl;
+          gsum += gl;
+          if (DL8) {  // bf16 round-to-nearest-even, channel-padded layout [b][pixel][8]
+            const uint32_t u32 = __float_as_uint(gl);
+            const uint32_t rb = u32 + 0x7FFFu + ((u32 >> 16) & 1u);
+            DL8[(int64_t)b * frame8 + pix8] = (uint16_t)(rb >> 16);
+          }
         }
       }
     }

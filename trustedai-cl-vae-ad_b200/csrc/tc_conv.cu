@@ -53,7 +53,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
 }
 
-__global__ void sum_partials_kernel(const float* partial, int nparts, int E, float* out);
+static void sum_partials(const float* partial, int nparts, int E, float* out, cudaStream_t st);
 
 struct OutConvParams {
   const __nv_bfloat16* wimg;  // [9 taps][CIN/16][2 chunks][NPAD][8] bf16 (tc_prep_out_weights)
@@ -549,12 +549,32 @@ tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutWgradParams p) 
   if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
-__global__ void sum_partials_kernel(const float* partial, int nparts, int E, float* out) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= E) return;
-  float s = 0.f;
-  for (int i = 0; i < nparts; ++i) s += partial[(int64_t)i * E + e];
-  out[e] = s;
+// out[e] = sum_i partial[i*E + e]: 8 threads per entry, each a contiguous slice of the partials,
+// folded in a fixed order (deterministic); launch with sum_partials().
+constexpr int SP_SLICES = 8;
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* partial, int nparts, int E, float* out) {
+  __shared__ float red[256];
+  const int oi = threadIdx.x / SP_SLICES, sl = threadIdx.x % SP_SLICES;
+  const int e = blockIdx.x * (256 / SP_SLICES) + oi;
+  float t = 0.f;
+  if (e < E) {
+    const int per = (nparts + SP_SLICES - 1) / SP_SLICES;
+    const int c0 = sl * per, c1 = min(nparts, c0 + per);
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) t += __ldg(partial + (int64_t)c * E + e);
+  }
+  red[threadIdx.x] = t;
+  __syncthreads();
+  if (sl == 0 && e < E) {
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < SP_SLICES; ++i) v += red[threadIdx.x + i];
+    out[e] = v;
+  }
+}
+static void sum_partials(const float* partial, int nparts, int E, float* out, cudaStream_t st) {
+  ++g_launches;
+  sum_partials_kernel<<<cdiv(E, 256 / SP_SLICES), 256, 0, st>>>(partial, nparts, E, out);
 }
 
 // ============================================================================================
@@ -1396,8 +1416,7 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   p.chan_partial = chan_sum ? chan_partial : nullptr;
   tc_out_dgrad_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
   if (chan_sum) {
-    ++g_launches;
-    sum_partials_kernel<<<1, 32, 0, st>>>(chan_partial, grid * 8, Cin, chan_sum);
+    sum_partials(chan_partial, grid * 8, Cin, chan_sum, st);
   }
   return 0;
 }
@@ -1429,10 +1448,10 @@ int tc_out_wgrad(const void* dl8_bf16, const void* act_bf16, float* dW, float* p
   const size_t smem = (size_t)kStages * ((size_t)DL_BYTES + (size_t)4 * NPIX * 16 + 128);
   const int E = 9 * Cout * Cin;
   ProfScope prof_("tc_out_wgrad", st);
-  g_launches += 2;
+  ++g_launches;
   cudaFuncSetAttribute(tc_out_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_out_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
-  sum_partials_kernel<<<cdiv(E, 256), 256, 0, st>>>(partial, grid, E, dW);
+  sum_partials(partial, grid, E, dW, st);
   return 0;
 }
 
@@ -1539,10 +1558,10 @@ int tc_convT_wgrad(const void* g_s2d, const void* a_prev8, float* dW, float* par
   const size_t smem = (size_t)kStages * ((size_t)AP_BYTES + GT_BYTES + 128);
   const int E = 9 * 32 * Cin;
   ProfScope prof_("tc_convT_wgrad", st);
-  g_launches += 2;
+  ++g_launches;
   cudaFuncSetAttribute(tc_convT_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_convT_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
-  sum_partials_kernel<<<cdiv(E, 256), 256, 0, st>>>(partial, grid, E, dW);
+  sum_partials(partial, grid, E, dW, st);
   return 0;
 }
 
