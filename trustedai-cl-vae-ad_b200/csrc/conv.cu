@@ -349,6 +349,28 @@ __global__ void __launch_bounds__(128) convT_s2_many2few_kernel(ConvArgs a, int6
   }
 }
 
+#ifndef KCVAE_EMU
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+// 4-byte async copy; !valid writes a zero without touching the source
+__device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+#else
+static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
+static inline void cp_async4_zfill(float* d, const float* s, bool valid) { *d = valid ? *s : 0.f; }
+static inline void cp_async_commit() {}
+template <int N> static inline void cp_async_wait() {}
+#endif
+
+
 // =========================================================================================
 // Lane-mapped kernels for the 32-channel <-> few-channel layers.  The 32-channel side is spread
 // over the lanes of a warp, so every global access of that side is one coalesced 128-byte line
@@ -360,13 +382,6 @@ __global__ void __launch_bounds__(128) convT_s2_many2few_kernel(ConvArgs a, int6
 //               partial sums of a pixel group are folded across the warp with a butterfly that
 //               halves the value count at every step (fixed order, deterministic).
 // =========================================================================================
-__device__ __forceinline__ float lane_epi(float v, int epi, const float* mask, int64_t o) {
-  if (epi == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
-  else if (epi == EPI_BIAS_SIGMOID) v = 1.0f / (1.0f + expf(-v));
-  else if (epi == EPI_MASK) v = __ldg(mask + o) > 0.f ? v : 0.f;
-  return v;
-}
-
 // ---- Conv2D s2, CI in {3,4,5,8} -> Co = 32*k.  block = one output row, warp = groups of 4 pixels
 template <int CI>
 __global__ void __launch_bounds__(256) conv_s2_lane_co_kernel(ConvArgs a, int rows, int epi) {
@@ -384,27 +399,45 @@ __global__ void __launch_bounds__(256) conv_s2_lane_co_kernel(ConvArgs a, int ro
   const int ncolf = (2 * Wo4 + 1) * CI;           // staged floats per row: column c holds ix = c - pad_l
   const int RW = ((ncolf + 3) & ~3) + 4;
   const int shift = a.pad_l * CI, rowf = a.Wi * CI;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+  const bool masked = epi == EPI_MASK;
+  auto stage = [&](int row, int sidx) {   // three zero-padded input rows of output row `row`, asynchronously
     const int n = row / a.Ho, oy = row % a.Ho;
-    __syncthreads();
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int iy = 2 * oy + kh - a.pad_t;
       const bool vrow = iy >= 0 && iy < a.Hi;
       const float* src = a.in + ((int64_t)n * a.Hi + (vrow ? iy : 0)) * rowf;
-      float* dst = srow + kh * RW;
+      float* dst = srow + (sidx * 3 + kh) * RW;
       for (int e = threadIdx.x; e < RW; e += blockDim.x) {
         const int g = e - shift;
-        dst[e] = (vrow && g >= 0 && g < rowf) ? __ldg(src + g) : 0.f;
+        const bool ok = vrow && g >= 0 && g < rowf;
+        cp_async4_zfill(dst + e, src + (ok ? g : 0), ok);
       }
     }
+    cp_async_commit();
+  };
+  int it = 0;
+  if ((int)blockIdx.x < rows) stage(blockIdx.x, 0);
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+    const int n = row / a.Ho, oy = row % a.Ho;
+    const int sidx = it & 1;
+    if (row + (int)gridDim.x < rows) { stage(row + gridDim.x, sidx ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
     __syncthreads();
+    const float* sbase = srow + sidx * 3 * RW;
     for (int grp = warp; grp < (Wo4 >> 2); grp += nwarps) {
       const int ox0 = grp * 4;
+      const int64_t o0 = (((int64_t)n * a.Ho + oy) * a.Wo + ox0) * a.Co + co;
+      float mk[4] = {1.f, 1.f, 1.f, 1.f};
+      if (masked) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (ox0 + p < a.Wo) mk[p] = __ldg(a.mask + o0 + (int64_t)p * a.Co);
+      }
       float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
-        const float4* rp = reinterpret_cast<const float4*>(srow + kh * RW + 2 * ox0 * CI);
+        const float4* rp = reinterpret_cast<const float4*>(sbase + kh * RW + 2 * ox0 * CI);
         float v[NV * 4];
 #pragma unroll
         for (int q = 0; q < NV; ++q) {
@@ -420,13 +453,16 @@ __global__ void __launch_bounds__(256) conv_s2_lane_co_kernel(ConvArgs a, int ro
       }
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        const int ox = ox0 + p;
-        if (ox < a.Wo) {
-          const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox) * a.Co + co;
-          a.out[o] = lane_epi(acc[p], epi, a.mask, o);
+        if (ox0 + p < a.Wo) {
+          float y = acc[p];
+          if (epi == EPI_BIAS_RELU) y = fmaxf(y, 0.f);
+          else if (epi == EPI_BIAS_SIGMOID) y = 1.0f / (1.0f + expf(-y));
+          else if (masked) y = mk[p] > 0.f ? y : 0.f;
+          a.out[o0 + (int64_t)p * a.Co] = y;
         }
       }
     }
+    __syncthreads();
   }
 }
 
@@ -448,29 +484,49 @@ __global__ void __launch_bounds__(256) convT_s2_lane_co_kernel(ConvArgs a, int r
   const int ncolf = (Wi4 + 1) * CI;               // column c holds ix = c - 1
   const int RW = ((ncolf + 3) & ~3) + 4;
   const int rowf = a.Wi * CI;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+  const bool masked = epi == EPI_MASK;
+  auto stage = [&](int row, int sidx) {   // input rows i-1 and i, zero padded, asynchronously
     const int n = row / a.Hi, i = row % a.Hi;
-    __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {                 // r = 0: input row i-1, r = 1: input row i
+    for (int r = 0; r < 2; ++r) {
       const int iy = i - 1 + r;
       const bool vrow = iy >= 0;
       const float* src = a.in + ((int64_t)n * a.Hi + (vrow ? iy : 0)) * rowf;
-      float* dst = srow + r * RW;
+      float* dst = srow + (sidx * 2 + r) * RW;
       for (int e = threadIdx.x; e < RW; e += blockDim.x) {
         const int g = e - CI;
-        dst[e] = (vrow && g >= 0 && g < rowf) ? __ldg(src + g) : 0.f;
+        const bool ok = vrow && g >= 0 && g < rowf;
+        cp_async4_zfill(dst + e, src + (ok ? g : 0), ok);
       }
     }
+    cp_async_commit();
+  };
+  int it = 0;
+  if ((int)blockIdx.x < rows) stage(blockIdx.x, 0);
+  for (int row = blockIdx.x; row < rows; row += gridDim.x, ++it) {
+    const int n = row / a.Hi, i = row % a.Hi;
+    const int sidx = it & 1;
+    if (row + (int)gridDim.x < rows) { stage(row + gridDim.x, sidx ^ 1); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
     __syncthreads();
+    const float* sbase = srow + sidx * 2 * RW;
     for (int grp = warp; grp < (Wi4 >> 2); grp += nwarps) {
       const int j0 = grp * 4;
+      const int64_t o0 = (((int64_t)n * a.Ho + 2 * i) * a.Wo + 2 * j0) * a.Co + co;
+      const int64_t orow = (int64_t)a.Wo * a.Co;
+      float mk[2][8];
+      if (masked) {      // issued before the arithmetic so the loads overlap it
+#pragma unroll
+        for (int pa = 0; pa < 2; ++pa)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) mk[pa][c] = (2 * j0 + c < a.Wo) ? __ldg(a.mask + o0 + pa * orow + (int64_t)c * a.Co) : 0.f;
+      }
       float acc[2][8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) { acc[0][c] = bias; acc[1][c] = bias; }
       float v[NV * 4];
       {  // input row i-1: taps kh = 2 land on output row 2i
-        const float4* rp = reinterpret_cast<const float4*>(srow + j0 * CI);
+        const float4* rp = reinterpret_cast<const float4*>(sbase + j0 * CI);
 #pragma unroll
         for (int q = 0; q < NV; ++q) { const float4 t = rp[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
 #pragma unroll
@@ -483,7 +539,7 @@ __global__ void __launch_bounds__(256) convT_s2_lane_co_kernel(ConvArgs a, int r
           }
       }
       {  // input row i: kh = 0 -> output row 2i, kh = 1 -> output row 2i+1
-        const float4* rp = reinterpret_cast<const float4*>(srow + RW + j0 * CI);
+        const float4* rp = reinterpret_cast<const float4*>(sbase + RW + j0 * CI);
 #pragma unroll
         for (int q = 0; q < NV; ++q) { const float4 t = rp[q]; v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
 #pragma unroll
@@ -501,13 +557,16 @@ __global__ void __launch_bounds__(256) convT_s2_lane_co_kernel(ConvArgs a, int r
       for (int pa = 0; pa < 2; ++pa)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const int ox = 2 * j0 + c;
-          if (ox < a.Wo) {
-            const int64_t o = (((int64_t)n * a.Ho + 2 * i + pa) * a.Wo + ox) * a.Co + co;
-            a.out[o] = lane_epi(acc[pa][c], epi, a.mask, o);
+          if (2 * j0 + c < a.Wo) {
+            float y = acc[pa][c];
+            if (epi == EPI_BIAS_RELU) y = fmaxf(y, 0.f);
+            else if (epi == EPI_BIAS_SIGMOID) y = 1.0f / (1.0f + expf(-y));
+            else if (masked) y = mk[pa][c] > 0.f ? y : 0.f;
+            a.out[o0 + pa * orow + (int64_t)c * a.Co] = y;
           }
         }
     }
+    __syncthreads();
   }
 }
 
@@ -542,7 +601,8 @@ __device__ __forceinline__ int lane_fold_index(int lane) {
   }
 }
 
-// ---- Conv2D s2, Ci = 32 -> CO in {5,8}.  warp = pairs of adjacent output pixels
+// ---- Conv2D s2, Ci = 32 -> CO in {5,8}.  warp = pairs of adjacent output pixels; the 15 input
+// lines of the next pair are loaded into registers while the current pair is reduced
 template <int CO>
 __global__ void __launch_bounds__(256) conv_s2_lane_ci_kernel(ConvArgs a, int64_t npairs, int WP, int epi) {
   const int lane = threadIdx.x & 31;
@@ -555,44 +615,65 @@ __global__ void __launch_bounds__(256) conv_s2_lane_ci_kernel(ConvArgs a, int64_
   const int idx = lane_fold_index<16, 16>(lane);
   const int mp = idx >> 3, mco = idx & 7;
   const bool writer = idx >= 0 && mco < CO;
-  const float bias = (writer && a.bias && epi != EPI_MASK) ? __ldg(a.bias + mco) : 0.f;
+  const bool masked = epi == EPI_MASK;
+  const float bias = (writer && a.bias && !masked) ? __ldg(a.bias + mco) : 0.f;
+  auto load = [&](int64_t pr, float (&x)[3][5]) {
+    const int pp = (int)(pr % WP);
+    const int oy = (int)((pr / WP) % a.Ho);
+    const int n = (int)(pr / ((int64_t)WP * a.Ho));
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = 2 * oy + kh - a.pad_t;
+      const bool vrow = iy >= 0 && iy < a.Hi;
+      const float* rowp = a.in + (((int64_t)n * a.Hi + (vrow ? iy : 0)) * a.Wi) * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        const int ix = 4 * pp + c - a.pad_l;
+        x[kh][c] = (vrow && ix >= 0 && ix < a.Wi) ? __ldg(rowp + (int64_t)ix * 32) : 0.f;
+      }
+    }
+  };
+  float xc[3][5], xn[3][5];
+  if (gw < npairs) load(gw, xc);
   for (int64_t pr = gw; pr < npairs; pr += nw) {
     const int pp = (int)(pr % WP);
     const int oy = (int)((pr / WP) % a.Ho);
     const int n = (int)(pr / ((int64_t)WP * a.Ho));
     const int ox0 = 2 * pp;
+    const bool wr = writer && ox0 + mp < a.Wo;
+    const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox0 + mp) * CO + mco;
+    float mk = 1.f;
+    if (masked && wr) mk = __ldg(a.mask + o);
+    if (pr + nw < npairs) load(pr + nw, xn);
     float v[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) v[k] = 0.f;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int iy = 2 * oy + kh - a.pad_t;
-      if (iy < 0 || iy >= a.Hi) continue;
-      const float* rowp = a.in + (((int64_t)n * a.Hi + iy) * a.Wi) * 32 + lane;
-      float x[5];
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        const int ix = 2 * ox0 + c - a.pad_l;
-        x[c] = (ix >= 0 && ix < a.Wi) ? __ldg(rowp + (int64_t)ix * 32) : 0.f;
-      }
+    for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw)
 #pragma unroll
         for (int co = 0; co < CO; ++co) {
-          v[co] = fmaf(x[kw], w[kh * 3 + kw][co], v[co]);
-          v[8 + co] = fmaf(x[2 + kw], w[kh * 3 + kw][co], v[8 + co]);
+          v[co] = fmaf(xc[kh][kw], w[kh * 3 + kw][co], v[co]);
+          v[8 + co] = fmaf(xc[kh][2 + kw], w[kh * 3 + kw][co], v[8 + co]);
         }
-    }
     lane_fold<16, 16>(v, lane);
-    if (writer && ox0 + mp < a.Wo) {
-      const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox0 + mp) * CO + mco;
-      a.out[o] = lane_epi(v[0] + bias, epi, a.mask, o);
+    if (wr) {
+      float y = v[0] + bias;
+      if (epi == EPI_BIAS_RELU) y = fmaxf(y, 0.f);
+      else if (epi == EPI_BIAS_SIGMOID) y = 1.0f / (1.0f + expf(-y));
+      else if (masked) y = mk > 0.f ? y : 0.f;
+      a.out[o] = y;
     }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) xc[kh][c] = xn[kh][c];
   }
 }
 
 // ---- Conv2DTranspose s2 (pad 0, Ho = 2 Hi, Wo = 2 Wi), Ci = 32 -> CO in {5,8}.  warp = one input
-// pixel's 2x2 output quad (9 taps), 4*CO partial sums folded across the warp
+// pixel's 2x2 output quad (9 taps), 4*CO partial sums folded across the warp; next quad prefetched
 template <int CO>
 __global__ void __launch_bounds__(256) convT_s2_lane_ci_kernel(ConvArgs a, int64_t nq, int epi) {
   constexpr int NVAL = 4 * CO;
@@ -605,16 +686,30 @@ __global__ void __launch_bounds__(256) convT_s2_lane_ci_kernel(ConvArgs a, int64
     for (int co = 0; co < CO; ++co) w[t][co] = __ldg(a.w + (int64_t)t * 32 * CO + (int64_t)lane * a.w_sci + (int64_t)co * a.w_sco);
   const int idx = lane_fold_index<NVAL, 16>(lane);
   const int mph = idx >= 0 ? idx / CO : 0, mco = idx >= 0 ? idx % CO : 0;
-  const float bias = (idx >= 0 && a.bias && epi != EPI_MASK) ? __ldg(a.bias + mco) : 0.f;
-  for (int64_t q = gw; q < nq; q += nw) {
+  const bool masked = epi == EPI_MASK;
+  const float bias = (idx >= 0 && a.bias && !masked) ? __ldg(a.bias + mco) : 0.f;
+  auto load = [&](int64_t q, float (&x)[4]) {
     const int j = (int)(q % a.Wi);
     const int i = (int)((q / a.Wi) % a.Hi);
     const int n = (int)(q / ((int64_t)a.Wi * a.Hi));
     const float* px = a.in + ((((int64_t)n * a.Hi + i) * a.Wi) + j) * 32 + lane;
-    const float x00 = __ldg(px);
-    const float x01 = j > 0 ? __ldg(px - 32) : 0.f;                                  // (i, j-1)
-    const float x10 = i > 0 ? __ldg(px - (int64_t)a.Wi * 32) : 0.f;                  // (i-1, j)
-    const float x11 = (i > 0 && j > 0) ? __ldg(px - (int64_t)a.Wi * 32 - 32) : 0.f;  // (i-1, j-1)
+    x[0] = __ldg(px);                                                           // (i, j)
+    x[1] = j > 0 ? __ldg(px - 32) : 0.f;                                        // (i, j-1)
+    x[2] = i > 0 ? __ldg(px - (int64_t)a.Wi * 32) : 0.f;                        // (i-1, j)
+    x[3] = (i > 0 && j > 0) ? __ldg(px - (int64_t)a.Wi * 32 - 32) : 0.f;        // (i-1, j-1)
+  };
+  float xc[4], xn[4];
+  if (gw < nq) load(gw, xc);
+  for (int64_t q = gw; q < nq; q += nw) {
+    const int j = (int)(q % a.Wi);
+    const int i = (int)((q / a.Wi) % a.Hi);
+    const int n = (int)(q / ((int64_t)a.Wi * a.Hi));
+    const int oy = 2 * i + (mph >> 1), ox = 2 * j + (mph & 1);
+    const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox) * CO + mco;
+    float mk = 1.f;
+    if (masked && idx >= 0) mk = __ldg(a.mask + o);
+    if (q + nw < nq) load(q + nw, xn);
+    const float x00 = xc[0], x01 = xc[1], x10 = xc[2], x11 = xc[3];
     float v[NVAL];
 #pragma unroll
     for (int co = 0; co < CO; ++co) {
@@ -625,10 +720,14 @@ __global__ void __launch_bounds__(256) convT_s2_lane_ci_kernel(ConvArgs a, int64
     }
     lane_fold<NVAL, 16>(v, lane);
     if (idx >= 0) {
-      const int oy = 2 * i + (mph >> 1), ox = 2 * j + (mph & 1);
-      const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox) * CO + mco;
-      a.out[o] = lane_epi(v[0] + bias, epi, a.mask, o);
+      float y = v[0] + bias;
+      if (epi == EPI_BIAS_RELU) y = fmaxf(y, 0.f);
+      else if (epi == EPI_BIAS_SIGMOID) y = 1.0f / (1.0f + expf(-y));
+      else if (masked) y = mk > 0.f ? y : 0.f;
+      a.out[o] = y;
     }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) xc[c] = xn[c];
   }
 }
 
@@ -654,9 +753,9 @@ static bool conv_forward_lane(int mode, int epi, const ConvArgs& a, cudaStream_t
     const int Wq4 = ((mode == CONV_S2 ? a.Wo : a.Wi) + 3) & ~3;
     const int ncolf = (mode == CONV_S2 ? 2 * Wq4 + 1 : Wq4 + 1) * a.Ci;
     const int RW = ((ncolf + 3) & ~3) + 4;
-    const size_t smem = (size_t)(mode == CONV_S2 ? 3 : 2) * RW * sizeof(float);
+    const size_t smem = (size_t)2 * (mode == CONV_S2 ? 3 : 2) * RW * sizeof(float);   // two stages
     if (smem > 160 * 1024) return false;
-    const dim3 grid(rows < kNumSMs * 6 ? rows : kNumSMs * 6, a.Co / 32);
+    const dim3 grid(rows < kNumSMs * 4 ? rows : kNumSMs * 4, a.Co / 32);
     ++g_launches;
 #define KC_LANE_CO(KERNEL, CI_)                                 \
   {                                                             \
@@ -682,7 +781,7 @@ static bool conv_forward_lane(int mode, int epi, const ConvArgs& a, cudaStream_t
     if (mode == CONV_S2) {
       const int WP = cdiv(a.Wo, 2);
       const int64_t npairs = (int64_t)a.B * a.Ho * WP;
-      const int grid = grid_for(npairs * 32, 256, 8, 4);
+      const int grid = grid_for(npairs * 32, 256, 3, 1);
       ++g_launches;
       if (a.Co == 5) KC_LAUNCH(conv_s2_lane_ci_kernel<5>, grid, 256, 0, st, a, npairs, WP, epi);
       else KC_LAUNCH(conv_s2_lane_ci_kernel<8>, grid, 256, 0, st, a, npairs, WP, epi);
@@ -690,7 +789,7 @@ static bool conv_forward_lane(int mode, int epi, const ConvArgs& a, cudaStream_t
     }
     if (mode == CONVT_S2 && up2) {
       const int64_t nq = (int64_t)a.B * a.Hi * a.Wi;
-      const int grid = grid_for(nq * 32, 256, 8, 4);
+      const int grid = grid_for(nq * 32, 256, 3, 1);
       ++g_launches;
       if (a.Co == 5) KC_LAUNCH(convT_s2_lane_ci_kernel<5>, grid, 256, 0, st, a, nq, epi);
       else KC_LAUNCH(convT_s2_lane_ci_kernel<8>, grid, 256, 0, st, a, nq, epi);
@@ -971,20 +1070,6 @@ __global__ void __launch_bounds__(256) wgrad_tiled_kernel(WgradArgs a, int rows,
 // hidden.  Each row (and the contiguous 3-row Q span) is one linear 16-byte-chunk copy; image
 // borders are handled by clipping each thread's pixel range for its tap, not by padding.
 // Optionally the same pass produces sum_pixels P[., a] (the bias gradient when P is a gradient).
-#ifndef KCVAE_EMU
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-#else
-static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
-static inline void cp_async_commit() {}
-template <int N> static inline void cp_async_wait() {}
-#endif
-
 // elements [k_lo, k_hi) of the float array starting at element `base` of `src` -> dst[mis + k],
 // mis = address misalignment (in floats) of element `base`, so 16-byte chunks line up
 __device__ __forceinline__ int stage_linear(float* dst, const float* src, int64_t base, int k_lo, int k_hi) {
