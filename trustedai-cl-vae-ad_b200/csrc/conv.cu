@@ -372,15 +372,14 @@ template <int N> static inline void cp_async_wait() {}
 
 
 // =========================================================================================
-// Lane-mapped kernels for the 32-channel <-> few-channel layers.  The 32-channel side is spread
+// Lane-mapped kernels for the few -> 32-channel layers.  The 32-channel side is spread
 // over the lanes of a warp, so every global access of that side is one coalesced 128-byte line
 // and no shared-memory bank is hit twice:
 //   *_lane_co : few -> many.  lane = output channel; its 9*CI weights live in registers; the
 //               few-channel input rows are staged in shared memory (zero padded) and read as
 //               warp-broadcast float4.
-//   *_lane_ci : many -> few.  lane = input channel; its 9*CO weights live in registers; the
-//               partial sums of a pixel group are folded across the warp with a butterfly that
-//               halves the value count at every step (fixed order, deterministic).
+// (The mirrored many -> few mapping, lane = input channel with a warp butterfly per pixel, was
+// measured slower than the pixel-pair kernels below on B200 and is not kept.)
 // =========================================================================================
 // ---- Conv2D s2, CI in {3,4,5,8} -> Co = 32*k.  block = one output row, warp = groups of 4 pixels
 template <int CI>
@@ -570,167 +569,6 @@ __global__ void __launch_bounds__(256) convT_s2_lane_co_kernel(ConvArgs a, int r
   }
 }
 
-// N partial values per lane -> their warp totals, one per lane: at every step the lanes exchange
-// half of the values with the partner lane^O and keep the other half.
-template <int N, int O>
-__device__ __forceinline__ void lane_fold(float* v, int lane) {
-  if constexpr (O >= 1) {
-    constexpr int H = (N + 1) / 2;
-    const bool up = (lane & O) != 0;
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-      const float lo = v[i];
-      const float hi = (i + H < N) ? v[i + H] : 0.f;
-      const float keep = up ? hi : lo, send = up ? lo : hi;
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
-    }
-    lane_fold<H, O / 2>(v, lane);
-  }
-}
-// index of the value whose total ends up in v[0] of `lane` after lane_fold<N,16>, or -1
-template <int N, int O>
-__device__ __forceinline__ int lane_fold_index(int lane) {
-  if constexpr (O >= 1) {
-    constexpr int H = (N + 1) / 2;
-    const int sub = lane_fold_index<H, O / 2>(lane);
-    if (sub < 0) return -1;
-    const int i = sub + ((lane & O) ? H : 0);
-    return i < N ? i : -1;
-  } else {
-    return 0;
-  }
-}
-
-// ---- Conv2D s2, Ci = 32 -> CO in {5,8}.  warp = pairs of adjacent output pixels; the 15 input
-// lines of the next pair are loaded into registers while the current pair is reduced
-template <int CO>
-__global__ void __launch_bounds__(256) conv_s2_lane_ci_kernel(ConvArgs a, int64_t npairs, int WP, int epi) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float w[9][CO];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int co = 0; co < CO; ++co) w[t][co] = __ldg(a.w + (int64_t)t * 32 * CO + (int64_t)lane * a.w_sci + (int64_t)co * a.w_sco);
-  const int idx = lane_fold_index<16, 16>(lane);
-  const int mp = idx >> 3, mco = idx & 7;
-  const bool writer = idx >= 0 && mco < CO;
-  const bool masked = epi == EPI_MASK;
-  const float bias = (writer && a.bias && !masked) ? __ldg(a.bias + mco) : 0.f;
-  auto load = [&](int64_t pr, float (&x)[3][5]) {
-    const int pp = (int)(pr % WP);
-    const int oy = (int)((pr / WP) % a.Ho);
-    const int n = (int)(pr / ((int64_t)WP * a.Ho));
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int iy = 2 * oy + kh - a.pad_t;
-      const bool vrow = iy >= 0 && iy < a.Hi;
-      const float* rowp = a.in + (((int64_t)n * a.Hi + (vrow ? iy : 0)) * a.Wi) * 32 + lane;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        const int ix = 4 * pp + c - a.pad_l;
-        x[kh][c] = (vrow && ix >= 0 && ix < a.Wi) ? __ldg(rowp + (int64_t)ix * 32) : 0.f;
-      }
-    }
-  };
-  float xc[3][5], xn[3][5];
-  if (gw < npairs) load(gw, xc);
-  for (int64_t pr = gw; pr < npairs; pr += nw) {
-    const int pp = (int)(pr % WP);
-    const int oy = (int)((pr / WP) % a.Ho);
-    const int n = (int)(pr / ((int64_t)WP * a.Ho));
-    const int ox0 = 2 * pp;
-    const bool wr = writer && ox0 + mp < a.Wo;
-    const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox0 + mp) * CO + mco;
-    float mk = 1.f;
-    if (masked && wr) mk = __ldg(a.mask + o);
-    if (pr + nw < npairs) load(pr + nw, xn);
-    float v[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) v[k] = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw)
-#pragma unroll
-        for (int co = 0; co < CO; ++co) {
-          v[co] = fmaf(xc[kh][kw], w[kh * 3 + kw][co], v[co]);
-          v[8 + co] = fmaf(xc[kh][2 + kw], w[kh * 3 + kw][co], v[8 + co]);
-        }
-    lane_fold<16, 16>(v, lane);
-    if (wr) {
-      float y = v[0] + bias;
-      if (epi == EPI_BIAS_RELU) y = fmaxf(y, 0.f);
-      else if (epi == EPI_BIAS_SIGMOID) y = 1.0f / (1.0f + expf(-y));
-      else if (masked) y = mk > 0.f ? y : 0.f;
-      a.out[o] = y;
-    }
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int c = 0; c < 5; ++c) xc[kh][c] = xn[kh][c];
-  }
-}
-
-// ---- Conv2DTranspose s2 (pad 0, Ho = 2 Hi, Wo = 2 Wi), Ci = 32 -> CO in {5,8}.  warp = one input
-// pixel's 2x2 output quad (9 taps), 4*CO partial sums folded across the warp; next quad prefetched
-template <int CO>
-__global__ void __launch_bounds__(256) convT_s2_lane_ci_kernel(ConvArgs a, int64_t nq, int epi) {
-  constexpr int NVAL = 4 * CO;
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  float w[9][CO];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int co = 0; co < CO; ++co) w[t][co] = __ldg(a.w + (int64_t)t * 32 * CO + (int64_t)lane * a.w_sci + (int64_t)co * a.w_sco);
-  const int idx = lane_fold_index<NVAL, 16>(lane);
-  const int mph = idx >= 0 ? idx / CO : 0, mco = idx >= 0 ? idx % CO : 0;
-  const bool masked = epi == EPI_MASK;
-  const float bias = (idx >= 0 && a.bias && !masked) ? __ldg(a.bias + mco) : 0.f;
-  auto load = [&](int64_t q, float (&x)[4]) {
-    const int j = (int)(q % a.Wi);
-    const int i = (int)((q / a.Wi) % a.Hi);
-    const int n = (int)(q / ((int64_t)a.Wi * a.Hi));
-    const float* px = a.in + ((((int64_t)n * a.Hi + i) * a.Wi) + j) * 32 + lane;
-    x[0] = __ldg(px);                                                           // (i, j)
-    x[1] = j > 0 ? __ldg(px - 32) : 0.f;                                        // (i, j-1)
-    x[2] = i > 0 ? __ldg(px - (int64_t)a.Wi * 32) : 0.f;                        // (i-1, j)
-    x[3] = (i > 0 && j > 0) ? __ldg(px - (int64_t)a.Wi * 32 - 32) : 0.f;        // (i-1, j-1)
-  };
-  float xc[4], xn[4];
-  if (gw < nq) load(gw, xc);
-  for (int64_t q = gw; q < nq; q += nw) {
-    const int j = (int)(q % a.Wi);
-    const int i = (int)((q / a.Wi) % a.Hi);
-    const int n = (int)(q / ((int64_t)a.Wi * a.Hi));
-    const int oy = 2 * i + (mph >> 1), ox = 2 * j + (mph & 1);
-    const int64_t o = (((int64_t)n * a.Ho + oy) * a.Wo + ox) * CO + mco;
-    float mk = 1.f;
-    if (masked && idx >= 0) mk = __ldg(a.mask + o);
-    if (q + nw < nq) load(q + nw, xn);
-    const float x00 = xc[0], x01 = xc[1], x10 = xc[2], x11 = xc[3];
-    float v[NVAL];
-#pragma unroll
-    for (int co = 0; co < CO; ++co) {
-      v[0 * CO + co] = fmaf(x00, w[0][co], fmaf(x10, w[6][co], fmaf(x01, w[2][co], x11 * w[8][co])));
-      v[1 * CO + co] = fmaf(x00, w[1][co], x10 * w[7][co]);
-      v[2 * CO + co] = fmaf(x00, w[3][co], x01 * w[5][co]);
-      v[3 * CO + co] = x00 * w[4][co];
-    }
-    lane_fold<NVAL, 16>(v, lane);
-    if (idx >= 0) {
-      float y = v[0] + bias;
-      if (epi == EPI_BIAS_RELU) y = fmaxf(y, 0.f);
-      else if (epi == EPI_BIAS_SIGMOID) y = 1.0f / (1.0f + expf(-y));
-      else if (masked) y = mk > 0.f ? y : 0.f;
-      a.out[o] = y;
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) xc[c] = xn[c];
-  }
-}
-
 #ifndef KCVAE_EMU
 #define KC_SET_SMEM(k, bytes) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #else
@@ -776,25 +614,6 @@ static bool conv_forward_lane(int mode, int epi, const ConvArgs& a, cudaStream_t
     }
 #undef KC_LANE_CO
     return true;
-  }
-  if (a.Ci == 32 && (a.Co == 5 || a.Co == 8)) {
-    if (mode == CONV_S2) {
-      const int WP = cdiv(a.Wo, 2);
-      const int64_t npairs = (int64_t)a.B * a.Ho * WP;
-      const int grid = grid_for(npairs * 32, 256, 3, 1);
-      ++g_launches;
-      if (a.Co == 5) KC_LAUNCH(conv_s2_lane_ci_kernel<5>, grid, 256, 0, st, a, npairs, WP, epi);
-      else KC_LAUNCH(conv_s2_lane_ci_kernel<8>, grid, 256, 0, st, a, npairs, WP, epi);
-      return true;
-    }
-    if (mode == CONVT_S2 && up2) {
-      const int64_t nq = (int64_t)a.B * a.Hi * a.Wi;
-      const int grid = grid_for(nq * 32, 256, 3, 1);
-      ++g_launches;
-      if (a.Co == 5) KC_LAUNCH(convT_s2_lane_ci_kernel<5>, grid, 256, 0, st, a, nq, epi);
-      else KC_LAUNCH(convT_s2_lane_ci_kernel<8>, grid, 256, 0, st, a, nq, epi);
-      return true;
-    }
   }
   return false;
 }

@@ -259,7 +259,7 @@ size_t max_partial_floats(const kcvae_model* h, int B) {
 #ifndef KCVAE_EMU
   if (h->use_tc_dgrad) up(tc_out_wgrad_partial_floats(h->dc[L], h->C));
   if (h->use_tc_convT_bwd) up(tc_convT_wgrad_partial_floats(h->dc[L - 1]));
-  if (h->use_tc_dgrad) up((size_t)kNumSMs * 8 * 32);
+  if (h->use_tc_dgrad) up((size_t)kNumSMs * 16 * 32);
 #endif
   return mx;
 }

@@ -34,6 +34,8 @@ constexpr int MT = (TR * PW) / 128;        // 8 M-tiles of 128 padded-row positi
 constexpr int NPAD = 16;                   // UMMA N (Cout padded)
 constexpr int kStages = 2;
 constexpr int kThreads = 192;
+constexpr int kSubD = 4;                   // tc_out_dgrad: epilogue warps per TMEM lane group
+constexpr int kThreadsD = 64 + 4 * kSubD * 32;
 constexpr int kThreadsE = 320;            // kernels with a per-tile epilogue: 2 + 8 warps (two epilogue warps per TMEM lane group)
 static_assert(TR * PW == MT * 128, "tile must be a whole number of M=128 tiles");
 
@@ -232,7 +234,7 @@ struct OutDgradParams {
 };
 constexpr int NPAD_D = 32;
 
-__global__ void __launch_bounds__(kThreadsE, 1)
+__global__ void __launch_bounds__(kThreadsD, 1)
 tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) {
   constexpr uint32_t CH = NPIX * 16;
   constexpr uint32_t TILE_BYTES = CH;                 // one 8-channel chunk plane
@@ -245,7 +247,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreadsE)
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreadsD)
     reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
   if (threadIdx.x < kStages * 8) {
     const int s = threadIdx.x / 8, j = threadIdx.x % 8;
@@ -254,7 +256,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   if (threadIdx.x == 32) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4 * kSubD); }
     fence_mbar_init();
   }
   fence_async_smem();
@@ -309,8 +311,11 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       __syncwarp();
     }
   } else {
+    // ============ epilogue: kSubD warps per TMEM lane group, each takes every kSubD-th M-tile ============
+    // The ReLU mask (the forward activation) does not depend on the MMAs: its four 16-byte units
+    // are requested BEFORE the accumulator wait, so the loads overlap the tensor-core work.
     const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int sub = (warp - 2) >> 2;
     float csum[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) csum[c] = 0.f;
@@ -321,40 +326,53 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       const int n = t / (p.tiles_y * p.tiles_x);
       const int rem = t % (p.tiles_y * p.tiles_x);
       const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
-      if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; break; }
-      fence_after_sync();
+      bool waited = false;
 #pragma unroll 1
-      for (int mt = half; mt < MT; mt += 2) {
-        float v[32];
-        const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MT * NPAD_D + mt * NPAD_D);
-        tmem_ld16(ta, v);
-        tmem_ld16(ta + 16, v + 16);
+      for (int mt = sub; mt < MT; mt += kSubD) {
         const int q = mt * 128 + lg * 32 + lane;
         const int r = q / PW, c = q % PW;
         const int oy = ty * TR + r, ox = tx * TW + c;
-        if (c < TW && oy < p.H && ox < p.W) {
-          const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
+        const bool live = c < TW && oy < p.H && ox < p.W;
+        const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
+        uint4 m[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) m[g] = make_uint4(0, 0, 0, 0);
+        if (live) {
           const uint4* mk = reinterpret_cast<const uint4*>(p.mask + pix * p.Cin);
-          float4* o = p.g_out ? reinterpret_cast<float4*>(p.g_out + pix * p.Cin) : nullptr;
-          uint4* o2 = nullptr;
-          if (p.g_s2d) {
-            const int64_t lp = ((int64_t)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
-            o2 = reinterpret_cast<uint4*>(p.g_s2d + (lp * 4 + ((oy & 1) * 2 + (ox & 1))) * p.Cin);
-          }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < 4; ++g)
+            if (g * 8 < p.Cin) m[g] = __ldg(mk + g);
+        }
+        if (!waited) {
+          if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; }
+          fence_after_sync();
+          waited = true;
+        }
+        const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MT * NPAD_D + mt * NPAD_D);
+        float4* o = (live && p.g_out) ? reinterpret_cast<float4*>(p.g_out + pix * p.Cin) : nullptr;
+        uint4* o2 = nullptr;
+        if (live && p.g_s2d) {
+          const int64_t lp = ((int64_t)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
+          o2 = reinterpret_cast<uint4*>(p.g_s2d + (lp * 4 + ((oy & 1) * 2 + (ox & 1))) * p.Cin);
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float v[16];
+          tmem_ld16(ta + 16 * hh, v);       // whole warp (sync.aligned), dead lanes discard
+#pragma unroll
+          for (int gg = 0; gg < 2; ++gg) {
+            const int g = hh * 2 + gg;
+            const uint32_t mw[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero (dead lanes: mask 0 -> y = 0)
+              const uint32_t h16 = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
+              const bool pos = (h16 & 0x8000u) == 0 && (h16 & 0x7FFFu) != 0;
+              y[j] = pos ? v[gg * 8 + j] : 0.f;
+              csum[g * 8 + j] += y[j];
+            }
             if (g * 8 < p.Cin) {
-              const uint4 m = __ldg(mk + g);
-              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-              float y[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero
-                const uint32_t h16 = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-                const bool pos = (h16 & 0x8000u) == 0 && (h16 & 0x7FFFu) != 0;
-                y[j] = pos ? v[g * 8 + j] : 0.f;
-                csum[g * 8 + j] += y[j];
-              }
               if (o) {
                 o[g * 2] = make_float4(y[0], y[1], y[2], y[3]);
                 o[g * 2 + 1] = make_float4(y[4], y[5], y[6], y[7]);
@@ -372,6 +390,9 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
           }
         }
       }
+      if (!waited) {   // kSubD > MT never happens, but keep the barrier protocol whole
+        if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; }
+      }
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
@@ -382,7 +403,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
         float t = csum[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (lane == 0) p.chan_partial[((int64_t)blockIdx.x * 8 + half * 4 + lg) * 32 + c] = t;
+        if (lane == 0) p.chan_partial[((int64_t)blockIdx.x * (4 * kSubD) + sub * 4 + lg) * 32 + c] = t;
       }
     }
   }
@@ -1414,9 +1435,9 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   ++g_launches;
   cudaFuncSetAttribute(tc_out_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   p.chan_partial = chan_sum ? chan_partial : nullptr;
-  tc_out_dgrad_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
+  tc_out_dgrad_kernel<<<grid, kThreadsD, smem, st>>>(tmap, p);
   if (chan_sum) {
-    sum_partials(chan_partial, grid * 8, Cin, chan_sum, st);
+    sum_partials(chan_partial, grid * 4 * kSubD, Cin, chan_sum, st);
   }
   return 0;
 }
