@@ -426,7 +426,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
 #ifndef KCVAE_EMU
   if (h->use_tc_out) {
     // tcgen05 implicit GEMM (tc_conv.cu): bf16 operands, fp32 accumulate in TMEM
-    if (!last_is_bf16) cast_f32_to_bf16(h->act_d[L], h->a_last_bf16, (int64_t)B * a.Hi * a.Wi * a.Ci, st);
+    if (!last_is_bf16) cast_f32_to_bf16_planar(h->act_d[L], h->a_last_bf16, B, (int64_t)a.Hi * a.Wi, a.Ci, st);
     tc_prep_out_weights(a.w, a.Co, a.Ci, h->wimg_out, st);
     if (tc_out_conv(h->a_last_bf16, h->wimg_out, a.bias, out, B, a.Hi, a.Wi, a.Ci, a.Co, apply_sigmoid, h->tc_error, st) == 0)
       return;

@@ -48,6 +48,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(mbar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// 3-D tiled TMA load from the chunk-planar activation layout [B*KC planes][H][W*8]: box (PW pixels x 8
+// channels = 512 contiguous bytes, PR rows, 1 plane) -> the same [pixel] x 16 B chunk plane in shared memory
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* mbar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(mbar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
 }
@@ -119,7 +128,7 @@ tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
         mbar_expect_tx(&full_bar[s], TILE_BYTES);
 #pragma unroll
         for (int c = 0; c < KC; ++c)   // one box per 8-channel chunk: smem = [chunk][row][col] x 16 B
-          tma_load_4d(s_tile + s * (TILE_BYTES + 128) + c * CH, &tmap, &full_bar[s], c * 8, tx * TW - 1, ty * TR - 1, n);
+          tma_load_3d(s_tile + s * (TILE_BYTES + 128) + c * CH, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TR - 1, n * KC + c);
       }
     }
   } else if (warp == 1) {
@@ -338,10 +347,13 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
 #pragma unroll
         for (int g = 0; g < 4; ++g) m[g] = make_uint4(0, 0, 0, 0);
         if (live) {
-          const uint4* mk = reinterpret_cast<const uint4*>(p.mask + pix * p.Cin);
+          // chunk-planar activation: plane (n, g) holds channels 8g..8g+7 of every pixel as one 16-byte unit
+          const int KCm = p.Cin >> 3;
+          const int64_t plane = (int64_t)p.H * p.W;
+          const uint4* mk = reinterpret_cast<const uint4*>(p.mask) + (int64_t)n * KCm * plane + (int64_t)oy * p.W + ox;
 #pragma unroll
           for (int g = 0; g < 4; ++g)
-            if (g * 8 < p.Cin) m[g] = __ldg(mk + g);
+            if (g < KCm) m[g] = __ldg(mk + g * plane);
         }
         if (!waited) {
           if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; }
@@ -488,7 +500,7 @@ tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutWgradParams p) 
         mbar_expect_tx(&full_bar[s], TILE_BYTES);
 #pragma unroll
         for (int c = 0; c < KC; ++c)
-          tma_load_4d(smem + s * STAGE + DL_BYTES + c * CH, &tmap, &full_bar[s], c * 8, tx * TW - 1, ty * TR - 1, n);
+          tma_load_3d(smem + s * STAGE + DL_BYTES + c * CH, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TR - 1, n * KC + c);
       }
     }
   } else if (warp == 1) {
@@ -610,7 +622,7 @@ static void sum_partials(const float* partial, int nparts, int E, float* out, cu
 struct ConvTParams {
   const __nv_bfloat16* wimg;   // [5 MMAs][2 chunks][32][8]
   const float* bias;           // [32]
-  __nv_bfloat16* out;          // [B,2h,2w,32] bf16
+  __nv_bfloat16* out;          // chunk-planar bf16 [B][4][2h][2w][8]
   int B, h, w;                 // low-res size
   int tiles_y, tiles_x, num_tiles;
   int* error_flag;
@@ -733,7 +745,8 @@ tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
           tmem_ld16(ta + 16, v + 16);
           if (valid) {
             const int oy = 2 * i + (phs >> 1), ox = 2 * j + (phs & 1);
-            uint4* o = reinterpret_cast<uint4*>(p.out + (((int64_t)n * H2 + oy) * W2 + ox) * 32);
+            const int64_t plane = (int64_t)H2 * W2;    // chunk-planar output [B][4][H2][W2][8]
+            uint4* o = reinterpret_cast<uint4*>(p.out) + (int64_t)n * 4 * plane + (int64_t)oy * W2 + ox;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               uint32_t w4[4];
@@ -744,7 +757,7 @@ tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
                 __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
                 w4[e] = *reinterpret_cast<uint32_t*>(&b2);
               }
-              o[g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              o[g * plane] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
           }
         }
@@ -1353,18 +1366,20 @@ __global__ void tail_score_finish_kernel(const float* partial, int tiles_per_fra
   if (err_minmax) { err_minmax[2 * b] = mn; err_minmax[2 * b + 1] = mx; }
 }
 
-__global__ void cast_f32_bf16_kernel(const float* in, __nv_bfloat16* out, int64_t n) {
-  const int64_t n4 = n >> 2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(in)[i];
-    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
-    uint2 o;
-    o.x = *reinterpret_cast<uint32_t*>(&a);
-    o.y = *reinterpret_cast<uint32_t*>(&b);
-    reinterpret_cast<uint2*>(out)[i] = o;
+// fp32 NHWC [B,HW,C] (C % 8 == 0) -> chunk-planar bf16 [B][C/8][HW][8]: thread = one 16-byte unit
+__global__ void cast_f32_bf16_planar_kernel(const float* in, uint4* out, int B, int64_t HW, int KC) {
+  const int64_t total = (int64_t)B * KC * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t px = i % HW;
+    const int g = (int)((i / HW) % KC);
+    const int64_t n = i / (HW * KC);
+    const float4* src = reinterpret_cast<const float4*>(in + ((n * HW + px) * KC + g) * 8);
+    const float4 v0 = __ldg(src), v1 = __ldg(src + 1);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v0.x, v0.y), b = __floats2bfloat162_rn(v0.z, v0.w);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v1.x, v1.y), d = __floats2bfloat162_rn(v1.z, v1.w);
+    out[i] = make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), *reinterpret_cast<uint32_t*>(&c),
+                        *reinterpret_cast<uint32_t*>(&d));
   }
-  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    out[i] = __float2bfloat16(in[i]);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1387,10 +1402,20 @@ bool tc_out_conv_supported(int Cin, int Cout) { return (Cin == 16 || Cin == 32) 
 
 size_t tc_out_weight_image_elems(int Cin) { return (size_t)9 * (Cin / 16) * 2 * NPAD * 8; }
 
-void cast_f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t st) {
+void cast_f32_to_bf16_planar(const float* in, void* out, int B, int64_t HW, int C, cudaStream_t st) {
   ProfScope prof_("cast_bf16", st);
   ++g_launches;
-  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1, 256, 8, 2), 256, 0, st>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  cast_f32_bf16_planar_kernel<<<grid_for((int64_t)B * HW * (C / 8), 256, 8, 2), 256, 0, st>>>(in, reinterpret_cast<uint4*>(out), B, HW, C / 8);
+}
+// tensor map of a chunk-planar bf16 activation [B][Cin/8][H][W][8]: dims (W*8, H, B*Cin/8), box = one halo plane
+static CUresult make_planar_tmap(CUtensorMap* tmap, const void* act, int B, int H, int W, int Cin) {
+  EncodeTiledFn enc = get_encode_fn();
+  const cuuint64_t gdim[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)B * (Cin / 8)};
+  const cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint32_t box[3] = {PW * 8, PR, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(act), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
 void tc_prep_out_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
@@ -1451,13 +1476,7 @@ int tc_out_wgrad(const void* dl8_bf16, const void* act_bf16, float* dW, float* p
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
   CUtensorMap tmap;
-  const cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  const cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-  const cuuint32_t box[4] = {8, PW, PR, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(act_bf16), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = make_planar_tmap(&tmap, act_bf16, B, H, W, Cin);
   if (r != CUDA_SUCCESS) return 2;
   OutWgradParams p{};
   p.dl8 = reinterpret_cast<const __nv_bfloat16*>(dl8_bf16);
@@ -1638,13 +1657,7 @@ int tc_out_conv(const void* act_bf16, const void* wimg, const float* bias, float
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
   CUtensorMap tmap;
-  const cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  const cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
-  const cuuint32_t box[4] = {8, PW, PR, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(act_bf16), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = make_planar_tmap(&tmap, act_bf16, B, H, W, Cin);
   if (r != CUDA_SUCCESS) return 2;
   OutConvParams p{};
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);

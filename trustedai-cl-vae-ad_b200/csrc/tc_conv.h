@@ -6,7 +6,9 @@ namespace kc {
 
 bool tc_out_conv_supported(int Cin, int Cout);
 size_t tc_out_weight_image_elems(int Cin);   // bf16 elements
-void cast_f32_to_bf16(const float* in, void* out_bf16, int64_t n, cudaStream_t st);
+// fp32 NHWC [B,HW,C] -> chunk-planar bf16 [B][C/8][HW][8], the layout every tensor-core consumer of the last
+// decoder activation reads (one TMA box row = 32 pixels x 16 B contiguous)
+void cast_f32_to_bf16_planar(const float* in, void* out_bf16, int B, int64_t HW, int C, cudaStream_t st);
 // W [3,3,Cout,Cin] fp32 (Keras Conv2DTranspose layout) -> UMMA B-operand image (bf16)
 void tc_prep_out_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
 // x_hat = [sigmoid](bias + conv3x3_s1_flipped(act)) ; act bf16 NHWC [B,H,W,Cin]; returns 0 on success
