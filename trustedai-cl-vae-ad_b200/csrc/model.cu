@@ -260,6 +260,7 @@ size_t max_partial_floats(const kcvae_model* h, int B) {
   if (h->use_tc_dgrad) up(tc_out_wgrad_partial_floats(h->dc[L], h->C));
   if (h->use_tc_convT_bwd) up(tc_convT_wgrad_partial_floats(h->dc[L - 1]));
   if (h->use_tc_dgrad) up((size_t)kNumSMs * 16 * 32);
+  if (h->use_tc_convT && h->use_tc_out) up(tc_tail_score_partial_floats(B, h->H, h->W));
 #endif
   return mx;
 }
@@ -383,7 +384,33 @@ void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st) {
   gemm(ga, st);
 }
 
-void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float* out, cudaStream_t st) {
+// true when the two last decoder layers can run as the single fused tensor-core kernel
+bool tail_fusable(const kcvae_model* h, int B) {
+#ifndef KCVAE_EMU
+  const int L = h->L;
+  return L >= 1 && h->use_tc_convT && h->use_tc_out && h->dc[L] == 32 &&
+         tc_tail_fused_supported(h->dc[L - 1], h->dc[L], h->C, h->dh[L], h->dw[L]) &&
+         h->partial_floats >= tc_tail_score_partial_floats(B, h->dh[L], h->dw[L]);
+#else
+  (void)h; (void)B;
+  return false;
+#endif
+}
+
+// What the fused decoder tail may produce besides / instead of x_hat (scoring, do_anomaly_detection.py:62,88)
+struct TailOut {
+  const float* x = nullptr;      // frames the reconstruction is compared with (needed for err / score)
+  float* err = nullptr;          // [B,H,W] or nullptr
+  float* score = nullptr;        // [B] or nullptr
+  float* err_minmax = nullptr;   // [B,2] or nullptr
+  bool done = false;             // set when the fused kernel produced them
+};
+
+// keep_last: the last 32-channel activation must exist in HBM afterwards (training: the backward reads it).
+// Inference entry points pass false: with the tensor-core tail the two last layers then run as ONE kernel and
+// that activation only ever exists as a shared-memory tile.  out may be nullptr when only the score is wanted.
+void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float* out, cudaStream_t st,
+                 bool keep_last = true, TailOut* tail = nullptr) {
   const int L = h->L;
   bool last_is_bf16 = false;   // the last activation was produced directly in bf16 by tc_convT_fwd
   GemmArgs ga{};
@@ -405,10 +432,24 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
     g_tag = l == L - 1 ? "dec.convT_last.fwd" : "dec.convT.fwd";
 #ifndef KCVAE_EMU
     if (l == L - 1 && h->use_tc_convT && h->use_tc_out) {
-      // sub-pixel phase decomposition on tcgen05, bf16 NHWC output straight into the buffer the
+      // sub-pixel phase decomposition on tcgen05, bf16 output straight into the buffer the
       // output-layer kernels read (no fp32 copy of the 224x300x32 activation exists in this mode)
       pack_c8_bf16(a.in, (int64_t)B * a.Hi * a.Wi, a.Ci, h->a_prev8, st);
       tc_prep_convT_weights(a.w, a.Co, a.Ci, h->wimg_convT, st);
+      if (!keep_last && tail_fusable(h, B)) {
+        const int vo = h->vi_out();
+        tc_prep_out_weights(h->wp(vo), h->C, h->dc[L], h->wimg_out, st);
+        g_tag = "dec.tail";
+        const bool want_score = tail && tail->x && (tail->err || tail->score);
+        if (tc_tail_fused(h->a_prev8, h->wimg_convT, h->wimg_out, a.bias, h->wp(vo + 1), want_score ? tail->x : nullptr, out,
+                          want_score ? tail->err : nullptr, want_score ? tail->score : nullptr,
+                          want_score ? tail->err_minmax : nullptr, h->partial, B, h->dh[L], h->dw[L], h->C, apply_sigmoid,
+                          h->tc_error, st) == 0) {
+          if (want_score) tail->done = true;
+          return;
+        }
+        g_tag = "dec.convT_last.fwd";
+      }
       if (tc_convT_fwd(h->a_prev8, h->wimg_convT, a.bias, h->a_last_bf16, B, a.Hi, a.Wi, h->tc_error, st) == 0) {
         last_is_bf16 = true;
         continue;
@@ -438,14 +479,15 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
 }
 
 // encode -> reparameterize -> decode+sigmoid into h->xhat (or user buffer); z/mean/logvar in h
-void run_forward(kcvae_model* h, const float* x, int B, int training, const float* eps, float* xhat, cudaStream_t st) {
+void run_forward(kcvae_model* h, const float* x, int B, int training, const float* eps, float* xhat, cudaStream_t st,
+                 bool keep_last = true, TailOut* tail = nullptr) {
   run_encoder(h, x, B, st);
   const int gen = (training && !eps) ? 1 : 0;
   g_tag = "latent";
   reparameterize(h->head, B, h->latent, eps, gen, h->seed, h->rng_counter, h->z, h->mean, h->logvar,
                  gen ? h->eps_buf : nullptr, st);
   if (gen) h->rng_counter += ((uint64_t)B * h->latent + 1) / 2;
-  run_decoder(h, h->z, B, 1, xhat, st);
+  run_decoder(h, h->z, B, 1, xhat, st, keep_last, tail);
   h->last_B = B;
 }
 
@@ -1048,7 +1090,7 @@ int kcvae_decode(kcvae_handle h, const float* d_z, int batch, int apply_sigmoid,
   if (!d_z || !d_out) return fail(h, KCVAE_ERR_INVALID, "decode: null pointer");
   KC_CUDA(h, cudaSetDevice(h->device));
   KC_TRY(ensure_fwd(h, batch));
-  run_decoder(h, d_z, batch, apply_sigmoid, d_out, (cudaStream_t)stream);
+  run_decoder(h, d_z, batch, apply_sigmoid, d_out, (cudaStream_t)stream, false);
   h->last_B = batch;
   return post(h);
 }
@@ -1060,7 +1102,7 @@ int kcvae_forward(kcvae_handle h, const float* d_x, int batch, int training, con
   cudaStream_t st = (cudaStream_t)stream;
   KC_CUDA(h, cudaSetDevice(h->device));
   KC_TRY(ensure_fwd(h, batch));
-  run_forward(h, d_x, batch, training, d_eps, d_xhat, st);
+  run_forward(h, d_x, batch, training, d_eps, d_xhat, st, false);
   const size_t nb = (size_t)batch * h->latent * sizeof(float);
   if (d_z) KC_CUDA(h, cudaMemcpyAsync(d_z, h->z, nb, cudaMemcpyDeviceToDevice, st));
   if (d_mean) KC_CUDA(h, cudaMemcpyAsync(d_mean, h->mean, nb, cudaMemcpyDeviceToDevice, st));
@@ -1078,7 +1120,7 @@ int kcvae_loss(kcvae_handle h, const float* d_x, int batch, int training, const 
   KC_CUDA(h, cudaSetDevice(h->device));
   KC_TRY(ensure_fwd(h, batch));
   float* xh = d_xhat ? d_xhat : h->xhat;
-  run_forward(h, d_x, batch, training, d_eps, xh, st);
+  run_forward(h, d_x, batch, training, d_eps, xh, st, false);
   KC_TRY(run_stats(h, d_x, xh, batch, tier, 0, st, st));
   run_finalize(h, batch, tier, d_metrics, st);
   return post(h);
@@ -1105,10 +1147,17 @@ int kcvae_score(kcvae_handle h, const float* d_x, int batch, float* d_err, float
   cudaStream_t st = (cudaStream_t)stream;
   KC_CUDA(h, cudaSetDevice(h->device));
   KC_TRY(ensure_fwd(h, batch));
-  float* xh = d_xhat ? d_xhat : h->xhat;
-  run_forward(h, d_x, batch, 0, nullptr, xh, st);
-  g_tag = "score";
-  score(d_x, xh, batch, (int64_t)h->H * h->W, h->C, d_err, d_score, d_err_minmax, h->partial, st);
+  TailOut tail;
+  tail.x = d_x; tail.err = d_err; tail.score = d_score; tail.err_minmax = d_err_minmax;
+  // fused tail: x_hat is only written when the caller asked for it
+  const bool fusable = tail_fusable(h, batch);
+  float* xh = d_xhat ? d_xhat : (fusable ? nullptr : h->xhat);
+  run_forward(h, d_x, batch, 0, nullptr, xh, st, false, &tail);
+  if (!tail.done) {
+    if (!xh) return fail(h, KCVAE_ERR_CUDA, "score: fused decoder tail unavailable (cuTensorMapEncodeTiled failed)");
+    g_tag = "score";
+    score(d_x, xh, batch, (int64_t)h->H * h->W, h->C, d_err, d_score, d_err_minmax, h->partial, st);
+  }
   return post(h);
 }
 

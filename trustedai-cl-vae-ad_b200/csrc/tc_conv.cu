@@ -1187,22 +1187,25 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (both phases) ===============================
+    // Issue order  A(0), A(1), B(0), A(2), B(1), ...  : phase A of the NEXT tile is queued in
+    // front of phase B of the current one, so while the tensor pipe grinds through the 144 phase-B
+    // MMAs the epilogue warps already turn A(t+1) into the next shared-memory tile.
     const bool leader = elect_one();
     const uint32_t idescA = make_idesc_bf16_f32(128, 32), idescB = make_idesc_bf16_f32(128, NPAD);
     const uint64_t wA0 = make_desc_kmajor_noswz(smem_u32(s_wA), 32 * 16, 128);
     const uint64_t wB0 = make_desc_kmajor_noswz(smem_u32(s_wB), NPAD * 16, 128);
-    int it = 0, ma = 0;
+    int ma = 0;
     bool ok = true;
-    for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      if (!mbar_wait(&a3_full[s], ph)) { if (leader) *p.error_flag = 1; break; }
+    auto issue_A = [&](int itA) {
+      const int s = itA & 1;
+      const uint32_t ph = (itA >> 1) & 1;
+      if (!mbar_wait(&a3_full[s], ph)) { if (leader) *p.error_flag = 1; ok = false; return; }
       fence_after_sync();
       const uint32_t a3b = smem_u32(s_a3 + s * A3_STAGE);
 #pragma unroll 1
       for (int mt = 0; mt < MTA; ++mt, ++ma) {
         const int slot = ma & 1;
-        if (!mbar_wait(&Aempty[slot], ((ma >> 1) & 1) ^ 1)) { if (leader) *p.error_flag = 1; ok = false; break; }
+        if (!mbar_wait(&Aempty[slot], ((ma >> 1) & 1) ^ 1)) { if (leader) *p.error_flag = 1; ok = false; return; }
         fence_after_sync();
         const uint32_t d0 = tmem + (uint32_t)(slot * 128);
         const uint32_t q0 = a3b + (uint32_t)(mt * 128) * 16;
@@ -1220,10 +1223,16 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
         }
         __syncwarp();
       }
-      if (!ok) break;
       if (leader) mma_commit(&a3_empty[s]);
       __syncwarp();
-      // ---- phase B on the smem tile the epilogue warps just produced
+    };
+    int it = 0;
+    if ((int)blockIdx.x < p.num_tiles) issue_A(0);
+    for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      if (t + (int)gridDim.x < p.num_tiles) { issue_A(it + 1); if (!ok) break; }
+      // ---- phase B on the smem tile the epilogue warps produced from A(it)
       if (!mbar_wait(&a4_ready[s], ph)) { if (leader) *p.error_flag = 1; break; }
       if (!mbar_wait(&Bempty[s], ph ^ 1)) { if (leader) *p.error_flag = 1; break; }
       fence_after_sync();
@@ -1250,24 +1259,28 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
       __syncwarp();
     }
   } else {
-    // ================================ epilogue warps (A then B per tile) =====================
+    // ================================ epilogue warps ========================================
+    // order  epiA(0), [epiA(t+1), epiB(t)]...  mirrors the MMA issue order above
     const int lg = warp & 3, half = (warp - 2) >> 2, ew = (warp - 2);
-    int it = 0, ma = 0;
+    int ma = 0;
     bool ok = true;
-    for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
-      const int s = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      const int n = t / (p.tiles_y * p.tiles_x);
+    auto tile_origin = [&](int t, int& n, int& ty0, int& tx0) {
+      n = t / (p.tiles_y * p.tiles_x);
       const int rem = t % (p.tiles_y * p.tiles_x);
-      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
-      const int ty0 = ty * TR, tx0 = tx * TW;
-      if (!mbar_wait(&a4_free[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; break; }   // phase B of tile it-2 done with this stage
+      ty0 = (rem / p.tiles_x) * TR; tx0 = (rem % p.tiles_x) * TW;
+    };
+    // ---- epilogue A: low-res phases -> bf16 halo tile of a_last in shared memory
+    auto epi_A = [&](int t, int itA) {
+      const int s = itA & 1;
+      const uint32_t ph = (itA >> 1) & 1;
+      int n, ty0, tx0;
+      tile_origin(t, n, ty0, tx0);
+      if (!mbar_wait(&a4_free[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; ok = false; return; }   // B(itA-2) done with this stage
       unsigned char* a4s = s_a4 + s * A4_STAGE;
-      // ---- epilogue A: low-res phases -> bf16 halo tile in shared memory
 #pragma unroll 1
       for (int mt = 0; mt < MTA; ++mt, ++ma) {
         const int slot = ma & 1;
-        if (!mbar_wait(&Afull[slot], (ma >> 1) & 1)) { if (lane == 0) *p.error_flag = 1; ok = false; break; }
+        if (!mbar_wait(&Afull[slot], (ma >> 1) & 1)) { if (lane == 0) *p.error_flag = 1; ok = false; return; }
         fence_after_sync();
         const int q = mt * 128 + lg * 32 + lane;
         const int r = q / PA, c = q % PA;
@@ -1302,12 +1315,17 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&Aempty[slot]);
       }
-      if (!ok) break;
       fence_async_smem();          // st.shared of the tile -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&a4_ready[s]);
-      // ---- epilogue B: sigmoid, reconstruction error, score partials
-      if (!mbar_wait(&Bfull[s], ph)) { if (lane == 0) *p.error_flag = 1; break; }
+    };
+    // ---- epilogue B: bias, sigmoid, reconstruction error, score partials
+    auto epi_B = [&](int t, int itB) {
+      const int s = itB & 1;
+      const uint32_t ph = (itB >> 1) & 1;
+      int n, ty0, tx0;
+      tile_origin(t, n, ty0, tx0);
+      if (!mbar_wait(&Bfull[s], ph)) { if (lane == 0) *p.error_flag = 1; ok = false; return; }
       fence_after_sync();
       float esum = 0.f, emin = 3.4e38f, emax = -3.4e38f;
 #pragma unroll 1
@@ -1348,6 +1366,12 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
           o3[0] = esum; o3[1] = emin; o3[2] = emax;
         }
       }
+    };
+    int it = 0;
+    if ((int)blockIdx.x < p.num_tiles) epi_A(blockIdx.x, 0);
+    for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
+      if (t + (int)gridDim.x < p.num_tiles) { epi_A(t + gridDim.x, it + 1); if (!ok) break; }
+      epi_B(t, it);
     }
   }
   fence_before_sync();
@@ -1355,15 +1379,32 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// per-frame reduction of the per-tile/per-warp partials written by tc_tail_fused_kernel
-__global__ void tail_score_finish_kernel(const float* partial, int tiles_per_frame, int B, float* score, float* err_minmax) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+// per-frame reduction of the per-tile/per-warp partials written by tc_tail_fused_kernel:
+// one block per frame, fixed strided order + fixed shuffle/shared-memory tree (deterministic)
+__global__ void __launch_bounds__(128) tail_score_finish_kernel(const float* partial, int entries_per_frame, float* score,
+                                                                float* err_minmax) {
+  __shared__ float red[3][4];
+  const int b = blockIdx.x;
+  const float* p0 = partial + (int64_t)b * entries_per_frame * 3;
   float s = 0.f, mn = 3.4e38f, mx = -3.4e38f;
-  const float* p0 = partial + (int64_t)b * tiles_per_frame * 8 * 3;
-  for (int i = 0; i < tiles_per_frame * 8; ++i) { s += p0[i * 3]; mn = fminf(mn, p0[i * 3 + 1]); mx = fmaxf(mx, p0[i * 3 + 2]); }
-  score[b] = s;
-  if (err_minmax) { err_minmax[2 * b] = mn; err_minmax[2 * b + 1] = mx; }
+  for (int i = threadIdx.x; i < entries_per_frame; i += 128) {
+    s += p0[i * 3]; mn = fminf(mn, p0[i * 3 + 1]); mx = fmaxf(mx, p0[i * 3 + 2]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = mn; red[2][threadIdx.x >> 5] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    score[b] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    if (err_minmax) {
+      err_minmax[2 * b] = fminf(fminf(red[1][0], red[1][1]), fminf(red[1][2], red[1][3]));
+      err_minmax[2 * b + 1] = fmaxf(fmaxf(red[2][0], red[2][1]), fmaxf(red[2][2], red[2][3]));
+    }
+  }
 }
 
 // fp32 NHWC [B,HW,C] (C % 8 == 0) -> chunk-planar bf16 [B][C/8][HW][8]: thread = one 16-byte unit
@@ -1646,7 +1687,7 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
   tc_tail_fused_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
   if (score) {
     ++g_launches;
-    tail_score_finish_kernel<<<cdiv(B, 128), 128, 0, st>>>(score_partial, p.tiles_y * p.tiles_x, B, score, err_minmax);
+    tail_score_finish_kernel<<<B, 128, 0, st>>>(score_partial, p.tiles_y * p.tiles_x * 8, score, err_minmax);
   }
   return 0;
 }
