@@ -5,6 +5,7 @@
 // score (do_anomaly_detection.py:57-117).
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -117,6 +118,7 @@ struct kcvae_model {
   float *minmax = nullptr, *metrics_dev = nullptr;
   // tensor-core path (precision == BF16_TC): bf16 copy of the last decoder activation, UMMA
   // weight image of the output layer, device-side error flag of the bounded barrier waits
+  bool fuse_train_tail = false;  // training forward: fused tail that also stores the activation for the backward
   bool tc_failed = false;        // a tensor-core launcher could not run (tensor map encode): the step is invalid
   bool use_tc_out = false, use_tc_dgrad = false, use_tc_convT = false, use_tc_convT_bwd = false;
   void* g_s2d = nullptr;         // bf16 space-to-depth d loss / d a_last [B,H/2,W/2,4,32]
@@ -436,13 +438,13 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
       // output-layer kernels read (no fp32 copy of the 224x300x32 activation exists in this mode)
       pack_c8_bf16(a.in, (int64_t)B * a.Hi * a.Wi, a.Ci, h->a_prev8, st);
       tc_prep_convT_weights(a.w, a.Co, a.Ci, h->wimg_convT, st);
-      if (!keep_last && tail_fusable(h, B)) {
+      if ((!keep_last || h->fuse_train_tail) && tail_fusable(h, B)) {
         const int vo = h->vi_out();
         tc_prep_out_weights(h->wp(vo), h->C, h->dc[L], h->wimg_out, st);
         g_tag = "dec.tail";
         const bool want_score = tail && tail->x && (tail->err || tail->score);
         if (tc_tail_fused(h->a_prev8, h->wimg_convT, h->wimg_out, a.bias, h->wp(vo + 1), want_score ? tail->x : nullptr, out,
-                          want_score ? tail->err : nullptr, want_score ? tail->score : nullptr,
+                          keep_last ? h->a_last_bf16 : nullptr, want_score ? tail->err : nullptr, want_score ? tail->score : nullptr,
                           want_score ? tail->err_minmax : nullptr, h->partial, B, h->dh[L], h->dw[L], h->C, apply_sigmoid,
                           h->tc_error, st) == 0) {
           if (want_score) tail->done = true;
@@ -831,6 +833,8 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
       if ((rc = dalloc(h, &wc, tc_convT_weight_image_elems()))) return bail(rc);
       h->wimg_convT = wc;
       h->use_tc_convT = true;
+      const char* ft = std::getenv("KCVAE_FUSE_TRAIN_TAIL");   // 0 = separate convT / out-conv kernels in the training forward
+      h->fuse_train_tail = !(ft && ft[0] == '0');
     }
     if (h->use_tc_convT && tc_convT_bwd_supported(h->dc[h->L - 1], h->dc[h->L], h->dh[h->L - 1], h->dw[h->L - 1]) &&
         tc_out_dgrad_supported(h->dc[h->L], h->C)) {

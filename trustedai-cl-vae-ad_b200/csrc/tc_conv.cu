@@ -1111,6 +1111,7 @@ tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
 constexpr int PA = 20;                     // pitch of the low-res a_prev tile
 constexpr int A3ROWS = 21;
 constexpr uint32_t A3_BYTES = A3ROWS * PA * 16;
+constexpr uint32_t A3_STAGE_BYTES = ((A3_BYTES + 128 + 127) / 128) * 128;   // TMA destinations must stay 128-byte aligned
 constexpr int LR_ROWS = 18, LR_COLS = 17;  // low-res pixels whose 2x2 phases cover the 34x32 halo tile
 constexpr int MTA = 3;                     // phase A M-tiles (LR_ROWS * PA = 360 <= 384)
 
@@ -1121,6 +1122,7 @@ struct TailParams {
   const float* biasB;          // [Cout]
   const float* x;              // [B,H,W,Cout] fp32 (needed for err / score) or nullptr
   float* xhat;                 // [B,H,W,Cout] or nullptr
+  uint4* a_last;               // chunk-planar bf16 [B][4][H][W][8] copy of the intermediate activation (training) or nullptr
   float* err;                  // [B,H,W] or nullptr
   float* score_partial;        // [num_tiles][8][3] (sum, min, max of err per epilogue warp) or nullptr
   int B, H, W, Cout;
@@ -1134,7 +1136,7 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
   constexpr uint32_t CH = NPIX * 16;
   constexpr uint32_t A4_BYTES = 4 * CH;
   constexpr uint32_t A4_STAGE = A4_BYTES + 128;
-  constexpr uint32_t A3_STAGE = A3_BYTES + 128;
+  constexpr uint32_t A3_STAGE = A3_STAGE_BYTES;
   constexpr uint32_t WA_BYTES = 5 * 2 * 32 * 16, WB_BYTES = 9 * 2 * 2 * NPAD * 16;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* s_a4 = smem;                               // 2 stages
@@ -1307,7 +1309,11 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
                 __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
                 w4[e] = *reinterpret_cast<uint32_t*>(&b2);
               }
-              dst[g * (CH / 16)] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              const uint4 u = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+              dst[g * (CH / 16)] = u;
+              // training: the backward needs this activation; every tile stores its own 32x30 interior
+              if (p.a_last && inside && hr >= 1 && hr <= TR && hc >= 1 && hc <= TW)
+                p.a_last[((int64_t)n * 4 + g) * ((int64_t)p.H * p.W) + (int64_t)Y * p.W + X] = u;
             }
           }
         }
@@ -1654,8 +1660,8 @@ size_t tc_tail_score_partial_floats(int B, int H, int W) { return (size_t)B * cd
 // fused Conv2DTranspose s2 -> Conv2DTranspose s1 (+ sigmoid, error map, per-frame score).
 // in8: bf16 [B,H/2,W/2,8]; any of xhat / err / score may be nullptr (x is required for err / score).
 int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, const float* biasA, const float* biasB,
-                  const float* x, float* xhat, float* err, float* score, float* err_minmax, float* score_partial, int B,
-                  int H, int W, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st) {
+                  const float* x, float* xhat, void* a_last_planar, float* err, float* score, float* err_minmax,
+                  float* score_partial, int B, int H, int W, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
   const int h = H / 2, w = W / 2;
@@ -1672,6 +1678,7 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
   p.wimgA = reinterpret_cast<const __nv_bfloat16*>(wimgA);
   p.wimgB = reinterpret_cast<const __nv_bfloat16*>(wimgB);
   p.biasA = biasA; p.biasB = biasB; p.x = x; p.xhat = xhat; p.err = err;
+  p.a_last = reinterpret_cast<uint4*>(a_last_planar);
   p.score_partial = score ? score_partial : nullptr;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
   p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
@@ -1679,7 +1686,7 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
   p.apply_sigmoid = apply_sigmoid;
   p.error_flag = error_flag;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  const size_t smem = (size_t)2 * ((size_t)4 * NPIX * 16 + 128) + (size_t)2 * (A3_BYTES + 128) + (size_t)5 * 2 * 32 * 16 +
+  const size_t smem = (size_t)2 * ((size_t)4 * NPIX * 16 + 128) + (size_t)2 * A3_STAGE_BYTES + (size_t)5 * 2 * 32 * 16 +
                       (size_t)9 * 2 * 2 * NPAD * 16;
   ProfScope prof_("tc_tail_fused", st);
   ++g_launches;

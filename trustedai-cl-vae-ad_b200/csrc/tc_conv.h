@@ -46,9 +46,10 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg_bf16, const float* bias,
 // 32-channel activation kept in shared memory; optional sigmoid, x_hat, error map and per-frame score
 bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W);
 size_t tc_tail_score_partial_floats(int B, int H, int W);
+// a_last_planar (optional): chunk-planar bf16 copy of the intermediate activation for the backward pass
 int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, const float* biasA, const float* biasB,
-                  const float* x, float* xhat, float* err, float* score, float* err_minmax, float* score_partial, int B,
-                  int H, int W, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st);
+                  const float* x, float* xhat, void* a_last_planar, float* err, float* score, float* err_minmax,
+                  float* score_partial, int B, int H, int W, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st);
 
 // output-layer weight gradient (MN-major tcgen05, K = pixels); partial >= tc_out_wgrad_partial_floats()
 bool tc_out_wgrad_supported(int Cin, int Cout);
