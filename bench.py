@@ -152,11 +152,36 @@ def algorithmic_bytes(cfg, B, world):
                         ("dec.convT_last.bwd/tc_convT_dgrad", "dec.convT_last.bwd/conv3x3")):
         if generic in tab:
             tab[tc] = tab[generic]
+    tab["dec.dense.fwd/dense_wide_fwd"] = tab["dec.dense.fwd/gemm"]
+    tab["dec.dense.bwd/dense_wide_wgrad"] = B * (4 * t.latent + act * dec[0]) + wd     # z, G in; dW (+ bias grad) out
+    tab["dec.dense.bwd/dense_wide_dgrad"] = B * (4 * t.latent + act * dec[0]) + wd     # G, W in; dz out
+    # fused decoder tail (last Conv2DTranspose s2 + output conv): a_prev in; a_last (training only) and x_hat out
+    wt = 4 * (nW[f"decoder/conv2d_transpose_{L - 1}/kernel"] + nW["decoder/conv2d_transpose_out/kernel"]) if L else 0
+    tab["dec.tail/tc_tail_fused"] = B * act * (dec[L - 1] + dec[L] + I) + wt if L else 0
     tab["loss/image_stats"] = B * (4 * I + act * I + act * I)      # x, xhat in; dlogit out
     P = sum(nW.values())
     tab["optimizer/adam"] = 7 * 4 * P                               # p,g,m,v read; p,m,v written
     step_bytes = B * (4 * I + act * (5 * (sum(enc[1:]) + sum(dec)) + 3 * I)) + 10 * 4 * P   # SURVEY 8d train
     return tab, step_bytes
+
+
+def measured_traffic(launcher_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `launcher_key`, from the
+    committed `ncu --set full` summary (profiles/ncu_traffic.json, written by tools/ncu_summarize.py); None if
+    that kernel was not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None
+    kern = launcher_key.split("/")[-1]
+    for name, rec in d.get("kernels", {}).items():
+        if kern in name:
+            return {"bytes_per_launch": rec["dram_bytes"], "frames_per_launch": d.get("frames_per_launch"),
+                    "source": d.get("source")}
+    return None
 
 
 def hbm_peak():
@@ -317,6 +342,10 @@ def run_ours(args):
         roof["frac"] = roof["achieved"] / peak
         roof["avg_launch_ms"] = top_ms / top_calls
         roof["algorithmic_bytes_per_launch"] = tab[top_key]
+        tr = measured_traffic(top_key)
+        if tr and tr.get("frames_per_launch") == B:
+            roof["traffic"] = tr["bytes_per_launch"]
+            roof["traffic_source"] = tr["source"]
     else:
         roof["achieved"], roof["frac"] = None, None
     step_ach = step_bytes / (ms_total / K * 1e-3) / 1e9

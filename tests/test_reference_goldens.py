@@ -94,7 +94,11 @@ def check_backend(backend, path, precision=None):
     d, mg = m.loss_and_grads(x, eps=eps)
     assert_metrics_close(d, as_dict(g, "loss_train"), rtol=r_loss, atol=1e-6)           # contract: 1e-3
     for i, (a, b) in enumerate(zip(mg, grads)):
-        assert rel_err(a, b) < r_grad, f"gradient of variable {i}: {rel_err(a, b)}"
+        if tc:   # bf16 operands: relative L2 bar (as tests/test_gpu_parity.py), max-abs only loosely
+            l2 = float(np.linalg.norm(np.asarray(a, np.float64) - b) / (np.linalg.norm(b) + 1e-30))
+            assert l2 < r_grad and rel_err(a, b) < 3 * r_grad, f"gradient of variable {i}: L2 {l2}, max {rel_err(a, b)}"
+        else:
+            assert rel_err(a, b) < r_grad, f"gradient of variable {i}: {rel_err(a, b)}"
     m.compile(optimizer=pkg.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
     keys = list(as_dict(g, "loss_train").keys())
     for s in range(3):

@@ -1124,7 +1124,7 @@ struct TailParams {
   float* xhat;                 // [B,H,W,Cout] or nullptr
   uint4* a_last;               // chunk-planar bf16 [B][4][H][W][8] copy of the intermediate activation (training) or nullptr
   float* err;                  // [B,H,W] or nullptr
-  float* score_partial;        // [num_tiles][8][3] (sum, min, max of err per epilogue warp) or nullptr
+  float* score_partial;        // [num_tiles][4][3] (sum, min, max of err per epilogue warp) or nullptr
   int B, H, W, Cout;
   int tiles_y, tiles_x, num_tiles;
   int apply_sigmoid;
@@ -1161,9 +1161,9 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
   if (threadIdx.x == 32) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a3_full[s], 1); mbar_init(&a3_empty[s], 1);
-      mbar_init(&Afull[s], 1);   mbar_init(&Aempty[s], 8);
-      mbar_init(&a4_ready[s], 8); mbar_init(&a4_free[s], 1);
-      mbar_init(&Bfull[s], 1);   mbar_init(&Bempty[s], 8);
+      mbar_init(&Afull[s], 1);   mbar_init(&Aempty[s], 4);
+      mbar_init(&a4_ready[s], 4); mbar_init(&a4_free[s], 1);
+      mbar_init(&Bfull[s], 1);   mbar_init(&Bempty[s], 4);
     }
     fence_mbar_init();
   }
@@ -1262,122 +1262,145 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
     }
   } else {
     // ================================ epilogue warps ========================================
-    // order  epiA(0), [epiA(t+1), epiB(t)]...  mirrors the MMA issue order above
-    const int lg = warp & 3, half = (warp - 2) >> 2, ew = (warp - 2);
-    int ma = 0;
+    // Two independent groups of four warps (one per TMEM lane group each): warps 2..5 turn the
+    // phase-A accumulators into the next shared-memory tile, warps 6..9 drain phase B.  Neither
+    // waits for the other, so both overlap the phase-B MMAs of the tile in flight.
+    const int lg = warp & 3;
+    const bool groupA = warp < 6;
     bool ok = true;
     auto tile_origin = [&](int t, int& n, int& ty0, int& tx0) {
       n = t / (p.tiles_y * p.tiles_x);
       const int rem = t % (p.tiles_y * p.tiles_x);
       ty0 = (rem / p.tiles_x) * TR; tx0 = (rem % p.tiles_x) * TW;
     };
-    // ---- epilogue A: low-res phases -> bf16 halo tile of a_last in shared memory
-    auto epi_A = [&](int t, int itA) {
-      const int s = itA & 1;
-      const uint32_t ph = (itA >> 1) & 1;
-      int n, ty0, tx0;
-      tile_origin(t, n, ty0, tx0);
-      if (!mbar_wait(&a4_free[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; ok = false; return; }   // B(itA-2) done with this stage
-      unsigned char* a4s = s_a4 + s * A4_STAGE;
+    if (groupA) {
+      // ---- epilogue A: low-res phases -> bf16 halo tile of a_last in shared memory
+      int ma = 0, it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        int n, ty0, tx0;
+        tile_origin(t, n, ty0, tx0);
+        if (!mbar_wait(&a4_free[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; break; }   // B(it-2) done with this stage
+        unsigned char* a4s = s_a4 + s * A4_STAGE;
 #pragma unroll 1
-      for (int mt = 0; mt < MTA; ++mt, ++ma) {
-        const int slot = ma & 1;
-        if (!mbar_wait(&Afull[slot], (ma >> 1) & 1)) { if (lane == 0) *p.error_flag = 1; ok = false; return; }
-        fence_after_sync();
-        const int q = mt * 128 + lg * 32 + lane;
-        const int r = q / PA, c = q % PA;
-        const bool live = r < LR_ROWS && c < LR_COLS;
+        for (int mt = 0; mt < MTA; ++mt, ++ma) {
+          const int slot = ma & 1;
+          if (!mbar_wait(&Afull[slot], (ma >> 1) & 1)) { if (lane == 0) *p.error_flag = 1; ok = false; break; }
+          fence_after_sync();
+          const int q = mt * 128 + lg * 32 + lane;
+          const int r = q / PA, c = q % PA;
+          const bool live = r < LR_ROWS && c < LR_COLS;
+#pragma unroll 1
+          for (int phs = 0; phs < 4; ++phs) {
+            const int pa = phs >> 1, pb = phs & 1;
+            float v[32];
+            const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * 128 + phs * 32);
+            tmem_ld16(ta, v);
+            tmem_ld16(ta + 16, v + 16);
+            const int hr = 2 * r + pa - 1, hc = 2 * c + pb - 1;
+            if (live && hr >= 0 && hr < PR && hc >= 0 && hc < PW) {
+              const int Y = ty0 - 1 + hr, X = tx0 - 1 + hc;
+              const bool inside = Y >= 0 && Y < p.H && X >= 0 && X < p.W;
+              const bool keep = p.a_last && inside && hr >= 1 && hr <= TR && hc >= 1 && hc <= TW;
+              uint4* dst = reinterpret_cast<uint4*>(a4s) + (hr * PW + hc);
+              uint4* gdst = keep ? p.a_last + (int64_t)n * 4 * ((int64_t)p.H * p.W) + (int64_t)Y * p.W + X : nullptr;
 #pragma unroll
-        for (int pb = 0; pb < 2; ++pb) {
-          const int phs = half * 2 + pb;              // this warp handles output rows of parity `half`
-          float v[32];
-          const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * 128 + phs * 32);
-          tmem_ld16(ta, v);
-          tmem_ld16(ta + 16, v + 16);
-          const int hr = 2 * r + half - 1, hc = 2 * c + pb - 1;
-          if (live && hr >= 0 && hr < PR && hc >= 0 && hc < PW) {
-            const int Y = ty0 - 1 + hr, X = tx0 - 1 + hc;
-            const bool inside = Y >= 0 && Y < p.H && X >= 0 && X < p.W;
-            uint4* dst = reinterpret_cast<uint4*>(a4s) + (hr * PW + hc);
+              for (int g = 0; g < 4; ++g) {
+                uint32_t w4[4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t w4[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float y0 = inside ? fmaxf(v[g * 8 + 2 * e] + s_biasA[g * 8 + 2 * e], 0.f) : 0.f;
-                const float y1 = inside ? fmaxf(v[g * 8 + 2 * e + 1] + s_biasA[g * 8 + 2 * e + 1], 0.f) : 0.f;
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-                w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+                for (int e = 0; e < 4; ++e) {
+                  const float y0 = inside ? fmaxf(v[g * 8 + 2 * e] + s_biasA[g * 8 + 2 * e], 0.f) : 0.f;
+                  const float y1 = inside ? fmaxf(v[g * 8 + 2 * e + 1] + s_biasA[g * 8 + 2 * e + 1], 0.f) : 0.f;
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                  w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                const uint4 u = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                dst[g * (CH / 16)] = u;
+                // training: the backward needs this activation; every tile stores its own 32x30 interior
+                if (keep) gdst[g * ((int64_t)p.H * p.W)] = u;
               }
-              const uint4 u = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-              dst[g * (CH / 16)] = u;
-              // training: the backward needs this activation; every tile stores its own 32x30 interior
-              if (p.a_last && inside && hr >= 1 && hr <= TR && hc >= 1 && hc <= TW)
-                p.a_last[((int64_t)n * 4 + g) * ((int64_t)p.H * p.W) + (int64_t)Y * p.W + X] = u;
             }
+          }
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&Aempty[slot]);
+        }
+        if (!ok) break;
+        fence_async_smem();          // st.shared of the tile -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a4_ready[s]);
+      }
+    } else {
+      // ---- epilogue B: bias, sigmoid, reconstruction error, score partials
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        int n, ty0, tx0;
+        tile_origin(t, n, ty0, tx0);
+        // the frame values this warp compares with do not depend on the MMAs: request the first
+        // M-tile's before the accumulator wait, and every next one while the current is reduced
+        auto pix_of = [&](int mt, bool& live) -> int64_t {
+          const int q = mt * 128 + lg * 32 + lane;
+          const int r = q / PW, c = q % PW;
+          const int oy = ty0 + r, ox = tx0 + c;
+          live = c < TW && oy < p.H && ox < p.W;
+          return ((int64_t)n * p.H + oy) * p.W + ox;
+        };
+        float xn[8];
+        auto load_x = [&](int mt) {
+          bool live;
+          const int64_t pix = pix_of(mt, live);
+#pragma unroll
+          for (int co = 0; co < 8; ++co) xn[co] = (p.x && live && co < p.Cout) ? __ldg(p.x + pix * p.Cout + co) : 0.f;
+        };
+        load_x(0);
+        if (!mbar_wait(&Bfull[s], ph)) { if (lane == 0) *p.error_flag = 1; break; }
+        fence_after_sync();
+        float esum = 0.f, emin = 3.4e38f, emax = -3.4e38f;
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+          float xc[8];
+#pragma unroll
+          for (int co = 0; co < 8; ++co) xc[co] = xn[co];
+          if (mt + 1 < MT) load_x(mt + 1);
+          float v[8];
+          tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + s * 128 + mt * NPAD), v);
+          bool live;
+          const int64_t pix = pix_of(mt, live);
+          if (live) {
+            float e = 0.f;
+#pragma unroll
+            for (int co = 0; co < 8; ++co) {
+              if (co < p.Cout) {
+                float y = v[co] + s_biasB[co];
+                if (p.apply_sigmoid) y = 1.0f / (1.0f + __expf(-y));
+                if (p.xhat) p.xhat[pix * p.Cout + co] = y;
+                const float d = xc[co] - y;
+                e = fmaf(d, d, e);
+              }
+            }
+            if (p.err) p.err[pix] = e;
+            esum += e; emin = fminf(emin, e); emax = fmaxf(emax, e);
           }
         }
         fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&Aempty[slot]);
-      }
-      fence_async_smem();          // st.shared of the tile -> visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a4_ready[s]);
-    };
-    // ---- epilogue B: bias, sigmoid, reconstruction error, score partials
-    auto epi_B = [&](int t, int itB) {
-      const int s = itB & 1;
-      const uint32_t ph = (itB >> 1) & 1;
-      int n, ty0, tx0;
-      tile_origin(t, n, ty0, tx0);
-      if (!mbar_wait(&Bfull[s], ph)) { if (lane == 0) *p.error_flag = 1; ok = false; return; }
-      fence_after_sync();
-      float esum = 0.f, emin = 3.4e38f, emax = -3.4e38f;
-#pragma unroll 1
-      for (int mt = half; mt < MT; mt += 2) {
-        float v[8];
-        tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + s * 128 + mt * NPAD), v);
-        const int q = mt * 128 + lg * 32 + lane;
-        const int r = q / PW, c = q % PW;
-        const int oy = ty0 + r, ox = tx0 + c;
-        if (c < TW && oy < p.H && ox < p.W) {
-          const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
-          float e = 0.f;
+        if (lane == 0) mbar_arrive(&Bempty[s]);
+        if (p.score_partial) {     // fixed shuffle tree -> deterministic
 #pragma unroll
-          for (int co = 0; co < 8; ++co) {
-            if (co < p.Cout) {
-              float y = v[co] + s_biasB[co];
-              if (p.apply_sigmoid) y = 1.0f / (1.0f + __expf(-y));
-              if (p.xhat) p.xhat[pix * p.Cout + co] = y;
-              if (p.x) { const float d = __ldg(p.x + pix * p.Cout + co) - y; e = fmaf(d, d, e); }
-            }
+          for (int o = 16; o > 0; o >>= 1) {
+            esum += __shfl_xor_sync(0xffffffffu, esum, o);
+            emin = fminf(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+            emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
           }
-          if (p.err) p.err[pix] = e;
-          esum += e; emin = fminf(emin, e); emax = fmaxf(emax, e);
+          if (lane == 0) {
+            float* o3 = p.score_partial + ((int64_t)t * 4 + lg) * 3;
+            o3[0] = esum; o3[1] = emin; o3[2] = emax;
+          }
         }
       }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&Bempty[s]);
-      if (p.score_partial) {     // fixed shuffle tree -> deterministic
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          esum += __shfl_xor_sync(0xffffffffu, esum, o);
-          emin = fminf(emin, __shfl_xor_sync(0xffffffffu, emin, o));
-          emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
-        }
-        if (lane == 0) {
-          float* o3 = p.score_partial + ((int64_t)t * 8 + ew) * 3;
-          o3[0] = esum; o3[1] = emin; o3[2] = emax;
-        }
-      }
-    };
-    int it = 0;
-    if ((int)blockIdx.x < p.num_tiles) epi_A(blockIdx.x, 0);
-    for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
-      if (t + (int)gridDim.x < p.num_tiles) { epi_A(t + gridDim.x, it + 1); if (!ok) break; }
-      epi_B(t, it);
     }
   }
   fence_before_sync();
@@ -1655,7 +1678,7 @@ int tc_convT_wgrad(const void* g_s2d, const void* a_prev8, float* dW, float* par
 bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W) {
   return Cprev >= 1 && Cprev <= 8 && Clast == 32 && Cout >= 1 && Cout <= 8 && H % 2 == 0 && W % 2 == 0;
 }
-size_t tc_tail_score_partial_floats(int B, int H, int W) { return (size_t)B * cdiv(H, TR) * cdiv(W, TW) * 8 * 3; }
+size_t tc_tail_score_partial_floats(int B, int H, int W) { return (size_t)B * cdiv(H, TR) * cdiv(W, TW) * 4 * 3; }
 
 // fused Conv2DTranspose s2 -> Conv2DTranspose s1 (+ sigmoid, error map, per-frame score).
 // in8: bf16 [B,H/2,W/2,8]; any of xhat / err / score may be nullptr (x is required for err / score).
@@ -1694,7 +1717,7 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
   tc_tail_fused_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
   if (score) {
     ++g_launches;
-    tail_score_finish_kernel<<<B, 128, 0, st>>>(score_partial, p.tiles_y * p.tiles_x * 8, score, err_minmax);
+    tail_score_finish_kernel<<<B, 128, 0, st>>>(score_partial, p.tiles_y * p.tiles_x * 4, score, err_minmax);
   }
   return 0;
 }
