@@ -360,12 +360,19 @@ __device__ __forceinline__ void cp_async4_zfill(float* smem_dst, const float* gs
   const int n = valid ? 4 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
+// 16-byte async copy; !valid writes zeros without touching the source
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 #else
 static inline void cp_async16(void* d, const void* s) { memcpy(d, s, 16); }
 static inline void cp_async4_zfill(float* d, const float* s, bool valid) { *d = valid ? *s : 0.f; }
+static inline void cp_async16_zfill(void* d, const void* s, bool valid) { if (valid) memcpy(d, s, 16); else memset(d, 0, 16); }
 static inline void cp_async_commit() {}
 template <int N> static inline void cp_async_wait() {}
 #endif
@@ -569,6 +576,242 @@ __global__ void __launch_bounds__(256) convT_s2_lane_co_kernel(ConvArgs a, int r
   }
 }
 
+// =========================================================================================
+// 32 -> few channel layers (encoder Conv2D #1, first decoder Conv2DTranspose): K = 288 per
+// output pixel, only CO <= 8 outputs.  Block = two output (resp. input) rows; the input rows are
+// staged once in shared memory with 16-byte async copies (coalesced 128-byte pixels) under an
+// XOR swizzle of the 16-byte chunk index, so the per-pixel float4 reads of a warp hit 32 distinct
+// banks.  The 32 input channels are split over four thread groups (8 channels each) whose
+// partial sums are folded through shared memory in a fixed order; weights are warp-broadcast
+// float4 reads of a [tap][ci][co] image.
+// =========================================================================================
+constexpr int M2F_SLOTS = 96;                  // pixel-pair slots per channel group
+constexpr int M2F_THREADS = 4 * M2F_SLOTS;
+
+template <int CO>
+__device__ __forceinline__ void m2f_stage_weights(const ConvArgs& a, float* ws) {
+  for (int i = threadIdx.x; i < 9 * 32 * CO; i += blockDim.x) {
+    const int co = i % CO, ci = (i / CO) % 32, tap = i / (CO * 32);
+    ws[i] = __ldg(a.w + (int64_t)tap * 32 * CO + (int64_t)ci * a.w_sci + (int64_t)co * a.w_sco);
+  }
+}
+__device__ __forceinline__ float m2f_epi(float v, int epi, float mk) {
+  if (epi == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+  else if (epi == EPI_BIAS_SIGMOID) v = 1.0f / (1.0f + expf(-v));
+  else if (epi == EPI_MASK) v = mk > 0.f ? v : 0.f;
+  return v;
+}
+
+// ---- Conv2D s2, Ci = 32 -> CO.  task = (image, pair of output rows); thread = 2 adjacent output pixels
+template <int CO>
+__global__ void __launch_bounds__(M2F_THREADS) conv_s2_m2f_kernel(ConvArgs a, int n_tasks, int HB, int NCOL, int PPR, int epi) {
+  KC_DYN_SMEM(float, sm);
+  float* tile = sm;                               // [5 rows][NCOL][32], chunk-swizzled; reused for the fold
+  float* ws = sm + 5 * NCOL * 32;                 // [9][32][CO]
+  const int tid = threadIdx.x;
+  m2f_stage_weights<CO>(a, ws);
+  const int p = tid % M2F_SLOTS, cg = tid / M2F_SLOTS;
+  const int rr = p / PPR, pp = p % PPR;
+  const bool pvalid = p < 2 * PPR;
+  const bool masked = epi == EPI_MASK;
+  for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+    const int n = task / HB, oy0 = 2 * (task % HB);
+    __syncthreads();
+    const int chunks = 5 * NCOL * 8;
+    for (int idx = tid; idx < chunks; idx += blockDim.x) {
+      const int c4 = idx & 7, pc = idx >> 3;
+      const int r = pc / NCOL, cs = pc - r * NCOL;
+      const int iy = 2 * oy0 + r - a.pad_t, ix = cs - a.pad_l;
+      const bool ok = iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
+      const float* src = a.in + ((((int64_t)n * a.Hi + (ok ? iy : 0)) * a.Wi) + (ok ? ix : 0)) * 32 + c4 * 4;
+      cp_async16_zfill(tile + (r * NCOL + cs) * 32 + ((c4 ^ ((cs >> 2) & 7)) << 2), src, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int oy = oy0 + rr;
+    const bool live = pvalid && oy < a.Ho;
+    float acc[2][CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) { acc[0][co] = 0.f; acc[1][co] = 0.f; }
+    if (live) {
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const float* rowp = tile + (2 * rr + kh) * NCOL * 32;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int c4 = 2 * cg + q;
+          float x[5][4];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int cs = 4 * pp + k;
+            const float4 t = *reinterpret_cast<const float4*>(rowp + cs * 32 + ((c4 ^ ((cs >> 2) & 7)) << 2));
+            x[k][0] = t.x; x[k][1] = t.y; x[k][2] = t.z; x[k][3] = t.w;
+          }
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float4* wp = reinterpret_cast<const float4*>(ws + ((kh * 3 + kw) * 8 + c4) * 4 * CO);
+            float wv[4 * CO];
+#pragma unroll
+            for (int u = 0; u < CO; ++u) { const float4 t = wp[u]; wv[4 * u] = t.x; wv[4 * u + 1] = t.y; wv[4 * u + 2] = t.z; wv[4 * u + 3] = t.w; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int co = 0; co < CO; ++co) {
+                acc[0][co] = fmaf(x[kw][c], wv[c * CO + co], acc[0][co]);
+                acc[1][co] = fmaf(x[kw + 2][c], wv[c * CO + co], acc[1][co]);
+              }
+          }
+        }
+      }
+    }
+    __syncthreads();                               // tile reads done: reuse it as [4][M2F_SLOTS][2][CO]
+    float* red = tile;
+    if (live) {
+#pragma unroll
+      for (int px = 0; px < 2; ++px)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) red[((cg * M2F_SLOTS + p) * 2 + px) * CO + co] = acc[px][co];
+    }
+    __syncthreads();
+    if (cg == 0 && live) {
+      float mk[2][CO];
+      const int64_t o0 = (((int64_t)n * a.Ho + oy) * a.Wo + 2 * pp) * CO;
+      if (masked) {
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+          for (int co = 0; co < CO; ++co) mk[px][co] = (2 * pp + px < a.Wo) ? __ldg(a.mask + o0 + px * CO + co) : 0.f;
+      }
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        if (2 * pp + px >= a.Wo) break;
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+          float v = (a.bias && !masked) ? __ldg(a.bias + co) : 0.f;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) v += red[((g * M2F_SLOTS + p) * 2 + px) * CO + co];
+          a.out[o0 + px * CO + co] = m2f_epi(v, epi, masked ? mk[px][co] : 1.f);
+        }
+      }
+    }
+  }
+}
+
+// ---- Conv2DTranspose s2 (pad 0, Ho = 2 Hi, Wo = 2 Wi), Ci = 32 -> CO.  task = (image, pair of input
+// rows); thread = 2 adjacent input pixels, each producing its 2x2 output quad (9 taps)
+template <int CO>
+__global__ void __launch_bounds__(M2F_THREADS) convT_s2_m2f_kernel(ConvArgs a, int n_tasks, int HB, int NCOL, int PPR, int epi,
+                                                                   int tile_floats) {
+  KC_DYN_SMEM(float, sm);
+  float* tile = sm;                               // [3 rows][NCOL][32], column c holds ix = c - 1; reused for the fold
+  float* ws = sm + tile_floats;
+  const int tid = threadIdx.x;
+  m2f_stage_weights<CO>(a, ws);
+  const int p = tid % M2F_SLOTS, cg = tid / M2F_SLOTS;
+  const int rr = p / PPR, pp = p % PPR;
+  const bool pvalid = p < 2 * PPR;
+  const bool masked = epi == EPI_MASK;
+  // tap -> (output parity phase, which of the four input pixels): x00 = (i,j), x01 = (i,j-1), x10 = (i-1,j), x11 = (i-1,j-1)
+  for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+    const int n = task / HB, i0 = 2 * (task % HB);
+    __syncthreads();
+    const int chunks = 3 * NCOL * 8;
+    for (int idx = tid; idx < chunks; idx += blockDim.x) {
+      const int c4 = idx & 7, pc = idx >> 3;
+      const int r = pc / NCOL, cs = pc - r * NCOL;
+      const int iy = i0 - 1 + r, ix = cs - 1;
+      const bool ok = iy >= 0 && iy < a.Hi && ix >= 0 && ix < a.Wi;
+      const float* src = a.in + ((((int64_t)n * a.Hi + (ok ? iy : 0)) * a.Wi) + (ok ? ix : 0)) * 32 + c4 * 4;
+      cp_async16_zfill(tile + (r * NCOL + cs) * 32 + ((c4 ^ ((cs >> 1) & 7)) << 2), src, ok);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    const int i = i0 + rr;
+    const bool live = pvalid && i < a.Hi;
+    float acc[2][4][CO];
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[px][ph][co] = 0.f;
+    if (live) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int c4 = 2 * cg + q;
+        float up[3][4], cur[3][4];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int cs = 2 * pp + k;
+          const int off = cs * 32 + ((c4 ^ ((cs >> 1) & 7)) << 2);
+          const float4 tu = *reinterpret_cast<const float4*>(tile + rr * NCOL * 32 + off);
+          const float4 tc = *reinterpret_cast<const float4*>(tile + (rr + 1) * NCOL * 32 + off);
+          up[k][0] = tu.x; up[k][1] = tu.y; up[k][2] = tu.z; up[k][3] = tu.w;
+          cur[k][0] = tc.x; cur[k][1] = tc.y; cur[k][2] = tc.z; cur[k][3] = tc.w;
+        }
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int kh = tap / 3, kw = tap % 3;
+          const int ph = (kh & 1) * 2 + (kw & 1);          // output parity phase this tap lands on
+          const bool use_up = kh == 2, use_left = kw == 2;  // input pixel (i - kh/2, j - kw/2)
+          const float4* wp = reinterpret_cast<const float4*>(ws + (tap * 8 + c4) * 4 * CO);
+          float wv[4 * CO];
+#pragma unroll
+          for (int u = 0; u < CO; ++u) { const float4 t = wp[u]; wv[4 * u] = t.x; wv[4 * u + 1] = t.y; wv[4 * u + 2] = t.z; wv[4 * u + 3] = t.w; }
+#pragma unroll
+          for (int px = 0; px < 2; ++px) {
+            const int k = px + (use_left ? 0 : 1);          // staged column of the input pixel, relative to 2*pp
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float xv = use_up ? up[k][c] : cur[k][c];
+#pragma unroll
+              for (int co = 0; co < CO; ++co) acc[px][ph][co] = fmaf(xv, wv[c * CO + co], acc[px][ph][co]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                               // tile reads done: reuse it as [4][M2F_SLOTS][2][4][CO]
+    float* red = tile;
+    if (live) {
+#pragma unroll
+      for (int px = 0; px < 2; ++px)
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph)
+#pragma unroll
+          for (int co = 0; co < CO; ++co) red[(((cg * M2F_SLOTS + p) * 2 + px) * 4 + ph) * CO + co] = acc[px][ph][co];
+    }
+    __syncthreads();
+    if (cg == 0 && live) {
+#pragma unroll
+      for (int pa = 0; pa < 2; ++pa) {               // output row 2i + pa: 4 consecutive pixels x CO channels
+        const int64_t o0 = (((int64_t)n * a.Ho + 2 * i + pa) * a.Wo + 4 * pp) * CO;
+        float mk[4][CO];
+        if (masked) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int co = 0; co < CO; ++co) mk[c][co] = (2 * pp + (c >> 1) < a.Wi) ? __ldg(a.mask + o0 + c * CO + co) : 0.f;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                // c = 2*px + pb
+          const int px = c >> 1, ph = pa * 2 + (c & 1);
+          if (2 * pp + px >= a.Wi) break;
+#pragma unroll
+          for (int co = 0; co < CO; ++co) {
+            float v = (a.bias && !masked) ? __ldg(a.bias + co) : 0.f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) v += red[(((g * M2F_SLOTS + p) * 2 + px) * 4 + ph) * CO + co];
+            a.out[o0 + c * CO + co] = m2f_epi(v, epi, masked ? mk[c][co] : 1.f);
+          }
+        }
+      }
+    }
+  }
+}
+
 #ifndef KCVAE_EMU
 #define KC_SET_SMEM(k, bytes) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))
 #else
@@ -614,6 +857,35 @@ static bool conv_forward_lane(int mode, int epi, const ConvArgs& a, cudaStream_t
     }
 #undef KC_LANE_CO
     return true;
+  }
+  if (a.Ci == 32 && (a.Co == 5 || a.Co == 8) && ((uintptr_t)a.in % 16 == 0)) {
+    if (mode == CONV_S2) {
+      const int PPR = cdiv(a.Wo, 2), NCOL = 4 * PPR + 1, HB = cdiv(a.Ho, 2);
+      const size_t smem = ((size_t)5 * NCOL * 32 + (size_t)9 * 32 * a.Co) * sizeof(float);
+      if (2 * PPR <= M2F_SLOTS && smem <= 110 * 1024 && (size_t)4 * M2F_SLOTS * 2 * a.Co <= (size_t)5 * NCOL * 32) {
+        const int n_tasks = a.B * HB;
+        const int grid = n_tasks < kNumSMs * 2 ? n_tasks : kNumSMs * 2;
+        ++g_launches;
+        if (a.Co == 5) { auto k = conv_s2_m2f_kernel<5>; KC_SET_SMEM(k, smem); KC_LAUNCH(k, grid, M2F_THREADS, smem, st, a, n_tasks, HB, NCOL, PPR, epi); }
+        else { auto k = conv_s2_m2f_kernel<8>; KC_SET_SMEM(k, smem); KC_LAUNCH(k, grid, M2F_THREADS, smem, st, a, n_tasks, HB, NCOL, PPR, epi); }
+        return true;
+      }
+    }
+    if (mode == CONVT_S2 && up2) {
+      const int PPR = cdiv(a.Wi, 2), NCOL = 2 * PPR + 1, HB = cdiv(a.Hi, 2);
+      size_t tile_floats = (size_t)3 * NCOL * 32;
+      const size_t fold = (size_t)4 * M2F_SLOTS * 2 * 4 * a.Co;
+      if (fold > tile_floats) tile_floats = fold;
+      const size_t smem = (tile_floats + (size_t)9 * 32 * a.Co) * sizeof(float);
+      if (2 * PPR <= M2F_SLOTS && smem <= 110 * 1024) {
+        const int n_tasks = a.B * HB;
+        const int grid = n_tasks < kNumSMs * 2 ? n_tasks : kNumSMs * 2;
+        ++g_launches;
+        if (a.Co == 5) { auto k = convT_s2_m2f_kernel<5>; KC_SET_SMEM(k, smem); KC_LAUNCH(k, grid, M2F_THREADS, smem, st, a, n_tasks, HB, NCOL, PPR, epi, (int)tile_floats); }
+        else { auto k = convT_s2_m2f_kernel<8>; KC_SET_SMEM(k, smem); KC_LAUNCH(k, grid, M2F_THREADS, smem, st, a, n_tasks, HB, NCOL, PPR, epi, (int)tile_floats); }
+        return true;
+      }
+    }
   }
   return false;
 }

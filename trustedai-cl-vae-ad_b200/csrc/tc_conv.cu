@@ -36,6 +36,7 @@ constexpr int kStages = 2;
 constexpr int kThreads = 192;
 constexpr int kSubD = 4;                   // tc_out_dgrad: epilogue warps per TMEM lane group
 constexpr int kThreadsD = 64 + 4 * kSubD * 32;
+constexpr int kThreadsT = 64 + 8 * 32 + 4 * 32;   // fused tail: TMA, MMA, 8 phase-A epilogue warps, 4 phase-B epilogue warps
 constexpr int kThreadsE = 320;            // kernels with a per-tile epilogue: 2 + 8 warps (two epilogue warps per TMEM lane group)
 static_assert(TR * PW == MT * 128, "tile must be a whole number of M=128 tiles");
 
@@ -1131,7 +1132,7 @@ struct TailParams {
   int* error_flag;
 };
 
-__global__ void __launch_bounds__(kThreadsE, 1)
+__global__ void __launch_bounds__(kThreadsT, 1)
 tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
   constexpr uint32_t CH = NPIX * 16;
   constexpr uint32_t A4_BYTES = 4 * CH;
@@ -1145,13 +1146,10 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
   unsigned char* s_wB = s_wA + WA_BYTES;
   __shared__ uint64_t a3_full[2], a3_empty[2], Afull[2], Aempty[2], a4_ready[2], a4_free[2], Bfull[2], Bempty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_biasA[32], s_biasB[NPAD];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < (int)(WA_BYTES / 16); i += kThreadsE) reinterpret_cast<uint4*>(s_wA)[i] = reinterpret_cast<const uint4*>(p.wimgA)[i];
-  for (int i = threadIdx.x; i < (int)(WB_BYTES / 16); i += kThreadsE) reinterpret_cast<uint4*>(s_wB)[i] = reinterpret_cast<const uint4*>(p.wimgB)[i];
-  if (threadIdx.x < 32) s_biasA[threadIdx.x] = p.biasA[threadIdx.x];
-  if (threadIdx.x < NPAD) s_biasB[threadIdx.x] = (int)threadIdx.x < p.Cout ? p.biasB[threadIdx.x] : 0.f;
+  for (int i = threadIdx.x; i < (int)(WA_BYTES / 16); i += kThreadsT) reinterpret_cast<uint4*>(s_wA)[i] = reinterpret_cast<const uint4*>(p.wimgA)[i];
+  for (int i = threadIdx.x; i < (int)(WB_BYTES / 16); i += kThreadsT) reinterpret_cast<uint4*>(s_wB)[i] = reinterpret_cast<const uint4*>(p.wimgB)[i];
   if (threadIdx.x < 32) {   // pads behind the tiles: only ever read into discarded rows/columns
     const int s = (threadIdx.x >> 3) & 1, j = threadIdx.x & 7;
     if (threadIdx.x < 16) reinterpret_cast<uint4*>(s_a4 + s * A4_STAGE + A4_BYTES)[j] = make_uint4(0, 0, 0, 0);
@@ -1161,8 +1159,8 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
   if (threadIdx.x == 32) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a3_full[s], 1); mbar_init(&a3_empty[s], 1);
-      mbar_init(&Afull[s], 1);   mbar_init(&Aempty[s], 4);
-      mbar_init(&a4_ready[s], 4); mbar_init(&a4_free[s], 1);
+      mbar_init(&Afull[s], 1);   mbar_init(&Aempty[s], 8);
+      mbar_init(&a4_ready[s], 8); mbar_init(&a4_free[s], 1);
       mbar_init(&Bfull[s], 1);   mbar_init(&Bempty[s], 4);
     }
     fence_mbar_init();
@@ -1262,11 +1260,14 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
     }
   } else {
     // ================================ epilogue warps ========================================
-    // Two independent groups of four warps (one per TMEM lane group each): warps 2..5 turn the
-    // phase-A accumulators into the next shared-memory tile, warps 6..9 drain phase B.  Neither
-    // waits for the other, so both overlap the phase-B MMAs of the tile in flight.
+    // Two independent groups: warps 2..9 (two per TMEM lane group, one per output-row parity) turn
+    // the phase-A accumulators into the next shared-memory tile, warps 10..13 drain phase B.
+    // Neither waits for the other, so both overlap the phase-B MMAs of the tile in flight.  Biases
+    // live in registers: with one or two warps per scheduler every shared-memory round trip in the
+    // per-element chain is exposed latency.
     const int lg = warp & 3;
-    const bool groupA = warp < 6;
+    const bool groupA = warp < 10;
+    const int halfA = (warp - 2) >> 2;
     bool ok = true;
     auto tile_origin = [&](int t, int& n, int& ty0, int& tx0) {
       n = t / (p.tiles_y * p.tiles_x);
@@ -1275,6 +1276,9 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
     };
     if (groupA) {
       // ---- epilogue A: low-res phases -> bf16 halo tile of a_last in shared memory
+      float bA[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) bA[c] = __ldg(p.biasA + c);
       int ma = 0, it = 0;
       for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
         const int s = it & 1;
@@ -1292,12 +1296,10 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
           const int r = q / PA, c = q % PA;
           const bool live = r < LR_ROWS && c < LR_COLS;
 #pragma unroll 1
-          for (int phs = 0; phs < 4; ++phs) {
-            const int pa = phs >> 1, pb = phs & 1;
+          for (int pb = 0; pb < 2; ++pb) {
+            const int pa = halfA, phs = halfA * 2 + pb;
             float v[32];
-            const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * 128 + phs * 32);
-            tmem_ld16(ta, v);
-            tmem_ld16(ta + 16, v + 16);
+            tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(slot * 128 + phs * 32), v);
             const int hr = 2 * r + pa - 1, hc = 2 * c + pb - 1;
             if (live && hr >= 0 && hr < PR && hc >= 0 && hc < PW) {
               const int Y = ty0 - 1 + hr, X = tx0 - 1 + hc;
@@ -1310,8 +1312,8 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
                 uint32_t w4[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float y0 = inside ? fmaxf(v[g * 8 + 2 * e] + s_biasA[g * 8 + 2 * e], 0.f) : 0.f;
-                  const float y1 = inside ? fmaxf(v[g * 8 + 2 * e + 1] + s_biasA[g * 8 + 2 * e + 1], 0.f) : 0.f;
+                  const float y0 = inside ? fmaxf(v[g * 8 + 2 * e] + bA[g * 8 + 2 * e], 0.f) : 0.f;
+                  const float y1 = inside ? fmaxf(v[g * 8 + 2 * e + 1] + bA[g * 8 + 2 * e + 1], 0.f) : 0.f;
                   __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
                   w4[e] = *reinterpret_cast<uint32_t*>(&b2);
                 }
@@ -1333,6 +1335,9 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
       }
     } else {
       // ---- epilogue B: bias, sigmoid, reconstruction error, score partials
+      float bB[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) bB[c] = c < p.Cout ? __ldg(p.biasB + c) : 0.f;
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int s = it & 1;
@@ -1374,7 +1379,7 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
 #pragma unroll
             for (int co = 0; co < 8; ++co) {
               if (co < p.Cout) {
-                float y = v[co] + s_biasB[co];
+                float y = v[co] + bB[co];
                 if (p.apply_sigmoid) y = 1.0f / (1.0f + __expf(-y));
                 if (p.xhat) p.xhat[pix * p.Cout + co] = y;
                 const float d = xc[co] - y;
@@ -1714,7 +1719,7 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
   ProfScope prof_("tc_tail_fused", st);
   ++g_launches;
   cudaFuncSetAttribute(tc_tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tc_tail_fused_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
+  tc_tail_fused_kernel<<<grid, kThreadsT, smem, st>>>(tmap, p);
   if (score) {
     ++g_launches;
     tail_score_finish_kernel<<<B, 128, 0, st>>>(score_partial, p.tiles_y * p.tiles_x * 4, score, err_minmax);
