@@ -111,7 +111,9 @@ def check_backend(backend, path, precision=None):
     keys = list(as_dict(g, "loss_train").keys())
     for s in range(3):
         ds = m.train_step(x, eps=g["step_eps"][s])
-        metrics_close(ds, dict(zip(keys, g["step_loss"][s])), max(r_loss, 5e-4), 2e-6, a_rec)
+        # from the second step on the two sides no longer hold identical weights (bf16 gradients move them by
+        # O(lr * 2^-9)), and |target - kurtosis| is a difference of nearly equal numbers: absolute slack there
+        metrics_close(ds, dict(zip(keys, g["step_loss"][s])), 5e-3 if tc else 5e-4, 3e-4 if tc else 2e-6, a_rec)
     lr = float(cfg["training"]["learning_rate"])
     for i, (w, rw) in enumerate(zip(m.get_weights(), w_after)):
         assert np.mean(np.abs(w - rw)) < (0.1 if tc else 0.02) * lr, f"variable {i} after 3 Adam steps"

@@ -665,33 +665,30 @@ __global__ void __launch_bounds__(M2F_THREADS) conv_s2_m2f_kernel(ConvArgs a, in
         }
       }
     }
-    __syncthreads();                               // tile reads done: reuse it as [4][M2F_SLOTS][2][CO]
+    __syncthreads();                               // tile reads done: reuse it as [4 groups][2*CO values][M2F_SLOTS]
     float* red = tile;
-    if (live) {
+    constexpr int NV = 2 * CO;
 #pragma unroll
-      for (int px = 0; px < 2; ++px)
+    for (int px = 0; px < 2; ++px)
 #pragma unroll
-        for (int co = 0; co < CO; ++co) red[((cg * M2F_SLOTS + p) * 2 + px) * CO + co] = acc[px][co];
-    }
+      for (int co = 0; co < CO; ++co) red[(cg * NV + px * CO + co) * M2F_SLOTS + p] = acc[px][co];
     __syncthreads();
-    if (cg == 0 && live) {
-      float mk[2][CO];
+    if (live) {   // the four groups share the final summation: group cg folds values k = cg, cg+4, ...
       const int64_t o0 = (((int64_t)n * a.Ho + oy) * a.Wo + 2 * pp) * CO;
-      if (masked) {
+      float mk[(NV + 3) / 4];
 #pragma unroll
-        for (int px = 0; px < 2; ++px)
-#pragma unroll
-          for (int co = 0; co < CO; ++co) mk[px][co] = (2 * pp + px < a.Wo) ? __ldg(a.mask + o0 + px * CO + co) : 0.f;
+      for (int u = 0; u < (NV + 3) / 4; ++u) {
+        const int k = cg + 4 * u;
+        mk[u] = (masked && k < NV && 2 * pp + k / CO < a.Wo) ? __ldg(a.mask + o0 + k) : 1.f;
       }
 #pragma unroll
-      for (int px = 0; px < 2; ++px) {
-        if (2 * pp + px >= a.Wo) break;
+      for (int u = 0; u < (NV + 3) / 4; ++u) {
+        const int k = cg + 4 * u;
+        if (k < NV && 2 * pp + k / CO < a.Wo) {
+          float v = (a.bias && !masked) ? __ldg(a.bias + k % CO) : 0.f;
 #pragma unroll
-        for (int co = 0; co < CO; ++co) {
-          float v = (a.bias && !masked) ? __ldg(a.bias + co) : 0.f;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) v += red[((g * M2F_SLOTS + p) * 2 + px) * CO + co];
-          a.out[o0 + px * CO + co] = m2f_epi(v, epi, masked ? mk[px][co] : 1.f);
+          for (int g = 0; g < 4; ++g) v += red[(g * NV + k) * M2F_SLOTS + p];
+          a.out[o0 + k] = m2f_epi(v, epi, mk[u]);
         }
       }
     }
@@ -773,39 +770,38 @@ __global__ void __launch_bounds__(M2F_THREADS) convT_s2_m2f_kernel(ConvArgs a, i
         }
       }
     }
-    __syncthreads();                               // tile reads done: reuse it as [4][M2F_SLOTS][2][4][CO]
+    __syncthreads();                               // tile reads done: reuse it as [4 groups][8*CO values][M2F_SLOTS]
     float* red = tile;
-    if (live) {
+    constexpr int NV = 8 * CO;                     // value k = (px*4 + ph)*CO + co
 #pragma unroll
-      for (int px = 0; px < 2; ++px)
+    for (int px = 0; px < 2; ++px)
 #pragma unroll
-        for (int ph = 0; ph < 4; ++ph)
+      for (int ph = 0; ph < 4; ++ph)
 #pragma unroll
-          for (int co = 0; co < CO; ++co) red[(((cg * M2F_SLOTS + p) * 2 + px) * 4 + ph) * CO + co] = acc[px][ph][co];
-    }
+        for (int co = 0; co < CO; ++co) red[(cg * NV + (px * 4 + ph) * CO + co) * M2F_SLOTS + p] = acc[px][ph][co];
     __syncthreads();
-    if (cg == 0 && live) {
+    if (live) {   // group cg folds the output pixel-phases (px, ph) with (px*4+ph) % 4 == cg
+      int64_t oo[2];
+      bool ok2[2];
+      float mk[2][CO];
 #pragma unroll
-      for (int pa = 0; pa < 2; ++pa) {               // output row 2i + pa: 4 consecutive pixels x CO channels
-        const int64_t o0 = (((int64_t)n * a.Ho + 2 * i + pa) * a.Wo + 4 * pp) * CO;
-        float mk[4][CO];
-        if (masked) {
+      for (int u = 0; u < 2; ++u) {
+        const int pq = cg + 4 * u, px = pq >> 2, ph = pq & 3;
+        ok2[u] = 2 * pp + px < a.Wi;
+        oo[u] = (((int64_t)n * a.Ho + 2 * i + (ph >> 1)) * a.Wo + 2 * (2 * pp + px) + (ph & 1)) * CO;
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+        for (int co = 0; co < CO; ++co) mk[u][co] = (masked && ok2[u]) ? __ldg(a.mask + oo[u] + co) : 1.f;
+      }
 #pragma unroll
-            for (int co = 0; co < CO; ++co) mk[c][co] = (2 * pp + (c >> 1) < a.Wi) ? __ldg(a.mask + o0 + c * CO + co) : 0.f;
-        }
+      for (int u = 0; u < 2; ++u) {
+        if (!ok2[u]) continue;
+        const int pq = cg + 4 * u;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {                // c = 2*px + pb
-          const int px = c >> 1, ph = pa * 2 + (c & 1);
-          if (2 * pp + px >= a.Wi) break;
+        for (int co = 0; co < CO; ++co) {
+          float v = (a.bias && !masked) ? __ldg(a.bias + co) : 0.f;
 #pragma unroll
-          for (int co = 0; co < CO; ++co) {
-            float v = (a.bias && !masked) ? __ldg(a.bias + co) : 0.f;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) v += red[(((g * M2F_SLOTS + p) * 2 + px) * 4 + ph) * CO + co];
-            a.out[o0 + c * CO + co] = m2f_epi(v, epi, masked ? mk[c][co] : 1.f);
-          }
+          for (int g = 0; g < 4; ++g) v += red[(g * NV + pq * CO + co) * M2F_SLOTS + p];
+          a.out[oo[u] + co] = m2f_epi(v, epi, mk[u][co]);
         }
       }
     }

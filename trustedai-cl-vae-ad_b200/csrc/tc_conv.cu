@@ -542,13 +542,21 @@ tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutWgradParams p) 
       const int rem = t % (p.tiles_y * p.tiles_x);
       const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
       uint4* dst = reinterpret_cast<uint4*>(smem + s * STAGE);
-      for (int u = lt; u < DLROWS * PW; u += 128) {
-        const int rho = u / PW - 2, c = u % PW;
-        const int y = ty * TR + rho, x = tx * TW + c;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (rho >= 0 && rho < TR && c < TW && y < p.H && x < p.W)
-          v = __ldg(reinterpret_cast<const uint4*>(p.dl8) + ((int64_t)n * p.H + y) * p.W + x);
-        dst[u] = v;
+      {  // all loads of the plane are issued before the first store: one memory round trip per tile, not nine
+        constexpr int NU = DLROWS * PW / 128;
+        static_assert(DLROWS * PW % 128 == 0, "dl plane must be a whole number of 128-thread passes");
+        uint4 vv[NU];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) {
+          const int u = lt + k * 128;
+          const int rho = u / PW - 2, c = u % PW;
+          const int y = ty * TR + rho, x = tx * TW + c;
+          vv[k] = make_uint4(0, 0, 0, 0);
+          if (rho >= 0 && rho < TR && c < TW && y < p.H && x < p.W)
+            vv[k] = __ldg(reinterpret_cast<const uint4*>(p.dl8) + ((int64_t)n * p.H + y) * p.W + x);
+        }
+#pragma unroll
+        for (int k = 0; k < NU; ++k) dst[lt + k * 128] = vv[k];
       }
       fence_async_smem();       // generic-proxy writes -> visible to the tensor core
       __syncwarp();
@@ -917,20 +925,31 @@ tc_convT_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
       const int n = t / (p.tiles_y * p.tiles_x);
       const int rem = t % (p.tiles_y * p.tiles_x);
       const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      // the ReLU mask of both M-tiles is requested before the accumulator wait (and before any store:
+      // g_prev and mask may alias as far as the compiler knows, which would serialise load/store pairs)
+      float mk[MTD][8];
+      int64_t pixs[MTD];
+      bool lives[MTD];
+#pragma unroll
+      for (int mt = 0; mt < MTD; ++mt) {
+        const int q = mt * 128 + lg * 32 + lane;
+        const int r = q / PW, c = q % PW;
+        const int i = ty * TRD + r, j = tx * TW + c;
+        lives[mt] = c < TW && i < p.h && j < p.w;
+        pixs[mt] = ((int64_t)n * p.h + i) * p.w + j;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) mk[mt][ci] = (lives[mt] && ci < p.Cin) ? __ldg(p.mask + pixs[mt] * p.Cin + ci) : 0.f;
+      }
       if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; break; }
       fence_after_sync();
 #pragma unroll
       for (int mt = 0; mt < MTD; ++mt) {
         float v[8];
         tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MTD * 16 + mt * 16), v);
-        const int q = mt * 128 + lg * 32 + lane;
-        const int r = q / PW, c = q % PW;
-        const int i = ty * TRD + r, j = tx * TW + c;
-        if (c < TW && i < p.h && j < p.w) {
-          const int64_t pix = ((int64_t)n * p.h + i) * p.w + j;
+        if (lives[mt]) {
 #pragma unroll
           for (int ci = 0; ci < 8; ++ci)
-            if (ci < p.Cin) p.g_prev[pix * p.Cin + ci] = __ldg(p.mask + pix * p.Cin + ci) > 0.f ? v[ci] : 0.f;
+            if (ci < p.Cin) p.g_prev[pixs[mt] * p.Cin + ci] = mk[mt][ci] > 0.f ? v[ci] : 0.f;
         }
       }
       fence_before_sync();
@@ -1051,13 +1070,21 @@ tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
       const int rem = t % (p.tiles_y * p.tiles_x);
       const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
       uint4* dst = reinterpret_cast<uint4*>(smem + s * STAGE);
-      for (int u = lt; u < APROWS * PW; u += 128) {
-        const int rho = u / PW - 1, c = u % PW;
-        const int i = ty * TRD + rho, j = tx * TW + c;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (rho >= 0 && rho < TRD && c < TW && i < p.h && j < p.w)
-          v = __ldg(reinterpret_cast<const uint4*>(p.a_prev8) + ((int64_t)n * p.h + i) * p.w + j);
-        dst[u] = v;
+      {  // loads first, stores after (see tc_out_wgrad_kernel)
+        constexpr int NU = (APROWS * PW + 127) / 128;
+        uint4 vv[NU];
+#pragma unroll
+        for (int k = 0; k < NU; ++k) {
+          const int u = lt + k * 128;
+          const int rho = u / PW - 1, c = u % PW;
+          const int i = ty * TRD + rho, j = tx * TW + c;
+          vv[k] = make_uint4(0, 0, 0, 0);
+          if (u < APROWS * PW && rho >= 0 && rho < TRD && c < TW && i < p.h && j < p.w)
+            vv[k] = __ldg(reinterpret_cast<const uint4*>(p.a_prev8) + ((int64_t)n * p.h + i) * p.w + j);
+        }
+#pragma unroll
+        for (int k = 0; k < NU; ++k)
+          if (lt + k * 128 < APROWS * PW) dst[lt + k * 128] = vv[k];
       }
       fence_async_smem();
       __syncwarp();
