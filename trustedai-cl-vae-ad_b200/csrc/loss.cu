@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.P;
        p += (int64_t)gridDim.x * blockDim.x) {
     float se = 0, xhx = 0, xh = 0, ex = 0, gsum = 0;
-    double sx = 0, sxx = 0, sh = 0, shh = 0;
+    // per-position batch moments about the fixed pivot 0.5 (frames and reconstructions live in [0,1]):
+    // fp32 sums of d and d^2 lose nothing to cancellation, and pivoted sums of different ranks still add
+    float sx = 0, sxx = 0, sh = 0, shh = 0;
     const int64_t pix8 = (p / a.C) * 8 + (p % a.C);   // slot inside one frame of the 8-channel bf16 layout
     const int64_t frame8 = (a.P / a.C) * 8;
     // four frames per trip: the eight loads are issued before any dependent store
@@ -55,8 +57,9 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
           ex += expf(xv);
         }
         if (want_std) {
-          sx += xv; sxx += (double)xv * xv;
-          sh += hv; shh += (double)hv * hv;
+          const float dx = xv - 0.5f, dh = hv - 0.5f;
+          sx += dx; sxx = fmaf(dx, dx, sxx);
+          sh += dh; shh = fmaf(dh, dh, shh);
         }
         if (DL || DL8) {
           const float gl = a.grad_scale * (hv - xv) * hv * (1.0f - hv);
@@ -81,8 +84,8 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
       a.pos_sums[2 * a.P + p] = sh; a.pos_sums[3 * a.P + p] = shh;
     } else if (a.std_acc) {
       const double inv = 1.0 / a.B;
-      const double vx = fmax(sxx * inv - (sx * inv) * (sx * inv), 0.0);
-      const double vh = fmax(shh * inv - (sh * inv) * (sh * inv), 0.0);
+      const double vx = fmax((double)sxx * inv - ((double)sx * inv) * ((double)sx * inv), 0.0);
+      const double vh = fmax((double)shh * inv - ((double)sh * inv) * ((double)sh * inv), 0.0);
       const double dd = sqrt(vx) - sqrt(vh);
       t_std += dd * dd;
     }
