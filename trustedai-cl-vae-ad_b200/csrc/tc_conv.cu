@@ -234,7 +234,8 @@ __global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __
 // distance between the two taps' pixels.  M=128 pixels, N=32 (Cin of the forward layer).
 struct OutDgradParams {
   const __nv_bfloat16* wimg;   // [5 pairs][2][NPAD_D][8]
-  const __nv_bfloat16* mask;   // forward activation a (bf16 NHWC, Cin channels)
+  const __nv_bfloat16* mask;   // forward activation a (chunk-planar bf16, Cin channels)
+  const uint32_t* relu_bits;   // [B,H,W] bit c = (a[.., c] > 0); when set it replaces the reads of `mask`
   float* g_out;                // [B,H,W,Cin] fp32 (or nullptr)
   __nv_bfloat16* g_s2d;        // [B,H/2,W/2,4,Cin] bf16 space-to-depth (or nullptr): parity (y&1)*2+(x&1)
   float* chan_partial;         // [grid*4][32] per-warp channel sums of g (bias gradient of the producer) or nullptr
@@ -322,10 +323,12 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
     }
   } else {
     // ============ epilogue: kSubD warps per TMEM lane group, each takes every kSubD-th M-tile ============
-    // The ReLU mask (the forward activation) does not depend on the MMAs: its four 16-byte units
-    // are requested BEFORE the accumulator wait, so the loads overlap the tensor-core work.
+    // The ReLU mask does not depend on the MMAs.  With the fused forward it is one 32-bit word per
+    // pixel (relu_bits); the words of ALL M-tiles this warp owns in the tile are requested before the
+    // accumulator wait.  Without it the four 16-byte units of the activation are read instead.
     const int lg = warp & 3;
     const int sub = (warp - 2) >> 2;
+    constexpr int NMT = (MT + kSubD - 1) / kSubD;      // M-tiles per warp and tile
     float csum[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) csum[c] = 0.f;
@@ -336,25 +339,41 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       const int n = t / (p.tiles_y * p.tiles_x);
       const int rem = t % (p.tiles_y * p.tiles_x);
       const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      uint32_t bits[NMT];
+      if (p.relu_bits) {
+#pragma unroll
+        for (int k = 0; k < NMT; ++k) {
+          const int mt = sub + k * kSubD;
+          const int q = mt * 128 + lg * 32 + lane;
+          const int r = q / PW, c = q % PW;
+          const int oy = ty * TR + r, ox = tx * TW + c;
+          const bool live = mt < MT && c < TW && oy < p.H && ox < p.W;
+          bits[k] = live ? __ldg(p.relu_bits + ((int64_t)n * p.H + oy) * p.W + ox) : 0u;
+        }
+      }
       bool waited = false;
-#pragma unroll 1
-      for (int mt = sub; mt < MT; mt += kSubD) {
+#pragma unroll
+      for (int k = 0; k < NMT; ++k) {
+        const int mt = sub + k * kSubD;
+        if (mt >= MT) break;
         const int q = mt * 128 + lg * 32 + lane;
         const int r = q / PW, c = q % PW;
         const int oy = ty * TR + r, ox = tx * TW + c;
         const bool live = c < TW && oy < p.H && ox < p.W;
         const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
         uint4 m[4];
+        if (!p.relu_bits) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) m[g] = make_uint4(0, 0, 0, 0);
-        if (live) {
-          // chunk-planar activation: plane (n, g) holds channels 8g..8g+7 of every pixel as one 16-byte unit
-          const int KCm = p.Cin >> 3;
-          const int64_t plane = (int64_t)p.H * p.W;
-          const uint4* mk = reinterpret_cast<const uint4*>(p.mask) + (int64_t)n * KCm * plane + (int64_t)oy * p.W + ox;
+          for (int g = 0; g < 4; ++g) m[g] = make_uint4(0, 0, 0, 0);
+          if (live) {
+            // chunk-planar activation: plane (n, g) holds channels 8g..8g+7 of every pixel as one 16-byte unit
+            const int KCm = p.Cin >> 3;
+            const int64_t plane = (int64_t)p.H * p.W;
+            const uint4* mk = reinterpret_cast<const uint4*>(p.mask) + (int64_t)n * KCm * plane + (int64_t)oy * p.W + ox;
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            if (g < KCm) m[g] = __ldg(mk + g * plane);
+            for (int g = 0; g < 4; ++g)
+              if (g < KCm) m[g] = __ldg(mk + g * plane);
+          }
         }
         if (!waited) {
           if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; }
@@ -375,13 +394,18 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
 #pragma unroll
           for (int gg = 0; gg < 2; ++gg) {
             const int g = hh * 2 + gg;
-            const uint32_t mw[4] = {m[g].x, m[g].y, m[g].z, m[g].w};
             float y[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero (dead lanes: mask 0 -> y = 0)
-              const uint32_t h16 = (mw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;
-              const bool pos = (h16 & 0x8000u) == 0 && (h16 & 0x7FFFu) != 0;
+              bool pos;
+              if (p.relu_bits) {
+                pos = (bits[k] >> (g * 8 + j)) & 1u;
+              } else {
+                // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero (dead lanes: mask 0 -> y = 0)
+                const uint32_t mw = j < 2 ? m[g].x : (j < 4 ? m[g].y : (j < 6 ? m[g].z : m[g].w));
+                const uint32_t h16 = (mw >> ((j & 1) * 16)) & 0xFFFFu;
+                pos = (h16 & 0x8000u) == 0 && (h16 & 0x7FFFu) != 0;
+              }
               y[j] = pos ? v[gg * 8 + j] : 0.f;
               csum[g * 8 + j] += y[j];
             }
@@ -403,7 +427,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
           }
         }
       }
-      if (!waited) {   // kSubD > MT never happens, but keep the barrier protocol whole
+      if (!waited) {
         if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; }
       }
       fence_before_sync();
@@ -614,9 +638,26 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* partial,
     out[e] = v;
   }
 }
+// few entries, many partials (channel sums): one block per entry, 256 threads stride over the partials,
+// then a fixed shared-memory tree (deterministic)
+__global__ void __launch_bounds__(256) sum_partials_wide_kernel(const float* partial, int nparts, int E, float* out) {
+  __shared__ float red[256];
+  const int e = blockIdx.x;
+  float t = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 256) t += __ldg(partial + (int64_t)i * E + e);
+  red[threadIdx.x] = t;
+  __syncthreads();
+#pragma unroll
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[e] = red[0];
+}
 static void sum_partials(const float* partial, int nparts, int E, float* out, cudaStream_t st) {
   ++g_launches;
-  sum_partials_kernel<<<cdiv(E, 256 / SP_SLICES), 256, 0, st>>>(partial, nparts, E, out);
+  if (E <= 64 && nparts >= 512) sum_partials_wide_kernel<<<E, 256, 0, st>>>(partial, nparts, E, out);
+  else sum_partials_kernel<<<cdiv(E, 256 / SP_SLICES), 256, 0, st>>>(partial, nparts, E, out);
 }
 
 // ============================================================================================
@@ -1151,6 +1192,7 @@ struct TailParams {
   const float* x;              // [B,H,W,Cout] fp32 (needed for err / score) or nullptr
   float* xhat;                 // [B,H,W,Cout] or nullptr
   uint4* a_last;               // chunk-planar bf16 [B][4][H][W][8] copy of the intermediate activation (training) or nullptr
+  uint32_t* relu_bits;         // [B,H,W]: bit c = (a_last[.., c] > 0), the ReLU mask the output-layer dgrad needs (training) or nullptr
   float* err;                  // [B,H,W] or nullptr
   float* score_partial;        // [num_tiles][4][3] (sum, min, max of err per epilogue warp) or nullptr
   int B, H, W, Cout;
@@ -1349,6 +1391,12 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
                 // training: the backward needs this activation; every tile stores its own 32x30 interior
                 if (keep) gdst[g * ((int64_t)p.H * p.W)] = u;
               }
+              if (keep && p.relu_bits) {   // one 32-bit word per pixel instead of a 64-byte re-read in the dgrad
+                uint32_t bits = 0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) bits |= (v[c] + bA[c] > 0.f ? 1u : 0u) << c;
+                p.relu_bits[((int64_t)n * p.H + Y) * p.W + X] = bits;
+              }
             }
           }
           fence_before_sync();
@@ -1536,8 +1584,9 @@ void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img, cudaStr
   tc_prep_dgrad_weights_kernel<<<4, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
 }
 
-int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, float* g_out, void* g_s2d_bf16,
-                 float* chan_sum, float* chan_partial, int B, int H, int W, int Cin, int* error_flag, cudaStream_t st) {
+int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, const uint32_t* relu_bits, float* g_out,
+                 void* g_s2d_bf16, float* chan_sum, float* chan_partial, int B, int H, int W, int Cin, int* error_flag,
+                 cudaStream_t st) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
   CUtensorMap tmap;
@@ -1552,6 +1601,7 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   OutDgradParams p{};
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.mask = reinterpret_cast<const __nv_bfloat16*>(mask_bf16);
+  p.relu_bits = relu_bits;
   p.g_out = g_out; p.g_s2d = reinterpret_cast<__nv_bfloat16*>(g_s2d_bf16); p.B = B; p.H = H; p.W = W; p.Cin = Cin;
   p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
   p.num_tiles = B * p.tiles_y * p.tiles_x;
@@ -1715,8 +1765,9 @@ size_t tc_tail_score_partial_floats(int B, int H, int W) { return (size_t)B * cd
 // fused Conv2DTranspose s2 -> Conv2DTranspose s1 (+ sigmoid, error map, per-frame score).
 // in8: bf16 [B,H/2,W/2,8]; any of xhat / err / score may be nullptr (x is required for err / score).
 int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, const float* biasA, const float* biasB,
-                  const float* x, float* xhat, void* a_last_planar, float* err, float* score, float* err_minmax,
-                  float* score_partial, int B, int H, int W, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st) {
+                  const float* x, float* xhat, void* a_last_planar, uint32_t* relu_bits, float* err, float* score,
+                  float* err_minmax, float* score_partial, int B, int H, int W, int Cout, int apply_sigmoid, int* error_flag,
+                  cudaStream_t st) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
   const int h = H / 2, w = W / 2;
@@ -1734,6 +1785,7 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
   p.wimgB = reinterpret_cast<const __nv_bfloat16*>(wimgB);
   p.biasA = biasA; p.biasB = biasB; p.x = x; p.xhat = xhat; p.err = err;
   p.a_last = reinterpret_cast<uint4*>(a_last_planar);
+  p.relu_bits = a_last_planar ? relu_bits : nullptr;
   p.score_partial = score ? score_partial : nullptr;
   p.B = B; p.H = H; p.W = W; p.Cout = Cout;
   p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
