@@ -118,6 +118,8 @@ struct kcvae_model {
   float *minmax = nullptr, *metrics_dev = nullptr;
   // tensor-core path (precision == BF16_TC): bf16 copy of the last decoder activation, UMMA
   // weight image of the output layer, device-side error flag of the bounded barrier waits
+  uint32_t* relu_bits = nullptr;  // [B,H,W] ReLU mask of the last activation, one bit per channel (written by the fused tail)
+  bool relu_bits_valid = false;
   bool fuse_train_tail = false;  // training forward: fused tail that also stores the activation for the backward
   bool tc_failed = false;        // a tensor-core launcher could not run (tensor map encode): the step is invalid
   bool use_tc_out = false, use_tc_dgrad = false, use_tc_convT = false, use_tc_convT_bwd = false;
@@ -293,6 +295,7 @@ int ensure_fwd(kcvae_model* h, int B) {
     unsigned short* tmp = reinterpret_cast<unsigned short*>(h->a_last_bf16);
     KC_TRY(dalloc(h, &tmp, (size_t)B * h->dh[L] * h->dw[L] * h->dc[L]));
     h->a_last_bf16 = tmp;
+    KC_TRY(dalloc(h, &h->relu_bits, (size_t)B * h->dh[L] * h->dw[L]));
     if (h->use_tc_convT) {
       unsigned short* t8 = reinterpret_cast<unsigned short*>(h->a_prev8);
       KC_TRY(dalloc(h, &t8, (size_t)B * h->dh[L - 1] * h->dw[L - 1] * 8));
@@ -415,6 +418,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
                  bool keep_last = true, TailOut* tail = nullptr) {
   const int L = h->L;
   bool last_is_bf16 = false;   // the last activation was produced directly in bf16 by tc_convT_fwd
+  h->relu_bits_valid = false;
   GemmArgs ga{};
   ga.A = z; ga.a_sm = h->latent; ga.a_sk = 1;
   ga.Bm = h->wp(h->vi_dec_dense()); ga.b_sk = h->dec_units; ga.b_sn = 1;
@@ -444,10 +448,12 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
         g_tag = "dec.tail";
         const bool want_score = tail && tail->x && (tail->err || tail->score);
         if (tc_tail_fused(h->a_prev8, h->wimg_convT, h->wimg_out, a.bias, h->wp(vo + 1), want_score ? tail->x : nullptr, out,
-                          keep_last ? h->a_last_bf16 : nullptr, want_score ? tail->err : nullptr, want_score ? tail->score : nullptr,
+                          keep_last ? h->a_last_bf16 : nullptr, h->relu_bits, want_score ? tail->err : nullptr,
+                          want_score ? tail->score : nullptr,
                           want_score ? tail->err_minmax : nullptr, h->partial, B, h->dh[L], h->dw[L], h->C, apply_sigmoid,
                           h->tc_error, st) == 0) {
           if (want_score) tail->done = true;
+          h->relu_bits_valid = keep_last && h->relu_bits;
           return;
         }
         g_tag = "dec.convT_last.fwd";
@@ -608,7 +614,8 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       // with the tensor-core Conv2DTranspose backward the gradient never exists in fp32: it is
       // written as bf16 space-to-depth and its channel sums (= that layer's bias gradient) come
       // out of the same epilogue
-      done = tc_out_dgrad(h->dl8, h->wimg_dgrad, h->a_last_bf16, s2d ? nullptr : h->g_act_d[L], s2d ? h->g_s2d : nullptr,
+      done = tc_out_dgrad(h->dl8, h->wimg_dgrad, h->a_last_bf16, h->relu_bits_valid ? h->relu_bits : nullptr,
+                          s2d ? nullptr : h->g_act_d[L], s2d ? h->g_s2d : nullptr,
                           s2d ? h->gp(h->vi_dec_convT(L - 1) + 1) : nullptr, h->partial, B, h->H, h->W, h->dc[L],
                           h->tc_error, st) == 0;
       tail_s2d = done && s2d;
@@ -877,6 +884,7 @@ int kcvae_destroy(kcvae_handle h) {
                  h->metrics_dev};
   for (float* p : fl) if (p) cudaFree(p);
   if (h->a_last_bf16) cudaFree(h->a_last_bf16);
+  if (h->relu_bits) cudaFree(h->relu_bits);
   if (h->wimg_out) cudaFree(h->wimg_out);
   if (h->wimg_dgrad) cudaFree(h->wimg_dgrad);
   if (h->wimg_convT) cudaFree(h->wimg_convT);

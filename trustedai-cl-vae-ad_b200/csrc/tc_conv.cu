@@ -245,6 +245,7 @@ struct OutDgradParams {
 };
 constexpr int NPAD_D = 32;
 
+template <bool BITS>   // BITS: ReLU mask = one 32-bit word per pixel (relu_bits); otherwise read the bf16 activation
 __global__ void __launch_bounds__(kThreadsD, 1)
 tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) {
   constexpr uint32_t CH = NPIX * 16;
@@ -340,7 +341,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       const int rem = t % (p.tiles_y * p.tiles_x);
       const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
       uint32_t bits[NMT];
-      if (p.relu_bits) {
+      if (BITS) {
 #pragma unroll
         for (int k = 0; k < NMT; ++k) {
           const int mt = sub + k * kSubD;
@@ -362,7 +363,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
         const bool live = c < TW && oy < p.H && ox < p.W;
         const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
         uint4 m[4];
-        if (!p.relu_bits) {
+        if (!BITS) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) m[g] = make_uint4(0, 0, 0, 0);
           if (live) {
@@ -398,7 +399,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               bool pos;
-              if (p.relu_bits) {
+              if (BITS) {
                 pos = (bits[k] >> (g * 8 + j)) & 1u;
               } else {
                 // bf16 > 0  <=>  sign bit clear and magnitude bits non-zero (dead lanes: mask 0 -> y = 0)
@@ -1610,9 +1611,14 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   const size_t smem = (size_t)kStages * ((size_t)NPIX * 16 + 128) + (size_t)5 * 2 * NPAD_D * 16;
   ProfScope prof_("tc_out_dgrad", st);
   ++g_launches;
-  cudaFuncSetAttribute(tc_out_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   p.chan_partial = chan_sum ? chan_partial : nullptr;
-  tc_out_dgrad_kernel<<<grid, kThreadsD, smem, st>>>(tmap, p);
+  if (relu_bits) {
+    cudaFuncSetAttribute(tc_out_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_out_dgrad_kernel<true><<<grid, kThreadsD, smem, st>>>(tmap, p);
+  } else {
+    cudaFuncSetAttribute(tc_out_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_out_dgrad_kernel<false><<<grid, kThreadsD, smem, st>>>(tmap, p);
+  }
   if (chan_sum) {
     sum_partials(chan_partial, grid * 4 * kSubD, Cin, chan_sum, st);
   }

@@ -22,7 +22,9 @@ void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img_bf16, cu
 // g_out fp32 NHWC and/or g_s2d bf16 space-to-depth [B,H/2,W/2,4,Cin] (either may be nullptr)
 // chan_sum [Cin] (optional) = sum over all pixels of g = bias gradient of the producing layer;
 // chan_partial >= 148*8*32 floats of scratch
-int tc_out_dgrad(const void* dl8_bf16, const void* wimg_bf16, const void* mask_bf16, float* g_out, void* g_s2d_bf16,
+// relu_bits (optional, [B,H,W] uint32 written by tc_tail_fused): replaces the reads of mask_bf16
+int tc_out_dgrad(const void* dl8_bf16, const void* wimg_bf16, const void* mask_bf16, const uint32_t* relu_bits, float* g_out,
+                 void* g_s2d_bf16,
                  float* chan_sum, float* chan_partial, int B, int H, int W, int Cin, int* error_flag, cudaStream_t st);
 // backward of the last Conv2DTranspose s2 (Cin <= 8 -> 32) from the space-to-depth gradient
 bool tc_convT_bwd_supported(int Cin, int Cout, int h, int w);
@@ -48,8 +50,9 @@ bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W);
 size_t tc_tail_score_partial_floats(int B, int H, int W);
 // a_last_planar (optional): chunk-planar bf16 copy of the intermediate activation for the backward pass
 int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, const float* biasA, const float* biasB,
-                  const float* x, float* xhat, void* a_last_planar, float* err, float* score, float* err_minmax,
-                  float* score_partial, int B, int H, int W, int Cout, int apply_sigmoid, int* error_flag, cudaStream_t st);
+                  const float* x, float* xhat, void* a_last_planar, uint32_t* relu_bits, float* err, float* score,
+                  float* err_minmax, float* score_partial, int B, int H, int W, int Cout, int apply_sigmoid, int* error_flag,
+                  cudaStream_t st);
 
 // output-layer weight gradient (MN-major tcgen05, K = pixels); partial >= tc_out_wgrad_partial_floats()
 bool tc_out_wgrad_supported(int Cin, int Cout);
