@@ -61,6 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     log = []
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags += os.environ.get("KCVAE_NVCC_EXTRA", "").split()   # development builds, e.g. -DKCVAE_TAIL_TIMING
 
     def one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

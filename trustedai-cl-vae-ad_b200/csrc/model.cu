@@ -444,7 +444,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
       tc_prep_convT_weights(a.w, a.Co, a.Ci, h->wimg_convT, st);
       if ((!keep_last || h->fuse_train_tail) && tail_fusable(h, B)) {
         const int vo = h->vi_out();
-        tc_prep_out_weights(h->wp(vo), h->C, h->dc[L], h->wimg_out, st);
+        tc_prep_tail_weights(h->wp(vo), h->C, h->dc[L], h->wimg_out, st);
         g_tag = "dec.tail";
         const bool want_score = tail && tail->x && (tail->err || tail->score);
         if (tc_tail_fused(h->a_prev8, h->wimg_convT, h->wimg_out, a.bias, h->wp(vo + 1), want_score ? tail->x : nullptr, out,

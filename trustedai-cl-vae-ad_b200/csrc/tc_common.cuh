@@ -131,6 +131,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
   for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// two 8-column loads in flight behind one wait (two M-tiles of a small-N epilogue)
+__device__ __forceinline__ void tmem_ld8x2(uint32_t taddr0, uint32_t taddr1, float v0[8], float v1[8]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr0)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+               : "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr1)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { v0[j] = __uint_as_float(r[j]); v1[j] = __uint_as_float(r[8 + j]); }
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(count) : "memory");

@@ -15,6 +15,9 @@
 //     store x_hat; TMA / MMA / epilogue overlap through mbarrier pipelines.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread),
 // warps 2..5 = epilogue (TMEM lane groups (warp & 3)).
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
 #include <cuda.h>
 
 #include "kernels.h"
@@ -225,6 +228,15 @@ __global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __
   }
 }
 
+// C2I image of the same weights (fused tail, Cout <= 3): B operand [N = 32 rows n = tap*Cout + co][K = 32 ci],
+// K-major canonical units [kchunk 4][n 32][8]; n = tap * 3 + co whatever Cout is (missing channels are zero columns)
+__global__ void tc_prep_tail_c2i_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * 32 * 8; i += gridDim.x * blockDim.x) {
+    const int j = i % 8, n = (i / 8) % 32, kchunk = i / 256;
+    const int ci = kchunk * 8 + j, tap = n / 3, co = n % 3;
+    img[i] = __float2bfloat16(tap < 9 && co < Cout && ci < Cin ? w[((int64_t)tap * Cout + co) * Cin + ci] : 0.f);
+  }
+}
 
 // ============================================================================================
 // Output-layer data gradient on tensor cores:
@@ -1199,24 +1211,60 @@ struct TailParams {
   int B, H, W, Cout;
   int tiles_y, tiles_x, num_tiles;
   int apply_sigmoid;
+  int xrow;                    // floats per shared-memory row of the frame tile (TMA box: xrow x TR), 0 without x
+  uint32_t x_stage;            // bytes per frame-tile stage (multiple of 128)
   int* error_flag;
 };
 
+// C2I ("col2im") form of the output convolution, Cout <= 3: instead of nine shifted K=32 products per output
+// tile (144 MMAs whose A operand is re-read from shared memory nine times - the tensor pipe then idles on
+// operand fetch), ONE product T[q][(tap,co)] = sum_ci a[q][ci] W[tap][co][ci] per halo position q (18 MMAs,
+// N = 32), and the nine taps are summed as shifted reads of T:  out[r,c,co] = sum_tap T[(r+2-kh, c+2-kw)][tap,co].
+// T travels TMEM -> shared memory through a 3-deep ring of M-tiles (4 halo rows each) in [n][q] order, so
+// both the transposing stores and the shifted loads are conflict-free.
+constexpr int C2I_MT = 9;       // M-tiles of 128 halo positions (34 x 32 = 1088 -> 8.5)
+constexpr int C2I_RING = 3;     // shared-memory ring depth (M-tiles)
+constexpr int C2I_TSLOTS = 4;   // TMEM ring of 32-column accumulators
+constexpr int C2I_NV = 27;      // 9 taps x 3 channels
+constexpr uint32_t C2I_T_BYTES = C2I_NV * C2I_RING * 128 * 4;
+
+// Development aid (-DKCVAE_TAIL_TIMING): every warp of CTA 0 accumulates the cycles it spends in each mbarrier
+// wait and its total time; the launcher prints them.  Compiled out of the product.
+#ifdef KCVAE_TAIL_TIMING
+__device__ long long g_tail_dbg[16 * 16];
+#define TAIL_TIMING_DECL long long tw_[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long tstart_ = clock64();
+#define TSPAN_BEGIN const long long ts_ = clock64();
+#define TSPAN_END(idx) tw_[idx] += clock64() - ts_;
+#define TWAIT(idx, bar, par) [&] { const long long t_ = clock64(); const bool r_ = mbar_wait(bar, par); tw_[idx] += clock64() - t_; return r_; }()
+#define TAIL_TIMING_DUMP if (blockIdx.x == 0 && lane == 0) { for (int i_ = 0; i_ < 14; ++i_) g_tail_dbg[warp * 16 + i_] = tw_[i_]; g_tail_dbg[warp * 16 + 14] = clock64() - tstart_; }
+#else
+#define TAIL_TIMING_DECL
+#define TSPAN_BEGIN
+#define TSPAN_END(idx)
+#define TWAIT(idx, bar, par) mbar_wait(bar, par)
+#define TAIL_TIMING_DUMP
+#endif
+
+template <bool C2I>
 __global__ void __launch_bounds__(kThreadsT, 1)
-tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
+tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapx, TailParams p) {
   constexpr uint32_t CH = NPIX * 16;
   constexpr uint32_t A4_BYTES = 4 * CH;
   constexpr uint32_t A4_STAGE = A4_BYTES + 128;
   constexpr uint32_t A3_STAGE = A3_STAGE_BYTES;
-  constexpr uint32_t WA_BYTES = 5 * 2 * 32 * 16, WB_BYTES = 9 * 2 * 2 * NPAD * 16;
+  constexpr uint32_t WA_BYTES = 5 * 2 * 32 * 16, WB_BYTES = C2I ? 2 * 2 * 32 * 16 : 9 * 2 * 2 * NPAD * 16;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* s_a4 = smem;                               // 2 stages
   unsigned char* s_a3 = smem + 2 * A4_STAGE;                // 2 stages
-  unsigned char* s_wA = s_a3 + 2 * A3_STAGE;
+  unsigned char* s_x = s_a3 + 2 * A3_STAGE;                 // 2 stages of the frame tile the error is taken against (scoring)
+  unsigned char* s_wA = s_x + 2 * p.x_stage;
   unsigned char* s_wB = s_wA + WA_BYTES;
+  float* s_T = reinterpret_cast<float*>(s_wB + WB_BYTES);   // C2I: [C2I_NV][C2I_RING * 128]
   __shared__ uint64_t a3_full[2], a3_empty[2], Afull[2], Aempty[2], a4_ready[2], a4_free[2], Bfull[2], Bempty[2];
+  __shared__ uint64_t Tfull[C2I_TSLOTS], Tempty[C2I_TSLOTS], x_full[2], x_empty[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TAIL_TIMING_DECL
 
   for (int i = threadIdx.x; i < (int)(WA_BYTES / 16); i += kThreadsT) reinterpret_cast<uint4*>(s_wA)[i] = reinterpret_cast<const uint4*>(p.wimgA)[i];
   for (int i = threadIdx.x; i < (int)(WB_BYTES / 16); i += kThreadsT) reinterpret_cast<uint4*>(s_wB)[i] = reinterpret_cast<const uint4*>(p.wimgB)[i];
@@ -1232,7 +1280,9 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
       mbar_init(&Afull[s], 1);   mbar_init(&Aempty[s], 8);
       mbar_init(&a4_ready[s], 8); mbar_init(&a4_free[s], 1);
       mbar_init(&Bfull[s], 1);   mbar_init(&Bempty[s], 4);
+      mbar_init(&x_full[s], 1);  mbar_init(&x_empty[s], 4);
     }
+    for (int s = 0; s < C2I_TSLOTS; ++s) { mbar_init(&Tfull[s], 1); mbar_init(&Tempty[s], 4); }
     fence_mbar_init();
   }
   fence_async_smem();
@@ -1247,12 +1297,17 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int s = it & 1;
-        if (!mbar_wait(&a3_empty[s], ((it >> 1) & 1) ^ 1)) { *p.error_flag = 1; break; }
+        if (!TWAIT(0, &a3_empty[s], ((it >> 1) & 1) ^ 1)) { *p.error_flag = 1; break; }
         const int n = t / (p.tiles_y * p.tiles_x);
         const int rem = t % (p.tiles_y * p.tiles_x);
         const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
         mbar_expect_tx(&a3_full[s], A3_BYTES);
         tma_load_4d(s_a3 + s * A3_STAGE, &tmap, &a3_full[s], 0, (tx * TW) / 2 - 2, (ty * TR) / 2 - 2, n);
+        if (p.x) {   // the frame tile lands a whole tile ahead of the epilogue that compares against it
+          if (!TWAIT(11, &x_empty[s], ((it >> 1) & 1) ^ 1)) { *p.error_flag = 1; break; }
+          mbar_expect_tx(&x_full[s], (uint32_t)(p.xrow * TR * 4));
+          tma_load_3d(s_x + s * p.x_stage, &tmapx, &x_full[s], (tx * TW * p.Cout) & ~3, ty * TR, n);   // 16-byte aligned box start
+        }
       }
     }
   } else if (warp == 1) {
@@ -1264,18 +1319,21 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
     const uint32_t idescA = make_idesc_bf16_f32(128, 32), idescB = make_idesc_bf16_f32(128, NPAD);
     const uint64_t wA0 = make_desc_kmajor_noswz(smem_u32(s_wA), 32 * 16, 128);
     const uint64_t wB0 = make_desc_kmajor_noswz(smem_u32(s_wB), NPAD * 16, 128);
-    int ma = 0;
+    int ma = 0, mb = 0;
     bool ok = true;
-    auto issue_A = [&](int itA) {
+    // M-tiles [mt_lo, mt_hi) of phase A of tile itA
+    auto issue_A = [&](int itA, int mt_lo, int mt_hi) {
       const int s = itA & 1;
       const uint32_t ph = (itA >> 1) & 1;
-      if (!mbar_wait(&a3_full[s], ph)) { if (leader) *p.error_flag = 1; ok = false; return; }
-      fence_after_sync();
+      if (mt_lo == 0) {
+        if (!TWAIT(1, &a3_full[s], ph)) { if (leader) *p.error_flag = 1; ok = false; return; }
+        fence_after_sync();
+      }
       const uint32_t a3b = smem_u32(s_a3 + s * A3_STAGE);
 #pragma unroll 1
-      for (int mt = 0; mt < MTA; ++mt, ++ma) {
+      for (int mt = mt_lo; mt < mt_hi; ++mt, ++ma) {
         const int slot = ma & 1;
-        if (!mbar_wait(&Aempty[slot], ((ma >> 1) & 1) ^ 1)) { if (leader) *p.error_flag = 1; ok = false; return; }
+        if (!TWAIT(2, &Aempty[slot], ((ma >> 1) & 1) ^ 1)) { if (leader) *p.error_flag = 1; ok = false; return; }
         fence_after_sync();
         const uint32_t d0 = tmem + (uint32_t)(slot * 128);
         const uint32_t q0 = a3b + (uint32_t)(mt * 128) * 16;
@@ -1293,40 +1351,71 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
         }
         __syncwarp();
       }
-      if (leader) mma_commit(&a3_empty[s]);
-      __syncwarp();
+      if (mt_hi == MTA) {
+        if (leader) mma_commit(&a3_empty[s]);
+        __syncwarp();
+      }
     };
     int it = 0;
-    if ((int)blockIdx.x < p.num_tiles) issue_A(0);
+    if ((int)blockIdx.x < p.num_tiles) issue_A(0, 0, MTA);
     for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      if (t + (int)gridDim.x < p.num_tiles) { issue_A(it + 1); if (!ok) break; }
+      // Only two TMEM slots hold phase-A accumulators, so the third M-tile of A(it+1) needs the first one drained
+      // by the epilogue warps: it is issued from the MIDDLE of phase B below, where that wait no longer idles the
+      // tensor pipe.
+      const bool more = t + (int)gridDim.x < p.num_tiles;
+      if (more) { issue_A(it + 1, 0, C2I ? MTA : 2); if (!ok) break; }
       // ---- phase B on the smem tile the epilogue warps produced from A(it)
-      if (!mbar_wait(&a4_ready[s], ph)) { if (leader) *p.error_flag = 1; break; }
-      if (!mbar_wait(&Bempty[s], ph ^ 1)) { if (leader) *p.error_flag = 1; break; }
-      fence_after_sync();
-      const uint64_t da0 = make_desc_kmajor_noswz(smem_u32(s_a4 + s * A4_STAGE), CH, 128);
-#pragma unroll 2
-      for (int mt = 0; mt < MT; ++mt) {
-        const uint32_t d_tmem = tmem + (uint32_t)(256 + s * 128 + mt * NPAD);
-        const uint64_t da_mt = desc_advance(da0, (uint32_t)(mt * 128));
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t shift = (uint32_t)((2 - tap / 3) * PW + (2 - tap % 3));
-#pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t da = desc_advance(da_mt, (uint32_t)(2 * ks) * (CH / 16) + shift);
-            const uint64_t db = desc_advance(wB0, (uint32_t)((tap * 2 + ks) * 2 * NPAD));
-            if (leader) mma_bf16_ss(d_tmem, da, db, idescB, (tap | ks) != 0);
+      if (!TWAIT(4, &a4_ready[s], ph)) { if (leader) *p.error_flag = 1; break; }
+      if constexpr (C2I) {
+        fence_after_sync();
+        const uint64_t da0 = make_desc_kmajor_noswz(smem_u32(s_a4 + s * A4_STAGE), CH, 128);
+        const uint64_t wT0 = make_desc_kmajor_noswz(smem_u32(s_wB), 32 * 16, 128);
+#pragma unroll 1
+        for (int mt = 0; mt < C2I_MT; ++mt, ++mb) {
+          const int slot = mb & (C2I_TSLOTS - 1);
+          if (!TWAIT(3, &Tempty[slot], ((mb / C2I_TSLOTS) & 1) ^ 1)) { if (leader) *p.error_flag = 1; ok = false; break; }
+          fence_after_sync();
+          const uint32_t d_tmem = tmem + (uint32_t)(256 + slot * 32);
+          const uint64_t da_mt = desc_advance(da0, (uint32_t)(mt * 128));
+          if (leader) {
+            mma_bf16_ss(d_tmem, da_mt, wT0, idescA, 0);                                                   // channels 0..15
+            mma_bf16_ss(d_tmem, desc_advance(da_mt, 2 * (CH / 16)), desc_advance(wT0, 2 * 32), idescA, 1);  // channels 16..31
+            mma_commit(&Tfull[slot]);
           }
+          __syncwarp();
         }
+        if (!ok) break;
+        if (leader) mma_commit(&a4_free[s]);
+        __syncwarp();
+      } else {
+        if (!TWAIT(5, &Bempty[s], ph ^ 1)) { if (leader) *p.error_flag = 1; break; }
+        fence_after_sync();
+        const uint64_t da0 = make_desc_kmajor_noswz(smem_u32(s_a4 + s * A4_STAGE), CH, 128);
+#pragma unroll 2
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d_tmem = tmem + (uint32_t)(256 + s * 128 + mt * NPAD);
+          const uint64_t da_mt = desc_advance(da0, (uint32_t)(mt * 128));
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t shift = (uint32_t)((2 - tap / 3) * PW + (2 - tap % 3));
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t da = desc_advance(da_mt, (uint32_t)(2 * ks) * (CH / 16) + shift);
+              const uint64_t db = desc_advance(wB0, (uint32_t)((tap * 2 + ks) * 2 * NPAD));
+              if (leader) mma_bf16_ss(d_tmem, da, db, idescB, (tap | ks) != 0);
+            }
+          }
+          if (mt == MT / 2 - 1 && more) { issue_A(it + 1, 2, MTA); if (!ok) break; }
+        }
+        if (!ok) break;
+        if (leader) {
+          mma_commit(&a4_free[s]);
+          mma_commit(&Bfull[s]);
+        }
+        __syncwarp();
       }
-      if (leader) {
-        mma_commit(&a4_free[s]);
-        mma_commit(&Bfull[s]);
-      }
-      __syncwarp();
     }
   } else {
     // ================================ epilogue warps ========================================
@@ -1355,12 +1444,12 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
         const uint32_t ph = (it >> 1) & 1;
         int n, ty0, tx0;
         tile_origin(t, n, ty0, tx0);
-        if (!mbar_wait(&a4_free[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; break; }   // B(it-2) done with this stage
+        if (!TWAIT(6, &a4_free[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; break; }   // B(it-2) done with this stage
         unsigned char* a4s = s_a4 + s * A4_STAGE;
 #pragma unroll 1
         for (int mt = 0; mt < MTA; ++mt, ++ma) {
           const int slot = ma & 1;
-          if (!mbar_wait(&Afull[slot], (ma >> 1) & 1)) { if (lane == 0) *p.error_flag = 1; ok = false; break; }
+          if (!TWAIT(7, &Afull[slot], (ma >> 1) & 1)) { if (lane == 0) *p.error_flag = 1; ok = false; break; }
           fence_after_sync();
           const int q = mt * 128 + lg * 32 + lane;
           const int r = q / PA, c = q % PA;
@@ -1414,58 +1503,142 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
       float bB[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) bB[c] = c < p.Cout ? __ldg(p.biasB + c) : 0.f;
+      if constexpr (C2I) {
+        constexpr int RW = C2I_RING * 128;          // ring pixels per value plane
+        const int u = lg * 32 + lane;               // position inside an M-tile this thread moves to shared memory
+        int mb = 0, it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+          int n, ty0, tx0;
+          tile_origin(t, n, ty0, tx0);
+          float esum = 0.f, emin = 3.4e38f, emax = -3.4e38f;
+          const float* xs = reinterpret_cast<const float*>(s_x + (it & 1) * p.x_stage) + ((tx0 * p.Cout) & 3);
+          if (p.x && !TWAIT(10, &x_full[it & 1], (it >> 1) & 1)) { if (lane == 0) *p.error_flag = 1; break; }
+#pragma unroll 1
+          for (int mt = 0; mt < C2I_MT; ++mt, ++mb) {
+            // output rows that become complete with this M-tile (halo rows 4mt..4mt+3): 4mt-2 .. 4mt+1
+            const int r0 = (mt == 0 ? 0 : 4 * mt - 2) + lg;
+            const int r_hi = 4 * mt + 1 < TR - 1 ? 4 * mt + 1 : TR - 1;
+            const int oy = ty0 + r0, ox = tx0 + lane;
+            const bool live = r0 <= r_hi && lane < TW && oy < p.H && ox < p.W;
+            const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
+            float xv[3];
+#pragma unroll
+            for (int co = 0; co < 3; ++co) xv[co] = (p.x && live && co < p.Cout) ? xs[r0 * p.xrow + lane * p.Cout + co] : 0.f;
+            const int slot = mb & (C2I_TSLOTS - 1);
+            if (!TWAIT(8, &Tfull[slot], (mb / C2I_TSLOTS) & 1)) { if (lane == 0) *p.error_flag = 1; }
+            fence_after_sync();
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + slot * 32), v);
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&Tempty[slot]);
+            float* dstT = s_T + (mt % C2I_RING) * 128 + u;
+#pragma unroll
+            for (int k = 0; k < C2I_NV; ++k) dstT[k * RW] = v[k];
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");     // the four phase-B warps
+            // nine shifted reads per channel; dead lanes read in-range garbage and drop it
+            float acc[3] = {bB[0], bB[1], bB[2]};
+            const int rr = r0 <= r_hi ? r0 : r_hi, cc = lane < TW ? lane : TW - 1;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const int qg = (rr + 2 - kh) * PW + (cc + 2 - kw);
+                const float* src = s_T + ((qg >> 7) % C2I_RING) * 128 + (qg & 127) + (kh * 3 + kw) * 3 * RW;
+#pragma unroll
+                for (int co = 0; co < 3; ++co) acc[co] += src[co * RW];
+              }
+            float e = 0.f, y[3];
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+              y[co] = p.apply_sigmoid ? __fdividef(1.0f, 1.0f + __expf(-acc[co])) : acc[co];
+              const float d = co < p.Cout ? xv[co] - y[co] : 0.f;
+              e = fmaf(d, d, e);
+            }
+            if (live) {
+              if (p.xhat) {
+#pragma unroll
+                for (int co = 0; co < 3; ++co)
+                  if (co < p.Cout) p.xhat[pix * p.Cout + co] = y[co];
+              }
+              if (p.err) p.err[pix] = e;
+              esum += e; emin = fminf(emin, e); emax = fmaxf(emax, e);
+            }
+          }
+          if (p.score_partial) {     // fixed shuffle tree -> deterministic
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              esum += __shfl_xor_sync(0xffffffffu, esum, o);
+              emin = fminf(emin, __shfl_xor_sync(0xffffffffu, emin, o));
+              emax = fmaxf(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+            }
+            if (lane == 0) {
+              float* o3 = p.score_partial + ((int64_t)t * 4 + lg) * 3;
+              o3[0] = esum; o3[1] = emin; o3[2] = emax;
+            }
+          }
+          if (p.x) { __syncwarp(); if (lane == 0) mbar_arrive(&x_empty[it & 1]); }
+        }
+      } else {
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int s = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         int n, ty0, tx0;
         tile_origin(t, n, ty0, tx0);
-        // the frame values this warp compares with do not depend on the MMAs: request the first
-        // M-tile's before the accumulator wait, and every next one while the current is reduced
-        auto pix_of = [&](int mt, bool& live) -> int64_t {
+        const float* xs = reinterpret_cast<const float*>(s_x + s * p.x_stage) + ((tx0 * p.Cout) & 3);
+        if (p.x && !TWAIT(10, &x_full[s], ph)) { if (lane == 0) *p.error_flag = 1; break; }
+        if (!TWAIT(9, &Bfull[s], ph)) { if (lane == 0) *p.error_flag = 1; break; }
+        fence_after_sync();
+        float esum = 0.f, emin = 3.4e38f, emax = -3.4e38f;
+        // Straight-line code over a fixed channel count (channels >= Cout are computed and dropped): the serial
+        // branchy per-channel form left this single warp per scheduler waiting on one sigmoid chain at a time.
+        auto finish = [&](auto cn, int mt, const float (&v)[8]) {
+          constexpr int CN = decltype(cn)::value;
           const int q = mt * 128 + lg * 32 + lane;
           const int r = q / PW, c = q % PW;
           const int oy = ty0 + r, ox = tx0 + c;
-          live = c < TW && oy < p.H && ox < p.W;
-          return ((int64_t)n * p.H + oy) * p.W + ox;
-        };
-        float xn[8];
-        auto load_x = [&](int mt) {
-          bool live;
-          const int64_t pix = pix_of(mt, live);
+          const bool live = c < TW && oy < p.H && ox < p.W;
+          const int64_t pix = ((int64_t)n * p.H + oy) * p.W + ox;
+          const float* xr = xs + r * p.xrow + c * p.Cout;
+          float xv[CN], y[CN];
 #pragma unroll
-          for (int co = 0; co < 8; ++co) xn[co] = (p.x && live && co < p.Cout) ? __ldg(p.x + pix * p.Cout + co) : 0.f;
-        };
-        load_x(0);
-        if (!mbar_wait(&Bfull[s], ph)) { if (lane == 0) *p.error_flag = 1; break; }
-        fence_after_sync();
-        float esum = 0.f, emin = 3.4e38f, emax = -3.4e38f;
-#pragma unroll 1
-        for (int mt = 0; mt < MT; ++mt) {
-          float xc[8];
+          for (int co = 0; co < CN; ++co) xv[co] = (p.x && live && co < p.Cout) ? xr[co] : 0.f;
 #pragma unroll
-          for (int co = 0; co < 8; ++co) xc[co] = xn[co];
-          if (mt + 1 < MT) load_x(mt + 1);
-          float v[8];
-          tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + s * 128 + mt * NPAD), v);
-          bool live;
-          const int64_t pix = pix_of(mt, live);
+          for (int co = 0; co < CN; ++co) {
+            y[co] = v[co] + bB[co];
+            if (p.apply_sigmoid) y[co] = __fdividef(1.0f, 1.0f + __expf(-y[co]));
+          }
+          float e = 0.f;
+#pragma unroll
+          for (int co = 0; co < CN; ++co) {
+            const float d = co < p.Cout ? xv[co] - y[co] : 0.f;
+            e = fmaf(d, d, e);
+          }
           if (live) {
-            float e = 0.f;
+            if (p.xhat) {
 #pragma unroll
-            for (int co = 0; co < 8; ++co) {
-              if (co < p.Cout) {
-                float y = v[co] + bB[co];
-                if (p.apply_sigmoid) y = 1.0f / (1.0f + __expf(-y));
-                if (p.xhat) p.xhat[pix * p.Cout + co] = y;
-                const float d = xc[co] - y;
-                e = fmaf(d, d, e);
-              }
+              for (int co = 0; co < CN; ++co)
+                if (co < p.Cout) p.xhat[pix * p.Cout + co] = y[co];
             }
             if (p.err) p.err[pix] = e;
             esum += e; emin = fminf(emin, e); emax = fmaxf(emax, e);
           }
+        };
+        const uint32_t tb = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + s * 128);
+#pragma unroll 1
+        for (int mt = 0; mt < MT; mt += 2) {
+          float v0[8], v1[8];
+          tmem_ld8x2(tb + (uint32_t)(mt * NPAD), tb + (uint32_t)((mt + 1) * NPAD), v0, v1);
+          if (p.Cout <= 4) {
+            finish(std::integral_constant<int, 4>{}, mt, v0);
+            finish(std::integral_constant<int, 4>{}, mt + 1, v1);
+          } else {
+            finish(std::integral_constant<int, 8>{}, mt, v0);
+            finish(std::integral_constant<int, 8>{}, mt + 1, v1);
+          }
         }
+        if (p.x) { __syncwarp(); if (lane == 0) mbar_arrive(&x_empty[s]); }
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&Bempty[s]);
@@ -1482,8 +1655,10 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, TailParams p) {
           }
         }
       }
+      }   // !C2I
     }
   }
+  TAIL_TIMING_DUMP
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
@@ -1766,6 +1941,20 @@ int tc_convT_wgrad(const void* g_s2d, const void* a_prev8, float* dW, float* par
 bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W) {
   return Cprev >= 1 && Cprev <= 8 && Clast == 32 && Cout >= 1 && Cout <= 8 && H % 2 == 0 && W % 2 == 0;
 }
+// KCVAE_TAIL_C2I=1 selects the col2im form of the output convolution (Cout <= 3).  Measured on B200 (128 frames,
+// README shape): nine-tap form 0.314 ms (tensor pipe busy issuing 159 small-N MMAs per tile at ~48 cycles each),
+// col2im form 0.398 ms (18 MMAs per tile, but its four epilogue warps then carry 27 shared-memory round trips per
+// pixel) - so the nine-tap form is the default.
+static bool tail_c2i(int Cout) {
+  static const int env = [] { const char* e = std::getenv("KCVAE_TAIL_C2I"); return (e && e[0] == '1') ? 1 : 0; }();
+  return env && Cout <= 3;
+}
+void tc_prep_tail_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
+  if (!tail_c2i(Cout)) { tc_prep_out_weights(w, Cout, Cin, img, st); return; }
+  ProfScope prof_("tc_prep_weights", st);
+  ++g_launches;
+  tc_prep_tail_c2i_weights_kernel<<<4, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+}
 size_t tc_tail_score_partial_floats(int B, int H, int W) { return (size_t)B * cdiv(H, TR) * cdiv(W, TW) * 4 * 3; }
 
 // fused Conv2DTranspose s2 -> Conv2DTranspose s1 (+ sigmoid, error map, per-frame score).
@@ -1798,13 +1987,48 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
   p.num_tiles = B * p.tiles_y * p.tiles_x;
   p.apply_sigmoid = apply_sigmoid;
   p.error_flag = error_flag;
+  CUtensorMap tmapx = tmap;   // unused without x
+  if (x) {
+    // frame tile [TR rows][TW pixels x Cout floats, padded to 16 bytes] by TMA; rows of x must be 16-byte multiples
+    if ((W * Cout) % 4 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return 3;
+    p.xrow = ((TW * Cout + 3 + 3) / 4) * 4;   // + up to 3 floats in front: the box starts 16-byte aligned
+    p.x_stage = (uint32_t)(((size_t)p.xrow * TR * 4 + 127) / 128 * 128);
+    const cuuint64_t xdim[3] = {(cuuint64_t)W * Cout, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t xstr[2] = {(cuuint64_t)W * Cout * 4, (cuuint64_t)H * W * Cout * 4};
+    const cuuint32_t xbox[3] = {(cuuint32_t)p.xrow, TR, 1};
+    const cuuint32_t xes[3] = {1, 1, 1};
+    if (enc(&tmapx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), xdim, xstr, xbox, xes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return 2;
+  }
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  const size_t smem = (size_t)2 * ((size_t)4 * NPIX * 16 + 128) + (size_t)2 * A3_STAGE_BYTES + (size_t)5 * 2 * 32 * 16 +
-                      (size_t)9 * 2 * 2 * NPAD * 16;
+  const size_t smem0 = (size_t)2 * ((size_t)4 * NPIX * 16 + 128) + (size_t)2 * A3_STAGE_BYTES + (size_t)5 * 2 * 32 * 16 +
+                       (size_t)2 * p.x_stage;
   ProfScope prof_("tc_tail_fused", st);
   ++g_launches;
-  cudaFuncSetAttribute(tc_tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tc_tail_fused_kernel<<<grid, kThreadsT, smem, st>>>(tmap, p);
+  if (tail_c2i(Cout)) {
+    const size_t smem = smem0 + (size_t)2 * 2 * 32 * 16 + C2I_T_BYTES;
+    cudaFuncSetAttribute(tc_tail_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_tail_fused_kernel<true><<<grid, kThreadsT, smem, st>>>(tmap, tmapx, p);
+  } else {
+    const size_t smem = smem0 + (size_t)9 * 2 * 2 * NPAD * 16;
+    cudaFuncSetAttribute(tc_tail_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_tail_fused_kernel<false><<<grid, kThreadsT, smem, st>>>(tmap, tmapx, p);
+  }
+#ifdef KCVAE_TAIL_TIMING
+  if (std::getenv("KCVAE_TAIL_DBG")) {
+    cudaStreamSynchronize(st);
+    long long hd[16 * 16];
+    cudaMemcpyFromSymbol(hd, g_tail_dbg, sizeof(hd));
+    static const char* nm[14] = {"a3_empty", "a3_full", "Aempty", "Tempty", "a4_ready", "Bempty", "a4_free", "Afull", "Tfull", "Bfull", "x_full", "x_empty", "tmem_ld", "epi_math"};
+    std::fprintf(stderr, "tail timing (CTA 0, cycles; tiles/CTA %.1f):\n", (double)p.num_tiles / grid);
+    for (int wv = 0; wv < kThreadsT / 32; ++wv) {
+      std::fprintf(stderr, "  warp %2d total %9lld |", wv, hd[wv * 16 + 14]);
+      for (int i = 0; i < 14; ++i) if (hd[wv * 16 + i]) std::fprintf(stderr, " %s %lld", nm[i], hd[wv * 16 + i]);
+      std::fprintf(stderr, "\n");
+    }
+  }
+#endif
   if (score) {
     ++g_launches;
     tail_score_finish_kernel<<<B, 128, 0, st>>>(score_partial, p.tiles_y * p.tiles_x * 4, score, err_minmax);

@@ -47,6 +47,8 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg_bf16, const float* bias,
 // fused decoder tail: Conv2DTranspose s2 (Cprev <= 8 -> 32) -> Conv2DTranspose s1 (32 -> Cout) with the
 // 32-channel activation kept in shared memory; optional sigmoid, x_hat, error map and per-frame score
 bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W);
+// weight image the fused tail reads for its output convolution (layout depends on Cout); img = tc_out_weight_image_elems()
+void tc_prep_tail_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
 size_t tc_tail_score_partial_floats(int B, int H, int W);
 // a_last_planar (optional): chunk-planar bf16 copy of the intermediate activation for the backward pass
 int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, const float* biasA, const float* biasB,
