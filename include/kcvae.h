@@ -171,6 +171,42 @@ int kcvae_train_step_host(kcvae_handle h, const float* h_x, int batch, const flo
 int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, float* h_score,
                      void* stream);
 
+/* ---- front end: uint8 frames -> model input --------------------------------- */
+/* src/data_loader.py:10-20 (_normalize_img, _resize_img) / camera_streamer_qt.py:1296:
+ * x = tf.image.resize(uint8 / 255., image_size[:2], antialias=True) for d_frames [B,in_h,in_w,C] uint8 NHWC;
+ * in_h == H and in_w == W: the cast alone.  d_x [B,H,W,C] fp32. */
+int kcvae_preprocess_u8(kcvae_handle h, const uint8_t* d_frames, int batch, int in_h, int in_w,
+                        float* d_x, void* stream);
+/* kcvae_score_host / kcvae_train_step_host fed with uint8 HOST frames (a quarter of the H2D bytes) */
+int kcvae_score_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w,
+                        float* h_err, float* h_score, void* stream);
+int kcvae_train_step_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w,
+                             const float* h_eps, float* h_metrics, float* h_xhat, int tier, void* stream);
+
+/* ---- streaming anomaly score of the camera tool ----------------------------- */
+/* camera_streamer_qt.py:1364-1400: per-pixel EMA mean / second moment of the error map, z scores, count of
+ * pixels whose z-of-z exceeds 3, EMA of that count -> anomaly_score; EMA-normalised uint8 error image. */
+typedef struct kcvae_stream* kcvae_stream_handle;
+int kcvae_stream_create(int H, int W, int device, kcvae_stream_handle* out);
+int kcvae_stream_destroy(kcvae_stream_handle s);
+int kcvae_stream_reset(kcvae_stream_handle s);
+const char* kcvae_stream_last_error(kcvae_stream_handle s);
+/* one frame.  d_err [H,W] = sum_c (x - x_rec)^2 (kcvae_score's error map); ma = stream_error_ma (:213, 0.99);
+ * d_err_u8 [H,W] (may be NULL) = round(255 (err - ema_min) / (ema_max - ema_min)), saturated;
+ * h_out[8] = anomaly_count, anomaly_score, frame min, frame max, ema_min, ema_max, z mean, z std.
+ * Synchronous (the reference reads the count on the host every frame). */
+int kcvae_stream_update(kcvae_stream_handle s, const float* d_err, double ma, uint8_t* d_err_u8,
+                        float* h_out, void* stream);
+
+/* ---- scorer outputs ------------------------------------------------------------ */
+/* do_anomaly_detection.py:166-170, output_reconstructions.py:68-83, camera_streamer_qt.py:1417-1418:
+ * err_u8 = round(255 norm_err); heatmap = cv2.applyColorMap(err_u8, COLORMAP_JET) (OpenCV channel order);
+ * rec_u8 = round(255 rec); overlay = cv2.addWeighted(heatmap, .5, rec_u8, .5, 0).  d_norm_err [B,H,W],
+ * d_rec [B,H,W,C]; every output may be NULL. */
+int kcvae_render_outputs(const float* d_norm_err, const float* d_rec, int batch, int H, int W, int C,
+                         uint8_t* d_err_u8, uint8_t* d_heatmap, uint8_t* d_overlay, uint8_t* d_rec_u8,
+                         void* stream);
+
 /* ---- introspection --------------------------------------------------------------------- */
 /* number of kernels this library launched on behalf of handle h since creation */
 int64_t kcvae_launch_count(kcvae_handle h);

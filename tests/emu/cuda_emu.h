@@ -29,6 +29,7 @@ using std::max;
 #define __forceinline__ inline __attribute__((always_inline))
 #define __restrict__ __restrict
 #define __shared__ static
+#define __constant__ static const
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 
@@ -149,6 +150,8 @@ template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { retu
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 static inline float __saturatef(float a) { return a < 0.f ? 0.f : (a > 1.f ? 1.f : a); }

@@ -10,6 +10,6 @@ x = torch.rand(B,224,300,3,device="cuda")
 for i in range(2): m.score(x)
 torch.cuda.synchronize()
 print("tc status", m.tc_status() if hasattr(m, "tc_status") else None)
-os.environ["KCVAE_TAIL_DBG"]="1"
+os.environ["KCVAE_TAIL_DBG"]="tail"
 m.score(x)
 torch.cuda.synchronize()

@@ -6,4 +6,5 @@ from .load_model import (import_vae_based_on_type, load_config, load_model_from_
 from .model import (AbstractCVAE, BetaAnnealingCallback, Callback, KTensor, KurtosisGlobalCVAE,  # noqa: F401
                     KurtosisSingleCVAE)
 from .optimizers import Adam  # noqa: F401
-from .scoring import evaluate_anomalies, get_data_scale, rank_anomalies  # noqa: F401
+from .scoring import evaluate_anomalies, get_data_scale, output_anomalies, rank_anomalies  # noqa: F401
+from .streaming import StreamingAnomalyScore, render_outputs  # noqa: F401

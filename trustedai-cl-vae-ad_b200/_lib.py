@@ -72,6 +72,15 @@ _SIGS = {
     "kcvae_prefetch_host": (C.c_int, [_P, _P, C.c_int]),
     "kcvae_train_step_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int, _P]),
     "kcvae_score_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
+    "kcvae_preprocess_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "kcvae_score_host_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "kcvae_train_step_host_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
+    "kcvae_stream_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "kcvae_stream_destroy": (C.c_int, [_P]),
+    "kcvae_stream_reset": (C.c_int, [_P]),
+    "kcvae_stream_last_error": (C.c_char_p, [_P]),
+    "kcvae_stream_update": (C.c_int, [_P, _P, C.c_double, _P, _P, _P]),
+    "kcvae_render_outputs": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "kcvae_launch_count": (C.c_int64, [_P]),
     "kcvae_debug_activation": (C.c_int64, [_P, C.c_int, _P, C.c_int64]),
     "kcvae_tc_status": (C.c_int, [_P]),

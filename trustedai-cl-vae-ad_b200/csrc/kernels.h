@@ -143,4 +143,13 @@ void adam_update(float* p, const float* g, float* m, float* v, int64_t n, float 
 void glorot_fill(float* p, int64_t n, float limit, uint64_t seed, uint32_t stream_id,
                  cudaStream_t st);
 
+// ---- frontend.cu: uint8 front end, streaming score, scorer outputs ----
+struct ResizePlan;
+ResizePlan* resize_plan_create(int in_h, int in_w, int out_h, int out_w, int C);
+void resize_plan_free(ResizePlan* p);
+bool resize_plan_matches(const ResizePlan* p, int in_h, int in_w, int out_h, int out_w, int C);
+int preprocess_u8(const uint8_t* in, int B, ResizePlan* plan, int64_t same_size_elems, float* out, cudaStream_t st);
+void render_outputs(const float* norm_err, const float* rec, int64_t npix, int C, uint8_t* err_u8, uint8_t* heatmap,
+                    uint8_t* overlay, uint8_t* rec_u8, cudaStream_t st);
+
 }  // namespace kc

@@ -103,6 +103,9 @@ struct kcvae_model {
   int cap_fwd = 0, cap_bwd = 0, last_B = 0;
   std::vector<float*> act_e, act_d, g_act_e, g_act_d;
   float* x_stage[2] = {nullptr, nullptr};   // double-buffered H2D staging for the *_host entry points
+  kc::ResizePlan* resize_plan = nullptr;    // uint8 front end: span tables of the last (in_h, in_w) seen
+  uint8_t* u8_stage = nullptr;              // H2D staging of uint8 host frames
+  size_t u8_stage_bytes = 0;
   const void* pend_src[2] = {nullptr, nullptr};   // host pointer whose prefetch sits in x_stage[i] (not yet consumed)
   int pend_batch[2] = {0, 0};
 #ifndef KCVAE_EMU
@@ -883,6 +886,8 @@ int kcvae_destroy(kcvae_handle h) {
                  h->x_noisy, h->dlogit, h->g_z, h->dhead, h->g_d1, h->partial, h->err_buf, h->score_buf, h->minmax,
                  h->metrics_dev};
   for (float* p : fl) if (p) cudaFree(p);
+  kc::resize_plan_free(h->resize_plan);
+  if (h->u8_stage) cudaFree(h->u8_stage);
   if (h->a_last_bf16) cudaFree(h->a_last_bf16);
   if (h->relu_bits) cudaFree(h->relu_bits);
   if (h->wimg_out) cudaFree(h->wimg_out);
@@ -1278,6 +1283,87 @@ int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, 
   release_host_input(h, d_x, st);
   if (h_err) KC_CUDA(h, cudaMemcpyAsync(h_err, h->err_buf, (size_t)batch * h->H * h->W * sizeof(float), cudaMemcpyDeviceToHost, st));
   KC_CUDA(h, cudaMemcpyAsync(h_score, h->score_buf, (size_t)batch * sizeof(float), cudaMemcpyDeviceToHost, st));
+  KC_CUDA(h, cudaStreamSynchronize(st));
+  return KCVAE_OK;
+}
+
+// ---- uint8 front end -------------------------------------------------------
+static int preprocess_impl(kcvae_model* h, const uint8_t* d_frames, int batch, int in_h, int in_w, float* d_x, cudaStream_t st) {
+  if (in_h <= 0 || in_w <= 0) return fail(h, KCVAE_ERR_INVALID, "preprocess_u8: invalid frame size");
+  kc::ResizePlan* plan = nullptr;
+  if (in_h != h->H || in_w != h->W) {
+    if (!kc::resize_plan_matches(h->resize_plan, in_h, in_w, h->H, h->W, h->C)) {
+      kc::resize_plan_free(h->resize_plan);
+      h->resize_plan = kc::resize_plan_create(in_h, in_w, h->H, h->W, h->C);
+      if (!h->resize_plan) return fail(h, KCVAE_ERR_CUDA, "preprocess_u8: could not allocate the span tables");
+    }
+    plan = h->resize_plan;
+  }
+  g_tag = "frontend";
+  if (kc::preprocess_u8(d_frames, batch, plan, (int64_t)batch * h->P, d_x, st))
+    return fail(h, KCVAE_ERR_CUDA, "preprocess_u8: could not allocate the row-pass scratch");
+  KC_CUDA(h, cudaPeekAtLastError());
+  return KCVAE_OK;
+}
+
+int kcvae_preprocess_u8(kcvae_handle h, const uint8_t* d_frames, int batch, int in_h, int in_w, float* d_x, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!d_frames || !d_x) return fail(h, KCVAE_ERR_INVALID, "preprocess_u8: null pointer");
+  KC_CUDA(h, cudaSetDevice(h->device));
+  return preprocess_impl(h, d_frames, batch, in_h, in_w, d_x, (cudaStream_t)stream);
+}
+
+// uint8 host frames -> device staging -> x_stage[0] (fp32 model input)
+static int stage_host_u8(kcvae_model* h, const uint8_t* h_frames, int batch, int in_h, int in_w, cudaStream_t st, const float** d_x) {
+  const size_t bytes = (size_t)batch * in_h * in_w * h->C;
+  if (bytes > h->u8_stage_bytes) {
+    if (h->u8_stage) { KC_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->u8_stage); h->u8_stage = nullptr; h->u8_stage_bytes = 0; }
+    KC_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->u8_stage), bytes));
+    h->u8_stage_bytes = bytes;
+  }
+  h->pend_src[0] = h->pend_src[1] = nullptr;     // a float prefetch in flight is abandoned
+#ifndef KCVAE_EMU
+  for (int i = 0; i < 2; ++i) if (h->copy_done[i]) KC_CUDA(h, cudaStreamWaitEvent(st, h->copy_done[i], 0));
+#endif
+  KC_CUDA(h, cudaMemcpyAsync(h->u8_stage, h_frames, bytes, cudaMemcpyHostToDevice, st));
+  KC_TRY(preprocess_impl(h, h->u8_stage, batch, in_h, in_w, h->x_stage[0], st));
+  *d_x = h->x_in = h->x_stage[0];
+  return KCVAE_OK;
+}
+
+int kcvae_score_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w, float* h_err, float* h_score,
+                        void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!h_frames || !h_score) return fail(h, KCVAE_ERR_INVALID, "score_host_u8: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_fwd(h, batch));
+  const float* d_x = nullptr;
+  KC_TRY(stage_host_u8(h, h_frames, batch, in_h, in_w, st, &d_x));
+  KC_TRY(kcvae_score(h, d_x, batch, h_err ? h->err_buf : nullptr, h->score_buf, nullptr, nullptr, stream));
+  if (h_err) KC_CUDA(h, cudaMemcpyAsync(h_err, h->err_buf, (size_t)batch * h->H * h->W * sizeof(float), cudaMemcpyDeviceToHost, st));
+  KC_CUDA(h, cudaMemcpyAsync(h_score, h->score_buf, (size_t)batch * sizeof(float), cudaMemcpyDeviceToHost, st));
+  KC_CUDA(h, cudaStreamSynchronize(st));
+  return KCVAE_OK;
+}
+
+int kcvae_train_step_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w, const float* h_eps,
+                             float* h_metrics, float* h_xhat, int tier, void* stream) {
+  KC_TRY(check_batch(h, batch));
+  if (!h_frames || !h_metrics) return fail(h, KCVAE_ERR_INVALID, "train_step_host_u8: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  KC_CUDA(h, cudaSetDevice(h->device));
+  KC_TRY(ensure_bwd(h, batch));
+  const float* d_x = nullptr;
+  KC_TRY(stage_host_u8(h, h_frames, batch, in_h, in_w, st, &d_x));
+  const float* eps = nullptr;
+  if (h_eps) {
+    KC_CUDA(h, cudaMemcpyAsync(h->eps_buf, h_eps, (size_t)batch * h->latent * sizeof(float), cudaMemcpyHostToDevice, st));
+    eps = h->eps_buf;
+  }
+  KC_TRY(step_impl(h, d_x, batch, eps, nullptr, h->metrics_dev, h->xhat, tier, 1, st));
+  KC_CUDA(h, cudaMemcpyAsync(h_metrics, h->metrics_dev, KCVAE_NUM_METRICS * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (h_xhat) KC_CUDA(h, cudaMemcpyAsync(h_xhat, h->xhat, (size_t)batch * h->P * sizeof(float), cudaMemcpyDeviceToHost, st));
   KC_CUDA(h, cudaStreamSynchronize(st));
   return KCVAE_OK;
 }

@@ -17,6 +17,7 @@
 // warps 2..5 = epilogue (TMEM lane groups (warp & 3)).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 #include <cuda.h>
 
@@ -69,6 +70,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
 }
 
 static void sum_partials(const float* partial, int nparts, int E, float* out, cudaStream_t st);
+
+// Development aid (-DKCVAE_TAIL_TIMING): every warp of CTA 0 accumulates the cycles it spends in each mbarrier
+// wait and its total time; the launcher prints them.  Compiled out of the product.
+#ifdef KCVAE_TAIL_TIMING
+__device__ long long g_tail_dbg[24 * 16];
+#define TAIL_TIMING_DECL long long tw_[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long tstart_ = clock64();
+#define TSPAN_BEGIN const long long ts_ = clock64();
+#define TSPAN_END(idx) tw_[idx] += clock64() - ts_;
+#define TWAIT(idx, bar, par) [&] { const long long t_ = clock64(); const bool r_ = mbar_wait(bar, par); tw_[idx] += clock64() - t_; return r_; }()
+#define TAIL_TIMING_DUMP if (blockIdx.x == 0 && lane == 0) { for (int i_ = 0; i_ < 14; ++i_) g_tail_dbg[warp * 16 + i_] = tw_[i_]; g_tail_dbg[warp * 16 + 14] = clock64() - tstart_; }
+#else
+#define TAIL_TIMING_DECL
+#define TSPAN_BEGIN
+#define TSPAN_END(idx)
+#define TWAIT(idx, bar, par) mbar_wait(bar, par)
+#define TAIL_TIMING_DUMP
+#endif
+
 
 struct OutConvParams {
   const __nv_bfloat16* wimg;  // [9 taps][CIN/16][2 chunks][NPAD][8] bf16 (tc_prep_out_weights)
@@ -270,6 +289,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TAIL_TIMING_DECL
 
   for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreadsD)
     reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
@@ -295,7 +315,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        if (!TWAIT(0, &empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
         const int n = t / (p.tiles_y * p.tiles_x);
         const int rem = t % (p.tiles_y * p.tiles_x);
         const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
@@ -311,8 +331,8 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int s = it % kStages, a = it & 1;
       const uint32_t ph = (it / kStages) & 1, aph = (it >> 1) & 1;
-      if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { if (leader) *p.error_flag = 1; break; }
-      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; break; }
+      if (!TWAIT(1, &tempty_bar[a], aph ^ 1)) { if (leader) *p.error_flag = 1; break; }
+      if (!TWAIT(2, &full_bar[s], ph)) { if (leader) *p.error_flag = 1; break; }
       fence_after_sync();
       const uint32_t tile_base = smem_u32(s_tile + s * STAGE);
 #pragma unroll 2
@@ -389,7 +409,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
           }
         }
         if (!waited) {
-          if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; }
+          if (!TWAIT(3, &tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; }
           fence_after_sync();
           waited = true;
         }
@@ -457,6 +477,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
       }
     }
   }
+  TAIL_TIMING_DUMP
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
@@ -1228,23 +1249,6 @@ constexpr int C2I_TSLOTS = 4;   // TMEM ring of 32-column accumulators
 constexpr int C2I_NV = 27;      // 9 taps x 3 channels
 constexpr uint32_t C2I_T_BYTES = C2I_NV * C2I_RING * 128 * 4;
 
-// Development aid (-DKCVAE_TAIL_TIMING): every warp of CTA 0 accumulates the cycles it spends in each mbarrier
-// wait and its total time; the launcher prints them.  Compiled out of the product.
-#ifdef KCVAE_TAIL_TIMING
-__device__ long long g_tail_dbg[16 * 16];
-#define TAIL_TIMING_DECL long long tw_[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long tstart_ = clock64();
-#define TSPAN_BEGIN const long long ts_ = clock64();
-#define TSPAN_END(idx) tw_[idx] += clock64() - ts_;
-#define TWAIT(idx, bar, par) [&] { const long long t_ = clock64(); const bool r_ = mbar_wait(bar, par); tw_[idx] += clock64() - t_; return r_; }()
-#define TAIL_TIMING_DUMP if (blockIdx.x == 0 && lane == 0) { for (int i_ = 0; i_ < 14; ++i_) g_tail_dbg[warp * 16 + i_] = tw_[i_]; g_tail_dbg[warp * 16 + 14] = clock64() - tstart_; }
-#else
-#define TAIL_TIMING_DECL
-#define TSPAN_BEGIN
-#define TSPAN_END(idx)
-#define TWAIT(idx, bar, par) mbar_wait(bar, par)
-#define TAIL_TIMING_DUMP
-#endif
-
 template <bool C2I>
 __global__ void __launch_bounds__(kThreadsT, 1)
 tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmapx, TailParams p) {
@@ -1724,6 +1728,23 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
+#ifdef KCVAE_TAIL_TIMING
+// KCVAE_TAIL_DBG=<kernel tag>: print the per-warp wait cycles of CTA 0 after that launch (synchronises the stream)
+static void tc_timing_dump(const char* tag, const char* const* names, int nwarps, double tiles_per_cta, cudaStream_t st) {
+  const char* e = std::getenv("KCVAE_TAIL_DBG");
+  if (!e || std::strcmp(e, tag) != 0) return;
+  cudaStreamSynchronize(st);
+  long long hd[24 * 16];
+  cudaMemcpyFromSymbol(hd, g_tail_dbg, sizeof(hd));
+  std::fprintf(stderr, "%s timing (CTA 0, cycles; tiles/CTA %.1f):\n", tag, tiles_per_cta);
+  for (int wv = 0; wv < nwarps; ++wv) {
+    std::fprintf(stderr, "  warp %2d total %9lld |", wv, hd[wv * 16 + 14]);
+    for (int i = 0; i < 14; ++i) if (hd[wv * 16 + i]) std::fprintf(stderr, " %s %lld", names[i], hd[wv * 16 + i]);
+    std::fprintf(stderr, "\n");
+  }
+}
+#endif
+
 bool tc_out_conv_supported(int Cin, int Cout) { return (Cin == 16 || Cin == 32) && Cout >= 1 && Cout <= 8; }
 
 size_t tc_out_weight_image_elems(int Cin) { return (size_t)9 * (Cin / 16) * 2 * NPAD * 8; }
@@ -1794,6 +1815,12 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
     cudaFuncSetAttribute(tc_out_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tc_out_dgrad_kernel<false><<<grid, kThreadsD, smem, st>>>(tmap, p);
   }
+#ifdef KCVAE_TAIL_TIMING
+  {
+    static const char* nm[14] = {"smem_empty", "tmem_empty", "tma_full", "tmem_full", "", "", "", "", "", "", "", "", "", ""};
+    tc_timing_dump("out_dgrad", nm, kThreadsD / 32, (double)p.num_tiles / grid, st);
+  }
+#endif
   if (chan_sum) {
     sum_partials(chan_partial, grid * 4 * kSubD, Cin, chan_sum, st);
   }
@@ -2016,17 +2043,9 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
     tc_tail_fused_kernel<false><<<grid, kThreadsT, smem, st>>>(tmap, tmapx, p);
   }
 #ifdef KCVAE_TAIL_TIMING
-  if (std::getenv("KCVAE_TAIL_DBG")) {
-    cudaStreamSynchronize(st);
-    long long hd[16 * 16];
-    cudaMemcpyFromSymbol(hd, g_tail_dbg, sizeof(hd));
+  {
     static const char* nm[14] = {"a3_empty", "a3_full", "Aempty", "Tempty", "a4_ready", "Bempty", "a4_free", "Afull", "Tfull", "Bfull", "x_full", "x_empty", "tmem_ld", "epi_math"};
-    std::fprintf(stderr, "tail timing (CTA 0, cycles; tiles/CTA %.1f):\n", (double)p.num_tiles / grid);
-    for (int wv = 0; wv < kThreadsT / 32; ++wv) {
-      std::fprintf(stderr, "  warp %2d total %9lld |", wv, hd[wv * 16 + 14]);
-      for (int i = 0; i < 14; ++i) if (hd[wv * 16 + i]) std::fprintf(stderr, " %s %lld", nm[i], hd[wv * 16 + i]);
-      std::fprintf(stderr, "\n");
-    }
+    tc_timing_dump("tail", nm, kThreadsT / 32, (double)p.num_tiles / grid, st);
   }
 #endif
   if (score) {

@@ -645,6 +645,45 @@ class AbstractCVAE:
                                              self._stream()), self._h)
         return out
 
+    # -- uint8 front end (src/data_loader.py:10-20, camera_streamer_qt.py:1296) ------------------
+    def _u8_dev(self, frames) -> torch.Tensor:
+        t = frames if isinstance(frames, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frames))
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[3] != self._img_shape()[2]:
+            raise ValueError(f"expected uint8 frames [B, h, w, {self._img_shape()[2]}], got {t.dtype} {tuple(t.shape)}")
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    def preprocess_u8(self, frames):
+        """uint8 NHWC frames of any size -> the model's fp32 input: ``tf.image.resize(frames / 255.,
+        image_size[:2], antialias=True)`` (only the cast when the size already matches)."""
+        t = self._u8_dev(frames)
+        H, W, Cc = self._img_shape()
+        out = self._empty(t.shape[0], H, W, Cc)
+        self._lib.check(self._lib.preprocess_u8(self._h, _ptr(t), t.shape[0], t.shape[1], t.shape[2], _ptr(out),
+                                                self._stream()), self._h)
+        return _wrap(out)
+
+    def score_host_u8(self, frames_host: torch.Tensor, score_host: Optional[torch.Tensor] = None,
+                      err_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """score_host fed with uint8 host frames [B,h,w,C]: a quarter of the H2D bytes, cast / resize on the GPU."""
+        assert frames_host.device.type == "cpu" and frames_host.dtype == torch.uint8 and frames_host.is_contiguous()
+        B, ih, iw, _ = frames_host.shape
+        out = score_host if score_host is not None else torch.empty(B, dtype=torch.float32)
+        self._lib.check(self._lib.score_host_u8(self._h, _ptr(frames_host), B, ih, iw, _ptr(err_host), _ptr(out),
+                                                self._stream()), self._h)
+        return out
+
+    def train_step_host_u8(self, frames_host: torch.Tensor, eps_host: Optional[torch.Tensor] = None,
+                           metrics_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.optimizer is None:
+            raise RuntimeError("You must compile your model before training/testing. Use `model.compile(optimizer=...)`.")
+        assert frames_host.device.type == "cpu" and frames_host.dtype == torch.uint8 and frames_host.is_contiguous()
+        B, ih, iw, _ = frames_host.shape
+        out = metrics_host if metrics_host is not None else torch.empty(_lib.NUM_METRICS, dtype=torch.float32)
+        self._push_hparams()
+        self._lib.check(self._lib.train_step_host_u8(self._h, _ptr(frames_host), B, ih, iw, _ptr(eps_host), _ptr(out), None,
+                                                     self.metric_tier, self._stream()), self._h)
+        return out
+
     def tc_status(self) -> int:
         """1 if the tcgen05 kernels are active, 0 if only the fp32 path runs; raises on a pipeline error."""
         return self._lib.check(self._lib.tc_status(self._h), self._h)

@@ -61,6 +61,37 @@ def evaluate_anomalies(model, config: dict, data, data_scale: dict, anomaly_thre
     }
 
 
+def output_anomalies(evaluation_data, anomaly_results: dict, data_scale: dict, output_path=None, anomaly_threshold: float = 3.0,
+                     filenames=None, model=None):
+    """do_anomaly_detection.py:118-198 without the plotting (and without the stray ``exit()`` at :157 that makes
+    the reference stop before it writes anything): uint8 error image, JET heat map, overlay and reconstruction
+    per frame (one kernel per batch) and the descending-z ranking.  Returns the arrays and the ranked
+    ``(name, z_score)`` rows; writes PNGs + ``anomaly_list.csv`` under ``output_path`` when given."""
+    import csv
+    import os
+    from .streaming import render_outputs
+    binding = model._lib if model is not None else None
+    r = render_outputs(anomaly_results['norm_errs'], anomaly_results['rec'], binding=binding)
+    out = {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
+    n = out['err'].shape[0]
+    names = list(filenames) if filenames is not None else [f'{i:06d}.png' for i in range(n)]
+    order = rank_anomalies(anomaly_results['z_scores'])
+    out['ranking'] = [(names[i], float(anomaly_results['z_scores'][i])) for i in order]
+    if output_path is not None:
+        from PIL import Image
+        for sub in ('err', 'heatmap', 'overlay', 'rec'):
+            os.makedirs(os.path.join(output_path, sub), exist_ok=True)
+        for i in range(n):
+            Image.fromarray(out['err'][i], mode='L').save(os.path.join(output_path, 'err', names[i]))
+            for sub in ('heatmap', 'overlay', 'rec'):
+                Image.fromarray(out[sub][i], mode='RGB').save(os.path.join(output_path, sub, names[i]))
+        with open(os.path.join(output_path, 'anomaly_list.csv'), 'w', newline='') as f:
+            w = csv.writer(f)
+            w.writerow(['orig_filepath', 'z_score'])
+            w.writerows(out['ranking'])
+    return out
+
+
 def rank_anomalies(z_scores: np.ndarray) -> np.ndarray:
     """Descending z-score order (do_anomaly_detection.py:190, dead code after exit() at :157)."""
     return np.argsort(-np.asarray(z_scores), kind='stable')
