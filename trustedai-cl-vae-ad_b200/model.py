@@ -134,20 +134,37 @@ class Sequential:
         print_fn(f"Total params: {self.count_params():,}")
         print_fn("_" * 65)
 
-    def save(self, path: str):
-        """``encoder.save(dir)`` / ``decoder.save(dir)`` (train.py:127-128).  Writes
-        ``<dir>/weights.npz`` keyed by Keras variable order + ``layers.json``; TensorFlow
-        SavedModel interop is the "next" row of SURVEY 8f."""
+    def save(self, path: str, tf_variables: bool = True):
+        """``encoder.save(dir)`` / ``decoder.save(dir)`` (train.py:127-128).  Writes ``<dir>/weights.npz`` keyed
+        by Keras variable order + ``layers.json`` and, unless ``tf_variables=False``, the same variables as a
+        TensorBundle under ``<dir>/variables/`` with the keys a Keras SavedModel uses (tf_bundle.py), readable with
+        ``tf.train.load_checkpoint`` on the TensorFlow side.  No ``saved_model.pb`` is written."""
         os.makedirs(path, exist_ok=True)
-        np.savez(os.path.join(path, "weights.npz"), **{f"{i:02d}": w for i, w in enumerate(self.get_weights())})
+        ws = self.get_weights()
+        np.savez(os.path.join(path, "weights.npz"), **{f"{i:02d}": w for i, w in enumerate(ws)})
         spec = [{"kind": l.kind, "name": l.name, "input_shape": list(l.input_shape),
                  "output_shape": list(l.output_shape)} for l in self.layers]
         with open(os.path.join(path, "layers.json"), "w") as f:
             json.dump({"name": self.name, "layers": spec, "variables": [v.name for v in self.variables]}, f, indent=1)
+        if tf_variables:
+            from .tf_bundle import keras_weights_to_bundle
+            keras_weights_to_bundle(os.path.join(path, "variables", "variables"), ws)
 
     def load(self, path: str):
-        z = np.load(os.path.join(path, "weights.npz"))
-        self.set_weights([z[k] for k in sorted(z.files)])
+        """Either this runtime's ``weights.npz`` or the ``variables/`` TensorBundle of a Keras SavedModel written by
+        the reference (``vae.encoder.save(dir)``): variables are matched by layer order, kernel before bias."""
+        npz = os.path.join(path, "weights.npz")
+        if os.path.exists(npz):
+            z = np.load(npz)
+            self.set_weights([z[k] for k in sorted(z.files)])
+            return
+        from .tf_bundle import keras_weights_from_bundle
+        ws = keras_weights_from_bundle(os.path.join(path, "variables", "variables"))
+        vs = self.variables
+        if len(ws) != len(vs) or any(tuple(w.shape) != v.shape for w, v in zip(ws, vs)):
+            raise ValueError(f"{path}: SavedModel variables {[tuple(w.shape) for w in ws]} do not match this "
+                             f"{self.name} {[v.shape for v in vs]} (config.yml differs from the checkpoint?)")
+        self.set_weights(ws)
 
 
 class History:
@@ -419,8 +436,6 @@ class AbstractCVAE:
         assert os.path.exists(encoder_path)
         decoder_path = os.path.join(model_path, "decoder")
         assert os.path.exists(decoder_path)
-        if os.path.exists(os.path.join(encoder_path, "saved_model.pb")):
-            raise NotImplementedError("TensorFlow SavedModel checkpoints need the TF->npz bridge (SURVEY 8f row 1)")
         self.encoder.load(encoder_path)
         self.decoder.load(decoder_path)
         opt = os.path.join(model_path, "optimizer.npz")
