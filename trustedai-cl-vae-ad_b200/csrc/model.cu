@@ -103,6 +103,10 @@ struct kcvae_model {
   int cap_fwd = 0, cap_bwd = 0, last_B = 0;
   std::vector<float*> act_e, act_d, g_act_e, g_act_d;
   float* x_stage[2] = {nullptr, nullptr};   // double-buffered H2D staging for the *_host entry points
+  // bf16 weight images of the tensor-core kernels are rebuilt only after the weights changed
+  uint64_t w_version = 1;                   // bumped by every writer of `w`
+  uint64_t img_version[4] = {0, 0, 0, 0};   // convT fwd, tail / out conv, out dgrad, convT dgrad
+  bool w_external = false;                  // the raw device pointer was handed out: never trust the cache
   kc::ResizePlan* resize_plan = nullptr;    // uint8 front end: span tables of the last (in_h, in_w) seen
   uint8_t* u8_stage = nullptr;              // H2D staging of uint8 host frames
   size_t u8_stage_bytes = 0;
@@ -170,6 +174,13 @@ namespace {
 int fail(kcvae_model* h, int code, const std::string& msg) {
   if (h) h->err = msg; else g_create_error = msg;
   return code;
+}
+
+// true when weight image k must be (re)built before use
+bool image_stale(kcvae_model* h, int k) {
+  if (!h->w_external && h->img_version[k] == h->w_version) return false;
+  h->img_version[k] = h->w_version;
+  return true;
 }
 
 void pad_before(int n_in, int& before) {  // TF SAME, k=3, s=2
@@ -444,10 +455,10 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
       // sub-pixel phase decomposition on tcgen05, bf16 output straight into the buffer the
       // output-layer kernels read (no fp32 copy of the 224x300x32 activation exists in this mode)
       pack_c8_bf16(a.in, (int64_t)B * a.Hi * a.Wi, a.Ci, h->a_prev8, st);
-      tc_prep_convT_weights(a.w, a.Co, a.Ci, h->wimg_convT, st);
+      if (image_stale(h, 0)) tc_prep_convT_weights(a.w, a.Co, a.Ci, h->wimg_convT, st);
       if ((!keep_last || h->fuse_train_tail) && tail_fusable(h, B)) {
         const int vo = h->vi_out();
-        tc_prep_tail_weights(h->wp(vo), h->C, h->dc[L], h->wimg_out, st);
+        if (image_stale(h, 1)) tc_prep_tail_weights(h->wp(vo), h->C, h->dc[L], h->wimg_out, st);
         g_tag = "dec.tail";
         const bool want_score = tail && tail->x && (tail->err || tail->score);
         if (tc_tail_fused(h->a_prev8, h->wimg_convT, h->wimg_out, a.bias, h->wp(vo + 1), want_score ? tail->x : nullptr, out,
@@ -479,6 +490,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   if (h->use_tc_out) {
     // tcgen05 implicit GEMM (tc_conv.cu): bf16 operands, fp32 accumulate in TMEM
     if (!last_is_bf16) cast_f32_to_bf16_planar(h->act_d[L], h->a_last_bf16, B, (int64_t)a.Hi * a.Wi, a.Ci, st);
+    h->img_version[1] = 0;   // this image shares its buffer with the fused tail's: always rebuilt on this (unfused) path
     tc_prep_out_weights(a.w, a.Co, a.Ci, h->wimg_out, st);
     if (tc_out_conv(h->a_last_bf16, h->wimg_out, a.bias, out, B, a.Hi, a.Wi, a.Ci, a.Co, apply_sigmoid, h->tc_error, st) == 0)
       return;
@@ -612,7 +624,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     bool done = false;
 #ifndef KCVAE_EMU
     if (h->use_tc_dgrad && h->use_tc_out) {  // tcgen05 paired-tap implicit GEMM (tc_conv.cu)
-      tc_prep_dgrad_weights(a.w, h->C, h->dc[L], h->wimg_dgrad, st);
+      if (image_stale(h, 2)) tc_prep_dgrad_weights(a.w, h->C, h->dc[L], h->wimg_dgrad, st);
       const bool s2d = h->use_tc_convT_bwd && h->use_tc_convT;
       // with the tensor-core Conv2DTranspose backward the gradient never exists in fp32: it is
       // written as bf16 space-to-depth and its channel sums (= that layer's bias gradient) come
@@ -639,7 +651,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
 #ifndef KCVAE_EMU
     if (l == L - 1 && tail_s2d) {
       bool ok = tc_convT_wgrad(h->g_s2d, h->a_prev8, h->gp(vi), h->partial, B, h->dh[l], h->dw[l], h->dc[l], h->tc_error, st) == 0;
-      tc_prep_convT_dgrad_weights(h->wp(vi), h->dc[l + 1], h->dc[l], h->wimg_convT_dgrad, st);
+      if (image_stale(h, 3)) tc_prep_convT_dgrad_weights(h->wp(vi), h->dc[l + 1], h->dc[l], h->wimg_convT_dgrad, st);
       ok = ok && tc_convT_dgrad(h->g_s2d, h->wimg_convT_dgrad, h->act_d[l], h->g_act_d[l], B, h->dh[l], h->dw[l], h->dc[l],
                                 h->tc_error, st) == 0;
       if (!ok) h->tc_failed = true;
@@ -771,6 +783,7 @@ int run_adam(kcvae_model* h, cudaStream_t st) {
   const double lr_t = (double)h->lr * std::sqrt(1.0 - std::pow(b2, (double)h->adam_t)) / (1.0 - std::pow(b1, (double)h->adam_t));
   g_tag = "optimizer";
   adam_update(h->w, h->g, h->m, h->v, h->nparams, (float)lr_t, (float)b1, (float)b2, 1e-7f, st);
+  ++h->w_version;
   return KCVAE_OK;
 }
 
@@ -785,12 +798,29 @@ int step_impl(kcvae_model* h, const float* d_x, int B, const float* d_eps, const
     add_noise(d_x, d_img_noise, (int64_t)B * h->P, 0.f, 0, 0, h->x_noisy, st);
     x = h->x_noisy;
   }
+#ifndef KCVAE_EMU
+  // tensor-core training configuration: the four bf16 weight images of this step in one launch
+  if (h->L >= 1 && h->use_tc_convT && h->use_tc_out && h->fuse_train_tail && h->use_tc_dgrad && h->use_tc_convT_bwd &&
+      h->wimg_dgrad && h->wimg_convT_dgrad && tail_fusable(h, B) &&
+      (h->w_external || h->img_version[0] != h->w_version || h->img_version[1] != h->w_version ||
+       h->img_version[2] != h->w_version || h->img_version[3] != h->w_version)) {
+    g_tag = "step";
+    tc_prep_all_weights(h->wp(h->vi_dec_convT(h->L - 1)), h->wp(h->vi_out()), h->dc[h->L - 1], h->dc[h->L], h->C, h->wimg_convT,
+                        h->wimg_out, h->wimg_dgrad, h->wimg_convT_dgrad, st);
+    for (int k = 0; k < 4; ++k) h->img_version[k] = h->w_version;
+  }
+  const bool ext = h->w_external;
+  h->w_external = false;          // the images built above are current for this step
+#endif
   float* xh = d_xhat ? d_xhat : h->xhat;
   run_forward(h, x, B, 1, d_eps, xh, st);
   cudaStream_t cs = (h->world > 1 && h->comm_stream) ? h->comm_stream : st;
   KC_TRY(run_stats(h, d_x, xh, B, tier, 1, st, cs));
   KC_TRY(run_backward(h, x, B, st, cs));
   if (h->tc_failed) return fail(h, KCVAE_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed; use precision fp32");
+#ifndef KCVAE_EMU
+  h->w_external = ext;
+#endif
   if (do_update) KC_TRY(run_adam(h, st));
   run_finalize(h, B, tier, d_metrics ? d_metrics : h->metrics_dev, st);
   return post(h);
@@ -931,6 +961,7 @@ int kcvae_set_weights(kcvae_handle h, const float* h_flat, int64_t n) {
   int64_t src = 0;
   for (const Var& v : h->vars) {
     KC_CUDA(h, cudaMemcpy(h->w + v.off, h_flat + src, v.n * sizeof(float), cudaMemcpyHostToDevice));
+    ++h->w_version;
     src += v.n;
   }
   return KCVAE_OK;
@@ -951,13 +982,17 @@ static int copy_out_flat(kcvae_handle h, const float* dev, float* h_flat, int64_
 int kcvae_get_weights(kcvae_handle h, float* h_flat, int64_t n) { return copy_out_flat(h, h ? h->w : nullptr, h_flat, n); }
 int kcvae_get_grads(kcvae_handle h, float* h_flat, int64_t n) { return copy_out_flat(h, h ? h->g : nullptr, h_flat, n); }
 
-float* kcvae_weights_device(kcvae_handle h) { return h ? h->w : nullptr; }
+float* kcvae_weights_device(kcvae_handle h) {
+  if (h) h->w_external = true;   // the caller may now write weights behind the library's back
+  return h ? h->w : nullptr;
+}
 float* kcvae_grads_device(kcvae_handle h) { return h ? h->g : nullptr; }
 
 int kcvae_init_glorot(kcvae_handle h, uint64_t seed, void* stream) {
   if (!h) return KCVAE_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   KC_CUDA(h, cudaSetDevice(h->device));
+  ++h->w_version;
   KC_CUDA(h, cudaMemsetAsync(h->w, 0, h->nparams * sizeof(float), st));
   uint32_t sid = 0;
   for (const Var& v : h->vars) {
@@ -1063,6 +1098,7 @@ int kcvae_broadcast_weights(kcvae_handle h, int root, void* stream) {
   (void)root; (void)stream;
   return fail(h, KCVAE_ERR_UNSUPPORTED, "emu: broadcast not emulated");
 #else
+  ++h->w_version;
   ncclResult_t r = g_nccl.Broadcast(h->w, h->w, (size_t)h->nparams, ncclFloat32, root, h->comm, (cudaStream_t)stream);
   if (r != ncclSuccess) return fail(h, KCVAE_ERR_NCCL, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r));
   return KCVAE_OK;

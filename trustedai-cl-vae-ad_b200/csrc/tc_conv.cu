@@ -232,7 +232,7 @@ tc_out_conv_kernel(const __grid_constant__ CUtensorMap tmap, OutConvParams p) {
 }
 
 // W [3,3,Cout,Cin] fp32 -> bf16 UMMA B-operand image [tap][ks][chunk(2)][n(NPAD)][8]
-__global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+__device__ __forceinline__ void tc_prep_out_weights_body(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
   const int KS = Cin / 16;
   const int total = 9 * KS * 2 * NPAD * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -249,7 +249,7 @@ __global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __
 
 // C2I image of the same weights (fused tail, Cout <= 3): B operand [N = 32 rows n = tap*Cout + co][K = 32 ci],
 // K-major canonical units [kchunk 4][n 32][8]; n = tap * 3 + co whatever Cout is (missing channels are zero columns)
-__global__ void tc_prep_tail_c2i_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+__device__ __forceinline__ void tc_prep_tail_c2i_weights_body(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * 32 * 8; i += gridDim.x * blockDim.x) {
     const int j = i % 8, n = (i / 8) % 32, kchunk = i / 256;
     const int ci = kchunk * 8 + j, tap = n / 3, co = n % 3;
@@ -484,7 +484,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
 }
 
 // W [3,3,Cout,Cin] fp32 -> paired-tap B image [pair][chunk(2)][n = ci (32)][8 = co]
-__global__ void tc_prep_dgrad_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+__device__ __forceinline__ void tc_prep_dgrad_weights_body(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
   const int total = 5 * 2 * NPAD_D * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int j = i % 8;
@@ -858,7 +858,7 @@ tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
 }
 
 // W [3,3,Cout=32,Cin<=8] fp32 -> five paired-tap B images [mma][chunk(2)][n = co][8 = ci]
-__global__ void tc_prep_convT_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+__device__ __forceinline__ void tc_prep_convT_weights_body(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
   // (kh,kw) of chunk 0 / chunk 1 of each MMA; -1 = zero weights
   const int taps[5][2] = {{8, 6}, {2, 0}, {7, 1}, {5, 3}, {4, -1}};
   const int total = 5 * 2 * 32 * 8;
@@ -1038,7 +1038,7 @@ tc_convT_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
 }
 
 // W [3,3,Cout=32,Cin<=8] fp32 -> dgrad B image [tap][ks][chunk(2)][n = ci (16)][8 = co]
-__global__ void tc_prep_convT_dgrad_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+__device__ __forceinline__ void tc_prep_convT_dgrad_weights_body(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
   const int total = 9 * 2 * 2 * 16 * 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int j = i % 8;
@@ -1049,6 +1049,32 @@ __global__ void tc_prep_convT_dgrad_weights_kernel(const float* w, int Cout, int
     const int co = ks * 16 + kc * 8 + j;
     const float v = (n < Cin && co < Cout) ? w[((int64_t)tap * Cout + co) * Cin + n] : 0.f;
     img[i] = __float2bfloat16(v);
+  }
+}
+
+__global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_out_weights_body(w, Cout, Cin, img); }
+__global__ void tc_prep_tail_c2i_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_tail_c2i_weights_body(w, Cout, Cin, img); }
+__global__ void tc_prep_dgrad_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_dgrad_weights_body(w, Cout, Cin, img); }
+__global__ void tc_prep_convT_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_convT_weights_body(w, Cout, Cin, img); }
+__global__ void tc_prep_convT_dgrad_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_convT_dgrad_weights_body(w, Cout, Cin, img); }
+
+// all four weight images of a training step in ONE launch (grid.y selects the image): the last Conv2DTranspose
+// forward, the fused tail's output convolution, the output-layer dgrad and the Conv2DTranspose dgrad
+struct PrepAllArgs {
+  const float* w_convT;   // [3,3,Clast,Cprev]
+  const float* w_out;     // [3,3,Cout,Clast]
+  int Cprev, Clast, Cout, tail_c2i;
+  __nv_bfloat16 *img_convT, *img_tail, *img_dgrad, *img_convT_dgrad;
+};
+__global__ void tc_prep_all_kernel(PrepAllArgs a) {
+  switch (blockIdx.y) {
+    case 0: tc_prep_convT_weights_body(a.w_convT, a.Clast, a.Cprev, a.img_convT); break;
+    case 1:
+      if (a.tail_c2i) tc_prep_tail_c2i_weights_body(a.w_out, a.Cout, a.Clast, a.img_tail);
+      else tc_prep_out_weights_body(a.w_out, a.Cout, a.Clast, a.img_tail);
+      break;
+    case 2: tc_prep_dgrad_weights_body(a.w_out, a.Cout, a.Clast, a.img_dgrad); break;
+    default: tc_prep_convT_dgrad_weights_body(a.w_convT, a.Clast, a.Cprev, a.img_convT_dgrad); break;
   }
 }
 
@@ -1981,6 +2007,15 @@ void tc_prep_tail_weights(const float* w, int Cout, int Cin, void* img, cudaStre
   ProfScope prof_("tc_prep_weights", st);
   ++g_launches;
   tc_prep_tail_c2i_weights_kernel<<<4, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+}
+void tc_prep_all_weights(const float* w_convT, const float* w_out, int Cprev, int Clast, int Cout, void* img_convT,
+                         void* img_tail, void* img_dgrad, void* img_convT_dgrad, cudaStream_t st) {
+  ProfScope prof_("tc_prep_weights", st);
+  ++g_launches;
+  PrepAllArgs a{w_convT, w_out, Cprev, Clast, Cout, tail_c2i(Cout) ? 1 : 0, reinterpret_cast<__nv_bfloat16*>(img_convT),
+                reinterpret_cast<__nv_bfloat16*>(img_tail), reinterpret_cast<__nv_bfloat16*>(img_dgrad),
+                reinterpret_cast<__nv_bfloat16*>(img_convT_dgrad)};
+  tc_prep_all_kernel<<<dim3(8, 4), 256, 0, st>>>(a);
 }
 size_t tc_tail_score_partial_floats(int B, int H, int W) { return (size_t)B * cdiv(H, TR) * cdiv(W, TW) * 4 * 3; }
 

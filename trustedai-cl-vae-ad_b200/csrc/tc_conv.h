@@ -49,6 +49,9 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg_bf16, const float* bias,
 bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W);
 // weight image the fused tail reads for its output convolution (layout depends on Cout); img = tc_out_weight_image_elems()
 void tc_prep_tail_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
+// the four weight images a training step needs (convT fwd, fused tail, out dgrad, convT dgrad) in one launch
+void tc_prep_all_weights(const float* w_convT, const float* w_out, int Cprev, int Clast, int Cout, void* img_convT,
+                         void* img_tail, void* img_dgrad, void* img_convT_dgrad, cudaStream_t st);
 size_t tc_tail_score_partial_floats(int B, int H, int W);
 // a_last_planar (optional): chunk-planar bf16 copy of the intermediate activation for the backward pass
 int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, const float* biasA, const float* biasB,
