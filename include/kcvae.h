@@ -178,6 +178,8 @@ int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, 
 int kcvae_preprocess_u8(kcvae_handle h, const uint8_t* d_frames, int batch, int in_h, int in_w,
                         float* d_x, void* stream);
 /* kcvae_score_host / kcvae_train_step_host fed with uint8 HOST frames (a quarter of the H2D bytes) */
+/* optional pipelining, as kcvae_prefetch_host: start the H2D copy of the NEXT call's uint8 frames now */
+int kcvae_prefetch_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w);
 int kcvae_score_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w,
                         float* h_err, float* h_score, void* stream);
 int kcvae_train_step_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w,

@@ -71,3 +71,25 @@ def test_u8_host_training_matches_float_host_training():
             x = torch.from_numpy(frames.astype(np.float32) / np.float32(255))
             outs.append(m.train_step_host(x, eps).numpy().copy())
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_u8_prefetch_pipeline_gives_the_same_scores():
+    cfg = O.readme_config()
+    m, _ = make(cfg, "cuda", precision="bf16")
+    rng = np.random.default_rng(13)
+    batches = [torch.from_numpy(rng.integers(0, 256, size=(3, 224, 300, 3), dtype=np.uint8)).pin_memory() for _ in range(5)]
+    want = [m.score_host_u8(b).numpy().copy() for b in batches]
+    got = []
+    m.prefetch_host_u8(batches[0])
+    for i, b in enumerate(batches):
+        if i + 1 < len(batches):
+            m.prefetch_host_u8(batches[i + 1])
+        got.append(m.score_host_u8(b).numpy().copy())
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    # a prefetch that is never consumed does not poison later calls (different pointer, different size)
+    m.prefetch_host_u8(batches[0])
+    other = torch.from_numpy(rng.integers(0, 256, size=(2, 100, 120, 3), dtype=np.uint8))
+    sc = m.score_host_u8(other).numpy()
+    ref = m.score(m.preprocess_u8(other), return_err=False)["score"].cpu().numpy()
+    assert np.array_equal(sc, ref)

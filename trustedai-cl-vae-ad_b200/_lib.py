@@ -73,6 +73,7 @@ _SIGS = {
     "kcvae_train_step_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int, _P]),
     "kcvae_score_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _P]),
     "kcvae_preprocess_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "kcvae_prefetch_host_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     "kcvae_score_host_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "kcvae_train_step_host_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int, _P]),
     "kcvae_stream_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),

@@ -108,8 +108,12 @@ struct kcvae_model {
   uint64_t img_version[4] = {0, 0, 0, 0};   // convT fwd, tail / out conv, out dgrad, convT dgrad
   bool w_external = false;                  // the raw device pointer was handed out: never trust the cache
   kc::ResizePlan* resize_plan = nullptr;    // uint8 front end: span tables of the last (in_h, in_w) seen
-  uint8_t* u8_stage = nullptr;              // H2D staging of uint8 host frames
-  size_t u8_stage_bytes = 0;
+  uint8_t* u8_stage[2] = {nullptr, nullptr};   // double-buffered H2D staging of uint8 host frames
+  size_t u8_stage_bytes[2] = {0, 0};
+  const void* u8_pend_src[2] = {nullptr, nullptr};   // host pointer whose prefetch sits in u8_stage[i]
+  size_t u8_pend_bytes[2] = {0, 0};
+  cudaEvent_t u8_copy_done[2] = {nullptr, nullptr}, u8_free[2] = {nullptr, nullptr};
+  int u8_last = 1;                             // slot the most recent step read
   const void* pend_src[2] = {nullptr, nullptr};   // host pointer whose prefetch sits in x_stage[i] (not yet consumed)
   int pend_batch[2] = {0, 0};
 #ifndef KCVAE_EMU
@@ -917,7 +921,13 @@ int kcvae_destroy(kcvae_handle h) {
                  h->metrics_dev};
   for (float* p : fl) if (p) cudaFree(p);
   kc::resize_plan_free(h->resize_plan);
-  if (h->u8_stage) cudaFree(h->u8_stage);
+  for (int i = 0; i < 2; ++i) {
+    if (h->u8_stage[i]) cudaFree(h->u8_stage[i]);
+#ifndef KCVAE_EMU
+    if (h->u8_copy_done[i]) cudaEventDestroy(h->u8_copy_done[i]);
+    if (h->u8_free[i]) cudaEventDestroy(h->u8_free[i]);
+#endif
+  }
   if (h->a_last_bf16) cudaFree(h->a_last_bf16);
   if (h->relu_bits) cudaFree(h->relu_bits);
   if (h->wimg_out) cudaFree(h->wimg_out);
@@ -1349,22 +1359,79 @@ int kcvae_preprocess_u8(kcvae_handle h, const uint8_t* d_frames, int batch, int 
   return preprocess_impl(h, d_frames, batch, in_h, in_w, d_x, (cudaStream_t)stream);
 }
 
-// uint8 host frames -> device staging -> x_stage[0] (fp32 model input)
+static int u8_slot_reserve(kcvae_model* h, int slot, size_t bytes, cudaStream_t waiter) {
+  if (bytes > h->u8_stage_bytes[slot]) {
+    if (h->u8_stage[slot]) { KC_CUDA(h, cudaDeviceSynchronize()); cudaFree(h->u8_stage[slot]); h->u8_stage[slot] = nullptr; h->u8_stage_bytes[slot] = 0; }
+    KC_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->u8_stage[slot]), bytes));
+    h->u8_stage_bytes[slot] = bytes;
+  }
+#ifndef KCVAE_EMU
+  if (h->u8_free[slot]) KC_CUDA(h, cudaStreamWaitEvent(waiter, h->u8_free[slot], 0));   // the cast that last read this slot
+#else
+  (void)waiter;
+#endif
+  return KCVAE_OK;
+}
+
+// uint8 host frames -> device staging -> x_stage[0] (fp32 model input).  A copy started by kcvae_prefetch_host_u8
+// for the same pointer is only waited for.
 static int stage_host_u8(kcvae_model* h, const uint8_t* h_frames, int batch, int in_h, int in_w, cudaStream_t st, const float** d_x) {
   const size_t bytes = (size_t)batch * in_h * in_w * h->C;
-  if (bytes > h->u8_stage_bytes) {
-    if (h->u8_stage) { KC_CUDA(h, cudaStreamSynchronize(st)); cudaFree(h->u8_stage); h->u8_stage = nullptr; h->u8_stage_bytes = 0; }
-    KC_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->u8_stage), bytes));
-    h->u8_stage_bytes = bytes;
-  }
   h->pend_src[0] = h->pend_src[1] = nullptr;     // a float prefetch in flight is abandoned
 #ifndef KCVAE_EMU
   for (int i = 0; i < 2; ++i) if (h->copy_done[i]) KC_CUDA(h, cudaStreamWaitEvent(st, h->copy_done[i], 0));
 #endif
-  KC_CUDA(h, cudaMemcpyAsync(h->u8_stage, h_frames, bytes, cudaMemcpyHostToDevice, st));
-  KC_TRY(preprocess_impl(h, h->u8_stage, batch, in_h, in_w, h->x_stage[0], st));
+  int slot = -1;
+  for (int i = 0; i < 2; ++i)
+    if (h->u8_pend_src[i] == h_frames && h->u8_pend_bytes[i] == bytes) slot = i;
+  if (slot >= 0) {
+#ifndef KCVAE_EMU
+    KC_CUDA(h, cudaStreamWaitEvent(st, h->u8_copy_done[slot], 0));
+#endif
+    h->u8_pend_src[slot] = nullptr;
+  } else {
+    slot = h->u8_pend_src[0] ? 1 : 0;            // never a slot that holds an unconsumed prefetch
+    if (h->u8_pend_src[slot]) {                  // both claimed: drop that prefetch once it has landed
+#ifndef KCVAE_EMU
+      KC_CUDA(h, cudaStreamWaitEvent(st, h->u8_copy_done[slot], 0));
+#endif
+      h->u8_pend_src[slot] = nullptr;
+    }
+    KC_TRY(u8_slot_reserve(h, slot, bytes, st));
+    KC_CUDA(h, cudaMemcpyAsync(h->u8_stage[slot], h_frames, bytes, cudaMemcpyHostToDevice, st));
+  }
+  KC_TRY(preprocess_impl(h, h->u8_stage[slot], batch, in_h, in_w, h->x_stage[0], st));
+#ifndef KCVAE_EMU
+  if (!h->u8_free[slot]) KC_CUDA(h, cudaEventCreateWithFlags(&h->u8_free[slot], cudaEventDisableTiming));
+  KC_CUDA(h, cudaEventRecord(h->u8_free[slot], st));
+#endif
+  h->u8_last = slot;
   *d_x = h->x_in = h->x_stage[0];
   return KCVAE_OK;
+}
+
+int kcvae_prefetch_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w) {
+  KC_TRY(check_batch(h, batch));
+  if (!h_frames || in_h <= 0 || in_w <= 0) return fail(h, KCVAE_ERR_INVALID, "prefetch_host_u8: invalid arguments");
+#ifdef KCVAE_EMU
+  return KCVAE_OK;   // the emulator copies inline
+#else
+  KC_CUDA(h, cudaSetDevice(h->device));
+  if (!h->copy_stream) {
+    KC_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) KC_CUDA(h, cudaEventCreateWithFlags(&h->copy_done[i], cudaEventDisableTiming));
+  }
+  int slot = 1 - h->u8_last;
+  if (h->u8_pend_src[slot]) slot = 1 - slot;
+  if (h->u8_pend_src[slot]) return fail(h, KCVAE_ERR_INVALID, "prefetch_host_u8: two prefetches already pending");
+  const size_t bytes = (size_t)batch * in_h * in_w * h->C;
+  KC_TRY(u8_slot_reserve(h, slot, bytes, h->copy_stream));
+  KC_CUDA(h, cudaMemcpyAsync(h->u8_stage[slot], h_frames, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  if (!h->u8_copy_done[slot]) KC_CUDA(h, cudaEventCreateWithFlags(&h->u8_copy_done[slot], cudaEventDisableTiming));
+  KC_CUDA(h, cudaEventRecord(h->u8_copy_done[slot], h->copy_stream));
+  h->u8_pend_src[slot] = h_frames; h->u8_pend_bytes[slot] = bytes;
+  return KCVAE_OK;
+#endif
 }
 
 int kcvae_score_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w, float* h_err, float* h_score,

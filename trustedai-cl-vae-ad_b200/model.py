@@ -677,6 +677,12 @@ class AbstractCVAE:
                                                 self._stream()), self._h)
         return _wrap(out)
 
+    def prefetch_host_u8(self, frames_host: torch.Tensor):
+        """Start copying the NEXT call's (pinned) uint8 host frames while the current call computes."""
+        assert frames_host.device.type == "cpu" and frames_host.dtype == torch.uint8 and frames_host.is_contiguous()
+        B, ih, iw, _ = frames_host.shape
+        self._lib.check(self._lib.prefetch_host_u8(self._h, _ptr(frames_host), B, ih, iw), self._h)
+
     def score_host_u8(self, frames_host: torch.Tensor, score_host: Optional[torch.Tensor] = None,
                       err_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """score_host fed with uint8 host frames [B,h,w,C]: a quarter of the H2D bytes, cast / resize on the GPU."""
