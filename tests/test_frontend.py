@@ -77,3 +77,28 @@ def test_emu_stream_score():
 
 def test_emu_render_outputs():
     FC.case_render("emu")
+
+
+def test_device_data_queue_follows_the_camera_tools_dataqueue():
+    """camera_streamer_qt.py:61-81 semantics (restated: capacity copies of the first sample, append advances the
+    index first) and the :1342 stacking with the replay buffer, through one continual-learning step."""
+    from kcvae_testlib import make, pkg, small_config
+    cfg = small_config()
+    H, W, C = cfg["data"]["image_size"]
+    rng = np.random.default_rng(4)
+    frames = rng.random((6, H, W, C), dtype=np.float32)
+    replay = rng.random((2, H, W, C), dtype=np.float32)
+    q = pkg.DeviceDataQueue(frames[0], 3, replay_buffer=replay)
+    ref = [frames[0].copy() for _ in range(3)]
+    idx = 0
+    for f in frames[1:]:
+        q.append(f)
+        idx = (idx + 1) % 3
+        ref[idx] = f
+        assert q._idx == idx and np.array_equal(q.get().numpy(), f)
+    assert np.array_equal(q.to_numpy(), np.array(ref))
+    assert np.array_equal(q.stacked().numpy(), np.vstack((np.array(ref), replay)))
+    m, _ = make(cfg, "emu")
+    m.compile(optimizer=pkg.Adam(learning_rate=1e-3))
+    loss, r_img = m.train_step_and_run(q.stacked())            # :1345
+    assert r_img[q._idx].shape == (H, W, C) and np.isfinite(float(loss["loss"]))   # :1347

@@ -7,4 +7,4 @@ from .model import (AbstractCVAE, BetaAnnealingCallback, Callback, KTensor, Kurt
                     KurtosisSingleCVAE)
 from .optimizers import Adam  # noqa: F401
 from .scoring import evaluate_anomalies, get_data_scale, output_anomalies, rank_anomalies  # noqa: F401
-from .streaming import StreamingAnomalyScore, render_outputs  # noqa: F401
+from .streaming import DeviceDataQueue, StreamingAnomalyScore, render_outputs  # noqa: F401

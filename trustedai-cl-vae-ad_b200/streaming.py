@@ -84,6 +84,44 @@ class StreamingAnomalyScore:
             pass
 
 
+class DeviceDataQueue:
+    """The camera tool's ``DataQueue`` (camera_streamer_qt.py:61-81) kept on the GPU together with the replay
+    buffer it is stacked with before every continual-learning step (:1341-1345): one preallocated
+    ``[capacity + n_replay, H, W, C]`` device tensor, so ``train_step_and_run(queue.stacked())`` uploads nothing
+    but the newest frame.  Same semantics: initialised with ``capacity`` copies of the first sample, ``append``
+    advances ``_idx`` first and overwrites that slot, ``to_numpy`` returns the slots in storage order."""
+
+    def __init__(self, data_sample, capacity: int, replay_buffer=None, device=None):
+        assert capacity > 0
+        first = torch.as_tensor(np.asarray(data_sample.cpu() if isinstance(data_sample, torch.Tensor) else data_sample),
+                                dtype=torch.float32)
+        n_rep = 0 if replay_buffer is None else int(replay_buffer.shape[0])
+        self._buf = torch.empty((capacity + n_rep,) + tuple(first.shape), dtype=torch.float32, device=device)
+        self._buf[:capacity] = first.to(self._buf.device)
+        if n_rep:
+            self._buf[capacity:] = torch.as_tensor(np.asarray(replay_buffer), dtype=torch.float32).to(self._buf.device)
+        self._idx = 0
+        self._capacity = capacity
+
+    def append(self, x):
+        self._increment()
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x), dtype=torch.float32)
+        self._buf[self._idx].copy_(t.as_subclass(torch.Tensor), non_blocking=True)
+
+    def _increment(self):
+        self._idx = (self._idx + 1) % self._capacity
+
+    def get(self):
+        return self._buf[self._idx]
+
+    def stacked(self):
+        """np.vstack((inf_buffer.to_numpy(), replay_buffer)) of :1342, as a device view (no copy)."""
+        return self._buf
+
+    def to_numpy(self):
+        return self._buf[:self._capacity].cpu().numpy()
+
+
 def render_outputs(norm_err=None, rec=None, device=None, binding: Optional[_lib.Binding] = None) -> dict:
     """``norm_err`` [B,H,W] in [0,1] and / or ``rec`` [B,H,W,C] in [0,1] -> uint8 tensors:
     ``err`` = round(255 norm_err), ``heatmap`` = cv2.applyColorMap(err, COLORMAP_JET) (OpenCV's channel order),
