@@ -38,7 +38,7 @@ constexpr int MT = (TR * PW) / 128;        // 8 M-tiles of 128 padded-row positi
 constexpr int NPAD = 16;                   // UMMA N (Cout padded)
 constexpr int kStages = 2;
 constexpr int kThreads = 192;
-constexpr int kSubD = 4;                   // tc_out_dgrad: epilogue warps per TMEM lane group
+constexpr int kSubD = 2;                   // tc_out_dgrad: epilogue warps per TMEM lane group
 constexpr int kThreadsD = 64 + 4 * kSubD * 32;
 constexpr int kThreadsT = 64 + 8 * 32 + 4 * 32;   // fused tail: TMA, MMA, 8 phase-A epilogue warps, 4 phase-B epilogue warps
 constexpr int kThreadsE = 320;            // kernels with a per-tile epilogue: 2 + 8 warps (two epilogue warps per TMEM lane group)
@@ -286,6 +286,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* s_tile = smem;
   unsigned char* s_w = smem + kStages * STAGE;
+  unsigned char* s_tr = s_w + WB;                     // 2 KB per epilogue warp: transposes the bf16 stores
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -415,15 +416,20 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
         }
         const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MT * NPAD_D + mt * NPAD_D);
         float4* o = (live && p.g_out) ? reinterpret_cast<float4*>(p.g_out + pix * p.Cin) : nullptr;
-        uint4* o2 = nullptr;
-        if (live && p.g_s2d) {
-          const int64_t lp = ((int64_t)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (ox >> 1);
-          o2 = reinterpret_cast<uint4*>(p.g_s2d + (lp * 4 + ((oy & 1) * 2 + (ox & 1))) * p.Cin);
-        }
+        // bf16 space-to-depth output: every lane holds the 64 bytes of ITS pixel; stored as they are, one STG.128
+        // touches 32 half-filled sectors in 16 lines and the L1 store path (about one partial sector every two
+        // cycles) becomes the bottleneck of the whole kernel.  The four 16-byte chunks go through a per-warp
+        // shared-memory scratch instead, so that lane L stores chunk L%4 of pixel L/4 + 8k: four full 128-byte lines
+        // per instruction.
+        uint4* tr = reinterpret_cast<uint4*>(s_tr + (warp - 2) * 2048);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float v[16];
+          { TSPAN_BEGIN
           tmem_ld16(ta + 16 * hh, v);       // whole warp (sync.aligned), dead lanes discard
+          { uint32_t sink_; asm volatile("mov.b32 %0, %1;" : "=r"(sink_) : "f"(v[0] + v[15])); (void)sink_; }
+          TSPAN_END(4) }
+          TSPAN_BEGIN
 #pragma unroll
           for (int gg = 0; gg < 2; ++gg) {
             const int g = hh * 2 + gg;
@@ -447,17 +453,33 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
                 o[g * 2] = make_float4(y[0], y[1], y[2], y[3]);
                 o[g * 2 + 1] = make_float4(y[4], y[5], y[6], y[7]);
               }
-              if (o2) {
+              if (p.g_s2d) {
                 uint32_t w4[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   __nv_bfloat162 b2 = __floats2bfloat162_rn(y[2 * e], y[2 * e + 1]);
                   w4[e] = *reinterpret_cast<uint32_t*>(&b2);
                 }
-                o2[g] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                tr[lane * 4 + (g ^ ((lane >> 1) & 3))] = make_uint4(w4[0], w4[1], w4[2], w4[3]);   // conflict-free both ways
               }
             }
           }
+          TSPAN_END(5)
+        }
+        if (p.g_s2d) {
+          __syncwarp();
+          const int cch = lane & 3;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int P = (lane >> 2) + 8 * kk;               // column of this row whose chunk this lane stores
+            const uint4 u = tr[P * 4 + (cch ^ ((P >> 1) & 3))];
+            const int oxp = tx * TW + P;
+            if (P < TW && oy < p.H && oxp < p.W) {
+              const int64_t lp = ((int64_t)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (oxp >> 1);
+              reinterpret_cast<uint4*>(p.g_s2d + (lp * 4 + ((oy & 1) * 2 + (oxp & 1))) * p.Cin)[cch] = u;
+            }
+          }
+          __syncwarp();                                       // scratch is reused by the next M-tile
         }
       }
       if (!waited) {
@@ -1830,7 +1852,7 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   p.num_tiles = B * p.tiles_y * p.tiles_x;
   p.error_flag = error_flag;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  const size_t smem = (size_t)kStages * ((size_t)NPIX * 16 + 128) + (size_t)5 * 2 * NPAD_D * 16;
+  const size_t smem = (size_t)kStages * ((size_t)NPIX * 16 + 128) + (size_t)5 * 2 * NPAD_D * 16 + (size_t)4 * kSubD * 2048;
   ProfScope prof_("tc_out_dgrad", st);
   ++g_launches;
   p.chan_partial = chan_sum ? chan_partial : nullptr;
@@ -1843,7 +1865,7 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   }
 #ifdef KCVAE_TAIL_TIMING
   {
-    static const char* nm[14] = {"smem_empty", "tmem_empty", "tma_full", "tmem_full", "", "", "", "", "", "", "", "", "", ""};
+    static const char* nm[14] = {"smem_empty", "tmem_empty", "tma_full", "tmem_full", "tmem_ld", "math_store", "", "", "", "", "", "", "", ""};
     tc_timing_dump("out_dgrad", nm, kThreadsD / 32, (double)p.num_tiles / grid, st);
   }
 #endif
