@@ -134,7 +134,7 @@ struct kcvae_model {
   bool fuse_train_tail = false;  // training forward: fused tail that also stores the activation for the backward
   bool tc_failed = false;        // a tensor-core launcher could not run (tensor map encode): the step is invalid
   bool use_tc_out = false, use_tc_dgrad = false, use_tc_convT = false, use_tc_convT_bwd = false;
-  void* g_s2d = nullptr;         // bf16 space-to-depth d loss / d a_last [B,H/2,W/2,4,32]
+  void* g_s2d = nullptr;         // bf16 space-to-depth d loss / d a_last, chunk-planar [B][4][4][H/2][W/2][8]
   void* wimg_convT_dgrad = nullptr;
   void* a_prev8 = nullptr;       // bf16 input of the last Conv2DTranspose s2, NHWC padded to 8 channels
   void* wimg_convT = nullptr;

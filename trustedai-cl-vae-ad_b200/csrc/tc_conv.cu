@@ -268,7 +268,7 @@ struct OutDgradParams {
   const __nv_bfloat16* mask;   // forward activation a (chunk-planar bf16, Cin channels)
   const uint32_t* relu_bits;   // [B,H,W] bit c = (a[.., c] > 0); when set it replaces the reads of `mask`
   float* g_out;                // [B,H,W,Cin] fp32 (or nullptr)
-  __nv_bfloat16* g_s2d;        // [B,H/2,W/2,4,Cin] bf16 space-to-depth (or nullptr): parity (y&1)*2+(x&1)
+  __nv_bfloat16* g_s2d;        // bf16 space-to-depth, chunk-planar [B][parity 4][Cin/8][H/2][W/2][8] (or nullptr): parity (y&1)*2+(x&1)
   float* chan_partial;         // [grid*4][32] per-warp channel sums of g (bias gradient of the producer) or nullptr
   int B, H, W, Cin;
   int tiles_y, tiles_x, num_tiles;
@@ -468,16 +468,18 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
         }
         if (p.g_s2d) {
           __syncwarp();
-          const int cch = lane & 3;
+          // chunk-planar space-to-depth: plane (parity, 8-channel chunk) holds one 16-byte unit per low-res pixel, so
+          // the pixels of one column parity form a contiguous run; lanes 0-15 / 16-31 store the even / odd run of chunk kk
+          const int xp = lane >> 4, P = 2 * (lane & 15) + xp;   // column of this row whose chunk this lane stores
+          const int oxp = tx * TW + P;
+          const bool ok = P < TW && oy < p.H && oxp < p.W;
+          const int64_t hw = (int64_t)(p.H >> 1) * (p.W >> 1);
+          uint4* gdst = reinterpret_cast<uint4*>(p.g_s2d) + ((int64_t)n * 16 + ((oy & 1) * 2 + (oxp & 1)) * 4) * hw +
+                        (int64_t)(oy >> 1) * (p.W >> 1) + (oxp >> 1);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const int P = (lane >> 2) + 8 * kk;               // column of this row whose chunk this lane stores
-            const uint4 u = tr[P * 4 + (cch ^ ((P >> 1) & 3))];
-            const int oxp = tx * TW + P;
-            if (P < TW && oy < p.H && oxp < p.W) {
-              const int64_t lp = ((int64_t)n * (p.H >> 1) + (oy >> 1)) * (p.W >> 1) + (oxp >> 1);
-              reinterpret_cast<uint4*>(p.g_s2d + (lp * 4 + ((oy & 1) * 2 + (oxp & 1))) * p.Cin)[cch] = u;
-            }
+            const uint4 u = tr[P * 4 + (kk ^ ((P >> 1) & 3))];
+            if (ok) gdst[kk * hw] = u;
           }
           __syncwarp();                                       // scratch is reused by the next M-tile
         }
@@ -976,7 +978,7 @@ tc_convT_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
         mbar_expect_tx(&full_bar[s], GT_BYTES);
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-          tma_load_4d(smem + s * STAGE + c * CHD, &tmap, &full_bar[s], c * 8, tx * TW, ty * TRD, n);
+          tma_load_3d(smem + s * STAGE + c * CHD, &tmap, &full_bar[s], tx * TW * 8, ty * TRD, n * 16 + c);
       }
     }
   } else if (warp == 1) {
@@ -1147,7 +1149,7 @@ tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
         mbar_expect_tx(&full_bar[s], GT_BYTES);
 #pragma unroll
         for (int c = 0; c < 16; ++c)
-          tma_load_4d(smem + s * STAGE + AP_BYTES + c * CHD, &tmap, &full_bar[s], c * 8, tx * TW, ty * TRD, n);
+          tma_load_3d(smem + s * STAGE + AP_BYTES + c * CHD, &tmap, &full_bar[s], tx * TW * 8, ty * TRD, n * 16 + c);
       }
     }
   } else if (warp == 1) {
@@ -1952,14 +1954,16 @@ bool tc_convT_bwd_supported(int Cin, int Cout, int h, int w) { return Cin >= 1 &
 size_t tc_convT_dgrad_weight_image_elems() { return (size_t)9 * 2 * 2 * 16 * 8; }
 size_t tc_convT_wgrad_partial_floats(int Cin) { return (size_t)kNumSMs * 9 * 32 * Cin; }
 
+// tensor map of the chunk-planar space-to-depth gradient [B*16 planes][h][w*8]: box = GROWS rows of PW pixels
+// (512 contiguous bytes each) of one plane -> the [pixel] x 16 B chunk plane the MMAs read
 static int make_s2d_map(CUtensorMap* tmap, const void* g_s2d, int B, int h, int w) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
-  const cuuint64_t gdim[4] = {128, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
-  const cuuint64_t gstr[3] = {256, (cuuint64_t)w * 256, (cuuint64_t)h * w * 256};
-  const cuuint32_t box[4] = {8, PW, GROWS, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g_s2d), gdim, gstr, box, estr,
+  const cuuint64_t gdim[3] = {(cuuint64_t)w * 8, (cuuint64_t)h, (cuuint64_t)B * 16};
+  const cuuint64_t gstr[2] = {(cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
+  const cuuint32_t box[3] = {PW * 8, GROWS, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(g_s2d), gdim, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 2;

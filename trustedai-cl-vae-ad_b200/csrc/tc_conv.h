@@ -19,7 +19,7 @@ int tc_out_conv(const void* act_bf16, const void* wimg_bf16, const float* bias, 
 bool tc_out_dgrad_supported(int Cin, int Cout);
 size_t tc_dgrad_weight_image_elems();
 void tc_prep_dgrad_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
-// g_out fp32 NHWC and/or g_s2d bf16 space-to-depth [B,H/2,W/2,4,Cin] (either may be nullptr)
+// g_out fp32 NHWC and/or g_s2d bf16 space-to-depth, chunk-planar [B][4 parities][Cin/8][H/2][W/2][8] (either may be nullptr)
 // chan_sum [Cin] (optional) = sum over all pixels of g = bias gradient of the producing layer;
 // chan_partial >= 148*8*32 floats of scratch
 // relu_bits (optional, [B,H,W] uint32 written by tc_tail_fused): replaces the reads of mask_bf16
