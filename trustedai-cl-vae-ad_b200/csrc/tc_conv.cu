@@ -321,7 +321,7 @@ tc_out_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutDgradParams p) 
         const int rem = t % (p.tiles_y * p.tiles_x);
         const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
         mbar_expect_tx(&full_bar[s], TILE_BYTES);
-        tma_load_4d(s_tile + s * STAGE, &tmap, &full_bar[s], 0, tx * TW - 1, ty * TR - 1, n);
+        tma_load_3d(s_tile + s * STAGE, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TR - 1, n);
       }
     }
   } else if (warp == 1) {
@@ -779,7 +779,7 @@ tc_convT_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTParams p) {
         const int rem = t % (p.tiles_y * p.tiles_x);
         const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
         mbar_expect_tx(&full_bar[s], TILE_BYTES);
-        tma_load_4d(s_tile + s * STAGE, &tmap, &full_bar[s], 0, tx * TW - 1, ty * TR - 1, n);
+        tma_load_3d(s_tile + s * STAGE, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TR - 1, n);
       }
     }
   } else if (warp == 1) {
@@ -1356,7 +1356,7 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         const int rem = t % (p.tiles_y * p.tiles_x);
         const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
         mbar_expect_tx(&a3_full[s], A3_BYTES);
-        tma_load_4d(s_a3 + s * A3_STAGE, &tmap, &a3_full[s], 0, (tx * TW) / 2 - 2, (ty * TR) / 2 - 2, n);
+        tma_load_3d(s_a3 + s * A3_STAGE, &tmap, &a3_full[s], ((tx * TW) / 2 - 2) * 8, (ty * TR) / 2 - 2, n);
         if (p.x) {   // the frame tile lands a whole tile ahead of the epilogue that compares against it
           if (!TWAIT(11, &x_empty[s], ((it >> 1) & 1) ^ 1)) { *p.error_flag = 1; break; }
           mbar_expect_tx(&x_full[s], (uint32_t)(p.xrow * TR * 4));
@@ -1815,6 +1815,19 @@ static CUresult make_planar_tmap(CUtensorMap* tmap, const void* act, int B, int 
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
 
+// tensor map of a bf16 NHWC tensor padded to 8 channels (one 16-byte unit per pixel) seen as [B][H][W*8]:
+// box = `rows` rows of `cols` pixels, each row cols*16 contiguous bytes (a 4-D {8, W, H, B} map moves the same box as
+// rows*cols separate 16-byte pieces)
+static CUresult make_c8_tmap(CUtensorMap* tmap, const void* t8, int B, int H, int W, int cols, int rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  const cuuint64_t gdim[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint32_t box[3] = {(cuuint32_t)cols * 8, (cuuint32_t)rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(t8), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
 void tc_prep_out_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
   ProfScope prof_("tc_prep_weights", st);
   ++g_launches;
@@ -1837,13 +1850,7 @@ int tc_out_dgrad(const void* dl8_bf16, const void* wimg, const void* mask_bf16, 
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
   CUtensorMap tmap;
-  const cuuint64_t gdim[4] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  const cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  const cuuint32_t box[4] = {8, PW, PR, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dl8_bf16), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = make_c8_tmap(&tmap, dl8_bf16, B, H, W, PW, PR);
   if (r != CUDA_SUCCESS) return 2;
   OutDgradParams p{};
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
@@ -1926,13 +1933,7 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg, const float* bias, void
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return 1;
   CUtensorMap tmap;
-  const cuuint64_t gdim[4] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
-  const cuuint64_t gstr[3] = {16, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
-  const cuuint32_t box[4] = {8, PW, PR, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in8_bf16), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = make_c8_tmap(&tmap, in8_bf16, B, h, w, PW, PR);
   if (r != CUDA_SUCCESS) return 2;
   ConvTParams p{};
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
@@ -2055,13 +2056,7 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
   if (!enc) return 1;
   const int h = H / 2, w = W / 2;
   CUtensorMap tmap;
-  const cuuint64_t gdim[4] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
-  const cuuint64_t gstr[3] = {16, (cuuint64_t)w * 16, (cuuint64_t)h * w * 16};
-  const cuuint32_t box[4] = {8, PA, A3ROWS, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in8_bf16), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = make_c8_tmap(&tmap, in8_bf16, B, h, w, PA, A3ROWS);
   if (r != CUDA_SUCCESS) return 2;
   TailParams p{};
   p.wimgA = reinterpret_cast<const __nv_bfloat16*>(wimgA);
