@@ -12,7 +12,7 @@ namespace kc {
 // ======================================================================= image statistics
 constexpr int kStatBlocks = kNumSMs * 8;
 constexpr int kStatSlots = 16;  // se, xhx, xh, ex, std, min, max, -, then 8 per-channel sums of dlogit
-size_t image_stats_partial_doubles() { return (size_t)kStatBlocks * kStatSlots; }
+size_t image_stats_partial_doubles() { return (size_t)kStatBlocks * kStatSlots + 1; }   // + the ticket of the pixel kernel (zero between launches)
 
 __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
   __shared__ double scratch[32];
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(256) image_stats_kernel(ImageStatsArgs a) {
   }
 }
 
-__global__ void image_stats_finish_kernel(const double* partial, int blocks, int want_ce,
-                                          double* sums, float* minmax, double* std_acc, float* dbias, int C) {
+__device__ __forceinline__ void image_stats_finish_body(const double* partial, int blocks, int want_ce,
+                                                        double* sums, float* minmax, double* std_acc, float* dbias, int C) {
   __shared__ double scratch[32];
   double v[5] = {0, 0, 0, 0, 0};
   float mn = 3.4e38f, mx = -3.4e38f;
@@ -158,8 +158,134 @@ __global__ void image_stats_finish_kernel(const double* partial, int blocks, int
   }
 }
 
+__global__ void image_stats_finish_kernel(const double* partial, int blocks, int want_ce,
+                                          double* sums, float* minmax, double* std_acc, float* dbias, int C) {
+  image_stats_finish_body(partial, blocks, want_ce, sums, minmax, std_acc, dbias, C);
+}
+
+// Tensor-core training path: thread = one PIXEL (all C channels) down the batch.  d(loss)/d(logit) leaves as one
+// 16-byte bf16 unit per pixel and frame (coalesced full sectors; the element-per-thread kernel above writes the
+// same units as scattered 2-byte stores), and the block that finishes last folds the per-block partials, so the
+// launch of a separate single-block kernel is gone.  Same partial layout and the same fixed summation orders.
+template <int C>
+__global__ void __launch_bounds__(256) image_stats_pix_kernel(ImageStatsArgs a, int64_t HW) {
+  __shared__ double scratch[32];
+  __shared__ bool is_last;
+  double t_se = 0, t_xhx = 0, t_xh = 0, t_ex = 0, t_std = 0;
+  double t_g[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) t_g[c] = 0;
+  float mn = 3.4e38f, mx = -3.4e38f;
+  const bool want_std = a.std_acc != nullptr || a.pos_sums != nullptr;
+  const float* __restrict__ X = a.x;
+  const float* __restrict__ XH = a.xhat;
+  uint4* __restrict__ DL8 = reinterpret_cast<uint4*>(a.dl8);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < HW; q += (int64_t)gridDim.x * blockDim.x) {
+    float se = 0, xhx = 0, xh = 0, ex = 0;
+    float gsum[C], sx[C], sxx[C], sh[C], shh[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { gsum[c] = 0; sx[c] = 0; sxx[c] = 0; sh[c] = 0; shh[c] = 0; }
+    for (int b0 = 0; b0 < a.B; b0 += 4) {
+      float xv4[4][C], hv4[4][C];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = ((int64_t)(b0 + u < a.B ? b0 + u : b0) * HW + q) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { xv4[u][c] = __ldg(X + i + c); hv4[u][c] = __ldg(XH + i + c); }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (b0 + u >= a.B) break;
+        uint32_t h16[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float xv = xv4[u][c], hv = hv4[u][c];
+          const float d = xv - hv;
+          se = fmaf(d, d, se);
+          mn = fminf(mn, hv);
+          mx = fmaxf(mx, hv);
+          if (a.want_ce) {
+            xhx = fmaf(hv, xv, xhx);
+            xh += hv;
+            ex += expf(xv);
+          }
+          if (want_std) {
+            const float dx = xv - 0.5f, dh = hv - 0.5f;
+            sx[c] += dx; sxx[c] = fmaf(dx, dx, sxx[c]);
+            sh[c] += dh; shh[c] = fmaf(dh, dh, shh[c]);
+          }
+          const float gl = a.grad_scale * (hv - xv) * hv * (1.0f - hv);
+          gsum[c] += gl;
+          const uint32_t u32 = __float_as_uint(gl);                 // bf16 round-to-nearest-even
+          h16[c] = (u32 + 0x7FFFu + ((u32 >> 16) & 1u)) >> 16;
+        }
+        DL8[(int64_t)(b0 + u) * HW + q] = make_uint4(h16[0] | (h16[1] << 16), h16[2] | (h16[3] << 16), h16[4] | (h16[5] << 16),
+                                                     h16[6] | (h16[7] << 16));
+      }
+    }
+    t_se += se; t_xhx += xhx; t_xh += xh; t_ex += ex;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      t_g[c] += (double)gsum[c];
+      const int64_t p = q * C + c;
+      if (a.pos_sums) {
+        a.pos_sums[p] = sx[c]; a.pos_sums[a.P + p] = sxx[c];
+        a.pos_sums[2 * a.P + p] = sh[c]; a.pos_sums[3 * a.P + p] = shh[c];
+      } else if (a.std_acc) {
+        const double inv = 1.0 / a.B;
+        const double vx = fmax((double)sxx[c] * inv - ((double)sx[c] * inv) * ((double)sx[c] * inv), 0.0);
+        const double vh = fmax((double)shh[c] * inv - ((double)sh[c] * inv) * ((double)sh[c] * inv), 0.0);
+        const double dd = sqrt(vx) - sqrt(vh);
+        t_std += dd * dd;
+      }
+    }
+  }
+  double* out = a.partial + (int64_t)blockIdx.x * kStatSlots;
+  double r;
+  r = block_sum(t_se, scratch);  if (threadIdx.x == 0) out[0] = r;
+  r = block_sum(t_xhx, scratch); if (threadIdx.x == 0) out[1] = r;
+  r = block_sum(t_xh, scratch);  if (threadIdx.x == 0) out[2] = r;
+  r = block_sum(t_ex, scratch);  if (threadIdx.x == 0) out[3] = r;
+  r = block_sum(t_std, scratch); if (threadIdx.x == 0) out[4] = r;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    r = block_sum(t_g[c], scratch);
+    if (threadIdx.x == 0) out[8 + c] = r;
+  }
+  __shared__ float fs[64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  mn = warp_min(mn); mx = warp_max(mx);
+  __syncthreads();
+  if (lane == 0) { fs[wid] = mn; fs[32 + wid] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int w = 1; w < nw; ++w) { mn = fminf(mn, fs[w]); mx = fmaxf(mx, fs[32 + w]); }
+    out[5] = mn; out[6] = mx;
+    // ticket: the block that arrives last sees every other block's partials (release / acquire through the fences)
+    __threadfence();
+    unsigned* ticket = reinterpret_cast<unsigned*>(a.partial + (int64_t)kStatBlocks * kStatSlots);
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    image_stats_finish_body(a.partial, (int)gridDim.x, a.want_ce, a.sums, a.minmax, a.pos_sums ? nullptr : a.std_acc, a.dbias, C);
+  }
+}
+
 void image_stats(const ImageStatsArgs& a, cudaStream_t st) {
   ProfScope prof_("image_stats", st);
+  if (a.dl8 && !a.dlogit && a.dbias && (a.C == 3 || a.C == 1) && a.P % a.C == 0 && ((uintptr_t)a.dl8 & 15) == 0) {
+    const int64_t HW = a.P / a.C;
+    int blocks = cdiv(HW, 256);
+    if (blocks > kStatBlocks) blocks = kStatBlocks;
+    ++g_launches;
+    if (a.C == 3) KC_LAUNCH(image_stats_pix_kernel<3>, blocks, 256, 0, st, a, HW);
+    else KC_LAUNCH(image_stats_pix_kernel<1>, blocks, 256, 0, st, a, HW);
+    return;
+  }
   int blocks = cdiv(a.P, 256);
   if (blocks > kStatBlocks) blocks = kStatBlocks;
   g_launches += 2;

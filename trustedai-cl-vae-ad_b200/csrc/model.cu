@@ -860,6 +860,7 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
       (rc = dalloc(h, &h->minmax, 4)) || (rc = dalloc(h, &h->metrics_dev, KCVAE_NUM_METRICS)) ||
       (rc = dalloc(h, &h->dpartial, image_stats_partial_doubles())))
     return bail(rc);
+  cudaMemset(h->dpartial, 0, image_stats_partial_doubles() * sizeof(double));   // holds the image_stats ticket
   cudaMemset(h->w, 0, h->nparams * sizeof(float));
   cudaMemset(h->g, 0, h->nparams * sizeof(float));
   cudaMemset(h->m, 0, h->nparams * sizeof(float));
