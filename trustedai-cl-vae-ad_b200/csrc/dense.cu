@@ -145,7 +145,7 @@ bool dense_wide_ok(const void* A, const void* W, const void* C, const void* bias
 
 __global__ void __launch_bounds__(128) dense_wide_fwd_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                              const float* __restrict__ bias, float* __restrict__ C,
-                                                             int M, int N, int K, int relu) {
+                                                             int M, int N, int K, int relu, uint2* __restrict__ Cp, int Cc) {
   KC_DYN_SMEM(float, As);   // [DW_BT][K]
   const int m0 = blockIdx.y * DW_BT;
   for (int i = threadIdx.x; i < DW_BT * K; i += blockDim.x) {
@@ -177,12 +177,22 @@ __global__ void __launch_bounds__(128) dense_wide_fwd_kernel(const float* __rest
     if (m0 + r >= M) break;
     float4 y = make_float4(acc[r][0] + b4.x, acc[r][1] + b4.y, acc[r][2] + b4.z, acc[r][3] + b4.w);
     if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-    *reinterpret_cast<float4*>(C + (int64_t)(m0 + r) * N + n) = y;
+    if (C) *reinterpret_cast<float4*>(C + (int64_t)(m0 + r) * N + n) = y;
+    if (Cp) {   // bf16 chunk-planar copy [M][Cc/8][N/Cc pixels][8] for a tensor-core consumer (output seen as [pixels][Cc])
+      const int px = n / Cc, ch = n - px * Cc;
+      const uint32_t lo = (__float_as_uint(y.x) + 0x7FFFu + ((__float_as_uint(y.x) >> 16) & 1u)) >> 16 |
+                          ((__float_as_uint(y.y) + 0x7FFFu + ((__float_as_uint(y.y) >> 16) & 1u)) & 0xFFFF0000u);
+      const uint32_t hi = (__float_as_uint(y.z) + 0x7FFFu + ((__float_as_uint(y.z) >> 16) & 1u)) >> 16 |
+                          ((__float_as_uint(y.w) + 0x7FFFu + ((__float_as_uint(y.w) >> 16) & 1u)) & 0xFFFF0000u);
+      const int64_t unit = ((int64_t)(m0 + r) * (Cc >> 3) + (ch >> 3)) * (N / Cc) + px;     // 16-byte unit index
+      Cp[unit * 2 + ((ch & 7) >> 2)] = make_uint2(lo, hi);
+    }
   }
 }
 
+// C (fp32 [M,N]) and / or Cp (bf16 chunk-planar copy, the output seen as [N/Cc pixels][Cc channels], Cc % 8 == 0)
 void dense_wide_forward(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
-                        cudaStream_t st) {
+                        cudaStream_t st, void* Cp, int Cc) {
   ProfScope prof_("dense_wide_fwd", st);
   dim3 grid(cdiv(N / 4, 128), cdiv(M, DW_BT));
   const size_t smem = (size_t)DW_BT * K * sizeof(float);
@@ -190,7 +200,7 @@ void dense_wide_forward(const float* A, const float* W, const float* bias, float
 #ifndef KCVAE_EMU
   if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  KC_LAUNCH(dense_wide_fwd_kernel, grid, 128, smem, st, A, W, bias, C, M, N, K, relu);
+  KC_LAUNCH(dense_wide_fwd_kernel, grid, 128, smem, st, A, W, bias, C, M, N, K, relu, reinterpret_cast<uint2*>(Cp), Cc > 0 ? Cc : 8);
 }
 
 // block (64 column quads) x (4 k-subgroups of 8): dW tile [32 k][256 n]; grid.y = k tiles

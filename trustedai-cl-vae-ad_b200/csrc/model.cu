@@ -105,7 +105,7 @@ struct kcvae_model {
   float* x_stage[2] = {nullptr, nullptr};   // double-buffered H2D staging for the *_host entry points
   // bf16 weight images of the tensor-core kernels are rebuilt only after the weights changed
   uint64_t w_version = 1;                   // bumped by every writer of `w`
-  uint64_t img_version[4] = {0, 0, 0, 0};   // convT fwd, tail / out conv, out dgrad, convT dgrad
+  uint64_t img_version[5] = {0, 0, 0, 0, 0};   // convT fwd, tail / out conv, out dgrad, convT dgrad, 32 -> few convT fwd
   bool w_external = false;                  // the raw device pointer was handed out: never trust the cache
   kc::ResizePlan* resize_plan = nullptr;    // uint8 front end: span tables of the last (in_h, in_w) seen
   uint8_t* u8_stage[2] = {nullptr, nullptr};   // double-buffered H2D staging of uint8 host frames
@@ -137,6 +137,10 @@ struct kcvae_model {
   void* g_s2d = nullptr;         // bf16 space-to-depth d loss / d a_last, chunk-planar [B][4][4][H/2][W/2][8]
   void* wimg_convT_dgrad = nullptr;
   void* a_prev8 = nullptr;       // bf16 input of the last Conv2DTranspose s2, NHWC padded to 8 channels
+  void* a_pp_planar = nullptr;   // chunk-planar bf16 copy of the activation before it (input of the 32 -> few tensor-core layer)
+  void* wimg_convT_few = nullptr;
+  bool use_tc_convT_few = false;   // inference entry points (scoring, forward, decode)
+  bool use_tc_convT_few_train = false;
   void* wimg_convT = nullptr;
   uint16_t* dl8 = nullptr;       // bf16 d(loss)/d(logit), NHWC padded to 8 channels
   void* wimg_dgrad = nullptr;
@@ -318,6 +322,11 @@ int ensure_fwd(kcvae_model* h, int B) {
       unsigned short* t8 = reinterpret_cast<unsigned short*>(h->a_prev8);
       KC_TRY(dalloc(h, &t8, (size_t)B * h->dh[L - 1] * h->dw[L - 1] * 8));
       h->a_prev8 = t8;
+      if (h->use_tc_convT_few) {
+        unsigned short* tp = reinterpret_cast<unsigned short*>(h->a_pp_planar);
+        KC_TRY(dalloc(h, &tp, (size_t)B * h->dh[L - 2] * h->dw[L - 2] * h->dc[L - 2]));
+        h->a_pp_planar = tp;
+      }
     }
   }
 #endif
@@ -436,6 +445,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
                  bool keep_last = true, TailOut* tail = nullptr) {
   const int L = h->L;
   bool last_is_bf16 = false;   // the last activation was produced directly in bf16 by tc_convT_fwd
+  bool prev8_ready = false;    // a_prev8 was written by the 32 -> few tensor-core layer (no pack pass needed)
   h->relu_bits_valid = false;
   GemmArgs ga{};
   ga.A = z; ga.a_sm = h->latent; ga.a_sk = 1;
@@ -443,10 +453,19 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   ga.C = h->act_d[0]; ga.bias = h->wp(h->vi_dec_dense() + 1); ga.relu = 1;
   ga.M = B; ga.N = h->dec_units; ga.K = h->latent; ga.partial = h->partial;
   g_tag = "dec.dense.fwd";
-  if (dense_wide_ok(z, ga.Bm, ga.C, ga.bias, B, h->dec_units, h->latent))
-    dense_wide_forward(z, ga.Bm, ga.bias, ga.C, B, h->dec_units, h->latent, 1, st);
-  else
+  // the 32 -> few tensor-core Conv2DTranspose reads the Dense output as chunk-planar bf16: when the Dense is the layer right
+  // before it, it writes that copy itself (and, with nothing else reading the fp32 activation, only that copy)
+  bool few_tc = false, pp_ready = false;
+#ifndef KCVAE_EMU
+  few_tc = L >= 2 && h->use_tc_convT_few && (!keep_last || h->use_tc_convT_few_train) && h->use_tc_convT && h->use_tc_out;
+#endif
+  if (dense_wide_ok(z, ga.Bm, ga.C, ga.bias, B, h->dec_units, h->latent)) {
+    pp_ready = few_tc && L == 2 && h->dc[0] % 8 == 0;
+    dense_wide_forward(z, ga.Bm, ga.bias, (pp_ready && !keep_last) ? nullptr : ga.C, B, h->dec_units, h->latent, 1, st,
+                       pp_ready ? h->a_pp_planar : nullptr, h->dc[0]);
+  } else {
     gemm(ga, st);
+  }
   for (int l = 0; l < L; ++l) {
     ConvArgs a{};
     a.in = h->act_d[l]; a.w = h->wp(h->vi_dec_convT(l)); a.bias = h->wp(h->vi_dec_convT(l) + 1); a.out = h->act_d[l + 1];
@@ -455,10 +474,21 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
     a.w_sci = 1; a.w_sco = a.Ci;  // [kh,kw,out,in]
     g_tag = l == L - 1 ? "dec.convT_last.fwd" : "dec.convT.fwd";
 #ifndef KCVAE_EMU
+    if (l == L - 2 && few_tc) {
+      // 32 -> few Conv2DTranspose on tcgen05: bf16 chunk-planar copy of the input, output straight into the 8-channel
+      // bf16 units the next tensor-core layer reads (+ the fp32 activation when the backward will need it)
+      if (!pp_ready) cast_f32_to_bf16_planar(a.in, h->a_pp_planar, B, (int64_t)a.Hi * a.Wi, a.Ci, st);
+      if (image_stale(h, 4)) tc_prep_convT_few_weights(a.w, a.Co, a.Ci, h->wimg_convT_few, st);
+      if (tc_convT_few_fwd(h->a_pp_planar, h->wimg_convT_few, a.bias, h->a_prev8, keep_last ? a.out : nullptr, B, a.Hi, a.Wi, a.Co,
+                           h->tc_error, st) == 0) {
+        prev8_ready = true;
+        continue;
+      }
+    }
     if (l == L - 1 && h->use_tc_convT && h->use_tc_out) {
       // sub-pixel phase decomposition on tcgen05, bf16 output straight into the buffer the
       // output-layer kernels read (no fp32 copy of the 224x300x32 activation exists in this mode)
-      pack_c8_bf16(a.in, (int64_t)B * a.Hi * a.Wi, a.Ci, h->a_prev8, st);
+      if (!prev8_ready) pack_c8_bf16(a.in, (int64_t)B * a.Hi * a.Wi, a.Ci, h->a_prev8, st);
       if (image_stale(h, 0)) tc_prep_convT_weights(a.w, a.Co, a.Ci, h->wimg_convT, st);
       if ((!keep_last || h->fuse_train_tail) && tail_fusable(h, B)) {
         const int vo = h->vi_out();
@@ -878,6 +908,18 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
       if ((rc = dalloc(h, &wc, tc_convT_weight_image_elems()))) return bail(rc);
       h->wimg_convT = wc;
       h->use_tc_convT = true;
+      // KCVAE_TC_CONVT_FEW: 0 = fp32 CUDA-core kernel for the 32 -> few Conv2DTranspose everywhere, 2 = tensor-core kernel in
+      // the training forward too.  Default: inference only - with one more bf16 layer in front of a ReLU the decoder Dense
+      // gradient of the small golden fixture moved from inside to just outside the 5e-2 relative-L2 bar the tests hold
+      // bf16 gradients to (6.1e-2), while losses and reconstructions stay inside theirs either way.
+      const char* cf = std::getenv("KCVAE_TC_CONVT_FEW");
+      if (h->L >= 2 && tc_convT_few_fwd_supported(h->dc[h->L - 2], h->dc[h->L - 1]) && !(cf && cf[0] == '0')) {
+        unsigned short* wf = nullptr;
+        if ((rc = dalloc(h, &wf, tc_convT_few_weight_image_elems()))) return bail(rc);
+        h->wimg_convT_few = wf;
+        h->use_tc_convT_few = true;
+        h->use_tc_convT_few_train = cf && cf[0] == '2';
+      }
       const char* ft = std::getenv("KCVAE_FUSE_TRAIN_TAIL");   // 0 = separate convT / out-conv kernels in the training forward
       h->fuse_train_tail = !(ft && ft[0] == '0');
     }
@@ -937,6 +979,8 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->wimg_convT_dgrad) cudaFree(h->wimg_convT_dgrad);
   if (h->g_s2d) cudaFree(h->g_s2d);
   if (h->a_prev8) cudaFree(h->a_prev8);
+  if (h->a_pp_planar) cudaFree(h->a_pp_planar);
+  if (h->wimg_convT_few) cudaFree(h->wimg_convT_few);
   if (h->dl8) cudaFree(h->dl8);
   if (h->tc_error) cudaFree(h->tc_error);
   double* dl[] = {h->dpartial, h->sums, h->std_acc, h->pos_sums};

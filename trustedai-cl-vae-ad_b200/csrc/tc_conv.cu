@@ -897,6 +897,191 @@ __device__ __forceinline__ void tc_prep_convT_weights_body(const float* w, int C
   }
 }
 
+// ============================================================================================
+// Conv2DTranspose s2 forward, MANY -> few channels (Cin = 32, Cout <= 8), on tensor cores:
+//   out[n, 2i+a, 2j+b, co] = relu(bias[co] + sum_{di,dj in {0,1}} sum_ci in[n, i-di, j-dj, ci] * W[a+2di, b+2dj, co, ci])
+// (taps with a+2di > 2 or b+2dj > 2 do not exist).  One GEMM per low-res tile: M = 128 low-res pixels,
+// N = 32 = (output parity a,b) x 8 padded channels, K = 32 channels x 4 input shifts = 8 MMAs per M-tile; the shifts
+// are descriptor start offsets into a halo tile (one row above, one column left) of the chunk-planar bf16 input.
+// The epilogue writes the bf16 8-channel units the next (few -> 32) tensor-core layer reads and, for training,
+// the fp32 activation the backward kernels use.
+constexpr int TRF = 8;                                // low-res rows per tile
+constexpr int FROWS = TRF + 1;
+constexpr uint32_t CHF = FROWS * PW * 16;             // bytes per chunk plane of the input tile
+constexpr int MTF = (TRF * PW) / 128;                 // 2 M-tiles
+struct ConvTFewParams {
+  const __nv_bfloat16* wimg;   // [4 shifts][2 ks][2 chunks][32][8]
+  const float* bias;           // [Cout]
+  uint4* out8;                 // bf16 [B,2h,2w,8] (one 16-byte unit per pixel) or nullptr
+  float* out_f32;              // fp32 [B,2h,2w,Cout] or nullptr
+  int B, h, w, Cout;
+  int tiles_y, tiles_x, num_tiles;
+  int* error_flag;
+};
+
+__global__ void __launch_bounds__(kThreadsE, 1)
+tc_convT_few_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTFewParams p) {
+  constexpr uint32_t TILE_BYTES = 4 * CHF;
+  constexpr uint32_t STAGE = TILE_BYTES + 128;
+  constexpr uint32_t WB = 4 * 2 * 2 * 32 * 16;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* s_tile = smem;
+  unsigned char* s_w = smem + kStages * STAGE;
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < (int)(WB / 16); i += kThreadsE)
+    reinterpret_cast<uint4*>(s_w)[i] = reinterpret_cast<const uint4*>(p.wimg)[i];
+  if (threadIdx.x < 8) s_bias[threadIdx.x] = threadIdx.x < p.Cout ? p.bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < kStages * 8) {
+    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
+    reinterpret_cast<uint4*>(s_tile + s * STAGE + TILE_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<64>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / (p.tiles_y * p.tiles_x);
+        const int rem = t % (p.tiles_y * p.tiles_x);
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        mbar_expect_tx(&full_bar[s], TILE_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_3d(s_tile + s * STAGE + c * CHF, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TRF - 1, n * 4 + c);
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16_f32(128, 32);
+    const uint64_t b0 = make_desc_kmajor_noswz(smem_u32(s_w), 32 * 16, 128);
+    int it = 0, mcount = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; break; }
+      fence_after_sync();
+      const uint64_t a0 = make_desc_kmajor_noswz(smem_u32(s_tile + s * STAGE), CHF, 128);
+      bool ok = true;
+#pragma unroll 1
+      for (int mt = 0; mt < MTF; ++mt, ++mcount) {
+        const int a = mcount & 1;
+        const uint32_t aph = (mcount >> 1) & 1;
+        if (!mbar_wait(&tempty_bar[a], aph ^ 1)) { if (leader) *p.error_flag = 1; ok = false; break; }
+        fence_after_sync();
+        const uint32_t d0 = tmem + (uint32_t)(a * 32);
+#pragma unroll
+        for (int sh = 0; sh < 4; ++sh) {
+          // input pixel (i - di, j - dj) of output low-res pixel q sits at tile position q + (1-di)*PW + (1-dj)
+          const uint32_t shift = (uint32_t)((1 - (sh >> 1)) * PW + (1 - (sh & 1)));
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t da = desc_advance(a0, (uint32_t)(2 * ks) * (CHF / 16) + (uint32_t)(mt * 128) + shift);
+            const uint64_t db = desc_advance(b0, (uint32_t)((sh * 2 + ks) * 2 * 32));
+            if (leader) mma_bf16_ss(d0, da, db, idesc, (sh | ks) != 0);
+          }
+        }
+        if (leader) mma_commit(&tfull_bar[a]);
+        __syncwarp();
+      }
+      if (!ok) break;
+      if (leader) mma_commit(&empty_bar[s]);
+      __syncwarp();
+    }
+  } else {
+    const int lg = warp & 3;
+    const int pa = (warp - 2) >> 2;               // output row parity this warp writes
+    const int H2 = 2 * p.h, W2 = 2 * p.w;
+    int it = 0, mcount = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int n = t / (p.tiles_y * p.tiles_x);
+      const int rem = t % (p.tiles_y * p.tiles_x);
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      bool ok = true;
+#pragma unroll 1
+      for (int mt = 0; mt < MTF; ++mt, ++mcount) {
+        const int a = mcount & 1;
+        const uint32_t aph = (mcount >> 1) & 1;
+        if (!mbar_wait(&tfull_bar[a], aph)) { if (lane == 0) *p.error_flag = 1; ok = false; break; }
+        fence_after_sync();
+        const int q = mt * 128 + lg * 32 + lane;
+        const int r = q / PW, c = q % PW;
+        const int i = ty * TRF + r, j = tx * TW + c;
+        const bool valid = c < TW && i < p.h && j < p.w;
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * 32 + pa * 16), v);
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[a]);          // accumulators are in registers: the slot is free
+        if (valid) {
+          const int oy = 2 * i + pa;
+          const int64_t pix = ((int64_t)n * H2 + oy) * W2 + 2 * j;       // pixels (oy, 2j) and (oy, 2j+1) are adjacent
+          float y[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) y[k] = (k & 7) < p.Cout ? fmaxf(v[k] + s_bias[k & 7], 0.f) : 0.f;
+          if (p.out8) {
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(y[b * 8 + 2 * e], y[b * 8 + 2 * e + 1]);
+                w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+              }
+              p.out8[pix + b] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          }
+          if (p.out_f32) {     // pixels (oy, 2j) and (oy, 2j+1): 2 * Cout consecutive floats
+            float* o = p.out_f32 + pix * p.Cout;
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+              for (int co = 0; co < 8; ++co)
+                if (co < p.Cout) o[b * p.Cout + co] = y[b * 8 + co];
+          }
+        }
+      }
+      if (!ok) break;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+// W [3,3,Cout<=8,Cin=32] fp32 -> B images [shift (di,dj)][ks][chunk(2)][n = (a*2+b)*8 + co][8 = ci]
+__device__ __forceinline__ void tc_prep_convT_few_weights_body(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+  const int total = 4 * 2 * 2 * 32 * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % 8;
+    const int n = (i / 8) % 32;
+    const int kc = (i / 256) % 2;
+    const int ks = (i / 512) % 2;
+    const int sh = i / 1024;
+    const int di = sh >> 1, dj = sh & 1, a = n >> 4, b = (n >> 3) & 1, co = n & 7;
+    const int kh = a + 2 * di, kw = b + 2 * dj, ci = ks * 16 + kc * 8 + j;
+    const float v = (kh <= 2 && kw <= 2 && co < Cout && ci < Cin) ? w[((int64_t)(kh * 3 + kw) * Cout + co) * Cin + ci] : 0.f;
+    img[i] = __float2bfloat16(v);
+  }
+}
+__global__ void tc_prep_convT_few_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_convT_few_weights_body(w, Cout, Cin, img); }
+
 // fp32 NHWC with C <= 8 channels -> bf16 NHWC padded to 8 channels (16 bytes per pixel)
 __global__ void pack_c8_bf16_kernel(const float* in, int64_t npix, int C, uint4* out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1805,11 +1990,11 @@ void cast_f32_to_bf16_planar(const float* in, void* out, int B, int64_t HW, int 
   cast_f32_bf16_planar_kernel<<<grid_for((int64_t)B * HW * (C / 8), 256, 8, 2), 256, 0, st>>>(in, reinterpret_cast<uint4*>(out), B, HW, C / 8);
 }
 // tensor map of a chunk-planar bf16 activation [B][Cin/8][H][W][8]: dims (W*8, H, B*Cin/8), box = one halo plane
-static CUresult make_planar_tmap(CUtensorMap* tmap, const void* act, int B, int H, int W, int Cin) {
+static CUresult make_planar_tmap(CUtensorMap* tmap, const void* act, int B, int H, int W, int Cin, int rows = PR) {
   EncodeTiledFn enc = get_encode_fn();
   const cuuint64_t gdim[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)B * (Cin / 8)};
   const cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-  const cuuint32_t box[3] = {PW * 8, PR, 1};
+  const cuuint32_t box[3] = {PW * 8, (cuuint32_t)rows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(act), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1948,6 +2133,35 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg, const float* bias, void
   ++g_launches;
   cudaFuncSetAttribute(tc_convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tc_convT_fwd_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
+  return 0;
+}
+
+bool tc_convT_few_fwd_supported(int Cin, int Cout) { return Cin == 32 && Cout >= 1 && Cout <= 8; }
+size_t tc_convT_few_weight_image_elems() { return (size_t)4 * 2 * 2 * 32 * 8; }
+void tc_prep_convT_few_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
+  ProfScope prof_("tc_prep_weights", st);
+  ++g_launches;
+  tc_prep_convT_few_weights_kernel<<<8, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+}
+// in: chunk-planar bf16 [B][4][h][w][8]; out8: bf16 [B,2h,2w,8] and/or out_f32: fp32 [B,2h,2w,Cout] = relu(bias + convT_s2(in))
+int tc_convT_few_fwd(const void* in_planar_bf16, const void* wimg, const float* bias, void* out8_bf16, float* out_f32, int B, int h,
+                     int w, int Cout, int* error_flag, cudaStream_t st) {
+  if (!get_encode_fn()) return 1;
+  CUtensorMap tmap;
+  if (make_planar_tmap(&tmap, in_planar_bf16, B, h, w, 32, FROWS) != CUDA_SUCCESS) return 2;
+  ConvTFewParams p{};
+  p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
+  p.bias = bias; p.out8 = reinterpret_cast<uint4*>(out8_bf16); p.out_f32 = out_f32;
+  p.B = B; p.h = h; p.w = w; p.Cout = Cout;
+  p.tiles_y = cdiv(h, TRF); p.tiles_x = cdiv(w, TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const size_t smem = (size_t)kStages * ((size_t)4 * CHF + 128) + (size_t)4 * 2 * 2 * 32 * 16;
+  ProfScope prof_("tc_convT_few_fwd", st);
+  ++g_launches;
+  cudaFuncSetAttribute(tc_convT_few_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tc_convT_few_fwd_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
   return 0;
 }
 

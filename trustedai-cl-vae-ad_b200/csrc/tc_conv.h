@@ -46,6 +46,13 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg_bf16, const float* bias,
 
 // fused decoder tail: Conv2DTranspose s2 (Cprev <= 8 -> 32) -> Conv2DTranspose s1 (32 -> Cout) with the
 // 32-channel activation kept in shared memory; optional sigmoid, x_hat, error map and per-frame score
+// Conv2DTranspose s2 forward 32 -> few channels (Cout <= 8) from a chunk-planar bf16 input [B][4][h][w][8]:
+// out8 = bf16 [B,2h,2w,8] (the input layout of the few -> 32 layers), out_f32 = fp32 [B,2h,2w,Cout]; either may be nullptr
+bool tc_convT_few_fwd_supported(int Cin, int Cout);
+size_t tc_convT_few_weight_image_elems();
+void tc_prep_convT_few_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
+int tc_convT_few_fwd(const void* in_planar_bf16, const void* wimg, const float* bias, void* out8_bf16, float* out_f32, int B, int h,
+                     int w, int Cout, int* error_flag, cudaStream_t st);
 bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W);
 // weight image the fused tail reads for its output convolution (layout depends on Cout); img = tc_out_weight_image_elems()
 void tc_prep_tail_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
