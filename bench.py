@@ -359,6 +359,11 @@ def run_ours(args):
     step_ach = step_bytes / (ms_total / K * 1e-3) / 1e9
     roof["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_ach, "frac": step_ach / peak}
     roof["kernel_breakdown_ms_per_step"] = {k: round(v[1] / K, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:12]}
+    # the same roofline for every launcher with an entry in the algorithmic-byte table (launch-averaged, events on the stream)
+    roof["per_kernel"] = [
+        {"kernel": k, "ms": round(v[1] / v[0], 4), "GBps": round(tab[k] / (v[1] / v[0] * 1e-3) / 1e9, 1),
+         "frac": round(tab[k] / (v[1] / v[0] * 1e-3) / 1e9 / peak, 3)}
+        for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1]) if k in tab and v[0] > 0]
 
     # anomaly scoring (do_anomaly_detection.py loops): frames/s resident and end to end
     score_info = None

@@ -128,6 +128,31 @@ def test_readme_config_scoring_and_ranking():
     np.testing.assert_allclose(mm[:, 1], oerr.numpy().reshape(12, -1).max(1), atol=2e-5)
 
 
+def test_readme_config_scoring_and_ranking_tensor_core_path():
+    """precision='bf16': the scorer runs the 32 -> few Conv2DTranspose and the fused decoder tail on tcgen05 (error map and
+    per-frame score come out of the tail's epilogue).  Bars: reconstruction max-abs <= 1e-2 (held to 4e-3), scores
+    within 1e-3 relative, identical ranking (BASELINE.json north_star)."""
+    cfg = O.readme_config()
+    m, ws = make(cfg, BACKEND, weight_gain=1.3, precision="bf16")
+    assert m.tc_status() == 1
+    om = O.OracleModel(cfg, ws)
+    x = frames(cfg, 12)
+    for i, b in enumerate((2, 7)):
+        x[b, 40:40 + 24 * (i + 1), 50:50 + 24 * (i + 1), :] = 1.0
+    r = m.score(x, return_err=True, return_rec=True)
+    assert m.tc_status() == 1
+    oxh = om.call(torch.from_numpy(x))
+    oerr = O.error_map(torch.from_numpy(x), oxh)
+    assert float(np.max(np.abs(r["rec"].numpy() - oxh.numpy()))) < 4e-3
+    osc = oerr.sum(dim=(1, 2)).numpy()
+    np.testing.assert_allclose(r["score"].numpy(), osc, rtol=1e-3)
+    np.testing.assert_allclose(r["err"].numpy().sum(axis=(1, 2)), r["score"].numpy(), rtol=1e-5)   # map and score agree
+    assert list(np.argsort(-r["score"].numpy(), kind="stable")) == list(np.argsort(-osc, kind="stable"))
+    # score-only call (no error map, no reconstruction) gives the same scores
+    r2 = m.score(x, return_err=False)
+    np.testing.assert_array_equal(r2["score"].numpy(), r["score"].numpy())
+
+
 # --------------------------------------------------- size-independent properties, full sizes
 def test_properties_at_baseline_batch():
     cfg = O.readme_config()
