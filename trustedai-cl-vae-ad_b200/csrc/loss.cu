@@ -154,7 +154,7 @@ __device__ __forceinline__ void image_stats_finish_body(const double* partial, i
   if (threadIdx.x == 0 && minmax) {
     const int nw = (blockDim.x + 31) >> 5;
     for (int w = 1; w < nw; ++w) { mn = fminf(mn, fs[w]); mx = fmaxf(mx, fs[32 + w]); }
-    minmax[0] = mn; minmax[1] = mx;
+    minmax[0] = mn; minmax[1] = mx; minmax[2] = -mx;   // [2]: lets data-parallel ranks fold min and max in ONE MIN all-reduce
   }
 }
 
@@ -437,7 +437,7 @@ __global__ void finalize_metrics_kernel(const double* sums, const float* minmax,
   const double NP = (double)Bg * (double)P;
   const double mse = sums[S_SE] / NP;
   const double z_l1 = sums[S_ABSZ] / ((double)Bg * L);
-  const double rmin = minmax ? minmax[0] : nan_, rmax = minmax ? minmax[1] : nan_;
+  const double rmin = minmax ? minmax[0] : nan_, rmax = minmax ? fmax((double)minmax[1], -(double)minmax[2]) : nan_;
   const double xstd = std_acc ? std_acc[0] / (double)P : nan_;
   for (int i = 0; i < 16; ++i) out[i] = 0.0f;
   if (model_type == 0) {

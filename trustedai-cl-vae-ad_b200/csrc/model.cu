@@ -605,15 +605,18 @@ int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier
   image_stats(ia, st);
   if (h->world > 1) {
     stream_after(h, st, cs);
-    KC_TRY(allreduce(h, h->sums, sums_len(h), 1, 0, cs));   // needed by latent_backward (batch-global moments)
+    // the moment sums are needed by latent_backward (batch-global moments), a whole decoder backward later.  FULL tier:
+    // the per-position batch moments (reported-only x_std_loss) sit right behind them in the same allocation and ride in
+    // the same collective; min and max share one MIN all-reduce over [min, max, -max] (two collectives instead of four)
+    const bool merged = full && h->pos_sums == h->sums + kSumsLen;
+    KC_TRY(allreduce(h, h->sums, merged ? (int64_t)kSumsLen + 4 * h->P : (int64_t)sums_len(h), 1, 0, cs));
 #ifndef KCVAE_EMU
     if (cs != st) cudaEventRecord(h->ev_sums, cs);
 #endif
     if (full) {   // reported-only metrics: nothing on the gradient path waits for these
-      KC_TRY(allreduce(h, h->pos_sums, 4 * h->P, 1, 0, cs));
+      if (!merged) KC_TRY(allreduce(h, h->pos_sums, 4 * h->P, 1, 0, cs));
       image_std_from_pos_sums(h->pos_sums, h->P, Bg, h->std_acc, h->dpartial, cs);
-      KC_TRY(allreduce(h, h->minmax, 1, 0, 1, cs));      // min over ranks of min(xhat)
-      KC_TRY(allreduce(h, h->minmax + 1, 1, 0, 2, cs));  // max over ranks of max(xhat)
+      KC_TRY(allreduce(h, h->minmax, 3, 0, 1, cs));      // [0] = global min, -[2] = global max (finalize_metrics)
     }
   }
   return KCVAE_OK;
@@ -983,6 +986,7 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->wimg_convT_few) cudaFree(h->wimg_convT_few);
   if (h->dl8) cudaFree(h->dl8);
   if (h->tc_error) cudaFree(h->tc_error);
+  if (h->pos_sums == h->sums + kSumsLen) h->pos_sums = nullptr;   // lives inside the sums allocation
   double* dl[] = {h->dpartial, h->sums, h->std_acc, h->pos_sums};
   for (double* p : dl) if (p) cudaFree(p);
   delete h;
@@ -1140,7 +1144,11 @@ int kcvae_comm_init(kcvae_handle h, const void* id128, int rank, int world_size)
     KC_CUDA(h, cudaEventCreateWithFlags(&h->ev_comm, cudaEventDisableTiming));
   }
 #endif
-  if (world_size > 1) KC_TRY(dalloc(h, &h->pos_sums, (size_t)4 * h->P));
+  if (world_size > 1) {   // per-position batch moments directly behind the moment sums: one all-reduce carries both
+    KC_TRY(dalloc(h, &h->sums, (size_t)kSumsLen + (size_t)4 * h->P));
+    KC_CUDA(h, cudaMemset(h->sums, 0, ((size_t)kSumsLen + (size_t)4 * h->P) * sizeof(double)));
+    h->pos_sums = h->sums + kSumsLen;
+  }
   return KCVAE_OK;
 }
 
