@@ -779,6 +779,15 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       gemm(gi, st);
     }
   }
+  int64_t enc_tail_floats = h->vars[h->vi_dec_dense()].off;   // encoder gradients still to be reduced at the end
+  if (h->world > 1 && L > 0) {
+    // the encoder Dense / head gradients (all but a few KB of the encoder range) are final here: reduce them under the
+    // encoder convolutions' backward, so that only the tiny convolution range is left for the exposed collective
+    const int64_t off_dense = h->vars[h->enc_dense ? h->vi_enc_dense() : h->vi_head()].off;
+    stream_after(h, st, cs);
+    KC_TRY(allreduce(h, h->g + off_dense, enc_tail_floats - off_dense, 0, 0, cs));
+    enc_tail_floats = off_dense;
+  }
   for (int l = L - 1; l >= 0; --l) {  // encoder Conv2D (s2) layers
     const int vi = h->vi_enc_conv(l);
     const float* in = l > 0 ? h->act_e[l] : x;
@@ -804,9 +813,8 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     }
   }
   if (h->world > 1) {
-    const int64_t off_dec = h->vars[h->vi_dec_dense()].off;
     stream_after(h, st, cs);
-    KC_TRY(allreduce(h, h->g, off_dec, 0, 0, cs));          // encoder range
+    if (enc_tail_floats > 0) KC_TRY(allreduce(h, h->g, enc_tail_floats, 0, 0, cs));   // what is left of the encoder range
 #ifndef KCVAE_EMU
     if (cs != st) { cudaEventRecord(h->ev_comm, cs); cudaStreamWaitEvent(st, h->ev_comm, 0); }
 #endif
