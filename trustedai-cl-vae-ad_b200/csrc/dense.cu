@@ -143,49 +143,67 @@ bool dense_wide_ok(const void* A, const void* W, const void* C, const void* bias
   return M > 0 && K > 0 && N >= 64 && (N & 3) == 0 && K <= 4096 && al(A) && al(W) && al(C) && (!bias || al(bias));
 }
 
+// NC = output columns per thread: 4, or 8 when the bf16 chunk-planar copy is written (one whole 16-byte unit per thread
+// and row, so that a warp's stores are four contiguous 128-byte runs instead of sixteen 16-byte pieces)
+template <int BT, int NC>
 __global__ void __launch_bounds__(128) dense_wide_fwd_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                              const float* __restrict__ bias, float* __restrict__ C,
-                                                             int M, int N, int K, int relu, uint2* __restrict__ Cp, int Cc) {
-  KC_DYN_SMEM(float, As);   // [DW_BT][K]
-  const int m0 = blockIdx.y * DW_BT;
-  for (int i = threadIdx.x; i < DW_BT * K; i += blockDim.x) {
+                                                             int M, int N, int K, int relu, uint4* __restrict__ Cp, int Cc) {
+  KC_DYN_SMEM(float, As);   // [BT][K]
+  constexpr int NV = NC / 4;
+  const int m0 = blockIdx.y * BT;
+  for (int i = threadIdx.x; i < BT * K; i += blockDim.x) {
     const int r = i / K, k = i - r * K;
     As[i] = (m0 + r < M) ? __ldg(A + (int64_t)(m0 + r) * K + k) : 0.f;
   }
   __syncthreads();
-  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * NC;
   if (n >= N) return;
-  float acc[DW_BT][4];
+  float acc[BT][NC];
 #pragma unroll
-  for (int r = 0; r < DW_BT; ++r) { acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f; }
+  for (int r = 0; r < BT; ++r)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) acc[r][c] = 0.f;
   const float4* wp = reinterpret_cast<const float4*>(W + n);
   const int64_t wstride = N >> 2;
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {
-    const float4 w = __ldg(wp + (int64_t)k * wstride);
+    float w[NC];
 #pragma unroll
-    for (int r = 0; r < DW_BT; ++r) {
+    for (int v = 0; v < NV; ++v) {
+      const float4 t = __ldg(wp + (int64_t)k * wstride + v);
+      w[4 * v] = t.x; w[4 * v + 1] = t.y; w[4 * v + 2] = t.z; w[4 * v + 3] = t.w;
+    }
+#pragma unroll
+    for (int r = 0; r < BT; ++r) {
       const float a = As[r * K + k];
-      acc[r][0] = fmaf(a, w.x, acc[r][0]); acc[r][1] = fmaf(a, w.y, acc[r][1]);
-      acc[r][2] = fmaf(a, w.z, acc[r][2]); acc[r][3] = fmaf(a, w.w, acc[r][3]);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[r][c] = fmaf(a, w[c], acc[r][c]);
     }
   }
-  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+  float bv[NC];
 #pragma unroll
-  for (int r = 0; r < DW_BT; ++r) {
+  for (int c = 0; c < NC; ++c) bv[c] = bias ? __ldg(bias + n + c) : 0.f;
+#pragma unroll
+  for (int r = 0; r < BT; ++r) {
     if (m0 + r >= M) break;
-    float4 y = make_float4(acc[r][0] + b4.x, acc[r][1] + b4.y, acc[r][2] + b4.z, acc[r][3] + b4.w);
-    if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-    if (C) *reinterpret_cast<float4*>(C + (int64_t)(m0 + r) * N + n) = y;
-    if (Cp) {   // bf16 chunk-planar copy [M][Cc/8][N/Cc pixels][8] for a tensor-core consumer (output seen as [pixels][Cc])
+    float y[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) { y[c] = acc[r][c] + bv[c]; if (relu) y[c] = fmaxf(y[c], 0.f); }
+    if (C) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        *reinterpret_cast<float4*>(C + (int64_t)(m0 + r) * N + n + 4 * v) = make_float4(y[4 * v], y[4 * v + 1], y[4 * v + 2], y[4 * v + 3]);
+    }
+    if (NC == 8 && Cp) {   // bf16 chunk-planar copy [M][Cc/8][N/Cc pixels][8] for a tensor-core consumer (output seen as [pixels][Cc])
       const int px = n / Cc, ch = n - px * Cc;
-      const uint32_t lo = (__float_as_uint(y.x) + 0x7FFFu + ((__float_as_uint(y.x) >> 16) & 1u)) >> 16 |
-                          ((__float_as_uint(y.y) + 0x7FFFu + ((__float_as_uint(y.y) >> 16) & 1u)) & 0xFFFF0000u);
-      const uint32_t hi = (__float_as_uint(y.z) + 0x7FFFu + ((__float_as_uint(y.z) >> 16) & 1u)) >> 16 |
-                          ((__float_as_uint(y.w) + 0x7FFFu + ((__float_as_uint(y.w) >> 16) & 1u)) & 0xFFFF0000u);
-      const int64_t unit = ((int64_t)(m0 + r) * (Cc >> 3) + (ch >> 3)) * (N / Cc) + px;     // 16-byte unit index
-      Cp[unit * 2 + ((ch & 7) >> 2)] = make_uint2(lo, hi);
+      uint32_t h2[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t lo = __float_as_uint(y[2 * e]), hi = __float_as_uint(y[2 * e + 1]);     // round to nearest even
+        h2[e] = ((lo + 0x7FFFu + ((lo >> 16) & 1u)) >> 16) | ((hi + 0x7FFFu + ((hi >> 16) & 1u)) & 0xFFFF0000u);
+      }
+      Cp[((int64_t)(m0 + r) * (Cc >> 3) + (ch >> 3)) * (N / Cc) + px] = make_uint4(h2[0], h2[1], h2[2], h2[3]);
     }
   }
 }
@@ -194,13 +212,21 @@ __global__ void __launch_bounds__(128) dense_wide_fwd_kernel(const float* __rest
 void dense_wide_forward(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
                         cudaStream_t st, void* Cp, int Cc) {
   ProfScope prof_("dense_wide_fwd", st);
-  dim3 grid(cdiv(N / 4, 128), cdiv(M, DW_BT));
+  const bool planar = Cp && Cc % 8 == 0 && N % 8 == 0;
+  dim3 grid(cdiv(N / (planar ? 8 : 4), 128), cdiv(M, DW_BT));
   const size_t smem = (size_t)DW_BT * K * sizeof(float);
   ++g_launches;
+  if (planar) {
 #ifndef KCVAE_EMU
-  if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_fwd_kernel<DW_BT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  KC_LAUNCH(dense_wide_fwd_kernel, grid, 128, smem, st, A, W, bias, C, M, N, K, relu, reinterpret_cast<uint2*>(Cp), Cc > 0 ? Cc : 8);
+    KC_LAUNCH((dense_wide_fwd_kernel<DW_BT, 8>), grid, 128, smem, st, A, W, bias, C, M, N, K, relu, reinterpret_cast<uint4*>(Cp), Cc);
+  } else {
+#ifndef KCVAE_EMU
+    if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_fwd_kernel<DW_BT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    KC_LAUNCH((dense_wide_fwd_kernel<DW_BT, 4>), grid, 128, smem, st, A, W, bias, C, M, N, K, relu, static_cast<uint4*>(nullptr), 8);
+  }
 }
 
 // block (64 column quads) x (4 k-subgroups of 8): dW tile [32 k][256 n]; grid.y = k tiles
