@@ -366,17 +366,18 @@ __global__ void __launch_bounds__(256) dense_wide_dgrad_reduce_kernel(const floa
 }
 
 // G [M,N] (gradient of the Dense output, ReLU mask already applied), A [M,K], W [K,N]
+// st_w: stream of the weight-gradient kernel (independent of the data gradient: may run beside it)
 void dense_wide_backward(const float* A, const float* G, const float* W, float* dW, float* db, float* dA, float* partial,
-                         int M, int N, int K, cudaStream_t st) {
+                         int M, int N, int K, cudaStream_t st, cudaStream_t st_w) {
   {
-    ProfScope prof_("dense_wide_wgrad", st);
+    ProfScope prof_("dense_wide_wgrad", st_w);
     dim3 grid(cdiv(N / 4, 64), cdiv(K, DW_KT));
     const size_t smem = (size_t)M * DW_KT * sizeof(float);
     ++g_launches;
 #ifndef KCVAE_EMU
     if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-    KC_LAUNCH(dense_wide_wgrad_kernel, grid, 256, smem, st, A, G, dW, db, M, N, K);
+    KC_LAUNCH(dense_wide_wgrad_kernel, grid, 256, smem, st_w, A, G, dW, db, M, N, K);
   }
   if (dA) {
     ProfScope prof_("dense_wide_dgrad", st);

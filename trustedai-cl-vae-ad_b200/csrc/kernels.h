@@ -64,7 +64,7 @@ void dense_wide_forward(const float* A, const float* W, const float* bias, float
 size_t dense_wide_partial_floats(int M, int N, int K);
 // dW[K,N] = A^T G, db[N] = colsum(G) (db may be nullptr), dA[M,K] = G W^T (dA may be nullptr)
 void dense_wide_backward(const float* A, const float* G, const float* W, float* dW, float* db, float* dA, float* partial,
-                         int M, int N, int K, cudaStream_t st);
+                         int M, int N, int K, cudaStream_t st, cudaStream_t st_w);
 
 // --------------------------------------------------------------------- loss (loss.cu)
 // slots of the fp64 `sums` vector shared by the loss kernels (all-reduced under DP)

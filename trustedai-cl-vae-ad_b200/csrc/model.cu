@@ -151,6 +151,11 @@ struct kcvae_model {
   int rank = 0, world = 1;
   // collectives run on their own stream so they overlap the backward pass (non-emulated build)
   cudaStream_t comm_stream = nullptr;
+  // weight-gradient kernels of the CUDA-core layers run beside the data-gradient kernels of the same layer
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
+  float* partial2 = nullptr;       // reduction scratch of the kernels on aux_stream
+  bool use_aux = false, aux_dirty = false;
 #ifndef KCVAE_EMU
   cudaEvent_t ev_fork = nullptr, ev_sums = nullptr, ev_comm = nullptr;
 #endif
@@ -332,6 +337,20 @@ int ensure_fwd(kcvae_model* h, int B) {
 #endif
   h->partial_floats = max_partial_floats(h, B);
   KC_TRY(dalloc(h, &h->partial, h->partial_floats));
+#ifndef KCVAE_EMU
+  {
+    const char* e = std::getenv("KCVAE_AUX_STREAM");     // 0 = every backward kernel on the caller's stream
+    h->use_aux = !(e && e[0] == '0');
+    if (h->use_aux) {
+      KC_TRY(dalloc(h, &h->partial2, h->partial_floats));
+      if (!h->aux_stream) {
+        KC_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        KC_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_fork, cudaEventDisableTiming));
+        KC_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_join, cudaEventDisableTiming));
+      }
+    }
+  }
+#endif
   h->cap_fwd = B;
   h->cap_bwd = 0;  // partial buffer was sized for this B; backward buffers follow
   return KCVAE_OK;
@@ -629,6 +648,32 @@ void run_finalize(kcvae_model* h, int B, int tier, float* d_metrics, cudaStream_
                    h->cfg.model_type, h->lw, full && h->cfg.model_type == KCVAE_GLOBAL, d_metrics, st);
 }
 
+// Side stream for kernels whose results nothing on `st` waits for until the gradients are consumed (weight gradients).
+// aux_fork: the side stream sees everything enqueued on st so far; aux_join: st waits for the side stream.
+static cudaStream_t aux_fork(kcvae_model* h, cudaStream_t st, float** partial) {
+  *partial = h->partial;
+#ifndef KCVAE_EMU
+  if (!h->use_aux) return st;
+  cudaEventRecord(h->ev_aux_fork, st);
+  cudaStreamWaitEvent(h->aux_stream, h->ev_aux_fork, 0);
+  h->aux_dirty = true;
+  *partial = h->partial2;
+  return h->aux_stream;
+#else
+  return st;
+#endif
+}
+static void aux_join(kcvae_model* h, cudaStream_t st) {
+#ifndef KCVAE_EMU
+  if (!h->use_aux || !h->aux_dirty) return;
+  cudaEventRecord(h->ev_aux_join, h->aux_stream);
+  cudaStreamWaitEvent(st, h->ev_aux_join, 0);
+  h->aux_dirty = false;
+#else
+  (void)h; (void)st;
+#endif
+}
+
 // ------------------------------------------------------------------------------ backward
 // cs != st: gradient all-reduces are issued on cs as soon as a parameter range is complete
 int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStream_t cs) {
@@ -695,8 +740,13 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       continue;   // bias gradient was produced by tc_out_dgrad
     }
 #endif
-    conv_wgrad(wa, st);
-    colsum(h->g_act_d[l + 1], (int64_t)B * h->dh[l + 1] * h->dw[l + 1], h->dc[l + 1], h->gp(vi + 1), h->partial, st);
+    {
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);
+      wa.partial = px;
+      conv_wgrad(wa, ax);
+      colsum(h->g_act_d[l + 1], (int64_t)B * h->dh[l + 1] * h->dw[l + 1], h->dc[l + 1], h->gp(vi + 1), px, ax);
+    }
     ConvArgs a{};
     a.in = h->g_act_d[l + 1]; a.w = h->wp(vi); a.mask = h->act_d[l]; a.out = h->g_act_d[l];
     a.B = B; a.Hi = h->dh[l + 1]; a.Wi = h->dw[l + 1]; a.Ci = h->dc[l + 1];
@@ -711,7 +761,9 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     g_tag = "dec.dense.bwd";
     if (dense_wide_ok(h->z, h->wp(vi), h->gp(vi), h->gp(vi + 1), B, h->dec_units, h->latent) &&
         dense_wide_ok(G, h->g_z, h->gp(vi), nullptr, B, h->dec_units, h->latent)) {
-      dense_wide_backward(h->z, G, h->wp(vi), h->gp(vi), h->gp(vi + 1), h->g_z, h->partial, B, h->dec_units, h->latent, st);
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);
+      dense_wide_backward(h->z, G, h->wp(vi), h->gp(vi), h->gp(vi + 1), h->g_z, h->partial, B, h->dec_units, h->latent, st, ax);
     } else {
       GemmArgs ga{};
       ga.A = h->z; ga.a_sm = 1; ga.a_sk = h->latent;
@@ -729,6 +781,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
   if (h->world > 1) {
     // every decoder gradient is final: reduce that range (93 % of the parameters) under the encoder backward
     const int64_t off_dec = h->vars[h->vi_dec_dense()].off;
+    aux_join(h, st);
     stream_after(h, st, cs);
     KC_TRY(allreduce(h, h->g + off_dec, h->nparams - off_dec, 0, 0, cs));
 #ifndef KCVAE_EMU
@@ -748,9 +801,11 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     GemmArgs ga{};
     ga.A = hin; ga.a_sm = 1; ga.a_sk = kin;
     ga.Bm = h->dhead; ga.b_sk = 2 * h->latent; ga.b_sn = 1;
-    ga.C = h->gp(vi); ga.M = kin; ga.N = 2 * h->latent; ga.K = B; ga.partial = h->partial;
-    gemm(ga, st);
-    colsum(h->dhead, B, 2 * h->latent, h->gp(vi + 1), h->partial, st);
+    float* px;
+    cudaStream_t ax = aux_fork(h, st, &px);
+    ga.C = h->gp(vi); ga.M = kin; ga.N = 2 * h->latent; ga.K = B; ga.partial = px;
+    gemm(ga, ax);
+    colsum(h->dhead, B, 2 * h->latent, h->gp(vi + 1), px, ax);
     float* dst = h->enc_dense ? h->g_d1 : g_flat;
     if (dst) {
       GemmArgs gi{};
@@ -767,9 +822,11 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     GemmArgs ga{};
     ga.A = flat_act; ga.a_sm = 1; ga.a_sk = h->flat;
     ga.Bm = h->g_d1; ga.b_sk = h->enc_dense; ga.b_sn = 1;
-    ga.C = h->gp(vi); ga.M = h->flat; ga.N = h->enc_dense; ga.K = B; ga.partial = h->partial;
-    gemm(ga, st);
-    colsum(h->g_d1, B, h->enc_dense, h->gp(vi + 1), h->partial, st);
+    float* px;
+    cudaStream_t ax = aux_fork(h, st, &px);
+    ga.C = h->gp(vi); ga.M = h->flat; ga.N = h->enc_dense; ga.K = B; ga.partial = px;
+    gemm(ga, ax);
+    colsum(h->g_d1, B, h->enc_dense, h->gp(vi + 1), px, ax);
     if (g_flat) {
       GemmArgs gi{};
       gi.A = h->g_d1; gi.a_sm = h->enc_dense; gi.a_sk = 1;
@@ -784,6 +841,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     // the encoder Dense / head gradients (all but a few KB of the encoder range) are final here: reduce them under the
     // encoder convolutions' backward, so that only the tiny convolution range is left for the exposed collective
     const int64_t off_dense = h->vars[h->enc_dense ? h->vi_enc_dense() : h->vi_head()].off;
+    aux_join(h, st);
     stream_after(h, st, cs);
     KC_TRY(allreduce(h, h->g + off_dense, enc_tail_floats - off_dense, 0, 0, cs));
     enc_tail_floats = off_dense;
@@ -801,7 +859,14 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     wa.o_sa = 1; wa.o_sb = wa.Ca;  // HWIO: [tap][in=b][out=a]
     g_tag = l == 0 ? "enc.conv0.bwd" : (l == 1 ? "enc.conv1.bwd" : "enc.convN.bwd");
     wa.pcolsum = h->gp(vi + 1);   // bias gradient = column sums of P, same pass
-    conv_wgrad(wa, st);
+    if (l > 0) {   // beside this layer's data gradient (and the next layer's weight gradient)
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);
+      wa.partial = px;
+      conv_wgrad(wa, ax);
+    } else {
+      conv_wgrad(wa, st);
+    }
     if (l > 0) {
       ConvArgs a{};
       a.in = h->g_act_e[l + 1]; a.w = h->wp(vi); a.mask = h->act_e[l]; a.out = h->g_act_e[l];
@@ -812,6 +877,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       conv_forward(CONVT_S2, EPI_MASK, a, st);
     }
   }
+  aux_join(h, st);   // every gradient is final from here on
   if (h->world > 1) {
     stream_after(h, st, cs);
     if (enc_tail_floats > 0) KC_TRY(allreduce(h, h->g, enc_tail_floats, 0, 0, cs));   // what is left of the encoder range
@@ -960,6 +1026,8 @@ int kcvae_destroy(kcvae_handle h) {
   cudaDeviceSynchronize();
 #ifndef KCVAE_EMU
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  if (h->aux_stream) { cudaStreamDestroy(h->aux_stream); cudaEventDestroy(h->ev_aux_fork); cudaEventDestroy(h->ev_aux_join); }
+  if (h->partial2) cudaFree(h->partial2);
   if (h->comm_stream) { cudaStreamDestroy(h->comm_stream); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_sums); cudaEventDestroy(h->ev_comm); }
 #endif
 #ifndef KCVAE_EMU
