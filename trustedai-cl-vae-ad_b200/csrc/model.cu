@@ -344,7 +344,9 @@ int ensure_fwd(kcvae_model* h, int B) {
     if (h->use_aux) {
       KC_TRY(dalloc(h, &h->partial2, h->partial_floats));
       if (!h->aux_stream) {
-        KC_CUDA(h, cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);      // side stream at the lowest priority: it only fills gaps
+        KC_CUDA(h, cudaStreamCreateWithPriority(&h->aux_stream, cudaStreamNonBlocking, prio_lo));
         KC_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_fork, cudaEventDisableTiming));
         KC_CUDA(h, cudaEventCreateWithFlags(&h->ev_aux_join, cudaEventDisableTiming));
       }
@@ -688,15 +690,13 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     wa.s = 1; wa.d = -1; wa.oy = 1; wa.ox = 1;
     wa.o_sa = wa.Cb; wa.o_sb = 1;  // [tap][out=a][in=b]
     g_tag = "dec.out.bwd";
-    bool wdone = false;
-#ifndef KCVAE_EMU
-    if (h->use_tc_dgrad && h->use_tc_out && tc_out_wgrad_supported(h->dc[L], h->C) &&
-        h->partial_floats >= tc_out_wgrad_partial_floats(h->dc[L], h->C))
-      wdone = tc_out_wgrad(h->dl8, h->a_last_bf16, h->gp(vi), h->partial, B, h->H, h->W, h->dc[L], h->C, h->tc_error, st) == 0;
-#endif
+    // The tensor-core weight gradient is enqueued AFTER the data gradient, on the side stream: the data-gradient chain is
+    // the critical path; the weight-gradient kernels fill in behind it and beside the CUDA-core kernels further down.
+    const bool tc_w = h->use_tc_dgrad && h->use_tc_out && tc_out_wgrad_supported(h->dc[L], h->C) &&
+                      h->partial_floats >= tc_out_wgrad_partial_floats(h->dc[L], h->C);
     const bool tc_tail_w = h->use_tc_dgrad && h->use_tc_out && h->C <= 8;
-    if (!wdone && tc_tail_w) h->tc_failed = true;   // no fp32 dlogit exists in this mode
-    if (!wdone && !tc_tail_w) conv_wgrad(wa, st);
+    if (!tc_w && tc_tail_w) h->tc_failed = true;   // no fp32 dlogit exists in this mode
+    if (!tc_w && !tc_tail_w) conv_wgrad(wa, st);
     const bool tc_tail = h->use_tc_dgrad && h->use_tc_out && h->C <= 8;   // bias gradient came from image_stats
     if (!tc_tail) colsum(h->dlogit, (int64_t)B * h->H * h->W, h->C, h->gp(vi + 1), h->partial, st);
     ConvArgs a{};
@@ -720,6 +720,14 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
 #endif
     if (!done && tc_tail) h->tc_failed = true;
     if (!done && !tc_tail) conv_forward(CONV_S1, EPI_MASK, a, st);
+#ifndef KCVAE_EMU
+    if (tc_w) {
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);
+      g_tag = "dec.out.bwd";
+      if (tc_out_wgrad(h->dl8, h->a_last_bf16, h->gp(vi), px, B, h->H, h->W, h->dc[L], h->C, h->tc_error, ax) != 0) h->tc_failed = true;
+    }
+#endif
   }
   for (int l = L - 1; l >= 0; --l) {  // decoder Conv2DTranspose (s2) layers
     const int vi = h->vi_dec_convT(l);
@@ -732,10 +740,12 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     g_tag = l == L - 1 ? "dec.convT_last.bwd" : "dec.convT.bwd";
 #ifndef KCVAE_EMU
     if (l == L - 1 && tail_s2d) {
-      bool ok = tc_convT_wgrad(h->g_s2d, h->a_prev8, h->gp(vi), h->partial, B, h->dh[l], h->dw[l], h->dc[l], h->tc_error, st) == 0;
       if (image_stale(h, 3)) tc_prep_convT_dgrad_weights(h->wp(vi), h->dc[l + 1], h->dc[l], h->wimg_convT_dgrad, st);
-      ok = ok && tc_convT_dgrad(h->g_s2d, h->wimg_convT_dgrad, h->act_d[l], h->g_act_d[l], B, h->dh[l], h->dw[l], h->dc[l],
-                                h->tc_error, st) == 0;
+      bool ok = tc_convT_dgrad(h->g_s2d, h->wimg_convT_dgrad, h->act_d[l], h->g_act_d[l], B, h->dh[l], h->dw[l], h->dc[l],
+                               h->tc_error, st) == 0;
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);
+      ok = ok && tc_convT_wgrad(h->g_s2d, h->a_prev8, h->gp(vi), px, B, h->dh[l], h->dw[l], h->dc[l], h->tc_error, ax) == 0;
       if (!ok) h->tc_failed = true;
       continue;   // bias gradient was produced by tc_out_dgrad
     }
