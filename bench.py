@@ -341,6 +341,8 @@ def run_ours(args):
     top = max(rep.items(), key=lambda kv: kv[1][1])
     top_key, (top_calls, top_ms) = top
     peak, peak_src = hbm_peak()
+    # (the per-launch pass runs every kernel alone on the launching stream; the timed steps overlap the weight-gradient
+    # kernels with the data-gradient chain on a side stream, so the launcher times add up to more than ms_per_step)
     roof = {"bound": "hbm", "kernel": top_key, "share_of_step": top_ms / tot, "unit": "GB/s", "peak": peak,
             "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": None,
             "convention": "algorithmic bytes: activations bf16, x/weights fp32 (SURVEY 8d)"}

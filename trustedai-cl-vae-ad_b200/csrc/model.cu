@@ -655,7 +655,7 @@ void run_finalize(kcvae_model* h, int B, int tier, float* d_metrics, cudaStream_
 static cudaStream_t aux_fork(kcvae_model* h, cudaStream_t st, float** partial) {
   *partial = h->partial;
 #ifndef KCVAE_EMU
-  if (!h->use_aux) return st;
+  if (!h->use_aux || g_prof_on) return st;   // per-launch profiling times every kernel alone on the caller's stream
   cudaEventRecord(h->ev_aux_fork, st);
   cudaStreamWaitEvent(h->aux_stream, h->ev_aux_fork, 0);
   h->aux_dirty = true;
