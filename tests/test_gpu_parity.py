@@ -363,3 +363,26 @@ def test_config5_scaled_model():
         assert l2 < 2e-3, (n, l2)
         assert rel_err(g, og) < 5e-2, (n, rel_err(g, og))
     assert float(np.max(np.abs(m.call(x, True, eps=eps).numpy() - oxh.numpy()))) < 1e-4
+
+
+def test_side_stream_backward_is_bitwise_identical_to_the_serial_one(monkeypatch):
+    """The weight-gradient kernels run on a side stream beside the
+    data-gradient chain; KCVAE_AUX_STREAM=0 keeps everything on the caller's stream.  Same kernels, same reduction orders:
+    gradients, metrics and the weights after three optimizer steps must agree bit for bit."""
+    cfg = O.readme_config()
+    B = 6
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    out = []
+    for aux in ("1", "0"):
+        monkeypatch.setenv("KCVAE_AUX_STREAM", aux)
+        m, _ = make(cfg, BACKEND, weight_gain=1.3, precision="bf16")
+        d, g = m.loss_and_grads(x, eps=eps)
+        m.compile(optimizer=pkg.Adam(learning_rate=1e-3))
+        steps = [m.train_step(x, eps=eps_for(cfg, B, step=s)) for s in range(3)]
+        out.append(([np.asarray(a) for a in g], [float(d[k]) for k in d], [float(s_["loss"]) for s_ in steps],
+                    [np.asarray(w) for w in m.get_weights()]))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert np.array_equal(a, b)
+    assert out[0][1] == out[1][1] and out[0][2] == out[1][2]
+    for a, b in zip(out[0][3], out[1][3]):
+        assert np.array_equal(a, b)
