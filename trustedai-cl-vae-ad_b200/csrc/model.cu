@@ -692,8 +692,12 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     g_tag = "dec.out.bwd";
     // The tensor-core weight gradient is enqueued AFTER the data gradient, on the side stream: the data-gradient chain is
     // the critical path; the weight-gradient kernels fill in behind it and beside the CUDA-core kernels further down.
+#ifndef KCVAE_EMU
     const bool tc_w = h->use_tc_dgrad && h->use_tc_out && tc_out_wgrad_supported(h->dc[L], h->C) &&
                       h->partial_floats >= tc_out_wgrad_partial_floats(h->dc[L], h->C);
+#else
+    const bool tc_w = false;
+#endif
     const bool tc_tail_w = h->use_tc_dgrad && h->use_tc_out && h->C <= 8;
     if (!tc_w && tc_tail_w) h->tc_failed = true;   // no fp32 dlogit exists in this mode
     if (!tc_w && !tc_tail_w) conv_wgrad(wa, st);
