@@ -44,17 +44,9 @@ constexpr int kThreadsT = 64 + 8 * 32 + 4 * 32;   // fused tail: TMA, MMA, 8 pha
 constexpr int kThreadsE = 320;            // kernels with a per-tile epilogue: 2 + 8 warps (two epilogue warps per TMEM lane group)
 static_assert(TR * PW == MT * 128, "tile must be a whole number of M=128 tiles");
 
-// 4-D tiled TMA load: box (8 channels, PW cols, PR rows, 1 image) -> one [pixel] x 16 B chunk plane
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* mbar, int c0, int c1,
-                                            int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(mbar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-// 3-D tiled TMA load from the chunk-planar activation layout [B*KC planes][H][W*8]: box (PW pixels x 8
-// channels = 512 contiguous bytes, PR rows, 1 plane) -> the same [pixel] x 16 B chunk plane in shared memory
+// 3-D tiled TMA load from a [planes][H][W*8] bf16 view (chunk-planar activations, 8-channel NHWC tensors): box (pixels x 8
+// channels = contiguous bytes, rows, 1 plane) -> a [pixel] x 16 B chunk plane in shared memory.  The box start must be
+// 16-byte aligned in global memory (an 8-byte aligned inner coordinate raises "illegal instruction").
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* mbar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
