@@ -148,7 +148,8 @@ bool dense_wide_ok(const void* A, const void* W, const void* C, const void* bias
 template <int BT, int NC>
 __global__ void __launch_bounds__(128) dense_wide_fwd_kernel(const float* __restrict__ A, const float* __restrict__ W,
                                                              const float* __restrict__ bias, float* __restrict__ C,
-                                                             int M, int N, int K, int relu, uint4* __restrict__ Cp, int Cc) {
+                                                             int M, int N, int K, int relu, uint4* __restrict__ Cp, int Cc,
+                                                             int split) {
   KC_DYN_SMEM(float, As);   // [BT][K]
   constexpr int NV = NC / 4;
   const int m0 = blockIdx.y * BT;
@@ -203,14 +204,28 @@ __global__ void __launch_bounds__(128) dense_wide_fwd_kernel(const float* __rest
         const uint32_t lo = __float_as_uint(y[2 * e]), hi = __float_as_uint(y[2 * e + 1]);     // round to nearest even
         h2[e] = ((lo + 0x7FFFu + ((lo >> 16) & 1u)) >> 16) | ((hi + 0x7FFFu + ((hi >> 16) & 1u)) & 0xFFFF0000u);
       }
-      Cp[((int64_t)(m0 + r) * (Cc >> 3) + (ch >> 3)) * (N / Cc) + px] = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+      const int KC = Cc >> 3;
+      const int64_t hwp = N / Cc;
+      const int64_t unit = ((int64_t)(m0 + r) * (split ? 2 * KC : KC) + (ch >> 3)) * hwp + px;
+      Cp[unit] = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+      if (split) {   // lo planes: what bf16 dropped, again in bf16 (y = hi + lo to 2^-17)
+        uint32_t l2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float r0 = y[2 * e] - __uint_as_float(h2[e] << 16), r1 = y[2 * e + 1] - __uint_as_float(h2[e] & 0xFFFF0000u);
+          const uint32_t lo = __float_as_uint(r0), hi = __float_as_uint(r1);
+          l2[e] = ((lo + 0x7FFFu + ((lo >> 16) & 1u)) >> 16) | ((hi + 0x7FFFu + ((hi >> 16) & 1u)) & 0xFFFF0000u);
+        }
+        Cp[unit + (int64_t)KC * hwp] = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+      }
     }
   }
 }
 
-// C (fp32 [M,N]) and / or Cp (bf16 chunk-planar copy, the output seen as [N/Cc pixels][Cc channels], Cc % 8 == 0)
+// C (fp32 [M,N]) and / or Cp (bf16 chunk-planar copy, the output seen as [N/Cc pixels][Cc channels], Cc % 8 == 0;
+// split: hi planes followed by lo planes per row of C)
 void dense_wide_forward(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
-                        cudaStream_t st, void* Cp, int Cc) {
+                        cudaStream_t st, void* Cp, int Cc, int split) {
   ProfScope prof_("dense_wide_fwd", st);
   const bool planar = Cp && Cc % 8 == 0 && N % 8 == 0;
   dim3 grid(cdiv(N / (planar ? 8 : 4), 128), cdiv(M, DW_BT));
@@ -220,12 +235,12 @@ void dense_wide_forward(const float* A, const float* W, const float* bias, float
 #ifndef KCVAE_EMU
     if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_fwd_kernel<DW_BT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-    KC_LAUNCH((dense_wide_fwd_kernel<DW_BT, 8>), grid, 128, smem, st, A, W, bias, C, M, N, K, relu, reinterpret_cast<uint4*>(Cp), Cc);
+    KC_LAUNCH((dense_wide_fwd_kernel<DW_BT, 8>), grid, 128, smem, st, A, W, bias, C, M, N, K, relu, reinterpret_cast<uint4*>(Cp), Cc, split);
   } else {
 #ifndef KCVAE_EMU
     if (smem > 48 * 1024) cudaFuncSetAttribute(dense_wide_fwd_kernel<DW_BT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-    KC_LAUNCH((dense_wide_fwd_kernel<DW_BT, 4>), grid, 128, smem, st, A, W, bias, C, M, N, K, relu, static_cast<uint4*>(nullptr), 8);
+    KC_LAUNCH((dense_wide_fwd_kernel<DW_BT, 4>), grid, 128, smem, st, A, W, bias, C, M, N, K, relu, static_cast<uint4*>(nullptr), 8, 0);
   }
 }
 

@@ -60,7 +60,7 @@ void gemm(const GemmArgs& a, cudaStream_t st);
 // the decoder Dense.  dense_wide_ok() says whether the shapes / pointers qualify.
 bool dense_wide_ok(const void* A, const void* W, const void* C, const void* bias, int M, int N, int K);
 void dense_wide_forward(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int relu,
-                        cudaStream_t st, void* Cp = nullptr, int Cc = 0);
+                        cudaStream_t st, void* Cp = nullptr, int Cc = 0, int split = 0);
 size_t dense_wide_partial_floats(int M, int N, int K);
 // dW[K,N] = A^T G, db[N] = colsum(G) (db may be nullptr), dA[M,K] = G W^T (dA may be nullptr)
 void dense_wide_backward(const float* A, const float* G, const float* W, float* dW, float* db, float* dA, float* partial,

@@ -911,11 +911,17 @@ struct ConvTFewParams {
   int* error_flag;
 };
 
+// SPLIT: operands arrive as bf16 hi + lo pairs (x = hi + lo to 2^-17) and every product is xh*wh + xl*wh + xh*wl with
+// fp32 accumulation - fp32-grade results (the training forward, whose ReLU masks and gradients are held to the fp32 bars)
+// for three times the (still negligible) MMA count.  Input planes per frame: [hi 4][lo 4]; weight image: [hi][lo].
+template <bool SPLIT>
 __global__ void __launch_bounds__(kThreadsE, 1)
 tc_convT_few_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTFewParams p) {
-  constexpr uint32_t TILE_BYTES = 4 * CHF;
+  constexpr int NPL = SPLIT ? 8 : 4;                  // chunk planes per tile
+  constexpr uint32_t TILE_BYTES = NPL * CHF;
   constexpr uint32_t STAGE = TILE_BYTES + 128;
-  constexpr uint32_t WB = 4 * 2 * 2 * 32 * 16;
+  constexpr uint32_t WB1 = 4 * 2 * 2 * 32 * 16;       // one weight image
+  constexpr uint32_t WB = (SPLIT ? 2 : 1) * WB1;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* s_tile = smem;
   unsigned char* s_w = smem + kStages * STAGE;
@@ -955,8 +961,8 @@ tc_convT_few_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTFewParams
         const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
         mbar_expect_tx(&full_bar[s], TILE_BYTES);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tma_load_3d(s_tile + s * STAGE + c * CHF, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TRF - 1, n * 4 + c);
+        for (int c = 0; c < NPL; ++c)
+          tma_load_3d(s_tile + s * STAGE + c * CHF, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TRF - 1, n * NPL + c);
       }
     }
   } else if (warp == 1) {
@@ -987,6 +993,14 @@ tc_convT_few_fwd_kernel(const __grid_constant__ CUtensorMap tmap, ConvTFewParams
             const uint64_t da = desc_advance(a0, (uint32_t)(2 * ks) * (CHF / 16) + (uint32_t)(mt * 128) + shift);
             const uint64_t db = desc_advance(b0, (uint32_t)((sh * 2 + ks) * 2 * 32));
             if (leader) mma_bf16_ss(d0, da, db, idesc, (sh | ks) != 0);
+            if constexpr (SPLIT) {
+              const uint64_t da_lo = desc_advance(da, 4 * (CHF / 16));      // lo planes sit four planes behind the hi planes
+              const uint64_t db_lo = desc_advance(db, WB1 / 16);            // lo weight image behind the hi image
+              if (leader) {
+                mma_bf16_ss(d0, da_lo, db, idesc, 1);
+                mma_bf16_ss(d0, da, db_lo, idesc, 1);
+              }
+            }
           }
         }
         if (leader) mma_commit(&tfull_bar[a]);
@@ -1069,7 +1083,9 @@ __device__ __forceinline__ void tc_prep_convT_few_weights_body(const float* w, i
     const int di = sh >> 1, dj = sh & 1, a = n >> 4, b = (n >> 3) & 1, co = n & 7;
     const int kh = a + 2 * di, kw = b + 2 * dj, ci = ks * 16 + kc * 8 + j;
     const float v = (kh <= 2 && kw <= 2 && co < Cout && ci < Cin) ? w[((int64_t)(kh * 3 + kw) * Cout + co) * Cin + ci] : 0.f;
-    img[i] = __float2bfloat16(v);
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    img[i] = hi;
+    img[total + i] = __float2bfloat16(v - __bfloat162float(hi));      // lo image (SPLIT kernels)
   }
 }
 __global__ void tc_prep_convT_few_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_convT_few_weights_body(w, Cout, Cin, img); }
@@ -2129,18 +2145,19 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg, const float* bias, void
 }
 
 bool tc_convT_few_fwd_supported(int Cin, int Cout) { return Cin == 32 && Cout >= 1 && Cout <= 8; }
-size_t tc_convT_few_weight_image_elems() { return (size_t)4 * 2 * 2 * 32 * 8; }
+size_t tc_convT_few_weight_image_elems() { return (size_t)2 * 4 * 2 * 2 * 32 * 8; }   // hi image + lo image
 void tc_prep_convT_few_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
   ProfScope prof_("tc_prep_weights", st);
   ++g_launches;
   tc_prep_convT_few_weights_kernel<<<8, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
 }
-// in: chunk-planar bf16 [B][4][h][w][8]; out8: bf16 [B,2h,2w,8] and/or out_f32: fp32 [B,2h,2w,Cout] = relu(bias + convT_s2(in))
+// in: chunk-planar bf16 [B][4][h][w][8] (split: [B][hi 4 | lo 4][h][w][8]); out8: bf16 [B,2h,2w,8] and/or
+// out_f32: fp32 [B,2h,2w,Cout] = relu(bias + convT_s2(in))
 int tc_convT_few_fwd(const void* in_planar_bf16, const void* wimg, const float* bias, void* out8_bf16, float* out_f32, int B, int h,
-                     int w, int Cout, int* error_flag, cudaStream_t st) {
+                     int w, int Cout, int split, int* error_flag, cudaStream_t st) {
   if (!get_encode_fn()) return 1;
   CUtensorMap tmap;
-  if (make_planar_tmap(&tmap, in_planar_bf16, B, h, w, 32, FROWS) != CUDA_SUCCESS) return 2;
+  if (make_planar_tmap(&tmap, in_planar_bf16, B, h, w, split ? 64 : 32, FROWS) != CUDA_SUCCESS) return 2;
   ConvTFewParams p{};
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.bias = bias; p.out8 = reinterpret_cast<uint4*>(out8_bf16); p.out_f32 = out_f32;
@@ -2149,11 +2166,16 @@ int tc_convT_few_fwd(const void* in_planar_bf16, const void* wimg, const float* 
   p.num_tiles = B * p.tiles_y * p.tiles_x;
   p.error_flag = error_flag;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  const size_t smem = (size_t)kStages * ((size_t)4 * CHF + 128) + (size_t)4 * 2 * 2 * 32 * 16;
+  const size_t smem = (size_t)kStages * ((size_t)(split ? 8 : 4) * CHF + 128) + (size_t)(split ? 2 : 1) * 4 * 2 * 2 * 32 * 16;
   ProfScope prof_("tc_convT_few_fwd", st);
   ++g_launches;
-  cudaFuncSetAttribute(tc_convT_few_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tc_convT_few_fwd_kernel<<<grid, kThreadsE, smem, st>>>(tmap, p);
+  if (split) {
+    cudaFuncSetAttribute(tc_convT_few_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_convT_few_fwd_kernel<true><<<grid, kThreadsE, smem, st>>>(tmap, p);
+  } else {
+    cudaFuncSetAttribute(tc_convT_few_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    tc_convT_few_fwd_kernel<false><<<grid, kThreadsE, smem, st>>>(tmap, p);
+  }
   return 0;
 }
 

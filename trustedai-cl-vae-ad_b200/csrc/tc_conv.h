@@ -51,8 +51,10 @@ int tc_convT_fwd(const void* in8_bf16, const void* wimg_bf16, const float* bias,
 bool tc_convT_few_fwd_supported(int Cin, int Cout);
 size_t tc_convT_few_weight_image_elems();
 void tc_prep_convT_few_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
+// split != 0: the input holds bf16 hi and lo planes ([B][hi 4 | lo 4][h][w][8]) and the products are xh*wh + xl*wh + xh*wl
+// (fp32-grade accuracy; the training forward)
 int tc_convT_few_fwd(const void* in_planar_bf16, const void* wimg, const float* bias, void* out8_bf16, float* out_f32, int B, int h,
-                     int w, int Cout, int* error_flag, cudaStream_t st);
+                     int w, int Cout, int split, int* error_flag, cudaStream_t st);
 bool tc_tail_fused_supported(int Cprev, int Clast, int Cout, int H, int W);
 // weight image the fused tail reads for its output convolution (layout depends on Cout); img = tc_out_weight_image_elems()
 void tc_prep_tail_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
