@@ -410,7 +410,8 @@ def run_ours(args):
             "config": {"workload": "KurtosisGlobalCVAE README config 224x300x3 layers[32,5] latent32 train_step (BASELINE configs[1])",
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "metrics_tier": args.metrics_tier, "l2_policy": f"inputs cycle through a {npool * batch_bytes >> 20} MiB pool (> 126 MiB L2)",
-                       "precision": args.precision},
+                       "precision": args.precision,
+                       "schedule": "weight-gradient kernels on a low-priority side stream beside the data-gradient chain (KCVAE_AUX_STREAM=0: serial)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": batch_bytes,
                     "d2h_bytes_per_step": 16 * 4, "ms_per_step": ms_e2e / K,
                     "uint8_frames": {"value": world * B * K / (ms_u8 * 1e-3), "h2d_bytes_per_step": batch_bytes // 4,
