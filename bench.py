@@ -149,7 +149,8 @@ def algorithmic_bytes(cfg, B, world):
     for tc, generic in (("dec.out.fwd/tc_out_conv", "dec.out.fwd/conv3x3"), ("dec.out.bwd/tc_out_dgrad", "dec.out.bwd/conv3x3"),
                         ("dec.out.bwd/tc_out_wgrad", "dec.out.bwd/wgrad"), ("dec.convT_last.fwd/tc_convT_fwd", "dec.convT_last.fwd/conv3x3"),
                         ("dec.convT_last.bwd/tc_convT_wgrad", "dec.convT_last.bwd/wgrad"),
-                        ("dec.convT_last.bwd/tc_convT_dgrad", "dec.convT_last.bwd/conv3x3")):
+                        ("dec.convT_last.bwd/tc_convT_dgrad", "dec.convT_last.bwd/conv3x3"),
+                        ("dec.convT.fwd/tc_convT_few_fwd", "dec.convT.fwd/conv3x3")):
         if generic in tab:
             tab[tc] = tab[generic]
     tab["dec.dense.fwd/dense_wide_fwd"] = tab["dec.dense.fwd/gemm"]
