@@ -672,6 +672,16 @@ static cudaStream_t aux_fork(kcvae_model* h, cudaStream_t st, float** partial) {
   return st;
 #endif
 }
+// the collective stream waits for what the side stream has produced so far; the caller's stream does not
+static void aux_feed(kcvae_model* h, cudaStream_t cs) {
+#ifndef KCVAE_EMU
+  if (!h->use_aux || !h->aux_dirty) return;
+  cudaEventRecord(h->ev_aux_join, h->aux_stream);
+  cudaStreamWaitEvent(cs, h->ev_aux_join, 0);
+#else
+  (void)h; (void)cs;
+#endif
+}
 static void aux_join(kcvae_model* h, cudaStream_t st) {
 #ifndef KCVAE_EMU
   if (!h->use_aux || !h->aux_dirty) return;
@@ -802,7 +812,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
   if (h->world > 1) {
     // every decoder gradient is final: reduce that range (93 % of the parameters) under the encoder backward
     const int64_t off_dec = h->vars[h->vi_dec_dense()].off;
-    aux_join(h, st);
+    if (cs != st) aux_feed(h, cs); else aux_join(h, st);   // weight gradients live on the side stream: only the collective waits
     stream_after(h, st, cs);
     KC_TRY(allreduce(h, h->g + off_dec, h->nparams - off_dec, 0, 0, cs));
 #ifndef KCVAE_EMU
@@ -862,7 +872,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     // the encoder Dense / head gradients (all but a few KB of the encoder range) are final here: reduce them under the
     // encoder convolutions' backward, so that only the tiny convolution range is left for the exposed collective
     const int64_t off_dense = h->vars[h->enc_dense ? h->vi_enc_dense() : h->vi_head()].off;
-    aux_join(h, st);
+    if (cs != st) aux_feed(h, cs); else aux_join(h, st);
     stream_after(h, st, cs);
     KC_TRY(allreduce(h, h->g + off_dense, enc_tail_floats - off_dense, 0, 0, cs));
     enc_tail_floats = off_dense;
