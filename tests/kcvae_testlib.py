@@ -54,6 +54,7 @@ def small_config(kind="global", H=16, W=24, C_=3, layers=(6, 5), enc=7, dec=4, l
 
 def make(cfg, backend, seed=1234, bias_scale=0.05, weight_gain=1.0, **kw):
     kind = "single" if cfg["model"].get("type") == "KurtosisSingle" else "global"
+    kw.setdefault("precision", "fp32")     # the library default is the tensor-core path; the tight fp32 bars are asked for
     m = model_class(backend, kind)(cfg, **kw)
     ws = O.glorot_init(cfg, seed, bias_scale=bias_scale)
     if weight_gain != 1.0:

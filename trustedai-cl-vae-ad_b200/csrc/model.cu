@@ -98,7 +98,7 @@ struct kcvae_model {
   int64_t adam_t = 0;
   float lr = 1e-3f, beta = 0.f;
   LossWeights lw;
-  uint64_t seed = 0x5eed5eedULL, rng_counter = 0;
+  uint64_t seed = 0x5eed5eedULL, seed_base = 0x5eed5eedULL, rng_counter = 0;
   // workspace
   int cap_fwd = 0, cap_bwd = 0, last_B = 0;
   std::vector<float*> act_e, act_d, g_act_e, g_act_d;
@@ -147,6 +147,7 @@ struct kcvae_model {
   void* a_last_bf16 = nullptr;
   void* wimg_out = nullptr;
   int* tc_error = nullptr;
+  int* tc_flag_host = nullptr;   // pinned: the *_host entry points read tc_error back with their results
   // data parallel
   int rank = 0, world = 1;
   // collectives run on their own stream so they overlap the backward pass (non-emulated build)
@@ -402,6 +403,22 @@ int post(kcvae_model* h) {
   return KCVAE_OK;
 }
 
+// A tensor-core launcher that could not run (cuTensorMapEncodeTiled) invalidates the call: there is no fallback kernel.
+int tc_check(kcvae_model* h) {
+  if (!h->tc_failed) return KCVAE_OK;
+  h->tc_failed = false;
+  return fail(h, KCVAE_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed; use precision fp32");
+}
+// Host entry points synchronise anyway: read the device flag the bounded tcgen05 barrier waits raise and refuse the
+// result when it is set (an expired wait must not feed garbage gradients to Adam silently).
+int tc_flag_check(kcvae_model* h, cudaStream_t st) {   // enqueue the flag read-back, synchronise, test
+  if (h->tc_error && h->tc_flag_host) KC_CUDA(h, cudaMemcpyAsync(h->tc_flag_host, h->tc_error, sizeof(int), cudaMemcpyDeviceToHost, st));
+  KC_CUDA(h, cudaStreamSynchronize(st));
+  if (h->tc_error && h->tc_flag_host && *h->tc_flag_host)
+    return fail(h, KCVAE_ERR_CUDA, "tcgen05 pipeline: bounded mbarrier wait expired (results of this call are invalid)");
+  return KCVAE_OK;
+}
+
 // ------------------------------------------------------------------------------ forward
 void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st) {
   const float* in = x;
@@ -556,8 +573,8 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
     tc_prep_out_weights(a.w, a.Co, a.Ci, h->wimg_out, st);
     if (tc_out_conv(h->a_last_bf16, h->wimg_out, a.bias, out, B, a.Hi, a.Wi, a.Ci, a.Co, apply_sigmoid, h->tc_error, st) == 0)
       return;
-    h->use_tc_out = false;  // tensor map could not be encoded: report through kcvae_tc_status
-    h->err = "tc_out_conv: cuTensorMapEncodeTiled failed; fp32 kernel used";
+    h->tc_failed = true;    // no silent downgrade: the entry point reports KCVAE_ERR_CUDA (tc_check)
+    return;
   }
 #endif
   conv_forward(CONV_S1, apply_sigmoid ? EPI_BIAS_SIGMOID : EPI_BIAS, a, st);
@@ -633,16 +650,15 @@ int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier
   image_stats(ia, st);
   if (h->world > 1) {
     stream_after(h, st, cs);
-    // the moment sums are needed by latent_backward (batch-global moments), a whole decoder backward later.  FULL tier:
-    // the per-position batch moments (reported-only x_std_loss) sit right behind them in the same allocation and ride in
-    // the same collective; min and max share one MIN all-reduce over [min, max, -max] (two collectives instead of four)
-    const bool merged = full && h->pos_sums == h->sums + kSumsLen;
-    KC_TRY(allreduce(h, h->sums, merged ? (int64_t)kSumsLen + 4 * h->P : (int64_t)sums_len(h), 1, 0, cs));
+    // the moment sums (<= 6 + 4 L doubles) are what latent_backward waits for: they go out alone, so the gradient path
+    // never waits behind reported-only payload.  FULL tier: the per-position batch moments of x / x_hat (4 P doubles,
+    // x_std_loss only) follow in their own collective; min and max share one MIN all-reduce over [min, max, -max].
+    KC_TRY(allreduce(h, h->sums, (int64_t)sums_len(h), 1, 0, cs));
 #ifndef KCVAE_EMU
     if (cs != st) cudaEventRecord(h->ev_sums, cs);
 #endif
     if (full) {   // reported-only metrics: nothing on the gradient path waits for these
-      if (!merged) KC_TRY(allreduce(h, h->pos_sums, 4 * h->P, 1, 0, cs));
+      KC_TRY(allreduce(h, h->pos_sums, 4 * h->P, 1, 0, cs));
       image_std_from_pos_sums(h->pos_sums, h->P, Bg, h->std_acc, h->dpartial, cs);
       KC_TRY(allreduce(h, h->minmax, 3, 0, 1, cs));      // [0] = global min, -[2] = global max (finalize_metrics)
     }
@@ -959,7 +975,7 @@ int step_impl(kcvae_model* h, const float* d_x, int B, const float* d_eps, const
   cudaStream_t cs = (h->world > 1 && h->comm_stream) ? h->comm_stream : st;
   KC_TRY(run_stats(h, d_x, xh, B, tier, 1, st, cs));
   KC_TRY(run_backward(h, x, B, st, cs));
-  if (h->tc_failed) return fail(h, KCVAE_ERR_CUDA, "tensor-core path: cuTensorMapEncodeTiled failed; use precision fp32");
+  KC_TRY(tc_check(h));
 #ifndef KCVAE_EMU
   h->w_external = ext;
 #endif
@@ -1011,6 +1027,8 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
     if ((rc = dalloc(h, &wi, tc_out_weight_image_elems(h->dc[h->L]))) || (rc = dalloc(h, &h->tc_error, 1))) return bail(rc);
     h->wimg_out = wi;
     cudaMemset(h->tc_error, 0, sizeof(int));
+    if (cudaMallocHost(reinterpret_cast<void**>(&h->tc_flag_host), sizeof(int)) == cudaSuccess) *h->tc_flag_host = 0;
+    else h->tc_flag_host = nullptr;
     if (h->L >= 1 && tc_convT_fwd_supported(h->dc[h->L - 1], h->dc[h->L])) {
       unsigned short* wc = nullptr;
       if ((rc = dalloc(h, &wc, tc_convT_weight_image_elems()))) return bail(rc);
@@ -1093,6 +1111,7 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->wimg_convT_few) cudaFree(h->wimg_convT_few);
   if (h->dl8) cudaFree(h->dl8);
   if (h->tc_error) cudaFree(h->tc_error);
+  if (h->tc_flag_host) cudaFreeHost(h->tc_flag_host);
   if (h->pos_sums == h->sums + kSumsLen) h->pos_sums = nullptr;   // lives inside the sums allocation
   double* dl[] = {h->dpartial, h->sums, h->std_acc, h->pos_sums};
   for (double* p : dl) if (p) cudaFree(p);
@@ -1213,7 +1232,13 @@ int kcvae_set_loss_weights(kcvae_handle h, float kurtosis_target, float w_mse, f
   h->lw = LossWeights{kurtosis_target, w_mse, w_kurtosis, w_skew, w_z_l1_reg};
   return KCVAE_OK;
 }
-int kcvae_seed(kcvae_handle h, uint64_t seed) { if (!h) return KCVAE_ERR_INVALID; h->seed = seed; h->rng_counter = 0; return KCVAE_OK; }
+int kcvae_seed(kcvae_handle h, uint64_t seed) {
+  if (!h) return KCVAE_ERR_INVALID;
+  h->seed_base = seed;
+  h->seed = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)h->rank;   // rank-distinct streams under data parallel
+  h->rng_counter = 0;
+  return KCVAE_OK;
+}
 
 // ---- data parallel ---------------------------------------------------------------------
 int kcvae_comm_unique_id(void* out_id128) {
@@ -1243,6 +1268,9 @@ int kcvae_comm_init(kcvae_handle h, const void* id128, int rank, int world_size)
   if (r != ncclSuccess) return fail(h, KCVAE_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
 #endif
   h->rank = rank; h->world = world_size;
+  // every replica draws its own reparameterisation noise: fold the rank into the Philox key (with one key the
+  // global batch would hold world-many copies of one eps tensor and bias the all-reduced kurtosis / skew moments)
+  h->seed = h->seed_base + 0x9E3779B97F4A7C15ULL * (uint64_t)rank;
 #ifndef KCVAE_EMU
   if (world_size > 1 && !h->comm_stream) {
     KC_CUDA(h, cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
@@ -1315,6 +1343,7 @@ int kcvae_decode(kcvae_handle h, const float* d_z, int batch, int apply_sigmoid,
   KC_TRY(ensure_fwd(h, batch));
   run_decoder(h, d_z, batch, apply_sigmoid, d_out, (cudaStream_t)stream, false);
   h->last_B = batch;
+  KC_TRY(tc_check(h));
   return post(h);
 }
 
@@ -1330,6 +1359,7 @@ int kcvae_forward(kcvae_handle h, const float* d_x, int batch, int training, con
   if (d_z) KC_CUDA(h, cudaMemcpyAsync(d_z, h->z, nb, cudaMemcpyDeviceToDevice, st));
   if (d_mean) KC_CUDA(h, cudaMemcpyAsync(d_mean, h->mean, nb, cudaMemcpyDeviceToDevice, st));
   if (d_logvar) KC_CUDA(h, cudaMemcpyAsync(d_logvar, h->logvar, nb, cudaMemcpyDeviceToDevice, st));
+  KC_TRY(tc_check(h));
   return post(h);
 }
 
@@ -1344,6 +1374,7 @@ int kcvae_loss(kcvae_handle h, const float* d_x, int batch, int training, const 
   KC_TRY(ensure_fwd(h, batch));
   float* xh = d_xhat ? d_xhat : h->xhat;
   run_forward(h, d_x, batch, training, d_eps, xh, st, false);
+  KC_TRY(tc_check(h));
   KC_TRY(run_stats(h, d_x, xh, batch, tier, 0, st, st));
   run_finalize(h, batch, tier, d_metrics, st);
   return post(h);
@@ -1376,6 +1407,7 @@ int kcvae_score(kcvae_handle h, const float* d_x, int batch, float* d_err, float
   const bool fusable = tail_fusable(h, batch);
   float* xh = d_xhat ? d_xhat : (fusable ? nullptr : h->xhat);
   run_forward(h, d_x, batch, 0, nullptr, xh, st, false, &tail);
+  KC_TRY(tc_check(h));
   if (!tail.done) {
     if (!xh) return fail(h, KCVAE_ERR_CUDA, "score: fused decoder tail unavailable (cuTensorMapEncodeTiled failed)");
     g_tag = "score";
@@ -1473,8 +1505,7 @@ int kcvae_train_step_host(kcvae_handle h, const float* h_x, int batch, const flo
   release_host_input(h, d_x, st);
   KC_CUDA(h, cudaMemcpyAsync(h_metrics, h->metrics_dev, KCVAE_NUM_METRICS * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (h_xhat) KC_CUDA(h, cudaMemcpyAsync(h_xhat, h->xhat, (size_t)batch * h->P * sizeof(float), cudaMemcpyDeviceToHost, st));
-  KC_CUDA(h, cudaStreamSynchronize(st));
-  return KCVAE_OK;
+  return tc_flag_check(h, st);
 }
 
 int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, float* h_score, void* stream) {
@@ -1489,8 +1520,7 @@ int kcvae_score_host(kcvae_handle h, const float* h_x, int batch, float* h_err, 
   release_host_input(h, d_x, st);
   if (h_err) KC_CUDA(h, cudaMemcpyAsync(h_err, h->err_buf, (size_t)batch * h->H * h->W * sizeof(float), cudaMemcpyDeviceToHost, st));
   KC_CUDA(h, cudaMemcpyAsync(h_score, h->score_buf, (size_t)batch * sizeof(float), cudaMemcpyDeviceToHost, st));
-  KC_CUDA(h, cudaStreamSynchronize(st));
-  return KCVAE_OK;
+  return tc_flag_check(h, st);
 }
 
 // ---- uint8 front end -------------------------------------------------------
@@ -1606,8 +1636,7 @@ int kcvae_score_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int 
   KC_TRY(kcvae_score(h, d_x, batch, h_err ? h->err_buf : nullptr, h->score_buf, nullptr, nullptr, stream));
   if (h_err) KC_CUDA(h, cudaMemcpyAsync(h_err, h->err_buf, (size_t)batch * h->H * h->W * sizeof(float), cudaMemcpyDeviceToHost, st));
   KC_CUDA(h, cudaMemcpyAsync(h_score, h->score_buf, (size_t)batch * sizeof(float), cudaMemcpyDeviceToHost, st));
-  KC_CUDA(h, cudaStreamSynchronize(st));
-  return KCVAE_OK;
+  return tc_flag_check(h, st);
 }
 
 int kcvae_train_step_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch, int in_h, int in_w, const float* h_eps,
@@ -1627,8 +1656,7 @@ int kcvae_train_step_host_u8(kcvae_handle h, const uint8_t* h_frames, int batch,
   KC_TRY(step_impl(h, d_x, batch, eps, nullptr, h->metrics_dev, h->xhat, tier, 1, st));
   KC_CUDA(h, cudaMemcpyAsync(h_metrics, h->metrics_dev, KCVAE_NUM_METRICS * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (h_xhat) KC_CUDA(h, cudaMemcpyAsync(h_xhat, h->xhat, (size_t)batch * h->P * sizeof(float), cudaMemcpyDeviceToHost, st));
-  KC_CUDA(h, cudaStreamSynchronize(st));
-  return KCVAE_OK;
+  return tc_flag_check(h, st);
 }
 
 // ---- introspection -------------------------------------------------------------------------

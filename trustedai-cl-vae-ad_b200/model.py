@@ -272,8 +272,10 @@ class AbstractCVAE:
         cfg.beta = self.beta
         cfg.learning_rate = float(t.get("learning_rate", 1e-3))
         cfg.max_batch = 0
-        prec = precision or m.get("precision", "fp32")
-        cfg.precision = _lib.PREC_BF16_TC if str(prec).lower() in ("bf16", "bf16_tc", "tc") else _lib.PREC_FP32
+        # default: the tcgen05 tensor-core path (bf16 operands - hi + lo pairs where the loss needs fp32-grade products -
+        # fp32 accumulation; holds north_star's 1e-3 / 1e-2 bars).  precision="fp32": CUDA-core kernels, tighter bars.
+        prec = precision or m.get("precision", "bf16")
+        cfg.precision = _lib.PREC_FP32 if str(prec).lower() in ("fp32", "f32", "float32") else _lib.PREC_BF16_TC
         return cfg
 
     # -- topology mirrors (src/abstract_cvae.py:22-92) -----------------------------------------
@@ -616,6 +618,8 @@ class AbstractCVAE:
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs} - " + " - ".join(f"{k}: {v:.6g}" for k, v in logs.items()))
             _call(callbacks, "on_epoch_end", epoch, logs)
+            if self._dev_type == "cuda":
+                self.tc_status()          # raises if a bounded tcgen05 barrier wait expired during this epoch
             if self.stop_training:
                 break
         _call(callbacks, "on_train_end")

@@ -15,9 +15,38 @@ def _iter(data):
     return data['train'] if isinstance(data, dict) else data
 
 
-def get_data_scale(model, config: dict, data):
+def set_statistics(err_reduced: torch.Tensor, emin: torch.Tensor, emax: torch.Tensor, distributed: bool = False):
+    """meu, sigma (population), min, max over the WHOLE frame set (do_anomaly_detection.py:63-71).  With the frames
+    sharded over ranks the set-level numbers come from one all-reduce of [sum s, sum s^2, n] (fp64)
+    and one MIN all-reduce of [min, -max]: every rank gets the statistics of the unsharded set."""
+    s64 = err_reduced.double()
+    acc = torch.stack([s64.sum(), (s64 * s64).sum(), torch.tensor(float(s64.numel()), dtype=torch.float64, device=s64.device)])
+    mm = torch.stack([emin.double(), -emax.double()])
+    if distributed:
+        import torch.distributed as dist
+        if dist.get_backend() != "nccl":
+            acc, mm = acc.cpu(), mm.cpu()
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mm, op=dist.ReduceOp.MIN)
+        acc, mm = acc.to(s64.device), mm.to(s64.device)
+    n = acc[2]
+    meu = acc[0] / n
+    # two-pass form on the local shard around the GLOBAL mean keeps fp32-grade scores from cancelling
+    dev = ((s64 - meu) ** 2).sum()
+    if distributed:
+        import torch.distributed as dist
+        d = dev.reshape(1).cpu() if dist.get_backend() != "nccl" else dev.reshape(1)
+        dist.all_reduce(d, op=dist.ReduceOp.SUM)
+        dev = d.to(s64.device)[0]
+    sigma = torch.sqrt(dev / n)
+    return meu.float(), sigma.float(), mm[0].float(), (-mm[1]).float()
+
+
+def get_data_scale(model, config: dict, data, distributed=None):
     """do_anomaly_detection.py:57-79.  Unlike the reference it does not keep every error map
-    in memory: min/max come from the per-frame (min,max) pairs the kernel emits."""
+    in memory: min/max come from the per-frame (min,max) pairs the kernel emits.
+    distributed (default: the model was attached with distribute()): `data` is this rank's shard of the frame set;
+    meu / sigma / min / max are those of the whole set, z_scores are this rank's frames."""
     scores, mins, maxs = [], [], []
     for batch in _iter(data):
         r = model.score(batch, return_err=False)
@@ -25,11 +54,12 @@ def get_data_scale(model, config: dict, data):
         mins.append(r['err_minmax'][:, 0])
         maxs.append(r['err_minmax'][:, 1])
     err_reduced = torch.cat(scores)
-    meu = err_reduced.mean()
-    sigma = err_reduced.std(unbiased=False)           # tf.math.reduce_std: population
+    if distributed is None:
+        distributed = getattr(model, "_dist_world", 1) > 1
+    meu, sigma, emin, emax = set_statistics(err_reduced, torch.cat(mins).min(), torch.cat(maxs).max(), bool(distributed))
     return {
-        'meu': _wrap(meu), 'sigma': _wrap(sigma),
-        'min': _wrap(torch.cat(mins).min()), 'max': _wrap(torch.cat(maxs).max()),
+        'meu': _wrap(meu), 'sigma': _wrap(sigma),            # tf.math.reduce_std: population
+        'min': _wrap(emin), 'max': _wrap(emax),
         'z_scores': _wrap((err_reduced - meu) / sigma),
     }
 

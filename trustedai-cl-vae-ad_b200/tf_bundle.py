@@ -176,7 +176,19 @@ def read_index(path: str, verify: bool = True) -> Dict[str, dict]:
 def read_bundle(prefix: str, verify: bool = True) -> Dict[str, np.ndarray]:
     """{checkpoint key: array} of ``<prefix>.index`` + ``<prefix>.data-*``."""
     entries = read_index(prefix + ".index", verify)
-    shards = sorted(p for p in os.listdir(os.path.dirname(prefix) or ".") if p.startswith(os.path.basename(prefix) + ".data-"))
+    # shard files are named exactly <prefix>.data-%05d-of-%05d; the shard count is the number of files matching that
+    # pattern with a common total (stray .tempstate / editor files next to them do not shift the shard index)
+    import re
+    pat = re.compile(re.escape(os.path.basename(prefix)) + r"\.data-(\d{5})-of-(\d{5})$")
+    byidx = {}
+    for fn in os.listdir(os.path.dirname(prefix) or "."):
+        m = pat.match(fn)
+        if m:
+            byidx.setdefault(int(m.group(2)), {})[int(m.group(1))] = fn
+    total = max((t for t, d in byidx.items() if len(d) == t), default=None)
+    if total is None:
+        raise ValueError(f"{prefix}: no complete set of .data-XXXXX-of-XXXXX shard files")
+    shards = [byidx[total][i] for i in range(total)]
     out = {}
     handles = {}
     for k, e in entries.items():
