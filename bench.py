@@ -1,15 +1,18 @@
 #!/usr/bin/env python3
-"""bench.py - KurtosisGlobalCVAE train step (+ anomaly scoring) throughput on B200.
+"""bench.py - KurtosisCVAE train step / anomaly scoring throughput on B200 (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
-  python bench.py --impl reference ...                     (CPU arm: the oracle port, TF absent)
+  python bench.py [--gpus N] [--steps K] [--warmup W]      default line = cfg2; N>1: launched under torchrun
+  python bench.py --config cfg1|cfg2|cfg3|cfg4|cfg5        one BASELINE config per line (see CONFIGS)
+  python bench.py --impl reference [--config ...]          CPU arm: the oracle port on the host cores (TF absent)
 
-One JSON line on stdout (rank 0).  A "step" is one train_step (forward, loss, backward,
-gradient all-reduce under DP, Adam) over one synthetic batch of README-config frames
-(224x300x3, layers [32,5], latent 32), BASELINE.json configs[1]: 32 frames per GPU, i.e.
-global batch 256 on 8 GPUs (weak scaling).  Inputs cycle through a pool larger than the
-126 MB L2.  `value` is device-timed with inputs resident in HBM; `e2e` is the same step
-through the host-buffer C-ABI call (pinned host frames, H2D and the metrics D2H inside).
+One JSON line on stdout (rank 0).  A "step" is one train_step (forward, loss, backward, gradient all-reduce under DP,
+Adam) - or, for cfg4, one scoring call (call_detailed + error map + per-frame score) - over one synthetic batch.
+Default = BASELINE.json configs[1]: KurtosisGlobalCVAE README config at GLOBAL batch 256, sharded 256/N per GPU
+(strong scaling, the curve SURVEY 8d defines: 256/1, 128/2, 64/4, 32/8); `--scaling weak --batch-per-gpu B` keeps the
+per-GPU batch fixed instead.  The default line also carries a short run of every other BASELINE config under
+"configs" and a >= 2 s sustained leg of the main config.  `value` is device-timed with inputs resident in HBM (inputs
+larger than / cycling through more than the 126 MB L2); `e2e` is the same step through the host-buffer C-ABI call
+(pinned host frames, H2D and the result D2H inside every step).
 """
 import argparse
 import importlib
@@ -25,10 +28,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-PER_GPU_BATCH = 32
 _REAL_STDOUT = sys.stdout
-CPU_SAMPLE_BATCH = 16
 L2_BYTES = 126 * 1024 * 1024
+
+# BASELINE.json configs (SURVEY 8d numbering cfg1..cfg5 = configs[0..4])
+CONFIGS = {
+    "cfg1": dict(kind="global", model="readme", global_batch=16, mode="train",
+                 workload="KurtosisGlobalCVAE README config 224x300x3 layers[32,5] latent32, batch 16 train_step (BASELINE configs[0])"),
+    "cfg2": dict(kind="global", model="readme", global_batch=256, mode="train",
+                 workload="KurtosisGlobalCVAE README config 224x300x3 layers[32,5] latent32, data-parallel train_step at global batch 256 (BASELINE configs[1])"),
+    "cfg3": dict(kind="single", model="readme", global_batch=128, mode="train",
+                 workload="KurtosisSingleCVAE README topology 224x300x3, batch 128 train_step (BASELINE configs[2])"),
+    "cfg4": dict(kind="global", model="readme", global_batch=1024, mode="score",
+                 workload="anomaly scoring (call_detailed + per-pixel error + per-frame score) of 224x300x3 frames at batch 1024 (BASELINE configs[3])"),
+    "cfg5": dict(kind="global", model="scaled", global_batch=512, mode="train",
+                 workload="scaled KurtosisGlobalCVAE 448x600x3 layers[64,128,32] enc64 dec64 latent256, train_step at global batch 512 (BASELINE configs[4])"),
+}
 
 
 def parse():
@@ -37,14 +52,46 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-per-gpu", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="one BASELINE config; default: cfg2 + a short run of the others")
+    ap.add_argument("--metric", default=None, choices=["train", "score"], help="score = --config cfg4")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--batch-per-gpu", type=int, default=0, help="per-GPU batch (implies --scaling weak)")
     ap.add_argument("--precision", default=os.environ.get("KCVAE_PRECISION", "bf16"),
-                    help="bf16: tcgen05 decoder kernels (bf16 operands, fp32 accumulate); fp32: CUDA-core path")
+                    help="bf16 (library default): tcgen05 kernels, bf16 operands (hi + lo pairs where needed), fp32 accumulate; fp32: CUDA-core path")
     ap.add_argument("--metrics-tier", default="full", choices=["full", "loss_only"],
                     help="full = the reference's whole metrics dict every step (default); loss_only skips reported-only terms")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-score", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-others", action="store_true", help="default run: skip the short runs of the other configs")
+    ap.add_argument("--no-sustained", action="store_true")
+    a = ap.parse_args()
+    if a.metric == "score" and not a.config:
+        a.config = "cfg4"
+    if a.batch_per_gpu:
+        a.scaling = "weak"
+    return a
+
+
+def model_config(name):
+    from oracle import kcvae_oracle as O
+    c = CONFIGS[name]
+    if c["model"] == "scaled":
+        return O.scaled_config()
+    return O.readme_config("KurtosisSingle" if c["kind"] == "single" else None)
+
+
+def local_batch(name, world, args):
+    if args.batch_per_gpu:
+        return args.batch_per_gpu
+    g = CONFIGS[name]["global_batch"]
+    return max(1, g // world)
+
+
+def config_dict(name, world, args):
+    """The workload description both arms print (identical for --impl ours / reference)."""
+    B = local_batch(name, world, args)
+    cfg = model_config(name)
+    return {"workload": CONFIGS[name]["workload"], "name": name, "image_size": cfg["data"]["image_size"],
+            "global_batch": B * world, "batch_per_gpu": B, "parallelism": f"dp{world}", "scaling": args.scaling}
 
 
 # --------------------------------------------------------------------------- clocks sampling
@@ -193,155 +240,129 @@ def hbm_peak():
     return 6650.0, "fallback"
 
 
+def score_step_bytes(cfg, B):
+    """SURVEY 8d scoring convention: x fp32 in, every inter-layer activation written + read once in bf16, err map + score out."""
+    from oracle import kcvae_oracle as O
+    t = O.topology(cfg)
+    I = t.H * t.W * t.C
+    A = sum(h * w * c for (h, w), c in zip(t.enc_hw, t.layers)) + t.enc_dense + 2 * t.latent + t.dec_h0 * t.dec_w0 * t.dec_dense
+    h, w = t.dec_h0, t.dec_w0
+    for f in reversed(t.layers):
+        h, w = 2 * h, 2 * w
+        A += h * w * f
+    return B * (4 * I + 2 * (2 * A) + 4 * t.H * t.W + 4)
+
+
 # --------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_rates(cfg, steps, warmup, batch):
-    """The reference's CPU implementation of the path.  TensorFlow is not installable in
-    this image, so this is the torch-CPU restatement (oracle), all host threads."""
+def cpu_oracle_rate(name, steps, warmup, batch, budget_s=None):
+    """The reference's CPU implementation of the path for config `name`.  TensorFlow is not installable in this image,
+    so this is the torch-CPU restatement (oracle), all host threads.  Returns (units/s, ms/step, steps run)."""
     import torch
     from oracle import kcvae_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
+    cfg = model_config(name)
     om = O.OracleModel(cfg)
     x, eps = O.synthetic_frames(batch, cfg), O.synthetic_eps(batch, cfg)
-    for _ in range(warmup):
-        om.train_step(x, eps)
-    t0 = time.perf_counter()
-    for s in range(steps):
-        om.train_step(x, eps)
-    dt = time.perf_counter() - t0
-    train = steps * batch / dt
     xt = torch.from_numpy(x)
-    for _ in range(1):
-        O.error_map(xt, om.call(xt)).sum(dim=(1, 2))
+    if CONFIGS[name]["mode"] == "score":
+        fn = lambda: O.error_map(xt, om.call(xt)).sum(dim=(1, 2))
+    else:
+        fn = lambda: om.train_step(x, eps)
     t0 = time.perf_counter()
-    ns = max(2, steps // 2)
-    for _ in range(ns):
-        O.error_map(xt, om.call(xt)).sum(dim=(1, 2))
-    score = ns * batch / (time.perf_counter() - t0)
-    return train, score, dt / steps * 1e3
+    for _ in range(max(1, warmup)):
+        fn()
+    per = (time.perf_counter() - t0) / max(1, warmup)
+    if budget_s is not None:
+        steps = max(2, min(steps, int(budget_s / max(per, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fn()
+    dt = time.perf_counter() - t0
+    return steps * batch / dt, dt / steps * 1e3, steps
+
+
+def cpu_sample_batch(name):
+    """Frames per CPU step: the config's batch, bounded so one step stays within seconds (throughput on the CPU does not
+    depend on the batch beyond a few frames)."""
+    cap = {"readme": 64, "scaled": 4}[CONFIGS[name]["model"]]
+    return min(CONFIGS[name]["global_batch"], cap)
+
+
+def metric_of(name):
+    return ("anomaly_score_frames_per_sec", "frames/s") if CONFIGS[name]["mode"] == "score" else ("train_images_per_sec", "images/s")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import kcvae_oracle as O
-    cfg = O.readme_config()
-    steps, warm = min(args.steps, 30), min(args.warmup, 3)
-    train, score, ms = cpu_oracle_rates(cfg, steps, warm, CPU_SAMPLE_BATCH)
+    name = args.config or "cfg2"
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    sb = cpu_sample_batch(name)
+    warm = min(max(args.warmup, 1), 3)
+    rate, ms, steps = cpu_oracle_rate(name, args.steps, warm, sb, budget_s=150.0)
     cores = os.cpu_count() or 1
-    sample = f"{steps} train_steps of batch {CPU_SAMPLE_BATCH} (README config) after {warm} warm-up; torch-CPU restatement, TF unavailable"
+    metric, unit = metric_of(name)
+    sample = (f"{steps} steps of {sb} frames ({'the whole batch' if sb == CONFIGS[name]['global_batch'] else 'a bounded sample of the batch'}) "
+              f"after {warm} warm-up; torch-CPU restatement of the TF path on {cores} threads, TF unavailable")
     line = {
-        "impl": "reference", "metric": "train_images_per_sec", "value": train, "unit": "images/s",
+        "impl": "reference", "metric": metric, "value": rate, "unit": unit,
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "KurtosisGlobalCVAE README config 224x300x3 layers[32,5] latent32 train_step",
-                   "batch": CPU_SAMPLE_BATCH},
-        "cpu_baseline": {"value": train, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
-                         "score_frames_per_sec": score},
-        "e2e": {"value": train, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(name, world, args),
+        "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
 
 
 # --------------------------------------------------------------------------------- GPU arm
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from oracle import kcvae_oracle as O
-    pkg = importlib.import_module("trustedai-cl-vae-ad_b200")
+class Ctx:
+    """Process-wide state of the GPU arm (device, distributed helpers, timers)."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = O.readme_config()
-    B = args.batch_per_gpu
-    model = pkg.load_model_from_config(cfg, device=local, precision=args.precision, metrics=args.metrics_tier)
-    model.set_weights(O.glorot_init(cfg, 1234))
-    model.compile(optimizer=pkg.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
-    model.seed(1000 + rank)
-    if world > 1:
-        model.distribute()
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.pkg = importlib.import_module("trustedai-cl-vae-ad_b200")
 
-    H, W, C = cfg["data"]["image_size"]
-    batch_bytes = B * H * W * C * 4
-    npool = max(2, math.ceil(L2_BYTES * 1.3 / batch_bytes) + 1)
-    g = torch.Generator(device=dev).manual_seed(42 + rank)
-    pool = [torch.rand((B, H, W, C), generator=g, device=dev, dtype=torch.float32) for _ in range(npool)]
-    host_pool = [torch.rand((B, H, W, C), dtype=torch.float32).pin_memory() for _ in range(min(npool, 4))]
-    metrics_host = torch.empty(16, dtype=torch.float32).pin_memory()
+    def sync_all(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local])
+            self.torch.cuda.synchronize(self.dev)
 
-    def sync_all():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier(device_ids=[local])
-            torch.cuda.synchronize(dev)
-
-    def max_over_ranks(ms):
-        if world == 1:
+    def max_over_ranks(self, ms):
+        if self.world == 1:
             return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([ms], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
+    def timed(self, fn, steps):
+        """K calls between two CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+        e0, e1 = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        self.sync_all()
         e0.record()
         for s in range(steps):
             fn(s)
         e1.record()
-        sync_all()
-        return max_over_ranks(e0.elapsed_time(e1))
+        self.sync_all()
+        return self.max_over_ranks(e0.elapsed_time(e1))
 
-    K, Wm = args.steps, max(args.warmup, 3)
-    train_fn = lambda s: model.train_step(pool[s % npool])          # eps: on-device Philox
-    for s in range(Wm):
-        train_fn(s)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.3)
-    n0 = model.launch_count()
-    t0 = clocks.mark()
-    ms_total = timed(train_fn, K)
-    t1 = clocks.mark()
-    launches = model.launch_count() - n0
-    clk = clocks.stop(t0, t1) if rank == 0 else None
-    value = world * B * K / (ms_total * 1e-3)
 
-    # end to end: pinned host frames -> H2D -> step -> metrics D2H, every step
-    def e2e_fn(s):   # H2D of step s+1 is started before step s is enqueued, so it overlaps its compute
-        model.prefetch_host(host_pool[(s + 1) % len(host_pool)])
-        model.train_step_host(host_pool[s % len(host_pool)], None, metrics_host)
-    for s in range(3):
-        e2e_fn(s)
-    ms_e2e = timed(e2e_fn, K)
-    e2e_value = world * B * K / (ms_e2e * 1e-3)
-    # the same step fed with uint8 host frames (what a camera / dataset delivers, SURVEY 8f row 2): a quarter of the H2D bytes
-    u8_pool = [torch.randint(0, 256, (B, H, W, C), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    def u8_fn(s):
-        model.prefetch_host_u8(u8_pool[(s + 1) % 2])
-        model.train_step_host_u8(u8_pool[s % 2], None, metrics_host)
-    for s in range(3):
-        u8_fn(s)
-    ms_u8 = timed(u8_fn, K)
-
-    # per-launch timing of the same K steps (events on the launching stream)
-    model.profile(True)
-    timed(train_fn, K)
-    rep = model.profile_report()
-    model.profile(False)
-    tab, step_bytes = algorithmic_bytes(cfg, B, world)
-    tot = sum(ms for _, ms in rep.values()) or 1.0
-    top = max(rep.items(), key=lambda kv: kv[1][1])
-    top_key, (top_calls, top_ms) = top
+def roofline_from_profile(rep, tab, step_bytes, ms_per_step, K):
     peak, peak_src = hbm_peak()
+    tot = sum(ms for _, ms in rep.values()) or 1.0
+    top_key, (top_calls, top_ms) = max(rep.items(), key=lambda kv: kv[1][1])
     # (the per-launch pass runs every kernel alone on the launching stream; the timed steps overlap the weight-gradient
     # kernels with the data-gradient chain on a side stream, so the launcher times add up to more than ms_per_step)
     roof = {"bound": "hbm", "kernel": top_key, "share_of_step": top_ms / tot, "unit": "GB/s", "peak": peak,
@@ -353,79 +374,213 @@ def run_ours(args):
         roof["frac"] = roof["achieved"] / peak
         roof["avg_launch_ms"] = top_ms / top_calls
         roof["algorithmic_bytes_per_launch"] = tab[top_key]
-        tr = measured_traffic(top_key)
-        if tr and tr.get("frames_per_launch") == B:
-            roof["traffic"] = tr["bytes_per_launch"]
-            roof["traffic_source"] = tr["source"]
     else:
         roof["achieved"], roof["frac"] = None, None
-    step_ach = step_bytes / (ms_total / K * 1e-3) / 1e9
+    step_ach = step_bytes / (ms_per_step * 1e-3) / 1e9
     roof["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_ach, "frac": step_ach / peak}
-    roof["kernel_breakdown_ms_per_step"] = {k: round(v[1] / K, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:12]}
-    # the same roofline for every launcher with an entry in the algorithmic-byte table (launch-averaged, events on the stream)
+    roof["kernel_breakdown_ms_per_step"] = {k: round(v[1] / K, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:14]}
     roof["per_kernel"] = [
         {"kernel": k, "ms": round(v[1] / v[0], 4), "GBps": round(tab[k] / (v[1] / v[0] * 1e-3) / 1e9, 1),
          "frac": round(tab[k] / (v[1] / v[0] * 1e-3) / 1e9 / peak, 3)}
         for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1]) if k in tab and v[0] > 0]
+    return roof, top_key
 
-    # anomaly scoring (do_anomaly_detection.py loops): frames/s resident and end to end
-    score_info = None
-    if not args.no_score:
-        Bs = 128
-        spool = [torch.rand((Bs, H, W, C), generator=g, device=dev, dtype=torch.float32) for _ in range(3)]
-        shost = [torch.rand((Bs, H, W, C), dtype=torch.float32).pin_memory() for _ in range(2)]
-        sc_host = torch.empty(Bs, dtype=torch.float32).pin_memory()
-        sfn = lambda s: model.score(spool[s % 3], return_err=True)
-        for s in range(2):
-            sfn(s)
-        Ks = max(3, K // 2)
-        ms_s = timed(sfn, Ks)
-        def hfn(s):
-            model.prefetch_host(shost[(s + 1) % 2])
-            model.score_host(shost[s % 2], sc_host)
-        hfn(0)
-        ms_sh = timed(hfn, Ks)
-        s8 = [torch.randint(0, 256, (Bs, H, W, C), dtype=torch.uint8).pin_memory() for _ in range(2)]
-        def h8(s):
-            model.prefetch_host_u8(s8[(s + 1) % 2])
-            model.score_host_u8(s8[s % 2], sc_host)
-        h8(0)
-        ms_s8 = timed(h8, Ks)
-        score_info = {"metric": "anomaly_score_frames_per_sec", "value": world * Bs * Ks / (ms_s * 1e-3),
-                      "e2e": world * Bs * Ks / (ms_sh * 1e-3), "e2e_uint8_frames": world * Bs * Ks / (ms_s8 * 1e-3),
-                      "unit": "frames/s", "batch_per_gpu": Bs,
-                      "outputs": "err map [B,H,W] + per-frame score"}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ctrain, cscore, cms = cpu_oracle_rates(cfg, 8, 2, CPU_SAMPLE_BATCH)
-        cpu = {"value": ctrain, "unit": "images/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"8 train_steps of batch {CPU_SAMPLE_BATCH} (README config), torch-CPU restatement of the TF path (TF unavailable)",
-               "score_frames_per_sec": cscore, "ms_per_step": cms}
-
-    if rank == 0:
-        line = {
-            "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
-            "warmup": Wm, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
-            "config": {"workload": "KurtosisGlobalCVAE README config 224x300x3 layers[32,5] latent32 train_step (BASELINE configs[1])",
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "metrics_tier": args.metrics_tier, "l2_policy": f"inputs cycle through a {npool * batch_bytes >> 20} MiB pool (> 126 MiB L2)",
-                       "precision": args.precision,
-                       "schedule": "weight-gradient kernels on a low-priority side stream beside the data-gradient chain (KCVAE_AUX_STREAM=0: serial)"},
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": batch_bytes,
-                    "d2h_bytes_per_step": 16 * 4, "ms_per_step": ms_e2e / K,
-                    "uint8_frames": {"value": world * B * K / (ms_u8 * 1e-3), "h2d_bytes_per_step": batch_bytes // 4,
-                                     "ms_per_step": ms_u8 / K}},
-            "gpu_launches": int(launches),
-            "clocks": clk,
-            "roofline": roof,
-            "cpu_baseline": cpu,
-            "score": score_info,
-        }
-        _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
+def run_config(ctx, name, K, Wm, full=True):
+    """One BASELINE config on the GPU arm.  full=False: the short form used for the "configs" block of the default line
+    (value, e2e, whole-step roofline; no per-kernel profile, no CPU leg, no sustained leg)."""
+    torch, args, world, rank, local, dev = ctx.torch, ctx.args, ctx.world, ctx.rank, ctx.local, ctx.dev
+    from oracle import kcvae_oracle as O
+    spec = CONFIGS[name]
+    cfg = model_config(name)
+    B = local_batch(name, world, args)
+    model = ctx.pkg.load_model_from_config(cfg, device=local, precision=args.precision, metrics=args.metrics_tier)
+    if spec["model"] == "readme":
+        model.set_weights(O.glorot_init(cfg, 1234))          # the scaled model keeps its on-device Glorot draw (78 M parameters)
+    model.compile(optimizer=ctx.pkg.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
+    model.seed(1000)                                          # the library folds the rank into the Philox key
     if world > 1:
-        dist.destroy_process_group()
+        model.distribute()
+    H, W, C = cfg["data"]["image_size"]
+    batch_bytes = B * H * W * C * 4
+    npool = max(2, math.ceil(L2_BYTES * 1.3 / batch_bytes) + 1)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    pool = [torch.rand((B, H, W, C), generator=g, device=dev, dtype=torch.float32) for _ in range(npool)]
+    nhost = 2 if batch_bytes > (64 << 20) else min(npool, 4)
+    host_pool = [torch.rand((B, H, W, C), dtype=torch.float32).pin_memory() for _ in range(nhost)]
+    metric, unit = metric_of(name)
+    scoring = spec["mode"] == "score"
+
+    if scoring:
+        sc_host = torch.empty(B, dtype=torch.float32).pin_memory()
+        step_fn = lambda s: model.score(pool[s % npool], return_err=True)
+        def e2e_fn(s):   # H2D of call s+1 is started before call s is enqueued, so it overlaps its compute
+            model.prefetch_host(host_pool[(s + 1) % nhost])
+            model.score_host(host_pool[s % nhost], sc_host)
+        d2h = B * 4
+    else:
+        metrics_host = torch.empty(16, dtype=torch.float32).pin_memory()
+        step_fn = lambda s: model.train_step(pool[s % npool])          # eps: on-device Philox
+        def e2e_fn(s):
+            model.prefetch_host(host_pool[(s + 1) % nhost])
+            model.train_step_host(host_pool[s % nhost], None, metrics_host)
+        d2h = 16 * 4
+
+    for s in range(Wm):
+        step_fn(s)
+    clocks = ClockSampler(local)
+    if rank == 0 and full:
+        clocks.start()
+        time.sleep(0.3)
+    n0 = model.launch_count()
+    t0 = clocks.mark()
+    ms_total = ctx.timed(step_fn, K)
+    t1 = clocks.mark()
+    launches = model.launch_count() - n0
+    clk = clocks.stop(t0, t1) if (rank == 0 and full) else None
+    value = world * B * K / (ms_total * 1e-3)
+    assert args.precision == "fp32" or model.tc_status() >= 0      # raises if a bounded tcgen05 barrier wait expired
+
+    for s in range(3):
+        e2e_fn(s)
+    ms_e2e = ctx.timed(e2e_fn, K)
+    e2e = {"value": world * B * K / (ms_e2e * 1e-3), "unit": unit, "h2d_bytes_per_step": batch_bytes,
+           "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K,
+           "input": "fp32 NHWC host frames (what train_step(x) / call(x) take), pinned, next batch prefetched on a copy stream"}
+    if spec["model"] == "readme":
+        # the same step fed with uint8 host frames (what a camera / dataset delivers before /255, SURVEY 8f row 2): 1/4 of the H2D bytes
+        u8_pool = [torch.randint(0, 256, (B, H, W, C), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        if scoring:
+            def u8_fn(s):
+                model.prefetch_host_u8(u8_pool[(s + 1) % 2])
+                model.score_host_u8(u8_pool[s % 2], sc_host)
+        else:
+            def u8_fn(s):
+                model.prefetch_host_u8(u8_pool[(s + 1) % 2])
+                model.train_step_host_u8(u8_pool[s % 2], None, metrics_host)
+        for s in range(3):
+            u8_fn(s)
+        ms_u8 = ctx.timed(u8_fn, K)
+        e2e["uint8_frames"] = {"value": world * B * K / (ms_u8 * 1e-3), "h2d_bytes_per_step": batch_bytes // 4, "ms_per_step": ms_u8 / K}
+        del u8_pool
+
+    tab, train_bytes = algorithmic_bytes(cfg, B, world)
+    step_bytes = score_step_bytes(cfg, B) if scoring else train_bytes
+    peak, _ = hbm_peak()
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": config_dict(name, world, args),
+        "run": {"precision": args.precision, "metrics_tier": args.metrics_tier,
+                "l2_policy": f"inputs cycle through {npool} buffers = {npool * batch_bytes >> 20} MiB (> 126 MiB L2)",
+                "schedule": "weight-gradient kernels on a low-priority side stream beside the data-gradient chain (KCVAE_AUX_STREAM=0: serial)",
+                "tc_status": int(model.tc_status())},
+        "e2e": e2e, "gpu_launches": int(launches),
+    }
+    if not full:
+        ach = step_bytes / (ms_total / K * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "unit": "GB/s", "peak": peak, "whole_step": {"algorithmic_bytes": step_bytes, "achieved": ach, "frac": ach / peak}}
+        del pool, host_pool, model
+        torch.cuda.empty_cache()
+        return line
+
+    # per-launch timing of the same K steps (events on the launching stream)
+    model.profile(True)
+    ctx.timed(step_fn, K)
+    rep = model.profile_report()
+    model.profile(False)
+    roof, top_key = roofline_from_profile(rep, tab, step_bytes, ms_total / K, K)
+    tr = measured_traffic(top_key)
+    if tr and tr.get("frames_per_launch") == B:
+        roof["traffic"] = tr["bytes_per_launch"]
+        roof["traffic_source"] = tr["source"]
+    line["clocks"] = clk
+    line["roofline"] = roof
+
+    if not args.no_sustained:
+        # sustained leg: the same step back to back for >= 2 s, with its own clock samples
+        Ks = max(K, int(math.ceil(2200.0 / (ms_total / K))))
+        cs = ClockSampler(local)
+        if rank == 0:
+            cs.start()
+            time.sleep(0.2)
+        ts0 = cs.mark()
+        ms_s = ctx.timed(step_fn, Ks)
+        ts1 = cs.mark()
+        line["sustained"] = {"steps": Ks, "seconds": ms_s * 1e-3, "ms_per_step": ms_s / Ks, "value": world * B * Ks / (ms_s * 1e-3),
+                             "unit": unit, "clocks": cs.stop(ts0, ts1) if rank == 0 else None}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sb = cpu_sample_batch(name)
+        crate, cms, csteps = cpu_oracle_rate(name, 6, 1, sb, budget_s=20.0)
+        line["cpu_baseline"] = {"value": crate, "unit": unit, "cores": os.cpu_count() or 1, "kind": "port", "ms_per_step": cms,
+                                "sample": f"{csteps} steps of {sb} frames of this config, torch-CPU restatement of the TF path (TF unavailable)"}
+    else:
+        line["cpu_baseline"] = None
+    del pool, host_pool, model
+    torch.cuda.empty_cache()
+    return line
+
+
+def dp_selfcheck(ctx):
+    """N > 1 only: data-parallel parity on the hardware the bench runs on.  Every rank computes loss + gradients of ITS
+    shard of one seeded batch (fixed eps) through the library's NCCL path; rank 0 also runs the whole batch on its own
+    GPU without a communicator.  Batch-global kurtosis / skew, every metric and the all-reduced gradient must agree."""
+    import numpy as np
+    from oracle import kcvae_oracle as O
+    torch, world, rank, local = ctx.torch, ctx.world, ctx.rank, ctx.local
+    out = {}
+    for kind in ("global", "single"):
+        cfg = O.readme_config("KurtosisSingle" if kind == "single" else None)
+        ws = O.glorot_init(cfg, 1234)
+        Bl = 2
+        x, eps = O.synthetic_frames(Bl * world, cfg), O.synthetic_eps(Bl * world, cfg)
+        m = ctx.pkg.load_model_from_config(cfg, device=local, precision=ctx.args.precision)
+        m.set_weights(ws)
+        m.distribute()
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        d, grads = m.loss_and_grads(x[sl], eps=eps[sl])
+        tc = int(m.tc_status())
+        if rank == 0:
+            ref = ctx.pkg.load_model_from_config(cfg, device=local, precision=ctx.args.precision)
+            ref.set_weights(ws)
+            dr, gr = ref.loss_and_grads(x, eps=eps)
+            merr = max(abs(float(d[k]) - float(dr[k])) / (abs(float(dr[k])) + 1e-12) for k in dr)
+            gerr = max(float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30)) for a, b in zip(grads, gr))
+            out[kind] = {"max_rel_metric_err": merr, "max_rel_grad_err": gerr, "frames": Bl * world, "tc_status": tc,
+                         "ok": bool(merr < 2e-3 and gerr < 2e-2)}
+            del ref
+        del m
+    torch.cuda.empty_cache()
+    ctx.sync_all()
+    return out if rank == 0 else None
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    K, Wm = args.steps, max(args.warmup, 3)
+    main_name = args.config or "cfg2"
+    line = run_config(ctx, main_name, K, Wm, full=True)
+    if ctx.world > 1:
+        line["dp_selfcheck"] = dp_selfcheck(ctx)
+    if not args.config and not args.no_others:
+        # every other BASELINE config, short form (their full lines: --config cfgN; committed under profiles/)
+        others = {}
+        for name in sorted(CONFIGS):
+            if name == main_name:
+                continue
+            if name == "cfg1" and ctx.world > 1:
+                continue                      # 16 frames are not sharded (SURVEY 8d)
+            big = CONFIGS[name]["model"] == "scaled"
+            others[name] = run_config(ctx, name, max(3, min(K, 4 if big else 10)), 3, full=False)
+        line["configs"] = others
+        if "cfg4" in others:                 # the scoring half of BASELINE.json's metric, also at top level
+            line["score"] = {k: others["cfg4"][k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "config")}
+    if ctx.rank == 0:
+        _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():

@@ -9,7 +9,7 @@ from kcvae_testlib import ROOT
 
 
 def test_reference_arm_prints_one_json_line():
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1", "--config", "cfg1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
@@ -19,7 +19,23 @@ def test_reference_arm_prints_one_json_line():
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and d["config"]["global_batch"] == 16 and d["config"]["name"] == "cfg1"
+
+
+def test_both_arms_describe_the_same_config():
+    """`config` is built by one function for --impl ours and --impl reference: the driver's same_config check compares them."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    a = argparse.Namespace(batch_per_gpu=0, scaling="strong")
+    for name, spec in bench.CONFIGS.items():
+        for world in (1, 2, 8):
+            c = bench.config_dict(name, world, a)
+            assert c["global_batch"] == spec["global_batch"] and c["batch_per_gpu"] * world == spec["global_batch"]
+            assert c["parallelism"] == f"dp{world}" and c["name"] == name
+    assert bench.local_batch("cfg2", 8, a) == 32 and bench.local_batch("cfg5", 8, a) == 64 and bench.local_batch("cfg4", 8, a) == 128
+    import oracle.kcvae_oracle as O
+    assert bench.score_step_bytes(O.readme_config(), 1) == 12_785_124          # SURVEY 8d: 12.79 MB / frame
 
 
 def test_algorithmic_byte_table_matches_the_survey_figures():

@@ -386,3 +386,40 @@ def test_side_stream_backward_is_bitwise_identical_to_the_serial_one(monkeypatch
     assert out[0][1] == out[1][1] and out[0][2] == out[1][2]
     for a, b in zip(out[0][3], out[1][3]):
         assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- tensor interop
+class _DLPackOnly:
+    """What a TF eager tensor looks like to the shim: only the DLPack protocol (tf.experimental.dlpack)."""
+
+    def __init__(self, t):
+        self._t = t
+
+    def __dlpack__(self, stream=None, **kw):
+        return self._t.__dlpack__() if stream is None else self._t.__dlpack__(stream=stream)
+
+    def __dlpack_device__(self):
+        return self._t.__dlpack_device__()
+
+
+class _CAIOnly:
+    """A device array that only speaks __cuda_array_interface__ (numba / cupy style)."""
+
+    def __init__(self, t):
+        self._t = t
+        self.__cuda_array_interface__ = t.__cuda_array_interface__
+
+
+def test_inputs_through_dlpack_and_cuda_array_interface():
+    cfg = small_config()
+    m, _ = make(cfg, BACKEND)
+    x = frames(cfg, 3)
+    want = m.call(x).numpy()
+    xd = torch.from_numpy(x).cuda()
+    for wrapped in (_DLPackOnly(xd), _CAIOnly(xd), _DLPackOnly(torch.from_numpy(x))):   # device DLPack, device CAI, host DLPack
+        got = m.call(wrapped).numpy()
+        np.testing.assert_array_equal(got, want)
+    # z handed to decode as a DLPack capsule holder (tools pass numpy z, TF passes eager tensors)
+    z = np.random.default_rng(3).standard_normal((2, int(cfg["model"]["latent_dimensions"]))).astype(np.float32)
+    np.testing.assert_array_equal(m.decode(_DLPackOnly(torch.from_numpy(z).cuda()), apply_sigmoid=True).numpy(),
+                                  m.decode(z, apply_sigmoid=True).numpy())
