@@ -223,6 +223,18 @@ int64_t kcvae_profile_report(char* buf, int64_t capacity);
  * then decoder stages; returns element count or negative status */
 int64_t kcvae_debug_activation(kcvae_handle h, int which, float* h_out, int64_t capacity);
 
+/* layer-level hooks of the general tensor-core convolution engine (csrc/tc_gen.cu), fp32 NHWC device tensors in and
+ * out: one forward-type product (kind 0: Conv2D k3 s2 / Conv2DTranspose s2 data gradient over a space-to-depth input,
+ * 1: Conv2DTranspose k3 s2 / Conv2D s2 data gradient, 2: 3x3 stride-1 - src/abstract_cvae.py:30-33, 81-89) or one weight +
+ * bias gradient.  w_mode 0: weight element (tap,k,n) at (tap*Ck + k)*Cn + n (HWIO), 1: (tap*Cn + n)*Ck + k ([kh,kw,out,in]).
+ * pre: 0 none, 1 bias+ReLU, 2 bias+sigmoid, 3 bias; out_mode 0 fp32 NHWC, 1 / 2 bf16 hi+lo planes (plain / space-to-depth)
+ * unpacked again; mask_mode 0 fp32 mask, 1 / 2 mask read from bf16 planes.  Used by the parity tests only. */
+int kcvae_gen_conv_test(int kind, int w_mode, int flip, int split, int pre, int in_x3, int out_mode, int mask_mode,
+                        const float* d_in, const float* d_w, const float* d_bias, const float* d_mask, float* d_out,
+                        int B, int Hi, int Wi, int Ck, int Cn, void* stream);
+int kcvae_gen_wgrad_test(int kind, int w_mode, int flip, int s_x3, const float* d_s, const float* d_u, float* d_dW, float* d_db,
+                         int B, int Hs, int Ws, int Cs, int Cu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,7 +18,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_LIB = os.path.join(EMU_DIR, "_build", "libkcvae_emu.so")
 
 SOURCES = ["conv.cu", "dense.cu", "loss.cu", "model.cu", "frontend.cu"]
-CUDA_ONLY_SOURCES = ["tc_conv.cu"]  # tcgen05 / TMA kernels: not emulated
+CUDA_ONLY_SOURCES = ["tc_conv.cu", "tc_gen.cu"]  # tcgen05 / TMA kernels: not emulated
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false", "-Xptxas", "-v"]

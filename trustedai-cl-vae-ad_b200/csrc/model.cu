@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include "tc_conv.h"
+#include "tc_gen.h"
 #endif
 
 using namespace kc;
@@ -1738,6 +1739,134 @@ int64_t kcvae_profile_report(char* buf, int64_t capacity) {
     buf[n] = 0;
   }
   return (int64_t)out.size();
+#endif
+}
+
+// ---- layer-level hooks of the general tensor-core convolution engine (tc_gen.cu) ------------------------------------
+// One product on fp32 NHWC device tensors: pack -> tcgen05 kernel -> unpack.  Parity tests drive every layer kind /
+// element map / epilogue of the engine through these without building a model.
+int kcvae_gen_conv_test(int kind, int w_mode, int flip, int split, int pre, int in_x3, int out_mode, int mask_mode,
+                        const float* d_in, const float* d_w, const float* d_bias, const float* d_mask, float* d_out,
+                        int B, int Hi, int Wi, int Ck, int Cn, void* stream) {
+#ifdef KCVAE_EMU
+  (void)kind; (void)w_mode; (void)flip; (void)split; (void)pre; (void)in_x3; (void)out_mode; (void)mask_mode; (void)d_in; (void)d_w;
+  (void)d_bias; (void)d_mask; (void)d_out; (void)B; (void)Hi; (void)Wi; (void)Ck; (void)Cn; (void)stream;
+  return fail(nullptr, KCVAE_ERR_UNSUPPORTED, "emu: tcgen05 kernels are not emulated");
+#else
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_in || !d_w || !d_out || B <= 0) return fail(nullptr, KCVAE_ERR_INVALID, "gen_conv_test: invalid arguments");
+  if (kind == GEN_CONV_S2 && ((Hi | Wi) & 1)) return fail(nullptr, KCVAE_ERR_INVALID, "gen_conv_test: stride-2 input must have even sizes");
+  const int KCk = (Ck + 7) / 8;
+  GenPlanes in{};
+  in.split = split; in.KC = KCk;
+  int Ho, Wo;
+  if (kind == GEN_CONV_S2) { in.layout = in_x3 ? GEN_X3 : GEN_S2D; in.H = Hi / 2; in.W = Wi / 2; Ho = Hi / 2; Wo = Wi / 2; }
+  else if (kind == GEN_CONVT_S2) { in.layout = GEN_PLAIN; in.H = Hi; in.W = Wi; Ho = 2 * Hi; Wo = 2 * Wi; }
+  else { in.layout = GEN_PLAIN; in.H = Hi; in.W = Wi; Ho = Hi; Wo = Wi; }
+  GenConvSpec sp{};
+  sp.kind = kind; sp.in_layout = in.layout; sp.Ck = Ck; sp.Cn = Cn; sp.KCk = KCk; sp.w_mode = w_mode; sp.flip = flip; sp.split = split;
+  sp.Hg = kind == GEN_CONVT_S2 ? Hi : Ho; sp.Wg = kind == GEN_CONVT_S2 ? Wi : Wo;
+  const char* why = "";
+  GenConvPlan* plan = gen_conv_plan_create(sp, &why);
+  if (!plan) return fail(nullptr, KCVAE_ERR_UNSUPPORTED, std::string("gen_conv_test: ") + why);
+  void *d_planes = nullptr, *d_img = nullptr, *d_oplanes = nullptr, *d_mplanes = nullptr;
+  int* d_err = nullptr;
+  int rc = KCVAE_OK;
+  const int KCo = (gen_conv_Cop(plan)) / 8;
+  GenPlanes out{}, mask{};
+  out.layout = out_mode == 2 ? GEN_S2D : GEN_PLAIN; out.KC = KCo; out.split = 1;
+  out.H = out_mode == 2 ? Ho / 2 : Ho; out.W = out_mode == 2 ? Wo / 2 : Wo;
+  mask = out; mask.split = 0; mask.layout = mask_mode == 2 ? GEN_S2D : GEN_PLAIN;
+  mask.H = mask_mode == 2 ? Ho / 2 : Ho; mask.W = mask_mode == 2 ? Wo / 2 : Wo;
+  auto done = [&](int code, const char* msg) {
+    cudaStreamSynchronize(st);
+    if (d_planes) cudaFree(d_planes); if (d_img) cudaFree(d_img); if (d_oplanes) cudaFree(d_oplanes);
+    if (d_mplanes) cudaFree(d_mplanes); if (d_err) cudaFree(d_err);
+    gen_conv_plan_free(plan);
+    return code == KCVAE_OK ? KCVAE_OK : fail(nullptr, code, msg);
+  };
+  if (cudaMalloc(&d_planes, in.units(B) * 16) != cudaSuccess || cudaMalloc(&d_img, gen_conv_weight_image_bytes(plan) + 16) != cudaSuccess ||
+      cudaMalloc(&d_oplanes, out.units(B) * 16) != cudaSuccess || cudaMalloc(&d_mplanes, mask.units(B) * 16) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&d_err), sizeof(int)) != cudaSuccess)
+    return done(KCVAE_ERR_CUDA, "gen_conv_test: cudaMalloc failed");
+  cudaMemsetAsync(d_err, 0, sizeof(int), st);
+  cudaMemsetAsync(d_oplanes, 0, out.units(B) * 16, st);
+  in.base = d_planes; out.base = d_oplanes; mask.base = d_mplanes;
+  if (in.layout == GEN_X3) gen_pack_x3(d_in, B, Hi, Wi, split, d_planes, st);
+  else if (in.layout == GEN_S2D) { GenPlanes full = in; gen_pack_nhwc(d_in, B, Hi, Wi, Ck, full, st); }
+  else gen_pack_nhwc(d_in, B, Hi, Wi, Ck, in, st);
+  if (d_mask && mask_mode) gen_pack_nhwc(d_mask, B, Ho, Wo, Cn, mask, st);
+  gen_conv_prep_weights(plan, d_w, d_img, st);
+  GenEpilogue e{};
+  e.pre = pre; e.bias = d_bias;
+  e.mask = (d_mask && mask_mode) ? &mask : nullptr;
+  e.mask_f32 = (d_mask && !mask_mode) ? d_mask : nullptr;
+  e.out = out_mode ? &out : nullptr;
+  e.out_f32 = out_mode ? nullptr : d_out;
+  rc = gen_conv_run(plan, in, d_img, e, B, d_err, "gen_conv_test", st);
+  if (rc != 0) return done(KCVAE_ERR_CUDA, "gen_conv_test: launcher failed (tensor map / plane count)");
+  if (out_mode) gen_unpack_nhwc(out, B, Ho, Wo, Cn, d_out, st);
+  int flag = 0;
+  cudaMemcpyAsync(&flag, d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_conv_test: kernel failed");
+  if (flag) return done(KCVAE_ERR_CUDA, "gen_conv_test: bounded mbarrier wait expired");
+  return done(KCVAE_OK, "");
+#endif
+}
+
+int kcvae_gen_wgrad_test(int kind, int w_mode, int flip, int s_x3, const float* d_s, const float* d_u, float* d_dW, float* d_db,
+                         int B, int Hs, int Ws, int Cs, int Cu, void* stream) {
+#ifdef KCVAE_EMU
+  (void)kind; (void)w_mode; (void)flip; (void)s_x3; (void)d_s; (void)d_u; (void)d_dW; (void)d_db; (void)B; (void)Hs; (void)Ws; (void)Cs;
+  (void)Cu; (void)stream;
+  return fail(nullptr, KCVAE_ERR_UNSUPPORTED, "emu: tcgen05 kernels are not emulated");
+#else
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_s || !d_u || !d_dW || B <= 0) return fail(nullptr, KCVAE_ERR_INVALID, "gen_wgrad_test: invalid arguments");
+  GenPlanes S{}, U{};
+  S.KC = (Cs + 7) / 8; U.KC = (Cu + 7) / 8;
+  int Hu, Wu;          // full-resolution dims of the gradient tensor as fp32 NHWC
+  if (kind == GEN_CONV_S2) {          // S: layer input at (Hs, Ws), stored S2D / X3; U: gradient at (Hs/2, Ws/2), PLAIN
+    if ((Hs | Ws) & 1) return fail(nullptr, KCVAE_ERR_INVALID, "gen_wgrad_test: stride-2 input must have even sizes");
+    S.layout = s_x3 ? GEN_X3 : GEN_S2D; S.H = Hs / 2; S.W = Ws / 2;
+    U.layout = GEN_PLAIN; U.H = Hs / 2; U.W = Ws / 2; Hu = Hs / 2; Wu = Ws / 2;
+  } else if (kind == GEN_CONVT_S2) {  // S: layer input at (Hs, Ws), PLAIN; U: gradient at (2Hs, 2Ws), stored S2D
+    S.layout = GEN_PLAIN; S.H = Hs; S.W = Ws;
+    U.layout = GEN_S2D; U.H = Hs; U.W = Ws; Hu = 2 * Hs; Wu = 2 * Ws;
+  } else {
+    S.layout = GEN_PLAIN; S.H = Hs; S.W = Ws; U.layout = GEN_PLAIN; U.H = Hs; U.W = Ws; Hu = Hs; Wu = Ws;
+  }
+  GenWgradSpec sp{};
+  sp.kind = kind; sp.flip = flip; sp.s_layout = S.layout; sp.s_KC = S.KC; sp.u_layout = U.layout; sp.u_KC = U.KC;
+  sp.Cs = Cs; sp.Cu = Cu; sp.w_mode = w_mode; sp.Hg = U.H; sp.Wg = U.W;
+  const char* why = "";
+  GenWgradPlan* plan = gen_wgrad_plan_create(sp, &why);
+  if (!plan) return fail(nullptr, KCVAE_ERR_UNSUPPORTED, std::string("gen_wgrad_test: ") + why);
+  void *ds = nullptr, *du = nullptr;
+  float* part = nullptr;
+  int* d_err = nullptr;
+  auto done = [&](int code, const char* msg) {
+    cudaStreamSynchronize(st);
+    if (ds) cudaFree(ds); if (du) cudaFree(du); if (part) cudaFree(part); if (d_err) cudaFree(d_err);
+    gen_wgrad_plan_free(plan);
+    return code == KCVAE_OK ? KCVAE_OK : fail(nullptr, code, msg);
+  };
+  if (cudaMalloc(&ds, S.units(B) * 16) != cudaSuccess || cudaMalloc(&du, U.units(B) * 16) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&part), gen_wgrad_partial_floats(plan) * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&d_err), sizeof(int)) != cudaSuccess)
+    return done(KCVAE_ERR_CUDA, "gen_wgrad_test: cudaMalloc failed");
+  cudaMemsetAsync(d_err, 0, sizeof(int), st);
+  S.base = ds; U.base = du;
+  if (S.layout == GEN_X3) gen_pack_x3(d_s, B, Hs, Ws, 0, ds, st);
+  else gen_pack_nhwc(d_s, B, Hs, Ws, Cs, S, st);
+  gen_pack_nhwc(d_u, B, Hu, Wu, Cu, U, st);
+  if (gen_wgrad_run(plan, S, U, d_dW, d_db, part, B, d_err, "gen_wgrad_test", st) != 0)
+    return done(KCVAE_ERR_CUDA, "gen_wgrad_test: launcher failed (tensor map / plane count)");
+  int flag = 0;
+  cudaMemcpyAsync(&flag, d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_wgrad_test: kernel failed");
+  if (flag) return done(KCVAE_ERR_CUDA, "gen_wgrad_test: bounded mbarrier wait expired");
+  return done(KCVAE_OK, "");
 #endif
 }
 

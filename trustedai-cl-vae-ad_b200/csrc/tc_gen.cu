@@ -1,0 +1,1104 @@
+// tc_gen.cu - general-shape tcgen05 / TMEM / TMA convolution engine: see tc_gen.h.
+//
+// Forward-type products (tc_gconv_kernel).  One persistent CTA per SM walks tiles of 4*MT rows x TW columns of the
+// GEMM pixel grid.  A tile's K dimension is cut into slabs of chunk planes; per slab the producer warp issues one TMA
+// box per plane (rows x 32 pixels x 16 B: the no-swizzle K-major operand with linear rows, tc_common.cuh) plus one bulk
+// copy of the slab's B-operand block from the prepared weight image.  The MMA warp runs a host-built list: every entry
+// is one tcgen05.mma M128 x N x K16 whose A descriptor starts at (plane, tap shift) inside the halo tile - taps are start
+// addresses, SAME padding is TMA zero fill, stride-2 layers become stride-1 products through the space-to-depth element
+// map.  Accumulators live in TMEM (double buffered when they fit); 8 epilogue warps apply bias / ReLU / sigmoid / the
+// ReLU mask of a data gradient and store bf16 planes (PLAIN or S2D, hi + lo) and / or fp32 NHWC.
+//
+// Weight-gradient products (tc_gwgrad_kernel).  Both operands are read MN-major from the same kind of tiles with
+// K = 16 pixels per MMA; the unshifted operand comes through a windowed tensor map whose innermost extent is the tile
+// width, so TMA zero fill clears the tile's padding columns; accumulators persist in TMEM over all tiles of the CTA;
+// a bias gradient is one more accumulator against a plane of ones.  Each CTA dumps its accumulators once; a gather
+// kernel folds the CTAs in a fixed order (deterministic) straight into the Keras weight layout.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda.h>
+
+#include "kernels.h"
+#include "tc_common.cuh"
+#include "tc_gen.h"
+
+namespace kc {
+
+using namespace tc;
+
+namespace {
+
+constexpr int GP = 32;                 // tile pitch: pixels per shared-memory row
+constexpr int G1_MAXMMA = 768;
+constexpr int G1_MAXSLAB = 32;
+constexpr int G1_MAXPL = 32;           // planes per slab (hi + lo)
+constexpr int G1_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
+constexpr int G1_STAGES = 2;
+constexpr size_t SMEM_BUDGET = 225 * 1024;
+
+struct G1Mma { uint32_t a_off, a_lbo, b_off, d_col, n, acc; };
+struct G1Slab { int mma0, mma_n, nplanes, b_src, b_bytes, pad0, pad1, pad2; int plane[G1_MAXPL]; };
+struct G1Group { int slab0, slab_n, a_par, pad; };
+struct G1PlanDev {
+  int n_groups, MT, NB, acc_cols, R_in, row0, col0, TW, in_PL, n_slabs, n_mma, type;
+  uint32_t CHb, a_region, stage_bytes, Cop;
+  G1Group groups[2];
+  G1Slab slabs[G1_MAXSLAB];
+  G1Mma mma[G1_MAXMMA];
+};
+constexpr uint32_t G1_PLAN_BYTES = ((sizeof(G1PlanDev) + 1023) / 1024) * 1024;
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* mbar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(mbar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* mbar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(mbar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(mbar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+// plane tensor addressing (16-byte units)
+struct PlaneRef {
+  uint4* base;
+  int layout, KC, PLimg, H, W;     // PLimg = planes per image (hi + lo); H, W = plane dims
+};
+__device__ __forceinline__ int64_t unit_index(const PlaneRef& t, int n, int oy, int ox, int chunk, int lo) {
+  if (t.layout == GEN_S2D) {
+    const int par = ((oy & 1) << 1) | (ox & 1);
+    const int plane = (lo * 4 + par) * t.KC + chunk;
+    return (((int64_t)n * t.PLimg + plane) * t.H + (oy >> 1)) * t.W + (ox >> 1);
+  }
+  const int plane = lo * t.KC + chunk;
+  return (((int64_t)n * t.PLimg + plane) * t.H + oy) * t.W + ox;
+}
+
+struct G1Params {
+  const G1PlanDev* plan;
+  const unsigned char* wimg;
+  int B, Hg, Wg, tiles_y, tiles_x, num_tiles;
+  int in_PL;         // planes per image of the K-side tensor (hi + lo)
+  int pre;
+  const float* bias;
+  PlaneRef mask; int has_mask;
+  const float* mask_f32;
+  PlaneRef out; int has_out, out_lo;
+  float* out_f32;
+  int Cn;            // real N-side channels
+  int Ho, Wo;        // logical output dims
+  int* error_flag;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// one 8-channel group of one output pixel: pre-op, mask, stores
+__device__ __forceinline__ void g1_emit8(const G1Params& p, float* v, int n, int oy, int ox, int chunk) {
+  const int c0 = chunk * 8;
+  if (p.pre != GEN_PRE_NONE) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float y = v[k] + (c0 + k < p.Cn ? __ldg(p.bias + c0 + k) : 0.f);
+      if (p.pre == GEN_PRE_BIAS_RELU) y = fmaxf(y, 0.f);
+      else if (p.pre == GEN_PRE_BIAS_SIGMOID) y = 1.0f / (1.0f + __expf(-y));
+      v[k] = c0 + k < p.Cn ? y : 0.f;
+    }
+  }
+  if (p.has_mask) {
+    const uint4 m = __ldg(p.mask.base + unit_index(p.mask, n, oy, ox, chunk, 0));
+    const uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t h = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;       // bf16 bits: positive <=> sign clear and not zero
+      if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[k] = 0.f;
+    }
+  }
+  if (p.mask_f32) {
+    const float* mk = p.mask_f32 + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.Cn + c0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c0 + k < p.Cn && !(__ldg(mk + k) > 0.f)) v[k] = 0.f;
+  }
+  if (p.has_out) {
+    uint32_t h4[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h4[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+    p.out.base[unit_index(p.out, n, oy, ox, chunk, 0)] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+    if (p.out_lo) {
+      uint32_t l4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float r0 = v[2 * e] - __uint_as_float(h4[e] << 16);
+        const float r1 = v[2 * e + 1] - __uint_as_float(h4[e] & 0xFFFF0000u);
+        l4[e] = pack_bf16x2(r0, r1);
+      }
+      p.out.base[unit_index(p.out, n, oy, ox, chunk, 1)] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+    }
+  }
+  if (p.out_f32) {
+    float* o = p.out_f32 + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.Cn + c0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (c0 + k < p.Cn) o[k] = v[k];
+  }
+}
+
+__global__ void __launch_bounds__(G1_THREADS, 1)
+tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  G1PlanDev* plan = reinterpret_cast<G1PlanDev*>(smem);
+  unsigned char* stages = smem + G1_PLAN_BYTES;
+  __shared__ uint64_t full_bar[G1_STAGES], empty_bar[G1_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  {  // plan -> shared memory (header + the used slab / MMA entries)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.plan);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
+    const int nw = (int)(sizeof(G1PlanDev) / 4);
+    for (int i = threadIdx.x; i < nw; i += G1_THREADS) dst[i] = __ldg(src + i);
+    // stages start as zeros: the pad units behind a slab's last plane are read by dummy K chunks (zero weights) and by
+    // discarded rows, and 0 * NaN would poison an accumulator
+    uint4* z = reinterpret_cast<uint4*>(stages);
+    const int nz = (int)((size_t)G1_STAGES * __ldg(&p.plan->stage_bytes) / 16);
+    for (int i = threadIdx.x; i < nz; i += G1_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < G1_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    fence_mbar_init();
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int n_groups = plan->n_groups, MT = plan->MT, NB = plan->NB, acc_cols = plan->acc_cols;
+  const int TW = plan->TW, TRr = 4 * MT;
+  const uint32_t stage_bytes = plan->stage_bytes;
+  const int per_img = p.tiles_y * p.tiles_x;
+
+  if (warp == 0) {
+    // ================================ TMA producer ========================================
+    if (lane == 0) {
+      const uint32_t CHb = plan->CHb, a_region = plan->a_region;
+      const int row0 = plan->row0, col0 = plan->col0, in_PL = p.in_PL;
+      int it = 0;
+      bool ok = true;
+      for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x) {
+        const int grp = t % n_groups, tt = t / n_groups;
+        const int n = tt / per_img, rem = tt % per_img;
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        const G1Group g = plan->groups[grp];
+        for (int sl = g.slab0; sl < g.slab0 + g.slab_n; ++sl, ++it) {
+          const int s = it % G1_STAGES;
+          const uint32_t ph = (it / G1_STAGES) & 1;
+          if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; ok = false; break; }
+          const G1Slab* S = &plan->slabs[sl];
+          unsigned char* dst = stages + (size_t)s * stage_bytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)S->nplanes * CHb + (uint32_t)S->b_bytes);
+          for (int pl = 0; pl < S->nplanes; ++pl)
+            tma_load_3d(dst + (size_t)pl * CHb, &tmap, &full_bar[s], (tx * TW + col0) * 8, ty * TRr + row0, n * in_PL + S->plane[pl]);
+          bulk_load(dst + a_region, p.wimg + S->b_src, (uint32_t)S->b_bytes, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==========================================
+    const bool leader = elect_one();
+    int it = 0, tcount = 0;
+    bool ok = true;
+    for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++tcount) {
+      const int grp = t % n_groups;
+      const G1Group g = plan->groups[grp];
+      const int buf = tcount % NB;
+      const uint32_t bph = (tcount / NB) & 1;
+      if (!mbar_wait(&tempty_bar[buf], bph ^ 1)) { if (leader) *p.error_flag = 1; break; }
+      fence_after_sync();
+      for (int sl = g.slab0; sl < g.slab0 + g.slab_n; ++sl, ++it) {
+        const int s = it % G1_STAGES;
+        const uint32_t ph = (it / G1_STAGES) & 1;
+        if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
+        fence_after_sync();
+        const uint32_t base = smem_u32(stages + (size_t)s * stage_bytes);
+        const int m0 = plan->slabs[sl].mma0, m1 = m0 + plan->slabs[sl].mma_n;
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t dbase = tmem + (uint32_t)((buf * MT + mt) * acc_cols);
+          const uint32_t abase = base + (uint32_t)mt * 2048u;
+#pragma unroll 2
+          for (int i = m0; i < m1; ++i) {
+            const G1Mma m = plan->mma[i];
+            const uint64_t da = make_desc_kmajor_noswz(abase + m.a_off, m.a_lbo, 128);
+            const uint64_t db = make_desc_kmajor_noswz(base + m.b_off, m.n * 16, 128);
+            const uint32_t idesc = make_idesc_bf16_f32(128, (int)m.n);
+            if (leader) mma_bf16_ss(dbase + m.d_col, da, db, idesc, m.acc);
+          }
+        }
+        if (leader) mma_commit(&empty_bar[s]);
+        __syncwarp();
+      }
+      if (ok && leader) mma_commit(&tfull_bar[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ================================ epilogue warps ======================================
+    const int e = warp - 2;
+    const int lg = warp & 3;                      // TMEM lane group this warp may access
+    const int half = e >> 2;                      // two warps per lane group share the (M-tile, column block) units
+    const int type = plan->type;
+    const int Cop = (int)plan->Cop;
+    const int NCB = (acc_cols + 31) / 32;
+    int tcount = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
+      const int grp = t % n_groups, tt = t / n_groups;
+      const int n = tt / per_img, rem = tt % per_img;
+      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+      const int a_par = plan->groups[grp].a_par;
+      const int buf = tcount % NB;
+      const uint32_t bph = (tcount / NB) & 1;
+      if (!mbar_wait(&tfull_bar[buf], bph)) { if (lane == 0) *p.error_flag = 1; break; }
+      fence_after_sync();
+      for (int u = half; u < MT * NCB; u += 2) {
+        const int mt = u / NCB, cb = u % NCB;
+        const int ncols = min(32, acc_cols - cb * 32);
+        const int q = mt * 128 + lg * 32 + lane;
+        const int r = q / GP, c = q % GP;
+        const int gy = ty * TRr + r, gx = tx * TW + c;
+        const bool valid = c < TW && gy < p.Hg && gx < p.Wg;
+        const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * MT + mt) * acc_cols + cb * 32);
+        float v[32];
+        if (ncols == 32) tmem_ld32(ta, v);
+        else tmem_ld16(ta, v);
+        if (valid) {
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            if (j8 * 8 < ncols) {
+              const int col0 = cb * 32 + j8 * 8;
+              int oy = gy, ox = gx, chunk = col0 >> 3;
+              if (type == GEN_CONVT_S2) {
+                const int b = col0 / Cop;
+                chunk = (col0 - b * Cop) >> 3;
+                oy = 2 * gy + a_par; ox = 2 * gx + b;
+              }
+              g1_emit8(p, v + j8 * 8, n, oy, ox, chunk);
+            }
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// fp32 weights -> bf16 image through a gather table: idx >= 0: hi part of w[idx]; idx | LO_FLAG: lo part; -1: zero
+constexpr int32_t LO_FLAG = 0x40000000;
+__global__ void gen_gather_weights_kernel(const float* __restrict__ w, const int32_t* __restrict__ idx, int64_t n, __nv_bfloat16* img) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t e = idx[i];
+    float v = 0.f;
+    if (e >= 0) {
+      const float x = __ldg(w + (e & (LO_FLAG - 1)));
+      const __nv_bfloat16 hi = __float2bfloat16(x);
+      v = (e & LO_FLAG) ? x - __bfloat162float(hi) : x;
+    }
+    img[i] = __float2bfloat16(v);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn gen_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// plane tensor [B*PL][H][W*8] bf16: box = `rows` rows of 32 pixels of one plane
+CUresult make_planes_map(CUtensorMap* tmap, const void* base, int64_t nplanes, int H, int W, int rows) {
+  EncodeTiledFn enc = gen_encode_fn();
+  const cuuint64_t gdim[3] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)nplanes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint32_t box[3] = {GP * 8, (cuuint32_t)rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+// the same tensor cut into windows of TW pixels: dims (TW*8, W/TW, H, planes); a 32-pixel box starting at element 0 of a
+// window gets its last 32-TW pixels zero filled (they lie outside the innermost extent)
+CUresult make_window_map(CUtensorMap* tmap, const void* base, int64_t nplanes, int H, int W, int TW, int rows) {
+  EncodeTiledFn enc = gen_encode_fn();
+  const cuuint64_t gdim[4] = {(cuuint64_t)TW * 8, (cuuint64_t)(W / TW), (cuuint64_t)H, (cuuint64_t)nplanes};
+  const cuuint64_t gstr[3] = {(cuuint64_t)TW * 16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+  const cuuint32_t box[4] = {GP * 8, 1, (cuuint32_t)rows, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// (parity, channel) of K element (plane, slot) of a plane tensor; channel = -1: unused slot
+void elem_of(int layout, int KC, int C, int plane, int slot, int* par, int* ch) {
+  if (layout == GEN_X3) {
+    const int e = plane * 8 + slot;
+    *par = e / 3; *ch = e < 12 ? e % 3 : -1;
+    if (e >= 12) *par = 0;
+  } else if (layout == GEN_S2D) {
+    *par = plane / KC;
+    const int c = (plane % KC) * 8 + slot;
+    *ch = c < C ? c : -1;
+  } else {
+    *par = -1;
+    const int c = plane * 8 + slot;
+    *ch = c < C ? c : -1;
+  }
+}
+int hi_planes(int layout, int KC) { return layout == GEN_S2D ? 4 * KC : (layout == GEN_X3 ? 2 : KC); }
+
+}  // namespace
+
+// ============================================================================================
+//                                  forward-type plan
+// ============================================================================================
+struct GenConvPlan {
+  GenConvSpec spec;
+  G1PlanDev host;
+  G1PlanDev* dev = nullptr;
+  std::vector<int32_t> table;     // weight gather table, one entry per bf16 element of the image
+  int32_t* table_dev = nullptr;
+  size_t smem = 0;
+};
+
+GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
+  static const char* msg = "";
+  auto no = [&](const char* m) -> GenConvPlan* { msg = m; if (why_not) *why_not = msg; return nullptr; };
+  if (s.Ck <= 0 || s.Cn <= 0 || s.Hg <= 0 || s.Wg <= 0) return no("empty shape");
+  const int Cop = (s.Cn + 15) / 16 * 16;
+  const int n_groups = s.kind == GEN_CONVT_S2 ? 2 : 1;
+  const int acc_cols = s.kind == GEN_CONVT_S2 ? 2 * Cop : Cop;
+  if (acc_cols > 256) return no("more than 256 accumulator columns per M-tile");
+  const int PLh = hi_planes(s.in_layout, s.KCk);
+  if (s.kind == GEN_CONV_S2 && s.in_layout == GEN_PLAIN) return no("stride-2 product needs an S2D / X3 input");
+  if (s.kind != GEN_CONV_S2 && s.in_layout != GEN_PLAIN) return no("product needs a PLAIN input");
+
+  GenConvPlan* P = new GenConvPlan();
+  P->spec = s;
+  G1PlanDev& D = P->host;
+  memset(&D, 0, sizeof(D));
+  D.n_groups = n_groups; D.type = s.kind; D.Cop = (uint32_t)Cop; D.acc_cols = acc_cols;
+  D.MT = (4 * acc_cols <= 512) ? 2 : 1;
+  D.NB = 2;
+  int halo_r, halo_c;
+  if (s.kind == GEN_CONV_S2) { D.row0 = 0; D.col0 = 0; halo_r = 1; halo_c = 1; }
+  else if (s.kind == GEN_CONVT_S2) { D.row0 = -1; D.col0 = -1; halo_r = 1; halo_c = 1; }
+  else { D.row0 = -1; D.col0 = -1; halo_r = 2; halo_c = 2; }
+  D.TW = GP - halo_c;
+  D.R_in = 4 * D.MT + halo_r;
+  D.CHb = (uint32_t)D.R_in * GP * 16;
+  D.in_PL = PLh * (s.split ? 2 : 1);
+
+  struct Tap { int t0, t1, shift; };     // (di,dj) or (kh,kw)
+  std::vector<Tap> taps;
+  if (s.kind == GEN_CONV_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, di * GP + dj});
+  else if (s.kind == GEN_CONVT_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, (1 - di) * GP + (1 - dj)});
+  else for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw)
+    taps.push_back({kh, kw, s.flip ? (2 - kh) * GP + (2 - kw) : kh * GP + kw});
+
+  // weight source of (group a, tap, K element (plane, slot), column n), -1 = structural zero
+  auto wsrc = [&](int a, const Tap& tp, int plane, int slot, int n) -> int32_t {
+    int par, ch;
+    elem_of(s.in_layout, s.KCk, s.Ck, plane, slot, &par, &ch);
+    if (ch < 0) return -1;
+    int kh, kw, cn;
+    if (s.kind == GEN_CONV_S2) {
+      kh = 2 * tp.t0 + (par >> 1); kw = 2 * tp.t1 + (par & 1); cn = n;
+    } else if (s.kind == GEN_CONVT_S2) {
+      const int b = n / Cop;
+      kh = a + 2 * tp.t0; kw = b + 2 * tp.t1; cn = n - b * Cop;
+    } else {
+      kh = tp.t0; kw = tp.t1; cn = n;
+    }
+    if (kh > 2 || kw > 2 || cn >= s.Cn) return -1;
+    const int tap = kh * 3 + kw;
+    return s.w_mode == 0 ? (tap * s.Ck + ch) * s.Cn + cn : (tap * s.Cn + cn) * s.Ck + ch;
+  };
+  // is K chunk (plane) of this tap / group structurally non-zero, and how many columns does the tap reach
+  auto tap_n = [&](int a, const Tap& tp) -> int {
+    if (s.kind != GEN_CONVT_S2) return Cop;
+    if (a + 2 * tp.t0 > 2) return 0;
+    return tp.t1 == 1 ? Cop : 2 * Cop;
+  };
+  auto chunk_live = [&](int a, const Tap& tp, int plane, int N) -> bool {
+    for (int slot = 0; slot < 8; ++slot)
+      for (int n = 0; n < N; n += 1)
+        if (wsrc(a, tp, plane, slot, n) >= 0) return true;
+    return false;
+  };
+
+  // planes per slab: the largest even count whose stage (A planes + B block) fits twice in shared memory
+  const size_t stage_cap = (SMEM_BUDGET - G1_PLAN_BYTES) / G1_STAGES;
+  auto slab_b_bytes = [&](int a, int p0, int p1) -> size_t {     // hi image bytes of planes [p0,p1)
+    size_t bytes = 0;
+    for (const Tap& tp : taps) {
+      const int N = tap_n(a, tp);
+      if (!N) continue;
+      int live = 0;
+      for (int pl = p0; pl < p1; ++pl) live += chunk_live(a, tp, pl, N) ? 1 : 0;
+      bytes += (size_t)((live + 1) / 2) * N * 32;
+    }
+    return bytes;
+  };
+  int PS = PLh;
+  const int mult = s.split ? 2 : 1;
+  for (;; ) {
+    size_t worst = 0;
+    for (int a = 0; a < n_groups; ++a)
+      for (int p0 = 0; p0 < PLh; p0 += PS) worst = std::max(worst, slab_b_bytes(a, p0, std::min(PLh, p0 + PS)) * mult);
+    const size_t need = (size_t)PS * mult * D.CHb + 128 + worst;
+    if (need <= stage_cap && PS * mult <= G1_MAXPL) break;
+    if (PS <= 1) { delete P; return no("one K chunk plane does not fit a shared-memory stage"); }
+    PS = (PS + 1) / 2;
+  }
+  D.a_region = (uint32_t)(PS * mult) * D.CHb + 128;
+
+  int n_slabs = 0, n_mma = 0;
+  size_t img_bytes = 0, worst_b = 0;
+  std::vector<int32_t>& T = P->table;
+  for (int a = 0; a < n_groups; ++a) {
+    D.groups[a].slab0 = n_slabs; D.groups[a].a_par = a;
+    bool first = true;
+    for (int p0 = 0; p0 < PLh; p0 += PS) {
+      const int p1 = std::min(PLh, p0 + PS);
+      if (n_slabs >= G1_MAXSLAB) { delete P; return no("too many K slabs"); }
+      G1Slab& S = D.slabs[n_slabs];
+      S.mma0 = n_mma; S.nplanes = 0;
+      for (int pl = p0; pl < p1; ++pl) S.plane[S.nplanes++] = pl;
+      if (s.split) for (int pl = p0; pl < p1; ++pl) S.plane[S.nplanes++] = PLh + pl;
+      const int np_hi = p1 - p0;
+      const size_t hi_bytes = slab_b_bytes(a, p0, p1);
+      S.b_src = (int)img_bytes; S.b_bytes = (int)(hi_bytes * mult);
+      size_t boff = 0;       // offset inside the slab's hi block
+      for (const Tap& tp : taps) {
+        const int N = tap_n(a, tp);
+        if (!N) continue;
+        std::vector<int> live;
+        for (int pl = p0; pl < p1; ++pl) if (chunk_live(a, tp, pl, N)) live.push_back(pl);
+        for (size_t i = 0; i < live.size(); i += 2) {
+          const int pa = live[i], pb = i + 1 < live.size() ? live[i + 1] : -1;
+          // B block of this MMA: [2 chunks][N rows][8]
+          const size_t e0 = (img_bytes + boff) / 2;
+          if (T.size() < (img_bytes + hi_bytes * mult) / 2) T.resize((img_bytes + hi_bytes * mult) / 2, -1);
+          for (int c = 0; c < 2; ++c) {
+            const int pl = c == 0 ? pa : pb;
+            for (int n = 0; n < N; ++n)
+              for (int slot = 0; slot < 8; ++slot) {
+                const int32_t src = pl >= 0 ? wsrc(a, tp, pl, slot, n) : -1;
+                T[e0 + ((size_t)c * N + n) * 8 + slot] = src;
+                if (s.split) T[e0 + hi_bytes / 2 + ((size_t)c * N + n) * 8 + slot] = src >= 0 ? (src | LO_FLAG) : -1;
+              }
+          }
+          const uint32_t a_off = (uint32_t)(pa - p0) * D.CHb + (uint32_t)tp.shift * 16;
+          const uint32_t a_lbo = pb >= 0 ? (uint32_t)(pb - pa) * D.CHb : 16u;      // dummy second chunk: the next pixel, zero weights
+          const uint32_t b_hi = D.a_region + (uint32_t)boff, b_lo = b_hi + (uint32_t)hi_bytes;
+          const uint32_t lo_planes = (uint32_t)np_hi * D.CHb;                       // lo planes sit behind the slab's hi planes
+          const int variants = s.split ? 3 : 1;
+          for (int vnt = 0; vnt < variants; ++vnt) {
+            if (n_mma >= G1_MAXMMA) { delete P; return no("MMA list too long"); }
+            G1Mma& M = D.mma[n_mma++];
+            M.a_off = a_off + (vnt == 1 ? lo_planes : 0);
+            M.a_lbo = a_lbo;
+            M.b_off = vnt == 2 ? b_lo : b_hi;
+            M.d_col = 0; M.n = (uint32_t)N; M.acc = first ? 0u : 1u;
+            first = false;
+          }
+          boff += (size_t)N * 32;
+        }
+      }
+      S.mma_n = n_mma - S.mma0;
+      img_bytes += hi_bytes * mult;
+      worst_b = std::max(worst_b, hi_bytes * mult);
+      ++n_slabs;
+    }
+    D.groups[a].slab_n = n_slabs - D.groups[a].slab0;
+  }
+  T.resize(img_bytes / 2, -1);
+  D.n_slabs = n_slabs; D.n_mma = n_mma;
+  D.stage_bytes = (uint32_t)(((size_t)D.a_region + worst_b + 1023) / 1024 * 1024);
+  P->smem = G1_PLAN_BYTES + (size_t)G1_STAGES * D.stage_bytes;
+  if (P->smem > 227 * 1024) { delete P; return no("shared-memory plan too large"); }
+  if (cudaMalloc(reinterpret_cast<void**>(&P->dev), sizeof(G1PlanDev)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&P->table_dev), std::max<size_t>(T.size(), 1) * sizeof(int32_t)) != cudaSuccess) {
+    gen_conv_plan_free(P);
+    return no("cudaMalloc failed");
+  }
+  cudaMemcpy(P->dev, &D, sizeof(G1PlanDev), cudaMemcpyHostToDevice);
+  cudaMemcpy(P->table_dev, T.data(), T.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  return P;
+}
+
+void gen_conv_plan_free(GenConvPlan* p) {
+  if (!p) return;
+  if (p->dev) cudaFree(p->dev);
+  if (p->table_dev) cudaFree(p->table_dev);
+  delete p;
+}
+size_t gen_conv_weight_image_bytes(const GenConvPlan* p) { return p->table.size() * 2; }
+int gen_conv_Cop(const GenConvPlan* p) { return (int)p->host.Cop; }
+
+void gen_conv_prep_weights(const GenConvPlan* p, const float* w, void* img, cudaStream_t st) {
+  ProfScope prof_("gen_prep_weights", st);
+  ++g_launches;
+  const int64_t n = (int64_t)p->table.size();
+  gen_gather_weights_kernel<<<grid_for(n, 256, 8, 1), 256, 0, st>>>(w, p->table_dev, n, reinterpret_cast<__nv_bfloat16*>(img));
+}
+
+static PlaneRef plane_ref(const GenPlanes& t) {
+  PlaneRef r;
+  r.base = reinterpret_cast<uint4*>(t.base);
+  r.layout = t.layout; r.KC = t.KC; r.PLimg = t.planes(); r.H = t.H; r.W = t.W;
+  return r;
+}
+
+int gen_conv_run(const GenConvPlan* P, const GenPlanes& in, const void* wimg, const GenEpilogue& e, int B, int* error_flag,
+                 const char* name, cudaStream_t st) {
+  if (!gen_encode_fn()) return 1;
+  const GenConvSpec& s = P->spec;
+  const G1PlanDev& D = P->host;
+  // a non-split plan may read the hi planes of a split tensor; a split plan needs the lo planes right behind the hi planes
+  if (s.split ? in.planes() != D.in_PL : in.planes() < D.in_PL) return 3;
+  CUtensorMap tmap;
+  if (make_planes_map(&tmap, in.base, (int64_t)B * in.planes(), in.H, in.W, D.R_in) != CUDA_SUCCESS) return 2;
+  G1Params p{};
+  p.plan = P->dev;
+  p.wimg = reinterpret_cast<const unsigned char*>(wimg);
+  p.B = B; p.Hg = s.Hg; p.Wg = s.Wg; p.in_PL = in.planes();
+  p.tiles_y = cdiv(s.Hg, 4 * D.MT); p.tiles_x = cdiv(s.Wg, D.TW);
+  p.num_tiles = B * p.tiles_y * p.tiles_x * D.n_groups;
+  p.pre = e.pre; p.bias = e.bias;
+  p.has_mask = e.mask != nullptr;
+  if (e.mask) p.mask = plane_ref(*e.mask);
+  p.mask_f32 = e.mask_f32;
+  p.has_out = e.out != nullptr;
+  if (e.out) { p.out = plane_ref(*e.out); p.out_lo = e.out->split; }
+  p.out_f32 = e.out_f32;
+  p.Cn = s.Cn;
+  p.Ho = s.kind == GEN_CONVT_S2 ? 2 * s.Hg : s.Hg;
+  p.Wo = s.kind == GEN_CONVT_S2 ? 2 * s.Wg : s.Wg;
+  p.error_flag = error_flag;
+  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  ProfScope prof_(name, st);
+  ++g_launches;
+  cudaFuncSetAttribute(tc_gconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem);
+  tc_gconv_kernel<<<grid, G1_THREADS, P->smem, st>>>(tmap, p);
+  return 0;
+}
+
+// ============================================================================================
+//                                  weight-gradient kernel
+// ============================================================================================
+namespace {
+
+constexpr int G2_THREADS = 192;        // TMA warp, MMA warp, 4 dump warps
+constexpr int G2_MAXMMA = 96;
+constexpr int G2_MAXROLE = 4;
+constexpr int G2_MAXPL = 64;
+constexpr int G2_COLS = 512;
+
+struct G2Mma { uint32_t a_off, b_off, a_sbo, b_sbo, d_col, n, m, b_ones; };
+struct G2Role { int mma0, mma_n, nS, nU, ncols, pad0, pad1, pad2; int s_plane[G2_MAXPL]; int u_plane[G2_MAXPL]; };
+struct G2PlanDev {
+  int n_roles, TRr, R_s, row0, col0, TW, s_PL, u_PL;
+  uint32_t CHs, CHu, s_region, u_region, stage_bytes, ones_off, pad0, pad1;
+  G2Role roles[G2_MAXROLE];
+  G2Mma mma[G2_MAXMMA];
+};
+constexpr uint32_t G2_PLAN_BYTES = ((sizeof(G2PlanDev) + 1023) / 1024) * 1024;
+
+struct G2Params {
+  const G2PlanDev* plan;
+  float* partial;              // [grid][G2_COLS][128]
+  int B, Hg, Wg, tiles_y, tiles_x, num_tiles;
+  int s_PL, u_PL;              // planes per image of the two tensors (hi + lo; only hi planes are read)
+  int* error_flag;
+};
+
+__global__ void __launch_bounds__(G2_THREADS, 1)
+tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_constant__ CUtensorMap tmap_u, G2Params p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  G2PlanDev* plan = reinterpret_cast<G2PlanDev*>(smem);
+  unsigned char* stages = smem + G2_PLAN_BYTES;
+  __shared__ uint64_t full_bar[G1_STAGES], empty_bar[G1_STAGES], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.plan);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
+    for (int i = threadIdx.x; i < (int)(sizeof(G2PlanDev) / 4); i += G2_THREADS) dst[i] = __ldg(src + i);
+    // stages start as zeros: plane positions a role never loads and the pad behind the last plane are read as K elements
+    // against zero-filled gradient pixels, and 0 * NaN would poison an accumulator
+    uint4* z = reinterpret_cast<uint4*>(stages);
+    const int nz = (int)((size_t)G1_STAGES * __ldg(&p.plan->stage_bytes) / 16);
+    for (int i = threadIdx.x; i < nz; i += G2_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (threadIdx.x == 32) {
+    for (int s = 0; s < G1_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  {  // two planes of ones (bias gradient operand) behind the stages
+    uint4* ones = reinterpret_cast<uint4*>(smem + plan->ones_off);
+    const int nu = (int)(2 * plan->CHu / 16);
+    for (int i = threadIdx.x; i < nu; i += G2_THREADS) ones[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const int n_roles = plan->n_roles;
+  const int role = blockIdx.x % n_roles;
+  const int rank_in_role = blockIdx.x / n_roles;
+  const int ctas_in_role = (gridDim.x - role + n_roles - 1) / n_roles;
+  const int TRr = plan->TRr, TW = plan->TW;
+  const uint32_t stage_bytes = plan->stage_bytes;
+  const int per_img = p.tiles_y * p.tiles_x;
+  const int my_tiles = p.num_tiles > rank_in_role ? (p.num_tiles - 1 - rank_in_role) / ctas_in_role + 1 : 0;
+  const G2Role* R = &plan->roles[role];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t CHs = plan->CHs, CHu = plan->CHu, s_region = plan->s_region;
+      int it = 0;
+      for (int t = rank_in_role; t < p.num_tiles; t += ctas_in_role, ++it) {
+        const int s = it % G1_STAGES;
+        const uint32_t ph = (it / G1_STAGES) & 1;
+        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int n = t / per_img, rem = t % per_img;
+        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
+        unsigned char* dst = stages + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], (uint32_t)R->nS * CHs + (uint32_t)R->nU * CHu);
+        for (int pl = 0; pl < R->nS; ++pl)
+          tma_load_3d(dst + (size_t)pl * CHs, &tmap_s, &full_bar[s], (tx * TW + plan->col0) * 8, ty * TRr + plan->row0,
+                      n * p.s_PL + R->s_plane[pl]);
+        for (int pl = 0; pl < R->nU; ++pl)
+          tma_load_4d(dst + s_region + (size_t)pl * CHu, &tmap_u, &full_bar[s], 0, tx, ty * TRr, n * p.u_PL + R->u_plane[pl]);
+      }
+    }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t ones_addr = smem_u32(smem + plan->ones_off);
+    const int KS = 2 * TRr;                       // 16-pixel K steps per tile
+    int it = 0;
+    bool ok = true;
+    for (int t = rank_in_role; t < p.num_tiles; t += ctas_in_role, ++it) {
+      const int s = it % G1_STAGES;
+      const uint32_t ph = (it / G1_STAGES) & 1;
+      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
+      fence_after_sync();
+      const uint32_t base = smem_u32(stages + (size_t)s * stage_bytes);
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t kadv = (uint32_t)ks * 256u;
+#pragma unroll 2
+        for (int i = R->mma0; i < R->mma0 + R->mma_n; ++i) {
+          const G2Mma m = plan->mma[i];
+          const uint64_t da = make_desc_kmajor_noswz(base + m.a_off + kadv, 128, m.a_sbo);
+          const uint64_t db = make_desc_kmajor_noswz((m.b_ones ? ones_addr : base + m.b_off) + kadv, 128, m.b_sbo);
+          const uint32_t idesc = make_idesc_bf16_f32((int)m.m, (int)m.n, 1, 1);
+          if (leader) mma_bf16_ss(tmem + m.d_col, da, db, idesc, (it | ks) != 0);
+        }
+      }
+      if (leader) mma_commit(&empty_bar[s]);
+      __syncwarp();
+    }
+    if (ok && leader) mma_commit(&done_bar);
+    __syncwarp();
+  } else if (my_tiles > 0) {
+    // ================================ dump: TMEM -> this CTA's partial block =====================================
+    const int lg = warp & 3;
+    bool landed = false;
+    for (uint32_t spin = 0; spin < (1u << 22) && !landed; ++spin) {     // the whole kernel lies before this barrier: back off
+      landed = mbar_try_wait(&done_bar, 0) != 0;
+      if (!landed) __nanosleep(256);
+    }
+    if (landed) {
+      fence_after_sync();
+      float* out = p.partial + (size_t)blockIdx.x * G2_COLS * 128 + (size_t)(lg * 32 + lane);
+      for (int cb = 0; cb * 32 < R->ncols; ++cb) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(cb * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) out[(size_t)(cb * 32 + j) * 128] = v[j];
+      }
+    } else if (lane == 0) {
+      *p.error_flag = 1;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// out[e] = sum over the CTAs of the entry's role of partial[cta][src] for up to 4 sources per entry (deterministic order)
+__global__ void __launch_bounds__(256) gen_wgrad_reduce_kernel(const float* __restrict__ partial, const int32_t* __restrict__ src, int E,
+                                                               int n_roles, int grid, int tiles, float* dW, float* db, int EW) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float acc = 0.f;
+  for (int k = 0; k < 4; ++k) {
+    const int32_t sidx = src[(size_t)e * 4 + k];
+    if (sidx < 0) continue;
+    const int role = sidx / (G2_COLS * 128), off = sidx % (G2_COLS * 128);
+    const int ctas = (grid - role + n_roles - 1) / n_roles;
+    const int live = tiles < ctas ? tiles : ctas;              // CTAs beyond the tile count never wrote their block
+    for (int c = 0; c < live; ++c) acc += __ldg(partial + (size_t)(c * n_roles + role) * G2_COLS * 128 + off);
+  }
+  if (e < EW) dW[e] = acc;
+  else if (db) db[e - EW] = acc;
+}
+
+}  // namespace
+
+struct GenWgradPlan {
+  GenWgradSpec spec;
+  G2PlanDev host;
+  G2PlanDev* dev = nullptr;
+  std::vector<int32_t> src;      // [EW + Cu][4]
+  int32_t* src_dev = nullptr;
+  int EW = 0;
+  size_t smem = 0;
+};
+
+GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not) {
+  static const char* msg = "";
+  auto no = [&](const char* m) -> GenWgradPlan* { msg = m; if (why_not) *why_not = msg; return nullptr; };
+  const int nS = hi_planes(s.s_layout, s.s_KC), nU = hi_planes(s.u_layout, s.u_KC);
+  int halo_r, halo_c, row0, col0;
+  if (s.kind == GEN_CONV_S2) { row0 = 0; col0 = 0; halo_r = 1; halo_c = 1; }
+  else if (s.kind == GEN_CONVT_S2) { row0 = -1; col0 = -1; halo_r = 1; halo_c = 1; }
+  else { row0 = -1; col0 = -1; halo_r = 2; halo_c = 2; }
+  int TW = 0;
+  for (int d = GP - halo_c; d >= 8; --d) if (s.Wg % d == 0) { TW = d; break; }
+  if (!TW) return no("no tile width in [8, 31] divides the gradient's width");
+  struct Tap { int t0, t1, shift; };
+  std::vector<Tap> taps;
+  if (s.kind == GEN_CONV_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, di * GP + dj});
+  else if (s.kind == GEN_CONVT_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, (1 - di) * GP + (1 - dj)});
+  else for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw)
+    taps.push_back({kh, kw, s.flip ? (2 - kh) * GP + (2 - kw) : kh * GP + kw});
+
+  GenWgradPlan* P = new GenWgradPlan();
+  P->spec = s;
+  G2PlanDev& D = P->host;
+  memset(&D, 0, sizeof(D));
+  // A (M side) = the operand with more planes; B (N side) = the other one (N = 8 * planes, a multiple of 16 for M = 128)
+  const bool a_is_s = nS >= nU;
+  const int nA = a_is_s ? nS : nU, nB = a_is_s ? nU : nS;
+  int Mblk = nA >= 16 ? 128 : 64;
+  int Nb = nB * 8;
+  if (Mblk == 128 && Nb % 16) Nb += 8;                  // reads one plane of the neighbouring region: ignored columns
+  if (Nb > 256) { delete P; return no("N side wider than 256"); }
+  const int blkA = Mblk / 8;
+  const int nblocks = (nA + blkA - 1) / blkA;
+  // bias accumulators: A = U planes (blocks of 16 / 8), B = ones, N = 16 (M = 128) or 8 (M = 64)
+  const int MblkU = nU >= 16 ? 128 : 64;
+  const int ublocks = (nU + MblkU / 8 - 1) / (MblkU / 8);
+  const int bias_n = MblkU == 128 ? 16 : 8;
+
+  // tile rows: largest of 8, 4, 2 whose two stages fit
+  int TRr = 8;
+  for (;; TRr /= 2) {
+    const size_t CHs = (size_t)(TRr + halo_r) * GP * 16, CHu = (size_t)TRr * GP * 16;
+    const size_t s_reg = (size_t)std::max(nS, a_is_s ? nblocks * blkA : nS) * CHs + 128;
+    const size_t u_reg = (size_t)std::max(nU, std::max(a_is_s ? nU : nblocks * blkA, ublocks * (MblkU / 8))) * CHu + (Nb > nB * 8 ? CHu : 0);
+    const size_t stage = (s_reg + u_reg + 1023) / 1024 * 1024;
+    if (G2_PLAN_BYTES + G1_STAGES * stage + 2 * CHu <= SMEM_BUDGET || TRr == 1) {
+      D.CHs = (uint32_t)CHs; D.CHu = (uint32_t)CHu; D.s_region = (uint32_t)s_reg; D.u_region = (uint32_t)u_reg;
+      D.stage_bytes = (uint32_t)stage;
+      break;
+    }
+  }
+  if (TRr < 2) { delete P; return no("operand planes do not fit two shared-memory stages"); }
+  D.TRr = TRr; D.R_s = TRr + halo_r; D.row0 = row0; D.col0 = col0; D.TW = TW; D.s_PL = nS; D.u_PL = nU;
+  D.ones_off = (uint32_t)(G2_PLAN_BYTES + (size_t)G1_STAGES * D.stage_bytes);
+  P->smem = (size_t)D.ones_off + 2 * D.CHu;    // regions are padded to whole M blocks: no operand runs past the allocation
+  if (P->smem > 227 * 1024) { delete P; return no("shared-memory plan too large"); }
+
+  // accumulators: (tap, A block) -> N columns; then the bias accumulators; packed into roles of <= 512 columns
+  struct Acc { int tap, blk, role, d_col; };
+  std::vector<Acc> accs;
+  int n_roles = 1, cols = 0, n_mma = 0;
+  auto new_role = [&]() { ++n_roles; cols = 0; };
+  const int bias_cols = ublocks * bias_n;
+  for (int blk = 0; blk < nblocks; ++blk)
+    for (size_t tp = 0; tp < taps.size(); ++tp) {
+      if (cols + Nb > G2_COLS - (n_roles == 1 ? bias_cols : 0)) new_role();
+      accs.push_back({(int)tp, blk, n_roles - 1, cols});
+      cols += Nb;
+    }
+  if (n_roles > G2_MAXROLE) { delete P; return no("too many accumulator roles"); }
+  D.n_roles = n_roles;
+  std::vector<int> role_cols(n_roles, 0);
+  for (const Acc& a : accs) role_cols[a.role] = std::max(role_cols[a.role], a.d_col + Nb);
+  const int bias_col0 = role_cols[0];
+  role_cols[0] += bias_cols;
+  if (role_cols[0] > G2_COLS) { delete P; return no("bias accumulators do not fit"); }
+
+  for (int r = 0; r < n_roles; ++r) {
+    G2Role& R = D.roles[r];
+    std::vector<int> needS, needU;
+    auto need = [](std::vector<int>& v, int pl, int limit) { if (pl < limit && std::find(v.begin(), v.end(), pl) == v.end()) v.push_back(pl); };
+    for (const Acc& a : accs) if (a.role == r) {
+      for (int k = 0; k < blkA; ++k) need(a_is_s ? needS : needU, a.blk * blkA + k, a_is_s ? nS : nU);
+      for (int k = 0; k < nB; ++k) need(a_is_s ? needU : needS, k, a_is_s ? nU : nS);
+    }
+    if (r == 0) for (int k = 0; k < nU; ++k) need(needU, k, nU);
+    std::sort(needS.begin(), needS.end()); std::sort(needU.begin(), needU.end());
+    // planes keep their own index as position inside the region (simple addressing; unused positions stay unloaded)
+    R.nS = (int)needS.size(); R.nU = (int)needU.size();
+    if (R.nS > G2_MAXPL || R.nU > G2_MAXPL) { delete P; return no("too many planes per role"); }
+    for (int i = 0; i < R.nS; ++i) R.s_plane[i] = needS[i];
+    for (int i = 0; i < R.nU; ++i) R.u_plane[i] = needU[i];
+    R.ncols = role_cols[r];
+  }
+  // the producer places plane i of a role at position i: make positions equal plane indices by loading contiguous ranges
+  // (roles split by A block: the A planes of a role are a contiguous range starting at a block boundary)
+  for (int r = 0; r < n_roles; ++r) {
+    G2Role& R = D.roles[r];
+    R.mma0 = n_mma;
+    const int s_first = R.nS ? R.s_plane[0] : 0, u_first = R.nU ? R.u_plane[0] : 0;
+    for (int i = 0; i < R.nS; ++i) if (R.s_plane[i] != s_first + i) { delete P; return no("non-contiguous S planes in a role"); }
+    for (int i = 0; i < R.nU; ++i) if (R.u_plane[i] != u_first + i) { delete P; return no("non-contiguous U planes in a role"); }
+    for (const Acc& a : accs) if (a.role == r) {
+      if (n_mma >= G2_MAXMMA) { delete P; return no("MMA list too long"); }
+      G2Mma& M = D.mma[n_mma++];
+      const uint32_t shift = (uint32_t)taps[a.tap].shift * 16;
+      const uint32_t s_base = (uint32_t)0, u_base = D.s_region;
+      if (a_is_s) {
+        M.a_off = s_base + (uint32_t)(a.blk * blkA - s_first) * D.CHs + shift; M.a_sbo = D.CHs;
+        M.b_off = u_base + (uint32_t)(0 - u_first) * D.CHu; M.b_sbo = D.CHu;
+      } else {
+        M.a_off = u_base + (uint32_t)(a.blk * blkA - u_first) * D.CHu; M.a_sbo = D.CHu;
+        M.b_off = s_base + (uint32_t)(0 - s_first) * D.CHs + shift; M.b_sbo = D.CHs;
+      }
+      M.d_col = (uint32_t)a.d_col; M.n = (uint32_t)Nb; M.m = (uint32_t)Mblk; M.b_ones = 0;
+    }
+    if (r == 0) {
+      for (int ub = 0; ub < ublocks; ++ub) {
+        if (n_mma >= G2_MAXMMA) { delete P; return no("MMA list too long"); }
+        G2Mma& M = D.mma[n_mma++];
+        M.a_off = D.s_region + (uint32_t)(ub * (MblkU / 8) - u_first) * D.CHu; M.a_sbo = D.CHu;
+        M.b_off = 0; M.b_sbo = D.CHu; M.b_ones = 1;
+        M.d_col = (uint32_t)(bias_col0 + ub * bias_n); M.n = (uint32_t)bias_n; M.m = (uint32_t)MblkU;
+      }
+    }
+    R.mma_n = n_mma - R.mma0;
+  }
+
+  // scatter table: dW element -> (role, column, TMEM lane)
+  auto lane_of = [](int M, int row) { return M == 128 ? row : (row / 16) * 32 + row % 16; };
+  const int Cs = s.Cs, Cu = s.Cu;
+  P->EW = 9 * Cs * Cu;
+  P->src.assign((size_t)(P->EW + Cu) * 4, -1);
+  for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) for (int cs = 0; cs < Cs; ++cs) for (int cu = 0; cu < Cu; ++cu) {
+    int tap_i, es, eu;
+    if (s.kind == GEN_CONV_S2) {
+      const int di = kh >> 1, a = kh & 1, dj = kw >> 1, b = kw & 1, par = a * 2 + b;
+      tap_i = di * 2 + dj;
+      es = s.s_layout == GEN_X3 ? par * 3 + cs : par * s.s_KC * 8 + cs;
+      eu = cu;
+    } else if (s.kind == GEN_CONVT_S2) {
+      const int di = kh >> 1, a = kh & 1, dj = kw >> 1, b = kw & 1, par = a * 2 + b;
+      tap_i = di * 2 + dj;
+      es = cs;
+      eu = par * s.u_KC * 8 + cu;
+    } else {
+      tap_i = kh * 3 + kw; es = cs; eu = cu;
+    }
+    const int ea = a_is_s ? es : eu, eb = a_is_s ? eu : es;
+    const int blk = ea / Mblk, row = ea % Mblk;
+    int found = -1;
+    for (const Acc& a : accs) if (a.tap == tap_i && a.blk == blk) { found = a.role * (G2_COLS * 128) + (a.d_col + eb) * 128 + lane_of(Mblk, row); break; }
+    const int tap9 = kh * 3 + kw;
+    const int e = s.w_mode == 0 ? (tap9 * Cs + cs) * Cu + cu : (tap9 * Cu + cu) * Cs + cs;
+    P->src[(size_t)e * 4] = found;
+  }
+  for (int cu = 0; cu < Cu; ++cu) {
+    const int npar = s.u_layout == GEN_S2D ? 4 : 1;
+    for (int par = 0; par < npar; ++par) {
+      const int eu = s.u_layout == GEN_S2D ? par * s.u_KC * 8 + cu : cu;
+      const int ub = eu / MblkU, row = eu % MblkU;
+      P->src[(size_t)(P->EW + cu) * 4 + par] = 0 * (G2_COLS * 128) + (bias_col0 + ub * bias_n) * 128 + lane_of(MblkU, row);
+    }
+  }
+  if (cudaMalloc(reinterpret_cast<void**>(&P->dev), sizeof(G2PlanDev)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&P->src_dev), P->src.size() * sizeof(int32_t)) != cudaSuccess) {
+    gen_wgrad_plan_free(P);
+    return no("cudaMalloc failed");
+  }
+  cudaMemcpy(P->dev, &D, sizeof(G2PlanDev), cudaMemcpyHostToDevice);
+  cudaMemcpy(P->src_dev, P->src.data(), P->src.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  return P;
+}
+
+void gen_wgrad_plan_free(GenWgradPlan* p) {
+  if (!p) return;
+  if (p->dev) cudaFree(p->dev);
+  if (p->src_dev) cudaFree(p->src_dev);
+  delete p;
+}
+size_t gen_wgrad_partial_floats(const GenWgradPlan*) { return (size_t)kNumSMs * G2_COLS * 128; }
+
+int gen_wgrad_run(const GenWgradPlan* P, const GenPlanes& S, const GenPlanes& U, float* dW, float* db, float* partial, int B,
+                  int* error_flag, const char* name, cudaStream_t st) {
+  if (!gen_encode_fn()) return 1;
+  const GenWgradSpec& s = P->spec;
+  const G2PlanDev& D = P->host;
+  CUtensorMap ms, mu;
+  // hi planes only: lo planes (split tensors) sit behind them and are skipped through the per-image plane count
+  if (make_planes_map(&ms, S.base, (int64_t)B * S.planes(), S.H, S.W, D.R_s) != CUDA_SUCCESS) return 2;
+  if (make_window_map(&mu, U.base, (int64_t)B * U.planes(), U.H, U.W, D.TW, D.TRr) != CUDA_SUCCESS) return 2;
+  G2Params p{};
+  p.plan = P->dev;
+  p.s_PL = S.planes(); p.u_PL = U.planes();        // planes per image INCLUDING lo planes (only the hi planes are read)
+  p.partial = partial;
+  p.B = B; p.Hg = s.Hg; p.Wg = s.Wg;
+  p.tiles_y = cdiv(s.Hg, D.TRr); p.tiles_x = s.Wg / D.TW;
+  p.num_tiles = B * p.tiles_y * p.tiles_x;
+  p.error_flag = error_flag;
+  if (S.planes() < D.s_PL || U.planes() < D.u_PL) return 3;
+  int grid = p.num_tiles * D.n_roles < kNumSMs ? p.num_tiles * D.n_roles : kNumSMs / D.n_roles * D.n_roles;
+  if (grid < D.n_roles) grid = D.n_roles;
+  ProfScope prof_(name, st);
+  g_launches += 2;
+  cudaFuncSetAttribute(tc_gwgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem);
+  tc_gwgrad_kernel<<<grid, G2_THREADS, P->smem, st>>>(ms, mu, p);
+  const int E = P->EW + (db ? s.Cu : 0);
+  gen_wgrad_reduce_kernel<<<cdiv(E, 256), 256, 0, st>>>(partial, P->src_dev, E, D.n_roles, grid, p.num_tiles, dW, db, P->EW);
+  return 0;
+}
+
+// ============================================================================================
+//                                         packers
+// ============================================================================================
+namespace {
+
+__global__ void gen_pack_x3_kernel(const float* __restrict__ x, int B, int H, int W, int split, uint4* out) {
+  const int h2 = H / 2, w2 = W / 2;
+  const int64_t total = (int64_t)B * h2 * w2;
+  const int PL = split ? 4 : 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % w2), r = (int)((i / w2) % h2);
+    const int64_t n = i / ((int64_t)w2 * h2);
+    float v[16];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const float* src = x + (((int64_t)n * H + 2 * r + a) * W + 2 * j) * 3;      // 6 contiguous floats: (b = 0,1) x 3 channels
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v[a * 6 + k] = __ldg(src + k);
+    }
+    v[12] = v[13] = v[14] = v[15] = 0.f;
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      hi[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      lo[e] = pack_bf16x2(v[2 * e] - __uint_as_float(hi[e] << 16), v[2 * e + 1] - __uint_as_float(hi[e] & 0xFFFF0000u));
+    }
+    const int64_t plane = (int64_t)h2 * w2;
+    uint4* o = out + (int64_t)n * PL * plane + (int64_t)r * w2 + j;
+    o[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    o[plane] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    if (split) {
+      o[2 * plane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      o[3 * plane] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+  }
+}
+
+// one thread per (image, output pixel, chunk)
+__global__ void gen_pack_nhwc_kernel(const float* __restrict__ in, int B, int H, int W, int C, PlaneRef out, int split) {
+  const int KC = out.KC;
+  const int64_t total = (int64_t)B * H * W * KC;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), y = (int)((i / W) % H), chunk = (int)((i / ((int64_t)W * H)) % KC);
+    const int n = (int)(i / ((int64_t)W * H * KC));
+    const float* src = in + (((int64_t)n * H + y) * W + x) * C + chunk * 8;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = chunk * 8 + k < C ? __ldg(src + k) : 0.f;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      lo[e] = pack_bf16x2(v[2 * e] - __uint_as_float(hi[e] << 16), v[2 * e + 1] - __uint_as_float(hi[e] & 0xFFFF0000u));
+    }
+    out.base[unit_index(out, n, y, x, chunk, 0)] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (split) out.base[unit_index(out, n, y, x, chunk, 1)] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__global__ void gen_unpack_nhwc_kernel(PlaneRef in, int split, int B, int H, int W, int C, float* out) {
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), x = (int)((i / C) % W), y = (int)((i / ((int64_t)C * W)) % H);
+    const int n = (int)(i / ((int64_t)C * W * H));
+    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(in.base + unit_index(in, n, y, x, c >> 3, 0));
+    float v = __bfloat162float(u[c & 7]);
+    if (split) {
+      const __nv_bfloat16* l = reinterpret_cast<const __nv_bfloat16*>(in.base + unit_index(in, n, y, x, c >> 3, 1));
+      v += __bfloat162float(l[c & 7]);
+    }
+    out[i] = v;
+  }
+}
+
+}  // namespace
+
+void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cudaStream_t st) {
+  ProfScope prof_("gen_pack_x3", st);
+  ++g_launches;
+  gen_pack_x3_kernel<<<grid_for((int64_t)B * (H / 2) * (W / 2), 256, 8, 4), 256, 0, st>>>(x, B, H, W, split, reinterpret_cast<uint4*>(out));
+}
+void gen_pack_nhwc(const float* in, int B, int H, int W, int C, const GenPlanes& out, cudaStream_t st) {
+  ProfScope prof_("gen_pack", st);
+  ++g_launches;
+  gen_pack_nhwc_kernel<<<grid_for((int64_t)B * H * W * out.KC, 256, 8, 4), 256, 0, st>>>(in, B, H, W, C, plane_ref(out), out.split);
+}
+void gen_unpack_nhwc(const GenPlanes& in, int B, int H, int W, int C, float* out, cudaStream_t st) {
+  ++g_launches;
+  gen_unpack_nhwc_kernel<<<grid_for((int64_t)B * H * W * C, 256, 8, 4), 256, 0, st>>>(plane_ref(in), in.split, B, H, W, C, out);
+}
+
+}  // namespace kc
