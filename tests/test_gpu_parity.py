@@ -365,6 +365,36 @@ def test_config5_scaled_model():
     assert float(np.max(np.abs(m.call(x, True, eps=eps).numpy() - oxh.numpy()))) < 1e-4
 
 
+def test_config5_scaled_model_on_tensor_cores():
+    """BASELINE configs[4] on the library default (tensor-core) path at batch 8: every Conv2D / Conv2DTranspose of the scaled
+    model (64 / 128 / 32 channels) runs on the general tcgen05 engine (tc_gen.cu).  Bars: north_star's 1e-3 relative on the
+    loss terms and 1e-2 max-abs on the reconstruction.  Gradients: bf16 operands carry 2^-9 relative rounding per factor
+    and a gradient entry is a product chain through up to four such layers plus ReLU masks, so an entry-wise bar is not
+    meaningful; what the optimiser sees is bounded instead - relative L2 per variable <= 3e-2 (measured ~1e-2) - and the
+    consequence is checked directly: the loss after three Adam steps stays within 1e-3 of the fp32 oracle's."""
+    cfg = O.scaled_config()
+    B = 8
+    m, ws = make(cfg, BACKEND, bias_scale=0.02, precision="bf16")
+    assert m.tc_status() == 1
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    d, grads = m.loss_and_grads(x, eps=eps)
+    od, ograds, oxh, _ = O.loss_and_grads(cfg, ws, x, eps)
+    assert_metrics_close(d, od, rtol=1e-3, atol=1e-6)
+    assert float(np.max(np.abs(m.call(x, True, eps=eps).numpy() - oxh.numpy()))) < 1e-2
+    for (n, _), g, og in zip(O.variable_shapes(cfg), grads, ograds):
+        og = og.numpy().astype(np.float64)
+        l2 = np.linalg.norm(g.astype(np.float64) - og) / (np.linalg.norm(og) + 1e-30)
+        assert l2 < 3e-2, (n, l2)
+    om = O.OracleModel(cfg, ws)
+    m.compile(optimizer=pkg.Adam(learning_rate=float(cfg["training"]["learning_rate"])))
+    for s_ in range(3):
+        e = eps_for(cfg, B, step=s_)
+        dd = m.train_step(x, eps=e)
+        odd, _ = om.train_step(x, e)
+    assert_metrics_close(dd, odd, rtol=1e-3, atol=1e-6)
+    assert m.tc_status() == 1
+
+
 def test_side_stream_backward_is_bitwise_identical_to_the_serial_one(monkeypatch):
     """The weight-gradient kernels run on a side stream beside the
     data-gradient chain; KCVAE_AUX_STREAM=0 keeps everything on the caller's stream.  Same kernels, same reduction orders:

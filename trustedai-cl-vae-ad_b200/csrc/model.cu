@@ -149,6 +149,31 @@ struct kcvae_model {
   void* wimg_out = nullptr;
   int* tc_error = nullptr;
   int* tc_flag_host = nullptr;   // pinned: the *_host entry points read tc_error back with their results
+  // general tensor-core convolution engine (tc_gen.cu): every Conv2D / Conv2DTranspose product the specialised kernels
+  // above do not cover runs as a table-driven tcgen05 kernel over bf16 plane tensors
+#ifndef KCVAE_EMU
+  struct GenLayerPlans {
+    GenConvPlan *fwd = nullptr, *fwd_split = nullptr, *dgrad = nullptr;
+    GenWgradPlan* wgrad = nullptr;
+    size_t img_fwd = 0, img_fwd_split = 0, img_dgrad = 0;      // byte offsets into gen_wimg
+  };
+  std::vector<GenLayerPlans> gen_e, gen_d;      // encoder convs [L]; decoder: Conv2DTranspose layers [L] + output layer [L]
+  bool gen_enc = false;        // encoder forward + backward on the engine
+  bool gen_dec = false;        // whole decoder on the engine (no specialised tail for this topology)
+  bool gen_dec0 = false;       // README-style decoder: specialised tail, the first Conv2DTranspose's backward on the engine
+  bool enc_split = true;       // training forward of the encoder with bf16 hi + lo operand pairs (fp32-grade z)
+  bool enc_split_live = false; // layout the encoder plane tensors were last written in
+  bool pp_live = false;        // a_pp_planar holds hi + lo planes of the Dense output of the last forward
+  bool force_split = false;    // kcvae_loss: loss terms are evaluated with the fp32-grade encoder as well
+  unsigned char* gen_wimg = nullptr;
+  size_t gen_wimg_bytes = 0;
+  std::vector<int32_t> gen_table_host;
+  int32_t* gen_table = nullptr;
+  uint64_t gen_img_version = 0;
+  void* x_pl = nullptr;
+  std::vector<void*> act_e_pl, g_e_pl, act_d_pl, g_d_pl;
+  float *gen_partial = nullptr, *gen_partial2 = nullptr;
+#endif
   // data parallel
   int rank = 0, world = 1;
   // collectives run on their own stream so they overlap the backward pass (non-emulated build)
@@ -253,6 +278,169 @@ int build_topology(kcvae_model* h) {
   return KCVAE_OK;
 }
 
+#ifndef KCVAE_EMU
+// ------------------------------------------------------------------ general convolution engine glue (tc_gen.cu)
+int kc16(int C) { return (C + 15) / 16 * 2; }          // 8-channel chunks of a channel count padded to 16
+GenPlanes pl_make(void* base, int layout, int KC, int split, int H, int W) {
+  GenPlanes p{};
+  p.base = base; p.layout = layout; p.KC = KC; p.split = split; p.H = H; p.W = W;
+  return p;
+}
+GenPlanes pl_x(const kcvae_model* h, int split) {        // the input image, 2x2 space-to-depth
+  return h->C == 3 ? pl_make(h->x_pl, GEN_X3, 1, split, h->H / 2, h->W / 2) : pl_make(h->x_pl, GEN_S2D, kc16(h->C), split, h->H / 2, h->W / 2);
+}
+GenPlanes pl_act_e(const kcvae_model* h, int l, int split) {   // encoder activation l in 1..L-1, stored space-to-depth
+  return pl_make(h->act_e_pl[l], GEN_S2D, kc16(h->ec[l]), split, h->eh[l] / 2, h->ew[l] / 2);
+}
+GenPlanes pl_g_e(const kcvae_model* h, int l) {                // encoder gradient l in 1..L
+  return pl_make(h->g_e_pl[l], GEN_PLAIN, kc16(h->ec[l]), 0, h->eh[l], h->ew[l]);
+}
+int kc_act_d(const kcvae_model* h, int l) { return l == 0 ? h->dc[0] / 8 : kc16(h->dc[l]); }   // the Dense writes exactly dc[0] / 8 chunks
+GenPlanes pl_act_d(const kcvae_model* h, int l, int split) {   // decoder activation l in 0..L
+  void* base = (l == 0 && h->gen_dec0) ? h->a_pp_planar : h->act_d_pl[l];
+  return pl_make(base, GEN_PLAIN, kc_act_d(h, l), split, h->dh[l], h->dw[l]);
+}
+GenPlanes pl_g_d(const kcvae_model* h, int l) {                // decoder gradient l in 1..L, stored space-to-depth
+  return pl_make(h->g_d_pl[l], GEN_S2D, kc16(h->dc[l]), 0, h->dh[l] / 2, h->dw[l] / 2);
+}
+
+void gen_free_plans(std::vector<kcvae_model::GenLayerPlans>& v) {
+  for (auto& g : v) {
+    gen_conv_plan_free(g.fwd); gen_conv_plan_free(g.fwd_split); gen_conv_plan_free(g.dgrad); gen_wgrad_plan_free(g.wgrad);
+  }
+  v.clear();
+}
+
+// appends the plan's gather table (indices shifted to the flat parameter vector) and returns the image's byte offset
+size_t gen_add_image(kcvae_model* h, const GenConvPlan* p, int vi) {
+  size_t n = 0;
+  const int32_t* t = gen_conv_table(p, &n);
+  const size_t off = h->gen_table_host.size() * 2;
+  const int32_t base = (int32_t)h->vars[vi].off;
+  for (size_t i = 0; i < n; ++i) {
+    const int32_t e = t[i];
+    h->gen_table_host.push_back(e < 0 ? -1 : (((e & (GEN_LO_FLAG - 1)) + base) | (e & GEN_LO_FLAG)));
+  }
+  while (h->gen_table_host.size() % 8) h->gen_table_host.push_back(-1);     // keep every image 16-byte aligned
+  return off;
+}
+
+// Chooses which layers run on the general engine and builds their plans (shape-based kernel selection, once per handle).
+int gen_setup(kcvae_model* h) {
+  const int L = h->L;
+  const char* off = std::getenv("KCVAE_GEN");               // 0 = specialised / CUDA-core kernels only (development switch)
+  if (L == 0 || (off && off[0] == '0')) return KCVAE_OK;
+  const char* es = std::getenv("KCVAE_ENC_SPLIT");          // 0 = plain bf16 operands in the training forward of the encoder
+  h->enc_split = !(es && es[0] == '0');
+  const char* why = "";
+  // ---- encoder: every Conv2D on the engine, or none
+  bool ok = true;
+  for (int l = 0; l < L; ++l) ok = ok && h->eh[l] % 2 == 0 && h->ew[l] % 2 == 0;
+  std::vector<kcvae_model::GenLayerPlans> E(L);
+  for (int l = 0; l < L && ok; ++l) {
+    const bool x3 = l == 0 && h->C == 3;
+    GenConvSpec f{};
+    f.kind = GEN_CONV_S2; f.in_layout = x3 ? GEN_X3 : GEN_S2D; f.Ck = h->ec[l]; f.Cn = h->ec[l + 1]; f.KCk = x3 ? 1 : kc16(h->ec[l]);
+    f.w_mode = 0; f.Hg = h->eh[l + 1]; f.Wg = h->ew[l + 1];
+    f.split = 0; E[l].fwd = gen_conv_plan_create(f, &why);
+    f.split = 1; E[l].fwd_split = gen_conv_plan_create(f, &why);
+    if (l > 0) {
+      GenConvSpec d{};
+      d.kind = GEN_CONVT_S2; d.in_layout = GEN_PLAIN; d.Ck = h->ec[l + 1]; d.Cn = h->ec[l]; d.KCk = kc16(h->ec[l + 1]); d.w_mode = 1;
+      d.Hg = h->eh[l + 1]; d.Wg = h->ew[l + 1];
+      E[l].dgrad = gen_conv_plan_create(d, &why);
+    }
+    GenWgradSpec w{};
+    w.kind = GEN_CONV_S2; w.s_layout = f.in_layout; w.s_KC = f.KCk; w.u_layout = GEN_PLAIN; w.u_KC = kc16(h->ec[l + 1]);
+    w.Cs = h->ec[l]; w.Cu = h->ec[l + 1]; w.w_mode = 0; w.Hg = h->eh[l + 1]; w.Wg = h->ew[l + 1];
+    E[l].wgrad = gen_wgrad_plan_create(w, &why);
+    ok = E[l].fwd && E[l].fwd_split && (l == 0 || E[l].dgrad) && E[l].wgrad;
+  }
+  if (ok) { h->gen_e = E; h->gen_enc = true; } else gen_free_plans(E);
+  // ---- decoder
+  const bool special_tail = h->use_tc_out;
+  const bool dense_planar = h->dc[0] % 8 == 0 && h->dec_units >= 64 && h->latent <= 4096;
+  std::vector<kcvae_model::GenLayerPlans> D(L + 1);
+  auto convT_plans = [&](int l, bool with_fwd) {
+    const int kin = kc_act_d(h, l);
+    if (with_fwd) {
+      GenConvSpec f{};
+      f.kind = GEN_CONVT_S2; f.in_layout = GEN_PLAIN; f.Ck = h->dc[l]; f.Cn = h->dc[l + 1]; f.KCk = kin; f.w_mode = 1;
+      f.Hg = h->dh[l]; f.Wg = h->dw[l];
+      D[l].fwd = gen_conv_plan_create(f, &why);
+    }
+    GenConvSpec d{};
+    d.kind = GEN_CONV_S2; d.in_layout = GEN_S2D; d.Ck = h->dc[l + 1]; d.Cn = h->dc[l]; d.KCk = kc16(h->dc[l + 1]); d.w_mode = 0;
+    d.Hg = h->dh[l]; d.Wg = h->dw[l];
+    D[l].dgrad = gen_conv_plan_create(d, &why);
+    GenWgradSpec w{};
+    w.kind = GEN_CONVT_S2; w.s_layout = GEN_PLAIN; w.s_KC = kin; w.u_layout = GEN_S2D; w.u_KC = kc16(h->dc[l + 1]);
+    w.Cs = h->dc[l]; w.Cu = h->dc[l + 1]; w.w_mode = 1; w.Hg = h->dh[l]; w.Wg = h->dw[l];
+    D[l].wgrad = gen_wgrad_plan_create(w, &why);
+    return (!with_fwd || D[l].fwd) && D[l].dgrad && D[l].wgrad;
+  };
+  if (!special_tail && dense_planar && h->C <= 8 && h->dh[L] == h->H && h->dw[L] == h->W) {
+    bool dok = true;
+    for (int l = 0; l < L && dok; ++l) dok = convT_plans(l, true);
+    if (dok) {
+      GenConvSpec f{};
+      f.kind = GEN_CONV_S1; f.in_layout = GEN_PLAIN; f.Ck = h->dc[L]; f.Cn = h->C; f.KCk = kc_act_d(h, L); f.w_mode = 1; f.flip = 1;
+      f.Hg = h->H; f.Wg = h->W;
+      D[L].fwd = gen_conv_plan_create(f, &why);
+      GenConvSpec d{};
+      d.kind = GEN_CONV_S1; d.in_layout = GEN_PLAIN; d.Ck = h->C; d.Cn = h->dc[L]; d.KCk = 1; d.w_mode = 0; d.flip = 0;
+      d.Hg = h->H; d.Wg = h->W;
+      D[L].dgrad = gen_conv_plan_create(d, &why);
+      GenWgradSpec w{};
+      w.kind = GEN_CONV_S1; w.flip = 1; w.s_layout = GEN_PLAIN; w.s_KC = kc_act_d(h, L); w.u_layout = GEN_PLAIN; w.u_KC = 1;
+      w.Cs = h->dc[L]; w.Cu = h->C; w.w_mode = 1; w.Hg = h->H; w.Wg = h->W;
+      D[L].wgrad = gen_wgrad_plan_create(w, &why);
+      dok = D[L].fwd && D[L].dgrad && D[L].wgrad;
+    }
+    if (dok) { h->gen_d = D; h->gen_dec = true; } else gen_free_plans(D);
+  } else if (special_tail && h->use_tc_convT && h->use_tc_convT_few && h->use_tc_convT_few_train && h->use_tc_convT_bwd && L == 2 &&
+             dense_planar) {
+    // README-style decoder: the specialised tail kernels stay; the backward of the first Conv2DTranspose joins the engine
+    if (convT_plans(0, false)) { h->gen_d = D; h->gen_dec0 = true; } else gen_free_plans(D);
+  }
+  if (!h->gen_enc && !h->gen_dec && !h->gen_dec0) return KCVAE_OK;
+  // ---- weight images: one gather table for all plans
+  for (int l = 0; l < L && h->gen_enc; ++l) {
+    const int vi = h->vi_enc_conv(l);
+    h->gen_e[l].img_fwd = gen_add_image(h, h->gen_e[l].fwd, vi);
+    h->gen_e[l].img_fwd_split = gen_add_image(h, h->gen_e[l].fwd_split, vi);
+    if (h->gen_e[l].dgrad) h->gen_e[l].img_dgrad = gen_add_image(h, h->gen_e[l].dgrad, vi);
+  }
+  for (int l = 0; l <= L && (h->gen_dec || h->gen_dec0); ++l) {
+    if (l >= (int)h->gen_d.size()) break;
+    const int vi = l < L ? h->vi_dec_convT(l) : h->vi_out();
+    if (h->gen_d[l].fwd) h->gen_d[l].img_fwd = gen_add_image(h, h->gen_d[l].fwd, vi);
+    if (h->gen_d[l].dgrad) h->gen_d[l].img_dgrad = gen_add_image(h, h->gen_d[l].dgrad, vi);
+  }
+  h->gen_wimg_bytes = h->gen_table_host.size() * 2;
+  KC_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->gen_wimg), h->gen_wimg_bytes + 16));
+  KC_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->gen_table), h->gen_table_host.size() * sizeof(int32_t) + 16));
+  KC_CUDA(h, cudaMemcpy(h->gen_table, h->gen_table_host.data(), h->gen_table_host.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  KC_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->gen_partial), gen_wgrad_partial_floats(nullptr) * sizeof(float)));
+  KC_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->gen_partial2), gen_wgrad_partial_floats(nullptr) * sizeof(float)));
+  return KCVAE_OK;
+}
+
+// all bf16 weight images of the engine in one launch, only after the weights changed
+void gen_refresh(kcvae_model* h, cudaStream_t st) {
+  if (!h->gen_wimg || (!h->w_external && h->gen_img_version == h->w_version)) return;
+  g_tag = "step";
+  gen_gather_weights(h->w, h->gen_table, (int64_t)h->gen_table_host.size(), h->gen_wimg, st);
+  h->gen_img_version = h->w_version;
+}
+
+int gen_alloc(kcvae_model* h, void** p, size_t units) {
+  if (*p) { cudaFree(*p); *p = nullptr; }
+  KC_CUDA(h, cudaMalloc(p, (units ? units : 1) * 16));
+  return KCVAE_OK;
+}
+#endif
+
 template <typename T>
 int dalloc(kcvae_model* h, T** p, size_t n) {
   if (*p) { cudaFree(*p); *p = nullptr; }
@@ -303,8 +491,27 @@ int ensure_fwd(kcvae_model* h, int B) {
   const int L = h->L;
   h->act_e.resize(L + 1, nullptr);
   h->act_d.resize(L + 1, nullptr);
-  for (int l = 1; l <= L; ++l) KC_TRY(dalloc(h, &h->act_e[l], (size_t)B * h->eh[l] * h->ew[l] * h->ec[l]));
-  for (int l = 0; l <= L; ++l) KC_TRY(dalloc(h, &h->act_d[l], (size_t)B * h->dh[l] * h->dw[l] * h->dc[l]));
+#ifndef KCVAE_EMU
+  const bool gen_enc = h->gen_enc, gen_dec = h->gen_dec;
+#else
+  const bool gen_enc = false, gen_dec = false;
+#endif
+  // fp32 NHWC activations exist only where a CUDA-core / specialised kernel or a Dense layer reads them
+  for (int l = 1; l <= L; ++l)
+    if (!gen_enc || l == L) KC_TRY(dalloc(h, &h->act_e[l], (size_t)B * h->eh[l] * h->ew[l] * h->ec[l]));
+  for (int l = 0; l <= L; ++l)
+    if (!gen_dec) KC_TRY(dalloc(h, &h->act_d[l], (size_t)B * h->dh[l] * h->dw[l] * h->dc[l]));
+#ifndef KCVAE_EMU
+  if (gen_enc) {
+    h->act_e_pl.resize(L + 1, nullptr);
+    KC_TRY(gen_alloc(h, &h->x_pl, pl_x(h, 1).units(B)));
+    for (int l = 1; l < L; ++l) KC_TRY(gen_alloc(h, &h->act_e_pl[l], pl_act_e(h, l, 1).units(B)));
+  }
+  if (gen_dec) {
+    h->act_d_pl.resize(L + 1, nullptr);
+    for (int l = 0; l <= L; ++l) KC_TRY(gen_alloc(h, &h->act_d_pl[l], pl_act_d(h, l, 0).units(B)));
+  }
+#endif
   KC_TRY(dalloc(h, &h->x_stage[0], (size_t)B * h->P));
   KC_TRY(dalloc(h, &h->x_stage[1], (size_t)B * h->P));
   h->x_in = h->x_stage[0];
@@ -367,8 +574,25 @@ int ensure_bwd(kcvae_model* h, int B) {
   const int Bc = h->cap_fwd;
   h->g_act_e.resize(L + 1, nullptr);
   h->g_act_d.resize(L + 1, nullptr);
-  for (int l = 1; l <= L; ++l) KC_TRY(dalloc(h, &h->g_act_e[l], (size_t)Bc * h->eh[l] * h->ew[l] * h->ec[l]));
-  for (int l = 0; l <= L; ++l) KC_TRY(dalloc(h, &h->g_act_d[l], (size_t)Bc * h->dh[l] * h->dw[l] * h->dc[l]));
+#ifndef KCVAE_EMU
+  const bool gen_enc = h->gen_enc, gen_dec = h->gen_dec;
+#else
+  const bool gen_enc = false, gen_dec = false;
+#endif
+  for (int l = 1; l <= L; ++l)
+    if (!gen_enc || l == L) KC_TRY(dalloc(h, &h->g_act_e[l], (size_t)Bc * h->eh[l] * h->ew[l] * h->ec[l]));
+  for (int l = 0; l <= L; ++l)
+    if (!gen_dec || l == 0) KC_TRY(dalloc(h, &h->g_act_d[l], (size_t)Bc * h->dh[l] * h->dw[l] * h->dc[l]));
+#ifndef KCVAE_EMU
+  if (gen_enc) {
+    h->g_e_pl.resize(L + 1, nullptr);
+    for (int l = 1; l <= L; ++l) KC_TRY(gen_alloc(h, &h->g_e_pl[l], pl_g_e(h, l).units(Bc)));
+  }
+  if (gen_dec || h->gen_dec0) {
+    h->g_d_pl.resize(L + 1, nullptr);
+    for (int l = 1; l <= (gen_dec ? L : 1); ++l) KC_TRY(gen_alloc(h, &h->g_d_pl[l], pl_g_d(h, l).units(Bc)));
+  }
+#endif
   KC_TRY(dalloc(h, &h->dlogit, (size_t)Bc * h->P));
   KC_TRY(dalloc(h, &h->g_z, (size_t)Bc * h->latent));
   KC_TRY(dalloc(h, &h->dhead, (size_t)Bc * 2 * h->latent));
@@ -378,7 +602,7 @@ int ensure_bwd(kcvae_model* h, int B) {
     KC_TRY(dalloc(h, &gs, (size_t)Bc * h->H * h->W * h->dc[L]));
     h->g_s2d = gs;
   }
-  if (h->use_tc_dgrad) {
+  if (h->use_tc_dgrad || gen_dec) {
     KC_TRY(dalloc(h, &h->dl8, (size_t)Bc * h->H * h->W * 8));
     KC_CUDA(h, cudaMemset(h->dl8, 0, (size_t)Bc * h->H * h->W * 8 * sizeof(uint16_t)));   // channel padding stays zero
   }
@@ -421,8 +645,40 @@ int tc_flag_check(kcvae_model* h, cudaStream_t st) {   // enqueue the flag read-
 }
 
 // ------------------------------------------------------------------------------ forward
-void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st) {
+#ifndef KCVAE_EMU
+// encoder convolutions on the general engine: x -> 2x2 space-to-depth bf16 planes (hi + lo when `split`), every Conv2D s2
+// as a stride-1 product over them; the last activation leaves as fp32 NHWC for the Dense layers
+void gen_run_encoder_convs(kcvae_model* h, const float* x, int B, int split, cudaStream_t st) {
+  const int L = h->L;
+  gen_refresh(h, st);
+  h->enc_split_live = split != 0;
+  GenPlanes in = pl_x(h, split);
+  g_tag = "enc.pack";
+  if (h->C == 3) gen_pack_x3(x, B, h->H, h->W, split, h->x_pl, st);
+  else gen_pack_nhwc(x, B, h->H, h->W, h->C, in, st);
+  for (int l = 0; l < L; ++l) {
+    const auto& g = h->gen_e[l];
+    GenEpilogue e{};
+    e.pre = GEN_PRE_BIAS_RELU; e.bias = h->wp(h->vi_enc_conv(l) + 1);
+    GenPlanes out{};
+    if (l + 1 < L) { out = pl_act_e(h, l + 1, split); e.out = &out; }
+    else e.out_f32 = h->act_e[L];
+    g_tag = l == 0 ? "enc.conv0.fwd" : (l == 1 ? "enc.conv1.fwd" : "enc.convN.fwd");
+    if (gen_conv_run(split ? g.fwd_split : g.fwd, in, h->gen_wimg + (split ? g.img_fwd_split : g.img_fwd), e, B, h->tc_error,
+                     "gen_conv", st) != 0) h->tc_failed = true;
+    in = out;
+  }
+}
+#endif
+
+void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st, int split = 0) {
   const float* in = x;
+#ifndef KCVAE_EMU
+  if (h->gen_enc) {
+    gen_run_encoder_convs(h, x, B, split && h->enc_split, st);
+    in = h->act_e[h->L];
+  } else
+#endif
   for (int l = 0; l < h->L; ++l) {
     ConvArgs a{};
     a.in = in; a.w = h->wp(h->vi_enc_conv(l)); a.bias = h->wp(h->vi_enc_conv(l) + 1); a.out = h->act_e[l + 1];
@@ -492,6 +748,29 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   ga.C = h->act_d[0]; ga.bias = h->wp(h->vi_dec_dense() + 1); ga.relu = 1;
   ga.M = B; ga.N = h->dec_units; ga.K = h->latent; ga.partial = h->partial;
   g_tag = "dec.dense.fwd";
+#ifndef KCVAE_EMU
+  if (h->gen_dec) {
+    // whole decoder on the general engine: Dense -> bf16 planes, every Conv2DTranspose and the output layer as tcgen05 products
+    gen_refresh(h, st);
+    dense_wide_forward(z, ga.Bm, ga.bias, nullptr, B, h->dec_units, h->latent, 1, st, h->act_d_pl[0], h->dc[0], 0);
+    for (int l = 0; l <= L; ++l) {
+      const auto& g = h->gen_d[l];
+      GenPlanes in = pl_act_d(h, l, 0), outp{};
+      GenEpilogue e{};
+      if (l < L) {
+        e.pre = GEN_PRE_BIAS_RELU; e.bias = h->wp(h->vi_dec_convT(l) + 1);
+        outp = pl_act_d(h, l + 1, 0); e.out = &outp;
+        g_tag = l == L - 1 ? "dec.convT_last.fwd" : "dec.convT.fwd";
+      } else {
+        e.pre = apply_sigmoid ? GEN_PRE_BIAS_SIGMOID : GEN_PRE_BIAS; e.bias = h->wp(h->vi_out() + 1);
+        e.out_f32 = out;
+        g_tag = "dec.out.fwd";
+      }
+      if (gen_conv_run(g.fwd, in, h->gen_wimg + g.img_fwd, e, B, h->tc_error, "gen_conv", st) != 0) h->tc_failed = true;
+    }
+    return;
+  }
+#endif
   // the 32 -> few tensor-core Conv2DTranspose reads the Dense output as chunk-planar bf16: when the Dense is the layer right
   // before it, it writes that copy itself (and, with nothing else reading the fp32 activation, only that copy)
   bool few_tc = false, pp_ready = false;
@@ -509,6 +788,9 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
     pp_ready = few_tc && L == 2 && h->dc[0] % 8 == 0;
     dense_wide_forward(z, ga.Bm, ga.bias, (pp_ready && !keep_last) ? nullptr : ga.C, B, h->dec_units, h->latent, 1, st,
                        pp_ready ? h->a_pp_planar : nullptr, h->dc[0], split ? 1 : 0);
+#ifndef KCVAE_EMU
+    h->pp_live = pp_ready && split;
+#endif
   } else {
     gemm(ga, st);
   }
@@ -584,7 +866,12 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
 // encode -> reparameterize -> decode+sigmoid into h->xhat (or user buffer); z/mean/logvar in h
 void run_forward(kcvae_model* h, const float* x, int B, int training, const float* eps, float* xhat, cudaStream_t st,
                  bool keep_last = true, TailOut* tail = nullptr) {
-  run_encoder(h, x, B, st);
+#ifndef KCVAE_EMU
+  const int esplit = (keep_last || h->force_split) ? 1 : 0;   // steps with a backward pass and loss evaluations: fp32-grade encoder products
+#else
+  const int esplit = 0;
+#endif
+  run_encoder(h, x, B, st, esplit);
   const int gen = (training && !eps) ? 1 : 0;
   g_tag = "latent";
   reparameterize(h->head, B, h->latent, eps, gen, h->seed, h->rng_counter, h->z, h->mean, h->logvar,
@@ -640,7 +927,11 @@ int run_stats(kcvae_model* h, const float* x, const float* xhat, int B, int tier
   ia.pos_sums = (full && h->world > 1) ? h->pos_sums : nullptr;
   // tensor-core tail: d(loss)/d(logit) only as bf16 8-channel units, and the output-layer bias
   // gradient (its channel sums) straight from this pass - no fp32 copy, no colsum pass
-  const bool tc_tail = with_grad && h->use_tc_dgrad && h->use_tc_out && h->C <= 8;
+#ifndef KCVAE_EMU
+  const bool tc_tail = with_grad && ((h->use_tc_dgrad && h->use_tc_out && h->C <= 8) || h->gen_dec);
+#else
+  const bool tc_tail = false;
+#endif
   ia.dlogit = (with_grad && !tc_tail) ? h->dlogit : nullptr;
   ia.dl8 = tc_tail ? h->dl8 : nullptr;
   ia.dbias = tc_tail ? h->gp(h->vi_out() + 1) : nullptr;
@@ -716,6 +1007,46 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
   const int L = h->L;
   const int Bg = B * h->world;
   bool tail_s2d = false;   // d loss / d a_last lives as bf16 space-to-depth (tensor-core tail)
+#ifndef KCVAE_EMU
+  const bool gen_dec = h->gen_dec;
+  if (gen_dec) {
+    // whole decoder backward on the general engine.  Per layer: data gradient on the caller's stream (the critical chain),
+    // weight + bias gradient on the side stream behind it.  Gradients travel as bf16 space-to-depth planes.
+    gen_refresh(h, st);
+    GenPlanes dl = pl_make(h->dl8, GEN_PLAIN, 1, 0, h->H, h->W);
+    {
+      const auto& g = h->gen_d[L];
+      GenPlanes act = pl_act_d(h, L, 0), gout = pl_g_d(h, L);
+      GenEpilogue e{};
+      e.pre = GEN_PRE_NONE; e.mask = &act; e.out = &gout;
+      g_tag = "dec.out.bwd";
+      if (gen_conv_run(g.dgrad, dl, h->gen_wimg + g.img_dgrad, e, B, h->tc_error, "gen_dgrad", st) != 0) h->tc_failed = true;
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);
+      g_tag = "dec.out.bwd";
+      if (gen_wgrad_run(g.wgrad, act, dl, h->gp(h->vi_out()), nullptr, ax == st ? h->gen_partial : h->gen_partial2, B, h->tc_error,
+                        "gen_wgrad", ax) != 0) h->tc_failed = true;      // bias gradient: image_stats
+    }
+    for (int l = L - 1; l >= 0; --l) {
+      const auto& g = h->gen_d[l];
+      const int vi = h->vi_dec_convT(l);
+      GenPlanes act = pl_act_d(h, l, 0), gin = pl_g_d(h, l + 1), gout{};
+      GenEpilogue e{};
+      e.pre = GEN_PRE_NONE; e.mask = &act;
+      if (l > 0) { gout = pl_g_d(h, l); e.out = &gout; } else e.out_f32 = h->g_act_d[0];
+      g_tag = l == L - 1 ? "dec.convT_last.bwd" : "dec.convT.bwd";
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);      // the incoming gradient is complete on st: the side stream may read it
+      if (gen_wgrad_run(g.wgrad, act, gin, h->gp(vi), h->gp(vi + 1), ax == st ? h->gen_partial : h->gen_partial2, B, h->tc_error,
+                        "gen_wgrad", ax) != 0) h->tc_failed = true;
+      g_tag = l == L - 1 ? "dec.convT_last.bwd" : "dec.convT.bwd";
+      if (gen_conv_run(g.dgrad, gin, h->gen_wimg + g.img_dgrad, e, B, h->tc_error, "gen_dgrad", st) != 0) h->tc_failed = true;
+    }
+  }
+#else
+  const bool gen_dec = false;
+#endif
+  if (!gen_dec)
   {  // output Conv2DTranspose (s1): wgrad, bias grad, dgrad (+ReLU mask of its input)
     const int vi = h->vi_out();
     WgradArgs wa{};
@@ -767,7 +1098,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     }
 #endif
   }
-  for (int l = L - 1; l >= 0; --l) {  // decoder Conv2DTranspose (s2) layers
+  for (int l = L - 1; l >= 0 && !gen_dec; --l) {  // decoder Conv2DTranspose (s2) layers
     const int vi = h->vi_dec_convT(l);
     WgradArgs wa{};
     wa.P = h->act_d[l]; wa.Q = h->g_act_d[l + 1]; wa.out = h->gp(vi); wa.partial = h->partial;
@@ -786,6 +1117,26 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       ok = ok && tc_convT_wgrad(h->g_s2d, h->a_prev8, h->gp(vi), px, B, h->dh[l], h->dw[l], h->dc[l], h->tc_error, ax) == 0;
       if (!ok) h->tc_failed = true;
       continue;   // bias gradient was produced by tc_out_dgrad
+    }
+#endif
+#ifndef KCVAE_EMU
+    if (l == 0 && h->gen_dec0 && tail_s2d && h->pp_live) {
+      // backward of the first Conv2DTranspose on the general engine: its incoming gradient (fp32 NHWC from the specialised
+      // kernel behind it) is repacked as bf16 space-to-depth planes; the layer input is the hi + lo plane copy the Dense wrote
+      gen_refresh(h, st);
+      const auto& g = h->gen_d[0];
+      GenPlanes act = pl_act_d(h, 0, 1), gin = pl_g_d(h, 1);
+      gen_pack_nhwc(h->g_act_d[1], B, h->dh[1], h->dw[1], h->dc[1], gin, st);
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);
+      g_tag = "dec.convT.bwd";
+      if (gen_wgrad_run(g.wgrad, act, gin, h->gp(vi), h->gp(vi + 1), ax == st ? h->gen_partial : h->gen_partial2, B, h->tc_error,
+                        "gen_wgrad", ax) != 0) h->tc_failed = true;
+      GenEpilogue e{};
+      e.pre = GEN_PRE_NONE; e.mask = &act; e.out_f32 = h->g_act_d[0];
+      g_tag = "dec.convT.bwd";
+      if (gen_conv_run(g.dgrad, gin, h->gen_wimg + g.img_dgrad, e, B, h->tc_error, "gen_dgrad", st) != 0) h->tc_failed = true;
+      continue;
     }
 #endif
     {
@@ -894,7 +1245,40 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     KC_TRY(allreduce(h, h->g + off_dense, enc_tail_floats - off_dense, 0, 0, cs));
     enc_tail_floats = off_dense;
   }
-  for (int l = L - 1; l >= 0; --l) {  // encoder Conv2D (s2) layers
+#ifndef KCVAE_EMU
+  const bool gen_enc = h->gen_enc;
+  if (gen_enc && L > 0) {
+    // encoder convolutions' backward on the general engine: the Dense layers hand over d loss / d act_e[L] as fp32 NHWC
+    // (ReLU mask applied); from there the gradient travels as bf16 planes.  S operand of every weight gradient = the
+    // space-to-depth planes the forward pass wrote (hi planes).
+    gen_refresh(h, st);
+    const int split = h->enc_split_live ? 1 : 0;
+    g_tag = "enc.pack";
+    gen_pack_nhwc(h->g_act_e[L], B, h->eh[L], h->ew[L], h->ec[L], pl_g_e(h, L), st);
+    for (int l = L - 1; l >= 0; --l) {
+      const auto& g = h->gen_e[l];
+      const int vi = h->vi_enc_conv(l);
+      GenPlanes act = l == 0 ? pl_x(h, split) : pl_act_e(h, l, split), gin = pl_g_e(h, l + 1);
+      g_tag = l == 0 ? "enc.conv0.bwd" : (l == 1 ? "enc.conv1.bwd" : "enc.convN.bwd");
+      if (l > 0) {
+        float* px;
+        cudaStream_t ax = aux_fork(h, st, &px);
+        if (gen_wgrad_run(g.wgrad, act, gin, h->gp(vi), h->gp(vi + 1), ax == st ? h->gen_partial : h->gen_partial2, B, h->tc_error,
+                          "gen_wgrad", ax) != 0) h->tc_failed = true;
+        GenPlanes gout = pl_g_e(h, l);
+        GenEpilogue e{};
+        e.pre = GEN_PRE_NONE; e.mask = &act; e.out = &gout;
+        g_tag = l == 1 ? "enc.conv1.bwd" : "enc.convN.bwd";
+        if (gen_conv_run(g.dgrad, gin, h->gen_wimg + g.img_dgrad, e, B, h->tc_error, "gen_dgrad", st) != 0) h->tc_failed = true;
+      } else {
+        if (gen_wgrad_run(g.wgrad, act, gin, h->gp(vi), h->gp(vi + 1), h->gen_partial, B, h->tc_error, "gen_wgrad", st) != 0) h->tc_failed = true;
+      }
+    }
+  }
+#else
+  const bool gen_enc = false;
+#endif
+  for (int l = L - 1; l >= 0 && !gen_enc; --l) {  // encoder Conv2D (s2) layers
     const int vi = h->vi_enc_conv(l);
     const float* in = l > 0 ? h->act_e[l] : x;
     int pt, pl;
@@ -1022,14 +1406,17 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
   cudaMemset(h->v, 0, h->nparams * sizeof(float));
   cudaMemset(h->sums, 0, kSumsLen * sizeof(double));
 #ifndef KCVAE_EMU
-  if (cfg->precision == KCVAE_PREC_BF16_TC && tc_out_conv_supported(h->dc[h->L], h->C)) {
-    h->use_tc_out = true;
-    unsigned short* wi = nullptr;
-    if ((rc = dalloc(h, &wi, tc_out_weight_image_elems(h->dc[h->L]))) || (rc = dalloc(h, &h->tc_error, 1))) return bail(rc);
-    h->wimg_out = wi;
+  if (cfg->precision == KCVAE_PREC_BF16_TC) {
+    if ((rc = dalloc(h, &h->tc_error, 1))) return bail(rc);
     cudaMemset(h->tc_error, 0, sizeof(int));
     if (cudaMallocHost(reinterpret_cast<void**>(&h->tc_flag_host), sizeof(int)) == cudaSuccess) *h->tc_flag_host = 0;
     else h->tc_flag_host = nullptr;
+  }
+  if (cfg->precision == KCVAE_PREC_BF16_TC && tc_out_conv_supported(h->dc[h->L], h->C)) {
+    h->use_tc_out = true;
+    unsigned short* wi = nullptr;
+    if ((rc = dalloc(h, &wi, tc_out_weight_image_elems(h->dc[h->L])))) return bail(rc);
+    h->wimg_out = wi;
     if (h->L >= 1 && tc_convT_fwd_supported(h->dc[h->L - 1], h->dc[h->L])) {
       unsigned short* wc = nullptr;
       if ((rc = dalloc(h, &wc, tc_convT_weight_image_elems()))) return bail(rc);
@@ -1064,6 +1451,7 @@ int kcvae_create(const kcvae_config* cfg, int device, kcvae_handle* out) {
       h->use_tc_dgrad = true;
     }
   }
+  if (cfg->precision == KCVAE_PREC_BF16_TC && (rc = gen_setup(h))) return bail(rc);
 #endif
   if (cfg->max_batch > 0 && (rc = ensure_fwd(h, cfg->max_batch))) return bail(rc);
   *out = h;
@@ -1112,6 +1500,15 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->wimg_convT_few) cudaFree(h->wimg_convT_few);
   if (h->dl8) cudaFree(h->dl8);
   if (h->tc_error) cudaFree(h->tc_error);
+#ifndef KCVAE_EMU
+  gen_free_plans(h->gen_e); gen_free_plans(h->gen_d);
+  if (h->gen_wimg) cudaFree(h->gen_wimg);
+  if (h->gen_table) cudaFree(h->gen_table);
+  if (h->x_pl) cudaFree(h->x_pl);
+  for (auto* v : {&h->act_e_pl, &h->g_e_pl, &h->act_d_pl, &h->g_d_pl}) for (void* q : *v) if (q) cudaFree(q);
+  if (h->gen_partial) cudaFree(h->gen_partial);
+  if (h->gen_partial2) cudaFree(h->gen_partial2);
+#endif
   if (h->tc_flag_host) cudaFreeHost(h->tc_flag_host);
   if (h->pos_sums == h->sums + kSumsLen) h->pos_sums = nullptr;   // lives inside the sums allocation
   double* dl[] = {h->dpartial, h->sums, h->std_acc, h->pos_sums};
@@ -1374,7 +1771,13 @@ int kcvae_loss(kcvae_handle h, const float* d_x, int batch, int training, const 
   KC_CUDA(h, cudaSetDevice(h->device));
   KC_TRY(ensure_fwd(h, batch));
   float* xh = d_xhat ? d_xhat : h->xhat;
+#ifndef KCVAE_EMU
+  h->force_split = true;
+#endif
   run_forward(h, d_x, batch, training, d_eps, xh, st, false);
+#ifndef KCVAE_EMU
+  h->force_split = false;
+#endif
   KC_TRY(tc_check(h));
   KC_TRY(run_stats(h, d_x, xh, batch, tier, 0, st, st));
   run_finalize(h, batch, tier, d_metrics, st);
@@ -1677,6 +2080,31 @@ int64_t kcvae_debug_activation(kcvae_handle h, int which, float* h_out, int64_t 
   else if (which == 350) { src = h->g_z; n = (int64_t)B * h->latent; }
   else if (which == 351) { src = h->dhead; n = (int64_t)B * 2 * h->latent; }
   else if (which >= 361 && which <= 360 + L && (int)h->g_act_e.size() > which - 360) { int l = which - 360; src = h->g_act_e[l]; n = (int64_t)B * h->eh[l] * h->ew[l] * h->ec[l]; }
+#ifndef KCVAE_EMU
+  // tensors that only exist as bf16 planes of the general engine are unpacked on demand
+  GenPlanes pl{};
+  int ph = 0, pw = 0, pc = 0;
+  bool planes = false;
+  if (!src && n > 0) {
+    if (which >= 1 && which < L && h->gen_enc) { pl = pl_act_e(h, which, h->enc_split_live ? 1 : 0); ph = h->eh[which]; pw = h->ew[which]; pc = h->ec[which]; planes = true; }
+    else if (which >= 100 && which <= 100 + L && h->gen_dec) { int l = which - 100; pl = pl_act_d(h, l, 0); ph = h->dh[l]; pw = h->dw[l]; pc = h->dc[l]; planes = true; }
+    else if (which >= 302 && which <= 301 + L && h->gen_dec && (int)h->g_d_pl.size() > which - 301) { int l = which - 301; pl = pl_g_d(h, l); ph = h->dh[l]; pw = h->dw[l]; pc = h->dc[l]; planes = true; }
+    else if (which >= 361 && which < 360 + L && h->gen_enc && (int)h->g_e_pl.size() > which - 360) { int l = which - 360; pl = pl_g_e(h, l); ph = h->eh[l]; pw = h->ew[l]; pc = h->ec[l]; planes = true; }
+    if (planes && !pl.base) planes = false;
+  }
+  if (planes) {
+    if (!h_out) return n;
+    if (capacity < n) return fail(h, KCVAE_ERR_INVALID, "debug_activation: buffer too small");
+    float* tmp = nullptr;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (cudaMalloc(reinterpret_cast<void**>(&tmp), n * sizeof(float)) != cudaSuccess) return fail(h, KCVAE_ERR_CUDA, "debug_activation: cudaMalloc failed");
+    gen_unpack_nhwc(pl, B, ph, pw, pc, tmp, nullptr);
+    const bool okc = cudaMemcpy(h_out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(tmp);
+    return okc ? n : fail(h, KCVAE_ERR_CUDA, "debug_activation: copy failed");
+  }
+#endif
   if (!src) return fail(h, KCVAE_ERR_INVALID, "debug_activation: unknown or unallocated tensor");
   if (!h_out) return n;
   if (capacity < n) return fail(h, KCVAE_ERR_INVALID, "debug_activation: buffer too small");
@@ -1696,7 +2124,11 @@ int kcvae_tc_status(kcvae_handle h) {
   if (cudaDeviceSynchronize() != cudaSuccess) return fail(h, KCVAE_ERR_CUDA, "tc_status: device error");
   cudaMemcpy(&flag, h->tc_error, sizeof(int), cudaMemcpyDeviceToHost);
   if (flag) return fail(h, KCVAE_ERR_CUDA, "tcgen05 pipeline: bounded mbarrier wait expired");
-  return h->use_tc_out ? 1 : 0;
+#ifndef KCVAE_EMU
+  return (h->use_tc_out || h->gen_enc || h->gen_dec) ? 1 : 0;
+#else
+  return 0;
+#endif
 }
 
 // ---- per-launch timing ---------------------------------------------------------------------

@@ -318,7 +318,7 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
 }
 
 // fp32 weights -> bf16 image through a gather table: idx >= 0: hi part of w[idx]; idx | LO_FLAG: lo part; -1: zero
-constexpr int32_t LO_FLAG = 0x40000000;
+constexpr int32_t LO_FLAG = GEN_LO_FLAG;
 __global__ void gen_gather_weights_kernel(const float* __restrict__ w, const int32_t* __restrict__ idx, int64_t n, __nv_bfloat16* img) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int32_t e = idx[i];
@@ -576,6 +576,12 @@ void gen_conv_plan_free(GenConvPlan* p) {
 size_t gen_conv_weight_image_bytes(const GenConvPlan* p) { return p->table.size() * 2; }
 int gen_conv_Cop(const GenConvPlan* p) { return (int)p->host.Cop; }
 
+const int32_t* gen_conv_table(const GenConvPlan* p, size_t* n) { *n = p->table.size(); return p->table.data(); }
+void gen_gather_weights(const float* w, const int32_t* table_dev, int64_t n, void* img, cudaStream_t st) {
+  ProfScope prof_("gen_prep_weights", st);
+  ++g_launches;
+  gen_gather_weights_kernel<<<grid_for(n, 256, 8, 2), 256, 0, st>>>(w, table_dev, n, reinterpret_cast<__nv_bfloat16*>(img));
+}
 void gen_conv_prep_weights(const GenConvPlan* p, const float* w, void* img, cudaStream_t st) {
   ProfScope prof_("gen_prep_weights", st);
   ++g_launches;

@@ -42,6 +42,12 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not);
 void gen_conv_plan_free(GenConvPlan* p);
 size_t gen_conv_weight_image_bytes(const GenConvPlan* p);
 int gen_conv_Cop(const GenConvPlan* p);          // padded N channels (per parity)
+// host copy of the plan's gather table: one entry per bf16 element of the image; >= 0: index into the layer's fp32 weight
+// tensor (| GEN_LO_FLAG: the lo part of that weight), -1: structural zero.  A model concatenates the tables of all its
+// plans (adding each variable's offset in the flat parameter vector) and builds every image with ONE gen_gather_weights.
+constexpr int32_t GEN_LO_FLAG = 0x40000000;
+const int32_t* gen_conv_table(const GenConvPlan* p, size_t* n);
+void gen_gather_weights(const float* w, const int32_t* table_dev, int64_t n, void* img, cudaStream_t st);
 // fp32 weights -> bf16 B-operand image of this plan (hi half, then lo half when split)
 void gen_conv_prep_weights(const GenConvPlan* p, const float* w, void* img, cudaStream_t st);
 
