@@ -867,7 +867,9 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
 void run_forward(kcvae_model* h, const float* x, int B, int training, const float* eps, float* xhat, cudaStream_t st,
                  bool keep_last = true, TailOut* tail = nullptr) {
 #ifndef KCVAE_EMU
-  const int esplit = (keep_last || h->force_split) ? 1 : 0;   // steps with a backward pass and loss evaluations: fp32-grade encoder products
+  // fp32-grade (hi + lo) encoder products everywhere z / mean / logvar or a loss term leave the library; the scorer
+  // (tail != nullptr: only reconstruction errors leave) runs the encoder with plain bf16 operands
+  const int esplit = (tail == nullptr || keep_last || h->force_split) ? 1 : 0;
 #else
   const int esplit = 0;
 #endif
@@ -1716,7 +1718,7 @@ int kcvae_encode(kcvae_handle h, const float* d_x, int batch, int training, cons
     if (!d_img_noise) h->rng_counter += (uint64_t)(n + 1) / 2;
     x = h->x_noisy;
   }
-  run_encoder(h, x, batch, st);
+  run_encoder(h, x, batch, st, 1);
   // split: z computed with eps = 0 into scratch, mean / logvar to the caller
   reparameterize(h->head, batch, h->latent, nullptr, 0, 0, 0, h->z, d_mean, d_logvar, nullptr, st);
   h->last_B = batch;

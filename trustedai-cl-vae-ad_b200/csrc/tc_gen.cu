@@ -39,7 +39,11 @@ constexpr int G1_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
 constexpr int G1_STAGES = 2;
 constexpr size_t SMEM_BUDGET = 225 * 1024;
 
-struct G1Mma { uint32_t a_off, a_lbo, b_off, d_col, n, acc; };
+// one tcgen05.mma of the list, ready to issue: low descriptor words (start address and leading byte offset, 16-byte units,
+// relative to the stage base), the instruction descriptor, and the accumulator column with the accumulate flag in bit 31.
+// The high descriptor words are the same for every entry (stride byte offset 128, descriptor version 1).
+struct G1Mma { uint32_t a_lo, b_lo, idesc, dcol_acc; };
+constexpr uint32_t G1_DESC_HI = (128u >> 4) | (1u << 14);
 struct G1Slab { int mma0, mma_n, nplanes, b_src, b_bytes, pad0, pad1, pad2; int plane[G1_MAXPL]; };
 struct G1Group { int slab0, slab_n, a_par, pad; };
 struct G1PlanDev {
@@ -113,20 +117,23 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// epilogue variants (template flags): only the code a product needs is compiled into its kernel
+constexpr int E_PRE = 1, E_MASK = 2, E_OUTP = 4, E_LO = 8, E_F32 = 16, E_MASKF = 32, E_ALL = 63;
+
 // one 8-channel group of one output pixel: pre-op, mask, stores
-__device__ __forceinline__ void g1_emit8(const G1Params& p, float* v, int n, int oy, int ox, int chunk) {
+template <int EPI>
+__device__ __forceinline__ void g1_emit8(const G1Params& p, const float* s_bias, float* v, int n, int oy, int ox, int chunk, uint4 m) {
   const int c0 = chunk * 8;
-  if (p.pre != GEN_PRE_NONE) {
+  if ((EPI & E_PRE) && p.pre != GEN_PRE_NONE) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float y = v[k] + (c0 + k < p.Cn ? __ldg(p.bias + c0 + k) : 0.f);
+      float y = v[k] + s_bias[c0 + k];
       if (p.pre == GEN_PRE_BIAS_RELU) y = fmaxf(y, 0.f);
-      else if (p.pre == GEN_PRE_BIAS_SIGMOID) y = 1.0f / (1.0f + __expf(-y));
+      else if (p.pre == GEN_PRE_BIAS_SIGMOID) y = __fdividef(1.0f, 1.0f + __expf(-y));
       v[k] = c0 + k < p.Cn ? y : 0.f;
     }
   }
-  if (p.has_mask) {
-    const uint4 m = __ldg(p.mask.base + unit_index(p.mask, n, oy, ox, chunk, 0));
+  if ((EPI & E_MASK) && p.has_mask) {
     const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -134,18 +141,18 @@ __device__ __forceinline__ void g1_emit8(const G1Params& p, float* v, int n, int
       if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[k] = 0.f;
     }
   }
-  if (p.mask_f32) {
+  if ((EPI & E_MASKF) && p.mask_f32) {
     const float* mk = p.mask_f32 + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.Cn + c0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (c0 + k < p.Cn && !(__ldg(mk + k) > 0.f)) v[k] = 0.f;
   }
-  if (p.has_out) {
+  if ((EPI & E_OUTP) && p.has_out) {
     uint32_t h4[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) h4[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
     p.out.base[unit_index(p.out, n, oy, ox, chunk, 0)] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
-    if (p.out_lo) {
+    if ((EPI & E_LO) && p.out_lo) {
       uint32_t l4[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -156,14 +163,20 @@ __device__ __forceinline__ void g1_emit8(const G1Params& p, float* v, int n, int
       p.out.base[unit_index(p.out, n, oy, ox, chunk, 1)] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
     }
   }
-  if (p.out_f32) {
+  if ((EPI & E_F32) && p.out_f32) {
     float* o = p.out_f32 + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.Cn + c0;
+    if ((p.Cn & 3) == 0 && c0 + 8 <= p.Cn) {           // rows of Cn floats stay 16-byte aligned: two vector stores
+      reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (c0 + k < p.Cn) o[k] = v[k];
+      for (int k = 0; k < 8; ++k)
+        if (c0 + k < p.Cn) o[k] = v[k];
+    }
   }
 }
 
+template <int EPI>
 __global__ void __launch_bounds__(G1_THREADS, 1)
 tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -171,7 +184,9 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   unsigned char* stages = smem + G1_PLAN_BYTES;
   __shared__ uint64_t full_bar[G1_STAGES], empty_bar[G1_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_bias[256 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 256 + 8; i += G1_THREADS) s_bias[i] = (p.bias && i < p.Cn) ? __ldg(p.bias + i) : 0.f;
 
   {  // plan -> shared memory (header + the used slab / MMA entries)
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.plan);
@@ -244,16 +259,22 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
         fence_after_sync();
         const uint32_t base = smem_u32(stages + (size_t)s * stage_bytes);
         const int m0 = plan->slabs[sl].mma0, m1 = m0 + plan->slabs[sl].mma_n;
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t dbase = tmem + (uint32_t)((buf * MT + mt) * acc_cols);
-          const uint32_t abase = base + (uint32_t)mt * 2048u;
-#pragma unroll 2
-          for (int i = m0; i < m1; ++i) {
-            const G1Mma m = plan->mma[i];
-            const uint64_t da = make_desc_kmajor_noswz(abase + m.a_off, m.a_lbo, 128);
-            const uint64_t db = make_desc_kmajor_noswz(base + m.b_off, m.n * 16, 128);
-            const uint32_t idesc = make_idesc_bf16_f32(128, (int)m.n);
-            if (leader) mma_bf16_ss(dbase + m.d_col, da, db, idesc, m.acc);
+        // list entry outer, M-tile inner: one 16-byte shared-memory read and two adds per entry, one add per issued MMA
+        const uint32_t base16 = base >> 4;
+        const uint32_t dbase = tmem + (uint32_t)(buf * MT * acc_cols);
+        const uint4* list = reinterpret_cast<const uint4*>(plan->mma);
+#pragma unroll 4
+        for (int i = m0; i < m1; ++i) {
+          const uint4 m = list[i];
+          const uint64_t hi = (uint64_t)G1_DESC_HI << 32;
+          uint64_t da = hi | (uint64_t)(m.x + base16);
+          const uint64_t db = hi | (uint64_t)(m.y + base16);
+          uint32_t d = dbase + (m.w & 0x7FFFFFFFu);
+          const uint32_t acc = m.w >> 31;
+          for (int mt = 0; mt < MT; ++mt) {
+            if (leader) mma_bf16_ss(d, da, db, m.z, acc);
+            da += 128;                        // next M-tile: 128 pixels x 16 B
+            d += (uint32_t)acc_cols;
           }
         }
         if (leader) mma_commit(&empty_bar[s]);
@@ -278,9 +299,49 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
       const int a_par = plan->groups[grp].a_par;
       const int buf = tcount % NB;
       const uint32_t bph = (tcount / NB) & 1;
+      // A warp owns at most four (M-tile, 32-column block) units of a tile.  The ReLU-mask units of ALL of them are requested
+      // before the accumulator wait: they do not depend on the MMAs, and their global-memory latency then overlaps the
+      // tile's MMAs instead of being paid once per unit by a warp with nothing else to run.
+      const int nunits = MT * NCB;
+      uint4 mk[4][4];
+      if (EPI & E_MASK) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int u = half + 2 * k;
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) mk[k][j8] = make_uint4(0, 0, 0, 0);
+          if (u < nunits && p.has_mask) {
+            const int mt = u / NCB, cb = u % NCB;
+            const int ncols = min(32, acc_cols - cb * 32);
+            const int q = mt * 128 + lg * 32 + lane;
+            const int r = q / GP, c = q % GP;
+            const int gy = ty * TRr + r, gx = tx * TW + c;
+            if (c < TW && gy < p.Hg && gx < p.Wg) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                if (j8 * 8 < ncols) {
+                  const int col0 = cb * 32 + j8 * 8;
+                  int oy = gy, ox = gx, chunk = col0 >> 3;
+                  if (type == GEN_CONVT_S2) {
+                    const int b = col0 / Cop;
+                    chunk = (col0 - b * Cop) >> 3;
+                    oy = 2 * gy + a_par; ox = 2 * gx + b;
+                  }
+                  mk[k][j8] = __ldg(p.mask.base + unit_index(p.mask, n, oy, ox, chunk, 0));
+                }
+              }
+            }
+          }
+        }
+      }
       if (!mbar_wait(&tfull_bar[buf], bph)) { if (lane == 0) *p.error_flag = 1; break; }
       fence_after_sync();
-      for (int u = half; u < MT * NCB; u += 2) {
+      // (unrolled only where the prefetched mask registers need static indices: the other variants keep one copy of the
+      // unit body, which then stays resident in the instruction cache)
+#pragma unroll(((EPI & E_MASK) ? 4 : 1))
+      for (int k = 0; k < 4; ++k) {
+        const int u = half + 2 * k;
+        if (u >= nunits) break;
         const int mt = u / NCB, cb = u % NCB;
         const int ncols = min(32, acc_cols - cb * 32);
         const int q = mt * 128 + lg * 32 + lane;
@@ -302,7 +363,7 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
                 chunk = (col0 - b * Cop) >> 3;
                 oy = 2 * gy + a_par; ox = 2 * gx + b;
               }
-              g1_emit8(p, v + j8 * 8, n, oy, ox, chunk);
+              g1_emit8<EPI>(p, s_bias, v + j8 * 8, n, oy, ox, chunk, (EPI & E_MASK) ? mk[k][j8] : make_uint4(0, 0, 0, 0));
             }
           }
         }
@@ -417,7 +478,7 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
   G1PlanDev& D = P->host;
   memset(&D, 0, sizeof(D));
   D.n_groups = n_groups; D.type = s.kind; D.Cop = (uint32_t)Cop; D.acc_cols = acc_cols;
-  D.MT = (4 * acc_cols <= 512) ? 2 : 1;
+  D.MT = (8 * acc_cols <= 512) ? 4 : ((4 * acc_cols <= 512) ? 2 : 1);    // rows per tile = 4 * MT; two TMEM buffers
   D.NB = 2;
   int halo_r, halo_c;
   if (s.kind == GEN_CONV_S2) { D.row0 = 0; D.col0 = 0; halo_r = 1; halo_c = 1; }
@@ -536,10 +597,11 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
           for (int vnt = 0; vnt < variants; ++vnt) {
             if (n_mma >= G1_MAXMMA) { delete P; return no("MMA list too long"); }
             G1Mma& M = D.mma[n_mma++];
-            M.a_off = a_off + (vnt == 1 ? lo_planes : 0);
-            M.a_lbo = a_lbo;
-            M.b_off = vnt == 2 ? b_lo : b_hi;
-            M.d_col = 0; M.n = (uint32_t)N; M.acc = first ? 0u : 1u;
+            const uint32_t ao = a_off + (vnt == 1 ? lo_planes : 0), bo = vnt == 2 ? b_lo : b_hi;
+            M.a_lo = (ao >> 4) | ((a_lbo >> 4) << 16);
+            M.b_lo = (bo >> 4) | (((uint32_t)N * 16u >> 4) << 16);
+            M.idesc = make_idesc_bf16_f32(128, N);
+            M.dcol_acc = 0u | (first ? 0u : 0x80000000u);
             first = false;
           }
           boff += (size_t)N * 32;
@@ -625,8 +687,26 @@ int gen_conv_run(const GenConvPlan* P, const GenPlanes& in, const void* wimg, co
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   ProfScope prof_(name, st);
   ++g_launches;
-  cudaFuncSetAttribute(tc_gconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem);
-  tc_gconv_kernel<<<grid, G1_THREADS, P->smem, st>>>(tmap, p);
+  int flags = 0;
+  if (e.pre != GEN_PRE_NONE) flags |= E_PRE;
+  if (e.mask) flags |= E_MASK;
+  if (e.mask_f32) flags |= E_MASKF;
+  if (e.out) flags |= E_OUTP | (e.out->split ? E_LO : 0);
+  if (e.out_f32) flags |= E_F32;
+#define KC_G1_LAUNCH(F)                                                                                      \
+  do {                                                                                                       \
+    cudaFuncSetAttribute(tc_gconv_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem);   \
+    tc_gconv_kernel<F><<<grid, G1_THREADS, P->smem, st>>>(tmap, p);                                          \
+  } while (0)
+  switch (flags) {     // the products the model issues get their own lean kernels; anything else runs the catch-all
+    case E_PRE | E_OUTP | E_LO: KC_G1_LAUNCH(E_PRE | E_OUTP | E_LO); break;
+    case E_PRE | E_OUTP: KC_G1_LAUNCH(E_PRE | E_OUTP); break;
+    case E_PRE | E_F32: KC_G1_LAUNCH(E_PRE | E_F32); break;
+    case E_MASK | E_OUTP: KC_G1_LAUNCH(E_MASK | E_OUTP); break;
+    case E_MASK | E_F32: KC_G1_LAUNCH(E_MASK | E_F32); break;
+    default: KC_G1_LAUNCH(E_ALL); break;
+  }
+#undef KC_G1_LAUNCH
   return 0;
 }
 
@@ -641,7 +721,9 @@ constexpr int G2_MAXROLE = 4;
 constexpr int G2_MAXPL = 64;
 constexpr int G2_COLS = 512;
 
-struct G2Mma { uint32_t a_off, b_off, a_sbo, b_sbo, d_col, n, m, b_ones; };
+// low / high descriptor words relative to the stage base (B relative to the plane of ones when b_ones), instruction
+// descriptor, accumulator column
+struct G2Mma { uint32_t a_lo, a_hi, b_lo, b_hi, idesc, d_col, b_ones, pad; };
 struct G2Role { int mma0, mma_n, nS, nU, ncols, pad0, pad1, pad2; int s_plane[G2_MAXPL]; int u_plane[G2_MAXPL]; };
 struct G2PlanDev {
   int n_roles, TRr, R_s, row0, col0, TW, s_PL, u_PL;
@@ -734,16 +816,21 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
       const uint32_t ph = (it / G1_STAGES) & 1;
       if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
       fence_after_sync();
-      const uint32_t base = smem_u32(stages + (size_t)s * stage_bytes);
-      for (int ks = 0; ks < KS; ++ks) {
-        const uint32_t kadv = (uint32_t)ks * 256u;
-#pragma unroll 2
-        for (int i = R->mma0; i < R->mma0 + R->mma_n; ++i) {
-          const G2Mma m = plan->mma[i];
-          const uint64_t da = make_desc_kmajor_noswz(base + m.a_off + kadv, 128, m.a_sbo);
-          const uint64_t db = make_desc_kmajor_noswz((m.b_ones ? ones_addr : base + m.b_off) + kadv, 128, m.b_sbo);
-          const uint32_t idesc = make_idesc_bf16_f32((int)m.m, (int)m.n, 1, 1);
-          if (leader) mma_bf16_ss(tmem + m.d_col, da, db, idesc, (it | ks) != 0);
+      const uint32_t base16 = smem_u32(stages + (size_t)s * stage_bytes) >> 4;
+      // list entry outer, K step inner (every entry owns its accumulator): descriptors are built once per entry and tile,
+      // each issued MMA costs two adds
+      for (int i = R->mma0; i < R->mma0 + R->mma_n; ++i) {
+        const uint4 w0 = reinterpret_cast<const uint4*>(plan->mma)[2 * i];
+        const uint4 w1 = reinterpret_cast<const uint4*>(plan->mma)[2 * i + 1];
+        uint64_t da = ((uint64_t)w0.y << 32) | (uint64_t)(w0.x + base16);
+        uint64_t db = ((uint64_t)w0.w << 32) | (uint64_t)(w0.z + (w1.z ? (ones_addr >> 4) : base16));
+        const uint32_t d = tmem + w1.y;
+        uint32_t acc = it != 0;
+#pragma unroll 4
+        for (int ks = 0; ks < KS; ++ks) {
+          if (leader) mma_bf16_ss(d, da, db, w1.x, acc);
+          da += 16; db += 16;                // 16 pixels x 16 B
+          acc = 1;
         }
       }
       if (leader) mma_commit(&empty_bar[s]);
@@ -912,22 +999,30 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
       G2Mma& M = D.mma[n_mma++];
       const uint32_t shift = (uint32_t)taps[a.tap].shift * 16;
       const uint32_t s_base = (uint32_t)0, u_base = D.s_region;
+      uint32_t a_off, b_off, a_sbo, b_sbo;
       if (a_is_s) {
-        M.a_off = s_base + (uint32_t)(a.blk * blkA - s_first) * D.CHs + shift; M.a_sbo = D.CHs;
-        M.b_off = u_base + (uint32_t)(0 - u_first) * D.CHu; M.b_sbo = D.CHu;
+        a_off = s_base + (uint32_t)(a.blk * blkA - s_first) * D.CHs + shift; a_sbo = D.CHs;
+        b_off = u_base + (uint32_t)(0 - u_first) * D.CHu; b_sbo = D.CHu;
       } else {
-        M.a_off = u_base + (uint32_t)(a.blk * blkA - u_first) * D.CHu; M.a_sbo = D.CHu;
-        M.b_off = s_base + (uint32_t)(0 - s_first) * D.CHs + shift; M.b_sbo = D.CHs;
+        a_off = u_base + (uint32_t)(a.blk * blkA - u_first) * D.CHu; a_sbo = D.CHu;
+        b_off = s_base + (uint32_t)(0 - s_first) * D.CHs + shift; b_sbo = D.CHs;
       }
-      M.d_col = (uint32_t)a.d_col; M.n = (uint32_t)Nb; M.m = (uint32_t)Mblk; M.b_ones = 0;
+      // MN-major operands: leading byte offset = 128 (8 pixels), stride byte offset = plane stride
+      M.a_lo = (a_off >> 4) | ((128u >> 4) << 16); M.a_hi = (a_sbo >> 4) | (1u << 14);
+      M.b_lo = (b_off >> 4) | ((128u >> 4) << 16); M.b_hi = (b_sbo >> 4) | (1u << 14);
+      M.idesc = make_idesc_bf16_f32(Mblk, Nb, 1, 1);
+      M.d_col = (uint32_t)a.d_col; M.b_ones = 0;
     }
     if (r == 0) {
       for (int ub = 0; ub < ublocks; ++ub) {
         if (n_mma >= G2_MAXMMA) { delete P; return no("MMA list too long"); }
         G2Mma& M = D.mma[n_mma++];
-        M.a_off = D.s_region + (uint32_t)(ub * (MblkU / 8) - u_first) * D.CHu; M.a_sbo = D.CHu;
-        M.b_off = 0; M.b_sbo = D.CHu; M.b_ones = 1;
-        M.d_col = (uint32_t)(bias_col0 + ub * bias_n); M.n = (uint32_t)bias_n; M.m = (uint32_t)MblkU;
+        const uint32_t a_off = D.s_region + (uint32_t)(ub * (MblkU / 8) - u_first) * D.CHu;
+        M.a_lo = (a_off >> 4) | ((128u >> 4) << 16); M.a_hi = (D.CHu >> 4) | (1u << 14);
+        M.b_lo = 0u | ((128u >> 4) << 16); M.b_hi = (D.CHu >> 4) | (1u << 14);
+        M.idesc = make_idesc_bf16_f32(MblkU, bias_n, 1, 1);
+        M.b_ones = 1;
+        M.d_col = (uint32_t)(bias_col0 + ub * bias_n);
       }
     }
     R.mma_n = n_mma - R.mma0;
