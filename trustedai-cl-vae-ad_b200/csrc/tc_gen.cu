@@ -15,6 +15,7 @@
 // a bias gradient is one more accumulator against a plane of ones.  Each CTA dumps its accumulators once; a gather
 // kernel folds the CTAs in a fixed order (deterministic) straight into the Keras weight layout.
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,7 +36,8 @@ constexpr int GP = 32;                 // tile pitch: pixels per shared-memory r
 constexpr int G1_MAXMMA = 768;
 constexpr int G1_MAXSLAB = 32;
 constexpr int G1_MAXPL = 32;           // planes per slab (hi + lo)
-constexpr int G1_THREADS = 320;        // TMA warp, MMA warp, 8 epilogue warps
+constexpr int G1_EPI_WARPS = 16;       // four epilogue warps per TMEM lane group
+constexpr int G1_THREADS = 64 + 32 * G1_EPI_WARPS;   // TMA warp, MMA warp, epilogue warps
 constexpr int G1_STAGES = 2;
 constexpr size_t SMEM_BUDGET = 225 * 1024;
 
@@ -101,6 +103,7 @@ struct G1Params {
   const unsigned char* wimg;
   int B, Hg, Wg, tiles_y, tiles_x, num_tiles;
   int in_PL;         // planes per image of the K-side tensor (hi + lo)
+  int plan_units;    // 16-byte units of the plan that are in use
   int pre;
   const float* bias;
   PlaneRef mask; int has_mask;
@@ -189,10 +192,15 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   for (int i = threadIdx.x; i < 256 + 8; i += G1_THREADS) s_bias[i] = (p.bias && i < p.Cn) ? __ldg(p.bias + i) : 0.f;
 
   {  // plan -> shared memory (header + the used slab / MMA entries)
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(p.plan);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
-    const int nw = (int)(sizeof(G1PlanDev) / 4);
-    for (int i = threadIdx.x; i < nw; i += G1_THREADS) dst[i] = __ldg(src + i);
+    const uint4* src = reinterpret_cast<const uint4*>(p.plan);
+    uint4* dst = reinterpret_cast<uint4*>(plan);
+    const int nv = p.plan_units;                       // header + slabs + the used MMA entries, in 16-byte units
+    constexpr int PER = (int)((sizeof(G1PlanDev) / 16 + G1_THREADS - 1) / G1_THREADS);
+    uint4 tmp[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int i = threadIdx.x + k * G1_THREADS; if (i < nv) tmp[k] = __ldg(src + i); }   // all loads in flight
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { const int i = threadIdx.x + k * G1_THREADS; if (i < nv) dst[i] = tmp[k]; }
     // stages start as zeros: the pad units behind a slab's last plane are read by dummy K chunks (zero weights) and by
     // discarded rows, and 0 * NaN would poison an accumulator
     uint4* z = reinterpret_cast<uint4*>(stages);
@@ -202,7 +210,7 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   if (threadIdx.x == 32) {
     for (int s = 0; s < G1_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], G1_EPI_WARPS); }
     fence_mbar_init();
   }
   fence_async_smem();
@@ -287,7 +295,9 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
     // ================================ epilogue warps ======================================
     const int e = warp - 2;
     const int lg = warp & 3;                      // TMEM lane group this warp may access
-    const int half = e >> 2;                      // two warps per lane group share the (M-tile, column block) units
+    const int half = e >> 2;                      // the warps of a lane group share the (M-tile, column block) units round robin
+    constexpr int WPG = G1_EPI_WARPS / 4;         // warps per lane group
+    constexpr int UPW = 8 / WPG;                  // units per warp and tile (a tile has at most 8 units)
     const int type = plan->type;
     const int Cop = (int)plan->Cop;
     const int NCB = (acc_cols + 31) / 32;
@@ -299,15 +309,15 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
       const int a_par = plan->groups[grp].a_par;
       const int buf = tcount % NB;
       const uint32_t bph = (tcount / NB) & 1;
-      // A warp owns at most four (M-tile, 32-column block) units of a tile.  The ReLU-mask units of ALL of them are requested
+      // A warp owns at most UPW (M-tile, 32-column block) units of a tile.  The ReLU-mask units of ALL of them are requested
       // before the accumulator wait: they do not depend on the MMAs, and their global-memory latency then overlaps the
       // tile's MMAs instead of being paid once per unit by a warp with nothing else to run.
       const int nunits = MT * NCB;
-      uint4 mk[4][4];
+      uint4 mk[UPW][4];
       if (EPI & E_MASK) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int u = half + 2 * k;
+        for (int k = 0; k < UPW; ++k) {
+          const int u = half + WPG * k;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) mk[k][j8] = make_uint4(0, 0, 0, 0);
           if (u < nunits && p.has_mask) {
@@ -338,9 +348,9 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
       fence_after_sync();
       // (unrolled only where the prefetched mask registers need static indices: the other variants keep one copy of the
       // unit body, which then stays resident in the instruction cache)
-#pragma unroll(((EPI & E_MASK) ? 4 : 1))
-      for (int k = 0; k < 4; ++k) {
-        const int u = half + 2 * k;
+#pragma unroll(((EPI & E_MASK) ? UPW : 1))
+      for (int k = 0; k < UPW; ++k) {
+        const int u = half + WPG * k;
         if (u >= nunits) break;
         const int mt = u / NCB, cb = u % NCB;
         const int ncols = min(32, acc_cols - cb * 32);
@@ -671,6 +681,7 @@ int gen_conv_run(const GenConvPlan* P, const GenPlanes& in, const void* wimg, co
   p.plan = P->dev;
   p.wimg = reinterpret_cast<const unsigned char*>(wimg);
   p.B = B; p.Hg = s.Hg; p.Wg = s.Wg; p.in_PL = in.planes();
+  p.plan_units = (int)((offsetof(G1PlanDev, mma) + (size_t)D.n_mma * sizeof(G1Mma) + 15) / 16);
   p.tiles_y = cdiv(s.Hg, 4 * D.MT); p.tiles_x = cdiv(s.Wg, D.TW);
   p.num_tiles = B * p.tiles_y * p.tiles_x * D.n_groups;
   p.pre = e.pre; p.bias = e.bias;
