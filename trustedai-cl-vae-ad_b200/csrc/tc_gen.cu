@@ -201,11 +201,15 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
     for (int k = 0; k < PER; ++k) { const int i = threadIdx.x + k * G1_THREADS; if (i < nv) tmp[k] = __ldg(src + i); }   // all loads in flight
 #pragma unroll
     for (int k = 0; k < PER; ++k) { const int i = threadIdx.x + k * G1_THREADS; if (i < nv) dst[i] = tmp[k]; }
-    // stages start as zeros: the pad units behind a slab's last plane are read by dummy K chunks (zero weights) and by
-    // discarded rows, and 0 * NaN would poison an accumulator
-    uint4* z = reinterpret_cast<uint4*>(stages);
-    const int nz = (int)((size_t)G1_STAGES * __ldg(&p.plan->stage_bytes) / 16);
-    for (int i = threadIdx.x; i < nz; i += G1_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    // the pad units behind a slab's last plane are read by dummy K chunks (zero weights) and by discarded rows, and
+    // 0 * NaN would poison an accumulator: they start as zeros
+    // (only the 8 units right behind every plane position can be such a pad; planes landing there later overwrite them)
+    const uint32_t sb = __ldg(&p.plan->stage_bytes), chb = __ldg(&p.plan->CHb), areg = __ldg(&p.plan->a_region);
+    const int npos = (int)((areg - 128) / chb);               // plane positions of a stage
+    for (int i = threadIdx.x; i < G1_STAGES * npos * 8; i += G1_THREADS) {
+      const int s_ = i / (npos * 8), r_ = i % (npos * 8);
+      reinterpret_cast<uint4*>(stages + (size_t)s_ * sb + (size_t)(r_ / 8 + 1) * chb)[r_ % 8] = make_uint4(0, 0, 0, 0);
+    }
   }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   if (threadIdx.x == 32) {
@@ -764,11 +768,16 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
     const uint32_t* src = reinterpret_cast<const uint32_t*>(p.plan);
     uint32_t* dst = reinterpret_cast<uint32_t*>(plan);
     for (int i = threadIdx.x; i < (int)(sizeof(G2PlanDev) / 4); i += G2_THREADS) dst[i] = __ldg(src + i);
-    // stages start as zeros: plane positions a role never loads and the pad behind the last plane are read as K elements
-    // against zero-filled gradient pixels, and 0 * NaN would poison an accumulator
-    uint4* z = reinterpret_cast<uint4*>(stages);
-    const int nz = (int)((size_t)G1_STAGES * __ldg(&p.plan->stage_bytes) / 16);
-    for (int i = threadIdx.x; i < nz; i += G2_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    // the pad behind a role's last S plane is read as K elements against zero-filled gradient pixels, and 0 * NaN would
+    // poison an accumulator: those units start as zeros
+    // (K elements = pixels: every pixel of a loaded plane is written by TMA; only the 8 units behind each S plane position can
+    // be read without having been written.  Plane positions a role never loads feed discarded rows / columns only.)
+    const uint32_t sb = __ldg(&p.plan->stage_bytes), chs = __ldg(&p.plan->CHs), sreg = __ldg(&p.plan->s_region);
+    const int npos = (int)((sreg - 128) / chs);
+    for (int i = threadIdx.x; i < G1_STAGES * npos * 8; i += G2_THREADS) {
+      const int s_ = i / (npos * 8), r_ = i % (npos * 8);
+      reinterpret_cast<uint4*>(stages + (size_t)s_ * sb + (size_t)(r_ / 8 + 1) * chs)[r_ % 8] = make_uint4(0, 0, 0, 0);
+    }
   }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   if (threadIdx.x == 32) {
@@ -923,30 +932,142 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
   else for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw)
     taps.push_back({kh, kw, s.flip ? (2 - kh) * GP + (2 - kw) : kh * GP + kw});
 
+  // An accumulator = one (tap, A plane run, B plane run) product: M = 8 * A planes (64 or 128, padded with whatever planes
+  // follow), N = 8 * B planes.  Two ways to cover a layer:
+  //   dense   A = 16- (or 8-) plane blocks of the operand with more planes, B = the whole other operand, every tap;
+  //   pruned  (stride-2 layers) one accumulator per VALID (tap, parity) pair - 9 of the 16 combinations exist in a 3x3
+  //           kernel - over one parity's planes of the space-to-depth operand and the whole plain operand.
+  // The cheaper one by MMA cycles per K step (tools/mma_bench.cu: 40 / 49 / 66 / 130 cycles at N <= 32 / 64 / 128 / 256)
+  // and by accumulator roles (each role streams its operands again) is taken.
+  struct Run { bool is_s; int plane0, nplanes; };
+  struct Acc { int tap; Run a, b; int M, N, role, d_col; bool bias; };
+  auto cyc = [](int N) { return N <= 32 ? 40 : (N <= 64 ? 49 : (N <= 128 ? 66 : 130)); };
+  auto score = [&](const std::vector<Acc>& v) {
+    double c = 0; int cols = 0;
+    for (const Acc& a : v) { c += cyc(a.N); cols += a.N; }
+    const int roles = (cols + 32 + G2_COLS - 1) / G2_COLS;
+    return c * (1.0 + 0.35 * (roles - 1));
+  };
+  auto dense_plan = [&](std::vector<Acc>& out) -> bool {
+    const bool a_is_s = nS >= nU;
+    const int nA = a_is_s ? nS : nU, nB = a_is_s ? nU : nS;
+    const int Mblk = nA >= 16 ? 128 : 64;
+    int Nb = nB * 8;
+    if (Mblk == 128 && Nb % 16) Nb += 8;                  // reads one more plane: ignored columns
+    if (Nb > 256) return false;
+    const int blkA = Mblk / 8;
+    for (int blk = 0; blk * blkA < nA; ++blk)
+      for (size_t tp = 0; tp < taps.size(); ++tp)
+        out.push_back({(int)tp, {a_is_s, blk * blkA, std::min(blkA, nA - blk * blkA)}, {!a_is_s, 0, nB}, Mblk, Nb, 0, 0, false});
+    return true;
+  };
+  auto pruned_plan = [&](std::vector<Acc>& out) -> bool {
+    if (s.kind == GEN_CONV_S1) return false;
+    const bool p_is_s = s.kind == GEN_CONV_S2;            // the space-to-depth operand: the layer input (Conv2D) or the gradient (ConvT)
+    if ((p_is_s ? s.s_layout : s.u_layout) != GEN_S2D) return false;
+    const int KCp = p_is_s ? s.s_KC : s.u_KC, nQ = p_is_s ? nU : nS;
+    int best = -1; double best_cost = 1e30;
+    for (int mode = 0; mode < 2; ++mode) {                // 0: A = parity block, B = plain operand; 1: A = plain operand, B = parity block
+      int M, N;
+      if (mode == 0) { if (KCp != 8 && KCp != 16) continue; M = KCp * 8; N = nQ * 8; }
+      else { if (nQ > 16) continue; M = nQ <= 8 ? 64 : 128; N = KCp * 8; }
+      if (M == 128 && N % 16) N += 8;
+      if (N > 256 || N < 8) continue;
+      const double cost = 9.0 * cyc(N) * (1.0 + 0.35 * ((9 * N + 32 + G2_COLS - 1) / G2_COLS - 1));
+      if (cost < best_cost) { best_cost = cost; best = mode; }
+    }
+    if (best < 0) return false;
+    for (size_t tp = 0; tp < taps.size(); ++tp)
+      for (int par = 0; par < 4; ++par) {
+        if (2 * taps[tp].t0 + (par >> 1) > 2 || 2 * taps[tp].t1 + (par & 1) > 2) continue;      // kh, kw of this (tap, parity)
+        Run pr{p_is_s, par * KCp, KCp}, qr{!p_is_s, 0, nQ};
+        int M, N;
+        if (best == 0) { M = KCp * 8; N = nQ * 8; } else { M = nQ <= 8 ? 64 : 128; N = KCp * 8; }
+        if (M == 128 && N % 16) N += 8;
+        out.push_back({(int)tp, best == 0 ? pr : qr, best == 0 ? qr : pr, M, N, 0, 0, false});
+      }
+    return true;
+  };
+  std::vector<Acc> accs, cand;
+  const bool have_dense = dense_plan(accs);
+  bool pruned = false;
+  if (pruned_plan(cand) && (!have_dense || score(cand) < score(accs))) { accs.swap(cand); pruned = true; }
+  else if (!have_dense) return no("N side wider than 256");
+  // bias accumulators: A = runs of the gradient's planes, B = two planes of ones.  With the pruned plan over a
+  // space-to-depth gradient the runs are the parity blocks the product accumulators already load.
+  std::vector<Acc> bias;
+  if (pruned && s.kind == GEN_CONVT_S2 && (s.u_KC == 8 || s.u_KC == 16)) {
+    for (int par = 0; par < 4; ++par)
+      bias.push_back({-1, {false, par * s.u_KC, s.u_KC}, {false, 0, 0}, s.u_KC * 8, s.u_KC == 16 ? 16 : 8, 0, 0, true});
+  } else {
+    const int MblkU = nU >= 16 ? 128 : 64, blkU = MblkU / 8;
+    for (int ub = 0; ub * blkU < nU; ++ub)
+      bias.push_back({-1, {false, ub * blkU, std::min(blkU, nU - ub * blkU)}, {false, 0, 0}, MblkU, MblkU == 128 ? 16 : 8, 0, 0, true});
+  }
+  // roles: product accumulators in order, balanced by columns, at most 512 columns each; every bias accumulator joins a
+  // role that already loads its planes (else the emptiest one)
+  int total_cols = 0;
+  for (const Acc& a : accs) total_cols += a.N;
+  for (const Acc& a : bias) total_cols += a.N;
+  const int n_roles = (total_cols + G2_COLS - 1) / G2_COLS;
+  if (n_roles > G2_MAXROLE) return no("too many accumulator roles");
+  {
+    const int target = (total_cols + n_roles - 1) / n_roles;
+    std::vector<int> cols(n_roles, 0);
+    int r = 0;
+    for (Acc& a : accs) {
+      if (cols[r] + a.N > G2_COLS || (cols[r] + a.N > target && cols[r] > 0 && r + 1 < n_roles)) ++r;
+      if (r >= n_roles) return no("accumulators do not pack into the planned roles");
+      a.role = r; a.d_col = cols[r]; cols[r] += a.N;
+    }
+    for (Acc& b : bias) {
+      int pick = -1;
+      for (int q = 0; q < n_roles && pick < 0; ++q) {
+        if (cols[q] + b.N > G2_COLS) continue;
+        for (const Acc& a : accs)
+          if (a.role == q && ((!a.a.is_s && a.a.plane0 == b.a.plane0 && a.a.nplanes == b.a.nplanes) ||
+                              (!a.b.is_s && a.b.plane0 == b.a.plane0 && a.b.nplanes == b.a.nplanes))) { pick = q; break; }
+      }
+      for (int q = 0; q < n_roles && pick < 0; ++q) if (cols[q] + b.N <= G2_COLS) pick = q;
+      if (pick < 0) return no("bias accumulators do not fit");
+      b.role = pick; b.d_col = cols[pick]; cols[pick] += b.N;
+    }
+    for (const Acc& b : bias) accs.push_back(b);
+  }
+
   GenWgradPlan* P = new GenWgradPlan();
   P->spec = s;
   G2PlanDev& D = P->host;
   memset(&D, 0, sizeof(D));
-  // A (M side) = the operand with more planes; B (N side) = the other one (N = 8 * planes, a multiple of 16 for M = 128)
-  const bool a_is_s = nS >= nU;
-  const int nA = a_is_s ? nS : nU, nB = a_is_s ? nU : nS;
-  int Mblk = nA >= 16 ? 128 : 64;
-  int Nb = nB * 8;
-  if (Mblk == 128 && Nb % 16) Nb += 8;                  // reads one plane of the neighbouring region: ignored columns
-  if (Nb > 256) { delete P; return no("N side wider than 256"); }
-  const int blkA = Mblk / 8;
-  const int nblocks = (nA + blkA - 1) / blkA;
-  // bias accumulators: A = U planes (blocks of 16 / 8), B = ones, N = 16 (M = 128) or 8 (M = 64)
-  const int MblkU = nU >= 16 ? 128 : 64;
-  const int ublocks = (nU + MblkU / 8 - 1) / (MblkU / 8);
-  const int bias_n = MblkU == 128 ? 16 : 8;
-
+  D.n_roles = n_roles;
+  // plane positions per role: every run an accumulator of the role touches is loaded once, runs back to back
+  struct Placed { bool is_s; int plane0, nplanes, pos; };
+  std::vector<std::vector<Placed>> placed(n_roles);
+  std::vector<int> s_cnt(n_roles, 0), u_cnt(n_roles, 0);
+  int s_extent = 1, u_extent = 1;                          // planes a region must hold (M / N padding included)
+  auto place = [&](int r, const Run& run, int span) -> int {
+    if (run.nplanes == 0) return 0;
+    for (const Placed& q : placed[r]) if (q.is_s == run.is_s && q.plane0 == run.plane0 && q.nplanes == run.nplanes) {
+      int& ext = run.is_s ? s_extent : u_extent; ext = std::max(ext, q.pos + span); return q.pos;
+    }
+    int& cnt = run.is_s ? s_cnt[r] : u_cnt[r];
+    placed[r].push_back({run.is_s, run.plane0, run.nplanes, cnt});
+    const int pos = cnt; cnt += run.nplanes;
+    int& ext = run.is_s ? s_extent : u_extent; ext = std::max(ext, std::max(cnt, pos + span));
+    return pos;
+  };
+  struct Pos { int a, b; };
+  std::vector<Pos> pos(accs.size());
+  for (size_t i = 0; i < accs.size(); ++i) {
+    pos[i].a = place(accs[i].role, accs[i].a, accs[i].M / 8);
+    pos[i].b = accs[i].bias ? 0 : place(accs[i].role, accs[i].b, accs[i].N / 8);
+  }
+  for (int r = 0; r < n_roles; ++r) if (s_cnt[r] > G2_MAXPL || u_cnt[r] > G2_MAXPL) { delete P; return no("too many planes per role"); }
   // tile rows: largest of 8, 4, 2 whose two stages fit
   int TRr = 8;
   for (;; TRr /= 2) {
     const size_t CHs = (size_t)(TRr + halo_r) * GP * 16, CHu = (size_t)TRr * GP * 16;
-    const size_t s_reg = (size_t)std::max(nS, a_is_s ? nblocks * blkA : nS) * CHs + 128;
-    const size_t u_reg = (size_t)std::max(nU, std::max(a_is_s ? nU : nblocks * blkA, ublocks * (MblkU / 8))) * CHu + (Nb > nB * 8 ? CHu : 0);
+    const size_t s_reg = (size_t)s_extent * CHs + 128, u_reg = (size_t)u_extent * CHu;
     const size_t stage = (s_reg + u_reg + 1023) / 1024 * 1024;
     if (G2_PLAN_BYTES + G1_STAGES * stage + 2 * CHu <= SMEM_BUDGET || TRr == 1) {
       D.CHs = (uint32_t)CHs; D.CHu = (uint32_t)CHu; D.s_region = (uint32_t)s_reg; D.u_region = (uint32_t)u_reg;
@@ -957,90 +1078,61 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
   if (TRr < 2) { delete P; return no("operand planes do not fit two shared-memory stages"); }
   D.TRr = TRr; D.R_s = TRr + halo_r; D.row0 = row0; D.col0 = col0; D.TW = TW; D.s_PL = nS; D.u_PL = nU;
   D.ones_off = (uint32_t)(G2_PLAN_BYTES + (size_t)G1_STAGES * D.stage_bytes);
-  P->smem = (size_t)D.ones_off + 2 * D.CHu;    // regions are padded to whole M blocks: no operand runs past the allocation
+  P->smem = (size_t)D.ones_off + 2 * D.CHu;
   if (P->smem > 227 * 1024) { delete P; return no("shared-memory plan too large"); }
 
-  // accumulators: (tap, A block) -> N columns; then the bias accumulators; packed into roles of <= 512 columns
-  struct Acc { int tap, blk, role, d_col; };
-  std::vector<Acc> accs;
-  int n_roles = 1, cols = 0, n_mma = 0;
-  auto new_role = [&]() { ++n_roles; cols = 0; };
-  const int bias_cols = ublocks * bias_n;
-  for (int blk = 0; blk < nblocks; ++blk)
-    for (size_t tp = 0; tp < taps.size(); ++tp) {
-      if (cols + Nb > G2_COLS - (n_roles == 1 ? bias_cols : 0)) new_role();
-      accs.push_back({(int)tp, blk, n_roles - 1, cols});
-      cols += Nb;
-    }
-  if (n_roles > G2_MAXROLE) { delete P; return no("too many accumulator roles"); }
-  D.n_roles = n_roles;
-  std::vector<int> role_cols(n_roles, 0);
-  for (const Acc& a : accs) role_cols[a.role] = std::max(role_cols[a.role], a.d_col + Nb);
-  const int bias_col0 = role_cols[0];
-  role_cols[0] += bias_cols;
-  if (role_cols[0] > G2_COLS) { delete P; return no("bias accumulators do not fit"); }
-
+  int n_mma = 0;
   for (int r = 0; r < n_roles; ++r) {
     G2Role& R = D.roles[r];
-    std::vector<int> needS, needU;
-    auto need = [](std::vector<int>& v, int pl, int limit) { if (pl < limit && std::find(v.begin(), v.end(), pl) == v.end()) v.push_back(pl); };
-    for (const Acc& a : accs) if (a.role == r) {
-      for (int k = 0; k < blkA; ++k) need(a_is_s ? needS : needU, a.blk * blkA + k, a_is_s ? nS : nU);
-      for (int k = 0; k < nB; ++k) need(a_is_s ? needU : needS, k, a_is_s ? nU : nS);
-    }
-    if (r == 0) for (int k = 0; k < nU; ++k) need(needU, k, nU);
-    std::sort(needS.begin(), needS.end()); std::sort(needU.begin(), needU.end());
-    // planes keep their own index as position inside the region (simple addressing; unused positions stay unloaded)
-    R.nS = (int)needS.size(); R.nU = (int)needU.size();
-    if (R.nS > G2_MAXPL || R.nU > G2_MAXPL) { delete P; return no("too many planes per role"); }
-    for (int i = 0; i < R.nS; ++i) R.s_plane[i] = needS[i];
-    for (int i = 0; i < R.nU; ++i) R.u_plane[i] = needU[i];
-    R.ncols = role_cols[r];
-  }
-  // the producer places plane i of a role at position i: make positions equal plane indices by loading contiguous ranges
-  // (roles split by A block: the A planes of a role are a contiguous range starting at a block boundary)
-  for (int r = 0; r < n_roles; ++r) {
-    G2Role& R = D.roles[r];
-    R.mma0 = n_mma;
-    const int s_first = R.nS ? R.s_plane[0] : 0, u_first = R.nU ? R.u_plane[0] : 0;
-    for (int i = 0; i < R.nS; ++i) if (R.s_plane[i] != s_first + i) { delete P; return no("non-contiguous S planes in a role"); }
-    for (int i = 0; i < R.nU; ++i) if (R.u_plane[i] != u_first + i) { delete P; return no("non-contiguous U planes in a role"); }
-    for (const Acc& a : accs) if (a.role == r) {
+    R.mma0 = n_mma; R.nS = 0; R.nU = 0; R.ncols = 0;
+    for (const Placed& q : placed[r])
+      for (int k = 0; k < q.nplanes; ++k) {
+        if (q.is_s) R.s_plane[q.pos + k] = q.plane0 + k; else R.u_plane[q.pos + k] = q.plane0 + k;
+      }
+    R.nS = s_cnt[r]; R.nU = u_cnt[r];
+    for (size_t i = 0; i < accs.size(); ++i) {
+      const Acc& a = accs[i];
+      if (a.role != r) continue;
       if (n_mma >= G2_MAXMMA) { delete P; return no("MMA list too long"); }
       G2Mma& M = D.mma[n_mma++];
-      const uint32_t shift = (uint32_t)taps[a.tap].shift * 16;
-      const uint32_t s_base = (uint32_t)0, u_base = D.s_region;
-      uint32_t a_off, b_off, a_sbo, b_sbo;
-      if (a_is_s) {
-        a_off = s_base + (uint32_t)(a.blk * blkA - s_first) * D.CHs + shift; a_sbo = D.CHs;
-        b_off = u_base + (uint32_t)(0 - u_first) * D.CHu; b_sbo = D.CHu;
-      } else {
-        a_off = u_base + (uint32_t)(a.blk * blkA - u_first) * D.CHu; a_sbo = D.CHu;
-        b_off = s_base + (uint32_t)(0 - s_first) * D.CHs + shift; b_sbo = D.CHs;
-      }
+      auto off = [&](const Run& run, int p, bool shifted) -> uint32_t {
+        const uint32_t o = run.is_s ? (uint32_t)p * D.CHs : D.s_region + (uint32_t)p * D.CHu;
+        return o + ((shifted && run.is_s && a.tap >= 0) ? (uint32_t)taps[a.tap].shift * 16 : 0u);
+      };
       // MN-major operands: leading byte offset = 128 (8 pixels), stride byte offset = plane stride
+      const uint32_t a_off = off(a.a, pos[i].a, true), a_sbo = a.a.is_s ? D.CHs : D.CHu;
       M.a_lo = (a_off >> 4) | ((128u >> 4) << 16); M.a_hi = (a_sbo >> 4) | (1u << 14);
-      M.b_lo = (b_off >> 4) | ((128u >> 4) << 16); M.b_hi = (b_sbo >> 4) | (1u << 14);
-      M.idesc = make_idesc_bf16_f32(Mblk, Nb, 1, 1);
-      M.d_col = (uint32_t)a.d_col; M.b_ones = 0;
-    }
-    if (r == 0) {
-      for (int ub = 0; ub < ublocks; ++ub) {
-        if (n_mma >= G2_MAXMMA) { delete P; return no("MMA list too long"); }
-        G2Mma& M = D.mma[n_mma++];
-        const uint32_t a_off = D.s_region + (uint32_t)(ub * (MblkU / 8) - u_first) * D.CHu;
-        M.a_lo = (a_off >> 4) | ((128u >> 4) << 16); M.a_hi = (D.CHu >> 4) | (1u << 14);
-        M.b_lo = 0u | ((128u >> 4) << 16); M.b_hi = (D.CHu >> 4) | (1u << 14);
-        M.idesc = make_idesc_bf16_f32(MblkU, bias_n, 1, 1);
-        M.b_ones = 1;
-        M.d_col = (uint32_t)(bias_col0 + ub * bias_n);
+      if (a.bias) {
+        M.b_lo = 0u | ((128u >> 4) << 16); M.b_hi = (D.CHu >> 4) | (1u << 14); M.b_ones = 1;
+      } else {
+        const uint32_t b_off = off(a.b, pos[i].b, true), b_sbo = a.b.is_s ? D.CHs : D.CHu;
+        M.b_lo = (b_off >> 4) | ((128u >> 4) << 16); M.b_hi = (b_sbo >> 4) | (1u << 14); M.b_ones = 0;
       }
+      M.idesc = make_idesc_bf16_f32(a.M, a.N, 1, 1);
+      M.d_col = (uint32_t)a.d_col;
+      R.ncols = std::max(R.ncols, a.d_col + a.N);
     }
     R.mma_n = n_mma - R.mma0;
   }
 
-  // scatter table: dW element -> (role, column, TMEM lane)
+  // scatter table: dW element -> (role, column, TMEM lane) of the accumulator whose element ranges contain it
   auto lane_of = [](int M, int row) { return M == 128 ? row : (row / 16) * 32 + row % 16; };
+  auto find = [&](int tap_i, int es, int eu, bool bias) -> int32_t {
+    for (const Acc& a : accs) {
+      if (a.bias != bias || (!bias && a.tap != tap_i)) continue;
+      const int ea = a.a.is_s ? es : eu;
+      if (ea < a.a.plane0 * 8 || ea >= a.a.plane0 * 8 + a.M) continue;
+      int col = 0;
+      if (!bias) {
+        const int eb = a.b.is_s ? es : eu;
+        if (eb < a.b.plane0 * 8 || eb >= a.b.plane0 * 8 + a.b.nplanes * 8) continue;
+        col = eb - a.b.plane0 * 8;
+      }
+      if (ea - a.a.plane0 * 8 >= a.a.nplanes * 8) continue;       // rows of the M padding belong to other planes
+      return a.role * (G2_COLS * 128) + (a.d_col + col) * 128 + lane_of(a.M, ea - a.a.plane0 * 8);
+    }
+    return -1;
+  };
   const int Cs = s.Cs, Cu = s.Cu;
   P->EW = 9 * Cs * Cu;
   P->src.assign((size_t)(P->EW + Cu) * 4, -1);
@@ -1059,22 +1151,18 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
     } else {
       tap_i = kh * 3 + kw; es = cs; eu = cu;
     }
-    const int ea = a_is_s ? es : eu, eb = a_is_s ? eu : es;
-    const int blk = ea / Mblk, row = ea % Mblk;
-    int found = -1;
-    for (const Acc& a : accs) if (a.tap == tap_i && a.blk == blk) { found = a.role * (G2_COLS * 128) + (a.d_col + eb) * 128 + lane_of(Mblk, row); break; }
     const int tap9 = kh * 3 + kw;
     const int e = s.w_mode == 0 ? (tap9 * Cs + cs) * Cu + cu : (tap9 * Cu + cu) * Cs + cs;
-    P->src[(size_t)e * 4] = found;
+    P->src[(size_t)e * 4] = find(tap_i, es, eu, false);
   }
   for (int cu = 0; cu < Cu; ++cu) {
     const int npar = s.u_layout == GEN_S2D ? 4 : 1;
     for (int par = 0; par < npar; ++par) {
       const int eu = s.u_layout == GEN_S2D ? par * s.u_KC * 8 + cu : cu;
-      const int ub = eu / MblkU, row = eu % MblkU;
-      P->src[(size_t)(P->EW + cu) * 4 + par] = 0 * (G2_COLS * 128) + (bias_col0 + ub * bias_n) * 128 + lane_of(MblkU, row);
+      P->src[(size_t)(P->EW + cu) * 4 + par] = find(-1, -1, eu, true);
     }
   }
+  for (size_t e = 0; e < (size_t)P->EW; ++e) if (P->src[e * 4] < 0) { delete P; return no("internal: a weight-gradient element has no accumulator"); }
   if (cudaMalloc(reinterpret_cast<void**>(&P->dev), sizeof(G2PlanDev)) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&P->src_dev), P->src.size() * sizeof(int32_t)) != cudaSuccess) {
     gen_wgrad_plan_free(P);
