@@ -105,6 +105,9 @@ int kcvae_get_adam_state(kcvae_handle h, float* h_m, float* h_v, int64_t n, int6
  * (train.py:46-47 BetaAnnealingCallback) */
 int kcvae_set_learning_rate(kcvae_handle h, float lr);
 int kcvae_set_beta(kcvae_handle h, float beta);
+/* opt-in README behaviour (src/abstract_cvae.py:117-118 applied to train_step, SURVEY Note A): when on, kcvae_train_step adds
+ * on-device Philox N(0, beta^2) noise to the encoder input unless the caller passes its own d_img_noise */
+int kcvae_set_train_image_noise(kcvae_handle h, int on);
 int kcvae_set_loss_weights(kcvae_handle h, float kurtosis_target, float w_mse, float w_kurtosis,
                            float w_skew, float w_z_l1_reg);
 int kcvae_seed(kcvae_handle h, uint64_t seed); /* Philox key for on-device eps / image noise */

@@ -53,6 +53,7 @@ _SIGS = {
     "kcvae_get_adam_state": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "kcvae_set_learning_rate": (C.c_int, [_P, C.c_float]),
     "kcvae_set_beta": (C.c_int, [_P, C.c_float]),
+    "kcvae_set_train_image_noise": (C.c_int, [_P, C.c_int]),
     "kcvae_set_loss_weights": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
     "kcvae_seed": (C.c_int, [_P, C.c_uint64]),
     "kcvae_comm_unique_id": (C.c_int, [_P]),

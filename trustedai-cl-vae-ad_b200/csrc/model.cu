@@ -134,6 +134,7 @@ struct kcvae_model {
   bool relu_bits_valid = false;
   bool fuse_train_tail = false;  // training forward: fused tail that also stores the activation for the backward
   bool tc_failed = false;        // a tensor-core launcher could not run (tensor map encode): the step is invalid
+  bool train_image_noise = false;   // train_step adds N(0, beta^2) to the encoder input (kcvae_set_train_image_noise)
   bool use_tc_out = false, use_tc_dgrad = false, use_tc_convT = false, use_tc_convT_bwd = false;
   void* g_s2d = nullptr;         // bf16 space-to-depth d loss / d a_last, chunk-planar [B][4][4][H/2][W/2][8]
   void* wimg_convT_dgrad = nullptr;
@@ -1339,8 +1340,12 @@ int step_impl(kcvae_model* h, const float* d_x, int B, const float* d_eps, const
   KC_CUDA(h, cudaSetDevice(h->device));
   KC_TRY(ensure_bwd(h, B));
   const float* x = d_x;
-  if (d_img_noise) {  // opt-in (unreachable in the reference's train_step, SURVEY Note A)
-    add_noise(d_x, d_img_noise, (int64_t)B * h->P, 0.f, 0, 0, h->x_noisy, st);
+  if (d_img_noise || h->train_image_noise) {  // opt-in (unreachable in the reference's train_step, SURVEY Note A)
+    // caller-supplied noise (parity runs) or on-device Philox N(0, beta^2), the draw src/abstract_cvae.py:117-118 makes
+    const int64_t n = (int64_t)B * h->P;
+    g_tag = "noise";
+    add_noise(d_x, d_img_noise, n, h->beta, h->seed, h->rng_counter, h->x_noisy, st);
+    if (!d_img_noise) h->rng_counter += (uint64_t)(n + 1) / 2;
     x = h->x_noisy;
   }
 #ifndef KCVAE_EMU
@@ -1626,6 +1631,7 @@ int kcvae_get_adam_state(kcvae_handle h, float* h_m, float* h_v, int64_t n, int6
 
 int kcvae_set_learning_rate(kcvae_handle h, float lr) { if (!h) return KCVAE_ERR_INVALID; h->lr = lr; return KCVAE_OK; }
 int kcvae_set_beta(kcvae_handle h, float beta) { if (!h) return KCVAE_ERR_INVALID; h->beta = beta; return KCVAE_OK; }
+int kcvae_set_train_image_noise(kcvae_handle h, int on) { if (!h) return KCVAE_ERR_INVALID; h->train_image_noise = on != 0; return KCVAE_OK; }
 int kcvae_set_loss_weights(kcvae_handle h, float kurtosis_target, float w_mse, float w_kurtosis, float w_skew,
                            float w_z_l1_reg) {
   if (!h) return KCVAE_ERR_INVALID;

@@ -884,22 +884,27 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
-// out[e] = sum over the CTAs of the entry's role of partial[cta][src] for up to 4 sources per entry (deterministic order)
+// out[e] = sum over the CTAs of the entry's role of partial[cta][src] for up to 4 sources per entry.  One warp per entry:
+// lane l folds CTAs l, l + 32, ... in order, then a fixed shuffle tree (deterministic for a given grid).
 __global__ void __launch_bounds__(256) gen_wgrad_reduce_kernel(const float* __restrict__ partial, const int32_t* __restrict__ src, int E,
                                                                int n_roles, int grid, int tiles, float* dW, float* db, int EW) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (e >= E) return;
   float acc = 0.f;
   for (int k = 0; k < 4; ++k) {
-    const int32_t sidx = src[(size_t)e * 4 + k];
+    const int32_t sidx = __ldg(src + (size_t)e * 4 + k);
     if (sidx < 0) continue;
     const int role = sidx / (G2_COLS * 128), off = sidx % (G2_COLS * 128);
     const int ctas = (grid - role + n_roles - 1) / n_roles;
     const int live = tiles < ctas ? tiles : ctas;              // CTAs beyond the tile count never wrote their block
-    for (int c = 0; c < live; ++c) acc += __ldg(partial + (size_t)(c * n_roles + role) * G2_COLS * 128 + off);
+    for (int c = lane; c < live; c += 32) acc += __ldg(partial + (size_t)(c * n_roles + role) * G2_COLS * 128 + off);
   }
-  if (e < EW) dW[e] = acc;
-  else if (db) db[e - EW] = acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (e < EW) dW[e] = acc;
+    else if (db) db[e - EW] = acc;
+  }
 }
 
 }  // namespace
@@ -1206,7 +1211,7 @@ int gen_wgrad_run(const GenWgradPlan* P, const GenPlanes& S, const GenPlanes& U,
   cudaFuncSetAttribute(tc_gwgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem);
   tc_gwgrad_kernel<<<grid, G2_THREADS, P->smem, st>>>(ms, mu, p);
   const int E = P->EW + (db ? s.Cu : 0);
-  gen_wgrad_reduce_kernel<<<cdiv(E, 256), 256, 0, st>>>(partial, P->src_dev, E, D.n_roles, grid, p.num_tiles, dW, db, P->EW);
+  gen_wgrad_reduce_kernel<<<cdiv(E, 8), 256, 0, st>>>(partial, P->src_dev, E, D.n_roles, grid, p.num_tiles, dW, db, P->EW);
   return 0;
 }
 

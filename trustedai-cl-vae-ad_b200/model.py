@@ -368,6 +368,7 @@ class AbstractCVAE:
         if self.optimizer is not None:
             self._lib.set_learning_rate(self._h, float(_as_float(self.optimizer.learning_rate)))
         self._lib.set_beta(self._h, float(self.beta))
+        self._lib.set_train_image_noise(self._h, int(bool(self.train_image_noise)))
         self._lib.set_loss_weights(self._h, self.kurtosis_target, self.w_mse, self.w_kurtosis, self.w_skew, self.w_z_l1_reg)
 
     def __del__(self):
@@ -554,9 +555,7 @@ class AbstractCVAE:
         nz = None
         if noise is not None:
             nz = self._to_dev(noise, self._img_shape())
-        elif self.train_image_noise:
-            nz = torch.randn_like(xt) * float(self.beta)
-        self._push_hparams()
+        self._push_hparams()          # carries train_image_noise: the library draws N(0, beta^2) with its own Philox stream
         if update:
             rc = self._lib.train_step(self._h, _ptr(xt), xt.shape[0], _ptr(e), _ptr(nz), _ptr(self._metrics_buf), _ptr(xh),
                                       self.metric_tier, self._stream())
