@@ -386,6 +386,14 @@ def roofline_from_profile(rep, tab, step_bytes, ms_per_step, K):
     return roof, top_key
 
 
+def log(ctx, msg, all_ranks=False):
+    """progress on stderr (stdout carries the one JSON line)"""
+    if all_ranks and os.environ.get("KCVAE_BENCH_TRACE"):
+        sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')} rank {ctx.rank}] {msg}\n"); sys.stderr.flush()
+    elif ctx.rank == 0 and not all_ranks:
+        sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n"); sys.stderr.flush()
+
+
 def run_config(ctx, name, K, Wm, full=True):
     """One BASELINE config on the GPU arm.  full=False: the short form used for the "configs" block of the default line
     (value, e2e, whole-step roofline; no per-kernel profile, no CPU leg, no sustained leg)."""
@@ -394,6 +402,7 @@ def run_config(ctx, name, K, Wm, full=True):
     spec = CONFIGS[name]
     cfg = model_config(name)
     B = local_batch(name, world, args)
+    log(ctx, f"{name}: {B} frames per GPU x {world} GPU(s), {K} steps")
     model = ctx.pkg.load_model_from_config(cfg, device=local, precision=args.precision, metrics=args.metrics_tier)
     if spec["model"] == "readme":
         model.set_weights(O.glorot_init(cfg, 1234))          # the scaled model keeps its on-device Glorot draw (78 M parameters)
@@ -426,6 +435,7 @@ def run_config(ctx, name, K, Wm, full=True):
             model.train_step_host(host_pool[s % nhost], None, metrics_host)
         d2h = 16 * 4
 
+    log(ctx, f"{name}: model and buffers ready, warming up")
     for s in range(Wm):
         step_fn(s)
     clocks = ClockSampler(local)
@@ -441,6 +451,7 @@ def run_config(ctx, name, K, Wm, full=True):
     value = world * B * K / (ms_total * 1e-3)
     assert args.precision == "fp32" or model.tc_status() >= 0      # raises if a bounded tcgen05 barrier wait expired
 
+    log(ctx, f"{name}: device-timed {ms_total / K:.3f} ms/step; end-to-end leg")
     for s in range(3):
         e2e_fn(s)
     ms_e2e = ctx.timed(e2e_fn, K)
@@ -481,8 +492,10 @@ def run_config(ctx, name, K, Wm, full=True):
     if not full:
         ach = step_bytes / (ms_total / K * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "unit": "GB/s", "peak": peak, "whole_step": {"algorithmic_bytes": step_bytes, "achieved": ach, "frac": ach / peak}}
+        ctx.sync_all()
         del pool, host_pool, model
         torch.cuda.empty_cache()
+        ctx.sync_all()
         return line
 
     # per-launch timing of the same K steps (events on the launching stream)
@@ -518,8 +531,10 @@ def run_config(ctx, name, K, Wm, full=True):
                                 "sample": f"{csteps} steps of {sb} frames of this config, torch-CPU restatement of the TF path (TF unavailable)"}
     else:
         line["cpu_baseline"] = None
+    ctx.sync_all()             # replicas drop their communicators together
     del pool, host_pool, model
     torch.cuda.empty_cache()
+    ctx.sync_all()
     return line
 
 
@@ -540,8 +555,11 @@ def dp_selfcheck(ctx):
         m.set_weights(ws)
         m.distribute()
         sl = slice(rank * Bl, (rank + 1) * Bl)
+        log(ctx, f"self-check {kind}: communicator up")
         d, grads = m.loss_and_grads(x[sl], eps=eps[sl])
         tc = int(m.tc_status())
+        log(ctx, f"self-check {kind}: sharded step done")
+        log(ctx, f"selfcheck {kind}: step done", True)
         if rank == 0:
             ref = ctx.pkg.load_model_from_config(cfg, device=local, precision=ctx.args.precision)
             ref.set_weights(ws)
@@ -551,9 +569,17 @@ def dp_selfcheck(ctx):
             out[kind] = {"max_rel_metric_err": merr, "max_rel_grad_err": gerr, "frames": Bl * world, "tc_status": tc,
                          "ok": bool(merr < 2e-3 and gerr < 2e-2)}
             del ref
+        # communicators are created and destroyed by all ranks together: nobody enters the next ncclCommInitRank while a
+        # peer still holds (or is tearing down) the previous communicator
+        log(ctx, f"selfcheck {kind}: before barrier", True)
+        ctx.sync_all()
+        log(ctx, f"selfcheck {kind}: dropping the communicator", True)
         del m
+        log(ctx, f"selfcheck {kind}: dropped", True)
+        ctx.sync_all()
     torch.cuda.empty_cache()
     ctx.sync_all()
+    log(ctx, "selfcheck: done", True)
     return out if rank == 0 else None
 
 
@@ -561,10 +587,14 @@ def run_ours(args):
     ctx = Ctx(args)
     K, Wm = args.steps, max(args.warmup, 3)
     main_name = args.config or "cfg2"
+    t_start = time.time()
     line = run_config(ctx, main_name, K, Wm, full=True)
     if ctx.world > 1:
+        log(ctx, "data-parallel self-check")
         line["dp_selfcheck"] = dp_selfcheck(ctx)
-    if not args.config and not args.no_others:
+    # (single-GPU runs only: under torchrun the line is the main config + the data-parallel self-check, so that the scaling
+    # runs stay short; every other config has its own `--config cfgN [--gpus N]` line)
+    if not args.config and not args.no_others and ctx.world == 1:
         # every other BASELINE config, short form (their full lines: --config cfgN; committed under profiles/)
         others = {}
         for name in sorted(CONFIGS):
@@ -573,9 +603,16 @@ def run_ours(args):
             if name == "cfg1" and ctx.world > 1:
                 continue                      # 16 frames are not sharded
             big = CONFIGS[name]["model"] == "scaled"
+            # the short runs must never endanger the main line: every rank takes the same decision from rank 0's clock
+            over = ctx.torch.tensor([1.0 if time.time() - t_start > 240 else 0.0], device=ctx.dev)
+            if ctx.world > 1:
+                ctx.dist.broadcast(over, src=0)
+            if float(over.item()) > 0:
+                others[name] = {"skipped": "time budget of the default run spent"}
+                continue
             others[name] = run_config(ctx, name, max(3, min(K, 4 if big else 10)), 3, full=False)
         line["configs"] = others
-        if "cfg4" in others:                 # the scoring half of BASELINE.json's metric, also at top level
+        if "cfg4" in others and "value" in others["cfg4"]:   # the scoring half of BASELINE.json's metric, also at top level
             line["score"] = {k: others["cfg4"][k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "config")}
     if ctx.rank == 0:
         _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
