@@ -493,6 +493,7 @@ def run_config(ctx, name, K, Wm, full=True):
         ach = step_bytes / (ms_total / K * 1e-3) / 1e9
         line["roofline"] = {"bound": "hbm", "unit": "GB/s", "peak": peak, "whole_step": {"algorithmic_bytes": step_bytes, "achieved": ach, "frac": ach / peak}}
         ctx.sync_all()
+        model.close()
         del pool, host_pool, model
         torch.cuda.empty_cache()
         ctx.sync_all()
@@ -531,7 +532,8 @@ def run_config(ctx, name, K, Wm, full=True):
                                 "sample": f"{csteps} steps of {sb} frames of this config, torch-CPU restatement of the TF path (TF unavailable)"}
     else:
         line["cpu_baseline"] = None
-    ctx.sync_all()             # replicas drop their communicators together
+    ctx.sync_all()             # replicas drop their communicators together (close(): not left to the garbage collector)
+    model.close()
     del pool, host_pool, model
     torch.cuda.empty_cache()
     ctx.sync_all()
@@ -568,12 +570,14 @@ def dp_selfcheck(ctx):
             gerr = max(float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30)) for a, b in zip(grads, gr))
             out[kind] = {"max_rel_metric_err": merr, "max_rel_grad_err": gerr, "frames": Bl * world, "tc_status": tc,
                          "ok": bool(merr < 2e-3 and gerr < 2e-2)}
+            ref.close()
             del ref
         # communicators are created and destroyed by all ranks together: nobody enters the next ncclCommInitRank while a
         # peer still holds (or is tearing down) the previous communicator
         log(ctx, f"selfcheck {kind}: before barrier", True)
         ctx.sync_all()
         log(ctx, f"selfcheck {kind}: dropping the communicator", True)
+        m.close()
         del m
         log(ctx, f"selfcheck {kind}: dropped", True)
         ctx.sync_all()

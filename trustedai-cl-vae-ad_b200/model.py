@@ -371,11 +371,18 @@ class AbstractCVAE:
         self._lib.set_train_image_noise(self._h, int(bool(self.train_image_noise)))
         self._lib.set_loss_weights(self._h, self.kurtosis_target, self.w_mse, self.w_kurtosis, self.w_skew, self.w_z_l1_reg)
 
+    def close(self):
+        """Release the library handle (device memory, streams, the NCCL communicator) NOW.  The object graph has reference
+        cycles (variables point back at the model), so ``del model`` alone leaves destruction to the cyclic garbage
+        collector at an arbitrary later time - under data parallel that would tear a communicator down while the peers
+        are inside another collective.  Call it on every rank at the same point (bench.py does, between barriers)."""
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.destroy(self._h)
+            self._h = C.c_void_p()
+
     def __del__(self):
         try:
-            if getattr(self, "_h", None) and self._h.value:
-                self._lib.destroy(self._h)
-                self._h = C.c_void_p()
+            self.close()
         except Exception:
             pass
 
