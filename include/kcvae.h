@@ -237,6 +237,11 @@ int kcvae_gen_conv_test(int kind, int w_mode, int flip, int split, int pre, int 
                         int B, int Hi, int Wi, int Ck, int Cn, void* stream);
 int kcvae_gen_wgrad_test(int kind, int w_mode, int flip, int s_x3, const float* d_s, const float* d_u, float* d_dW, float* d_db,
                          int B, int Hs, int Ws, int Cs, int Cu, void* stream);
+/* Dense-layer products of the same engine (src/abstract_cvae.py:41-45, 75-77) on fp32 device matrices, A = [R][N] row-major:
+ * mode 0 forward out[c][n] = act(bias[n] + sum_r A[r][n] Bm[c][r]); mode 1 weight + bias gradient out[c][n] = sum_r A[r][n] Bm[r][c],
+ * out[C][n] = sum_r A[r][n]; mode 2 data gradient out[u][s] = sum_n A[u][n] Bm[s][n].  Used by the parity tests only. */
+int kcvae_gen_dense_test(int mode, int split, int relu, const float* d_a, const float* d_b, const float* d_bias, float* d_out,
+                         int R, int N, int C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -223,3 +223,47 @@ def test_output_layer_weight_gradient(Ci, Co, H, W):
     dW, db = gen_wgrad(CONV_S1, 1, 1, x, g, (3, 3, Co, Ci), Co)
     assert _err(dW, gw.numpy()) < _tol(0), _err(dW, gw.numpy())
     assert _err(db, gb.numpy()) < _tol(0)
+
+
+# ------------------------------------------------------------------------------------------ Dense layers on the engine
+def gen_dense(mode, split, relu, a, b, bias, out_shape):
+    lib = _lib()
+    ad, bd = _dev(a), _dev(b)
+    biasd = _dev(bias) if bias is not None else None
+    out = torch.full(out_shape, float("nan"), dtype=torch.float32, device="cuda")
+    rc = lib.gen_dense_test(mode, split, relu, _ptr(ad), _ptr(bd), _ptr(biasd), _ptr(out), a.shape[0], a.shape[1], b.shape[0] if mode != 1 else b.shape[1], None)
+    lib.check(rc, None)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("K,N,B,split", [(32, 56 * 75 * 32, 16, 1), (32, 4096, 256, 0), (256, 8192, 37, 1), (8, 640, 3, 0)])
+def test_dense_forward(K, N, B, split):
+    """Decoder Dense (src/abstract_cvae.py:75-77): relu(z W + b) from the weight matrix's long dimension."""
+    rng = np.random.default_rng(K + N + B)
+    W = _rand(rng, K, N, scale=(1.0 / K) ** 0.5)
+    z = _rand(rng, B, K)
+    bias = _rand(rng, N, scale=0.1)
+    want = np.maximum(z.astype(np.float64) @ W.astype(np.float64) + bias, 0.0)
+    got = gen_dense(0, split, 1, W, z, bias, (B, N))
+    assert _err(got, want) < _tol(split), _err(got, want)
+
+
+@pytest.mark.parametrize("K,N,B", [(32, 56 * 75 * 32, 16), (32, 4096, 256), (192, 8192, 40), (8, 640, 3)])   # K + 1 <= 256 columns per product
+def test_dense_weight_and_bias_gradient(K, N, B):
+    rng = np.random.default_rng(K * 3 + N + B)
+    G = _rand(rng, B, N)
+    z = _rand(rng, B, K)
+    want = np.concatenate([z.astype(np.float64).T @ G.astype(np.float64), G.astype(np.float64).sum(0, keepdims=True)], 0)   # [K + 1][N]
+    got = gen_dense(1, 0, 0, G, z, None, (K + 1, N))
+    assert _err(got, want) < _tol(0), _err(got, want)
+
+
+@pytest.mark.parametrize("K,N,B", [(32, 56 * 75 * 32, 16), (32, 4096, 256), (256, 8192, 40), (8, 640, 3)])
+def test_dense_data_gradient(K, N, B):
+    rng = np.random.default_rng(K * 5 + N + B)
+    G = _rand(rng, B, N)
+    W = _rand(rng, K, N, scale=(1.0 / K) ** 0.5)
+    want = G.astype(np.float64) @ W.astype(np.float64).T          # [B][K]
+    got = gen_dense(2, 0, 0, G, W, None, (B, K))
+    assert _err(got, want) < _tol(0), _err(got, want)

@@ -90,6 +90,7 @@ _SIGS = {
     "kcvae_profile_report": (C.c_int64, [C.c_char_p, C.c_int64]),
     "kcvae_gen_conv_test": (C.c_int, [C.c_int] * 8 + [_P] * 5 + [C.c_int] * 5 + [_P]),
     "kcvae_gen_wgrad_test": (C.c_int, [C.c_int] * 4 + [_P] * 4 + [C.c_int] * 5 + [_P]),
+    "kcvae_gen_dense_test": (C.c_int, [C.c_int] * 3 + [_P] * 4 + [C.c_int] * 3 + [_P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -174,6 +174,21 @@ struct kcvae_model {
   void* x_pl = nullptr;
   std::vector<void*> act_e_pl, g_e_pl, act_d_pl, g_d_pl;
   float *gen_partial = nullptr, *gen_partial2 = nullptr;
+  // decoder Dense layer on the engine (GEN_DENSE products): W^T and G^T as plane tensors, plans per batch size
+  bool gen_dense = false;
+  void *wT_pl = nullptr, *gT_pl = nullptr;
+  uint64_t wT_version = 0;
+  struct DensePlans {
+    int B = 0, ones_cap = 0;
+    GenConvPlan *fwd = nullptr, *fwd_split = nullptr;
+    std::vector<GenConvPlan*> wgrad;           // column blocks of the latent dimension (the last one carries the ones column)
+    std::vector<int> wgrad_col0;
+    std::vector<size_t> off_wgrad;
+    GenWgradPlan* dgrad = nullptr;
+    unsigned char* img = nullptr;
+    size_t off_fwd = 0, off_fwd_split = 0;
+  };
+  std::vector<DensePlans> dense_plans;
 #endif
   // data parallel
   int rank = 0, world = 1;
@@ -327,6 +342,8 @@ size_t gen_add_image(kcvae_model* h, const GenConvPlan* p, int vi) {
 }
 
 // Chooses which layers run on the general engine and builds their plans (shape-based kernel selection, once per handle).
+#define KC_TRY_SETUP(expr) do { int rc_ = (expr); if (rc_ != KCVAE_OK) return rc_; } while (0)
+int gen_alloc(kcvae_model* h, void** p, size_t units);
 int gen_setup(kcvae_model* h) {
   const int L = h->L;
   const char* off = std::getenv("KCVAE_GEN");               // 0 = specialised / CUDA-core kernels only (development switch)
@@ -404,6 +421,13 @@ int gen_setup(kcvae_model* h) {
     // README-style decoder: the specialised tail kernels stay; the backward of the first Conv2DTranspose joins the engine
     if (convT_plans(0, false)) { h->gen_d = D; h->gen_dec0 = true; } else gen_free_plans(D);
   }
+  {
+    const char* gd = std::getenv("KCVAE_GEN_DENSE");        // 0 = decoder Dense on the fp32 CUDA-core kernels
+    const int vi = h->vi_dec_dense();
+    h->gen_dense = (h->gen_dec || h->gen_dec0) && dense_planar && h->dec_units % 32 == 0 && !(gd && gd[0] == '0') &&
+                   h->vars[vi + 1].off == h->vars[vi].off + (int64_t)h->latent * h->dec_units;     // dW and db contiguous: one product writes both
+    if (h->gen_dense) KC_TRY_SETUP(gen_alloc(h, &h->wT_pl, (size_t)2 * ((h->latent + 7) / 8) * h->dec_units));
+  }
   if (!h->gen_enc && !h->gen_dec && !h->gen_dec0) return KCVAE_OK;
   // ---- weight images: one gather table for all plans
   for (int l = 0; l < L && h->gen_enc; ++l) {
@@ -439,6 +463,83 @@ int gen_alloc(kcvae_model* h, void** p, size_t units) {
   if (*p) { cudaFree(*p); *p = nullptr; }
   KC_CUDA(h, cudaMalloc(p, (units ? units : 1) * 16));
   return KCVAE_OK;
+}
+
+// ---- decoder Dense (src/abstract_cvae.py:75-77) on the engine ---------------------------------------------------------
+void dense_plans_free(kcvae_model::DensePlans& d) {
+  gen_conv_plan_free(d.fwd); gen_conv_plan_free(d.fwd_split);
+  for (GenConvPlan* q : d.wgrad) gen_conv_plan_free(q);
+  gen_wgrad_plan_free(d.dgrad);
+  if (d.img) cudaFree(d.img);
+  d = kcvae_model::DensePlans();
+}
+// plans of the three Dense products for batch size B (the batch is a GEMM dimension here: columns of the forward product,
+// K of the weight gradient); nullptr when the engine does not take this size (the CUDA-core kernels run instead)
+kcvae_model::DensePlans* dense_plans_get(kcvae_model* h, int B) {
+  if (!h->gen_dense || B > 256) return nullptr;
+  for (auto& d : h->dense_plans) {
+    if (d.B == B && d.ones_cap == h->cap_fwd) return &d;
+  }
+  for (auto& d : h->dense_plans) if (d.B == B) dense_plans_free(d);      // the ones slot moved with the workspace
+  const int K = h->latent, N = h->dec_units, NR = N / 32;
+  const char* why = "";
+  kcvae_model::DensePlans d;
+  d.B = B; d.ones_cap = h->cap_fwd;
+  GenConvSpec f{};
+  f.kind = GEN_DENSE; f.in_layout = GEN_PLAIN; f.Ck = K; f.KCk = (K + 7) / 8; f.Cn = B; f.w_mode = 1; f.Hg = NR; f.Wg = 32;
+  f.split = 0; d.fwd = gen_conv_plan_create(f, &why);
+  f.split = 1; d.fwd_split = gen_conv_plan_create(f, &why);
+  bool ok = d.fwd && d.fwd_split;
+  for (int c0 = 0; c0 < K && ok; c0 += 240) {
+    const int nc = std::min(240, K - c0);
+    const bool last = c0 + nc == K;
+    GenConvSpec w{};
+    w.kind = GEN_DENSE; w.in_layout = GEN_PLAIN; w.Ck = B; w.KCk = (B + 7) / 8; w.Cn = nc + (last ? 1 : 0); w.w_mode = 0;
+    w.w_stride = K; w.w_col0 = c0; w.ones_col1 = last ? nc + 1 : 0; w.ones_src = h->cap_fwd * K; w.Hg = NR; w.Wg = 32;
+    GenConvPlan* q = gen_conv_plan_create(w, &why);
+    ok = q != nullptr;
+    if (q) { d.wgrad.push_back(q); d.wgrad_col0.push_back(c0); }
+  }
+  if (ok) {
+    GenWgradSpec g{};
+    g.kind = GEN_DENSE; g.s_layout = GEN_PLAIN; g.s_KC = (K + 7) / 8; g.u_layout = GEN_PLAIN; g.u_KC = (B + 7) / 8;
+    g.Cs = K; g.Cu = B; g.w_mode = 1; g.Hg = NR; g.Wg = 32;
+    d.dgrad = gen_wgrad_plan_create(g, &why);
+    ok = d.dgrad != nullptr;
+  }
+  if (ok) {
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t total = 0;
+    d.off_fwd = total; total += up(gen_conv_weight_image_bytes(d.fwd));
+    d.off_fwd_split = total; total += up(gen_conv_weight_image_bytes(d.fwd_split));
+    for (GenConvPlan* q : d.wgrad) { d.off_wgrad.push_back(total); total += up(gen_conv_weight_image_bytes(q)); }
+    ok = cudaMalloc(reinterpret_cast<void**>(&d.img), total + 256) == cudaSuccess;
+  }
+  if (!ok) { dense_plans_free(d); return nullptr; }
+  h->dense_plans.push_back(d);
+  return &h->dense_plans.back();
+}
+
+// relu(z W + b) -> the bf16 image of the Dense output (planes_out, hi + lo when split) and / or fp32 [B][N]
+bool gen_dense_forward(kcvae_model* h, const float* z, int B, int split, void* planes_out, float* f32_out, cudaStream_t st) {
+  kcvae_model::DensePlans* dp = dense_plans_get(h, B);
+  if (!dp) return false;
+  const int vi = h->vi_dec_dense(), K = h->latent, N = h->dec_units;
+  if (h->w_external || h->wT_version != h->w_version) {          // W^T as planes (hi + lo), once per weight version
+    gen_pack_rows_T(h->wp(vi), K, N, 1, h->wT_pl, st);
+    h->wT_version = h->w_version;
+  }
+  GenConvPlan* plan = split ? dp->fwd_split : dp->fwd;
+  unsigned char* img = dp->img + (split ? dp->off_fwd_split : dp->off_fwd);
+  gen_conv_prep_weights(plan, z, img, st);                       // this step's z as the B operand
+  GenPlanes in = pl_make(h->wT_pl, GEN_PLAIN, (K + 7) / 8, 1, N / 32, 32);
+  GenPlanes outp = pl_make(planes_out, GEN_PLAIN, h->dc[0] / 8, split, h->dh[0], h->dw[0]);
+  GenEpilogue e{};
+  e.pre = GEN_PRE_BIAS_RELU; e.bias = h->wp(vi + 1);
+  e.out = planes_out ? &outp : nullptr; e.out_f32 = f32_out;
+  e.dense_n = N; e.dense_ld = N; e.dense_cc = h->dc[0];
+  if (gen_conv_run(plan, in, img, e, 1, h->tc_error, "gen_dense", st) != 0) h->tc_failed = true;
+  return true;
 }
 #endif
 
@@ -520,7 +621,11 @@ int ensure_fwd(kcvae_model* h, int B) {
   KC_TRY(dalloc(h, &h->x_noisy, (size_t)B * h->P));
   KC_TRY(dalloc(h, &h->d1, (size_t)B * (h->enc_dense ? h->enc_dense : 1)));
   KC_TRY(dalloc(h, &h->head, (size_t)B * 2 * h->latent));
-  KC_TRY(dalloc(h, &h->z, (size_t)B * h->latent));
+  KC_TRY(dalloc(h, &h->z, (size_t)B * h->latent + 4));       // + a 1.0f behind it: the "ones column" source of the Dense bias gradient
+  {
+    const float one = 1.0f;
+    KC_CUDA(h, cudaMemcpy(h->z + (size_t)B * h->latent, &one, sizeof(float), cudaMemcpyHostToDevice));
+  }
   KC_TRY(dalloc(h, &h->mean, (size_t)B * h->latent));
   KC_TRY(dalloc(h, &h->logvar, (size_t)B * h->latent));
   KC_TRY(dalloc(h, &h->eps_buf, (size_t)B * h->latent));
@@ -589,6 +694,7 @@ int ensure_bwd(kcvae_model* h, int B) {
     h->g_e_pl.resize(L + 1, nullptr);
     for (int l = 1; l <= L; ++l) KC_TRY(gen_alloc(h, &h->g_e_pl[l], pl_g_e(h, l).units(Bc)));
   }
+  if (h->gen_dense) KC_TRY(gen_alloc(h, &h->gT_pl, (size_t)((Bc + 7) / 8) * h->dec_units));
   if (gen_dec || h->gen_dec0) {
     h->g_d_pl.resize(L + 1, nullptr);
     for (int l = 1; l <= (gen_dec ? L : 1); ++l) KC_TRY(gen_alloc(h, &h->g_d_pl[l], pl_g_d(h, l).units(Bc)));
@@ -753,7 +859,8 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   if (h->gen_dec) {
     // whole decoder on the general engine: Dense -> bf16 planes, every Conv2DTranspose and the output layer as tcgen05 products
     gen_refresh(h, st);
-    dense_wide_forward(z, ga.Bm, ga.bias, nullptr, B, h->dec_units, h->latent, 1, st, h->act_d_pl[0], h->dc[0], 0);
+    if (!gen_dense_forward(h, z, B, 0, h->act_d_pl[0], nullptr, st))
+      dense_wide_forward(z, ga.Bm, ga.bias, nullptr, B, h->dec_units, h->latent, 1, st, h->act_d_pl[0], h->dc[0], 0);
     for (int l = 0; l <= L; ++l) {
       const auto& g = h->gen_d[l];
       GenPlanes in = pl_act_d(h, l, 0), outp{};
@@ -787,6 +894,9 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
 #endif
   if (wide) {
     pp_ready = few_tc && L == 2 && h->dc[0] % 8 == 0;
+#ifndef KCVAE_EMU
+    if (!(pp_ready && gen_dense_forward(h, z, B, split ? 1 : 0, h->a_pp_planar, (pp_ready && !keep_last) ? nullptr : ga.C, st)))
+#endif
     dense_wide_forward(z, ga.Bm, ga.bias, (pp_ready && !keep_last) ? nullptr : ga.C, B, h->dec_units, h->latent, 1, st,
                        pp_ready ? h->a_pp_planar : nullptr, h->dc[0], split ? 1 : 0);
 #ifndef KCVAE_EMU
@@ -1161,6 +1271,29 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     const int vi = h->vi_dec_dense();
     const float* G = h->g_act_d[0];
     g_tag = "dec.dense.bwd";
+#ifndef KCVAE_EMU
+    kcvae_model::DensePlans* dp = (h->gen_dense && h->wT_version == h->w_version) ? dense_plans_get(h, B) : nullptr;
+    if (dp) {
+      // Dense backward on the engine: G -> planes [frames / 8][n][8] once; weight + bias gradient = a forward-type product over
+      // them (columns = latent + a ones column, K = frames) on the side stream; data gradient = a pixel-K product of G^T and W^T
+      const int K = h->latent, N = h->dec_units;
+      gen_pack_rows_T(G, B, N, 0, h->gT_pl, st);
+      GenPlanes gT = pl_make(h->gT_pl, GEN_PLAIN, (B + 7) / 8, 0, N / 32, 32);
+      float* px;
+      cudaStream_t ax = aux_fork(h, st, &px);
+      for (size_t i = 0; i < dp->wgrad.size(); ++i) {
+        unsigned char* img = dp->img + dp->off_wgrad[i];
+        g_tag = "dec.dense.bwd";
+        gen_conv_prep_weights(dp->wgrad[i], h->z, img, ax);
+        GenEpilogue e{};
+        e.pre = GEN_PRE_NONE; e.out_f32 = h->gp(vi) + (int64_t)dp->wgrad_col0[i] * N; e.dense_n = N; e.dense_ld = N; e.dense_cc = 32;
+        if (gen_conv_run(dp->wgrad[i], gT, img, e, 1, h->tc_error, "gen_dense_wgrad", ax) != 0) h->tc_failed = true;
+      }
+      GenPlanes wT = pl_make(h->wT_pl, GEN_PLAIN, (K + 7) / 8, 1, N / 32, 32);
+      g_tag = "dec.dense.bwd";
+      if (gen_wgrad_run(dp->dgrad, wT, gT, h->g_z, nullptr, h->gen_partial, 1, h->tc_error, "gen_dense_dgrad", st) != 0) h->tc_failed = true;
+    } else
+#endif
     if (dense_wide_ok(h->z, h->wp(vi), h->gp(vi), h->gp(vi + 1), B, h->dec_units, h->latent) &&
         dense_wide_ok(G, h->g_z, h->gp(vi), nullptr, B, h->dec_units, h->latent)) {
       float* px;
@@ -1360,6 +1493,7 @@ int step_impl(kcvae_model* h, const float* d_x, int B, const float* d_eps, const
     for (int k = 0; k < 4; ++k) h->img_version[k] = h->w_version;
   }
   const bool ext = h->w_external;
+  if (ext) { h->gen_img_version = 0; h->wT_version = 0; }   // weights may have been written behind the library's back: the engine's images are rebuilt in this step
   h->w_external = false;          // the images built above are current for this step
 #endif
   float* xh = d_xhat ? d_xhat : h->xhat;
@@ -1513,6 +1647,9 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->gen_table) cudaFree(h->gen_table);
   if (h->x_pl) cudaFree(h->x_pl);
   for (auto* v : {&h->act_e_pl, &h->g_e_pl, &h->act_d_pl, &h->g_d_pl}) for (void* q : *v) if (q) cudaFree(q);
+  for (auto& d : h->dense_plans) dense_plans_free(d);
+  if (h->wT_pl) cudaFree(h->wT_pl);
+  if (h->gT_pl) cudaFree(h->gT_pl);
   if (h->gen_partial) cudaFree(h->gen_partial);
   if (h->gen_partial2) cudaFree(h->gen_partial2);
 #endif
@@ -2306,6 +2443,83 @@ int kcvae_gen_wgrad_test(int kind, int w_mode, int flip, int s_x3, const float* 
   cudaMemcpyAsync(&flag, d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_wgrad_test: kernel failed");
   if (flag) return done(KCVAE_ERR_CUDA, "gen_wgrad_test: bounded mbarrier wait expired");
+  return done(KCVAE_OK, "");
+#endif
+}
+
+// Dense-layer products of the engine on fp32 device matrices (tests): A is [R][N] row-major (N % 32 == 0).
+//   mode 0  out[c][n] = act(bias[n] + sum_r A[r][n] * Bm[c][r])     Dense forward      (A = W [K][N], Bm = z [batch][K])
+//   mode 1  out[c][n] = sum_r A[r][n] * Bm[r][c], out[C][n] = sum_r A[r][n]   weight + bias gradient (A = G [batch][N], Bm = z [batch][K])
+//   mode 2  out[u][s] = sum_n A[u][n] * Bm[s][n]                    data gradient      (A = G [batch][N], Bm = W [K][N]), R = rows of A, C = rows of Bm
+int kcvae_gen_dense_test(int mode, int split, int relu, const float* d_a, const float* d_b, const float* d_bias, float* d_out,
+                         int R, int N, int C, void* stream) {
+#ifdef KCVAE_EMU
+  (void)mode; (void)split; (void)relu; (void)d_a; (void)d_b; (void)d_bias; (void)d_out; (void)R; (void)N; (void)C; (void)stream;
+  return fail(nullptr, KCVAE_ERR_UNSUPPORTED, "emu: tcgen05 kernels are not emulated");
+#else
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_a || !d_b || !d_out || R <= 0 || C <= 0 || N <= 0 || N % 32) return fail(nullptr, KCVAE_ERR_INVALID, "gen_dense_test: invalid arguments");
+  const char* why = "";
+  void *pa = nullptr, *pb = nullptr, *img = nullptr;
+  float *src = nullptr, *part = nullptr;
+  int32_t* tab = nullptr;
+  int* d_err = nullptr;
+  GenConvPlan* cp = nullptr;
+  GenWgradPlan* wp = nullptr;
+  auto done = [&](int code, const char* msg) {
+    cudaStreamSynchronize(st);
+    for (void* q : {pa, pb, img, (void*)src, (void*)part, (void*)tab, (void*)d_err}) if (q) cudaFree(q);
+    gen_conv_plan_free(cp); gen_wgrad_plan_free(wp);
+    return code == KCVAE_OK ? KCVAE_OK : fail(nullptr, code, msg);
+  };
+  if (cudaMalloc(reinterpret_cast<void**>(&d_err), sizeof(int)) != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_dense_test: cudaMalloc failed");
+  cudaMemsetAsync(d_err, 0, sizeof(int), st);
+  const int KCa = (R + 7) / 8;
+  GenPlanes A = pl_make(nullptr, GEN_PLAIN, KCa, mode == 0 ? split : 0, N / 32, 32);
+  if (cudaMalloc(&pa, A.units(1) * 16) != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_dense_test: cudaMalloc failed");
+  A.base = pa;
+  gen_pack_rows_T(d_a, R, N, A.split, pa, st);
+  int rc = 0;
+  if (mode == 0 || mode == 1) {
+    GenConvSpec sp{};
+    sp.kind = GEN_DENSE; sp.in_layout = GEN_PLAIN; sp.Ck = R; sp.KCk = KCa; sp.Hg = N / 32; sp.Wg = 32; sp.split = mode == 0 ? split : 0;
+    if (mode == 0) { sp.Cn = C; sp.w_mode = 1; }
+    else { sp.Cn = C + 1; sp.w_mode = 0; sp.w_stride = C; sp.ones_col1 = C + 1; sp.ones_src = R * C; }
+    cp = gen_conv_plan_create(sp, &why);
+    if (!cp) return done(KCVAE_ERR_UNSUPPORTED, why);
+    // "weight" source: Bm followed by a 1.0f
+    const size_t nb = (size_t)(mode == 0 ? C * R : R * C);
+    const float one = 1.0f;
+    if (cudaMalloc(reinterpret_cast<void**>(&src), (nb + 4) * sizeof(float)) != cudaSuccess ||
+        cudaMalloc(&img, gen_conv_weight_image_bytes(cp) + 16) != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_dense_test: cudaMalloc failed");
+    cudaMemcpyAsync(src, d_b, nb * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(src + nb, &one, sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+    gen_conv_prep_weights(cp, src, img, st);
+    GenEpilogue e{};
+    e.pre = mode == 0 ? (relu ? GEN_PRE_BIAS_RELU : GEN_PRE_BIAS) : GEN_PRE_NONE;
+    e.bias = mode == 0 ? d_bias : nullptr;
+    e.out_f32 = d_out; e.dense_n = N; e.dense_ld = N; e.dense_cc = 32;
+    rc = gen_conv_run(cp, A, img, e, 1, d_err, "gen_dense_test", st);
+  } else {
+    const int KCb = (C + 7) / 8;
+    GenPlanes Bp = pl_make(nullptr, GEN_PLAIN, KCb, 0, N / 32, 32);
+    if (cudaMalloc(&pb, Bp.units(1) * 16) != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_dense_test: cudaMalloc failed");
+    Bp.base = pb;
+    gen_pack_rows_T(d_b, C, N, 0, pb, st);
+    GenWgradSpec sp{};
+    sp.kind = GEN_DENSE; sp.s_layout = GEN_PLAIN; sp.s_KC = KCb; sp.u_layout = GEN_PLAIN; sp.u_KC = KCa; sp.Cs = C; sp.Cu = R; sp.w_mode = 1;
+    sp.Hg = N / 32; sp.Wg = 32;
+    wp = gen_wgrad_plan_create(sp, &why);
+    if (!wp) return done(KCVAE_ERR_UNSUPPORTED, why);
+    if (cudaMalloc(reinterpret_cast<void**>(&part), gen_wgrad_partial_floats(wp) * sizeof(float)) != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_dense_test: cudaMalloc failed");
+    rc = gen_wgrad_run(wp, Bp, A, d_out, nullptr, part, 1, d_err, "gen_dense_test", st);
+  }
+  if (rc != 0) return done(KCVAE_ERR_CUDA, "gen_dense_test: launcher failed");
+  int flag = 0;
+  cudaMemcpyAsync(&flag, d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_dense_test: kernel failed");
+  if (flag) return done(KCVAE_ERR_CUDA, "gen_dense_test: bounded mbarrier wait expired");
   return done(KCVAE_OK, "");
 #endif
 }

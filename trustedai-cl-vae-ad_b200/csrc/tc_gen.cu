@@ -111,6 +111,7 @@ struct G1Params {
   PlaneRef out; int has_out, out_lo;
   float* out_f32;
   int Cn;            // real N-side channels
+  int dense_n, dense_ld, dense_cc;   // GEN_DENSE epilogue (see GenEpilogue)
   int Ho, Wo;        // logical output dims
   int* error_flag;
 };
@@ -121,7 +122,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 }
 
 // epilogue variants (template flags): only the code a product needs is compiled into its kernel
-constexpr int E_PRE = 1, E_MASK = 2, E_OUTP = 4, E_LO = 8, E_F32 = 16, E_MASKF = 32, E_ALL = 63;
+constexpr int E_PRE = 1, E_MASK = 2, E_OUTP = 4, E_LO = 8, E_F32 = 16, E_MASKF = 32, E_ALL = 63, E_DENSE = 64;
 
 // one 8-channel group of one output pixel: pre-op, mask, stores
 template <int EPI>
@@ -189,7 +190,7 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   __shared__ uint32_t tmem_slot;
   __shared__ float s_bias[256 + 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 256 + 8; i += G1_THREADS) s_bias[i] = (p.bias && i < p.Cn) ? __ldg(p.bias + i) : 0.f;
+  for (int i = threadIdx.x; i < 256 + 8; i += G1_THREADS) s_bias[i] = (!(EPI & E_DENSE) && p.bias && i < p.Cn) ? __ldg(p.bias + i) : 0.f;
 
   {  // plan -> shared memory (header + the used slab / MMA entries)
     const uint4* src = reinterpret_cast<const uint4*>(p.plan);
@@ -366,6 +367,33 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
         float v[32];
         if (ncols == 32) tmem_ld32(ta, v);
         else tmem_ld16(ta, v);
+        if constexpr ((EPI & E_DENSE) != 0) {
+          // Dense product: this thread holds GEMM row n (an output unit of the Dense layer / a column of its weight matrix)
+          // for 32 columns (batch rows / latent columns).  Bias is per row; fp32 output is [column][n] (coalesced over the
+          // warp's 32 consecutive n); the bf16 image of the Dense output is [column = frame][chunk][pixel][8].
+          const int n_row = gy * GP + gx;
+          if (valid && n_row < p.dense_n) {
+            const float rb = p.bias ? __ldg(p.bias + n_row) : 0.f;
+            const int pc = n_row / p.dense_cc, cc = n_row - pc * p.dense_cc;
+            const int64_t hw = (int64_t)p.out.H * p.out.W;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = cb * 32 + j;
+              if (j < ncols && col < p.Cn) {
+                float y = v[j] + rb;
+                if (p.pre == GEN_PRE_BIAS_RELU) y = fmaxf(y, 0.f);
+                if (p.out_f32) p.out_f32[(int64_t)col * p.dense_ld + n_row] = y;
+                if (p.has_out) {
+                  __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out.base);
+                  const __nv_bfloat16 hi = __float2bfloat16(y);
+                  const int64_t u = ((int64_t)col * p.out.PLimg + (cc >> 3)) * hw + pc;
+                  ob[u * 8 + (cc & 7)] = hi;
+                  if (p.out_lo) ob[(u + (int64_t)p.out.KC * hw) * 8 + (cc & 7)] = __float2bfloat16(y - __bfloat162float(hi));
+                }
+              }
+            }
+          }
+        } else
         if (valid) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
@@ -482,6 +510,7 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
   const int Cop = (s.Cn + 15) / 16 * 16;
   const int n_groups = s.kind == GEN_CONVT_S2 ? 2 : 1;
   const int acc_cols = s.kind == GEN_CONVT_S2 ? 2 * Cop : Cop;
+  if (s.kind == GEN_DENSE && s.Wg != GP) return no("a Dense product is laid out 32 pixels wide");
   if (acc_cols > 256) return no("more than 256 accumulator columns per M-tile");
   const int PLh = hi_planes(s.in_layout, s.KCk);
   if (s.kind == GEN_CONV_S2 && s.in_layout == GEN_PLAIN) return no("stride-2 product needs an S2D / X3 input");
@@ -497,6 +526,7 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
   int halo_r, halo_c;
   if (s.kind == GEN_CONV_S2) { D.row0 = 0; D.col0 = 0; halo_r = 1; halo_c = 1; }
   else if (s.kind == GEN_CONVT_S2) { D.row0 = -1; D.col0 = -1; halo_r = 1; halo_c = 1; }
+  else if (s.kind == GEN_DENSE) { D.row0 = 0; D.col0 = 0; halo_r = 0; halo_c = 0; }
   else { D.row0 = -1; D.col0 = -1; halo_r = 2; halo_c = 2; }
   D.TW = GP - halo_c;
   D.R_in = 4 * D.MT + halo_r;
@@ -507,6 +537,7 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
   std::vector<Tap> taps;
   if (s.kind == GEN_CONV_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, di * GP + dj});
   else if (s.kind == GEN_CONVT_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, (1 - di) * GP + (1 - dj)});
+  else if (s.kind == GEN_DENSE) taps.push_back({0, 0, 0});
   else for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw)
     taps.push_back({kh, kw, s.flip ? (2 - kh) * GP + (2 - kw) : kh * GP + kw});
 
@@ -515,6 +546,11 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
     int par, ch;
     elem_of(s.in_layout, s.KCk, s.Ck, plane, slot, &par, &ch);
     if (ch < 0) return -1;
+    if (s.kind == GEN_DENSE) {
+      if (n >= s.Cn) return -1;
+      if (s.ones_col1 && n == s.ones_col1 - 1) return s.ones_src;
+      return s.w_mode == 0 ? ch * (s.w_stride ? s.w_stride : s.Cn) + n + s.w_col0 : (n + s.w_col0) * (s.w_stride ? s.w_stride : s.Ck) + ch;
+    }
     int kh, kw, cn;
     if (s.kind == GEN_CONV_S2) {
       kh = 2 * tp.t0 + (par >> 1); kw = 2 * tp.t1 + (par & 1); cn = n;
@@ -696,6 +732,7 @@ int gen_conv_run(const GenConvPlan* P, const GenPlanes& in, const void* wimg, co
   if (e.out) { p.out = plane_ref(*e.out); p.out_lo = e.out->split; }
   p.out_f32 = e.out_f32;
   p.Cn = s.Cn;
+  p.dense_n = e.dense_n; p.dense_ld = e.dense_ld; p.dense_cc = e.dense_cc > 0 ? e.dense_cc : 1;
   p.Ho = s.kind == GEN_CONVT_S2 ? 2 * s.Hg : s.Hg;
   p.Wo = s.kind == GEN_CONVT_S2 ? 2 * s.Wg : s.Wg;
   p.error_flag = error_flag;
@@ -713,6 +750,7 @@ int gen_conv_run(const GenConvPlan* P, const GenPlanes& in, const void* wimg, co
     cudaFuncSetAttribute(tc_gconv_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem);   \
     tc_gconv_kernel<F><<<grid, G1_THREADS, P->smem, st>>>(tmap, p);                                          \
   } while (0)
+  if (s.kind == GEN_DENSE) { KC_G1_LAUNCH(E_DENSE); return 0; }
   switch (flags) {     // the products the model issues get their own lean kernels; anything else runs the catch-all
     case E_PRE | E_OUTP | E_LO: KC_G1_LAUNCH(E_PRE | E_OUTP | E_LO); break;
     case E_PRE | E_OUTP: KC_G1_LAUNCH(E_PRE | E_OUTP); break;
@@ -926,6 +964,7 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
   int halo_r, halo_c, row0, col0;
   if (s.kind == GEN_CONV_S2) { row0 = 0; col0 = 0; halo_r = 1; halo_c = 1; }
   else if (s.kind == GEN_CONVT_S2) { row0 = -1; col0 = -1; halo_r = 1; halo_c = 1; }
+  else if (s.kind == GEN_DENSE) { row0 = 0; col0 = 0; halo_r = 0; halo_c = 0; }
   else { row0 = -1; col0 = -1; halo_r = 2; halo_c = 2; }
   int TW = 0;
   for (int d = GP - halo_c; d >= 8; --d) if (s.Wg % d == 0) { TW = d; break; }
@@ -934,6 +973,7 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
   std::vector<Tap> taps;
   if (s.kind == GEN_CONV_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, di * GP + dj});
   else if (s.kind == GEN_CONVT_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, (1 - di) * GP + (1 - dj)});
+  else if (s.kind == GEN_DENSE) taps.push_back({0, 0, 0});
   else for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw)
     taps.push_back({kh, kw, s.flip ? (2 - kh) * GP + (2 - kw) : kh * GP + kw});
 
@@ -967,7 +1007,7 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
     return true;
   };
   auto pruned_plan = [&](std::vector<Acc>& out) -> bool {
-    if (s.kind == GEN_CONV_S1) return false;
+    if (s.kind == GEN_CONV_S1 || s.kind == GEN_DENSE) return false;
     const bool p_is_s = s.kind == GEN_CONV_S2;            // the space-to-depth operand: the layer input (Conv2D) or the gradient (ConvT)
     if ((p_is_s ? s.s_layout : s.u_layout) != GEN_S2D) return false;
     const int KCp = p_is_s ? s.s_KC : s.u_KC, nQ = p_is_s ? nU : nS;
@@ -1001,7 +1041,9 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
   // bias accumulators: A = runs of the gradient's planes, B = two planes of ones.  With the pruned plan over a
   // space-to-depth gradient the runs are the parity blocks the product accumulators already load.
   std::vector<Acc> bias;
-  if (pruned && s.kind == GEN_CONVT_S2 && (s.u_KC == 8 || s.u_KC == 16)) {
+  if (s.kind == GEN_DENSE) {
+    // a Dense data gradient: no bias accumulator
+  } else if (pruned && s.kind == GEN_CONVT_S2 && (s.u_KC == 8 || s.u_KC == 16)) {
     for (int par = 0; par < 4; ++par)
       bias.push_back({-1, {false, par * s.u_KC, s.u_KC}, {false, 0, 0}, s.u_KC * 8, s.u_KC == 16 ? 16 : 8, 0, 0, true});
   } else {
@@ -1139,8 +1181,12 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
     return -1;
   };
   const int Cs = s.Cs, Cu = s.Cu;
-  P->EW = 9 * Cs * Cu;
+  P->EW = (s.kind == GEN_DENSE ? 1 : 9) * Cs * Cu;
   P->src.assign((size_t)(P->EW + Cu) * 4, -1);
+  if (s.kind == GEN_DENSE) {       // out[(cs, cu)]: w_mode 0 -> cs * Cu + cu ; 1 -> cu * Cs + cs
+    for (int cs = 0; cs < Cs; ++cs) for (int cu = 0; cu < Cu; ++cu)
+      P->src[(size_t)(s.w_mode == 0 ? cs * Cu + cu : cu * Cs + cs) * 4] = find(0, cs, cu, false);
+  } else
   for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) for (int cs = 0; cs < Cs; ++cs) for (int cu = 0; cu < Cu; ++cu) {
     int tap_i, es, eu;
     if (s.kind == GEN_CONV_S2) {
@@ -1160,7 +1206,7 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
     const int e = s.w_mode == 0 ? (tap9 * Cs + cs) * Cu + cu : (tap9 * Cu + cu) * Cs + cs;
     P->src[(size_t)e * 4] = find(tap_i, es, eu, false);
   }
-  for (int cu = 0; cu < Cu; ++cu) {
+  for (int cu = 0; cu < Cu && s.kind != GEN_DENSE; ++cu) {
     const int npar = s.u_layout == GEN_S2D ? 4 : 1;
     for (int par = 0; par < npar; ++par) {
       const int eu = s.u_layout == GEN_S2D ? par * s.u_KC * 8 + cu : cu;
@@ -1291,6 +1337,32 @@ __global__ void gen_unpack_nhwc_kernel(PlaneRef in, int split, int B, int H, int
 
 }  // namespace
 
+namespace {
+// one thread per (chunk, n): 8 loads with stride N (coalesced across the warp), one 16-byte store (two when split)
+__global__ void gen_pack_rows_T_kernel(const float* __restrict__ in, int R, int N, int split, uint4* out) {
+  const int KC = (R + 7) / 8;
+  const int64_t total = (int64_t)KC * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % N), chunk = (int)(i / N);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = chunk * 8 + k < R ? __ldg(in + (int64_t)(chunk * 8 + k) * N + n) : 0.f;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      lo[e] = pack_bf16x2(v[2 * e] - __uint_as_float(hi[e] << 16), v[2 * e + 1] - __uint_as_float(hi[e] & 0xFFFF0000u));
+    }
+    out[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (split) out[total + i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+}  // namespace
+void gen_pack_rows_T(const float* in, int R, int N, int split, void* out, cudaStream_t st) {
+  ProfScope prof_("gen_pack_rows_T", st);
+  ++g_launches;
+  gen_pack_rows_T_kernel<<<grid_for((int64_t)((R + 7) / 8) * N, 256, 8, 4), 256, 0, st>>>(in, R, N, split, reinterpret_cast<uint4*>(out));
+}
 void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cudaStream_t st) {
   ProfScope prof_("gen_pack_x3", st);
   ++g_launches;

@@ -21,6 +21,9 @@ enum GenKind {
   GEN_CONV_S2 = 0,    // K side: S2D / X3 input, taps (di,dj) in {0,1}^2   (Conv2D s2 forward, Conv2DTranspose s2 dgrad)
   GEN_CONVT_S2 = 1,   // K side: PLAIN input, N side: (col parity, channel), one group per row parity (ConvT s2 fwd, Conv2D s2 dgrad)
   GEN_CONV_S1 = 2,    // K side: PLAIN input, 9 taps (output layer forward and dgrad)
+  GEN_DENSE = 3,      // a Dense layer product seen from its LONG dimension: GEMM rows = the n of a [R][n] matrix viewed as
+                      // [n/32][32] "pixels", K side = that matrix as planes [R/8][n][8] (gen_pack_rows_T), columns = the short
+                      // dimension (batch rows of z / latent columns) supplied through the weight image; one tap
 };
 enum GenPre { GEN_PRE_NONE = 0, GEN_PRE_BIAS_RELU = 1, GEN_PRE_BIAS_SIGMOID = 2, GEN_PRE_BIAS = 3 };
 
@@ -34,6 +37,10 @@ struct GenConvSpec {
   int w_mode;      // fp32 weight element (tap, k, n): 0 -> (tap*Ck + k)*Cn + n ; 1 -> (tap*Cn + n)*Ck + k
   int flip;        // GEN_CONV_S1: 1 = in[y+1-kh] (Conv2DTranspose s1 forward), 0 = in[y-1+kh]
   int split;       // K-side tensor carries lo planes behind the hi planes; weight image has a lo half
+  int w_stride;    // GEN_DENSE: row stride of the fp32 "weight" source (0: Cn for w_mode 0, Ck for w_mode 1)
+  int ones_col1;   // GEN_DENSE: 1 + index of a column whose B operand is all ones (row sums = a bias gradient), 0 = none
+  int ones_src;    // GEN_DENSE: index of a 1.0f in the fp32 "weight" source (read for the ones column)
+  int w_col0;      // GEN_DENSE: first source column (wide weight gradients run as several column blocks of <= 256)
   int Hg, Wg;      // GEMM grid: output pixels per image (CONV_S2 / CONV_S1) or input pixels (CONVT_S2)
 };
 
@@ -66,7 +73,9 @@ struct GenEpilogue {
   const float* bias;       // [Cn]
   const GenPlanes* mask;   // multiply by (mask > 0): activation stored at the OUTPUT pixel (PLAIN or S2D), hi planes; or nullptr
   const GenPlanes* out;    // bf16 plane output (PLAIN or S2D; split -> hi + lo) or nullptr
-  float* out_f32;          // fp32 NHWC [B,Ho,Wo,Cn] or nullptr
+  float* out_f32;          // fp32 NHWC [B,Ho,Wo,Cn] or nullptr (GEN_DENSE: [Cn][dense_ld], element (column, row))
+  int dense_n, dense_ld;   // GEN_DENSE: valid GEMM rows n and leading dimension of out_f32; bias is per ROW; `out` planes are
+  int dense_cc;            //   written as [column][chunk(c)][pixel p][8] with row n = p * dense_cc + c (the Dense output as an image)
   const float* mask_f32;   // fp32 NHWC mask [B,Ho,Wo,Cn] (alternative to `mask`) or nullptr
 };
 // in: K-side plane tensor; returns 0 on success (1: no driver entry point, 2: tensor map encode failed)
@@ -96,6 +105,9 @@ int gen_wgrad_run(const GenWgradPlan* p, const GenPlanes& S, const GenPlanes& U,
 void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cudaStream_t st);
 // fp32 NHWC [B,H,W,C] -> PLAIN / S2D planes (channels padded with zeros; split -> lo planes too)
 void gen_pack_nhwc(const float* in, int B, int H, int W, int C, const GenPlanes& out, cudaStream_t st);
+// fp32 [R][N] row-major -> planes [ceil(R/8) (x2 when split)][N][8]: unit (chunk, n) holds rows 8*chunk .. 8*chunk+7 of column n
+// (rows >= R are zero).  The K-side tensor of GEN_DENSE products (n viewed as [N/32][32] pixels; N % 32 == 0).
+void gen_pack_rows_T(const float* in, int R, int N, int split, void* out, cudaStream_t st);
 // planes -> fp32 NHWC [B,H,W,C] (hi + lo when split); tests / debug
 void gen_unpack_nhwc(const GenPlanes& in, int B, int H, int W, int C, float* out, cudaStream_t st);
 
