@@ -176,6 +176,7 @@ struct kcvae_model {
   float *gen_partial = nullptr, *gen_partial2 = nullptr;
   // decoder Dense layer on the engine (GEN_DENSE products): W^T and G^T as plane tensors, plans per batch size
   bool gen_dense = false;
+  bool dense_f32_skipped = false;   // the last forward left no fp32 copy of the Dense output (debug_activation unpacks the planes)
   void *wT_pl = nullptr, *gT_pl = nullptr;
   uint64_t wT_version = 0;
   struct DensePlans {
@@ -476,7 +477,11 @@ void dense_plans_free(kcvae_model::DensePlans& d) {
 // plans of the three Dense products for batch size B (the batch is a GEMM dimension here: columns of the forward product,
 // K of the weight gradient); nullptr when the engine does not take this size (the CUDA-core kernels run instead)
 kcvae_model::DensePlans* dense_plans_get(kcvae_model* h, int B) {
-  if (!h->gen_dense || B > 256) return nullptr;
+  // measured (profiles/r02_x_*): at 256 frames the three engine products replace 0.40 ms of CUDA-core kernels with 0.25 ms; at
+  // 32 frames the Dense layer is bound by its 17 MB weight matrix either way and the extra pack / gather launches cost 0.02 ms
+  const char* mb = std::getenv("KCVAE_GEN_DENSE_MIN_BATCH");       // tests lower it so that small batches drive the engine path too
+  const int min_batch = mb ? std::atoi(mb) : 64;
+  if (!h->gen_dense || B > 256 || B < min_batch) return nullptr;
   for (auto& d : h->dense_plans) {
     if (d.B == B && d.ones_cap == h->cap_fwd) return &d;
   }
@@ -895,7 +900,12 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
   if (wide) {
     pp_ready = few_tc && L == 2 && h->dc[0] % 8 == 0;
 #ifndef KCVAE_EMU
-    if (!(pp_ready && gen_dense_forward(h, z, B, split ? 1 : 0, h->a_pp_planar, (pp_ready && !keep_last) ? nullptr : ga.C, st)))
+    // (training with the engine's backward behind it: the hi + lo planes are the only copy of the Dense output anybody reads)
+    h->dense_f32_skipped = false;
+    if (pp_ready && gen_dense_forward(h, z, B, split ? 1 : 0, h->a_pp_planar,
+                                      (!keep_last || (h->gen_dec0 && split)) ? nullptr : ga.C, st)) {
+      h->dense_f32_skipped = keep_last && h->gen_dec0 && split;
+    } else
 #endif
     dense_wide_forward(z, ga.Bm, ga.bias, (pp_ready && !keep_last) ? nullptr : ga.C, B, h->dec_units, h->latent, 1, st,
                        pp_ready ? h->a_pp_planar : nullptr, h->dc[0], split ? 1 : 0);
@@ -2230,7 +2240,10 @@ int64_t kcvae_debug_activation(kcvae_handle h, int which, float* h_out, int64_t 
   GenPlanes pl{};
   int ph = 0, pw = 0, pc = 0;
   bool planes = false;
-  if (!src && n > 0) {
+  if (which == 100 && h->dense_f32_skipped && h->a_pp_planar) {      // the Dense output of the last forward only exists as hi + lo planes
+    pl = pl_act_d(h, 0, 1); ph = h->dh[0]; pw = h->dw[0]; pc = h->dc[0]; planes = true; src = nullptr;
+  }
+  if (!src && n > 0 && !planes) {
     if (which >= 1 && which < L && h->gen_enc) { pl = pl_act_e(h, which, h->enc_split_live ? 1 : 0); ph = h->eh[which]; pw = h->ew[which]; pc = h->ec[which]; planes = true; }
     else if (which >= 100 && which <= 100 + L && h->gen_dec) { int l = which - 100; pl = pl_act_d(h, l, 0); ph = h->dh[l]; pw = h->dw[l]; pc = h->dc[l]; planes = true; }
     else if (which >= 302 && which <= 301 + L && h->gen_dec && (int)h->g_d_pl.size() > which - 301) { int l = which - 301; pl = pl_g_d(h, l); ph = h->dh[l]; pw = h->dw[l]; pc = h->dc[l]; planes = true; }
