@@ -477,3 +477,22 @@ def test_train_image_noise_is_drawn_in_the_library():
     assert abs(a1["mse"] - off["mse"]) < 0.05    # beta = 0.05 perturbs, it does not replace, the input
     zero = run(5, True, noise=np.zeros_like(x))  # explicit noise wins over the switch
     assert zero == off
+
+
+def test_dense_backward_on_the_engine_beyond_256_frames():
+    """Above 256 frames the decoder Dense forward stays on the streaming CUDA-core kernel (the batch is the column dimension
+    of the forward product) while its weight / bias / data gradients still run as tcgen05 products (K = frames): gradients
+    of a 288-frame README-config batch against the fp32 path, same bars as test_tc_backward_parity."""
+    cfg = O.readme_config()
+    B = 288
+    x, eps = frames(cfg, B), eps_for(cfg, B)
+    m, _ = make(cfg, BACKEND, weight_gain=1.3, precision="bf16")
+    m32, _ = make(cfg, BACKEND, weight_gain=1.3)
+    d, grads = m.loss_and_grads(x, eps=eps)
+    d32, grads32 = m32.loss_and_grads(x, eps=eps)
+    assert m.tc_status() == 1
+    assert_metrics_close(d, d32, rtol=1e-3, atol=1e-6)
+    for (n, _), g, og in zip(O.variable_shapes(cfg), grads, grads32):
+        og = np.asarray(og, np.float64)
+        l2 = np.linalg.norm(np.asarray(g, np.float64) - og) / (np.linalg.norm(og) + 1e-30)
+        assert l2 < 5e-2, (n, l2)

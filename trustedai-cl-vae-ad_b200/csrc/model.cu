@@ -481,7 +481,7 @@ kcvae_model::DensePlans* dense_plans_get(kcvae_model* h, int B) {
   // 32 frames the Dense layer is bound by its 17 MB weight matrix either way and the extra pack / gather launches cost 0.02 ms
   const char* mb = std::getenv("KCVAE_GEN_DENSE_MIN_BATCH");       // tests lower it so that small batches drive the engine path too
   const int min_batch = mb ? std::atoi(mb) : 64;
-  if (!h->gen_dense || B > 256 || B < min_batch) return nullptr;
+  if (!h->gen_dense || B > 1024 || B < min_batch) return nullptr;
   for (auto& d : h->dense_plans) {
     if (d.B == B && d.ones_cap == h->cap_fwd) return &d;
   }
@@ -492,9 +492,12 @@ kcvae_model::DensePlans* dense_plans_get(kcvae_model* h, int B) {
   d.B = B; d.ones_cap = h->cap_fwd;
   GenConvSpec f{};
   f.kind = GEN_DENSE; f.in_layout = GEN_PLAIN; f.Ck = K; f.KCk = (K + 7) / 8; f.Cn = B; f.w_mode = 1; f.Hg = NR; f.Wg = 32;
-  f.split = 0; d.fwd = gen_conv_plan_create(f, &why);
-  f.split = 1; d.fwd_split = gen_conv_plan_create(f, &why);
-  bool ok = d.fwd && d.fwd_split;
+  bool ok = true;
+  if (B <= 256) {            // the batch is the column dimension of the forward product (<= 256 accumulator columns); beyond
+    f.split = 0; d.fwd = gen_conv_plan_create(f, &why);       // that the forward stays on the streaming CUDA-core kernel and
+    f.split = 1; d.fwd_split = gen_conv_plan_create(f, &why); // only the two backward products run here
+    ok = d.fwd && d.fwd_split;
+  }
   for (int c0 = 0; c0 < K && ok; c0 += 240) {
     const int nc = std::min(240, K - c0);
     const bool last = c0 + nc == K;
@@ -515,8 +518,10 @@ kcvae_model::DensePlans* dense_plans_get(kcvae_model* h, int B) {
   if (ok) {
     auto up = [](size_t v) { return (v + 255) / 256 * 256; };
     size_t total = 0;
-    d.off_fwd = total; total += up(gen_conv_weight_image_bytes(d.fwd));
-    d.off_fwd_split = total; total += up(gen_conv_weight_image_bytes(d.fwd_split));
+    if (d.fwd) {
+      d.off_fwd = total; total += up(gen_conv_weight_image_bytes(d.fwd));
+      d.off_fwd_split = total; total += up(gen_conv_weight_image_bytes(d.fwd_split));
+    }
     for (GenConvPlan* q : d.wgrad) { d.off_wgrad.push_back(total); total += up(gen_conv_weight_image_bytes(q)); }
     ok = cudaMalloc(reinterpret_cast<void**>(&d.img), total + 256) == cudaSuccess;
   }
@@ -525,15 +530,18 @@ kcvae_model::DensePlans* dense_plans_get(kcvae_model* h, int B) {
   return &h->dense_plans.back();
 }
 
+// W^T of the decoder Dense as planes (hi + lo), once per weight version
+void dense_refresh_wT(kcvae_model* h, cudaStream_t st) {
+  if (!h->w_external && h->wT_version == h->w_version) return;
+  gen_pack_rows_T(h->wp(h->vi_dec_dense()), h->latent, h->dec_units, 1, h->wT_pl, st);
+  h->wT_version = h->w_version;
+}
 // relu(z W + b) -> the bf16 image of the Dense output (planes_out, hi + lo when split) and / or fp32 [B][N]
 bool gen_dense_forward(kcvae_model* h, const float* z, int B, int split, void* planes_out, float* f32_out, cudaStream_t st) {
   kcvae_model::DensePlans* dp = dense_plans_get(h, B);
-  if (!dp) return false;
+  if (!dp || !dp->fwd) return false;
   const int vi = h->vi_dec_dense(), K = h->latent, N = h->dec_units;
-  if (h->w_external || h->wT_version != h->w_version) {          // W^T as planes (hi + lo), once per weight version
-    gen_pack_rows_T(h->wp(vi), K, N, 1, h->wT_pl, st);
-    h->wT_version = h->w_version;
-  }
+  dense_refresh_wT(h, st);
   GenConvPlan* plan = split ? dp->fwd_split : dp->fwd;
   unsigned char* img = dp->img + (split ? dp->off_fwd_split : dp->off_fwd);
   gen_conv_prep_weights(plan, z, img, st);                       // this step's z as the B operand
@@ -1282,8 +1290,9 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     const float* G = h->g_act_d[0];
     g_tag = "dec.dense.bwd";
 #ifndef KCVAE_EMU
-    kcvae_model::DensePlans* dp = (h->gen_dense && h->wT_version == h->w_version) ? dense_plans_get(h, B) : nullptr;
+    kcvae_model::DensePlans* dp = h->gen_dense ? dense_plans_get(h, B) : nullptr;
     if (dp) {
+      dense_refresh_wT(h, st);
       // Dense backward on the engine: G -> planes [frames / 8][n][8] once; weight + bias gradient = a forward-type product over
       // them (columns = latent + a ones column, K = frames) on the side stream; data gradient = a pixel-K product of G^T and W^T
       const int K = h->latent, N = h->dec_units;
