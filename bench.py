@@ -173,7 +173,7 @@ def algorithmic_bytes(cfg, B, world):
         if l > 0:
             tab[f"{nm}.bwd/conv3x3"] = B * (act * enc[l + 1] + 2 * act * enc[l]) + wk
     for l in range(L):
-        nm = "dec.convT_last" if l == L - 1 else "dec.convT"
+        nm = "dec.convT_last" if l == L - 1 else ("dec.convT" if l == L - 2 else "dec.convT_early")
         wk = 4 * nW[f"decoder/conv2d_transpose_{l}/kernel"]
         tab[f"{nm}.fwd/conv3x3"] = B * act * (dec[l] + dec[l + 1]) + wk
         tab[f"{nm}.bwd/wgrad"] = B * act * (dec[l] + dec[l + 1]) + wk
@@ -200,6 +200,18 @@ def algorithmic_bytes(cfg, B, world):
                         ("dec.convT.fwd/tc_convT_few_fwd", "dec.convT.fwd/conv3x3")):
         if generic in tab:
             tab[tc] = tab[generic]
+    # the general engine's kernels (tc_gen.cu) move the same tensors as the launchers they replace
+    for key in list(tab):
+        tag, kern = key.split("/")
+        if kern == "conv3x3" and tag.endswith(".fwd"):
+            tab[f"{tag}/gen_conv"] = tab[key]
+        elif kern == "conv3x3" and tag.endswith(".bwd"):
+            tab[f"{tag}/gen_dgrad"] = tab[key]
+        elif kern == "wgrad":
+            tab[f"{tag}/gen_wgrad"] = tab[key]
+    tab["dec.dense.fwd/gen_dense"] = tab["dec.dense.fwd/gemm"]
+    tab["dec.dense.bwd/gen_dense_wgrad"] = B * (4 * t.latent + act * dec[0]) + wd
+    tab["dec.dense.bwd/gen_dense_dgrad"] = B * (4 * t.latent + act * dec[0]) + wd
     tab["dec.dense.fwd/dense_wide_fwd"] = tab["dec.dense.fwd/gemm"]
     tab["dec.dense.bwd/dense_wide_wgrad"] = B * (4 * t.latent + act * dec[0]) + wd     # z, G in; dW (+ bias grad) out
     tab["dec.dense.bwd/dense_wide_dgrad"] = B * (4 * t.latent + act * dec[0]) + wd     # G, W in; dz out
@@ -238,6 +250,40 @@ def hbm_peak():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def flops_per_frame(cfg):
+    """(forward, train) FLOP per frame, 2 x MACs; train = 3 x forward - the first convolution's data gradient."""
+    from oracle import kcvae_oracle as O
+    t = O.topology(cfg)
+    macs, cin, first = 0, t.C, 0
+    for i, ((h, w), f) in enumerate(zip(t.enc_hw, t.layers)):
+        m = h * w * 9 * cin * f
+        macs += m
+        if i == 0:
+            first = m
+        cin = f
+    k = t.flat
+    if t.enc_dense:
+        macs += k * t.enc_dense
+        k = t.enc_dense
+    macs += k * 2 * t.latent
+    units = t.dec_h0 * t.dec_w0 * t.dec_dense
+    macs += t.latent * units
+    h, w, cin = t.dec_h0, t.dec_w0, t.dec_dense
+    for f in reversed(t.layers):
+        macs += (2 * h) * (2 * w) * 9 * cin * f // 4            # 9 taps per 4 output pixels
+        h, w, cin = 2 * h, 2 * w, f
+    macs += h * w * 9 * cin * t.C
+    return 2 * macs, 2 * (3 * macs - first)
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1393.7))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback"
 
 
 def score_step_bytes(cfg, B):
@@ -505,6 +551,11 @@ def run_config(ctx, name, K, Wm, full=True):
     rep = model.profile_report()
     model.profile(False)
     roof, top_key = roofline_from_profile(rep, tab, step_bytes, ms_total / K, K)
+    f_fwd, f_train = flops_per_frame(cfg)
+    tpk, tsrc = tensor_peak()
+    ach_tf = (f_fwd if scoring else f_train) * B / (ms_total / K * 1e-3) / 1e12
+    roof["tensor"] = {"useful_flop_per_step": (f_fwd if scoring else f_train) * B, "achieved": ach_tf, "peak": tpk, "unit": "TFLOP/s",
+                      "frac": ach_tf / tpk, "peak_source": tsrc}
     tr = measured_traffic(top_key)
     if tr and tr.get("frames_per_launch") == B:
         roof["traffic"] = tr["bytes_per_launch"]

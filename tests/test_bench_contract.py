@@ -50,3 +50,11 @@ def test_algorithmic_byte_table_matches_the_survey_figures():
               "enc.conv1.bwd/conv3x3", "loss/image_stats", "optimizer/adam", "dec.dense.fwd/dense_wide_fwd"):
         assert tab.get(k, 0) > 0, k
     assert tab["optimizer/adam"] == 7 * 4 * 4_778_429
+    # the general engine's launchers have entries too (per_kernel roofline of the default path)
+    for k in ("enc.conv0.fwd/gen_conv", "enc.conv1.bwd/gen_dgrad", "enc.conv0.bwd/gen_wgrad", "dec.convT.bwd/gen_wgrad",
+              "dec.dense.fwd/gen_dense", "dec.dense.bwd/gen_dense_wgrad", "dec.dense.bwd/gen_dense_dgrad"):
+        assert tab.get(k, 0) > 0, k
+    # 227.0 / 652.0 MFLOP per frame (README config), 15.41 / 45.98 GFLOP (scaled instance)
+    assert bench.flops_per_frame(O.readme_config()) == (227_003_648, 651_980_544)
+    f5 = bench.flops_per_frame(O.scaled_config())
+    assert abs(f5[0] - 15.41e9) < 0.01e9 and abs(f5[1] - 45.98e9) < 0.02e9

@@ -881,7 +881,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
       if (l < L) {
         e.pre = GEN_PRE_BIAS_RELU; e.bias = h->wp(h->vi_dec_convT(l) + 1);
         outp = pl_act_d(h, l + 1, 0); e.out = &outp;
-        g_tag = l == L - 1 ? "dec.convT_last.fwd" : "dec.convT.fwd";
+        g_tag = l == L - 1 ? "dec.convT_last.fwd" : (l == L - 2 ? "dec.convT.fwd" : "dec.convT_early.fwd");
       } else {
         e.pre = apply_sigmoid ? GEN_PRE_BIAS_SIGMOID : GEN_PRE_BIAS; e.bias = h->wp(h->vi_out() + 1);
         e.out_f32 = out;
@@ -929,7 +929,7 @@ void run_decoder(kcvae_model* h, const float* z, int B, int apply_sigmoid, float
     a.B = B; a.Hi = h->dh[l]; a.Wi = h->dw[l]; a.Ci = h->dc[l];
     a.Ho = h->dh[l + 1]; a.Wo = h->dw[l + 1]; a.Co = h->dc[l + 1];
     a.w_sci = 1; a.w_sco = a.Ci;  // [kh,kw,out,in]
-    g_tag = l == L - 1 ? "dec.convT_last.fwd" : "dec.convT.fwd";
+    g_tag = l == L - 1 ? "dec.convT_last.fwd" : (l == L - 2 ? "dec.convT.fwd" : "dec.convT_early.fwd");
 #ifndef KCVAE_EMU
     if (l == L - 2 && few_tc) {
       // 32 -> few Conv2DTranspose on tcgen05: bf16 chunk-planar copy of the input, output straight into the 8-channel
@@ -1165,12 +1165,12 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       GenEpilogue e{};
       e.pre = GEN_PRE_NONE; e.mask = &act;
       if (l > 0) { gout = pl_g_d(h, l); e.out = &gout; } else e.out_f32 = h->g_act_d[0];
-      g_tag = l == L - 1 ? "dec.convT_last.bwd" : "dec.convT.bwd";
+      g_tag = l == L - 1 ? "dec.convT_last.bwd" : (l == L - 2 ? "dec.convT.bwd" : "dec.convT_early.bwd");
       float* px;
       cudaStream_t ax = aux_fork(h, st, &px);      // the incoming gradient is complete on st: the side stream may read it
       if (gen_wgrad_run(g.wgrad, act, gin, h->gp(vi), h->gp(vi + 1), ax == st ? h->gen_partial : h->gen_partial2, B, h->tc_error,
                         "gen_wgrad", ax) != 0) h->tc_failed = true;
-      g_tag = l == L - 1 ? "dec.convT_last.bwd" : "dec.convT.bwd";
+      g_tag = l == L - 1 ? "dec.convT_last.bwd" : (l == L - 2 ? "dec.convT.bwd" : "dec.convT_early.bwd");
       if (gen_conv_run(g.dgrad, gin, h->gen_wimg + g.img_dgrad, e, B, h->tc_error, "gen_dgrad", st) != 0) h->tc_failed = true;
     }
   }
@@ -1237,7 +1237,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
     wa.Hq = h->dh[l + 1]; wa.Wq = h->dw[l + 1]; wa.Cb = h->dc[l + 1];
     wa.s = 2; wa.d = 1; wa.oy = 0; wa.ox = 0;
     wa.o_sa = 1; wa.o_sb = wa.Ca;  // [tap][out=b][in=a]
-    g_tag = l == L - 1 ? "dec.convT_last.bwd" : "dec.convT.bwd";
+    g_tag = l == L - 1 ? "dec.convT_last.bwd" : (l == L - 2 ? "dec.convT.bwd" : "dec.convT_early.bwd");
 #ifndef KCVAE_EMU
     if (l == L - 1 && tail_s2d) {
       if (image_stale(h, 3)) tc_prep_convT_dgrad_weights(h->wp(vi), h->dc[l + 1], h->dc[l], h->wimg_convT_dgrad, st);
