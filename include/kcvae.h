@@ -242,6 +242,9 @@ int kcvae_gen_wgrad_test(int kind, int w_mode, int flip, int s_x3, const float* 
  * out[C][n] = sum_r A[r][n]; mode 2 data gradient out[u][s] = sum_n A[u][n] Bm[s][n].  Used by the parity tests only. */
 int kcvae_gen_dense_test(int mode, int split, int relu, const float* d_a, const float* d_b, const float* d_bias, float* d_out,
                          int R, int N, int C, void* stream);
+/* the host-side plan (MMA list, K slabs, weight gather table / accumulator roles, scatter table) of one product as a flat
+ * int32 array; needs no GPU.  The CPU test-suite interprets it with numpy against the oracle.  Returns the length needed. */
+int64_t kcvae_gen_plan_dump(int which, const int32_t* spec, int nspec, int32_t* out, int64_t capacity);
 
 #ifdef __cplusplus
 }

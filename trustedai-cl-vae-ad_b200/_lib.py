@@ -91,6 +91,7 @@ _SIGS = {
     "kcvae_gen_conv_test": (C.c_int, [C.c_int] * 8 + [_P] * 5 + [C.c_int] * 5 + [_P]),
     "kcvae_gen_wgrad_test": (C.c_int, [C.c_int] * 4 + [_P] * 4 + [C.c_int] * 5 + [_P]),
     "kcvae_gen_dense_test": (C.c_int, [C.c_int] * 3 + [_P] * 4 + [C.c_int] * 3 + [_P]),
+    "kcvae_gen_plan_dump": (C.c_int64, [C.c_int, _P, C.c_int, _P, C.c_int64]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

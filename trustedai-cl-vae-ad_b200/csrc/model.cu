@@ -2546,6 +2546,40 @@ int kcvae_gen_dense_test(int mode, int split, int relu, const float* d_a, const 
 #endif
 }
 
+// Host-side plan of one product of the general engine as a flat int32 array (no GPU needed): the CPU test-suite interprets
+// the MMA list / gather table / scatter table with numpy (tests/engine_sim.py) and checks the planner against the oracle.
+// which 0: spec = {kind, in_layout, Ck, Cn, KCk, w_mode, flip, split, w_stride, ones_col1, ones_src, w_col0, Hg, Wg}
+// which 1: spec = {kind, flip, s_layout, s_KC, u_layout, u_KC, Cs, Cu, w_mode, Hg, Wg}
+int64_t kcvae_gen_plan_dump(int which, const int32_t* spec, int nspec, int32_t* out, int64_t capacity) {
+#ifdef KCVAE_EMU
+  (void)which; (void)spec; (void)nspec; (void)out; (void)capacity;
+  return fail(nullptr, KCVAE_ERR_UNSUPPORTED, "emu: the engine's planners live in the CUDA library");
+#else
+  const char* why = "";
+  if (!spec) return fail(nullptr, KCVAE_ERR_INVALID, "gen_plan_dump: null spec");
+  if (which == 0) {
+    if (nspec < 14) return fail(nullptr, KCVAE_ERR_INVALID, "gen_plan_dump: 14 spec entries expected");
+    GenConvSpec s{};
+    s.kind = spec[0]; s.in_layout = spec[1]; s.Ck = spec[2]; s.Cn = spec[3]; s.KCk = spec[4]; s.w_mode = spec[5]; s.flip = spec[6];
+    s.split = spec[7]; s.w_stride = spec[8]; s.ones_col1 = spec[9]; s.ones_src = spec[10]; s.w_col0 = spec[11]; s.Hg = spec[12]; s.Wg = spec[13];
+    GenConvPlan* p = gen_conv_plan_create(s, &why, false);
+    if (!p) return fail(nullptr, KCVAE_ERR_UNSUPPORTED, std::string("gen_plan_dump: ") + why);
+    const int64_t n = gen_conv_plan_dump(p, out, capacity);
+    gen_conv_plan_free(p);
+    return n;
+  }
+  if (nspec < 11) return fail(nullptr, KCVAE_ERR_INVALID, "gen_plan_dump: 11 spec entries expected");
+  GenWgradSpec s{};
+  s.kind = spec[0]; s.flip = spec[1]; s.s_layout = spec[2]; s.s_KC = spec[3]; s.u_layout = spec[4]; s.u_KC = spec[5]; s.Cs = spec[6];
+  s.Cu = spec[7]; s.w_mode = spec[8]; s.Hg = spec[9]; s.Wg = spec[10];
+  GenWgradPlan* p = gen_wgrad_plan_create(s, &why, false);
+  if (!p) return fail(nullptr, KCVAE_ERR_UNSUPPORTED, std::string("gen_plan_dump: ") + why);
+  const int64_t n = gen_wgrad_plan_dump(p, out, capacity);
+  gen_wgrad_plan_free(p);
+  return n;
+#endif
+}
+
 #ifdef KCVAE_EMU
 // tests only: route the data-parallel all-reduce through a host callback (gloo in pytest)
 void kcvae_emu_set_allreduce(void (*fn)(void*, int64_t, int, int)) { g_emu_allreduce = fn; }

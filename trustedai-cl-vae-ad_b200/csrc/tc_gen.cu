@@ -503,7 +503,7 @@ struct GenConvPlan {
   size_t smem = 0;
 };
 
-GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
+GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not, bool upload) {
   static const char* msg = "";
   auto no = [&](const char* m) -> GenConvPlan* { msg = m; if (why_not) *why_not = msg; return nullptr; };
   if (s.Ck <= 0 || s.Cn <= 0 || s.Hg <= 0 || s.Wg <= 0) return no("empty shape");
@@ -669,6 +669,7 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
   D.stage_bytes = (uint32_t)(((size_t)D.a_region + worst_b + 1023) / 1024 * 1024);
   P->smem = G1_PLAN_BYTES + (size_t)G1_STAGES * D.stage_bytes;
   if (P->smem > 227 * 1024) { delete P; return no("shared-memory plan too large"); }
+  if (!upload) return P;
   if (cudaMalloc(reinterpret_cast<void**>(&P->dev), sizeof(G1PlanDev)) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&P->table_dev), std::max<size_t>(T.size(), 1) * sizeof(int32_t)) != cudaSuccess) {
     gen_conv_plan_free(P);
@@ -677,6 +678,26 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not) {
   cudaMemcpy(P->dev, &D, sizeof(G1PlanDev), cudaMemcpyHostToDevice);
   cudaMemcpy(P->table_dev, T.data(), T.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   return P;
+}
+
+int64_t gen_conv_plan_dump(const GenConvPlan* p, int32_t* out, int64_t capacity) {
+  const G1PlanDev& D = p->host;
+  std::vector<int32_t> v = {1, D.n_groups, D.MT, D.NB, D.acc_cols, D.R_in, D.row0, D.col0, D.TW, D.in_PL, D.n_slabs, D.n_mma, D.type,
+                            (int32_t)D.CHb, (int32_t)D.a_region, (int32_t)D.stage_bytes, (int32_t)D.Cop};
+  for (int g = 0; g < 2; ++g) { v.push_back(D.groups[g].slab0); v.push_back(D.groups[g].slab_n); v.push_back(D.groups[g].a_par); }
+  for (int i = 0; i < D.n_slabs; ++i) {
+    const G1Slab& S = D.slabs[i];
+    v.insert(v.end(), {S.mma0, S.mma_n, S.nplanes, S.b_src, S.b_bytes});
+    for (int k = 0; k < G1_MAXPL; ++k) v.push_back(S.plane[k]);
+  }
+  for (int i = 0; i < D.n_mma; ++i) {
+    const G1Mma& M = D.mma[i];
+    v.insert(v.end(), {(int32_t)M.a_lo, (int32_t)M.b_lo, (int32_t)M.idesc, (int32_t)M.dcol_acc});
+  }
+  v.push_back((int32_t)p->table.size());
+  v.insert(v.end(), p->table.begin(), p->table.end());
+  if (out && capacity >= (int64_t)v.size()) memcpy(out, v.data(), v.size() * sizeof(int32_t));
+  return (int64_t)v.size();
 }
 
 void gen_conv_plan_free(GenConvPlan* p) {
@@ -710,7 +731,7 @@ static PlaneRef plane_ref(const GenPlanes& t) {
 
 int gen_conv_run(const GenConvPlan* P, const GenPlanes& in, const void* wimg, const GenEpilogue& e, int B, int* error_flag,
                  const char* name, cudaStream_t st) {
-  if (!gen_encode_fn()) return 1;
+  if (!gen_encode_fn() || !P->dev) return 1;
   const GenConvSpec& s = P->spec;
   const G1PlanDev& D = P->host;
   // a non-split plan may read the hi planes of a split tensor; a split plan needs the lo planes right behind the hi planes
@@ -957,7 +978,7 @@ struct GenWgradPlan {
   size_t smem = 0;
 };
 
-GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not) {
+GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not, bool upload) {
   static const char* msg = "";
   auto no = [&](const char* m) -> GenWgradPlan* { msg = m; if (why_not) *why_not = msg; return nullptr; };
   const int nS = hi_planes(s.s_layout, s.s_KC), nU = hi_planes(s.u_layout, s.u_KC);
@@ -1214,6 +1235,7 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
     }
   }
   for (size_t e = 0; e < (size_t)P->EW; ++e) if (P->src[e * 4] < 0) { delete P; return no("internal: a weight-gradient element has no accumulator"); }
+  if (!upload) return P;
   if (cudaMalloc(reinterpret_cast<void**>(&P->dev), sizeof(G2PlanDev)) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&P->src_dev), P->src.size() * sizeof(int32_t)) != cudaSuccess) {
     gen_wgrad_plan_free(P);
@@ -1222,6 +1244,29 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not)
   cudaMemcpy(P->dev, &D, sizeof(G2PlanDev), cudaMemcpyHostToDevice);
   cudaMemcpy(P->src_dev, P->src.data(), P->src.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
   return P;
+}
+
+int64_t gen_wgrad_plan_dump(const GenWgradPlan* p, int32_t* out, int64_t capacity) {
+  const G2PlanDev& D = p->host;
+  std::vector<int32_t> v = {2, D.n_roles, D.TRr, D.R_s, D.row0, D.col0, D.TW, D.s_PL, D.u_PL, (int32_t)D.CHs, (int32_t)D.CHu,
+                            (int32_t)D.s_region, (int32_t)D.u_region, (int32_t)D.stage_bytes, (int32_t)D.ones_off, p->EW, p->spec.Cu};
+  int n_mma = 0;
+  for (int r = 0; r < D.n_roles; ++r) {
+    const G2Role& R = D.roles[r];
+    v.insert(v.end(), {R.mma0, R.mma_n, R.nS, R.nU, R.ncols});
+    for (int k = 0; k < G2_MAXPL; ++k) v.push_back(R.s_plane[k]);
+    for (int k = 0; k < G2_MAXPL; ++k) v.push_back(R.u_plane[k]);
+    n_mma = std::max(n_mma, R.mma0 + R.mma_n);
+  }
+  v.push_back(n_mma);
+  for (int i = 0; i < n_mma; ++i) {
+    const G2Mma& M = D.mma[i];
+    v.insert(v.end(), {(int32_t)M.a_lo, (int32_t)M.a_hi, (int32_t)M.b_lo, (int32_t)M.b_hi, (int32_t)M.idesc, (int32_t)M.d_col, (int32_t)M.b_ones});
+  }
+  v.push_back((int32_t)p->src.size());
+  v.insert(v.end(), p->src.begin(), p->src.end());
+  if (out && capacity >= (int64_t)v.size()) memcpy(out, v.data(), v.size() * sizeof(int32_t));
+  return (int64_t)v.size();
 }
 
 void gen_wgrad_plan_free(GenWgradPlan* p) {
@@ -1234,7 +1279,7 @@ size_t gen_wgrad_partial_floats(const GenWgradPlan*) { return (size_t)kNumSMs * 
 
 int gen_wgrad_run(const GenWgradPlan* P, const GenPlanes& S, const GenPlanes& U, float* dW, float* db, float* partial, int B,
                   int* error_flag, const char* name, cudaStream_t st) {
-  if (!gen_encode_fn()) return 1;
+  if (!gen_encode_fn() || !P->dev) return 1;
   const GenWgradSpec& s = P->spec;
   const G2PlanDev& D = P->host;
   CUtensorMap ms, mu;

@@ -45,7 +45,10 @@ struct GenConvSpec {
 };
 
 struct GenConvPlan;   // opaque: device-resident MMA list, weight gather table, tile geometry
-GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not);
+// upload = false: host-side plan only (no device copies): what kcvae_gen_plan_dump hands to the CPU-side plan simulator
+GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not, bool upload = true);
+// flat int32 description of a plan (tests/engine_sim.py documents the layout); returns the length needed
+int64_t gen_conv_plan_dump(const GenConvPlan* p, int32_t* out, int64_t capacity);
 void gen_conv_plan_free(GenConvPlan* p);
 size_t gen_conv_weight_image_bytes(const GenConvPlan* p);
 int gen_conv_Cop(const GenConvPlan* p);          // padded N channels (per parity)
@@ -93,7 +96,8 @@ struct GenWgradSpec {
   int Hg, Wg;          // pixel grid both operands are indexed on (plane dims of U)
 };
 struct GenWgradPlan;
-GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not);
+GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not, bool upload = true);
+int64_t gen_wgrad_plan_dump(const GenWgradPlan* p, int32_t* out, int64_t capacity);
 void gen_wgrad_plan_free(GenWgradPlan* p);
 size_t gen_wgrad_partial_floats(const GenWgradPlan* p);
 // dW (9*Cs*Cu floats) and db (Cu floats, may be nullptr) from S (shifted input planes) and U (gradient planes)
