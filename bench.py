@@ -213,6 +213,11 @@ def algorithmic_bytes(cfg, B, world):
     tab["dec.dense.fwd/gen_dense"] = tab["dec.dense.fwd/gemm"]
     tab["dec.dense.bwd/gen_dense_wgrad"] = B * (4 * t.latent + act * dec[0]) + wd
     tab["dec.dense.bwd/gen_dense_dgrad"] = B * (4 * t.latent + act * dec[0]) + wd
+    if t.enc_dense:
+        we = 4 * nW["encoder/dense/kernel"]
+        tab["enc.dense.fwd/gen_edense"] = B * (act * enc[L] + 4 * t.enc_dense) + we
+        tab["enc.dense.bwd/gen_edense_wgrad"] = B * (act * enc[L] + 4 * t.enc_dense) + we
+        tab["enc.dense.bwd/gen_edense_dgrad"] = B * (2 * act * enc[L] + 4 * t.enc_dense) + we
     tab["dec.dense.fwd/dense_wide_fwd"] = tab["dec.dense.fwd/gemm"]
     tab["dec.dense.bwd/dense_wide_wgrad"] = B * (4 * t.latent + act * dec[0]) + wd     # z, G in; dW (+ bias grad) out
     tab["dec.dense.bwd/dense_wide_dgrad"] = B * (4 * t.latent + act * dec[0]) + wd     # G, W in; dz out
@@ -426,6 +431,7 @@ def roofline_from_profile(rep, tab, step_bytes, ms_per_step, K):
     step_ach = step_bytes / (ms_per_step * 1e-3) / 1e9
     roof["whole_step"] = {"algorithmic_bytes": step_bytes, "achieved": step_ach, "frac": step_ach / peak}
     roof["kernel_breakdown_ms_per_step"] = {k: round(v[1] / K, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])[:14]}
+    roof["all_launchers_ms_per_step"] = {k: round(v[1] / K, 4) for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1])}
     roof["per_kernel"] = [
         {"kernel": k, "ms": round(v[1] / v[0], 4), "GBps": round(tab[k] / (v[1] / v[0] * 1e-3) / 1e9, 1),
          "frac": round(tab[k] / (v[1] / v[0] * 1e-3) / 1e9 / peak, 3)}

@@ -192,3 +192,33 @@ def test_planner_refuses_what_the_kernels_cannot_run():
         _wgrad_plan(S.CONV_S2, 0, S.S2D, 2, S.PLAIN, 2, 16, 16, 0, 8, 37)              # 37 has no divisor in [8, 31]
     with pytest.raises(RuntimeError, match="S2D / X3 input"):
         _conv_plan(S.CONV_S2, S.PLAIN, 16, 16, 2, 0, 0, 0, 8, 8)
+
+
+def test_long_k_dense_forward_plan_with_hi_lo_quadrants():
+    """encoder Dense (src/abstract_cvae.py:41-44) as a pixel-K product: K = the flattened activation (padded to a multiple of 32
+    with a "ones pixel" that carries the bias), both tensors with lo planes behind the hi planes, every output the sum of the
+    hi*hi, hi*lo and lo*hi accumulators."""
+    rng = np.random.default_rng(61)
+    F, E, B = 75, 16, 5
+    Fp = (F + 1 + 31) // 32 * 32
+    flat, Wm, bias = rng.random((B, F), dtype=np.float32), _rand(rng, F, E, scale=0.3), _rand(rng, E, scale=0.1)
+    KCb, KCe = (B + 7) // 8, (E + 7) // 8
+    xh, xl = S.hi_lo(flat)
+    wh, wl = S.hi_lo(Wm)
+    bh, bl = S.hi_lo(bias)
+    U = np.zeros((1, 2 * KCb, Fp // 32, 32, 8))           # [hi | lo][i][8 frames]
+    Sp = np.zeros((1, 2 * KCe, Fp // 32, 32, 8))          # [hi | lo][i][8 outputs]
+    Uf, Sf = U.reshape(1, 2 * KCb, Fp, 8), Sp.reshape(1, 2 * KCe, Fp, 8)
+    for b in range(B):
+        Uf[0, b // 8, :F, b % 8] = xh[b]
+        Uf[0, KCb + b // 8, :F, b % 8] = xl[b]
+        Uf[0, b // 8, F, b % 8] = 1.0                      # the ones pixel
+    for e in range(E):
+        Sf[0, e // 8, :F, e % 8] = wh[:, e]
+        Sf[0, KCe + e // 8, :F, e % 8] = wl[:, e]
+        Sf[0, e // 8, F, e % 8] = bh[e]
+        Sf[0, KCe + e // 8, F, e % 8] = bl[e]
+    plan = S.WgradPlan(S.dump(1, [S.DENSE, 0, S.PLAIN, 2 * KCe, S.PLAIN, 2 * KCb, E, B, 1, Fp // 32, 32, 1]))
+    out, _ = S.run_wgrad(plan, Sp, U, Fp // 32, 32)
+    want = flat.astype(np.float64) @ Wm.astype(np.float64) + bias
+    assert _rel(out.reshape(B, E), want) < 5e-5

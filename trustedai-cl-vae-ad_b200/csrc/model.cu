@@ -190,6 +190,20 @@ struct kcvae_model {
     size_t off_fwd = 0, off_fwd_split = 0;
   };
   std::vector<DensePlans> dense_plans;
+  // encoder Dense (flatten -> enc_dense units) on the engine: forward = a pixel-K product over the flattened activation
+  // (K = flat, hi + lo quadrants, bias through a ones pixel); weight and data gradients = GEN_DENSE forward-type products
+  bool gen_edense = false, xT_live = false;
+  int ed_F = 0, ed_Fp = 0, ed_E = 0;
+  void *xT_pl = nullptr, *wE_pl = nullptr;
+  uint64_t wE_version = 0;
+  struct EncDensePlans {
+    int B = 0;
+    GenWgradPlan* fwd = nullptr;
+    GenConvPlan *wgrad = nullptr, *dgrad = nullptr;
+    unsigned char* img = nullptr;
+    size_t off_wgrad = 0, off_dgrad = 0;
+  };
+  std::vector<EncDensePlans> edense_plans;
 #endif
   // data parallel
   int rank = 0, world = 1;
@@ -429,6 +443,19 @@ int gen_setup(kcvae_model* h) {
                    h->vars[vi + 1].off == h->vars[vi].off + (int64_t)h->latent * h->dec_units;     // dW and db contiguous: one product writes both
     if (h->gen_dense) KC_TRY_SETUP(gen_alloc(h, &h->wT_pl, (size_t)2 * ((h->latent + 7) / 8) * h->dec_units));
   }
+  {
+    const char* gd = std::getenv("KCVAE_GEN_DENSE");
+    // the Dense right behind Flatten: K = flat (thousands), few outputs; the 16 -> 64 head behind it stays a CUDA-core GEMM
+    // measured at 256 frames (profiles/r03_b_*): forward 0.061 ms and backward 0.12 ms through the engine against 0.042 / 0.09 ms for
+    // the split-K CUDA-core GEMMs (K = 21,000, 16 outputs: no reuse for a tensor core to exploit) - implemented, verified,
+    // and OFF unless KCVAE_GEN_EDENSE=1
+    const char* ge = std::getenv("KCVAE_GEN_EDENSE");
+    h->gen_edense = h->gen_enc && h->enc_dense > 0 && h->enc_dense <= 128 && h->flat >= 1024 && !(gd && gd[0] == '0') && ge && ge[0] == '1';
+    if (h->gen_edense) {
+      h->ed_F = h->flat; h->ed_E = h->enc_dense; h->ed_Fp = (h->flat + 1 + 31) / 32 * 32;
+      KC_TRY_SETUP(gen_alloc(h, &h->wE_pl, (size_t)2 * ((h->ed_E + 7) / 8) * h->ed_Fp));
+    }
+  }
   if (!h->gen_enc && !h->gen_dec && !h->gen_dec0) return KCVAE_OK;
   // ---- weight images: one gather table for all plans
   for (int l = 0; l < L && h->gen_enc; ++l) {
@@ -538,6 +565,11 @@ void dense_refresh_wT(kcvae_model* h, cudaStream_t st) {
 }
 // relu(z W + b) -> the bf16 image of the Dense output (planes_out, hi + lo when split) and / or fp32 [B][N]
 bool gen_dense_forward(kcvae_model* h, const float* z, int B, int split, void* planes_out, float* f32_out, cudaStream_t st) {
+  // measured at 256 frames (profiles/r03_b_*): 0.147 ms here (W^T pack, z gather, product with its transposing 2-byte stores)
+  // against 0.104 ms for the streaming CUDA-core kernel, which writes the same hi + lo planes: the forward stays there unless
+  // asked for; the two backward products (0.12 ms against 0.30 ms) are the ones that run on the engine by default
+  const char* fw = std::getenv("KCVAE_GEN_DENSE_FWD");
+  if (!(fw && fw[0] == '1')) return false;
   kcvae_model::DensePlans* dp = dense_plans_get(h, B);
   if (!dp || !dp->fwd) return false;
   const int vi = h->vi_dec_dense(), K = h->latent, N = h->dec_units;
@@ -552,6 +584,60 @@ bool gen_dense_forward(kcvae_model* h, const float* z, int B, int split, void* p
   e.out = planes_out ? &outp : nullptr; e.out_f32 = f32_out;
   e.dense_n = N; e.dense_ld = N; e.dense_cc = h->dc[0];
   if (gen_conv_run(plan, in, img, e, 1, h->tc_error, "gen_dense", st) != 0) h->tc_failed = true;
+  return true;
+}
+
+// ---- encoder Dense (src/abstract_cvae.py:41-44) on the engine ---------------------------------------------------------
+void edense_plans_free(kcvae_model::EncDensePlans& d) {
+  gen_wgrad_plan_free(d.fwd); gen_conv_plan_free(d.wgrad); gen_conv_plan_free(d.dgrad);
+  if (d.img) cudaFree(d.img);
+  d = kcvae_model::EncDensePlans();
+}
+kcvae_model::EncDensePlans* edense_plans_get(kcvae_model* h, int B) {
+  const char* mb = std::getenv("KCVAE_GEN_DENSE_MIN_BATCH");
+  const int min_batch = mb ? std::atoi(mb) : 64;
+  if (!h->gen_edense || B > 256 || B < min_batch) return nullptr;
+  for (auto& d : h->edense_plans) if (d.B == B) return &d;
+  const int F = h->ed_F, Fp = h->ed_Fp, E = h->ed_E, KCb = (B + 7) / 8, KCe = (E + 7) / 8;
+  const char* why = "";
+  kcvae_model::EncDensePlans d;
+  d.B = B;
+  GenWgradSpec f{};        // d1[b][e] = sum_i flat[b][i] W[i][e] + bias[e]: S = weight planes, U = transposed activation planes
+  f.kind = GEN_DENSE; f.s_layout = GEN_PLAIN; f.s_KC = 2 * KCe; f.u_layout = GEN_PLAIN; f.u_KC = 2 * KCb; f.Cs = E; f.Cu = B; f.w_mode = 1;
+  f.Hg = Fp / 32; f.Wg = 32; f.split_dense = 1;
+  d.fwd = gen_wgrad_plan_create(f, &why);
+  GenConvSpec w{};         // dW[i][e] = sum_b flat[b][i] g[b][e]: rows i, K = frames, columns e
+  w.kind = GEN_DENSE; w.in_layout = GEN_PLAIN; w.Ck = B; w.KCk = KCb; w.Cn = E; w.w_mode = 0; w.w_stride = E; w.Hg = Fp / 32; w.Wg = 32;
+  d.wgrad = gen_conv_plan_create(w, &why);
+  GenConvSpec g{};         // g_flat[b][i] = sum_e g[b][e] W[i][e]: rows i, K = e, columns b
+  g.kind = GEN_DENSE; g.in_layout = GEN_PLAIN; g.Ck = E; g.KCk = KCe; g.Cn = B; g.w_mode = 1; g.w_stride = E; g.Hg = Fp / 32; g.Wg = 32;
+  d.dgrad = gen_conv_plan_create(g, &why);
+  bool ok = d.fwd && d.wgrad && d.dgrad;
+  if (ok) {
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    d.off_wgrad = 0;
+    d.off_dgrad = up(gen_conv_weight_image_bytes(d.wgrad));
+    ok = cudaMalloc(reinterpret_cast<void**>(&d.img), d.off_dgrad + up(gen_conv_weight_image_bytes(d.dgrad)) + 256) == cudaSuccess;
+  }
+  if (!ok) { edense_plans_free(d); return nullptr; }
+  h->edense_plans.push_back(d);
+  return &h->edense_plans.back();
+}
+// d1 = flat W + b (linear) through the engine; false = not taken (the CUDA-core GEMM runs)
+bool gen_edense_forward(kcvae_model* h, const float* flat, int B, float* out, cudaStream_t st) {
+  h->xT_live = false;
+  kcvae_model::EncDensePlans* ep = edense_plans_get(h, B);
+  if (!ep || !h->xT_pl) return false;
+  const int vi = h->vi_enc_dense(), F = h->ed_F, Fp = h->ed_Fp, E = h->ed_E;
+  if (h->w_external || h->wE_version != h->w_version) {       // weight planes (hi + lo) with the bias in the ones pixel
+    gen_pack_cols(h->wp(vi), h->wp(vi + 1), F, E, 1, h->wE_pl, Fp, F, st);
+    h->wE_version = h->w_version;
+  }
+  gen_pack_rows_T(flat, B, F, 1, h->xT_pl, st, Fp, F);         // [frames / 8 (hi | lo)][flat index][8 frames], ones pixel at index F
+  GenPlanes S = pl_make(h->wE_pl, GEN_PLAIN, 2 * ((E + 7) / 8), 0, Fp / 32, 32);
+  GenPlanes U = pl_make(h->xT_pl, GEN_PLAIN, 2 * ((B + 7) / 8), 0, Fp / 32, 32);
+  if (gen_wgrad_run(ep->fwd, S, U, out, nullptr, h->gen_partial, 1, h->tc_error, "gen_edense", st) != 0) h->tc_failed = true;
+  h->xT_live = true;
   return true;
 }
 #endif
@@ -617,6 +703,7 @@ int ensure_fwd(kcvae_model* h, int B) {
   for (int l = 0; l <= L; ++l)
     if (!gen_dec) KC_TRY(dalloc(h, &h->act_d[l], (size_t)B * h->dh[l] * h->dw[l] * h->dc[l]));
 #ifndef KCVAE_EMU
+  if (h->gen_edense) KC_TRY(gen_alloc(h, &h->xT_pl, (size_t)2 * ((B + 7) / 8) * h->ed_Fp));
   if (gen_enc) {
     h->act_e_pl.resize(L + 1, nullptr);
     KC_TRY(gen_alloc(h, &h->x_pl, pl_x(h, 1).units(B)));
@@ -819,6 +906,9 @@ void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st, int spl
     ga.C = h->d1; ga.bias = h->wp(h->vi_enc_dense() + 1);
     ga.M = B; ga.N = h->enc_dense; ga.K = k; ga.partial = h->partial;
     g_tag = "enc.dense.fwd";
+#ifndef KCVAE_EMU
+    if (!gen_edense_forward(h, flat, B, h->d1, st))
+#endif
     gemm(ga, st);
     flat = h->d1; k = h->enc_dense;
   }
@@ -1370,6 +1460,29 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       gemm(gi, st);
     }
   }
+#ifndef KCVAE_EMU
+  kcvae_model::EncDensePlans* edp = (h->enc_dense && h->xT_live && g_flat) ? edense_plans_get(h, B) : nullptr;
+  if (edp) {
+    // encoder Dense backward on the engine: dW[i][e] over the transposed activation planes the forward wrote (side stream),
+    // g_flat[b][i] over the weight planes with the ReLU mask of the flattened activation; db = column sums of g (tiny)
+    const int vi = h->vi_enc_dense(), F = h->ed_F, Fp = h->ed_Fp, E = h->ed_E;
+    g_tag = "enc.dense.bwd";
+    float* px;
+    cudaStream_t ax = aux_fork(h, st, &px);
+    gen_conv_prep_weights(edp->wgrad, h->g_d1, edp->img + edp->off_wgrad, ax);
+    GenPlanes xT = pl_make(h->xT_pl, GEN_PLAIN, (B + 7) / 8, 1, Fp / 32, 32);
+    GenEpilogue ew{};
+    ew.pre = GEN_PRE_NONE; ew.out_f32 = h->gp(vi); ew.dense_n = F; ew.dense_ld = E; ew.dense_tr = 1; ew.dense_cc = 32;
+    if (gen_conv_run(edp->wgrad, xT, edp->img + edp->off_wgrad, ew, 1, h->tc_error, "gen_edense_wgrad", ax) != 0) h->tc_failed = true;
+    colsum(h->g_d1, B, h->enc_dense, h->gp(vi + 1), px, ax);
+    g_tag = "enc.dense.bwd";
+    gen_conv_prep_weights(edp->dgrad, h->g_d1, edp->img + edp->off_dgrad, st);
+    GenPlanes wE = pl_make(h->wE_pl, GEN_PLAIN, (E + 7) / 8, 1, Fp / 32, 32);
+    GenEpilogue eg{};
+    eg.pre = GEN_PRE_NONE; eg.out_f32 = g_flat; eg.mask_f32 = relu_mask; eg.dense_n = F; eg.dense_ld = F; eg.dense_cc = 32;
+    if (gen_conv_run(edp->dgrad, wE, edp->img + edp->off_dgrad, eg, 1, h->tc_error, "gen_edense_dgrad", st) != 0) h->tc_failed = true;
+  } else
+#endif
   if (h->enc_dense) {
     const int vi = h->vi_enc_dense();
     g_tag = "enc.dense.bwd";
@@ -1512,7 +1625,7 @@ int step_impl(kcvae_model* h, const float* d_x, int B, const float* d_eps, const
     for (int k = 0; k < 4; ++k) h->img_version[k] = h->w_version;
   }
   const bool ext = h->w_external;
-  if (ext) { h->gen_img_version = 0; h->wT_version = 0; }   // weights may have been written behind the library's back: the engine's images are rebuilt in this step
+  if (ext) { h->gen_img_version = 0; h->wT_version = 0; h->wE_version = 0; }   // weights may have been written behind the library's back: the engine's images are rebuilt in this step
   h->w_external = false;          // the images built above are current for this step
 #endif
   float* xh = d_xhat ? d_xhat : h->xhat;
@@ -1667,6 +1780,9 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->x_pl) cudaFree(h->x_pl);
   for (auto* v : {&h->act_e_pl, &h->g_e_pl, &h->act_d_pl, &h->g_d_pl}) for (void* q : *v) if (q) cudaFree(q);
   for (auto& d : h->dense_plans) dense_plans_free(d);
+  for (auto& d : h->edense_plans) edense_plans_free(d);
+  if (h->xT_pl) cudaFree(h->xT_pl);
+  if (h->wE_pl) cudaFree(h->wE_pl);
   if (h->wT_pl) cudaFree(h->wT_pl);
   if (h->gT_pl) cudaFree(h->gT_pl);
   if (h->gen_partial) cudaFree(h->gen_partial);
@@ -2572,6 +2688,7 @@ int64_t kcvae_gen_plan_dump(int which, const int32_t* spec, int nspec, int32_t* 
   GenWgradSpec s{};
   s.kind = spec[0]; s.flip = spec[1]; s.s_layout = spec[2]; s.s_KC = spec[3]; s.u_layout = spec[4]; s.u_KC = spec[5]; s.Cs = spec[6];
   s.Cu = spec[7]; s.w_mode = spec[8]; s.Hg = spec[9]; s.Wg = spec[10];
+  if (nspec > 11) s.split_dense = spec[11];
   GenWgradPlan* p = gen_wgrad_plan_create(s, &why, false);
   if (!p) return fail(nullptr, KCVAE_ERR_UNSUPPORTED, std::string("gen_plan_dump: ") + why);
   const int64_t n = gen_wgrad_plan_dump(p, out, capacity);

@@ -111,7 +111,7 @@ struct G1Params {
   PlaneRef out; int has_out, out_lo;
   float* out_f32;
   int Cn;            // real N-side channels
-  int dense_n, dense_ld, dense_cc;   // GEN_DENSE epilogue (see GenEpilogue)
+  int dense_n, dense_ld, dense_cc, dense_tr;   // GEN_DENSE epilogue (see GenEpilogue)
   int Ho, Wo;        // logical output dims
   int* error_flag;
 };
@@ -382,7 +382,9 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
               if (j < ncols && col < p.Cn) {
                 float y = v[j] + rb;
                 if (p.pre == GEN_PRE_BIAS_RELU) y = fmaxf(y, 0.f);
-                if (p.out_f32) p.out_f32[(int64_t)col * p.dense_ld + n_row] = y;
+                const int64_t oi = p.dense_tr ? (int64_t)n_row * p.dense_ld + col : (int64_t)col * p.dense_ld + n_row;
+                if (p.mask_f32 && !(__ldg(p.mask_f32 + oi) > 0.f)) y = 0.f;
+                if (p.out_f32) p.out_f32[oi] = y;
                 if (p.has_out) {
                   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out.base);
                   const __nv_bfloat16 hi = __float2bfloat16(y);
@@ -753,7 +755,7 @@ int gen_conv_run(const GenConvPlan* P, const GenPlanes& in, const void* wimg, co
   if (e.out) { p.out = plane_ref(*e.out); p.out_lo = e.out->split; }
   p.out_f32 = e.out_f32;
   p.Cn = s.Cn;
-  p.dense_n = e.dense_n; p.dense_ld = e.dense_ld; p.dense_cc = e.dense_cc > 0 ? e.dense_cc : 1;
+  p.dense_n = e.dense_n; p.dense_ld = e.dense_ld; p.dense_cc = e.dense_cc > 0 ? e.dense_cc : 1; p.dense_tr = e.dense_tr;
   p.Ho = s.kind == GEN_CONVT_S2 ? 2 * s.Hg : s.Hg;
   p.Wo = s.kind == GEN_CONVT_S2 ? 2 * s.Wg : s.Wg;
   p.error_flag = error_flag;
@@ -1205,8 +1207,12 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not,
   P->EW = (s.kind == GEN_DENSE ? 1 : 9) * Cs * Cu;
   P->src.assign((size_t)(P->EW + Cu) * 4, -1);
   if (s.kind == GEN_DENSE) {       // out[(cs, cu)]: w_mode 0 -> cs * Cu + cu ; 1 -> cu * Cs + cs
-    for (int cs = 0; cs < Cs; ++cs) for (int cu = 0; cu < Cu; ++cu)
-      P->src[(size_t)(s.w_mode == 0 ? cs * Cu + cu : cu * Cs + cs) * 4] = find(0, cs, cu, false);
+    const int sh = s.split_dense ? s.s_KC / 2 * 8 : 0, uh = s.split_dense ? s.u_KC / 2 * 8 : 0;   // element offsets of the lo halves
+    for (int cs = 0; cs < Cs; ++cs) for (int cu = 0; cu < Cu; ++cu) {
+      int32_t* e = &P->src[(size_t)(s.w_mode == 0 ? cs * Cu + cu : cu * Cs + cs) * 4];
+      e[0] = find(0, cs, cu, false);
+      if (s.split_dense) { e[1] = find(0, cs + sh, cu, false); e[2] = find(0, cs, cu + uh, false); }
+    }
   } else
   for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) for (int cs = 0; cs < Cs; ++cs) for (int cu = 0; cu < Cu; ++cu) {
     int tap_i, es, eu;
@@ -1384,14 +1390,15 @@ __global__ void gen_unpack_nhwc_kernel(PlaneRef in, int split, int B, int H, int
 
 namespace {
 // one thread per (chunk, n): 8 loads with stride N (coalesced across the warp), one 16-byte store (two when split)
-__global__ void gen_pack_rows_T_kernel(const float* __restrict__ in, int R, int N, int split, uint4* out) {
+__global__ void gen_pack_rows_T_kernel(const float* __restrict__ in, int R, int N, int split, uint4* out, int Np, int ones_n) {
   const int KC = (R + 7) / 8;
-  const int64_t total = (int64_t)KC * N;
+  const int64_t total = (int64_t)KC * Np;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int n = (int)(i % N), chunk = (int)(i / N);
+    const int n = (int)(i % Np), chunk = (int)(i / Np);
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = chunk * 8 + k < R ? __ldg(in + (int64_t)(chunk * 8 + k) * N + n) : 0.f;
+    for (int k = 0; k < 8; ++k)
+      v[k] = chunk * 8 + k < R ? (n < N ? __ldg(in + (int64_t)(chunk * 8 + k) * N + n) : (n == ones_n ? 1.f : 0.f)) : 0.f;
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -1403,10 +1410,40 @@ __global__ void gen_pack_rows_T_kernel(const float* __restrict__ in, int R, int 
   }
 }
 }  // namespace
-void gen_pack_rows_T(const float* in, int R, int N, int split, void* out, cudaStream_t st) {
+void gen_pack_rows_T(const float* in, int R, int N, int split, void* out, cudaStream_t st, int Np, int ones_n) {
   ProfScope prof_("gen_pack_rows_T", st);
   ++g_launches;
-  gen_pack_rows_T_kernel<<<grid_for((int64_t)((R + 7) / 8) * N, 256, 8, 4), 256, 0, st>>>(in, R, N, split, reinterpret_cast<uint4*>(out));
+  if (Np < N) Np = N;
+  gen_pack_rows_T_kernel<<<grid_for((int64_t)((R + 7) / 8) * Np, 256, 8, 4), 256, 0, st>>>(in, R, N, split, reinterpret_cast<uint4*>(out), Np, ones_n);
+}
+namespace {
+__global__ void gen_pack_cols_kernel(const float* __restrict__ in, const float* __restrict__ bias, int N, int C, int split, uint4* out,
+                                     int Np, int ones_n) {
+  const int KC = (C + 7) / 8;
+  const int64_t total = (int64_t)KC * Np;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % Np), chunk = (int)(i / Np);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = chunk * 8 + k;
+      v[k] = c < C ? (n < N ? __ldg(in + (int64_t)n * C + c) : ((n == ones_n && bias) ? __ldg(bias + c) : 0.f)) : 0.f;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      lo[e] = pack_bf16x2(v[2 * e] - __uint_as_float(hi[e] << 16), v[2 * e + 1] - __uint_as_float(hi[e] & 0xFFFF0000u));
+    }
+    out[i] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (split) out[total + i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+}  // namespace
+void gen_pack_cols(const float* in, const float* bias, int N, int C, int split, void* out, int Np, int ones_n, cudaStream_t st) {
+  ProfScope prof_("gen_pack_cols", st);
+  ++g_launches;
+  gen_pack_cols_kernel<<<grid_for((int64_t)((C + 7) / 8) * Np, 256, 8, 4), 256, 0, st>>>(in, bias, N, C, split, reinterpret_cast<uint4*>(out), Np, ones_n);
 }
 void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cudaStream_t st) {
   ProfScope prof_("gen_pack_x3", st);

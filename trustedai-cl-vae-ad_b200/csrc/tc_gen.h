@@ -79,6 +79,8 @@ struct GenEpilogue {
   float* out_f32;          // fp32 NHWC [B,Ho,Wo,Cn] or nullptr (GEN_DENSE: [Cn][dense_ld], element (column, row))
   int dense_n, dense_ld;   // GEN_DENSE: valid GEMM rows n and leading dimension of out_f32; bias is per ROW; `out` planes are
   int dense_cc;            //   written as [column][chunk(c)][pixel p][8] with row n = p * dense_cc + c (the Dense output as an image)
+  int dense_tr;            // GEN_DENSE: out_f32 element (column, row) at row * dense_ld + column instead (a [rows][columns] matrix);
+                           //   mask_f32 is read at the same index as out_f32
   const float* mask_f32;   // fp32 NHWC mask [B,Ho,Wo,Cn] (alternative to `mask`) or nullptr
 };
 // in: K-side plane tensor; returns 0 on success (1: no driver entry point, 2: tensor map encode failed)
@@ -94,6 +96,8 @@ struct GenWgradSpec {
   int Cs, Cu;          // real channels of the input / output-gradient tensors (per parity for S2D)
   int w_mode;          // dW element (tap, s-channel, u-channel): 0 -> (tap*Cs + cs)*Cu + cu ; 1 -> (tap*Cu + cu)*Cs + cs
   int Hg, Wg;          // pixel grid both operands are indexed on (plane dims of U)
+  int split_dense;     // GEN_DENSE: both tensors carry lo planes right behind their hi planes (s_KC / u_KC count hi + lo); every
+                       // output sums the hi*hi, hi*lo and lo*hi accumulators (fp32-grade Dense forward over a long K)
 };
 struct GenWgradPlan;
 GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not, bool upload = true);
@@ -111,7 +115,12 @@ void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cuda
 void gen_pack_nhwc(const float* in, int B, int H, int W, int C, const GenPlanes& out, cudaStream_t st);
 // fp32 [R][N] row-major -> planes [ceil(R/8) (x2 when split)][N][8]: unit (chunk, n) holds rows 8*chunk .. 8*chunk+7 of column n
 // (rows >= R are zero).  The K-side tensor of GEN_DENSE products (n viewed as [N/32][32] pixels; N % 32 == 0).
-void gen_pack_rows_T(const float* in, int R, int N, int split, void* out, cudaStream_t st);
+void gen_pack_rows_T(const float* in, int R, int N, int split, void* out, cudaStream_t st, int Np = 0, int ones_n = -1);
+// (Np > N: plane pitch, columns N..Np-1 are zero except column ones_n, which holds 1.0 for every row < R: a "ones pixel"
+// through which a pixel-K product adds a bias)
+// fp32 [N][C] row-major -> planes [ceil(C/8) (x2 when split)][Np][8]: unit (chunk, n) = in[n][8*chunk .. 8*chunk+7]; column
+// ones_n (>= N) holds bias[c]; other columns >= N are zero
+void gen_pack_cols(const float* in, const float* bias, int N, int C, int split, void* out, int Np, int ones_n, cudaStream_t st);
 // planes -> fp32 NHWC [B,H,W,C] (hi + lo when split); tests / debug
 void gen_unpack_nhwc(const GenPlanes& in, int B, int H, int W, int C, float* out, cudaStream_t st);
 
