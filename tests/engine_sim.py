@@ -26,7 +26,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GP = 32
 LO_FLAG = 0x40000000
-PLAIN, S2D, X3 = 0, 1, 2
+PLAIN, S2D, X3, X27 = 0, 1, 2, 3
 CONV_S2, CONVT_S2, CONV_S1, DENSE = 0, 1, 2, 3
 
 
@@ -63,7 +63,7 @@ def hi_lo(a):
 
 # ------------------------------------------------------------------------------------------ plane tensors
 def planes_count(layout, KC, split):
-    return (4 * KC if layout == S2D else (2 if layout == X3 else KC)) * (2 if split else 1)
+    return (4 * KC if layout == S2D else (2 if layout == X3 else (4 if layout == X27 else KC))) * (2 if split else 1)
 
 
 def pack_planes(x, layout, KC, split):
@@ -79,6 +79,15 @@ def pack_planes(x, layout, KC, split):
         return out
     Hp, Wp = H // 2, W // 2
     out = np.zeros((B, planes_count(layout, KC, split), Hp, Wp, 8))
+    if layout == X27:                      # element (kh*3 + kw)*3 + c of pixel (i, j) = x[2i + kh][2j + kw][c], zero outside the image
+        pad = np.zeros((B, H + 2, W + 2, Cc))
+        pad[:, :H, :W] = hi
+        for kh in range(3):
+            for kw in range(3):
+                for c in range(Cc):
+                    e = (kh * 3 + kw) * 3 + c
+                    out[:, e // 8, :, :, e % 8] = pad[:, kh:kh + H:2, kw:kw + W:2, c]
+        return out
     for a in range(2):
         for b in range(2):
             par = a * 2 + b

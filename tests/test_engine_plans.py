@@ -143,13 +143,13 @@ def test_dense_forward_and_gradient_plans():
 
 
 # ------------------------------------------------------------------------------------------ weight / bias gradients
-@pytest.mark.parametrize("Ci,Co,H,W,x3", [(3, 16, 8, 32, 1), (16, 5, 8, 32, 0), (64, 16, 4, 32, 0), (128, 8, 4, 32, 0)])
+@pytest.mark.parametrize("Ci,Co,H,W,x3", [(3, 16, 8, 32, 1), (3, 32, 12, 60, 2), (16, 5, 8, 32, 0), (64, 16, 4, 32, 0), (128, 8, 4, 32, 0)])
 def test_conv_s2_weight_gradient_plan(Ci, Co, H, W, x3):
     """dense accumulators (small parity blocks) and the pruned (tap, parity) plan of wide layers; the bias gradient against ones"""
     rng = np.random.default_rng(31 + Ci)
     x = rng.random((2, H, W, Ci), dtype=np.float32)
     g = _rand(rng, 2, H // 2, W // 2, Co)
-    layout, KC = (S.X3, 1) if x3 else (S.S2D, kc16(Ci))
+    layout, KC = (S.X27, 1) if x3 == 2 else ((S.X3, 1) if x3 else (S.S2D, kc16(Ci)))      # X27: the 27-value patches, one tap
     plan = _wgrad_plan(S.CONV_S2, 0, layout, KC, S.PLAIN, kc16(Co), Ci, Co, 0, H // 2, W // 2)
     dW, db = S.run_wgrad(plan, S.pack_planes(x, layout, KC, 0), S.pack_planes(g, S.PLAIN, kc16(Co), 0), H // 2, W // 2)
     wt = torch.zeros(3, 3, Ci, Co, dtype=torch.float64, requires_grad=True)

@@ -180,7 +180,7 @@ def test_output_layer_data_gradient(Ci, Co, H, W):
 
 
 # ------------------------------------------------------------------------------------------ weight + bias gradients
-@pytest.mark.parametrize("Ci,Co,H,W,x3", [(3, 32, 24, 60, 1), (32, 5, 24, 50, 0), (3, 64, 16, 60, 1), (64, 128, 16, 60, 0), (128, 32, 12, 50, 0)])
+@pytest.mark.parametrize("Ci,Co,H,W,x3", [(3, 32, 24, 60, 1), (3, 32, 24, 60, 2), (32, 5, 24, 50, 0), (3, 64, 16, 60, 2), (64, 128, 16, 60, 0), (128, 32, 12, 50, 0)])   # x3 = 2: X27 patch planes
 def test_conv_s2_weight_gradient(Ci, Co, H, W, x3):
     rng = np.random.default_rng(17 * Ci + Co)
     B = 3

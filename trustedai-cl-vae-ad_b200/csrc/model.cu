@@ -172,6 +172,7 @@ struct kcvae_model {
   int32_t* gen_table = nullptr;
   uint64_t gen_img_version = 0;
   void* x_pl = nullptr;
+  void* x27_pl = nullptr;      // X27 patch planes of the input image (training: shifted operand of the first layer's weight gradient)
   std::vector<void*> act_e_pl, g_e_pl, act_d_pl, g_d_pl;
   float *gen_partial = nullptr, *gen_partial2 = nullptr;
   // decoder Dense layer on the engine (GEN_DENSE products): W^T and G^T as plane tensors, plans per batch size
@@ -384,7 +385,7 @@ int gen_setup(kcvae_model* h) {
       E[l].dgrad = gen_conv_plan_create(d, &why);
     }
     GenWgradSpec w{};
-    w.kind = GEN_CONV_S2; w.s_layout = f.in_layout; w.s_KC = f.KCk; w.u_layout = GEN_PLAIN; w.u_KC = kc16(h->ec[l + 1]);
+    w.kind = GEN_CONV_S2; w.s_layout = x3 ? GEN_X27 : f.in_layout; w.s_KC = f.KCk; w.u_layout = GEN_PLAIN; w.u_KC = kc16(h->ec[l + 1]);
     w.Cs = h->ec[l]; w.Cu = h->ec[l + 1]; w.w_mode = 0; w.Hg = h->eh[l + 1]; w.Wg = h->ew[l + 1];
     E[l].wgrad = gen_wgrad_plan_create(w, &why);
     ok = E[l].fwd && E[l].fwd_split && (l == 0 || E[l].dgrad) && E[l].wgrad;
@@ -707,6 +708,7 @@ int ensure_fwd(kcvae_model* h, int B) {
   if (gen_enc) {
     h->act_e_pl.resize(L + 1, nullptr);
     KC_TRY(gen_alloc(h, &h->x_pl, pl_x(h, 1).units(B)));
+    if (h->C == 3) KC_TRY(gen_alloc(h, &h->x27_pl, (size_t)B * 4 * (h->H / 2) * (h->W / 2)));
     for (int l = 1; l < L; ++l) KC_TRY(gen_alloc(h, &h->act_e_pl[l], pl_act_e(h, l, 1).units(B)));
   }
   if (gen_dec) {
@@ -855,13 +857,13 @@ int tc_flag_check(kcvae_model* h, cudaStream_t st) {   // enqueue the flag read-
 #ifndef KCVAE_EMU
 // encoder convolutions on the general engine: x -> 2x2 space-to-depth bf16 planes (hi + lo when `split`), every Conv2D s2
 // as a stride-1 product over them; the last activation leaves as fp32 NHWC for the Dense layers
-void gen_run_encoder_convs(kcvae_model* h, const float* x, int B, int split, cudaStream_t st) {
+void gen_run_encoder_convs(kcvae_model* h, const float* x, int B, int split, cudaStream_t st, int train) {
   const int L = h->L;
   gen_refresh(h, st);
   h->enc_split_live = split != 0;
   GenPlanes in = pl_x(h, split);
   g_tag = "enc.pack";
-  if (h->C == 3) gen_pack_x3(x, B, h->H, h->W, split, h->x_pl, st);
+  if (h->C == 3) gen_pack_x3(x, B, h->H, h->W, split, h->x_pl, st, train ? h->x27_pl : nullptr);
   else gen_pack_nhwc(x, B, h->H, h->W, h->C, in, st);
   for (int l = 0; l < L; ++l) {
     const auto& g = h->gen_e[l];
@@ -882,7 +884,7 @@ void run_encoder(kcvae_model* h, const float* x, int B, cudaStream_t st, int spl
   const float* in = x;
 #ifndef KCVAE_EMU
   if (h->gen_enc) {
-    gen_run_encoder_convs(h, x, B, split && h->enc_split, st);
+    gen_run_encoder_convs(h, x, B, split && h->enc_split, st, split);
     in = h->act_e[h->L];
   } else
 #endif
@@ -1527,6 +1529,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       const auto& g = h->gen_e[l];
       const int vi = h->vi_enc_conv(l);
       GenPlanes act = l == 0 ? pl_x(h, split) : pl_act_e(h, l, split), gin = pl_g_e(h, l + 1);
+      if (l == 0 && h->C == 3) act = pl_make(h->x27_pl, GEN_X27, 1, 0, h->H / 2, h->W / 2);   // the 27-value patches: one tap
       g_tag = l == 0 ? "enc.conv0.bwd" : (l == 1 ? "enc.conv1.bwd" : "enc.convN.bwd");
       if (l > 0) {
         float* px;
@@ -1778,6 +1781,7 @@ int kcvae_destroy(kcvae_handle h) {
   if (h->gen_wimg) cudaFree(h->gen_wimg);
   if (h->gen_table) cudaFree(h->gen_table);
   if (h->x_pl) cudaFree(h->x_pl);
+  if (h->x27_pl) cudaFree(h->x27_pl);
   for (auto* v : {&h->act_e_pl, &h->g_e_pl, &h->act_d_pl, &h->g_d_pl}) for (void* q : *v) if (q) cudaFree(q);
   for (auto& d : h->dense_plans) dense_plans_free(d);
   for (auto& d : h->edense_plans) edense_plans_free(d);
@@ -2543,7 +2547,7 @@ int kcvae_gen_wgrad_test(int kind, int w_mode, int flip, int s_x3, const float* 
   int Hu, Wu;          // full-resolution dims of the gradient tensor as fp32 NHWC
   if (kind == GEN_CONV_S2) {          // S: layer input at (Hs, Ws), stored S2D / X3; U: gradient at (Hs/2, Ws/2), PLAIN
     if ((Hs | Ws) & 1) return fail(nullptr, KCVAE_ERR_INVALID, "gen_wgrad_test: stride-2 input must have even sizes");
-    S.layout = s_x3 ? GEN_X3 : GEN_S2D; S.H = Hs / 2; S.W = Ws / 2;
+    S.layout = s_x3 == 2 ? GEN_X27 : (s_x3 ? GEN_X3 : GEN_S2D); S.H = Hs / 2; S.W = Ws / 2;
     U.layout = GEN_PLAIN; U.H = Hs / 2; U.W = Ws / 2; Hu = Hs / 2; Wu = Ws / 2;
   } else if (kind == GEN_CONVT_S2) {  // S: layer input at (Hs, Ws), PLAIN; U: gradient at (2Hs, 2Ws), stored S2D
     S.layout = GEN_PLAIN; S.H = Hs; S.W = Ws;
@@ -2572,7 +2576,13 @@ int kcvae_gen_wgrad_test(int kind, int w_mode, int flip, int s_x3, const float* 
     return done(KCVAE_ERR_CUDA, "gen_wgrad_test: cudaMalloc failed");
   cudaMemsetAsync(d_err, 0, sizeof(int), st);
   S.base = ds; U.base = du;
-  if (S.layout == GEN_X3) gen_pack_x3(d_s, B, Hs, Ws, 0, ds, st);
+  if (s_x3 == 2) {            // X27 patch planes (written beside the X3 planes by the same packer)
+    void* tmp = nullptr;
+    if (cudaMalloc(&tmp, (size_t)B * 2 * (Hs / 2) * (Ws / 2) * 16) != cudaSuccess) return done(KCVAE_ERR_CUDA, "gen_wgrad_test: cudaMalloc failed");
+    gen_pack_x3(d_s, B, Hs, Ws, 0, tmp, st, ds);
+    cudaStreamSynchronize(st);
+    cudaFree(tmp);
+  } else if (S.layout == GEN_X3) gen_pack_x3(d_s, B, Hs, Ws, 0, ds, st);
   else gen_pack_nhwc(d_s, B, Hs, Ws, Cs, S, st);
   gen_pack_nhwc(d_u, B, Hu, Wu, Cu, U, st);
   if (gen_wgrad_run(plan, S, U, d_dW, d_db, part, B, d_err, "gen_wgrad_test", st) != 0)

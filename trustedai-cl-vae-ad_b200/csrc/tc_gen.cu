@@ -489,7 +489,7 @@ void elem_of(int layout, int KC, int C, int plane, int slot, int* par, int* ch) 
     *ch = c < C ? c : -1;
   }
 }
-int hi_planes(int layout, int KC) { return layout == GEN_S2D ? 4 * KC : (layout == GEN_X3 ? 2 : KC); }
+int hi_planes(int layout, int KC) { return layout == GEN_S2D ? 4 * KC : (layout == GEN_X3 ? 2 : (layout == GEN_X27 ? 4 : KC)); }
 
 }  // namespace
 
@@ -994,7 +994,8 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not,
   if (!TW) return no("no tile width in [8, 31] divides the gradient's width");
   struct Tap { int t0, t1, shift; };
   std::vector<Tap> taps;
-  if (s.kind == GEN_CONV_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, di * GP + dj});
+  if (s.kind == GEN_CONV_S2 && s.s_layout == GEN_X27) taps.push_back({0, 0, 0});     // the patch planes hold all nine taps of a pixel
+  else if (s.kind == GEN_CONV_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, di * GP + dj});
   else if (s.kind == GEN_CONVT_S2) for (int di = 0; di < 2; ++di) for (int dj = 0; dj < 2; ++dj) taps.push_back({di, dj, (1 - di) * GP + (1 - dj)});
   else if (s.kind == GEN_DENSE) taps.push_back({0, 0, 0});
   else for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw)
@@ -1216,7 +1217,9 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not,
   } else
   for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) for (int cs = 0; cs < Cs; ++cs) for (int cu = 0; cu < Cu; ++cu) {
     int tap_i, es, eu;
-    if (s.kind == GEN_CONV_S2) {
+    if (s.kind == GEN_CONV_S2 && s.s_layout == GEN_X27) {
+      tap_i = 0; es = (kh * 3 + kw) * 3 + cs; eu = cu;
+    } else if (s.kind == GEN_CONV_S2) {
       const int di = kh >> 1, a = kh & 1, dj = kw >> 1, b = kw & 1, par = a * 2 + b;
       tap_i = di * 2 + dj;
       es = s.s_layout == GEN_X3 ? par * 3 + cs : par * s.s_KC * 8 + cs;
@@ -1317,7 +1320,7 @@ int gen_wgrad_run(const GenWgradPlan* P, const GenPlanes& S, const GenPlanes& U,
 // ============================================================================================
 namespace {
 
-__global__ void gen_pack_x3_kernel(const float* __restrict__ x, int B, int H, int W, int split, uint4* out) {
+__global__ void gen_pack_x3_kernel(const float* __restrict__ x, int B, int H, int W, int split, uint4* out, uint4* x27) {
   const int h2 = H / 2, w2 = W / 2;
   const int64_t total = (int64_t)B * h2 * w2;
   const int PL = split ? 4 : 2;
@@ -1345,6 +1348,33 @@ __global__ void gen_pack_x3_kernel(const float* __restrict__ x, int B, int H, in
     if (split) {
       o[2 * plane] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       o[3 * plane] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+    if (x27) {
+      // the 3x3 stride-2 patch of output pixel (r, j): element (kh*3 + kw)*3 + c = x[2r + kh][2j + kw][c], zero outside the image
+      // (TF SAME on even sizes pads bottom / right only).  Rows 2r, 2r+1 and columns 2j, 2j+1 are the values loaded above.
+      float pv[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) pv[e] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int y = 2 * r + kh;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int xx = 2 * j + kw;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float val;
+            if (kh < 2 && kw < 2) val = v[kh * 6 + kw * 3 + c];
+            else val = (y < H && xx < W) ? __ldg(x + (((int64_t)n * H + y) * W + xx) * 3 + c) : 0.f;
+            pv[(kh * 3 + kw) * 3 + c] = val;
+          }
+        }
+      }
+      uint4* o27 = x27 + (int64_t)n * 4 * plane + (int64_t)r * w2 + j;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        o27[q * plane] = make_uint4(pack_bf16x2(pv[8 * q], pv[8 * q + 1]), pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]),
+                                    pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]), pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]));
     }
   }
 }
@@ -1445,10 +1475,11 @@ void gen_pack_cols(const float* in, const float* bias, int N, int C, int split, 
   ++g_launches;
   gen_pack_cols_kernel<<<grid_for((int64_t)((C + 7) / 8) * Np, 256, 8, 4), 256, 0, st>>>(in, bias, N, C, split, reinterpret_cast<uint4*>(out), Np, ones_n);
 }
-void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cudaStream_t st) {
+void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cudaStream_t st, void* x27_out) {
   ProfScope prof_("gen_pack_x3", st);
   ++g_launches;
-  gen_pack_x3_kernel<<<grid_for((int64_t)B * (H / 2) * (W / 2), 256, 8, 4), 256, 0, st>>>(x, B, H, W, split, reinterpret_cast<uint4*>(out));
+  gen_pack_x3_kernel<<<grid_for((int64_t)B * (H / 2) * (W / 2), 256, 8, 4), 256, 0, st>>>(x, B, H, W, split, reinterpret_cast<uint4*>(out),
+                                                                                          reinterpret_cast<uint4*>(x27_out));
 }
 void gen_pack_nhwc(const float* in, int B, int H, int W, int C, const GenPlanes& out, cudaStream_t st) {
   ProfScope prof_("gen_pack", st);

@@ -6,6 +6,8 @@
 //   PLAIN  plane = chunk                         (decoder activations, encoder gradients)
 //   S2D    plane = (row parity*2 + col parity)*KC + chunk at (y/2, x/2)   (encoder activations, decoder gradients)
 //   X3     the 3-channel input image, 2x2 space-to-depth, 12 values packed into 2 planes
+//   X27    the 3-channel input image as the 27-value 3x3 stride-2 patch of every output pixel (4 planes): the first layer's
+//          weight gradient is then ONE tap (2 MMAs per K step instead of 5)
 // A stride-2 Conv2D over an S2D tensor and a stride-2 Conv2DTranspose over a PLAIN tensor are both stride-1 products
 // whose taps are descriptor start offsets into one TMA-loaded halo tile (tc_common.cuh), so one forward kernel
 // (tc_gconv_kernel, MMA list built on the host) covers forward and data-gradient of every layer, and one
@@ -16,7 +18,7 @@
 
 namespace kc {
 
-enum GenLayout { GEN_PLAIN = 0, GEN_S2D = 1, GEN_X3 = 2 };
+enum GenLayout { GEN_PLAIN = 0, GEN_S2D = 1, GEN_X3 = 2, GEN_X27 = 3 };
 enum GenKind {
   GEN_CONV_S2 = 0,    // K side: S2D / X3 input, taps (di,dj) in {0,1}^2   (Conv2D s2 forward, Conv2DTranspose s2 dgrad)
   GEN_CONVT_S2 = 1,   // K side: PLAIN input, N side: (col parity, channel), one group per row parity (ConvT s2 fwd, Conv2D s2 dgrad)
@@ -67,7 +69,7 @@ struct GenPlanes {     // a plane tensor
   int KC;              // chunks per parity
   int split;           // lo planes present
   int H, W;            // plane dims (pixels)
-  int planes() const { return (layout == GEN_S2D ? 4 * KC : (layout == GEN_X3 ? 2 : KC)) * (split ? 2 : 1); }
+  int planes() const { return (layout == GEN_S2D ? 4 * KC : (layout == GEN_X3 ? 2 : (layout == GEN_X27 ? 4 : KC))) * (split ? 2 : 1); }
   size_t units(int B) const { return (size_t)B * planes() * H * W; }
 };
 
@@ -110,7 +112,8 @@ int gen_wgrad_run(const GenWgradPlan* p, const GenPlanes& S, const GenPlanes& U,
 
 // ---- packers -----------------------------------------------------------------------------------------------------------
 // x fp32 NHWC [B,H,W,3] (H, W even) -> X3 planes [B][2 (x2 when split)][H/2][W/2][8]
-void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cudaStream_t st);
+void gen_pack_x3(const float* x, int B, int H, int W, int split, void* out, cudaStream_t st, void* x27_out = nullptr);
+// (x27_out: also the X27 patch planes [B][4][H/2][W/2][8], hi only - the shifted operand of the first layer's weight gradient)
 // fp32 NHWC [B,H,W,C] -> PLAIN / S2D planes (channels padded with zeros; split -> lo planes too)
 void gen_pack_nhwc(const float* in, int B, int H, int W, int C, const GenPlanes& out, cudaStream_t st);
 // fp32 [R][N] row-major -> planes [ceil(R/8) (x2 when split)][N][8]: unit (chunk, n) holds rows 8*chunk .. 8*chunk+7 of column n
