@@ -124,29 +124,67 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // epilogue variants (template flags): only the code a product needs is compiled into its kernel
 constexpr int E_PRE = 1, E_MASK = 2, E_OUTP = 4, E_LO = 8, E_F32 = 16, E_MASKF = 32, E_ALL = 63, E_DENSE = 64;
 
-// one 8-channel group of one output pixel: pre-op, mask, stores
+// Steps of a plane tensor in 16-byte units, computed once per kernel: the epilogue then addresses "pixel base + b * db +
+// chunk * cs (+ lo)" with 32-bit arithmetic instead of evaluating unit_index() per 8-channel group.
+struct PlaneStep { int cs, db, lo; };     // next chunk plane; output column parity b = 1 (transposed convolution); lo planes
+__device__ __forceinline__ PlaneStep plane_step(const PlaneRef& t) {
+  const int hw = t.H * t.W;
+  PlaneStep s;
+  s.cs = hw;
+  s.db = t.layout == GEN_S2D ? t.KC * hw : 1;
+  s.lo = (t.layout == GEN_S2D ? 4 : 1) * t.KC * hw;
+  return s;
+}
+
+// walks tiles t = blockIdx.x, + gridDim.x, ... as mixed-radix digits (group, tile column, tile row, image): one division
+// chain at the start, additions with carry per tile
+struct TileWalk {
+  int grp, tx, ty, n, dgrp, dtx, dty, dn, n_groups, tiles_x, tiles_y;
+  __device__ __forceinline__ void init(int t0, int step, int n_groups_, int tiles_x_, int tiles_y_) {
+    n_groups = n_groups_; tiles_x = tiles_x_; tiles_y = tiles_y_;
+    grp = t0 % n_groups; t0 /= n_groups; tx = t0 % tiles_x; t0 /= tiles_x; ty = t0 % tiles_y; n = t0 / tiles_y;
+    dgrp = step % n_groups; step /= n_groups; dtx = step % tiles_x; step /= tiles_x; dty = step % tiles_y; dn = step / tiles_y;
+  }
+  __device__ __forceinline__ void next() {
+    grp += dgrp; int c = grp >= n_groups; grp -= c ? n_groups : 0;
+    tx += dtx + c; c = tx >= tiles_x; tx -= c ? tiles_x : 0;
+    ty += dty + c; c = ty >= tiles_y; ty -= c ? tiles_y : 0;
+    n += dn + c;
+  }
+};
+
+// one 8-channel group of one output pixel: pre-op, mask, stores.  optr = the group's hi unit in the output planes,
+// fpix = the pixel's index in the NHWC fp32 tensors
 template <int EPI>
-__device__ __forceinline__ void g1_emit8(const G1Params& p, const float* s_bias, float* v, int n, int oy, int ox, int chunk, uint4 m) {
+__device__ __forceinline__ void g1_emit8(const G1Params& p, const float* s_bias, float* v, int chunk, uint4 m, uint4* optr, int lo_off,
+                                         int64_t fpix) {
   const int c0 = chunk * 8;
   if ((EPI & E_PRE) && p.pre != GEN_PRE_NONE) {
+    const float4 b0 = *reinterpret_cast<const float4*>(s_bias + c0), b1 = *reinterpret_cast<const float4*>(s_bias + c0 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    // channels past Cn: zero weights (structural zeros of the gather table) and zero bias, so bias / ReLU leave 0 there
+    if (p.pre == GEN_PRE_BIAS_RELU) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float y = v[k] + s_bias[c0 + k];
-      if (p.pre == GEN_PRE_BIAS_RELU) y = fmaxf(y, 0.f);
-      else if (p.pre == GEN_PRE_BIAS_SIGMOID) y = __fdividef(1.0f, 1.0f + __expf(-y));
-      v[k] = c0 + k < p.Cn ? y : 0.f;
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k] + bb[k], 0.f);
+    } else if (p.pre == GEN_PRE_BIAS_SIGMOID) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = c0 + k < p.Cn ? __fdividef(1.0f, 1.0f + __expf(-(v[k] + bb[k]))) : 0.f;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += bb[k];
     }
   }
   if ((EPI & E_MASK) && p.has_mask) {
+    // bf16 pairs of the activation: "> 0" <=> sign clear and not zero; as integers: low half (w << 16) > 0, high half w > 0xFFFF
     const uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const uint32_t h = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;       // bf16 bits: positive <=> sign clear and not zero
-      if ((h & 0x8000u) || (h & 0x7FFFu) == 0) v[k] = 0.f;
+    for (int e = 0; e < 4; ++e) {
+      v[2 * e] = (int32_t)(w[e] << 16) > 0 ? v[2 * e] : 0.f;
+      v[2 * e + 1] = (int32_t)w[e] > 0xFFFF ? v[2 * e + 1] : 0.f;
     }
   }
   if ((EPI & E_MASKF) && p.mask_f32) {
-    const float* mk = p.mask_f32 + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.Cn + c0;
+    const float* mk = p.mask_f32 + fpix * p.Cn + c0;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (c0 + k < p.Cn && !(__ldg(mk + k) > 0.f)) v[k] = 0.f;
@@ -155,7 +193,7 @@ __device__ __forceinline__ void g1_emit8(const G1Params& p, const float* s_bias,
     uint32_t h4[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) h4[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
-    p.out.base[unit_index(p.out, n, oy, ox, chunk, 0)] = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+    *optr = make_uint4(h4[0], h4[1], h4[2], h4[3]);
     if ((EPI & E_LO) && p.out_lo) {
       uint32_t l4[4];
 #pragma unroll
@@ -164,11 +202,11 @@ __device__ __forceinline__ void g1_emit8(const G1Params& p, const float* s_bias,
         const float r1 = v[2 * e + 1] - __uint_as_float(h4[e] & 0xFFFF0000u);
         l4[e] = pack_bf16x2(r0, r1);
       }
-      p.out.base[unit_index(p.out, n, oy, ox, chunk, 1)] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+      optr[lo_off] = make_uint4(l4[0], l4[1], l4[2], l4[3]);
     }
   }
   if ((EPI & E_F32) && p.out_f32) {
-    float* o = p.out_f32 + (((int64_t)n * p.Ho + oy) * p.Wo + ox) * p.Cn + c0;
+    float* o = p.out_f32 + fpix * p.Cn + c0;
     if ((p.Cn & 3) == 0 && c0 + 8 <= p.Cn) {           // rows of Cn floats stay 16-byte aligned: two vector stores
       reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], v[3]);
       reinterpret_cast<float4*>(o)[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -188,9 +226,23 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   unsigned char* stages = smem + G1_PLAN_BYTES;
   __shared__ uint64_t full_bar[G1_STAGES], empty_bar[G1_STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_bias[256 + 8];
+  __shared__ __align__(16) float s_bias[256 + 8];
+  __shared__ uint32_t s_unit[8][2];       // epilogue unit u = (M-tile, 32-column block): {mt | cb << 8 | ncols << 16, 4 x (b << 7 | chunk)}
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 256 + 8; i += G1_THREADS) s_bias[i] = (!(EPI & E_DENSE) && p.bias && i < p.Cn) ? __ldg(p.bias + i) : 0.f;
+  if (threadIdx.x < 8) {                  // tile-invariant index arithmetic of the epilogue, done once
+    const int acc = __ldg(&p.plan->acc_cols), ncb = (acc + 31) / 32, u = threadIdx.x;
+    const int cop = (int)__ldg(&p.plan->Cop), convt = __ldg(&p.plan->type) == GEN_CONVT_S2;
+    const int mt = u / ncb, cb = u % ncb, ncols = min(32, acc - cb * 32);
+    uint32_t bc = 0;
+    for (int j8 = 0; j8 < 4; ++j8) {
+      const int col0 = cb * 32 + j8 * 8;
+      const int b = convt ? col0 / cop : 0;
+      bc |= (uint32_t)((b << 7) | ((col0 - b * cop) >> 3)) << (8 * j8);
+    }
+    s_unit[u][0] = (uint32_t)(mt | (cb << 8) | (ncols << 16));
+    s_unit[u][1] = bc;
+  }
 
   {  // plan -> shared memory (header + the used slab / MMA entries)
     const uint4* src = reinterpret_cast<const uint4*>(p.plan);
@@ -226,7 +278,6 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   const int n_groups = plan->n_groups, MT = plan->MT, NB = plan->NB, acc_cols = plan->acc_cols;
   const int TW = plan->TW, TRr = 4 * MT;
   const uint32_t stage_bytes = plan->stage_bytes;
-  const int per_img = p.tiles_y * p.tiles_x;
 
   if (warp == 0) {
     // ================================ TMA producer ========================================
@@ -235,11 +286,11 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
       const int row0 = plan->row0, col0 = plan->col0, in_PL = p.in_PL;
       int it = 0;
       bool ok = true;
-      for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x) {
-        const int grp = t % n_groups, tt = t / n_groups;
-        const int n = tt / per_img, rem = tt % per_img;
-        const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
-        const G1Group g = plan->groups[grp];
+      TileWalk tw;
+      tw.init(blockIdx.x, gridDim.x, n_groups, p.tiles_x, p.tiles_y);
+      for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, tw.next()) {
+        const int n = tw.n, ty = tw.ty, tx = tw.tx;
+        const G1Group g = plan->groups[tw.grp];
         for (int sl = g.slab0; sl < g.slab0 + g.slab_n; ++sl, ++it) {
           const int s = it % G1_STAGES;
           const uint32_t ph = (it / G1_STAGES) & 1;
@@ -258,11 +309,13 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
     const bool leader = elect_one();
     int it = 0, tcount = 0;
     bool ok = true;
+    int grp = blockIdx.x % n_groups;
+    const int dgrp = gridDim.x % n_groups;
     for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, ++tcount) {
-      const int grp = t % n_groups;
       const G1Group g = plan->groups[grp];
-      const int buf = tcount % NB;
-      const uint32_t bph = (tcount / NB) & 1;
+      grp += dgrp; grp -= grp >= n_groups ? n_groups : 0;
+      const int buf = NB == 2 ? (tcount & 1) : 0;
+      const uint32_t bph = (uint32_t)(NB == 2 ? (tcount >> 1) : tcount) & 1u;
       if (!mbar_wait(&tempty_bar[buf], bph ^ 1)) { if (leader) *p.error_flag = 1; break; }
       fence_after_sync();
       for (int sl = g.slab0; sl < g.slab0 + g.slab_n; ++sl, ++it) {
@@ -303,21 +356,21 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
     const int half = e >> 2;                      // the warps of a lane group share the (M-tile, column block) units round robin
     constexpr int WPG = G1_EPI_WARPS / 4;         // warps per lane group
     constexpr int UPW = 8 / WPG;                  // units per warp and tile (a tile has at most 8 units)
-    const int type = plan->type;
-    const int Cop = (int)plan->Cop;
+    const bool convt = plan->type == GEN_CONVT_S2;
     const int NCB = (acc_cols + 31) / 32;
+    const int nunits = MT * NCB;
+    const PlaneStep os = plane_step(p.out), ms = plane_step(p.mask);
+    TileWalk tw;
+    tw.init(blockIdx.x, gridDim.x, n_groups, p.tiles_x, p.tiles_y);
     int tcount = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount) {
-      const int grp = t % n_groups, tt = t / n_groups;
-      const int n = tt / per_img, rem = tt % per_img;
-      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
-      const int a_par = plan->groups[grp].a_par;
-      const int buf = tcount % NB;
-      const uint32_t bph = (tcount / NB) & 1;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++tcount, tw.next()) {
+      const int n = tw.n, ty = tw.ty, tx = tw.tx;
+      const int a_par = plan->groups[tw.grp].a_par;
+      const int buf = NB == 2 ? (tcount & 1) : 0;
+      const uint32_t bph = (uint32_t)(NB == 2 ? (tcount >> 1) : tcount) & 1u;
       // A warp owns at most UPW (M-tile, 32-column block) units of a tile.  The ReLU-mask units of ALL of them are requested
       // before the accumulator wait: they do not depend on the MMAs, and their global-memory latency then overlaps the
       // tile's MMAs instead of being paid once per unit by a warp with nothing else to run.
-      const int nunits = MT * NCB;
       uint4 mk[UPW][4];
       if (EPI & E_MASK) {
 #pragma unroll
@@ -326,23 +379,16 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) mk[k][j8] = make_uint4(0, 0, 0, 0);
           if (u < nunits && p.has_mask) {
-            const int mt = u / NCB, cb = u % NCB;
-            const int ncols = min(32, acc_cols - cb * 32);
-            const int q = mt * 128 + lg * 32 + lane;
-            const int r = q / GP, c = q % GP;
-            const int gy = ty * TRr + r, gx = tx * TW + c;
-            if (c < TW && gy < p.Hg && gx < p.Wg) {
+            const uint32_t u0 = s_unit[u][0], bc = s_unit[u][1];
+            const int mt = u0 & 0xFF, ncols = u0 >> 16;
+            const int gy = ty * TRr + mt * 4 + lg, gx = tx * TW + lane;
+            if (lane < TW && gy < p.Hg && gx < p.Wg) {
+              const uint4* mptr = p.mask.base + unit_index(p.mask, n, convt ? 2 * gy + a_par : gy, convt ? 2 * gx : gx, 0, 0);
 #pragma unroll
               for (int j8 = 0; j8 < 4; ++j8) {
                 if (j8 * 8 < ncols) {
-                  const int col0 = cb * 32 + j8 * 8;
-                  int oy = gy, ox = gx, chunk = col0 >> 3;
-                  if (type == GEN_CONVT_S2) {
-                    const int b = col0 / Cop;
-                    chunk = (col0 - b * Cop) >> 3;
-                    oy = 2 * gy + a_par; ox = 2 * gx + b;
-                  }
-                  mk[k][j8] = __ldg(p.mask.base + unit_index(p.mask, n, oy, ox, chunk, 0));
+                  const uint32_t q = (bc >> (8 * j8)) & 0xFFu;
+                  mk[k][j8] = __ldg(mptr + (int)(q >> 7) * ms.db + (int)(q & 0x7Fu) * ms.cs);
                 }
               }
             }
@@ -357,12 +403,10 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
       for (int k = 0; k < UPW; ++k) {
         const int u = half + WPG * k;
         if (u >= nunits) break;
-        const int mt = u / NCB, cb = u % NCB;
-        const int ncols = min(32, acc_cols - cb * 32);
-        const int q = mt * 128 + lg * 32 + lane;
-        const int r = q / GP, c = q % GP;
-        const int gy = ty * TRr + r, gx = tx * TW + c;
-        const bool valid = c < TW && gy < p.Hg && gx < p.Wg;
+        const uint32_t u0 = s_unit[u][0], bc = s_unit[u][1];
+        const int mt = u0 & 0xFF, cb = (u0 >> 8) & 0xFF, ncols = u0 >> 16;
+        const int gy = ty * TRr + mt * 4 + lg, gx = tx * TW + lane;       // GEMM pixel of this thread: row mt * 4 + lg, column lane
+        const bool valid = lane < TW && gy < p.Hg && gx < p.Wg;
         const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)((buf * MT + mt) * acc_cols + cb * 32);
         float v[32];
         if (ncols == 32) tmem_ld32(ta, v);
@@ -388,26 +432,25 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
                 if (p.has_out) {
                   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out.base);
                   const __nv_bfloat16 hi = __float2bfloat16(y);
-                  const int64_t u = ((int64_t)col * p.out.PLimg + (cc >> 3)) * hw + pc;
-                  ob[u * 8 + (cc & 7)] = hi;
-                  if (p.out_lo) ob[(u + (int64_t)p.out.KC * hw) * 8 + (cc & 7)] = __float2bfloat16(y - __bfloat162float(hi));
+                  const int64_t uu = ((int64_t)col * p.out.PLimg + (cc >> 3)) * hw + pc;
+                  ob[uu * 8 + (cc & 7)] = hi;
+                  if (p.out_lo) ob[(uu + (int64_t)p.out.KC * hw) * 8 + (cc & 7)] = __float2bfloat16(y - __bfloat162float(hi));
                 }
               }
             }
           }
         } else
         if (valid) {
+          const int oy = convt ? 2 * gy + a_par : gy, ox0 = convt ? 2 * gx : gx;
+          uint4* optr = ((EPI & E_OUTP) && p.has_out) ? p.out.base + unit_index(p.out, n, oy, ox0, 0, 0) : nullptr;
+          const int64_t fpix0 = (EPI & (E_F32 | E_MASKF)) ? ((int64_t)n * p.Ho + oy) * p.Wo + ox0 : 0;
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             if (j8 * 8 < ncols) {
-              const int col0 = cb * 32 + j8 * 8;
-              int oy = gy, ox = gx, chunk = col0 >> 3;
-              if (type == GEN_CONVT_S2) {
-                const int b = col0 / Cop;
-                chunk = (col0 - b * Cop) >> 3;
-                oy = 2 * gy + a_par; ox = 2 * gx + b;
-              }
-              g1_emit8<EPI>(p, s_bias, v + j8 * 8, n, oy, ox, chunk, (EPI & E_MASK) ? mk[k][j8] : make_uint4(0, 0, 0, 0));
+              const uint32_t q = (bc >> (8 * j8)) & 0xFFu;
+              const int b = (int)(q >> 7), chunk = (int)(q & 0x7Fu);
+              g1_emit8<EPI>(p, s_bias, v + j8 * 8, chunk, (EPI & E_MASK) ? mk[k][j8] : make_uint4(0, 0, 0, 0),
+                            optr + (b * os.db + chunk * os.cs), os.lo, fpix0 + b);
             }
           }
         }
