@@ -516,42 +516,71 @@ __device__ __forceinline__ void tc_prep_dgrad_weights_body(const float* w, int C
 // ============================================================================================
 // Output-layer weight gradient on tensor cores (MN-major operands, K = pixels):
 //   dW[kh,kw,co,ci] = sum_{n,y,x} dl[n,y,x,co] * a[n, y+1-kh, x+1-kw, ci]
-// Per 32x30 tile: B operand = the bf16 halo tile of `a` (TMA, same [chunk][pixel] planes as the
-// forward kernel, read MN-major: N = 32 channels = 4 chunk planes, K = 16 pixels per MMA);
-// A operand = a zero-padded plane of dl (36 rows x 32 cols, 8 channels per pixel) written by
-// the loader warps, read MN-major with M-groups strided by ONE PLANE ROW, so M-group g holds
-// the vertical tap kh = g; the horizontal tap kw is the B start address.  Three accumulators
-// (kw) of M=64 x N=32 stay in TMEM over all tiles of the persistent CTA; each CTA writes one
-// partial dW that a reduction kernel sums (deterministic).
+// Per 32x30 tile ONE MMA (M=128, N=32, K=16) per 16 halo pixels covers all nine taps:
+//   B operand = the bf16 halo tile of `a` (TMA, [chunk plane][row][32 pixels] x 16 B, read MN-major: N = 32 channels =
+//     4 chunk planes, K = 16 consecutive pixels of a halo row);
+//   A operand = THREE zero-padded copies of the tile of dl (8 channels per pixel = one 16-byte unit), copy kw shifted
+//     by kw columns, stored row-interleaved: unit ((R*3 + kw)*32 + c) = dl[R - 2][c - 2 + kw] (tile-local, zero
+//     outside the tile).  Read MN-major with M-groups strided by one copy row (512 B), M-group G = kh*3 + kw of the
+//     descriptor that starts at halo pixel (r, c) reads unit ((r + kh)*3 + kw)*32 + c = dl[r - 2 + kh][c - 2 + kw]:
+//     exactly the dl pixel that halo pixel (r, c) of `a` meets under tap (kh, kw).
+// What bounds such a kernel is the ISSUE of the MMAs, not the tensor pipe (tools/mma_cost.cu: 42 cycles per M=128,
+// N=32 MMA whatever the majors and strides): the previous version kept kw in the B start address - three M=64 MMAs
+// per K step, 204 per tile - and ran exactly at the rate its issuing thread could build descriptors and issue
+// (33 cycles per MMA).  Here the issuing loop adds constants to two 32-bit descriptor words per MMA and nothing else.
+// `a` tiles are double-buffered whole (big TMA boxes stream at 7 TB/s, tools/tma_stream.cu; 4 KB boxes do not: 2.6
+// TB/s); the tile of dl arrives by TMA in a two-deep staging ring (zero fill outside the image) and the loader
+// warps copy it shared -> shared into the three copies, which are single-buffered: the staged tile waits in
+// registers while the previous tile's MMAs run, only the shared-memory stores wait for them.  The accumulator (128
+// lanes x 32 columns) stays in TMEM over all tiles of the persistent CTA; each CTA writes one partial dW that a
+// reduction kernel sums (deterministic).
 struct OutWgradParams {
-  const __nv_bfloat16* dl8;    // [B,H,W,8] bf16
   float* partial;              // [grid][9*Cout*Cin]
   int B, H, W, Cout, Cin;
   int tiles_y, tiles_x, num_tiles;
   int* error_flag;
 };
-constexpr int DLROWS = TR + 4;                 // dl plane rows (-2 .. TR+1)
-constexpr uint32_t DL_BYTES = DLROWS * PW * 16;
+constexpr int DLROWS = TR + 4;                      // dl copy rows (-2 .. TR+1)
+constexpr uint32_t DL_BYTES = DLROWS * 3 * PW * 16; // three row-interleaved copies
+constexpr uint32_t OW_DL_STAGE = TR * TW * 16;      // staged dl tile, dense rows of TW pixels
+constexpr uint32_t OW_STAGE = 4 * NPIX * 16;        // Cin = 32: 4 chunk planes of the halo tile
+constexpr uint32_t OW_B_OFF = DL_BYTES + 2 * OW_DL_STAGE;
+constexpr uint32_t OW_SMEM = OW_B_OFF + kStages * OW_STAGE;
+static_assert(PW == 32, "K steps of 16 pixels must not cross a halo row");
+static_assert(OW_B_OFF % 1024 == 0 && OW_SMEM <= 227 * 1024 - 1024, "tc_out_wgrad shared memory");
+
+// tcgen05.mma with the descriptors given as (low word, high word): the low words carry the start address and are what
+// an issuing loop advances
+__device__ __forceinline__ void mma_bf16_ss_words(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
-tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutWgradParams p) {
+tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_dl, OutWgradParams p) {
   constexpr int KC = 4;                               // Cin = 32
   constexpr uint32_t CH = NPIX * 16;
-  constexpr uint32_t TILE_BYTES = KC * CH;
-  constexpr uint32_t STAGE = DL_BYTES + TILE_BYTES + 128;   // [dl plane][a tile][pad]
-  constexpr int KSTEPS = NPIX / 16;                   // 68
-  extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], done_bar;
+  extern __shared__ __align__(1024) unsigned char smem[];        // [dl copies][dl stage 0][dl stage 1][a tile 0][a tile 1]
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages], dfull_bar[2], dempty_bar[2], afull_bar, aempty_bar, done_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x < kStages * 8) {
-    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
-    reinterpret_cast<uint4*>(smem + s * STAGE + DL_BYTES + TILE_BYTES)[j] = make_uint4(0, 0, 0, 0);
-  }
-  if (warp == 0) tmem_alloc<128>(&tmem_slot);
+  // border cells of the copies are zero for every tile: cleared once, the loaders only ever write the interior
+  for (uint32_t i = threadIdx.x; i < DL_BYTES / 16; i += kThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tmem_alloc<32>(&tmem_slot);
   if (threadIdx.x == 32) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1 + 4); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&dfull_bar[s], 1); mbar_init(&dempty_bar[s], 4); }
+    mbar_init(&afull_bar, 4); mbar_init(&aempty_bar, 1);
     mbar_init(&done_bar, 1);
     fence_mbar_init();
   }
@@ -561,99 +590,110 @@ tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutWgradParams p) 
   fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const int my_tiles = p.num_tiles > (int)blockIdx.x ? (p.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  unsigned char* dstage = smem + DL_BYTES;
+  unsigned char* btiles = smem + OW_B_OFF;
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
+        const int s = it % kStages, d = it & 1;
         const int n = t / (p.tiles_y * p.tiles_x);
         const int rem = t % (p.tiles_y * p.tiles_x);
         const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
-        mbar_expect_tx(&full_bar[s], TILE_BYTES);
+        if (!mbar_wait(&dempty_bar[d], (uint32_t)((it >> 1) & 1) ^ 1u)) { *p.error_flag = 1; break; }
+        mbar_expect_tx(&dfull_bar[d], OW_DL_STAGE);
+        tma_load_3d(dstage + d * OW_DL_STAGE, &tmap_dl, &dfull_bar[d], tx * TW * 8, ty * TR, n);
+        if (!mbar_wait(&empty_bar[s], (uint32_t)((it / kStages) & 1) ^ 1u)) { *p.error_flag = 1; break; }
+        mbar_expect_tx(&full_bar[s], OW_STAGE);
 #pragma unroll
         for (int c = 0; c < KC; ++c)
-          tma_load_3d(smem + s * STAGE + DL_BYTES + c * CH, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TR - 1, n * KC + c);
+          tma_load_3d(btiles + s * OW_STAGE + c * CH, &tmap, &full_bar[s], (tx * TW - 1) * 8, ty * TR - 1, n * KC + c);
       }
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16_f32(64, 32, 1, 1);   // both operands MN-major
+    const uint32_t idesc = make_idesc_bf16_f32(128, 32, 1, 1);   // both operands MN-major
+    // descriptor words (tc_common.cuh): low = start >> 4 | (leading byte offset >> 4) << 16, high = (stride byte offset >> 4) | version
+    const uint32_t a_hi = (uint32_t)((PW * 16) >> 4) | (1u << 14), b_hi = (uint32_t)(CH >> 4) | (1u << 14);
+    const uint32_t a_lo0 = (smem_u32(smem) >> 4) | ((128u >> 4) << 16);
+    const uint32_t b_lo0 = (smem_u32(btiles) >> 4) | ((128u >> 4) << 16);
     int it = 0;
     bool ok = true;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
       const int s = it % kStages;
-      const uint32_t ph = (it / kStages) & 1;
-      if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
-      fence_after_sync();
-      const uint32_t dl_base = smem_u32(smem + s * STAGE);
-      const uint64_t da0 = make_desc_kmajor_noswz(dl_base, 128, PW * 16);
-      const uint64_t db0 = make_desc_kmajor_noswz(dl_base + DL_BYTES, 128, CH);
-#pragma unroll 4
-      for (int ks = 0; ks < KSTEPS; ++ks) {
-        const uint64_t da = desc_advance(da0, (uint32_t)(ks * 16));
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const uint64_t db = desc_advance(db0, (uint32_t)(ks * 16 + 2 - kw));
-          if (leader) mma_bf16_ss(tmem + (uint32_t)(kw * 32), da, db, idesc, (it | ks) != 0);
-        }
+      if (!mbar_wait(&full_bar[s], (uint32_t)(it / kStages) & 1u) || !mbar_wait(&afull_bar, (uint32_t)(it & 1))) {
+        if (leader) *p.error_flag = 1;
+        ok = false;
+        break;
       }
-      if (leader) mma_commit(&empty_bar[s]);
+      fence_after_sync();
+      if (leader) {
+        uint32_t a_lo = a_lo0, b_lo = b_lo0 + (uint32_t)s * (OW_STAGE >> 4);
+        mma_bf16_ss_words(tmem, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)(it != 0));
+        mma_bf16_ss_words(tmem, a_lo + 16, a_hi, b_lo + 16, b_hi, idesc, 1u);
+#pragma unroll 3
+        for (int r = 1; r < PR; ++r) {                 // halo row r: two K steps; the copies advance three copy rows per halo row
+          a_lo += 3 * PW; b_lo += PW;
+          mma_bf16_ss_words(tmem, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          mma_bf16_ss_words(tmem, a_lo + 16, a_hi, b_lo + 16, b_hi, idesc, 1u);
+        }
+        mma_commit(&empty_bar[s]);
+        mma_commit(&aempty_bar);
+      }
       __syncwarp();
     }
     if (ok && leader) mma_commit(&done_bar);
   } else {
-    // ============================ dl-plane loaders (4 warps) ==============================
+    // ============================ dl-copy loaders (4 warps) ===============================
     const int lt = threadIdx.x - 64;              // 0..127
+    constexpr int NU = (TR * TW + 127) / 128;     // interior pixels per thread
     int it = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
-      const int s = it % kStages;
-      const uint32_t ph = (it / kStages) & 1;
-      if (!mbar_wait(&empty_bar[s], ph ^ 1)) { if (lane == 0) *p.error_flag = 1; break; }
-      const int n = t / (p.tiles_y * p.tiles_x);
-      const int rem = t % (p.tiles_y * p.tiles_x);
-      const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
-      uint4* dst = reinterpret_cast<uint4*>(smem + s * STAGE);
-      {  // all loads of the plane are issued before the first store: one memory round trip per tile, not nine
-        constexpr int NU = DLROWS * PW / 128;
-        static_assert(DLROWS * PW % 128 == 0, "dl plane must be a whole number of 128-thread passes");
-        uint4 vv[NU];
+      const int d = it & 1;
+      if (!mbar_wait(&dfull_bar[d], (uint32_t)(it >> 1) & 1u)) { if (lane == 0) *p.error_flag = 1; break; }
+      // the staged tile goes to registers (and its ring slot back to the producer) before the wait for the previous
+      // tile's MMAs
+      const uint4* src = reinterpret_cast<const uint4*>(dstage + d * OW_DL_STAGE);
+      uint4 vv[NU];
 #pragma unroll
-        for (int k = 0; k < NU; ++k) {
-          const int u = lt + k * 128;
-          const int rho = u / PW - 2, c = u % PW;
-          const int y = ty * TR + rho, x = tx * TW + c;
-          vv[k] = make_uint4(0, 0, 0, 0);
-          if (rho >= 0 && rho < TR && c < TW && y < p.H && x < p.W)
-            vv[k] = __ldg(reinterpret_cast<const uint4*>(p.dl8) + ((int64_t)n * p.H + y) * p.W + x);
+      for (int k = 0; k < NU; ++k) {
+        const int u = lt + k * 128;
+        vv[k] = u < TR * TW ? src[u] : make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dempty_bar[d]);
+      if (!mbar_wait(&aempty_bar, (uint32_t)((it & 1) ^ 1))) { if (lane == 0) *p.error_flag = 1; break; }
+      uint4* dst = reinterpret_cast<uint4*>(smem);
+#pragma unroll
+      for (int k = 0; k < NU; ++k) {
+        const int u = lt + k * 128;
+        const int rho = u / TW, c = u % TW;
+        if (u < TR * TW) {
+          uint4* row = dst + (rho + 2) * (3 * PW) + c + 2;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) row[kw * PW - kw] = vv[k];       // copy kw, column c + 2 - kw
         }
-#pragma unroll
-        for (int k = 0; k < NU; ++k) dst[lt + k * 128] = vv[k];
       }
       fence_async_smem();       // generic-proxy writes -> visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (lane == 0) mbar_arrive(&afull_bar);
     }
     // ================================ final epilogue =====================================
     const int lg = warp & 3;
-    if (lg < 2 && my_tiles > 0) {
+    if (my_tiles > 0) {
       if (mbar_wait(&done_bar, 0)) {
         fence_after_sync();
         const int E = 9 * p.Cout * p.Cin;
         float* out = p.partial + (int64_t)blockIdx.x * E;
-#pragma unroll 1
-        for (int kw = 0; kw < 3; ++kw) {
-          float v[32];
-          const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(kw * 32);
-          tmem_ld16(ta, v);
-          tmem_ld16(ta + 16, v + 16);
-          const int m = lg * 16 + lane;              // M row held by this TMEM lane (lanes 0..15 of the group)
-          const int g = m >> 3, co = m & 7;
-          if (lane < 16 && g < 3 && co < p.Cout) {
-            for (int ci = 0; ci < p.Cin; ++ci) out[((g * 3 + kw) * p.Cout + co) * p.Cin + ci] = v[ci];
-          }
+        float v[32];
+        const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16);
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + 16, v + 16);
+        const int m = lg * 32 + lane;                // M row held by this TMEM lane: tap group G = kh*3 + kw, channel co
+        const int g = m >> 3, co = m & 7;
+        if (g < 9 && co < p.Cout) {
+          for (int ci = 0; ci < p.Cin; ++ci) out[(g * p.Cout + co) * p.Cin + ci] = v[ci];
         }
       } else if (lane == 0) {
         *p.error_flag = 1;
@@ -662,7 +702,7 @@ tc_out_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, OutWgradParams p) 
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<128>(tmem);
+  if (warp == 0) tmem_dealloc<32>(tmem);
 }
 
 // out[e] = sum_i partial[i*E + e]: 8 threads per entry, each a contiguous slice of the partials,
@@ -2089,18 +2129,20 @@ int tc_out_wgrad(const void* dl8_bf16, const void* act_bf16, float* dW, float* p
   CUresult r = make_planar_tmap(&tmap, act_bf16, B, H, W, Cin);
   if (r != CUDA_SUCCESS) return 2;
   OutWgradParams p{};
-  p.dl8 = reinterpret_cast<const __nv_bfloat16*>(dl8_bf16);
   p.partial = partial; p.B = B; p.H = H; p.W = W; p.Cout = Cout; p.Cin = Cin;
   p.tiles_y = cdiv(H, TR); p.tiles_x = cdiv(W, TW);
   p.num_tiles = B * p.tiles_y * p.tiles_x;
   p.error_flag = error_flag;
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  const size_t smem = (size_t)kStages * ((size_t)DL_BYTES + (size_t)4 * NPIX * 16 + 128);
+  CUtensorMap tmap_dl;
+  r = make_c8_tmap(&tmap_dl, dl8_bf16, B, H, W, TW, TR);
+  if (r != CUDA_SUCCESS) return 2;
+  const size_t smem = OW_SMEM;
   const int E = 9 * Cout * Cin;
   ProfScope prof_("tc_out_wgrad", st);
   ++g_launches;
   cudaFuncSetAttribute(tc_out_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tc_out_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, p);
+  tc_out_wgrad_kernel<<<grid, kThreads, smem, st>>>(tmap, tmap_dl, p);
   sum_partials(partial, grid, E, dW, st);
   return 0;
 }
