@@ -1335,28 +1335,35 @@ __global__ void tc_prep_all_kernel(PrepAllArgs a) {
   }
 }
 
-// dW[kh,kw,co,ci] = sum a_prev[i,j,ci] * G[2i+kh, 2j+kw, co] : MN-major, K = low-res pixels.
-// A = zero-padded plane of a_prev (rows -1..TRD) written by the loader warps, M-groups strided
-// by one plane row (group 0 <-> vertical low-res shift 1, group 1 <-> shift 0); B = one parity
-// block of the G tile (N = 32 = 4 chunk planes) started at the horizontal shift.  Six
-// accumulators (parity x horizontal shift) persist in TMEM over the CTA's tiles.
+// dW[kh,kw,co,ci] = sum a_prev[i,j,ci] * G[2i+kh, 2j+kw, co] : MN-major, K = low-res pixels, ONE MMA (M=64, N=128)
+// per 16 pixels of the G tile:
+//   B = the whole space-to-depth G tile, N = 128 = 4 parities x 32 channels = its 16 chunk planes (constant stride);
+//   A = TWO zero-padded copies of the a_prev plane (rows -1..TRD), copy dh shifted right by dh columns, stored
+//     row-interleaved: unit ((R*2 + dh)*PW + c) = a[R - 1][c - dh].  M-groups are strided by one copy row, so M-group
+//     2*g + dh of the descriptor that starts at G pixel (gr, gc) reads a[gr + g - 1][gc - dh]: group g = 0 <-> vertical
+//     low-res shift 1, g = 1 <-> shift 0; dh = the horizontal shift.
+// (Before: the horizontal shift was the B start address and every parity its own MMA - six M=64, N=32 MMAs per K
+// step at 38 cycles each, tools/mma_cost.cu - and the kernel ran at their rate.)  The accumulator (M rows (g, dh, ci),
+// columns (parity, co)) persists in TMEM over the CTA's tiles; combinations that are no tap of the 3x3 kernel are
+// dropped by the epilogue.
 constexpr int APROWS = TRD + 2;
-constexpr uint32_t AP_BYTES = APROWS * PW * 16;
-constexpr int KSTEPS_D = GROWS * PW / 16;        // 18
+constexpr uint32_t AP_BYTES = APROWS * 2 * PW * 16;
+static_assert(PW == 32, "two 16-pixel K steps per G row");
 
 __global__ void __launch_bounds__(kThreads, 1)
 tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p) {
-  constexpr uint32_t STAGE = AP_BYTES + GT_BYTES + 128;    // [a_prev plane][G tile][pad]
+  constexpr uint32_t STAGE = AP_BYTES + GT_BYTES + 128;    // [a_prev copies][G tile][pad]
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages], done_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x < kStages * 8) {
-    const int s = threadIdx.x / 8, j = threadIdx.x % 8;
-    reinterpret_cast<uint4*>(smem + s * STAGE + AP_BYTES + GT_BYTES)[j] = make_uint4(0, 0, 0, 0);
+  // column 0 of the shifted copy is never written by the loaders: zero for every tile
+  for (int i = threadIdx.x; i < kStages * APROWS; i += kThreads) {
+    const int s = i / APROWS, R = i % APROWS;
+    reinterpret_cast<uint4*>(smem + s * STAGE)[(R * 2 + 1) * PW] = make_uint4(0, 0, 0, 0);
   }
-  if (warp == 0) tmem_alloc<256>(&tmem_slot);
+  if (warp == 0) tmem_alloc<128>(&tmem_slot);
   if (threadIdx.x == 32) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1 + 4); mbar_init(&empty_bar[s], 1); }
     mbar_init(&done_bar, 1);
@@ -1387,8 +1394,10 @@ tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16_f32(64, 32, 1, 1);
-    // accumulator a: (parity, horizontal shift) = (0,0) (0,1) | (1,0) | (2,0) (2,1) | (3,0)
+    const uint32_t idesc = make_idesc_bf16_f32(64, 128, 1, 1);
+    // descriptor words (tc_common.cuh): low = start >> 4 | (leading byte offset >> 4) << 16, high = (stride byte offset >> 4) | version
+    const uint32_t a_hi = (uint32_t)((PW * 16) >> 4) | (1u << 14), b_hi = (uint32_t)(CHD >> 4) | (1u << 14);
+    const uint32_t a_lo0 = (smem_u32(smem) >> 4) | ((128u >> 4) << 16);
     int it = 0;
     bool ok = true;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
@@ -1396,24 +1405,18 @@ tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
       const uint32_t ph = (it / kStages) & 1;
       if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
       fence_after_sync();
-      const uint32_t ap_base = smem_u32(smem + s * STAGE);
-      const uint64_t da0 = make_desc_kmajor_noswz(ap_base, 128, PW * 16);
-      const uint64_t db0 = make_desc_kmajor_noswz(ap_base + AP_BYTES, 128, CHD);
-#pragma unroll 2
-      for (int ks = 0; ks < KSTEPS_D; ++ks) {
-        const uint64_t da = desc_advance(da0, (uint32_t)(ks * 16));
-        const uint32_t acc = (uint32_t)((it | ks) != 0);
-        const uint64_t dbk = desc_advance(db0, (uint32_t)(ks * 16));
-        if (leader) {
-          mma_bf16_ss(tmem + 0, da, desc_advance(dbk, 0 * 4 * (CHD / 16) + 0), idesc, acc);
-          mma_bf16_ss(tmem + 32, da, desc_advance(dbk, 0 * 4 * (CHD / 16) + 1), idesc, acc);
-          mma_bf16_ss(tmem + 64, da, desc_advance(dbk, 1 * 4 * (CHD / 16) + 0), idesc, acc);
-          mma_bf16_ss(tmem + 96, da, desc_advance(dbk, 2 * 4 * (CHD / 16) + 0), idesc, acc);
-          mma_bf16_ss(tmem + 128, da, desc_advance(dbk, 2 * 4 * (CHD / 16) + 1), idesc, acc);
-          mma_bf16_ss(tmem + 160, da, desc_advance(dbk, 3 * 4 * (CHD / 16) + 0), idesc, acc);
+      if (leader) {
+        uint32_t a_lo = a_lo0 + (uint32_t)s * (STAGE >> 4), b_lo = a_lo + (AP_BYTES >> 4);
+        mma_bf16_ss_words(tmem, a_lo, a_hi, b_lo, b_hi, idesc, (uint32_t)(it != 0));
+        mma_bf16_ss_words(tmem, a_lo + 16, a_hi, b_lo + 16, b_hi, idesc, 1u);
+#pragma unroll 4
+        for (int gr = 1; gr < GROWS; ++gr) {           // G row gr: two K steps; the copies advance two copy rows per G row
+          a_lo += 2 * PW; b_lo += PW;
+          mma_bf16_ss_words(tmem, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          mma_bf16_ss_words(tmem, a_lo + 16, a_hi, b_lo + 16, b_hi, idesc, 1u);
         }
+        mma_commit(&empty_bar[s]);
       }
-      if (leader) mma_commit(&empty_bar[s]);
       __syncwarp();
     }
     if (ok && leader) mma_commit(&done_bar);
@@ -1441,32 +1444,38 @@ tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
             vv[k] = __ldg(reinterpret_cast<const uint4*>(p.a_prev8) + ((int64_t)n * p.h + i) * p.w + j);
         }
 #pragma unroll
-        for (int k = 0; k < NU; ++k)
-          if (lt + k * 128 < APROWS * PW) dst[lt + k * 128] = vv[k];
+        for (int k = 0; k < NU; ++k) {
+          const int u = lt + k * 128;
+          if (u < APROWS * PW) {
+            const int R = u / PW, c = u % PW;
+            dst[(R * 2) * PW + c] = vv[k];                              // copy 0
+            if (c + 1 < PW) dst[(R * 2 + 1) * PW + c + 1] = vv[k];      // copy 1: one column to the right
+          }
+        }
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
     }
-    if ((warp & 3) == 0 && my_tiles > 0) {     // TMEM lanes 0..15 hold M rows (g, ci)
+    const int lg = warp & 3;
+    if (lg < 2 && my_tiles > 0) {     // M = 64: rows 0..15 sit in TMEM lanes 0..15, rows 16..31 in lanes 32..47
       if (mbar_wait(&done_bar, 0)) {
         fence_after_sync();
         const int E = 9 * 32 * p.Cin;
         float* out = p.partial + (int64_t)blockIdx.x * E;
-        const int g = lane >> 3, ci = lane & 7;
+        const int row = lg * 16 + lane;            // (g, dh, ci)
+        const int g = row >> 4, dh = (row >> 3) & 1, ci = row & 7;
 #pragma unroll 1
-        for (int a = 0; a < 6; ++a) {
+        for (int par = 0; par < 4; ++par) {
           float v[32];
-          const uint32_t ta = tmem + (uint32_t)(a * 32);
+          const uint32_t ta = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(par * 32);
           tmem_ld16(ta, v);
           tmem_ld16(ta + 16, v + 16);
-          const int par = a < 2 ? 0 : (a == 2 ? 1 : (a < 5 ? 2 : 3));
-          const int dh = (a == 1 || a == 4) ? 1 : 0;
           const int pa = par >> 1, pb = par & 1;
           // vertical: parity row 0 -> kh = 2 (group 0) or 0 (group 1); parity row 1 -> kh = 1 (group 1 only)
           const int kh = pa == 0 ? (g == 0 ? 2 : 0) : 1;
           const int kw = pb == 0 ? 2 * dh : 1;
-          const bool use = lane < 16 && ci < p.Cin && (pa == 0 || g == 1);
+          const bool use = lane < 16 && ci < p.Cin && (pa == 0 || g == 1) && (pb == 0 || dh == 0);
           if (use) {
             for (int co = 0; co < 32; ++co) out[((kh * 3 + kw) * 32 + co) * p.Cin + ci] = v[co];
           }
@@ -1478,7 +1487,7 @@ tc_convT_wgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
+  if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
 // ============================================================================================
@@ -1753,15 +1762,16 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
               const bool keep = p.a_last && inside && hr >= 1 && hr <= TR && hc >= 1 && hc <= TW;
               uint4* dst = reinterpret_cast<uint4*>(a4s) + (hr * PW + hc);
               uint4* gdst = keep ? p.a_last + (int64_t)n * 4 * ((int64_t)p.H * p.W) + (int64_t)Y * p.W + X : nullptr;
+              // bias + ReLU once per channel; positions outside the image become zero words (SAME padding of the next layer)
+#pragma unroll
+              for (int c2 = 0; c2 < 32; ++c2) v[c2] = fmaxf(v[c2] + bA[c2], 0.f);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 uint32_t w4[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float y0 = inside ? fmaxf(v[g * 8 + 2 * e] + bA[g * 8 + 2 * e], 0.f) : 0.f;
-                  const float y1 = inside ? fmaxf(v[g * 8 + 2 * e + 1] + bA[g * 8 + 2 * e + 1], 0.f) : 0.f;
-                  __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-                  w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+                  w4[e] = inside ? *reinterpret_cast<uint32_t*>(&b2) : 0u;
                 }
                 const uint4 u = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                 dst[g * (CH / 16)] = u;
@@ -1771,7 +1781,7 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
               if (keep && p.relu_bits) {   // one 32-bit word per pixel instead of a 64-byte re-read in the dgrad
                 uint32_t bits = 0;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) bits |= (v[c] + bA[c] > 0.f ? 1u : 0u) << c;
+                for (int c2 = 0; c2 < 32; ++c2) bits |= (__float_as_int(v[c2]) > 0 ? 1u : 0u) << c2;   // v >= +0 after the ReLU
                 p.relu_bits[((int64_t)n * p.H + Y) * p.W + X] = bits;
               }
             }
