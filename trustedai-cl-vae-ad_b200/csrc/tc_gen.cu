@@ -38,7 +38,7 @@ constexpr int G1_MAXSLAB = 32;
 constexpr int G1_MAXPL = 32;           // planes per slab (hi + lo)
 constexpr int G1_EPI_WARPS = 16;       // four epilogue warps per TMEM lane group
 constexpr int G1_THREADS = 64 + 32 * G1_EPI_WARPS;   // TMA warp, MMA warp, epilogue warps
-constexpr int G1_STAGES = 2;
+constexpr int G1_MAXSTAGES = 6;       // shared-memory stages of both engines: as many as fit (plan field n_stages), at least 2
 constexpr size_t SMEM_BUDGET = 225 * 1024;
 
 // one tcgen05.mma of the list, ready to issue: low descriptor words (start address and leading byte offset, 16-byte units,
@@ -51,6 +51,7 @@ struct G1Group { int slab0, slab_n, a_par, pad; };
 struct G1PlanDev {
   int n_groups, MT, NB, acc_cols, R_in, row0, col0, TW, in_PL, n_slabs, n_mma, type;
   uint32_t CHb, a_region, stage_bytes, Cop;
+  int n_stages, pad_a, pad_b, pad_c;
   G1Group groups[2];
   G1Slab slabs[G1_MAXSLAB];
   G1Mma mma[G1_MAXMMA];
@@ -224,7 +225,7 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   G1PlanDev* plan = reinterpret_cast<G1PlanDev*>(smem);
   unsigned char* stages = smem + G1_PLAN_BYTES;
-  __shared__ uint64_t full_bar[G1_STAGES], empty_bar[G1_STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t full_bar[G1_MAXSTAGES], empty_bar[G1_MAXSTAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[256 + 8];
   __shared__ uint32_t s_unit[8][2];       // epilogue unit u = (M-tile, 32-column block): {mt | cb << 8 | ncols << 16, 4 x (b << 7 | chunk)}
@@ -259,14 +260,15 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
     // (only the 8 units right behind every plane position can be such a pad; planes landing there later overwrite them)
     const uint32_t sb = __ldg(&p.plan->stage_bytes), chb = __ldg(&p.plan->CHb), areg = __ldg(&p.plan->a_region);
     const int npos = (int)((areg - 128) / chb);               // plane positions of a stage
-    for (int i = threadIdx.x; i < G1_STAGES * npos * 8; i += G1_THREADS) {
+    const int nst = __ldg(&p.plan->n_stages);
+    for (int i = threadIdx.x; i < nst * npos * 8; i += G1_THREADS) {
       const int s_ = i / (npos * 8), r_ = i % (npos * 8);
       reinterpret_cast<uint4*>(stages + (size_t)s_ * sb + (size_t)(r_ / 8 + 1) * chb)[r_ % 8] = make_uint4(0, 0, 0, 0);
     }
   }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   if (threadIdx.x == 32) {
-    for (int s = 0; s < G1_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < G1_MAXSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], G1_EPI_WARPS); }
     fence_mbar_init();
   }
@@ -278,22 +280,22 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
   const int n_groups = plan->n_groups, MT = plan->MT, NB = plan->NB, acc_cols = plan->acc_cols;
   const int TW = plan->TW, TRr = 4 * MT;
   const uint32_t stage_bytes = plan->stage_bytes;
+  const int n_stages = plan->n_stages;
 
   if (warp == 0) {
     // ================================ TMA producer ========================================
     if (lane == 0) {
       const uint32_t CHb = plan->CHb, a_region = plan->a_region;
       const int row0 = plan->row0, col0 = plan->col0, in_PL = p.in_PL;
-      int it = 0;
+      int s = 0;                       // ring position and its phase
+      uint32_t ph = 0;
       bool ok = true;
       TileWalk tw;
       tw.init(blockIdx.x, gridDim.x, n_groups, p.tiles_x, p.tiles_y);
       for (int t = blockIdx.x; t < p.num_tiles && ok; t += gridDim.x, tw.next()) {
         const int n = tw.n, ty = tw.ty, tx = tw.tx;
         const G1Group g = plan->groups[tw.grp];
-        for (int sl = g.slab0; sl < g.slab0 + g.slab_n; ++sl, ++it) {
-          const int s = it % G1_STAGES;
-          const uint32_t ph = (it / G1_STAGES) & 1;
+        for (int sl = g.slab0; sl < g.slab0 + g.slab_n; ++sl) {
           if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; ok = false; break; }
           const G1Slab* S = &plan->slabs[sl];
           unsigned char* dst = stages + (size_t)s * stage_bytes;
@@ -301,13 +303,15 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
           for (int pl = 0; pl < S->nplanes; ++pl)
             tma_load_3d(dst + (size_t)pl * CHb, &tmap, &full_bar[s], (tx * TW + col0) * 8, ty * TRr + row0, n * in_PL + S->plane[pl]);
           bulk_load(dst + a_region, p.wimg + S->b_src, (uint32_t)S->b_bytes, &full_bar[s]);
+          if (++s == n_stages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==========================================
     const bool leader = elect_one();
-    int it = 0, tcount = 0;
+    int s = 0, tcount = 0;
+    uint32_t ph = 0;
     bool ok = true;
     int grp = blockIdx.x % n_groups;
     const int dgrp = gridDim.x % n_groups;
@@ -318,9 +322,7 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
       const uint32_t bph = (uint32_t)(NB == 2 ? (tcount >> 1) : tcount) & 1u;
       if (!mbar_wait(&tempty_bar[buf], bph ^ 1)) { if (leader) *p.error_flag = 1; break; }
       fence_after_sync();
-      for (int sl = g.slab0; sl < g.slab0 + g.slab_n; ++sl, ++it) {
-        const int s = it % G1_STAGES;
-        const uint32_t ph = (it / G1_STAGES) & 1;
+      for (int sl = g.slab0; sl < g.slab0 + g.slab_n; ++sl) {
         if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
         fence_after_sync();
         const uint32_t base = smem_u32(stages + (size_t)s * stage_bytes);
@@ -345,6 +347,7 @@ tc_gconv_kernel(const __grid_constant__ CUtensorMap tmap, G1Params p) {
         }
         if (leader) mma_commit(&empty_bar[s]);
         __syncwarp();
+        if (++s == n_stages) { s = 0; ph ^= 1; }
       }
       if (ok && leader) mma_commit(&tfull_bar[buf]);
       __syncwarp();
@@ -622,8 +625,10 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not, bo
     return false;
   };
 
-  // planes per slab: the largest even count whose stage (A planes + B block) fits twice in shared memory
-  const size_t stage_cap = (SMEM_BUDGET - G1_PLAN_BYTES) / G1_STAGES;
+  // planes per slab: the largest even count whose stage (A planes + B block) fits twice in shared memory; room that is
+  // left becomes further stages (n_stages).  Measured: cutting slabs smaller to get a deeper ring loses more to the
+  // per-slab fixed costs (TMA boxes of 2-4 KB, commits) than the depth wins - conv1's weight gradient 0.112 -> 0.154 ms
+  // with 4-row tiles and three stages - while extra stages of the SAME size are free: conv0's 0.167 -> 0.139 ms.
   auto slab_b_bytes = [&](int a, int p0, int p1) -> size_t {     // hi image bytes of planes [p0,p1)
     size_t bytes = 0;
     for (const Tap& tp : taps) {
@@ -635,17 +640,21 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not, bo
     }
     return bytes;
   };
-  int PS = PLh;
   const int mult = s.split ? 2 : 1;
-  for (;; ) {
-    size_t worst = 0;
-    for (int a = 0; a < n_groups; ++a)
-      for (int p0 = 0; p0 < PLh; p0 += PS) worst = std::max(worst, slab_b_bytes(a, p0, std::min(PLh, p0 + PS)) * mult);
-    const size_t need = (size_t)PS * mult * D.CHb + 128 + worst;
-    if (need <= stage_cap && PS * mult <= G1_MAXPL) break;
-    if (PS <= 1) { delete P; return no("one K chunk plane does not fit a shared-memory stage"); }
-    PS = (PS + 1) / 2;
-  }
+  auto planes_per_slab = [&](size_t stage_cap) -> int {          // 0: not even one plane fits
+    int ps = PLh;
+    for (;; ) {
+      size_t worst = 0;
+      for (int a = 0; a < n_groups; ++a)
+        for (int p0 = 0; p0 < PLh; p0 += ps) worst = std::max(worst, slab_b_bytes(a, p0, std::min(PLh, p0 + ps)) * mult);
+      const size_t need = (size_t)ps * mult * D.CHb + 128 + worst;
+      if (need <= stage_cap && ps * mult <= G1_MAXPL) return ps;
+      if (ps <= 1) return 0;
+      ps = (ps + 1) / 2;
+    }
+  };
+  const int PS = planes_per_slab((SMEM_BUDGET - G1_PLAN_BYTES) / 2);
+  if (!PS) { delete P; return no("one K chunk plane does not fit a shared-memory stage"); }
   D.a_region = (uint32_t)(PS * mult) * D.CHb + 128;
 
   int n_slabs = 0, n_mma = 0;
@@ -712,7 +721,9 @@ GenConvPlan* gen_conv_plan_create(const GenConvSpec& s, const char** why_not, bo
   T.resize(img_bytes / 2, -1);
   D.n_slabs = n_slabs; D.n_mma = n_mma;
   D.stage_bytes = (uint32_t)(((size_t)D.a_region + worst_b + 1023) / 1024 * 1024);
-  P->smem = G1_PLAN_BYTES + (size_t)G1_STAGES * D.stage_bytes;
+  D.n_stages = (int)std::min<size_t>(G1_MAXSTAGES, (SMEM_BUDGET - G1_PLAN_BYTES) / D.stage_bytes);
+  if (D.n_stages < 2) { delete P; return no("shared-memory plan too large"); }
+  P->smem = G1_PLAN_BYTES + (size_t)D.n_stages * D.stage_bytes;
   if (P->smem > 227 * 1024) { delete P; return no("shared-memory plan too large"); }
   if (!upload) return P;
   if (cudaMalloc(reinterpret_cast<void**>(&P->dev), sizeof(G1PlanDev)) != cudaSuccess ||
@@ -846,7 +857,7 @@ struct G2Mma { uint32_t a_lo, a_hi, b_lo, b_hi, idesc, d_col, b_ones, pad; };
 struct G2Role { int mma0, mma_n, nS, nU, ncols, pad0, pad1, pad2; int s_plane[G2_MAXPL]; int u_plane[G2_MAXPL]; };
 struct G2PlanDev {
   int n_roles, TRr, R_s, row0, col0, TW, s_PL, u_PL;
-  uint32_t CHs, CHu, s_region, u_region, stage_bytes, ones_off, pad0, pad1;
+  uint32_t CHs, CHu, s_region, u_region, stage_bytes, ones_off, n_stages, pad1;
   G2Role roles[G2_MAXROLE];
   G2Mma mma[G2_MAXMMA];
 };
@@ -865,7 +876,7 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
   extern __shared__ __align__(1024) unsigned char smem[];
   G2PlanDev* plan = reinterpret_cast<G2PlanDev*>(smem);
   unsigned char* stages = smem + G2_PLAN_BYTES;
-  __shared__ uint64_t full_bar[G1_STAGES], empty_bar[G1_STAGES], done_bar;
+  __shared__ uint64_t full_bar[G1_MAXSTAGES], empty_bar[G1_MAXSTAGES], done_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
@@ -878,14 +889,15 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
     // be read without having been written.  Plane positions a role never loads feed discarded rows / columns only.)
     const uint32_t sb = __ldg(&p.plan->stage_bytes), chs = __ldg(&p.plan->CHs), sreg = __ldg(&p.plan->s_region);
     const int npos = (int)((sreg - 128) / chs);
-    for (int i = threadIdx.x; i < G1_STAGES * npos * 8; i += G2_THREADS) {
+    const int nst = (int)__ldg(&p.plan->n_stages);
+    for (int i = threadIdx.x; i < nst * npos * 8; i += G2_THREADS) {
       const int s_ = i / (npos * 8), r_ = i % (npos * 8);
       reinterpret_cast<uint4*>(stages + (size_t)s_ * sb + (size_t)(r_ / 8 + 1) * chs)[r_ % 8] = make_uint4(0, 0, 0, 0);
     }
   }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   if (threadIdx.x == 32) {
-    for (int s = 0; s < G1_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < G1_MAXSTAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&done_bar, 1);
     fence_mbar_init();
   }
@@ -906,6 +918,7 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
   const int ctas_in_role = (gridDim.x - role + n_roles - 1) / n_roles;
   const int TRr = plan->TRr, TW = plan->TW;
   const uint32_t stage_bytes = plan->stage_bytes;
+  const int n_stages = plan->n_stages;
   const int per_img = p.tiles_y * p.tiles_x;
   const int my_tiles = p.num_tiles > rank_in_role ? (p.num_tiles - 1 - rank_in_role) / ctas_in_role + 1 : 0;
   const G2Role* R = &plan->roles[role];
@@ -913,10 +926,9 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t CHs = plan->CHs, CHu = plan->CHu, s_region = plan->s_region;
-      int it = 0;
-      for (int t = rank_in_role; t < p.num_tiles; t += ctas_in_role, ++it) {
-        const int s = it % G1_STAGES;
-        const uint32_t ph = (it / G1_STAGES) & 1;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = rank_in_role; t < p.num_tiles; t += ctas_in_role) {
         if (!mbar_wait(&empty_bar[s], ph ^ 1)) { *p.error_flag = 1; break; }
         const int n = t / per_img, rem = t % per_img;
         const int ty = rem / p.tiles_x, tx = rem % p.tiles_x;
@@ -927,17 +939,17 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
                       n * p.s_PL + R->s_plane[pl]);
         for (int pl = 0; pl < R->nU; ++pl)
           tma_load_4d(dst + s_region + (size_t)pl * CHu, &tmap_u, &full_bar[s], 0, tx, ty * TRr, n * p.u_PL + R->u_plane[pl]);
+        if (++s == n_stages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
     const uint32_t ones_addr = smem_u32(smem + plan->ones_off);
     const int KS = 2 * TRr;                       // 16-pixel K steps per tile
-    int it = 0;
+    int it = 0, s = 0;
+    uint32_t ph = 0;
     bool ok = true;
     for (int t = rank_in_role; t < p.num_tiles; t += ctas_in_role, ++it) {
-      const int s = it % G1_STAGES;
-      const uint32_t ph = (it / G1_STAGES) & 1;
       if (!mbar_wait(&full_bar[s], ph)) { if (leader) *p.error_flag = 1; ok = false; break; }
       fence_after_sync();
       const uint32_t base16 = smem_u32(stages + (size_t)s * stage_bytes) >> 4;
@@ -959,6 +971,7 @@ tc_gwgrad_kernel(const __grid_constant__ CUtensorMap tmap_s, const __grid_consta
       }
       if (leader) mma_commit(&empty_bar[s]);
       __syncwarp();
+      if (++s == n_stages) { s = 0; ph ^= 1; }
     }
     if (ok && leader) mma_commit(&done_bar);
     __syncwarp();
@@ -1177,21 +1190,25 @@ GenWgradPlan* gen_wgrad_plan_create(const GenWgradSpec& s, const char** why_not,
     pos[i].b = accs[i].bias ? 0 : place(accs[i].role, accs[i].b, accs[i].N / 8);
   }
   for (int r = 0; r < n_roles; ++r) if (s_cnt[r] > G2_MAXPL || u_cnt[r] > G2_MAXPL) { delete P; return no("too many planes per role"); }
-  // tile rows: largest of 8, 4, 2 whose two stages fit
-  int TRr = 8;
-  for (;; TRr /= 2) {
-    const size_t CHs = (size_t)(TRr + halo_r) * GP * 16, CHu = (size_t)TRr * GP * 16;
+  // tile rows: the largest of 8, 4, 2 whose two stages fit; spare room becomes extra stages of the same size (with two
+  // stages one is always being consumed, so a single tile is in flight per SM; see the note at the forward planner)
+  auto stages_that_fit = [&](int trr, size_t* CHs_, size_t* CHu_, size_t* s_reg_, size_t* u_reg_, size_t* stage_) -> int {
+    const size_t CHs = (size_t)(trr + halo_r) * GP * 16, CHu = (size_t)trr * GP * 16;
     const size_t s_reg = (size_t)s_extent * CHs + 128, u_reg = (size_t)u_extent * CHu;
     const size_t stage = (s_reg + u_reg + 1023) / 1024 * 1024;
-    if (G2_PLAN_BYTES + G1_STAGES * stage + 2 * CHu <= SMEM_BUDGET || TRr == 1) {
-      D.CHs = (uint32_t)CHs; D.CHu = (uint32_t)CHu; D.s_region = (uint32_t)s_reg; D.u_region = (uint32_t)u_reg;
-      D.stage_bytes = (uint32_t)stage;
-      break;
-    }
-  }
-  if (TRr < 2) { delete P; return no("operand planes do not fit two shared-memory stages"); }
+    *CHs_ = CHs; *CHu_ = CHu; *s_reg_ = s_reg; *u_reg_ = u_reg; *stage_ = stage;
+    if (G2_PLAN_BYTES + 2 * CHu >= SMEM_BUDGET) return 0;
+    return (int)((SMEM_BUDGET - G2_PLAN_BYTES - 2 * CHu) / stage);
+  };
+  int TRr = 0, n_stages = 0;
+  size_t CHs = 0, CHu = 0, s_reg = 0, u_reg = 0, stage = 0;
+  for (int trr : {8, 4, 2}) if (!TRr && stages_that_fit(trr, &CHs, &CHu, &s_reg, &u_reg, &stage) >= 2) TRr = trr;
+  if (!TRr) { delete P; return no("operand planes do not fit two shared-memory stages"); }
+  n_stages = std::min(G1_MAXSTAGES, stages_that_fit(TRr, &CHs, &CHu, &s_reg, &u_reg, &stage));
+  D.CHs = (uint32_t)CHs; D.CHu = (uint32_t)CHu; D.s_region = (uint32_t)s_reg; D.u_region = (uint32_t)u_reg;
+  D.stage_bytes = (uint32_t)stage; D.n_stages = (uint32_t)n_stages;
   D.TRr = TRr; D.R_s = TRr + halo_r; D.row0 = row0; D.col0 = col0; D.TW = TW; D.s_PL = nS; D.u_PL = nU;
-  D.ones_off = (uint32_t)(G2_PLAN_BYTES + (size_t)G1_STAGES * D.stage_bytes);
+  D.ones_off = (uint32_t)(G2_PLAN_BYTES + (size_t)n_stages * D.stage_bytes);
   P->smem = (size_t)D.ones_off + 2 * D.CHu;
   if (P->smem > 227 * 1024) { delete P; return no("shared-memory plan too large"); }
 
