@@ -239,6 +239,21 @@ __device__ __forceinline__ void tc_prep_out_weights_body(const float* w, int Cou
   }
 }
 
+// Fused tail, nine-tap form with the three horizontal taps in the N dimension (Cin = 32): B operand
+// [kh 3][ks 2][chunk 2][n = kw*8 + co (32)][8]; one MMA then yields, per pixel q, the three partial sums
+// T_kw[q][co] = sum_ci a[q + (2-kh) rows][ci] W[kh][kw][co][ci], and the epilogue adds T_2[q] + T_1[q+1] + T_0[q+2]
+// with two warp shuffles (an M-tile row is one 32-pixel halo row = one warp).
+constexpr int TAILB_N = 32;
+__device__ __forceinline__ void tc_prep_tail_kw_weights_body(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
+  const int total = 3 * 2 * 2 * TAILB_N * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i % 8, n = (i / 8) % TAILB_N, kc = (i / (8 * TAILB_N)) % 2, ks = (i / (16 * TAILB_N)) % 2, kh = i / (32 * TAILB_N);
+    const int kw = n >> 3, co = n & 7, ci = ks * 16 + kc * 8 + j;
+    const float v = (kw < 3 && co < Cout && ci < Cin) ? w[((int64_t)(kh * 3 + kw) * Cout + co) * Cin + ci] : 0.f;
+    img[i] = __float2bfloat16(v);
+  }
+}
+
 // C2I image of the same weights (fused tail, Cout <= 3): B operand [N = 32 rows n = tap*Cout + co][K = 32 ci],
 // K-major canonical units [kchunk 4][n 32][8]; n = tap * 3 + co whatever Cout is (missing channels are zero columns)
 __device__ __forceinline__ void tc_prep_tail_c2i_weights_body(const float* w, int Cout, int Cin, __nv_bfloat16* img) {
@@ -1311,6 +1326,7 @@ __device__ __forceinline__ void tc_prep_convT_dgrad_weights_body(const float* w,
 
 __global__ void tc_prep_out_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_out_weights_body(w, Cout, Cin, img); }
 __global__ void tc_prep_tail_c2i_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_tail_c2i_weights_body(w, Cout, Cin, img); }
+__global__ void tc_prep_tail_kw_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_tail_kw_weights_body(w, Cout, Cin, img); }
 __global__ void tc_prep_dgrad_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_dgrad_weights_body(w, Cout, Cin, img); }
 __global__ void tc_prep_convT_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_convT_weights_body(w, Cout, Cin, img); }
 __global__ void tc_prep_convT_dgrad_weights_kernel(const float* w, int Cout, int Cin, __nv_bfloat16* img) { tc_prep_convT_dgrad_weights_body(w, Cout, Cin, img); }
@@ -1328,7 +1344,7 @@ __global__ void tc_prep_all_kernel(PrepAllArgs a) {
     case 0: tc_prep_convT_weights_body(a.w_convT, a.Clast, a.Cprev, a.img_convT); break;
     case 1:
       if (a.tail_c2i) tc_prep_tail_c2i_weights_body(a.w_out, a.Cout, a.Clast, a.img_tail);
-      else tc_prep_out_weights_body(a.w_out, a.Cout, a.Clast, a.img_tail);
+      else tc_prep_tail_kw_weights_body(a.w_out, a.Cout, a.Clast, a.img_tail);
       break;
     case 2: tc_prep_dgrad_weights_body(a.w_out, a.Cout, a.Clast, a.img_dgrad); break;
     default: tc_prep_convT_dgrad_weights_body(a.w_convT, a.Clast, a.Cprev, a.img_convT_dgrad); break;
@@ -1548,7 +1564,7 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
   constexpr uint32_t A4_BYTES = 4 * CH;
   constexpr uint32_t A4_STAGE = A4_BYTES + 128;
   constexpr uint32_t A3_STAGE = A3_STAGE_BYTES;
-  constexpr uint32_t WA_BYTES = 5 * 2 * 32 * 16, WB_BYTES = C2I ? 2 * 2 * 32 * 16 : 9 * 2 * 2 * NPAD * 16;
+  constexpr uint32_t WA_BYTES = 5 * 2 * 32 * 16, WB_BYTES = C2I ? 2 * 2 * 32 * 16 : 3 * 2 * 2 * TAILB_N * 16;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* s_a4 = smem;                               // 2 stages
   unsigned char* s_a3 = smem + 2 * A4_STAGE;                // 2 stages
@@ -1612,9 +1628,9 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
     // front of phase B of the current one, so while the tensor pipe grinds through the 144 phase-B
     // MMAs the epilogue warps already turn A(t+1) into the next shared-memory tile.
     const bool leader = elect_one();
-    const uint32_t idescA = make_idesc_bf16_f32(128, 32), idescB = make_idesc_bf16_f32(128, NPAD);
+    const uint32_t idescA = make_idesc_bf16_f32(128, 32), idescB = make_idesc_bf16_f32(128, TAILB_N);
     const uint64_t wA0 = make_desc_kmajor_noswz(smem_u32(s_wA), 32 * 16, 128);
-    const uint64_t wB0 = make_desc_kmajor_noswz(smem_u32(s_wB), NPAD * 16, 128);
+    const uint64_t wB0 = make_desc_kmajor_noswz(smem_u32(s_wB), TAILB_N * 16, 128);
     int ma = 0, mb = 0;
     bool ok = true;
     // M-tiles [mt_lo, mt_hi) of phase A of tile itA
@@ -1686,30 +1702,33 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         if (leader) mma_commit(&a4_free[s]);
         __syncwarp();
       } else {
-        if (!TWAIT(5, &Bempty[s], ph ^ 1)) { if (leader) *p.error_flag = 1; break; }
-        fence_after_sync();
+        // Two TMEM buffers of four M-tiles (32 columns each: 3 horizontal taps x 8 channels); the epilogue drains one
+        // half while the other is computed.  Per M-tile: 3 vertical taps x 2 K steps.
         const uint64_t da0 = make_desc_kmajor_noswz(smem_u32(s_a4 + s * A4_STAGE), CH, 128);
+        for (int hh = 0; hh < 2 && ok; ++hh) {
+          if (!TWAIT(5, &Bempty[hh], (uint32_t)((it & 1) ^ 1))) { if (leader) *p.error_flag = 1; ok = false; break; }
+          fence_after_sync();
 #pragma unroll 2
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t d_tmem = tmem + (uint32_t)(256 + s * 128 + mt * NPAD);
-          const uint64_t da_mt = desc_advance(da0, (uint32_t)(mt * 128));
+          for (int mi = 0; mi < MT / 2; ++mi) {
+            const int mt = hh * (MT / 2) + mi;
+            const uint32_t d_tmem = tmem + (uint32_t)(256 + hh * 128 + mi * TAILB_N);
+            const uint64_t da_mt = desc_advance(da0, (uint32_t)(mt * 128));
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t shift = (uint32_t)((2 - tap / 3) * PW + (2 - tap % 3));
+            for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da = desc_advance(da_mt, (uint32_t)(2 * ks) * (CH / 16) + shift);
-              const uint64_t db = desc_advance(wB0, (uint32_t)((tap * 2 + ks) * 2 * NPAD));
-              if (leader) mma_bf16_ss(d_tmem, da, db, idescB, (tap | ks) != 0);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t da = desc_advance(da_mt, (uint32_t)(2 * ks) * (CH / 16) + (uint32_t)((2 - kh) * PW));
+                const uint64_t db = desc_advance(wB0, (uint32_t)((kh * 2 + ks) * 2 * TAILB_N));
+                if (leader) mma_bf16_ss(d_tmem, da, db, idescB, (kh | ks) != 0);
+              }
             }
           }
-          if (mt == MT / 2 - 1 && more) { issue_A(it + 1, 2, MTA); if (!ok) break; }
+          if (leader) mma_commit(&Bfull[hh]);
+          __syncwarp();
+          if (hh == 0 && more) { issue_A(it + 1, 2, MTA); if (!ok) break; }   // (needs the first phase-A slot drained: see above)
         }
         if (!ok) break;
-        if (leader) {
-          mma_commit(&a4_free[s]);
-          mma_commit(&Bfull[s]);
-        }
+        if (leader) mma_commit(&a4_free[s]);
         __syncwarp();
       }
     }
@@ -1885,8 +1904,6 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
         tile_origin(t, n, ty0, tx0);
         const float* xs = reinterpret_cast<const float*>(s_x + s * p.x_stage) + ((tx0 * p.Cout) & 3);
         if (p.x && !TWAIT(10, &x_full[s], ph)) { if (lane == 0) *p.error_flag = 1; break; }
-        if (!TWAIT(9, &Bfull[s], ph)) { if (lane == 0) *p.error_flag = 1; break; }
-        fence_after_sync();
         float esum = 0.f, emin = 3.4e38f, emax = -3.4e38f;
         // Straight-line code over a fixed channel count (channels >= Cout are computed and dropped): the serial
         // branchy per-channel form left this single warp per scheduler waiting on one sigmoid chain at a time.
@@ -1922,23 +1939,39 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
             esum += e; emin = fminf(emin, e); emax = fmaxf(emax, e);
           }
         };
-        const uint32_t tb = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + s * 128);
+        bool okb = true;
 #pragma unroll 1
-        for (int mt = 0; mt < MT; mt += 2) {
-          float v0[8], v1[8];
-          tmem_ld8x2(tb + (uint32_t)(mt * NPAD), tb + (uint32_t)((mt + 1) * NPAD), v0, v1);
-          if (p.Cout <= 4) {
-            finish(std::integral_constant<int, 4>{}, mt, v0);
-            finish(std::integral_constant<int, 4>{}, mt + 1, v1);
-          } else {
-            finish(std::integral_constant<int, 8>{}, mt, v0);
-            finish(std::integral_constant<int, 8>{}, mt + 1, v1);
+        for (int hh = 0; hh < 2; ++hh) {            // the two TMEM buffers of four M-tiles (see the MMA issuer)
+          if (!TWAIT(9, &Bfull[hh], (uint32_t)(it & 1))) { if (lane == 0) *p.error_flag = 1; okb = false; break; }
+          fence_after_sync();
+          const uint32_t tb = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + hh * 128);
+#pragma unroll 1
+          for (int mi = 0; mi < MT / 2; ++mi) {
+            // columns kw*8 + co: partial sums over the vertical taps and channels for horizontal tap kw, taken at THIS
+            // halo position; output pixel c needs tap 2 from lane c, tap 1 from lane c+1, tap 0 from lane c+2 (lanes = the
+            // 32 pixels of one halo row; c < 30 never reaches past lane 31)
+            float v[32], acc[8];
+            tmem_ld32(tb + (uint32_t)(mi * TAILB_N), v);
+            if (p.Cout <= 4) {
+#pragma unroll
+              for (int co = 0; co < 4; ++co)
+                acc[co] = v[16 + co] + __shfl_down_sync(0xffffffffu, v[8 + co], 1) + __shfl_down_sync(0xffffffffu, v[co], 2);
+#pragma unroll
+              for (int co = 4; co < 8; ++co) acc[co] = 0.f;
+              finish(std::integral_constant<int, 4>{}, hh * (MT / 2) + mi, acc);
+            } else {
+#pragma unroll
+              for (int co = 0; co < 8; ++co)
+                acc[co] = v[16 + co] + __shfl_down_sync(0xffffffffu, v[8 + co], 1) + __shfl_down_sync(0xffffffffu, v[co], 2);
+              finish(std::integral_constant<int, 8>{}, hh * (MT / 2) + mi, acc);
+            }
           }
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&Bempty[hh]);
         }
+        if (!okb) break;
         if (p.x) { __syncwarp(); if (lane == 0) mbar_arrive(&x_empty[s]); }
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&Bempty[s]);
         if (p.score_partial) {     // fixed shuffle tree -> deterministic
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
@@ -2310,10 +2343,10 @@ static bool tail_c2i(int Cout) {
   return env && Cout <= 3;
 }
 void tc_prep_tail_weights(const float* w, int Cout, int Cin, void* img, cudaStream_t st) {
-  if (!tail_c2i(Cout)) { tc_prep_out_weights(w, Cout, Cin, img, st); return; }
   ProfScope prof_("tc_prep_weights", st);
   ++g_launches;
-  tc_prep_tail_c2i_weights_kernel<<<4, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+  if (!tail_c2i(Cout)) tc_prep_tail_kw_weights_kernel<<<8, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
+  else tc_prep_tail_c2i_weights_kernel<<<4, 256, 0, st>>>(w, Cout, Cin, reinterpret_cast<__nv_bfloat16*>(img));
 }
 void tc_prep_all_weights(const float* w_convT, const float* w_out, int Cprev, int Clast, int Cout, void* img_convT,
                          void* img_tail, void* img_dgrad, void* img_convT_dgrad, cudaStream_t st) {
@@ -2374,7 +2407,7 @@ int tc_tail_fused(const void* in8_bf16, const void* wimgA, const void* wimgB, co
     cudaFuncSetAttribute(tc_tail_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tc_tail_fused_kernel<true><<<grid, kThreadsT, smem, st>>>(tmap, tmapx, p);
   } else {
-    const size_t smem = smem0 + (size_t)9 * 2 * 2 * NPAD * 16;
+    const size_t smem = smem0 + (size_t)3 * 2 * 2 * TAILB_N * 16;
     cudaFuncSetAttribute(tc_tail_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tc_tail_fused_kernel<false><<<grid, kThreadsT, smem, st>>>(tmap, tmapx, p);
   }
