@@ -1946,24 +1946,31 @@ tc_tail_fused_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_cons
           fence_after_sync();
           const uint32_t tb = tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(256 + hh * 128);
 #pragma unroll 1
-          for (int mi = 0; mi < MT / 2; ++mi) {
+          for (int mi = 0; mi < MT / 2; mi += 2) {
             // columns kw*8 + co: partial sums over the vertical taps and channels for horizontal tap kw, taken at THIS
             // halo position; output pixel c needs tap 2 from lane c, tap 1 from lane c+1, tap 0 from lane c+2 (lanes = the
-            // 32 pixels of one halo row; c < 30 never reaches past lane 31)
-            float v[32], acc[8];
-            tmem_ld32(tb + (uint32_t)(mi * TAILB_N), v);
+            // 32 pixels of one halo row; c < 30 never reaches past lane 31).  Two M-tiles per pass: their loads, shuffles
+            // and sigmoid chains interleave (this role has one warp per scheduler).
+            float v0[32], v1[32], acc0[8], acc1[8];
+            tmem_ld32x2(tb + (uint32_t)(mi * TAILB_N), tb + (uint32_t)((mi + 1) * TAILB_N), v0, v1);
             if (p.Cout <= 4) {
 #pragma unroll
-              for (int co = 0; co < 4; ++co)
-                acc[co] = v[16 + co] + __shfl_down_sync(0xffffffffu, v[8 + co], 1) + __shfl_down_sync(0xffffffffu, v[co], 2);
+              for (int co = 0; co < 4; ++co) {
+                acc0[co] = v0[16 + co] + __shfl_down_sync(0xffffffffu, v0[8 + co], 1) + __shfl_down_sync(0xffffffffu, v0[co], 2);
+                acc1[co] = v1[16 + co] + __shfl_down_sync(0xffffffffu, v1[8 + co], 1) + __shfl_down_sync(0xffffffffu, v1[co], 2);
+              }
 #pragma unroll
-              for (int co = 4; co < 8; ++co) acc[co] = 0.f;
-              finish(std::integral_constant<int, 4>{}, hh * (MT / 2) + mi, acc);
+              for (int co = 4; co < 8; ++co) { acc0[co] = 0.f; acc1[co] = 0.f; }
+              finish(std::integral_constant<int, 4>{}, hh * (MT / 2) + mi, acc0);
+              finish(std::integral_constant<int, 4>{}, hh * (MT / 2) + mi + 1, acc1);
             } else {
 #pragma unroll
-              for (int co = 0; co < 8; ++co)
-                acc[co] = v[16 + co] + __shfl_down_sync(0xffffffffu, v[8 + co], 1) + __shfl_down_sync(0xffffffffu, v[co], 2);
-              finish(std::integral_constant<int, 8>{}, hh * (MT / 2) + mi, acc);
+              for (int co = 0; co < 8; ++co) {
+                acc0[co] = v0[16 + co] + __shfl_down_sync(0xffffffffu, v0[8 + co], 1) + __shfl_down_sync(0xffffffffu, v0[co], 2);
+                acc1[co] = v1[16 + co] + __shfl_down_sync(0xffffffffu, v1[8 + co], 1) + __shfl_down_sync(0xffffffffu, v1[co], 2);
+              }
+              finish(std::integral_constant<int, 8>{}, hh * (MT / 2) + mi, acc0);
+              finish(std::integral_constant<int, 8>{}, hh * (MT / 2) + mi + 1, acc1);
             }
           }
           fence_before_sync();
