@@ -174,6 +174,7 @@ struct kcvae_model {
   void* x_pl = nullptr;
   void* x27_pl = nullptr;      // X27 patch planes of the input image (training: shifted operand of the first layer's weight gradient)
   std::vector<void*> act_e_pl, g_e_pl, act_d_pl, g_d_pl;
+  bool g_d1_planes_only = false;   // the last backward wrote d loss / d act_d[1] only as planes (g_d_pl[1]), not as fp32
   float *gen_partial = nullptr, *gen_partial2 = nullptr;
   // decoder Dense layer on the engine (GEN_DENSE products): W^T and G^T as plane tensors, plans per batch size
   bool gen_dense = false;
@@ -799,7 +800,11 @@ int ensure_bwd(kcvae_model* h, int B) {
   if (h->gen_dense) KC_TRY(gen_alloc(h, &h->gT_pl, (size_t)((Bc + 7) / 8) * h->dec_units));
   if (gen_dec || h->gen_dec0) {
     h->g_d_pl.resize(L + 1, nullptr);
-    for (int l = 1; l <= (gen_dec ? L : 1); ++l) KC_TRY(gen_alloc(h, &h->g_d_pl[l], pl_g_d(h, l).units(Bc)));
+    for (int l = 1; l <= (gen_dec ? L : 1); ++l) {
+      KC_TRY(gen_alloc(h, &h->g_d_pl[l], pl_g_d(h, l).units(Bc)));
+      // planes of channels a producer never writes (8..15 of a 5-channel gradient) must read as zeros
+      KC_CUDA(h, cudaMemset(h->g_d_pl[l], 0, pl_g_d(h, l).units(Bc) * 16));
+    }
   }
 #endif
   KC_TRY(dalloc(h, &h->dlogit, (size_t)Bc * h->P));
@@ -1333,8 +1338,13 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
 #ifndef KCVAE_EMU
     if (l == L - 1 && tail_s2d) {
       if (image_stale(h, 3)) tc_prep_convT_dgrad_weights(h->wp(vi), h->dc[l + 1], h->dc[l], h->wimg_convT_dgrad, st);
-      bool ok = tc_convT_dgrad(h->g_s2d, h->wimg_convT_dgrad, h->act_d[l], h->g_act_d[l], B, h->dh[l], h->dw[l], h->dc[l],
-                               h->tc_error, st) == 0;
+      // when the layer below runs its backward on the general engine, the gradient goes straight into the planes that
+      // backward reads (one 16-byte store per pixel) instead of fp32 NHWC + a repack launch
+      const bool to_planes = l == 1 && h->gen_dec0 && h->pp_live && h->dc[l] <= 8 && l < (int)h->g_d_pl.size() && h->g_d_pl[l];
+      GenPlanes gpl = to_planes ? pl_g_d(h, l) : GenPlanes{};
+      bool ok = tc_convT_dgrad(h->g_s2d, h->wimg_convT_dgrad, h->act_d[l], to_planes ? nullptr : h->g_act_d[l], B, h->dh[l], h->dw[l],
+                               h->dc[l], h->tc_error, st, to_planes ? gpl.base : nullptr, gpl.KC) == 0;
+      h->g_d1_planes_only = to_planes;
       float* px;
       cudaStream_t ax = aux_fork(h, st, &px);
       ok = ok && tc_convT_wgrad(h->g_s2d, h->a_prev8, h->gp(vi), px, B, h->dh[l], h->dw[l], h->dc[l], h->tc_error, ax) == 0;
@@ -1349,7 +1359,7 @@ int run_backward(kcvae_model* h, const float* x, int B, cudaStream_t st, cudaStr
       gen_refresh(h, st);
       const auto& g = h->gen_d[0];
       GenPlanes act = pl_act_d(h, 0, 1), gin = pl_g_d(h, 1);
-      gen_pack_nhwc(h->g_act_d[1], B, h->dh[1], h->dw[1], h->dc[1], gin, st);
+      if (!h->g_d1_planes_only) gen_pack_nhwc(h->g_act_d[1], B, h->dh[1], h->dw[1], h->dc[1], gin, st);
       float* px;
       cudaStream_t ax = aux_fork(h, st, &px);
       g_tag = "dec.convT.bwd";
@@ -2371,6 +2381,9 @@ int64_t kcvae_debug_activation(kcvae_handle h, int which, float* h_out, int64_t 
   bool planes = false;
   if (which == 100 && h->dense_f32_skipped && h->a_pp_planar) {      // the Dense output of the last forward only exists as hi + lo planes
     pl = pl_act_d(h, 0, 1); ph = h->dh[0]; pw = h->dw[0]; pc = h->dc[0]; planes = true; src = nullptr;
+  }
+  if (which == 302 && h->g_d1_planes_only && (int)h->g_d_pl.size() > 1 && h->g_d_pl[1]) {   // written as planes only by the last backward
+    pl = pl_g_d(h, 1); ph = h->dh[1]; pw = h->dw[1]; pc = h->dc[1]; planes = true; src = nullptr;
   }
   if (!src && n > 0 && !planes) {
     if (which >= 1 && which < L && h->gen_enc) { pl = pl_act_e(h, which, h->enc_split_live ? 1 : 0); ph = h->eh[which]; pw = h->ew[which]; pc = h->ec[which]; planes = true; }

@@ -1177,7 +1177,9 @@ constexpr int MTD = (TRD * PW) / 128;            // 2 M-tiles
 struct ConvTBwdParams {
   const __nv_bfloat16* wimg;     // dgrad: [9 taps][2 ks][2 chunks][16][8]
   const float* mask;             // dgrad: previous activation fp32 [B,h,w,Cin]
-  float* g_prev;                 // dgrad: [B,h,w,Cin] fp32
+  float* g_prev;                 // dgrad: [B,h,w,Cin] fp32, or nullptr
+  uint4* g_planes;               // dgrad: the same gradient as bf16 space-to-depth planes [B][4*KC][h/2][w/2][8] (chunk 0 of every
+  int g_KC;                      //        parity is written; the general engine reads them), or nullptr
   const __nv_bfloat16* a_prev8;  // wgrad: previous activation bf16 [B,h,w,8]
   float* partial;                // wgrad: [grid][9*32*Cin]
   int B, h, w, Cin;
@@ -1295,8 +1297,25 @@ tc_convT_dgrad_kernel(const __grid_constant__ CUtensorMap tmap, ConvTBwdParams p
         tmem_ld8(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(a * MTD * 16 + mt * 16), v);
         if (lives[mt]) {
 #pragma unroll
-          for (int ci = 0; ci < 8; ++ci)
-            if (ci < p.Cin) p.g_prev[pixs[mt] * p.Cin + ci] = mk[mt][ci] > 0.f ? v[ci] : 0.f;
+          for (int ci = 0; ci < 8; ++ci) v[ci] = (ci < p.Cin && mk[mt][ci] > 0.f) ? v[ci] : 0.f;
+          if (p.g_prev) {
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci)
+              if (ci < p.Cin) p.g_prev[pixs[mt] * p.Cin + ci] = v[ci];
+          }
+          if (p.g_planes) {      // one 16-byte unit per pixel straight into the planes the next layer's backward reads
+            const int q = mt * 128 + lg * 32 + lane;
+            const int i = ty * TRD + q / PW, j = tx * TW + q % PW;
+            const int par = ((i & 1) << 1) | (j & 1);
+            const int64_t u = (((int64_t)n * (4 * p.g_KC) + par * p.g_KC) * (p.h >> 1) + (i >> 1)) * (p.w >> 1) + (j >> 1);
+            uint32_t w4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+              w4[e] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            p.g_planes[u] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+          }
         }
       }
       fence_before_sync();
@@ -2298,12 +2317,14 @@ void tc_prep_convT_dgrad_weights(const float* w, int Cout, int Cin, void* img, c
 
 // g_prev[B,h,w,Cin] = (mask > 0) * stride-2 gather of G (space-to-depth bf16) with W
 int tc_convT_dgrad(const void* g_s2d, const void* wimg, const float* mask, float* g_prev, int B, int h, int w, int Cin,
-                   int* error_flag, cudaStream_t st) {
+                   int* error_flag, cudaStream_t st, void* g_planes, int g_KC) {
   CUtensorMap tmap;
   if (int rc = make_s2d_map(&tmap, g_s2d, B, h, w)) return rc;
   ConvTBwdParams p{};
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.mask = mask; p.g_prev = g_prev; p.B = B; p.h = h; p.w = w; p.Cin = Cin;
+  p.g_planes = reinterpret_cast<uint4*>(g_planes); p.g_KC = g_KC;
+  if (g_planes && ((h | w) & 1)) return 3;
   p.tiles_y = cdiv(h, TRD); p.tiles_x = cdiv(w, TW);
   p.num_tiles = B * p.tiles_y * p.tiles_x;
   p.error_flag = error_flag;

@@ -32,7 +32,7 @@ size_t tc_convT_dgrad_weight_image_elems();
 size_t tc_convT_wgrad_partial_floats(int Cin);
 void tc_prep_convT_dgrad_weights(const float* w, int Cout, int Cin, void* img_bf16, cudaStream_t st);
 int tc_convT_dgrad(const void* g_s2d, const void* wimg, const float* mask, float* g_prev, int B, int h, int w, int Cin,
-                   int* error_flag, cudaStream_t st);
+                   int* error_flag, cudaStream_t st, void* g_planes = nullptr, int g_KC = 0);
 int tc_convT_wgrad(const void* g_s2d, const void* a_prev8, float* dW, float* partial, int B, int h, int w, int Cin,
                    int* error_flag, cudaStream_t st);
 
